@@ -1,0 +1,217 @@
+/*
+ * loik_b200.h -- C ABI of libloik_b200.so: batched, B200-native (sm_100a) replacement for the hot
+ * path of LoIK's FirstOrderLoikOptimizedTpl<double>.
+ *
+ * The reference has no FFI layer; its boundary is the public C++ surface of
+ *   FirstOrderLoikOptimizedTpl      /root/reference/include/loik/loik-loid-optimized.hpp:22
+ * exported from libloik.so by explicit instantiation (src/loik-loid-optimized.cpp:10-13).  Each entry
+ * point below names the reference member it replaces.  One handle = one solver object over a batch
+ * of `batch` independent problem instances that share the robot model and the hyper-parameters
+ * (the reference: one solver object = one instance).
+ *
+ * Conventions
+ *   - extern "C", opaque handle, int status (0 ok, <0 error; text via loik_last_error()).
+ *     No exceptions cross the ABI.  The reference throws std::runtime_error for the same conditions
+ *     (ik-id-description-optimized.hpp:38,42,133,143,185,198,329,334; loik-loid-optimized.hxx:634-639).
+ *   - All floating point is IEEE double.  Spatial vectors are [linear(0:3); angular(3:6)]
+ *     (pinocchio Motion/Force), 6x6 matrices row-major, rotations row-major 3x3.
+ *   - Batched arrays are batch-major (instance-major): q[batch][nq], b[batch][nc][6], z[batch][nv] ...
+ *     i.e. one contiguous row per problem instance, exactly what a caller looping over reference
+ *     solver objects would hold.  The library keeps its own joint-major SoA copy in HBM.
+ *   - Every pointer argument may be a HOST pointer or a DEVICE pointer; `loc` says which
+ *     (LOIK_HOST / LOIK_DEVICE).  Host buffers are staged through the library's pinned buffers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work of a call
+ *     is enqueued on it; calls that return data to HOST memory synchronize that stream before returning.
+ *   - Not thread-safe per handle (same as the reference: one solver+data pair per thread).
+ *   - 1-DoF joints only (revolute / prismatic, aligned or unaligned): idx_q = idx_v = joint_id - 1.
+ */
+#ifndef LOIK_B200_H_
+#define LOIK_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LOIK_API __attribute__((visibility("default")))
+#else
+#define LOIK_API
+#endif
+
+#define LOIK_MAX_JOINTS 64 /* njoints incl. universe */
+#define LOIK_MAX_TASKS 8
+
+/* joint type codes: pinocchio JointModelRX/RY/RZ, PX/PY/PZ, RevoluteUnaligned, PrismaticUnaligned */
+enum { LOIK_JOINT_RX = 0, LOIK_JOINT_RY, LOIK_JOINT_RZ, LOIK_JOINT_PX, LOIK_JOINT_PY, LOIK_JOINT_PZ,
+       LOIK_JOINT_RU, LOIK_JOINT_PU };
+
+enum { LOIK_HOST = 0, LOIK_DEVICE = 1 };
+
+/* error codes */
+enum { LOIK_OK = 0, LOIK_ERR_INVALID = -1, LOIK_ERR_CUDA = -2, LOIK_ERR_UNSUPPORTED = -3, LOIK_ERR_STATE = -4 };
+
+/* ADMMPenaltyUpdateStrat (task-solver-base.hpp:13-18); only DEFAULT is implemented by the reference */
+enum { LOIK_MU_DEFAULT = 0, LOIK_MU_OSQP = 1, LOIK_MU_MAXEIGENVALUE = 3 };
+
+/* What the hot path reads from pinocchio::Model (loik-loid-optimized.hxx:46-47,258-265). */
+typedef struct loik_model_desc {
+  int32_t njoints;            /* model.njoints, incl. universe joint 0 */
+  const int32_t* parents;     /* [njoints] model.parents, parents[i] < i */
+  const int32_t* joint_types; /* [njoints] LOIK_JOINT_* (entry 0 ignored) */
+  const double* joint_axes;   /* [njoints][3] unit axis (used by the unaligned types) */
+  const double* placement_R;  /* [njoints][9] model.jointPlacements[i].rotation(), row-major */
+  const double* placement_p;  /* [njoints][3] model.jointPlacements[i].translation() */
+} loik_model_desc;
+
+/* Constructor arguments of FirstOrderLoikOptimizedTpl (loik-loid-optimized.hpp:129-134), same order. */
+typedef struct loik_params {
+  int32_t max_iter;
+  double tol_abs, tol_rel, tol_primal_inf, tol_dual_inf;
+  double rho, mu, mu_equality_scale_factor;
+  int32_t mu_update_strat; /* LOIK_MU_* */
+  int32_t num_eq_c;        /* number of 6-D task constraints (<= LOIK_MAX_TASKS) */
+  int32_t eq_c_dim;        /* must be 6 (ik-id-description-optimized.hpp:41-44) */
+  int32_t warm_start;
+  double tol_tail_solve;
+  int32_t verbose; /* accepted, ignored on device */
+  int32_t logging; /* accepted, ignored on device */
+} loik_params;
+
+typedef struct loik_solver loik_solver;
+
+/* Per-instance fields readable with loik_get().  Shapes are per instance; the batch dimension leads. */
+typedef enum loik_field {
+  LOIK_F_Z = 0,        /* [nv]      ik_id_data.z   -- the answer (loik-loid-optimized.hpp:333) */
+  LOIK_F_NU,           /* [nv]      ik_id_data.nu */
+  LOIK_F_W,            /* [nv]      ik_id_data.w */
+  LOIK_F_Y,            /* [nc][6]   ik_id_data.yis */
+  LOIK_F_V,            /* [nb][6]   ik_id_data.vis[1..] */
+  LOIK_F_F,            /* [nb][6]   ik_id_data.fis[1..] */
+  LOIK_F_ATY,          /* [nc][6]   ik_id_data.Aty */
+  LOIK_F_FDPA,         /* [nb][6]   ik_id_data.fis_diff_plus_Aty[1..] */
+  LOIK_F_STF_PLUS_W,   /* [nv]      ik_id_data.Stf_plus_w */
+  LOIK_F_H,            /* [nb][36]  ik_id_data.His[1..] after the backward pass (accumulated, un-projected) */
+  LOIK_F_P,            /* [nb][6]   ik_id_data.pis[1..] */
+  LOIK_F_UDINV,        /* [nb][6]   jdata.UDinv() */
+  LOIK_F_DINV,         /* [nb]      jdata.Dinv() */
+  LOIK_F_R,            /* [nv]      ik_id_data.r (after the backward pass) */
+  LOIK_F_LIMI,         /* [nb][12]  ik_id_data.liMi[1..]: rotation (9, row-major) then translation (3) */
+  LOIK_F_MU,           /* [1]       get_mu() */
+  LOIK_F_ITER,         /* [1] int32 get_iter() */
+  LOIK_F_STATUS,       /* [1] int32 bit0 converged, bit1 primal_infeasible, bit2 stopped at max_iter */
+  LOIK_F_RESIDUALS,    /* [4]       primal_residual, dual_residual, tol_primal, tol_dual */
+  LOIK_F_NORMS,        /* [LOIK_NUM_NORMS] the running norms / sums of IkIdDataTypeOptimized + feasibility scalars
+                          (only maintained when loik_set_debug(h,1)); order: loik_norm_index */
+  LOIK_F_PRIMAL_RES_VEC, /* [6nb+nv] get_primal_residual_vec() (debug mode only) */
+  LOIK_F_DUAL_RES_VEC    /* [6nb+nv] get_dual_residual_vec()   (debug mode only) */
+} loik_field;
+
+/* index into LOIK_F_NORMS (names = members of IkIdDataTypeOptimizedTpl, loik-loid-data-optimized.hpp:259-329,
+ * and the solver's feasibility scalars, loik-loid-optimized.hpp:781-787) */
+typedef enum loik_norm_index {
+  LOIK_N_BT_DELTA_Y_PLUS = 0, LOIK_N_BT_DELTA_Y_MINUS, LOIK_N_AV_INF, LOIK_N_NU_INF, LOIK_N_HREF_V_INF,
+  LOIK_N_FDPA_INF, LOIK_N_STF_PLUS_W_INF, LOIK_N_DELTA_FDPA_INF, LOIK_N_DELTA_STF_PLUS_W_INF,
+  LOIK_N_DELTA_VIS_INF, LOIK_N_DELTA_NU_INF, LOIK_N_DELTA_Z_INF, LOIK_N_DELTA_FIS_INF, LOIK_N_DELTA_YIS_INF,
+  LOIK_N_DELTA_W_INF,
+  LOIK_N_PRIMAL_RES_TASK, LOIK_N_PRIMAL_RES_SLACK, LOIK_N_DUAL_RES_V, LOIK_N_DUAL_RES_NU,
+  LOIK_N_DELTA_Y_QP_INF, LOIK_N_AT_DELTA_Y_QP_INF, LOIK_N_UB_T_DELTA_Y_PLUS, LOIK_N_LB_T_DELTA_Y_MINUS,
+  LOIK_N_PINF_COND_1, LOIK_N_PINF_COND_2, LOIK_N_DELTA_X_QP_INF,
+  LOIK_NUM_NORMS
+} loik_norm_index;
+
+/* The fused steps of one ADMM iteration, for step-by-step parity tests (the reference exposes the
+ * individual passes as public members, loik-loid-optimized.hpp:192-264, and its tests call them one
+ * by one, tests/loik-loid.cpp:340-478). */
+typedef enum loik_step_id {
+  LOIK_STEP_BACKWARD = 0, /* UpdatePrev + ResetInfNorms + FwdPass1 + BwdPassOptimizedVisitor      (hxx:290-354) */
+  LOIK_STEP_FORWARD,      /* FwdPass2OptimizedVisitor + BoxProj + DualUpdate + ComputePrimalResiduals (hxx:361-503) */
+  LOIK_STEP_RESIDUAL      /* ComputeDualResiduals + CheckConvergence + CheckFeasibility + UpdateMu
+                             + the loop-control of Solve()/InfeasibilityTailSolve()               (hxx:510-641) */
+} loik_step_id;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* FirstOrderLoikOptimizedTpl ctor (hpp:129-162) + IkIdDataTypeOptimizedTpl ctor (data hxx:40-104).
+ * Copies the model (the reference holds `Model model_;` by value, hpp:762).  `device` = CUDA ordinal. */
+LOIK_API int loik_create(const loik_model_desc* model, const loik_params* params, int32_t batch, int32_t device,
+                         loik_solver** out);
+LOIK_API void loik_destroy(loik_solver* h);
+LOIK_API const char* loik_last_error(void);
+
+/* ---- problem set-up -------------------------------------------------------------------------- */
+/* SolveInit(q, H_ref, v_ref, ids, Ais, bis, lb, ub)  (hpp:335-361): problem_.Reset, ik_id_data_.Reset(warm_start),
+ * ResetSolver, UpdateReference / UpdateIneqConstraints / UpdateEqConstraints, FwdPassInit(q).
+ *   q        [batch][nq]
+ *   H_ref    [36] one symmetric 6x6 broadcast to all joints (UpdateReference), v_ref [6]
+ *   task_joint_ids [nc] joint ids carrying a task (distinct, in 1..njoints-1), shared by the batch
+ *   A        [nc][36] shared by the batch
+ *   b        [batch][nc][6] if b_per_instance else [nc][6]
+ *   lb, ub   [batch][nv] if bounds_per_instance else [nv]
+ * H_ref, v_ref, task_joint_ids, A are always HOST pointers (small, batch-uniform); `loc` applies to q, b, lb, ub. */
+LOIK_API int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const double* v_ref, int32_t n_ids,
+                             const int32_t* task_joint_ids, const double* A, const double* b, int32_t b_per_instance,
+                             const double* lb, const double* ub, int32_t bounds_per_instance, int32_t loc, void* stream);
+
+/* problem_.UpdateReferences(H_refs, v_refs)  (ik-id-description-optimized.hpp:103-121): per-joint references,
+ * H_refs [njoints][36], v_refs [njoints][6], HOST pointers; call after loik_solve_init. */
+LOIK_API int loik_update_references(loik_solver* h, const double* H_refs, const double* v_refs, void* stream);
+
+/* ---- solving --------------------------------------------------------------------------------- */
+/* Solve()  (hpp:368-455): ResetRecursion + ResetSolver + main loop, every instance to its own
+ * convergence / infeasibility tail / max_iter. */
+LOIK_API int loik_solve(loik_solver* h, void* stream);
+/* Solve(q, H_ref, v_ref, ids, Ais, bis, lb, ub)  (hpp:475-580) = SolveInit + main loop (no ResetRecursion). */
+LOIK_API int loik_solve_full(loik_solver* h, const double* q, const double* H_ref, const double* v_ref, int32_t n_ids,
+                             const int32_t* task_joint_ids, const double* A, const double* b, int32_t b_per_instance,
+                             const double* lb, const double* ub, int32_t bounds_per_instance, int32_t loc, void* stream);
+/* Solve(q, c_id, Ai, bi)  (hpp:596-695): tailored / trajectory-tracking form: Reset(warm_start), ResetSolver,
+ * UpdateEqConstraint(c_id, Ai, bi), FwdPassInit(q), main loop.  Ai [36] HOST; q [batch][nq], bi [batch][6]
+ * (or [6] if !b_per_instance) at `loc`. */
+LOIK_API int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double* Ai, const double* bi,
+                             int32_t b_per_instance, int32_t loc, void* stream);
+
+/* Fixed-iteration mode for throughput measurement: ResetRecursion + ResetSolver, then exactly `iters`
+ * ADMM iterations on every instance with stopping disabled (convergence/feasibility still evaluated,
+ * UpdateMu still applied).  Not a reference entry point. */
+LOIK_API int loik_iterate_fixed(loik_solver* h, int32_t iters, int32_t reset, void* stream);
+
+/* ---- step-by-step interface (parity tests) ---------------------------------------------------- */
+/* ik_id_data_.ResetRecursion() + ResetSolver(): what Solve() does before its loop (hpp:370-374). */
+LOIK_API int loik_reset_recursion(loik_solver* h, void* stream);
+/* One fused step of the current iteration on every still-active instance. */
+LOIK_API int loik_step(loik_solver* h, int32_t step_id, void* stream);
+/* Keep the reference's running norms, feasibility scalars and residual vectors readable (slower). */
+LOIK_API int loik_set_debug(loik_solver* h, int32_t on);
+
+/* ---- results --------------------------------------------------------------------------------- */
+/* Copy a per-instance field of all `batch` instances to dst ([batch][field shape], batch-major).
+ * dst is double* except LOIK_F_ITER / LOIK_F_STATUS (int32_t*). */
+LOIK_API int loik_get(loik_solver* h, int32_t field, void* dst, int32_t loc, void* stream);
+/* Aggregates of the last solve: out[0] = #converged, out[1] = #primal infeasible, out[2] = #stopped at
+ * max_iter, out[3] = sum of per-instance iteration counts, out[4] = ADMM sweeps launched (kernel iterations). */
+LOIK_API int loik_get_stats(loik_solver* h, int64_t out[5]);
+/* Number of CUDA kernels this handle has launched so far (bench.py's gpu_launches). */
+LOIK_API int64_t loik_launch_count(loik_solver* h);
+
+/* setters of the base class (task-solver-base.hpp:105-141, loik-loid-optimized.hpp:703) */
+LOIK_API int loik_set_max_iter(loik_solver* h, int32_t max_iter);
+LOIK_API int loik_set_rho(loik_solver* h, double rho);
+LOIK_API int loik_set_mu(loik_solver* h, double mu);
+LOIK_API int loik_set_tol_tail_solve(loik_solver* h, double tol);
+LOIK_API int loik_set_warm_start(loik_solver* h, int32_t warm_start);
+/* Global stop criterion hook for the batch-sharded multi-GPU mode: number of still-active instances
+ * on this rank after the last loik_solve_chunk (device-resident int32, for an NCCL all-reduce). */
+LOIK_API int loik_active_count_device_ptr(loik_solver* h, void** dev_ptr);
+/* Run at most `iters` iterations of the main loop (no reset); returns immediately (async).  Used by
+ * the multi-GPU driver, which interleaves chunks with the stop-criterion all-reduce. */
+LOIK_API int loik_solve_begin(loik_solver* h, void* stream);
+LOIK_API int loik_solve_chunk(loik_solver* h, int32_t iters, void* stream);
+LOIK_API int loik_solve_end(loik_solver* h, void* stream);
+
+LOIK_API int32_t loik_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOIK_B200_H_ */

@@ -1,0 +1,628 @@
+// loik_device.cuh -- device-side data model and the three tree sweeps of one LoIK ADMM iteration.
+//
+// Mapping: ONE THREAD = ONE PROBLEM INSTANCE.  A warp therefore walks the same joint of 32 instances
+// in lock-step: every global access is a fully coalesced 256 B line per field row, there is no
+// divergence (joint types / tree topology are batch-uniform and live in __constant__ memory), and
+// the chain dependency between a joint and its parent never leaves the thread's registers.
+//
+// HBM layout (joint-major SoA): every per-instance quantity is a set of "rows" of `cap` doubles,
+// row index = (joint-1)*width + component, element index = instance slot.
+//
+// The maths restates loik-loid-optimized.hxx (reference file:line cited per block); nothing here is
+// a translation of the Eigen/Pinocchio templates: H is kept as three 3x3 blocks (LL sym, LA, AA sym
+// = 21 scalars), liMi is rebuilt from (sin q, cos q) and the constant placement, and UpdatePrev /
+// ResetInfNorms / the delta_* copies of the reference become "read the old value before
+// overwriting it" inside the sweeps.
+#pragma once
+#include <cstdint>
+
+namespace loik {
+
+constexpr int kMaxJoints = 64;
+constexpr int kMaxTasks = 8;
+
+// status of an instance (per-instance loop control of Solve()/InfeasibilityTailSolve())
+enum : int { ST_RUNNING = 0, ST_TAIL = 1, ST_CONVERGED = 2, ST_INFEASIBLE_DONE = 3, ST_MAXITER = 4 };
+
+struct JointC {
+  double plR[9], plp[3], axis[3];   // model.jointPlacements[i], joint axis
+  double HrA[6], HrB[9], HrD[6];    // problem_.H_refs_[i] as blocks LL (sym), LA, AA (sym)
+  double Hv[6];                     // problem_.Hv[i] = H_ref v_ref
+  double lb, ub;                    // problem_.lb_/ub_ for this joint's dof (when shared by the batch)
+  int parent, jtype, task, pend;    // task: slot of the task on this joint or -1; pend: own pending slot or -1
+  int carry;                        // contribution to the parent travels in registers (parent == i-1)
+  int pfirst;                       // first non-carried contribution into the parent's pending slot ('=' not '+=')
+  int ppend;                        // the parent's pending slot (when !carry && parent > 0)
+  int pad;
+};
+
+struct TaskC {
+  double A[36];                     // problem_.Ais_[k]
+  double AtA_A[6], AtA_B[9], AtA_D[6];
+  int joint, pad;
+};
+
+struct ModelC {
+  int nj, nb, nc, npend;
+  int max_iter, pad;
+  double rho, mu0, mu_scale, tol_abs, tol_rel, tol_pinf, tol_dinf, tol_tail, Hv_inf;
+  JointC j[kMaxJoints];
+  TaskC t[kMaxTasks];
+};
+
+// Sweep-to-sweep scalars of one iteration (the reference keeps them in IkIdData, data hpp:259-329).
+struct Carry {
+  double nu_inf, dfis_inf, dvis_inf, dnu_inf, dz_inf, dyis_inf, dw_inf, Av_inf;
+  double bTdy_p, bTdy_m, ubdw_p, lbdw_m, pres_task, pres_slack;
+};
+constexpr int kCarryRows = 14;
+
+struct StateP {
+  int cap;   // row stride (slots)
+  int n;     // slots in use
+  // persistent per-instance state (22 nb + 12 nc rows)
+  double *v, *f, *F, *nu, *z, *w, *T, *y, *Aty;
+  // per-instance problem data
+  double *jq, *b, *Atb, *binf, *lbv, *ubv;
+  // per-instance control + results
+  double *mu, *res;   // res: primal_residual, dual_residual, tol_primal, tol_dual
+  int *status, *iter;
+  // workspace written by the backward sweep and read by the forward sweep (35 nb rows + pending slots)
+  double *H, *p, *UDinv, *Dinv, *r, *pendH, *pendF;
+  double *carry;      // [kCarryRows][cap] (step-by-step interface only)
+  // debug mirrors of reference members
+  double *norms, *prv, *drv;
+  int *n_active;
+};
+
+extern __constant__ ModelC c_model;
+
+#define LOIK_DEV __device__ __forceinline__
+
+__host__ __device__ __forceinline__ constexpr int si(int i, int j) { return i <= j ? (i * (5 - i)) / 2 + j : (j * (5 - j)) / 2 + i; }
+LOIK_DEV double ld(const double* base, int row, int cap, int s) { return base[(size_t)row * cap + s]; }
+LOIK_DEV void st(double* base, int row, int cap, int s, double x) { base[(size_t)row * cap + s] = x; }
+LOIK_DEV double amax(double m, double x) { return fmax(m, fabs(x)); }
+
+// liMi = jointPlacements[i] * M_i(q)   (FwdPassInit, hxx:263-264).  (a, b) = (sin q, cos q) for
+// revolute joints, (q, -) for prismatic ones.
+LOIK_DEV void make_xf(const JointC& J, double a, double b, double (&R)[9], double (&t)[3]) {
+  const double* P = J.plR;
+  t[0] = J.plp[0]; t[1] = J.plp[1]; t[2] = J.plp[2];
+  switch (J.jtype) {
+    case 0:  // RX: columns 1,2 rotate
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { R[3 * i] = P[3 * i]; R[3 * i + 1] = b * P[3 * i + 1] + a * P[3 * i + 2]; R[3 * i + 2] = b * P[3 * i + 2] - a * P[3 * i + 1]; }
+      break;
+    case 1:  // RY: columns 0,2 rotate
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { R[3 * i] = b * P[3 * i] - a * P[3 * i + 2]; R[3 * i + 1] = P[3 * i + 1]; R[3 * i + 2] = b * P[3 * i + 2] + a * P[3 * i]; }
+      break;
+    case 2:  // RZ: columns 0,1 rotate
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { R[3 * i] = b * P[3 * i] + a * P[3 * i + 1]; R[3 * i + 1] = b * P[3 * i + 1] - a * P[3 * i]; R[3 * i + 2] = P[3 * i + 2]; }
+      break;
+    case 6: {  // revolute unaligned: Rodrigues (pinocchio toRotationMatrix)
+      const double x = J.axis[0], y = J.axis[1], z = J.axis[2], v = 1.0 - b;
+      double M[9];
+      M[0] = b + v * x * x;     M[1] = v * x * y - a * z; M[2] = v * x * z + a * y;
+      M[3] = v * y * x + a * z; M[4] = b + v * y * y;     M[5] = v * y * z - a * x;
+      M[6] = v * z * x - a * y; M[7] = v * z * y + a * x; M[8] = b + v * z * z;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) R[3 * i + k] = P[3 * i] * M[k] + P[3 * i + 1] * M[3 + k] + P[3 * i + 2] * M[6 + k];
+      break;
+    }
+    default: {  // prismatic: R = placement, t = p + R axis q
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = P[i];
+      double ax, ay, az;
+      if (J.jtype == 7) { ax = J.axis[0]; ay = J.axis[1]; az = J.axis[2]; }
+      else { ax = J.jtype == 3 ? 1.0 : 0.0; ay = J.jtype == 4 ? 1.0 : 0.0; az = J.jtype == 5 ? 1.0 : 0.0; }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) t[i] += (P[3 * i] * ax + P[3 * i + 1] * ay + P[3 * i + 2] * az) * a;
+      break;
+    }
+  }
+}
+
+// S^T x for a 6-vector x = [lin; ang]   (jdata.S().transpose() * x, hxx:70,231)
+LOIK_DEV double St_dot(const JointC& J, const double (&x)[6]) {
+  switch (J.jtype) {
+    case 0: return x[3];
+    case 1: return x[4];
+    case 2: return x[5];
+    case 3: return x[0];
+    case 4: return x[1];
+    case 5: return x[2];
+    case 6: return J.axis[0] * x[3] + J.axis[1] * x[4] + J.axis[2] * x[5];
+    default: return J.axis[0] * x[0] + J.axis[1] * x[1] + J.axis[2] * x[2];
+  }
+}
+// x += S * s   (jdata.S() * nu, hxx:134)
+LOIK_DEV void S_axpy(const JointC& J, double s, double (&x)[6]) {
+  switch (J.jtype) {
+    case 0: x[3] += s; break;
+    case 1: x[4] += s; break;
+    case 2: x[5] += s; break;
+    case 3: x[0] += s; break;
+    case 4: x[1] += s; break;
+    case 5: x[2] += s; break;
+    case 6: x[3] += J.axis[0] * s; x[4] += J.axis[1] * s; x[5] += J.axis[2] * s; break;
+    default: x[0] += J.axis[0] * s; x[1] += J.axis[1] * s; x[2] += J.axis[2] * s; break;
+  }
+}
+// U = H S for H = [[A, B], [B^T, D]]   (calc_aba: U = I.col(k) for aligned joints, I*S otherwise; P1)
+LOIK_DEV void H_times_S(const JointC& J, const double (&A)[6], const double (&B)[9], const double (&D)[6], double (&U)[6]) {
+#define LOIK_COL_LIN(k) { U[0] = A[si(0, k)]; U[1] = A[si(1, k)]; U[2] = A[si(2, k)]; U[3] = B[3 * k]; U[4] = B[3 * k + 1]; U[5] = B[3 * k + 2]; }
+#define LOIK_COL_ANG(k) { U[0] = B[k]; U[1] = B[3 + k]; U[2] = B[6 + k]; U[3] = D[si(0, k)]; U[4] = D[si(1, k)]; U[5] = D[si(2, k)]; }
+  switch (J.jtype) {
+    case 0: LOIK_COL_ANG(0) break;
+    case 1: LOIK_COL_ANG(1) break;
+    case 2: LOIK_COL_ANG(2) break;
+    case 3: LOIK_COL_LIN(0) break;
+    case 4: LOIK_COL_LIN(1) break;
+    case 5: LOIK_COL_LIN(2) break;
+    case 6: {
+      const double x = J.axis[0], y = J.axis[1], z = J.axis[2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        U[i] = B[3 * i] * x + B[3 * i + 1] * y + B[3 * i + 2] * z;
+        U[3 + i] = D[si(i, 0)] * x + D[si(i, 1)] * y + D[si(i, 2)] * z;
+      }
+      break;
+    }
+    default: {
+      const double x = J.axis[0], y = J.axis[1], z = J.axis[2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        U[i] = A[si(i, 0)] * x + A[si(i, 1)] * y + A[si(i, 2)] * z;
+        U[3 + i] = B[i] * x + B[3 + i] * y + B[6 + i] * z;
+      }
+      break;
+    }
+  }
+#undef LOIK_COL_LIN
+#undef LOIK_COL_ANG
+}
+
+// out = R M R^T for symmetric M (6 unique in, 6 unique out)
+LOIK_DEV void rot_sym(const double (&R)[9], const double (&M)[6], double (&out)[6]) {
+  double T[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) T[3 * i + j] = R[3 * i] * M[si(0, j)] + R[3 * i + 1] * M[si(1, j)] + R[3 * i + 2] * M[si(2, j)];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j) out[si(i, j)] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
+}
+// out = R M R^T for general 3x3 M
+LOIK_DEV void rot_gen(const double (&R)[9], const double (&M)[9], double (&out)[9]) {
+  double T[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) T[3 * i + j] = R[3 * i] * M[j] + R[3 * i + 1] * M[3 + j] + R[3 * i + 2] * M[6 + j];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) out[3 * i + j] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
+}
+
+// X* H X*^T with X* = [[R, 0], [t^ R, R]]  (pinocchio SE3actOn, call site hxx:66; P2):
+//   A' = Ab;  B' = Bb + (t^ Ab)^T;  D' = Db + t^ B' + (t^ Bb)^T     with Xb = R X R^T.
+LOIK_DEV void congruence(const double (&R)[9], const double (&t)[3], const double (&A)[6], const double (&B)[9],
+                         const double (&D)[6], double (&Ao)[6], double (&Bo)[9], double (&Do)[6]) {
+  double Bb[9], Db[6];
+  rot_sym(R, A, Ao);
+  rot_gen(R, B, Bb);
+  rot_sym(R, D, Db);
+  // TA = t^ Ab (column-wise cross products), B' = Bb + TA^T
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double a0 = Ao[si(0, j)], a1 = Ao[si(1, j)], a2 = Ao[si(2, j)];
+    Bo[3 * j + 0] = Bb[3 * j + 0] + (t[1] * a2 - t[2] * a1);
+    Bo[3 * j + 1] = Bb[3 * j + 1] + (t[2] * a0 - t[0] * a2);
+    Bo[3 * j + 2] = Bb[3 * j + 2] + (t[0] * a1 - t[1] * a0);
+  }
+  // M2 = t^ B' (need upper triangle), N = t^ Bb (need lower triangle): D'(i,j) = Db + M2(i,j) + N(j,i), i <= j
+  double M2[9], N[9];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    M2[0 + j] = t[1] * Bo[6 + j] - t[2] * Bo[3 + j];
+    M2[3 + j] = t[2] * Bo[0 + j] - t[0] * Bo[6 + j];
+    M2[6 + j] = t[0] * Bo[3 + j] - t[1] * Bo[0 + j];
+    N[0 + j] = t[1] * Bb[6 + j] - t[2] * Bb[3 + j];
+    N[3 + j] = t[2] * Bb[0 + j] - t[0] * Bb[6 + j];
+    N[6 + j] = t[0] * Bb[3 + j] - t[1] * Bb[0 + j];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j) Do[si(i, j)] = Db[si(i, j)] + M2[3 * i + j] + N[3 * j + i];
+}
+
+// SE3::act(Force): [R f_lin ; R f_ang + t x (R f_lin)]   (hxx:74,212; P3)
+LOIK_DEV void act_force(const double (&R)[9], const double (&t)[3], const double (&f)[6], double (&o)[6]) {
+  double l[3], a[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    l[i] = R[3 * i] * f[0] + R[3 * i + 1] * f[1] + R[3 * i + 2] * f[2];
+    a[i] = R[3 * i] * f[3] + R[3 * i + 1] * f[4] + R[3 * i + 2] * f[5];
+  }
+  o[0] = l[0]; o[1] = l[1]; o[2] = l[2];
+  o[3] = a[0] + (t[1] * l[2] - t[2] * l[1]);
+  o[4] = a[1] + (t[2] * l[0] - t[0] * l[2]);
+  o[5] = a[2] + (t[0] * l[1] - t[1] * l[0]);
+}
+// SE3::actInv(Motion): [R^T (v_lin - t x v_ang) ; R^T v_ang]   (hxx:125; P3)
+LOIK_DEV void actinv_motion(const double (&R)[9], const double (&t)[3], const double (&v)[6], double (&o)[6]) {
+  const double l0 = v[0] - (t[1] * v[5] - t[2] * v[4]);
+  const double l1 = v[1] - (t[2] * v[3] - t[0] * v[5]);
+  const double l2 = v[2] - (t[0] * v[4] - t[1] * v[3]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    o[i] = R[i] * l0 + R[3 + i] * l1 + R[6 + i] * l2;
+    o[3 + i] = R[i] * v[3] + R[3 + i] * v[4] + R[6 + i] * v[5];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward sweep: FwdPass1 (hxx:290-338) fused into BwdPassOptimizedVisitor (hxx:345-354, algo :31-81).
+// Leaves for the forward sweep, per joint: H_i and p_i (accumulated over the subtree, un-projected,
+// = His[i]/pis[i] after the reference's BwdPass), UDinv_i, Dinv_i, r_i.
+// ---------------------------------------------------------------------------------------------
+LOIK_DEV void sweep_backward(const StateP& S, const int s, const double mu, const double mu_eq) {
+  const int cap = S.cap, nb = c_model.nb;
+  const double rho = c_model.rho;
+  double cA[6], cB[9], cD[6], cp[6];  // contribution carried from child i+1
+  bool have_carry = false;
+  for (int i = nb; i >= 1; --i) {
+    const JointC& J = c_model.j[i];
+    const int ji = i - 1;
+    double A[6], B[9], D[6], p[6];
+    // FwdPass1: H_i = rho I + Href_i (:304-306); p_i = -rho v_prev_i - Hv_i (:310-313).  v still holds the
+    // previous iterate here, which is the reference's vis_prev (UpdatePrev, data hxx:192-197).
+#pragma unroll
+    for (int c = 0; c < 6; ++c) p[c] = -rho * ld(S.v, 6 * ji + c, cap, s) - J.Hv[c];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { A[c] = J.HrA[c]; D[c] = J.HrD[c]; }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) B[c] = J.HrB[c];
+    A[0] += rho; A[3] += rho; A[5] += rho; D[0] += rho; D[3] += rho; D[5] += rho;
+    if (J.task >= 0) {  // H_c += mu_eq AtA; p_c += Aty - mu_eq Atb (:327-330)
+      const TaskC& K = c_model.t[J.task];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { A[c] += mu_eq * K.AtA_A[c]; D[c] += mu_eq * K.AtA_D[c]; }
+#pragma unroll
+      for (int c = 0; c < 9; ++c) B[c] += mu_eq * K.AtA_B[c];
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        p[c] += ld(S.Aty, 6 * J.task + c, cap, s) - mu_eq * ld(S.Atb, 6 * J.task + c, cap, s);
+    }
+    // children's contributions: His[parent] += SE3actOn(...), pis[parent] += liMi.act(...) (:66,:74)
+    if (J.pend >= 0) {
+      const int r0 = 27 * J.pend;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { A[c] += ld(S.pendH, r0 + c, cap, s); D[c] += ld(S.pendH, r0 + 15 + c, cap, s); p[c] += ld(S.pendH, r0 + 21 + c, cap, s); }
+#pragma unroll
+      for (int c = 0; c < 9; ++c) B[c] += ld(S.pendH, r0 + 6 + c, cap, s);
+    }
+    if (have_carry) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { A[c] += cA[c]; D[c] += cD[c]; p[c] += cp[c]; }
+#pragma unroll
+      for (int c = 0; c < 9; ++c) B[c] += cB[c];
+    }
+    // calc_aba (:60-63): U = H S, Dinv = 1/(S^T U + R_i) with armature R_i = mu_ineq (:294-295), UDinv = U Dinv
+    double U[6], UD[6];
+    H_times_S(J, A, B, D, U);
+    const double Dinv = 1.0 / (St_dot(J, U) + mu);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) UD[c] = U[c] * Dinv;
+    // r_i = w_i - mu_ineq z_i (:296) + S^T p_i (:70)
+    const double ri = (ld(S.w, ji, cap, s) - mu * ld(S.z, ji, cap, s)) + St_dot(J, p);
+    // hand H_i, p_i, UDinv_i, Dinv_i, r_i to the forward sweep
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { st(S.H, 21 * ji + c, cap, s, A[c]); st(S.H, 21 * ji + 15 + c, cap, s, D[c]); st(S.p, 6 * ji + c, cap, s, p[c]); st(S.UDinv, 6 * ji + c, cap, s, UD[c]); }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) st(S.H, 21 * ji + 6 + c, cap, s, B[c]);
+    st(S.Dinv, ji, cap, s, Dinv);
+    st(S.r, ji, cap, s, ri);
+    have_carry = false;
+    if (J.parent > 0) {
+      // projection: H -= UDinv U^T (calc_aba update_I, :63), p -= UDinv r_i (:71-73)
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a; b < 3; ++b) { A[si(a, b)] -= UD[a] * U[b]; D[si(a, b)] -= UD[3 + a] * U[3 + b]; }
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) B[3 * a + b] -= UD[a] * U[3 + b];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) p[c] -= UD[c] * ri;
+      double R[9], t[3];
+      make_xf(J, ld(S.jq, 2 * ji, cap, s), ld(S.jq, 2 * ji + 1, cap, s), R, t);
+      congruence(R, t, A, B, D, cA, cB, cD);
+      act_force(R, t, p, cp);
+      if (J.carry) {
+        have_carry = true;
+      } else {
+        const int r0 = 27 * J.ppend;
+        if (J.pfirst) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) { st(S.pendH, r0 + c, cap, s, cA[c]); st(S.pendH, r0 + 15 + c, cap, s, cD[c]); st(S.pendH, r0 + 21 + c, cap, s, cp[c]); }
+#pragma unroll
+          for (int c = 0; c < 9; ++c) st(S.pendH, r0 + 6 + c, cap, s, cB[c]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            st(S.pendH, r0 + c, cap, s, ld(S.pendH, r0 + c, cap, s) + cA[c]);
+            st(S.pendH, r0 + 15 + c, cap, s, ld(S.pendH, r0 + 15 + c, cap, s) + cD[c]);
+            st(S.pendH, r0 + 21 + c, cap, s, ld(S.pendH, r0 + 21 + c, cap, s) + cp[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < 9; ++c) st(S.pendH, r0 + 6 + c, cap, s, ld(S.pendH, r0 + 6 + c, cap, s) + cB[c]);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward sweep: FwdPass2OptimizedVisitor (hxx:361-377, algo :102-163) + BoxProj (:384-397) +
+// DualUpdate (:404-461) + ComputePrimalResiduals (:494-503), joint by joint, root to leaves.
+// ---------------------------------------------------------------------------------------------
+template <bool DEBUG>
+LOIK_DEV void sweep_forward(const StateP& S, const int s, const double mu, const double mu_eq, Carry& cy) {
+  const int cap = S.cap, nb = c_model.nb;
+  cy.nu_inf = cy.dfis_inf = cy.dvis_inf = cy.dnu_inf = cy.dz_inf = cy.dyis_inf = cy.dw_inf = cy.Av_inf = 0.0;
+  cy.bTdy_p = cy.bTdy_m = cy.ubdw_p = cy.lbdw_m = cy.pres_task = cy.pres_slack = 0.0;
+  const double inv_mu = 1.0 / mu;
+  double vprev[6] = {0, 0, 0, 0, 0, 0};  // v of joint i-1
+  for (int i = 1; i <= nb; ++i) {
+    const JointC& J = c_model.j[i];
+    const int ji = i - 1;
+    double vin[6];
+    if (J.parent == 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) vin[c] = 0.0;
+    } else if (J.parent == i - 1) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) vin[c] = vprev[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) vin[c] = ld(S.v, 6 * (J.parent - 1) + c, cap, s);
+    }
+    double R[9], t[3], v[6];
+    make_xf(J, ld(S.jq, 2 * ji, cap, s), ld(S.jq, 2 * ji + 1, cap, s), R, t);
+    actinv_motion(R, t, vin, v);  // vi_parent (:125)
+    // nu_i = -UDinv^T vp - Dinv r_i (:127)
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc += ld(S.UDinv, 6 * ji + c, cap, s) * v[c];
+    const double nu = -acc - ld(S.Dinv, ji, cap, s) * ld(S.r, ji, cap, s);
+    cy.nu_inf = amax(cy.nu_inf, nu);  // (:129-131)
+    S_axpy(J, nu, v);                 // v_i = vp + S nu_i (:133-134)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {     // delta_vis_inf_norm vs the previous iterate (:156-158)
+      cy.dvis_inf = amax(cy.dvis_inf, v[c] - ld(S.v, 6 * ji + c, cap, s));
+      st(S.v, 6 * ji + c, cap, s, v[c]);
+      vprev[c] = v[c];
+    }
+    // f_i = H_i v_i + p_i (:139-140), delta_fis (:137-146)
+    {
+      double A[6], B[9], D[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { A[c] = ld(S.H, 21 * ji + c, cap, s); D[c] = ld(S.H, 21 * ji + 15 + c, cap, s); }
+#pragma unroll
+      for (int c = 0; c < 9; ++c) B[c] = ld(S.H, 21 * ji + 6 + c, cap, s);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const double fl = A[si(a, 0)] * v[0] + A[si(a, 1)] * v[1] + A[si(a, 2)] * v[2] + B[3 * a] * v[3] + B[3 * a + 1] * v[4] + B[3 * a + 2] * v[5] + ld(S.p, 6 * ji + a, cap, s);
+        const double fa = B[a] * v[0] + B[3 + a] * v[1] + B[6 + a] * v[2] + D[si(a, 0)] * v[3] + D[si(a, 1)] * v[4] + D[si(a, 2)] * v[5] + ld(S.p, 6 * ji + 3 + a, cap, s);
+        cy.dfis_inf = amax(cy.dfis_inf, fl - ld(S.f, 6 * ji + a, cap, s));
+        cy.dfis_inf = amax(cy.dfis_inf, fa - ld(S.f, 6 * ji + 3 + a, cap, s));
+        st(S.f, 6 * ji + a, cap, s, fl);
+        st(S.f, 6 * ji + 3 + a, cap, s, fa);
+      }
+    }
+    // this joint's dof: delta_nu (:375), BoxProj (:388-394), w update (:454-458), CheckFeasibility's dot products (:588,590)
+    {
+      const double lb = S.lbv ? ld(S.lbv, ji, cap, s) : J.lb, ub = S.ubv ? ld(S.ubv, ji, cap, s) : J.ub;
+      const double w_old = ld(S.w, ji, cap, s);
+      cy.dnu_inf = amax(cy.dnu_inf, nu - ld(S.nu, ji, cap, s));
+      const double z = fmin(ub, fmax(lb, nu + inv_mu * w_old));
+      cy.dz_inf = amax(cy.dz_inf, z - ld(S.z, ji, cap, s));
+      const double rp = nu - z;
+      cy.pres_slack = amax(cy.pres_slack, rp);
+      const double dw = mu * rp;
+      cy.dw_inf = amax(cy.dw_inf, dw);
+      cy.ubdw_p += ub * fmax(dw, 0.0);
+      cy.lbdw_m += lb * fmin(dw, 0.0);
+      st(S.nu, ji, cap, s, nu);
+      st(S.z, ji, cap, s, z);
+      st(S.w, ji, cap, s, w_old + dw);
+      if (DEBUG) st(S.prv, 6 * nb + ji, cap, s, rp);
+    }
+    if (J.task >= 0) {  // DualUpdate for the task on this joint (:410-451)
+      const int k = J.task;
+      const TaskC& K = c_model.t[k];
+      double y[6];
+      double plus = 0.0, minus = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const double Av = K.A[6 * a] * v[0] + K.A[6 * a + 1] * v[1] + K.A[6 * a + 2] * v[2] + K.A[6 * a + 3] * v[3] + K.A[6 * a + 4] * v[4] + K.A[6 * a + 5] * v[5];
+        const double bi = ld(S.b, 6 * k + a, cap, s);
+        const double e = Av - bi;          // Av_minus_b (:416)
+        const double dy = mu_eq * e;       // delta_yis (:419)
+        y[a] = ld(S.y, 6 * k + a, cap, s) + dy;
+        st(S.y, 6 * k + a, cap, s, y[a]);
+        cy.dyis_inf = amax(cy.dyis_inf, dy);
+        cy.Av_inf = amax(cy.Av_inf, Av);
+        cy.pres_task = amax(cy.pres_task, e);
+        plus += bi * fmax(dy, 0.0);
+        minus += bi * fmin(dy, 0.0);
+        if (DEBUG) st(S.prv, 6 * ji + a, cap, s, e);
+      }
+      cy.bTdy_p += plus;
+      cy.bTdy_m += minus;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)  // Aty = A^T y (:425)
+        st(S.Aty, 6 * k + a, cap, s, K.A[a] * y[0] + K.A[6 + a] * y[1] + K.A[12 + a] * y[2] + K.A[18 + a] * y[3] + K.A[24 + a] * y[4] + K.A[30 + a] * y[5]);
+    }
+  }
+}
+
+struct Resid {
+  double dres_v, dres_nu, Hrefv_inf, F_inf, T_inf, dF_inf, dT_inf;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Residual sweep: BwdPass2OptimizedVisitor (hxx:468-487, algo :185-241) + ComputeDualResiduals (:510-522),
+// leaves to root.  F = fis_diff_plus_Aty, T = Stf_plus_w.  The reference's "copy F to delta_F, zero F,
+// set F_c = Aty" choreography (:364,:370,:438-439) reduces to: F_old is what is in memory, F_new is rebuilt.
+// ---------------------------------------------------------------------------------------------
+template <bool DEBUG>
+LOIK_DEV void sweep_residual(const StateP& S, const int s, Resid& rs) {
+  const int cap = S.cap, nb = c_model.nb;
+  rs.dres_v = rs.dres_nu = rs.Hrefv_inf = rs.F_inf = rs.T_inf = rs.dF_inf = rs.dT_inf = 0.0;
+  double cF[6];
+  bool have_carry = false;
+  for (int i = nb; i >= 1; --i) {
+    const JointC& J = c_model.j[i];
+    const int ji = i - 1;
+    double f[6], F[6], v[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { f[c] = ld(S.f, 6 * ji + c, cap, s); v[c] = ld(S.v, 6 * ji + c, cap, s); }
+    if (J.task >= 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) F[c] = ld(S.Aty, 6 * J.task + c, cap, s);  // (:438-439)
+    } else {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) F[c] = 0.0;  // (:370)
+    }
+    if (J.pend >= 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) F[c] += ld(S.pendF, 6 * J.pend + c, cap, s);
+    }
+    if (have_carry) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) F[c] += cF[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) F[c] += -f[c];  // (:210)
+    // Href_v (fwd pass 2, :149-153) is recomputed here from v_i instead of being stored
+    double Hrv[6];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      Hrv[a] = J.HrA[si(a, 0)] * v[0] + J.HrA[si(a, 1)] * v[1] + J.HrA[si(a, 2)] * v[2] + J.HrB[3 * a] * v[3] + J.HrB[3 * a + 1] * v[4] + J.HrB[3 * a + 2] * v[5];
+      Hrv[3 + a] = J.HrB[a] * v[0] + J.HrB[3 + a] * v[1] + J.HrB[6 + a] * v[2] + J.HrD[si(a, 0)] * v[3] + J.HrD[si(a, 1)] * v[4] + J.HrD[si(a, 2)] * v[5];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      rs.dF_inf = amax(rs.dF_inf, F[c] - ld(S.F, 6 * ji + c, cap, s));  // (:215-220)
+      rs.F_inf = amax(rs.F_inf, F[c]);                                  // (:223-225)
+      rs.Hrefv_inf = amax(rs.Hrefv_inf, Hrv[c]);
+      const double rd = Hrv[c] - J.Hv[c] + F[c];                        // (:228)
+      rs.dres_v = amax(rs.dres_v, rd);
+      st(S.F, 6 * ji + c, cap, s, F[c]);
+      if (DEBUG) st(S.drv, 6 * ji + c, cap, s, rd);
+    }
+    // Stf_plus_w (:231-236) and its delta (:471,:482-483)
+    const double T = St_dot(J, f) + ld(S.w, ji, cap, s);
+    rs.T_inf = amax(rs.T_inf, T);
+    rs.dT_inf = amax(rs.dT_inf, T - ld(S.T, ji, cap, s));
+    st(S.T, ji, cap, s, T);
+    if (DEBUG) st(S.drv, 6 * nb + ji, cap, s, T);
+    have_carry = false;
+    if (J.parent > 0) {  // fis_diff_plus_Aty[parent] += liMi.act(f_i) (:212)
+      double R[9], t[3];
+      make_xf(J, ld(S.jq, 2 * ji, cap, s), ld(S.jq, 2 * ji + 1, cap, s), R, t);
+      act_force(R, t, f, cF);
+      if (J.carry) {
+        have_carry = true;
+      } else if (J.pfirst) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) st(S.pendF, 6 * J.ppend + c, cap, s, cF[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) st(S.pendF, 6 * J.ppend + c, cap, s, ld(S.pendF, 6 * J.ppend + c, cap, s) + cF[c]);
+      }
+    }
+  }
+  rs.dres_nu = rs.T_inf;  // dual_residual_vec[6nb:] = Stf_plus_w (:484)
+}
+
+// ---------------------------------------------------------------------------------------------
+// CheckConvergence (hxx:540-565) + CheckFeasibility (:572-606) + UpdateMu (:613-641) + the loop control
+// of Solve() (hpp:377-454) and InfeasibilityTailSolve() (hpp:271-319), per instance.
+// `fixed`: stopping disabled (throughput mode).  Returns the new status; updates mu.
+// ---------------------------------------------------------------------------------------------
+template <bool DEBUG>
+LOIK_DEV int decide(const StateP& S, const int s, const int status, const int it, const bool fixed, const Carry& cy,
+                    const Resid& rs, double& mu) {
+  const int cap = S.cap;
+  const ModelC& M = c_model;
+  const double pres = fmax(cy.pres_task, cy.pres_slack);  // (:498)
+  const double dres = fmax(rs.dres_v, rs.dres_nu);        // (:517)
+  st(S.res, 0, cap, s, pres);
+  st(S.res, 1, cap, s, dres);
+  int ns = status;
+  double dyqp = 0.0, ATdy = 0.0, ubp = 0.0, lbm = 0.0, c1 = 0.0, c2 = 0.0;
+  double dx = fmax(cy.dvis_inf, cy.dnu_inf);
+  if (status == ST_RUNNING) {
+    const double binf = ld(S.binf, 0, cap, s);
+    const double tol_p = M.tol_abs + M.tol_rel * fmax(fmax(cy.Av_inf, cy.nu_inf), fmax(binf, cy.nu_inf));            // (:544-546)
+    const double tol_d = M.tol_abs + M.tol_rel * fmax(fmax(rs.Hrefv_inf, fmax(rs.F_inf, rs.T_inf)), M.Hv_inf);      // (:548-552)
+    st(S.res, 2, cap, s, tol_p);
+    st(S.res, 3, cap, s, tol_d);
+    const bool converged = (pres < tol_p) && (dres < tol_d);                                                        // (:555)
+    bool infeasible = false;
+    if (it > 1) {                                                                                                   // (hpp:425-427)
+      dyqp = fmax(cy.dfis_inf, fmax(cy.dyis_inf, cy.dw_inf));                                                       // (:576-578)
+      ATdy = fmax(rs.dF_inf, rs.dT_inf);                                                                            // (:580-581)
+      const bool cond1 = ATdy <= M.tol_pinf * dyqp;                                                                 // (:583-584)
+      ubp = cy.bTdy_p + cy.ubdw_p;                                                                                  // (:587-588)
+      lbm = cy.bTdy_m + cy.lbdw_m;                                                                                  // (:589-590)
+      const bool cond2 = (ubp + lbm) <= M.tol_pinf * dyqp;                                                          // (:592-593)
+      infeasible = cond1 && cond2;
+      c1 = cond1; c2 = cond2;
+    }
+    if (fixed) {
+      if (pres > 10 * dres) mu *= 10; else if (dres > 10 * pres) mu *= 0.1;
+    } else if (converged) {
+      ns = ST_CONVERGED;
+    } else if (infeasible) {
+      // entering InfeasibilityTailSolve: first evaluation of its while-condition (hpp:275-284)
+      if (dx >= M.tol_tail || cy.dz_inf >= M.tol_tail) ns = (it >= M.max_iter) ? ST_INFEASIBLE_DONE : ST_TAIL;
+      else ns = ST_INFEASIBLE_DONE;
+    } else {
+      if (pres > 10 * dres) mu *= 10; else if (dres > 10 * pres) mu *= 0.1;                                         // (:617-628)
+      if (it >= M.max_iter - 1) ns = ST_MAXITER;                                                                    // loop bound (hpp:377)
+    }
+  } else {  // ST_TAIL: one tail iteration just ran (hpp:286-308); re-evaluate the while-condition
+    if (dx >= M.tol_tail || cy.dz_inf >= M.tol_tail) ns = (it >= M.max_iter) ? ST_INFEASIBLE_DONE : ST_TAIL;
+    else ns = ST_INFEASIBLE_DONE;
+  }
+  if (DEBUG) {
+    double* N = S.norms;
+    st(N, 0, cap, s, cy.bTdy_p); st(N, 1, cap, s, cy.bTdy_m); st(N, 2, cap, s, cy.Av_inf); st(N, 3, cap, s, cy.nu_inf);
+    st(N, 4, cap, s, rs.Hrefv_inf); st(N, 5, cap, s, rs.F_inf); st(N, 6, cap, s, rs.T_inf); st(N, 7, cap, s, rs.dF_inf);
+    st(N, 8, cap, s, rs.dT_inf); st(N, 9, cap, s, cy.dvis_inf); st(N, 10, cap, s, cy.dnu_inf); st(N, 11, cap, s, cy.dz_inf);
+    st(N, 12, cap, s, cy.dfis_inf); st(N, 13, cap, s, cy.dyis_inf); st(N, 14, cap, s, cy.dw_inf);
+    st(N, 15, cap, s, cy.pres_task); st(N, 16, cap, s, cy.pres_slack); st(N, 17, cap, s, rs.dres_v); st(N, 18, cap, s, rs.dres_nu);
+    if (status == ST_RUNNING && it > 1) {
+      st(N, 19, cap, s, dyqp); st(N, 20, cap, s, ATdy); st(N, 21, cap, s, ubp); st(N, 22, cap, s, lbm);
+      st(N, 23, cap, s, c1); st(N, 24, cap, s, c2);
+    }
+    if (status == ST_TAIL || it > 1) st(N, 25, cap, s, dx);
+  }
+  return ns;
+}
+
+}  // namespace loik

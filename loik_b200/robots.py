@@ -1,0 +1,227 @@
+"""Flat kinematic-tree tables for the benchmark robots.
+
+The reference takes a ``pinocchio::Model`` built from example-robot-data URDFs
+(`tests/loik-loid.cpp:108-111,208`).  Neither Pinocchio nor any URDF exists
+offline, so the robots are described here by the only things the LoIK hot path
+reads from the model (`loik-loid-optimized.hxx:46-47,258-265`): ``njoints``,
+``parents``, the joint type/axis, and ``jointPlacements``.  The kinematic
+constants are synthetic stand-ins recalled from the public URDFs; parity is
+always oracle-vs-CUDA on the *same* table.
+
+Joint type codes (shared with ``include/loik_b200.h`` and ``oracle/loik_oracle.c``)::
+
+    0,1,2  revolute about +x,+y,+z   (pinocchio JointModelRX/RY/RZ)
+    3,4,5  prismatic along +x,+y,+z  (JointModelPX/PY/PZ)
+    6      revolute, unaligned axis  (JointModelRevoluteUnaligned)
+    7      prismatic, unaligned axis (JointModelPrismaticUnaligned)
+
+All joints are 1-DoF, so ``idx_q = idx_v = joint_id - 1`` and ``nq = nv = nb``.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+
+import numpy as np
+
+RX, RY, RZ, PX, PY, PZ, RU, PU = range(8)
+_AXES = {"x": (1.0, 0.0, 0.0), "y": (0.0, 1.0, 0.0), "z": (0.0, 0.0, 1.0)}
+
+
+def rpy_to_matrix(r: float, p: float, y: float) -> np.ndarray:
+    """URDF fixed-axis roll/pitch/yaw -> rotation matrix (Rz(y) Ry(p) Rx(r))."""
+    cr, sr, cp, sp, cy, sy = math.cos(r), math.sin(r), math.cos(p), math.sin(p), math.cos(y), math.sin(y)
+    Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]], dtype=np.float64)
+    Ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]], dtype=np.float64)
+    Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]], dtype=np.float64)
+    return Rz @ Ry @ Rx
+
+
+@dataclasses.dataclass
+class RobotModel:
+    """What the LoIK hot path needs from ``pinocchio::Model`` (joint 0 = universe)."""
+
+    name: str
+    parent: np.ndarray        # [nj] int32, parent[0] = 0
+    jtype: np.ndarray         # [nj] int32 joint type code (entry 0 unused)
+    axis: np.ndarray          # [nj,3] unit axis in the joint frame
+    placement_R: np.ndarray   # [nj,3,3] jointPlacements[i].rotation()
+    placement_p: np.ndarray   # [nj,3]   jointPlacements[i].translation()
+    q_min: np.ndarray         # [nv]
+    q_max: np.ndarray         # [nv]
+    v_max: np.ndarray         # [nv] joint velocity limits (ub = -lb)
+    joint_names: list
+
+    @property
+    def nj(self) -> int:
+        return int(self.parent.shape[0])
+
+    @property
+    def nb(self) -> int:
+        return self.nj - 1
+
+    @property
+    def nv(self) -> int:
+        return self.nj - 1
+
+    @property
+    def nq(self) -> int:
+        return self.nj - 1
+
+    def neutral(self) -> np.ndarray:
+        return np.zeros(self.nq)
+
+    def validate(self) -> None:
+        assert self.parent[0] == 0
+        for i in range(1, self.nj):
+            assert 0 <= self.parent[i] < i, "joints must be numbered parent < child"
+            assert 0 <= self.jtype[i] <= PU
+            assert abs(np.linalg.norm(self.axis[i]) - 1.0) < 1e-12
+            R = self.placement_R[i]
+            assert np.allclose(R @ R.T, np.eye(3), atol=1e-12)
+
+
+def _build(name, joints) -> RobotModel:
+    """joints: list of (name, parent_id, type, axis, xyz, rpy, qmin, qmax, vmax), ids from 1."""
+    nj = len(joints) + 1
+    parent = np.zeros(nj, np.int32)
+    jtype = np.zeros(nj, np.int32)
+    axis = np.zeros((nj, 3))
+    axis[0] = (0.0, 0.0, 1.0)
+    R = np.tile(np.eye(3), (nj, 1, 1))
+    p = np.zeros((nj, 3))
+    qmin, qmax, vmax, names = [], [], [], ["universe"]
+    for i, (jn, par, jt, ax, xyz, rpy, lo, hi, vm) in enumerate(joints, start=1):
+        parent[i] = par
+        if isinstance(ax, str):
+            a = np.array(_AXES[ax])
+            code = {"x": 0, "y": 1, "z": 2}[ax] + (0 if jt == "R" else 3)
+        else:
+            a = np.asarray(ax, np.float64)
+            a = a / np.linalg.norm(a)
+            code = RU if jt == "R" else PU
+        jtype[i] = code
+        axis[i] = a
+        R[i] = rpy_to_matrix(*rpy)
+        p[i] = xyz
+        qmin.append(lo)
+        qmax.append(hi)
+        vmax.append(vm)
+        names.append(jn)
+    m = RobotModel(name, parent, jtype, axis, R, p, np.array(qmin), np.array(qmax), np.array(vmax), names)
+    m.validate()
+    return m
+
+
+_H = math.pi / 2
+
+
+def panda(fingers: bool = False) -> RobotModel:
+    """Franka Panda arm, 7 revolute-z joints (BASELINE.json "Panda 7-DoF").
+
+    ``fingers=True`` adds the two prismatic finger joints of the real URDF (nv = 9,
+    `tests/loik-loid.cpp:214-215`): finger 1 slides along +y (PY), finger 2 along -y
+    (unaligned prismatic); both hang off joint 7, which makes the tree branch.
+    """
+    J = [
+        ("panda_joint1", 0, "R", "z", (0, 0, 0.333), (0, 0, 0), -2.8973, 2.8973, 2.175),
+        ("panda_joint2", 1, "R", "z", (0, 0, 0), (-_H, 0, 0), -1.7628, 1.7628, 2.175),
+        ("panda_joint3", 2, "R", "z", (0, -0.316, 0), (_H, 0, 0), -2.8973, 2.8973, 2.175),
+        ("panda_joint4", 3, "R", "z", (0.0825, 0, 0), (_H, 0, 0), -3.0718, -0.0698, 2.175),
+        ("panda_joint5", 4, "R", "z", (-0.0825, 0.384, 0), (-_H, 0, 0), -2.8973, 2.8973, 2.61),
+        ("panda_joint6", 5, "R", "z", (0, 0, 0), (_H, 0, 0), -0.0175, 3.7525, 2.61),
+        ("panda_joint7", 6, "R", "z", (0.088, 0, 0), (_H, 0, 0), -2.8973, 2.8973, 2.61),
+    ]
+    if fingers:
+        # joint8 (0,0,0.107) * hand Rz(-pi/4) * (0,0,0.0584)
+        J += [
+            ("panda_finger_joint1", 7, "P", "y", (0, 0, 0.1654), (0, 0, -math.pi / 4), 0.0, 0.04, 0.2),
+            ("panda_finger_joint2", 7, "P", (0.0, -1.0, 0.0), (0, 0, 0.1654), (0, 0, -math.pi / 4), 0.0, 0.04, 0.2),
+        ]
+    return _build("panda9" if fingers else "panda", J)
+
+
+def ur10() -> RobotModel:
+    """UR10, 6-DoF serial chain (BASELINE.json "UR10 6-DoF")."""
+    tp = 2 * math.pi
+    J = [
+        ("shoulder_pan_joint", 0, "R", "z", (0, 0, 0.1273), (0, 0, 0), -tp, tp, 2.16),
+        ("shoulder_lift_joint", 1, "R", "y", (0, 0.220941, 0), (0, _H, 0), -tp, tp, 2.16),
+        ("elbow_joint", 2, "R", "y", (0, -0.1719, 0.612), (0, 0, 0), -tp, tp, 3.15),
+        ("wrist_1_joint", 3, "R", "y", (0, 0, 0.5723), (0, _H, 0), -tp, tp, 3.2),
+        ("wrist_2_joint", 4, "R", "z", (0, 0.1149, 0), (0, 0, 0), -tp, tp, 3.2),
+        ("wrist_3_joint", 5, "R", "y", (0, 0, 0.1157), (0, 0, 0), -tp, tp, 3.2),
+    ]
+    return _build("ur10", J)
+
+
+def talos() -> RobotModel:
+    """Talos humanoid, fixed base, 32 revolute joints, five branches.
+
+    Topology is the structural part (joint 0 has three children, joint 14 three);
+    link offsets are plausible synthetic values.
+    """
+    J = []
+
+    def leg(side, sgn, root_parent):
+        base = len(J)
+        ax = ["z", "x", "y", "y", "y", "x"]
+        xyz = [(-0.02, sgn * 0.085, -0.27105), (0, 0, 0), (0, 0, 0), (0, 0, -0.38), (0, 0, -0.325), (0, 0, 0)]
+        lim = [(-0.35, 1.57), (-0.52, 0.52), (-2.10, 0.70), (0.0, 2.62), (-1.27, 0.68), (-0.52, 0.52)]
+        vm = [3.87, 5.8, 5.8, 7.0, 5.8, 4.8]
+        for k in range(6):
+            par = root_parent if k == 0 else base + k
+            J.append((f"leg_{side}_{k+1}_joint", par, "R", ax[k], xyz[k], (0, 0, 0), lim[k][0], lim[k][1], vm[k]))
+
+    leg("left", +1.0, 0)          # joints 1..6
+    leg("right", -1.0, 0)         # joints 7..12
+    J.append(("torso_1_joint", 0, "R", "z", (0, 0, 0.0722), (0, 0, 0), -1.26, 1.26, 5.4))     # 13
+    J.append(("torso_2_joint", 13, "R", "y", (0, 0, 0), (0, 0, 0), -0.23, 0.73, 5.4))         # 14
+
+    def arm(side, sgn):
+        base = len(J)
+        ax = ["z", "x", "z", "y", "z", "x", "y", "y"]
+        xyz = [(0, sgn * 0.1575, 0.232), (0.00493, sgn * 0.1365, 0.04673), (0, 0, 0), (0.02, 0, -0.273),
+               (-0.02, 0, -0.2643), (0, 0, 0), (0, 0, 0), (0, 0, -0.09)]
+        lim = [(-1.57, 0.52), (0.01, 2.86), (-2.43, 2.43), (-2.23, 0.0), (-2.51, 2.51), (-1.37, 1.37), (-0.68, 0.68), (-0.96, 0.0)]
+        vm = [2.7, 3.66, 4.58, 4.58, 1.95, 1.76, 1.76, 1.0]
+        names = [f"arm_{side}_{k+1}_joint" for k in range(7)] + [f"gripper_{side}_joint"]
+        for k in range(8):
+            par = 14 if k == 0 else base + k
+            J.append((names[k], par, "R", ax[k], xyz[k], (0, 0, 0), lim[k][0], lim[k][1], vm[k]))
+
+    arm("left", +1.0)             # joints 15..22
+    arm("right", -1.0)            # joints 23..30
+    J.append(("head_1_joint", 14, "R", "y", (0, 0, 0.316), (0, 0, 0), -0.21, 0.79, 3.0))      # 31
+    J.append(("head_2_joint", 31, "R", "z", (0.039, 0, 0), (0, 0, 0), -1.31, 1.31, 3.0))      # 32
+    m = _build("talos", J)
+    assert m.nj == 33
+    return m
+
+
+def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0.3, prismatic: float = 0.25) -> RobotModel:
+    """Seeded random kinematic tree covering every joint type (parity stress tests)."""
+    rng = np.random.default_rng(seed)
+    J = []
+    for i in range(1, nb + 1):
+        par = i - 1 if (i == 1 or rng.random() > branching) else int(rng.integers(0, i))
+        kind = "P" if rng.random() < prismatic else "R"
+        if rng.random() < unaligned:
+            ax = rng.normal(size=3)
+        else:
+            ax = "xyz"[int(rng.integers(0, 3))]
+        xyz = tuple(rng.uniform(-0.4, 0.4, size=3))
+        rpy = tuple(rng.uniform(-math.pi, math.pi, size=3))
+        lo, hi = (-0.3, 0.3) if kind == "P" else (-2.5, 2.5)
+        J.append((f"j{i}", par, kind, ax, xyz, rpy, lo, hi, float(rng.uniform(1.0, 4.0))))
+    return _build(f"random{nb}_s{seed}", J)
+
+
+ROBOTS = {"panda": panda, "panda9": lambda: panda(True), "ur10": ur10, "talos": talos}
+
+# End-effector task joints used by the BASELINE.json configs.
+TASK_JOINTS = {"panda": [7], "panda9": [7], "ur10": [6], "talos": [21, 29]}
+
+
+def get_robot(name: str) -> RobotModel:
+    return ROBOTS[name]()
