@@ -75,7 +75,7 @@ struct StateP {
   int *n_active;
 };
 
-extern __constant__ ModelC c_model;
+__constant__ ModelC c_model;  // single translation unit (loik_solver.cu)
 
 #define LOIK_DEV __device__ __forceinline__
 
@@ -271,6 +271,14 @@ LOIK_DEV void actinv_motion(const double (&R)[9], const double (&t)[3], const do
 }
 
 // ---------------------------------------------------------------------------------------------
+// Memory-access discipline of the sweeps: every joint step is written as  LOAD PHASE -> maths ->
+// STORE PHASE.  All global loads of a step are issued back to back before the first dependent
+// instruction, so one warp keeps tens of 256 B requests in flight (the compiler cannot hoist a load
+// above a store to a possibly-aliasing row, so interleaving them would serialise on DRAM latency).
+// ---------------------------------------------------------------------------------------------
+LOIK_DEV double ldc(const double* base, int row, int cap, int s) { return __ldg(base + (size_t)row * cap + s); }  // read-only data
+
+// ---------------------------------------------------------------------------------------------
 // Backward sweep: FwdPass1 (hxx:290-338) fused into BwdPassOptimizedVisitor (hxx:345-354, algo :31-81).
 // Leaves for the forward sweep, per joint: H_i and p_i (accumulated over the subtree, un-projected,
 // = His[i]/pis[i] after the reference's BwdPass), UDinv_i, Dinv_i, r_i.
@@ -283,11 +291,21 @@ LOIK_DEV void sweep_backward(const StateP& S, const int s, const double mu, cons
   for (int i = nb; i >= 1; --i) {
     const JointC& J = c_model.j[i];
     const int ji = i - 1;
-    double A[6], B[9], D[6], p[6];
-    // FwdPass1: H_i = rho I + Href_i (:304-306); p_i = -rho v_prev_i - Hv_i (:310-313).  v still holds the
-    // previous iterate here, which is the reference's vis_prev (UpdatePrev, data hxx:192-197).
+    // ---- load phase
+    double vold[6], aty[6], atb[6];
+    const double w_i = ld(S.w, ji, cap, s), z_i = ld(S.z, ji, cap, s);
+    const double qa = ldc(S.jq, 2 * ji, cap, s), qb = ldc(S.jq, 2 * ji + 1, cap, s);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) p[c] = -rho * ld(S.v, 6 * ji + c, cap, s) - J.Hv[c];
+    for (int c = 0; c < 6; ++c) vold[c] = ld(S.v, 6 * ji + c, cap, s);
+    if (J.task >= 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { aty[c] = ld(S.Aty, 6 * J.task + c, cap, s); atb[c] = ldc(S.Atb, 6 * J.task + c, cap, s); }
+    }
+    // ---- FwdPass1: H_i = rho I + Href_i (:304-306); p_i = -rho v_prev_i - Hv_i (:310-313).  v still holds the
+    // previous iterate here, which is the reference's vis_prev (UpdatePrev, data hxx:192-197).
+    double A[6], B[9], D[6], p[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) p[c] = -rho * vold[c] - J.Hv[c];
 #pragma unroll
     for (int c = 0; c < 6; ++c) { A[c] = J.HrA[c]; D[c] = J.HrD[c]; }
 #pragma unroll
@@ -300,8 +318,7 @@ LOIK_DEV void sweep_backward(const StateP& S, const int s, const double mu, cons
 #pragma unroll
       for (int c = 0; c < 9; ++c) B[c] += mu_eq * K.AtA_B[c];
 #pragma unroll
-      for (int c = 0; c < 6; ++c)
-        p[c] += ld(S.Aty, 6 * J.task + c, cap, s) - mu_eq * ld(S.Atb, 6 * J.task + c, cap, s);
+      for (int c = 0; c < 6; ++c) p[c] += aty[c] - mu_eq * atb[c];
     }
     // children's contributions: His[parent] += SE3actOn(...), pis[parent] += liMi.act(...) (:66,:74)
     if (J.pend >= 0) {
@@ -324,8 +341,8 @@ LOIK_DEV void sweep_backward(const StateP& S, const int s, const double mu, cons
 #pragma unroll
     for (int c = 0; c < 6; ++c) UD[c] = U[c] * Dinv;
     // r_i = w_i - mu_ineq z_i (:296) + S^T p_i (:70)
-    const double ri = (ld(S.w, ji, cap, s) - mu * ld(S.z, ji, cap, s)) + St_dot(J, p);
-    // hand H_i, p_i, UDinv_i, Dinv_i, r_i to the forward sweep
+    const double ri = (w_i - mu * z_i) + St_dot(J, p);
+    // ---- store phase 1: hand H_i, p_i, UDinv_i, Dinv_i, r_i to the forward sweep
 #pragma unroll
     for (int c = 0; c < 6; ++c) { st(S.H, 21 * ji + c, cap, s, A[c]); st(S.H, 21 * ji + 15 + c, cap, s, D[c]); st(S.p, 6 * ji + c, cap, s, p[c]); st(S.UDinv, 6 * ji + c, cap, s, UD[c]); }
 #pragma unroll
@@ -346,28 +363,26 @@ LOIK_DEV void sweep_backward(const StateP& S, const int s, const double mu, cons
 #pragma unroll
       for (int c = 0; c < 6; ++c) p[c] -= UD[c] * ri;
       double R[9], t[3];
-      make_xf(J, ld(S.jq, 2 * ji, cap, s), ld(S.jq, 2 * ji + 1, cap, s), R, t);
+      make_xf(J, qa, qb, R, t);
       congruence(R, t, A, B, D, cA, cB, cD);
       act_force(R, t, p, cp);
       if (J.carry) {
         have_carry = true;
       } else {
         const int r0 = 27 * J.ppend;
-        if (J.pfirst) {
+        if (!J.pfirst) {  // read-modify-write of the parent's pending slot: all loads first
+          double oH[27];
 #pragma unroll
-          for (int c = 0; c < 6; ++c) { st(S.pendH, r0 + c, cap, s, cA[c]); st(S.pendH, r0 + 15 + c, cap, s, cD[c]); st(S.pendH, r0 + 21 + c, cap, s, cp[c]); }
+          for (int c = 0; c < 27; ++c) oH[c] = ld(S.pendH, r0 + c, cap, s);
 #pragma unroll
-          for (int c = 0; c < 9; ++c) st(S.pendH, r0 + 6 + c, cap, s, cB[c]);
-        } else {
+          for (int c = 0; c < 6; ++c) { cA[c] += oH[c]; cD[c] += oH[15 + c]; cp[c] += oH[21 + c]; }
 #pragma unroll
-          for (int c = 0; c < 6; ++c) {
-            st(S.pendH, r0 + c, cap, s, ld(S.pendH, r0 + c, cap, s) + cA[c]);
-            st(S.pendH, r0 + 15 + c, cap, s, ld(S.pendH, r0 + 15 + c, cap, s) + cD[c]);
-            st(S.pendH, r0 + 21 + c, cap, s, ld(S.pendH, r0 + 21 + c, cap, s) + cp[c]);
-          }
-#pragma unroll
-          for (int c = 0; c < 9; ++c) st(S.pendH, r0 + 6 + c, cap, s, ld(S.pendH, r0 + 6 + c, cap, s) + cB[c]);
+          for (int c = 0; c < 9; ++c) cB[c] += oH[6 + c];
         }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { st(S.pendH, r0 + c, cap, s, cA[c]); st(S.pendH, r0 + 15 + c, cap, s, cD[c]); st(S.pendH, r0 + 21 + c, cap, s, cp[c]); }
+#pragma unroll
+        for (int c = 0; c < 9; ++c) st(S.pendH, r0 + 6 + c, cap, s, cB[c]);
       }
     }
   }
@@ -387,7 +402,14 @@ LOIK_DEV void sweep_forward(const StateP& S, const int s, const double mu, const
   for (int i = 1; i <= nb; ++i) {
     const JointC& J = c_model.j[i];
     const int ji = i - 1;
-    double vin[6];
+    // ---- load phase A: what nu_i, v_i and the dof update need
+    double vin[6], UD[6], vold[6];
+    const double qa = ldc(S.jq, 2 * ji, cap, s), qb = ldc(S.jq, 2 * ji + 1, cap, s);
+    const double Dinv = ld(S.Dinv, ji, cap, s), ri = ld(S.r, ji, cap, s);
+    const double w_old = ld(S.w, ji, cap, s), nu_old = ld(S.nu, ji, cap, s), z_old = ld(S.z, ji, cap, s);
+    const double lb = S.lbv ? ldc(S.lbv, ji, cap, s) : J.lb, ub = S.ubv ? ldc(S.ubv, ji, cap, s) : J.ub;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { UD[c] = ld(S.UDinv, 6 * ji + c, cap, s); vold[c] = ld(S.v, 6 * ji + c, cap, s); }
     if (J.parent == 0) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) vin[c] = 0.0;
@@ -398,82 +420,86 @@ LOIK_DEV void sweep_forward(const StateP& S, const int s, const double mu, const
 #pragma unroll
       for (int c = 0; c < 6; ++c) vin[c] = ld(S.v, 6 * (J.parent - 1) + c, cap, s);
     }
+    // ---- maths A
     double R[9], t[3], v[6];
-    make_xf(J, ld(S.jq, 2 * ji, cap, s), ld(S.jq, 2 * ji + 1, cap, s), R, t);
+    make_xf(J, qa, qb, R, t);
     actinv_motion(R, t, vin, v);  // vi_parent (:125)
     // nu_i = -UDinv^T vp - Dinv r_i (:127)
     double acc = 0.0;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) acc += ld(S.UDinv, 6 * ji + c, cap, s) * v[c];
-    const double nu = -acc - ld(S.Dinv, ji, cap, s) * ld(S.r, ji, cap, s);
+    for (int c = 0; c < 6; ++c) acc += UD[c] * v[c];
+    const double nu = -acc - Dinv * ri;
     cy.nu_inf = amax(cy.nu_inf, nu);  // (:129-131)
     S_axpy(J, nu, v);                 // v_i = vp + S nu_i (:133-134)
 #pragma unroll
     for (int c = 0; c < 6; ++c) {     // delta_vis_inf_norm vs the previous iterate (:156-158)
-      cy.dvis_inf = amax(cy.dvis_inf, v[c] - ld(S.v, 6 * ji + c, cap, s));
-      st(S.v, 6 * ji + c, cap, s, v[c]);
+      cy.dvis_inf = amax(cy.dvis_inf, v[c] - vold[c]);
       vprev[c] = v[c];
     }
-    // f_i = H_i v_i + p_i (:139-140), delta_fis (:137-146)
+    // this joint's dof: delta_nu (:375), BoxProj (:388-394), w update (:454-458), CheckFeasibility's dot products (:588,590)
+    cy.dnu_inf = amax(cy.dnu_inf, nu - nu_old);
+    const double z = fmin(ub, fmax(lb, nu + inv_mu * w_old));
+    cy.dz_inf = amax(cy.dz_inf, z - z_old);
+    const double rp = nu - z;
+    cy.pres_slack = amax(cy.pres_slack, rp);
+    const double dw = mu * rp;
+    cy.dw_inf = amax(cy.dw_inf, dw);
+    cy.ubdw_p += ub * fmax(dw, 0.0);
+    cy.lbdw_m += lb * fmin(dw, 0.0);
+    // ---- load phase B: f_i = H_i v_i + p_i (:139-140), delta_fis (:137-146).  Issued before the stores of
+    // phase A so the requests overlap the maths above.
     {
-      double A[6], B[9], D[6];
+      double fold[6], p[6], A[6], B[9], D[6], f[6];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) { A[c] = ld(S.H, 21 * ji + c, cap, s); D[c] = ld(S.H, 21 * ji + 15 + c, cap, s); }
+      for (int c = 0; c < 6; ++c) {
+        fold[c] = ld(S.f, 6 * ji + c, cap, s); p[c] = ld(S.p, 6 * ji + c, cap, s);
+        A[c] = ld(S.H, 21 * ji + c, cap, s); D[c] = ld(S.H, 21 * ji + 15 + c, cap, s);
+      }
 #pragma unroll
       for (int c = 0; c < 9; ++c) B[c] = ld(S.H, 21 * ji + 6 + c, cap, s);
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        const double fl = A[si(a, 0)] * v[0] + A[si(a, 1)] * v[1] + A[si(a, 2)] * v[2] + B[3 * a] * v[3] + B[3 * a + 1] * v[4] + B[3 * a + 2] * v[5] + ld(S.p, 6 * ji + a, cap, s);
-        const double fa = B[a] * v[0] + B[3 + a] * v[1] + B[6 + a] * v[2] + D[si(a, 0)] * v[3] + D[si(a, 1)] * v[4] + D[si(a, 2)] * v[5] + ld(S.p, 6 * ji + 3 + a, cap, s);
-        cy.dfis_inf = amax(cy.dfis_inf, fl - ld(S.f, 6 * ji + a, cap, s));
-        cy.dfis_inf = amax(cy.dfis_inf, fa - ld(S.f, 6 * ji + 3 + a, cap, s));
-        st(S.f, 6 * ji + a, cap, s, fl);
-        st(S.f, 6 * ji + 3 + a, cap, s, fa);
+        f[a] = A[si(a, 0)] * v[0] + A[si(a, 1)] * v[1] + A[si(a, 2)] * v[2] + B[3 * a] * v[3] + B[3 * a + 1] * v[4] + B[3 * a + 2] * v[5] + p[a];
+        f[3 + a] = B[a] * v[0] + B[3 + a] * v[1] + B[6 + a] * v[2] + D[si(a, 0)] * v[3] + D[si(a, 1)] * v[4] + D[si(a, 2)] * v[5] + p[3 + a];
       }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) cy.dfis_inf = amax(cy.dfis_inf, f[c] - fold[c]);
+      // ---- store phase
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { st(S.v, 6 * ji + c, cap, s, v[c]); st(S.f, 6 * ji + c, cap, s, f[c]); }
     }
-    // this joint's dof: delta_nu (:375), BoxProj (:388-394), w update (:454-458), CheckFeasibility's dot products (:588,590)
-    {
-      const double lb = S.lbv ? ld(S.lbv, ji, cap, s) : J.lb, ub = S.ubv ? ld(S.ubv, ji, cap, s) : J.ub;
-      const double w_old = ld(S.w, ji, cap, s);
-      cy.dnu_inf = amax(cy.dnu_inf, nu - ld(S.nu, ji, cap, s));
-      const double z = fmin(ub, fmax(lb, nu + inv_mu * w_old));
-      cy.dz_inf = amax(cy.dz_inf, z - ld(S.z, ji, cap, s));
-      const double rp = nu - z;
-      cy.pres_slack = amax(cy.pres_slack, rp);
-      const double dw = mu * rp;
-      cy.dw_inf = amax(cy.dw_inf, dw);
-      cy.ubdw_p += ub * fmax(dw, 0.0);
-      cy.lbdw_m += lb * fmin(dw, 0.0);
-      st(S.nu, ji, cap, s, nu);
-      st(S.z, ji, cap, s, z);
-      st(S.w, ji, cap, s, w_old + dw);
-      if (DEBUG) st(S.prv, 6 * nb + ji, cap, s, rp);
-    }
+    st(S.nu, ji, cap, s, nu);
+    st(S.z, ji, cap, s, z);
+    st(S.w, ji, cap, s, w_old + dw);
+    if (DEBUG) st(S.prv, 6 * nb + ji, cap, s, rp);
     if (J.task >= 0) {  // DualUpdate for the task on this joint (:410-451)
       const int k = J.task;
       const TaskC& K = c_model.t[k];
-      double y[6];
+      double y[6], bk[6], yk[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { bk[c] = ldc(S.b, 6 * k + c, cap, s); yk[c] = ld(S.y, 6 * k + c, cap, s); }
       double plus = 0.0, minus = 0.0;
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
         const double Av = K.A[6 * a] * v[0] + K.A[6 * a + 1] * v[1] + K.A[6 * a + 2] * v[2] + K.A[6 * a + 3] * v[3] + K.A[6 * a + 4] * v[4] + K.A[6 * a + 5] * v[5];
-        const double bi = ld(S.b, 6 * k + a, cap, s);
-        const double e = Av - bi;          // Av_minus_b (:416)
+        const double e = Av - bk[a];       // Av_minus_b (:416)
         const double dy = mu_eq * e;       // delta_yis (:419)
-        y[a] = ld(S.y, 6 * k + a, cap, s) + dy;
-        st(S.y, 6 * k + a, cap, s, y[a]);
+        y[a] = yk[a] + dy;
         cy.dyis_inf = amax(cy.dyis_inf, dy);
         cy.Av_inf = amax(cy.Av_inf, Av);
         cy.pres_task = amax(cy.pres_task, e);
-        plus += bi * fmax(dy, 0.0);
-        minus += bi * fmin(dy, 0.0);
+        plus += bk[a] * fmax(dy, 0.0);
+        minus += bk[a] * fmin(dy, 0.0);
         if (DEBUG) st(S.prv, 6 * ji + a, cap, s, e);
       }
       cy.bTdy_p += plus;
       cy.bTdy_m += minus;
 #pragma unroll
-      for (int a = 0; a < 6; ++a)  // Aty = A^T y (:425)
+      for (int a = 0; a < 6; ++a) {
+        st(S.y, 6 * k + a, cap, s, y[a]);
+        // Aty = A^T y (:425)
         st(S.Aty, 6 * k + a, cap, s, K.A[a] * y[0] + K.A[6 + a] * y[1] + K.A[12 + a] * y[2] + K.A[18 + a] * y[3] + K.A[24 + a] * y[4] + K.A[30 + a] * y[5]);
+      }
     }
   }
 }
@@ -496,9 +522,12 @@ LOIK_DEV void sweep_residual(const StateP& S, const int s, Resid& rs) {
   for (int i = nb; i >= 1; --i) {
     const JointC& J = c_model.j[i];
     const int ji = i - 1;
-    double f[6], F[6], v[6];
+    // ---- load phase
+    double f[6], F[6], v[6], Fold[6], pF[6], oF[6];
+    const double w_i = ld(S.w, ji, cap, s), T_old = ld(S.T, ji, cap, s);
+    const double qa = ldc(S.jq, 2 * ji, cap, s), qb = ldc(S.jq, 2 * ji + 1, cap, s);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { f[c] = ld(S.f, 6 * ji + c, cap, s); v[c] = ld(S.v, 6 * ji + c, cap, s); }
+    for (int c = 0; c < 6; ++c) { f[c] = ld(S.f, 6 * ji + c, cap, s); v[c] = ld(S.v, 6 * ji + c, cap, s); Fold[c] = ld(S.F, 6 * ji + c, cap, s); }
     if (J.task >= 0) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) F[c] = ld(S.Aty, 6 * J.task + c, cap, s);  // (:438-439)
@@ -508,7 +537,17 @@ LOIK_DEV void sweep_residual(const StateP& S, const int s, Resid& rs) {
     }
     if (J.pend >= 0) {
 #pragma unroll
-      for (int c = 0; c < 6; ++c) F[c] += ld(S.pendF, 6 * J.pend + c, cap, s);
+      for (int c = 0; c < 6; ++c) pF[c] = ld(S.pendF, 6 * J.pend + c, cap, s);
+    }
+    const bool rmw = J.parent > 0 && !J.carry && !J.pfirst;
+    if (rmw) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) oF[c] = ld(S.pendF, 6 * J.ppend + c, cap, s);
+    }
+    // ---- maths
+    if (J.pend >= 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) F[c] += pF[c];
     }
     if (have_carry) {
 #pragma unroll
@@ -517,7 +556,7 @@ LOIK_DEV void sweep_residual(const StateP& S, const int s, Resid& rs) {
 #pragma unroll
     for (int c = 0; c < 6; ++c) F[c] += -f[c];  // (:210)
     // Href_v (fwd pass 2, :149-153) is recomputed here from v_i instead of being stored
-    double Hrv[6];
+    double Hrv[6], rd[6];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       Hrv[a] = J.HrA[si(a, 0)] * v[0] + J.HrA[si(a, 1)] * v[1] + J.HrA[si(a, 2)] * v[2] + J.HrB[3 * a] * v[3] + J.HrB[3 * a + 1] * v[4] + J.HrB[3 * a + 2] * v[5];
@@ -525,39 +564,43 @@ LOIK_DEV void sweep_residual(const StateP& S, const int s, Resid& rs) {
     }
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      rs.dF_inf = amax(rs.dF_inf, F[c] - ld(S.F, 6 * ji + c, cap, s));  // (:215-220)
-      rs.F_inf = amax(rs.F_inf, F[c]);                                  // (:223-225)
+      rs.dF_inf = amax(rs.dF_inf, F[c] - Fold[c]);  // (:215-220)
+      rs.F_inf = amax(rs.F_inf, F[c]);              // (:223-225)
       rs.Hrefv_inf = amax(rs.Hrefv_inf, Hrv[c]);
-      const double rd = Hrv[c] - J.Hv[c] + F[c];                        // (:228)
-      rs.dres_v = amax(rs.dres_v, rd);
-      st(S.F, 6 * ji + c, cap, s, F[c]);
-      if (DEBUG) st(S.drv, 6 * ji + c, cap, s, rd);
+      rd[c] = Hrv[c] - J.Hv[c] + F[c];              // (:228)
+      rs.dres_v = amax(rs.dres_v, rd[c]);
     }
     // Stf_plus_w (:231-236) and its delta (:471,:482-483)
-    const double T = St_dot(J, f) + ld(S.w, ji, cap, s);
+    const double T = St_dot(J, f) + w_i;
     rs.T_inf = amax(rs.T_inf, T);
-    rs.dT_inf = amax(rs.dT_inf, T - ld(S.T, ji, cap, s));
+    rs.dT_inf = amax(rs.dT_inf, T - T_old);
+    // ---- store phase
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      st(S.F, 6 * ji + c, cap, s, F[c]);
+      if (DEBUG) st(S.drv, 6 * ji + c, cap, s, rd[c]);
+    }
     st(S.T, ji, cap, s, T);
     if (DEBUG) st(S.drv, 6 * nb + ji, cap, s, T);
     have_carry = false;
     if (J.parent > 0) {  // fis_diff_plus_Aty[parent] += liMi.act(f_i) (:212)
       double R[9], t[3];
-      make_xf(J, ld(S.jq, 2 * ji, cap, s), ld(S.jq, 2 * ji + 1, cap, s), R, t);
+      make_xf(J, qa, qb, R, t);
       act_force(R, t, f, cF);
       if (J.carry) {
         have_carry = true;
-      } else if (J.pfirst) {
+      } else {
+        if (rmw) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) cF[c] += oF[c];
+        }
 #pragma unroll
         for (int c = 0; c < 6; ++c) st(S.pendF, 6 * J.ppend + c, cap, s, cF[c]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) st(S.pendF, 6 * J.ppend + c, cap, s, ld(S.pendF, 6 * J.ppend + c, cap, s) + cF[c]);
       }
     }
   }
   rs.dres_nu = rs.T_inf;  // dual_residual_vec[6nb:] = Stf_plus_w (:484)
 }
-
 // ---------------------------------------------------------------------------------------------
 // CheckConvergence (hxx:540-565) + CheckFeasibility (:572-606) + UpdateMu (:613-641) + the loop control
 // of Solve() (hpp:377-454) and InfeasibilityTailSolve() (hpp:271-319), per instance.

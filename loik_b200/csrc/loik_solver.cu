@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -16,7 +17,6 @@
 
 namespace loik {
 
-__constant__ ModelC c_model;
 
 constexpr int kBlock = 128;
 
@@ -26,8 +26,8 @@ constexpr int kBlock = 128;
 
 // One launch = up to `iters` ADMM iterations of every active instance (all three sweeps + decisions
 // fused; instances are independent so no grid-wide synchronisation is needed between iterations).
-template <bool DEBUG>
-__global__ void __launch_bounds__(kBlock) k_iterate(const StateP S, const int iters, const int fixed) {
+template <bool DEBUG, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_iterate(const StateP S, const int iters, const int fixed) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   bool active = false;
   if (s < S.n) {
@@ -258,6 +258,7 @@ struct loik_solver {
   int64_t launches = 0;
   int64_t sweeps = 0;
   int chunk_it = 0;  // iterations issued in the current solve
+  int minb = 3;
 };
 
 static uint64_t g_const_owner = 0;  // which solver's ModelC currently sits in c_model
@@ -281,6 +282,18 @@ static int upload_consts(loik_solver* h, cudaStream_t st) {
 }
 
 static inline int grid_for(int n) { return (n + kBlock - 1) / kBlock; }
+
+// One place that launches the fused iteration kernel.  `minb` (resident CTAs per SM the kernel is
+// compiled for: 2 -> <=255 regs, 3 -> <=168, 4 -> <=128) is a tuning knob (env LOIK_MINB).
+static void launch_iterate(loik_solver* h, cudaStream_t st, int iters, int fixed) {
+  const int g = grid_for(h->batch);
+#define LOIK_LAUNCH(DBG, MB) k_iterate<DBG, MB><<<g, kBlock, 0, st>>>(h->S, iters, fixed)
+  if (h->debug) { LOIK_LAUNCH(true, 2); }
+  else if (h->minb == 2) { LOIK_LAUNCH(false, 2); }
+  else if (h->minb == 3) { LOIK_LAUNCH(false, 3); }
+  else { LOIK_LAUNCH(false, 4); }
+#undef LOIK_LAUNCH
+}
 
 static int ensure_stage(loik_solver* h, size_t bytes) {
   if (bytes > h->h_stage_bytes) {
@@ -349,6 +362,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   loik_solver* h = new loik_solver();
   h->device = device; h->batch = batch; h->cap = (batch + 31) / 32 * 32;
   h->nj = nj; h->nb = nj - 1; h->nc = params->num_eq_c; h->prm = *params;
+  if (const char* e = std::getenv("LOIK_MINB")) { const int v = std::atoi(e); if (v >= 2 && v <= 4) h->minb = v; }
   ModelC& M = h->mc;
   std::memset(&M, 0, sizeof(M));
   M.nj = nj; M.nb = nj - 1; M.nc = h->nc;
@@ -538,8 +552,7 @@ static int run_loop(loik_solver* h, cudaStream_t st, int max_sweeps, bool fixed)
   while (done < max_sweeps) {
     const int chunk = std::min(fixed ? max_sweeps : 4, max_sweeps - done);
     CK(cudaMemsetAsync(h->d_n_active, 0, sizeof(int), st));
-    if (h->debug) k_iterate<true><<<grid_for(B), kBlock, 0, st>>>(h->S, chunk, fixed ? 1 : 0);
-    else k_iterate<false><<<grid_for(B), kBlock, 0, st>>>(h->S, chunk, fixed ? 1 : 0);
+    launch_iterate(h, st, chunk, fixed ? 1 : 0);
     h->launches++;
     h->sweeps += chunk;
     done += chunk;
@@ -631,8 +644,7 @@ int loik_iterate_fixed(loik_solver* h, int32_t iters, int32_t reset, void* strea
   if (rc) return rc;
   // one launch per iteration: this is the quantity the roofline is quoted on
   for (int i = 0; i < iters; ++i) {
-    if (h->debug) k_iterate<true><<<grid_for(h->batch), kBlock, 0, st>>>(h->S, 1, 1);
-    else k_iterate<false><<<grid_for(h->batch), kBlock, 0, st>>>(h->S, 1, 1);
+    launch_iterate(h, st, 1, 1);
   }
   h->launches += iters; h->sweeps += iters;
   CK(cudaGetLastError());
@@ -653,8 +665,7 @@ int loik_solve_chunk(loik_solver* h, int32_t iters, void* stream) {
   int rc = upload_consts(h, st);
   if (rc) return rc;
   CK(cudaMemsetAsync(h->d_n_active, 0, sizeof(int), st));
-  if (h->debug) k_iterate<true><<<grid_for(h->batch), kBlock, 0, st>>>(h->S, iters, 0);
-  else k_iterate<false><<<grid_for(h->batch), kBlock, 0, st>>>(h->S, iters, 0);
+  launch_iterate(h, st, iters, 0);
   h->launches++; h->sweeps += iters; h->chunk_it += iters;
   CK(cudaGetLastError());
   return LOIK_OK;

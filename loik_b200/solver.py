@@ -151,6 +151,7 @@ class FirstOrderLoikOptimized:
         self.model = model
         self.batch = int(batch)
         self.nc = int(num_eq_c)
+        self.max_iter = int(max_iter)
         self._keep = [np.ascontiguousarray(model.parent, np.int32), np.ascontiguousarray(model.jtype, np.int32),
                       np.ascontiguousarray(model.axis, np.float64), np.ascontiguousarray(model.placement_R, np.float64),
                       np.ascontiguousarray(model.placement_p, np.float64)]
@@ -188,6 +189,9 @@ class FirstOrderLoikOptimized:
         if A.shape[0] != ids.shape[0]:
             raise RuntimeError("[IkProblemFormulation::UpdateEqConstraints]: task_constraint_ids, Ais, and bis have "
                                "different size !!!")
+        if ids.shape[0] != nc:
+            raise RuntimeError("[IkProblemFormulation::UpdateEqConstraints]: number of equality constraints doesn't "
+                               "match initialization!!!")
         qb, bb, lbb, ubb = _Buf(q), _Buf(bis), _Buf(lb), _Buf(ub)
         if qb.shape not in ((B, self.model.nq),) and not (B == 1 and qb.shape == (self.model.nq,)):
             raise RuntimeError(f"q must be [batch={B}, nq={self.model.nq}]")
@@ -290,6 +294,7 @@ class FirstOrderLoikOptimized:
     # ---- setters / getters ----------------------------------------------------------------------
     def set_max_iter(self, m):
         self._check(self._lib.loik_set_max_iter(self._h, int(m)))
+        self.max_iter = int(m)
 
     def set_rho(self, rho):
         self._check(self._lib.loik_set_rho(self._h, float(rho)))

@@ -1,0 +1,57 @@
+"""The C-ABI library loads and exports every symbol include/loik_b200.h declares (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "loik_b200.h")).read()
+    return sorted(set(re.findall(r"LOIK_API\s+[\w\s\*]+?\b(loik_\w+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    from loik_b200 import build, solver
+    lib_path = build.build()
+    lib = ctypes.CDLL(lib_path)
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/loik_b200.h but not exported"
+    assert sorted(solver.EXPORTS) == names
+    lib.loik_abi_version.restype = ctypes.c_int32
+    assert lib.loik_abi_version() == 1
+
+
+def test_enums_match_header():
+    from loik_b200 import solver
+    src = open(os.path.join(ROOT, "include", "loik_b200.h")).read()
+    body = src[src.index("typedef enum loik_norm_index"):src.index("} loik_norm_index")]
+    names = re.findall(r"LOIK_N_\w+", body)
+    assert len(names) == len(solver.NORM_NAMES)
+    body = src[src.index("typedef enum loik_field"):src.index("} loik_field")]
+    fields = re.findall(r"^\s*(LOIK_F_\w+)", body, flags=re.M)
+    assert len(fields) == 22 and fields[solver.F_RESIDUALS] == "LOIK_F_RESIDUALS" and fields[solver.F_Z] == "LOIK_F_Z"
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device the product path fails loudly (it must never route through the oracle)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from loik_b200 import problems, robots, solver
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
+        solver.make_solver(robots.panda(), problems.bench_params(1), 8)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "loik_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("oracle-vs", "").lower() or f == "robots.py" or "import oracle" not in txt, f
+                assert "import oracle" not in txt and "from oracle" not in txt, f

@@ -1,0 +1,329 @@
+"""CUDA path (through the C ABI) vs oracle B on the same seeded inputs.  Run on the B200 box: -m gpu.
+
+Structure follows the reference's tests (``/root/reference/tests/loik-loid.cpp``): component-wise after each
+(fused) step :305-556, end-to-end :559-671, reset / repeated solves :674-984, with the CUDA solver in the role
+of the optimized solver and the oracle in the role of the ground truth.
+
+Tolerances: the reference compares its two solvers at 1e-10 abs-or-rel (:39-83); north_star's gate is 1e-6
+rel-inf on z, nu, w, y plus identical iteration counts / mu / flags.  Per-step comparisons use 1e-10
+(scaled by the magnitude of the quantity), full solves use 1e-6 rel-inf and report the number of instances
+whose decision trace (iteration count, final mu, status) diverged.
+"""
+import numpy as np
+import pytest
+
+from loik_b200 import problems, robots
+from tests.helpers import check_abs_or_rel, ctor_kwargs, instance, prob_args, rel_inf
+
+pytestmark = pytest.mark.gpu
+
+STEP_TOL = 1e-10
+
+
+def _oracle(model, params):
+    from oracle import recursion
+    return recursion.FirstOrderLoikOptimized(model, **ctor_kwargs(params))
+
+
+def _gpu(model, params, batch):
+    from loik_b200 import solver
+    return solver.make_solver(model, params, batch)
+
+
+def _oracle_batch(model, params, pb, nthreads=8, **kw):
+    from oracle import recursion
+    return recursion.batch_solve(model, params, pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"],
+                                 pb["lb"], pb["ub"], nthreads=nthreads, **kw)
+
+
+def _solve_init(G, pb):
+    G.SolveInit(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
+
+
+def _compare_steps(model, params, pb, n_iters, what):
+    """Step-by-step: after each fused CUDA step compare every field the oracle exposes at the same point."""
+    B = pb["q"].shape[0]
+    G = _gpu(model, params, B)
+    G.set_debug(True)
+    _solve_init(G, pb)
+    G.ResetRecursion()
+    O = []
+    for i in range(B):
+        o = _oracle(model, params)
+        o.SolveInit(*instance(pb, i))
+        o.ResetSolver()
+        O.append(o)
+    nb = model.nb
+    for it in range(1, n_iters + 1):
+        tag = f"{what} it{it}"
+        # ---- backward: UpdatePrev + ResetInfNorms + FwdPass1 + BwdPass
+        for o in O:
+            o.UpdatePrev(); o.ResetInfNorms(); o.FwdPass1(); o.BwdPassOptimizedVisitor()
+        G.StepBackward()
+        H, p, UD, Di, r = G.His, G.pis, G.UDinv, G.Dinv, G.r
+        for i, o in enumerate(O):
+            check_abs_or_rel(H[i], o.His[1:], STEP_TOL, tag + " His")
+            check_abs_or_rel(p[i], o.pis[1:], STEP_TOL, tag + " pis")
+            check_abs_or_rel(UD[i], o.UDinv[1:], STEP_TOL, tag + " UDinv")
+            check_abs_or_rel(Di[i], o.Dinv[1:], STEP_TOL, tag + " Dinv")
+            check_abs_or_rel(r[i], o.r, STEP_TOL, tag + " r")
+        # ---- forward: FwdPass2 + BoxProj + DualUpdate (+ primal residuals)
+        for o in O:
+            o.FwdPass2OptimizedVisitor(); o.BoxProj(); o.DualUpdate()
+        G.StepForward()
+        nu, v, f, z, w, y, Aty = G.nu, G.vis, G.fis, G.z, G.w, G.yis, G.Aty
+        for i, o in enumerate(O):
+            check_abs_or_rel(nu[i], o.nu, STEP_TOL, tag + " nu")
+            check_abs_or_rel(v[i], o.vis[1:], STEP_TOL, tag + " vis")
+            check_abs_or_rel(f[i], o.fis[1:], STEP_TOL, tag + " fis")
+            check_abs_or_rel(z[i], o.z, STEP_TOL, tag + " z")
+            check_abs_or_rel(w[i], o.w, STEP_TOL, tag + " w")
+            check_abs_or_rel(y[i], o.yis, STEP_TOL, tag + " yis")
+            check_abs_or_rel(Aty[i], o.Aty, STEP_TOL, tag + " Aty")
+        # ---- residual: ComputeResiduals + CheckConvergence + CheckFeasibility + UpdateMu
+        for o in O:
+            o.ComputeResiduals(); o.CheckConvergence()
+            if it > 1:
+                o.CheckFeasibility()
+        G.StepResidual()
+        F, T, res, nrm = G.fis_diff_plus_Aty, G.Stf_plus_w, G.get(18), G.norms()
+        prv, drv = G.get_primal_residual_vec(), G.get_dual_residual_vec()
+        for i, o in enumerate(O):
+            fscale = max(1.0, np.abs(o.fis).max())
+            assert np.abs(F[i] - o.fis_diff_plus_Aty[1:]).max() < 1e-12 * fscale * 10, tag + " fis_diff_plus_Aty"
+            assert np.abs(T[i] - o.Stf_plus_w).max() < 1e-12 * fscale * 10, tag + " Stf_plus_w"
+            check_abs_or_rel(prv[i], o.get_primal_residual_vec(), STEP_TOL, tag + " primal_residual_vec")
+            assert np.abs(drv[i] - o.get_dual_residual_vec()).max() < 1e-12 * fscale * 10, tag + " dual_residual_vec"
+            check_abs_or_rel(res[i, 0], o.get_primal_residual(), STEP_TOL, tag + " primal_residual")
+            assert abs(res[i, 1] - o.get_dual_residual()) < 1e-12 * fscale * 10, tag + " dual_residual"
+            check_abs_or_rel(res[i, 2], o.get_tol_primal(), STEP_TOL, tag + " tol_primal")
+            check_abs_or_rel(res[i, 3], o.get_tol_dual(), 1e-9, tag + " tol_dual")
+            for nm in ("Av_inf_norm", "nu_inf_norm", "delta_vis_inf_norm", "delta_z_inf_norm", "delta_fis_inf_norm",
+                       "delta_yis_inf_norm", "delta_w_inf_norm", "bT_delta_y_plus", "bT_delta_y_minus",
+                       "primal_residual_task", "primal_residual_slack"):
+                ref = o.scalar(nm)
+                assert abs(nrm[nm][i] - ref) <= 1e-9 * max(1.0, abs(ref)) * (fscale if "fis" in nm else 1.0), f"{tag} {nm}"
+            if it > 1:
+                assert bool(nrm["primal_infeasibility_cond_1"][i]) == o.get_primal_infeasibility_cond_1(), tag
+                assert bool(nrm["primal_infeasibility_cond_2"][i]) == o.get_primal_infeasibility_cond_2(), tag
+        # loop control: oracle instances that stopped are frozen exactly like the CUDA ones
+        st = G.get_status()
+        for i, o in enumerate(O):
+            stopped = o.get_convergence_status() or o.get_primal_infeasibility_status()
+            if not stopped:
+                o.UpdateMu()
+            assert bool(st[i] & 1) == o.get_convergence_status(), tag + " converged flag"
+        mu = G.get_mu()
+        for i, o in enumerate(O):
+            assert mu[i] == o.get_mu(), tag + " mu"
+        if any(o.get_convergence_status() or o.get_primal_infeasibility_status() for o in O):
+            break  # per-step driving of stopped instances is the end-to-end tests' job
+    G.close()
+
+
+@pytest.mark.parametrize("name,bound", [("talos", 1.0), ("panda", 1.0), ("panda9", 2.0), ("ur10", 1.0)])
+def test_component_wise_fixture(name, bound):
+    """tests/loik-loid.cpp:305-556 on the reference's fixture shape (neutral q, A = I, b = (0,0,.5,0,0,0))."""
+    model = robots.get_robot(name)
+    pr = problems.fixture_problem(model, bound)
+    pb = dict(pr, q=pr["q"][None], bis=pr["bis"][None])
+    _compare_steps(model, dict(problems.FIXTURE_PARAMS, max_iter=200), pb, 3, name)
+
+
+@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "panda9"])
+def test_component_wise_random_batch(name):
+    model = robots.get_robot(name)
+    pb = problems.random_batch(model, 40, seed=11)
+    _compare_steps(model, problems.bench_params(len(pb["ids"])), pb, 4, name)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_component_wise_random_trees(seed):
+    """Every joint type, random branching, non-identity A and H_ref, non-zero v_ref, two tasks."""
+    model = robots.random_tree(10 + 3 * seed, seed)
+    rng = np.random.default_rng(100 + seed)
+    B = 33
+    ids = np.array(sorted(rng.choice(np.arange(1, model.nj), size=2, replace=False)), np.int32)
+    Hs = rng.normal(size=(6, 6))
+    pb = dict(q=rng.uniform(model.q_min, model.q_max, size=(B, model.nq)), H_ref=np.eye(6) + 0.1 * (Hs + Hs.T),
+              v_ref=0.1 * rng.normal(size=6), ids=ids,
+              Ais=np.stack([np.eye(6) + 0.3 * rng.normal(size=(6, 6)) for _ in range(2)]),
+              bis=rng.uniform(-0.5, 0.5, size=(B, 2, 6)), lb=-model.v_max, ub=model.v_max)
+    _compare_steps(model, dict(problems.FIXTURE_PARAMS, max_iter=200, num_eq_c=2), pb, 3, f"tree{seed}")
+
+
+def _compare_solves(model, params, pb, what, tol=1e-6, max_diverged_frac=0.0):
+    B = pb["q"].shape[0]
+    G = _gpu(model, params, B)
+    _solve_init(G, pb)
+    G.Solve()
+    ref = _oracle_batch(model, params, pb)
+    it, mu, st = G.get_iter(), G.get_mu(), G.get_status()
+    ref_st = ref["status"]
+    same = (it == ref["iters"]) & (mu == ref["mu"]) & ((st & 3) == (ref_st & 3))
+    diverged = int((~same).sum())
+    z, nu, w, y = G.z, G.nu, G.w, G.yis
+    worst = 0.0
+    for i in np.nonzero(same)[0]:
+        worst = max(worst, rel_inf(z[i], ref["z"][i]), rel_inf(nu[i], ref["nu"][i]), rel_inf(w[i], ref["w"][i]),
+                    rel_inf(y[i], ref["y"][i]))
+    print(f"[{what}] B={B} diverged decision traces: {diverged}/{B}; worst rel-inf over z,nu,w,y: {worst:.3e}; "
+          f"mean iters {it.mean():.2f}")
+    assert worst < tol, f"{what}: rel-inf {worst:.3e} >= {tol}"
+    assert diverged <= max_diverged_frac * B, f"{what}: {diverged} instances with a different iteration count / mu / status"
+    s = G.stats()
+    assert s["total_iters"] == int(it.sum())
+    assert s["converged"] == int((st & 1).sum())
+    G.close()
+
+
+@pytest.mark.parametrize("name,bound", [("talos", 2.0), ("panda", 2.0), ("ur10", 2.0)])
+def test_end_to_end_fixture(name, bound):
+    """tests/loik-loid.cpp:559-671 (max_iter = 8, bounds +-2)."""
+    model = robots.get_robot(name)
+    pr = problems.fixture_problem(model, bound)
+    pb = dict(pr, q=pr["q"][None], bis=pr["bis"][None])
+    _compare_solves(model, dict(problems.FIXTURE_PARAMS, max_iter=8), pb, name + " fixture")
+
+
+@pytest.mark.parametrize("name,B", [("panda", 4096), ("ur10", 4096), ("talos", 1024), ("panda9", 1024)])
+def test_end_to_end_random_batch(name, B):
+    """Full solves (max_iter = 200) of the BASELINE configs at a size the oracle finishes in seconds."""
+    model = robots.get_robot(name)
+    pb = problems.random_batch(model, B, seed=0)
+    _compare_solves(model, problems.bench_params(len(pb["ids"])), pb, name, max_diverged_frac=0.002)
+
+
+def test_solve_full_and_repeat():
+    """Solve(args) == SolveInit + Solve(), and repeated solves reproduce themselves (tests/loik-loid.cpp:261-303,868-984)."""
+    model = robots.panda()
+    pb = problems.random_batch(model, 512, seed=5)
+    params = problems.bench_params(1)
+    G = _gpu(model, params, 512)
+    _solve_init(G, pb)
+    G.Solve()
+    z1, it1 = G.z, G.get_iter()
+    G.Solve()
+    np.testing.assert_array_equal(G.z, z1)
+    np.testing.assert_array_equal(G.get_iter(), it1)
+    G.Solve(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
+    np.testing.assert_array_equal(G.z, z1)
+    np.testing.assert_array_equal(G.get_iter(), it1)
+    G.close()
+
+
+def test_device_pointer_inputs_and_outputs():
+    """Same results when q / b arrive as CUDA tensors and z is written to a CUDA tensor."""
+    import torch
+    model = robots.ur10()
+    pb = problems.random_batch(model, 300, seed=9)
+    params = problems.bench_params(1)
+    G = _gpu(model, params, 300)
+    _solve_init(G, pb)
+    G.Solve()
+    z_host = G.z
+    G2 = _gpu(model, params, 300)
+    G2.SolveInit(torch.as_tensor(pb["q"]).cuda(), pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"],
+                 torch.as_tensor(pb["bis"]).cuda(), pb["lb"], pb["ub"])
+    G2.Solve()
+    out = torch.empty(300, model.nv, dtype=torch.float64, device="cuda")
+    from loik_b200 import solver
+    G2.get(solver.F_Z, out=out)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), z_host)
+    G.close(); G2.close()
+
+
+def test_per_instance_bounds_and_shared_b():
+    model = robots.panda()
+    B = 64
+    pb = problems.random_batch(model, B, seed=2)
+    rng = np.random.default_rng(0)
+    ub = model.v_max[None] * rng.uniform(0.05, 1.0, size=(B, model.nv))
+    pb2 = dict(pb, lb=-ub, ub=ub, bis=pb["bis"][0])
+    params = problems.bench_params(1)
+    G = _gpu(model, params, B)
+    _solve_init(G, pb2)
+    G.Solve()
+    z, it = G.z, G.get_iter()
+    for i in range(B):
+        o = _oracle(model, params)
+        o.SolveInit(pb["q"][i], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"][0], -ub[i], ub[i])
+        o.Solve()
+        assert o.get_iter() == it[i]
+        assert rel_inf(z[i], o.z) < 1e-6
+    G.close()
+
+
+def test_tailored_solve_and_warm_start():
+    """Solve(q, c_id, Ai, bi) (hpp:596-695), cold and warm-started, against the oracle's same call sequence."""
+    model = robots.panda()
+    B = 128
+    pb = problems.random_batch(model, B, seed=4)
+    pb_next = problems.random_batch(model, B, seed=5)
+    for warm in (False, True):
+        params = dict(problems.bench_params(1), warm_start=warm)
+        G = _gpu(model, params, B)
+        G.Solve(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
+        q2 = pb["q"] + 0.01 * (pb_next["q"] - pb["q"])
+        b2 = pb_next["bis"][:, 0]
+        G.Solve(q2, int(pb["ids"][0]), pb["Ais"][0], b2)
+        z, it, mu = G.z, G.get_iter(), G.get_mu()
+        bad = 0
+        for i in range(B):
+            o = _oracle(model, params)
+            o.Solve(*instance(pb, i))
+            o.Solve(q2[i], int(pb["ids"][0]), pb["Ais"][0], b2[i])
+            if o.get_iter() != it[i] or o.get_mu() != mu[i]:
+                bad += 1
+                continue
+            assert rel_inf(z[i], o.z) < 1e-6, f"warm={warm} instance {i}"
+        assert bad == 0, f"warm={warm}: {bad} diverged decision traces"
+        G.close()
+
+
+def test_fixed_iteration_mode_matches_oracle():
+    """Fixed-iteration (throughput) mode == the oracle driven the same way.  5 iterations: once an instance has
+    converged its residuals are rounding noise and the mu-update ratio tests (hxx:617-628) become arbitrary."""
+    model = robots.panda()
+    B = 256
+    pb = problems.random_batch(model, B, seed=6)
+    params = problems.bench_params(1)
+    G = _gpu(model, params, B)
+    _solve_init(G, pb)
+    G.IterateFixed(5)
+    ref = _oracle_batch(model, params, pb, mode=1, fixed_iters=5)
+    assert (G.get_iter() == 5).all()
+    same = G.get_mu() == ref["mu"]
+    assert same.mean() > 0.99
+    z = G.z
+    for i in np.nonzero(same)[0]:
+        assert rel_inf(z[i], ref["z"][i]) < 1e-6
+    G.close()
+
+
+def test_error_paths():
+    """Same error conditions as the reference's std::runtime_error sites, surfaced as RuntimeError."""
+    from loik_b200 import solver
+    model = robots.panda()
+    p = problems.bench_params(1)
+    with pytest.raises(RuntimeError, match="equality constraint dimension is not 6"):
+        solver.make_solver(model, dict(p, eq_c_dim=3), 4)
+    G = _gpu(model, p, 4)
+    pb = problems.random_batch(model, 4, seed=0)
+    with pytest.raises(RuntimeError, match="call loik_solve_init first"):
+        G.Solve()
+    with pytest.raises(RuntimeError, match="number of equality constraints"):
+        G.SolveInit(pb["q"], pb["H_ref"], pb["v_ref"], np.array([3, 5], np.int32), np.tile(np.eye(6), (2, 1, 1)),
+                    np.zeros((4, 2, 6)), pb["lb"], pb["ub"])
+    with pytest.raises(RuntimeError, match="dimension"):
+        G.SolveInit(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], np.zeros(3), np.zeros(3))
+    _solve_init(G, pb)
+    with pytest.raises(RuntimeError, match="doesn't yet exist"):
+        G.Solve(pb["q"], 2, np.eye(6), np.zeros((4, 6)))
+    G.close()
+    Go = _gpu(model, dict(p, mu_update_strat=1), 4)
+    _solve_init(Go, pb)
+    with pytest.raises(RuntimeError, match="not yet implemented"):
+        Go.Solve()
+    Go.close()
