@@ -5,8 +5,11 @@
 // divergence (joint types / tree topology are batch-uniform and live in __constant__ memory), and
 // the chain dependency between a joint and its parent never leaves the thread's registers.
 //
-// HBM layout (joint-major SoA): every per-instance quantity is a set of "rows" of `cap` doubles,
-// row index = (joint-1)*width + component, element index = instance slot.
+// HBM layout (tile-major, joint-major SoA inside a tile): instances are grouped in tiles of 32 (one
+// warp).  A tile is one contiguous record of `rows` rows x 32 lanes of doubles; every per-instance
+// quantity is a set of rows, row index = field offset + (joint-1)*width + component.  A warp reads a
+// row as one 256 B line, and because the lane stride is fixed the row offsets inside a joint step are
+// compile-time immediates of the load/store instructions (no per-access address arithmetic).
 //
 // The maths restates loik-loid-optimized.hxx (reference file:line cited per block); nothing here is
 // a translation of the Eigen/Pinocchio templates: H is kept as three 3x3 blocks (LL sym, LA, AA sym
@@ -42,9 +45,29 @@ struct TaskC {
   int joint, pad;
 };
 
+// Tile record layout.  Rows are grouped so that everything one joint step touches is contiguous and
+// addressed as  base(joint) + compile-time row * 256 B:
+//   [ globals | joint 1 | joint 2 | ... | task 0 | ... | pending slots | debug vectors ]
+enum : int {  // rows of a joint block
+  JR_V = 0, JR_F = 6, JR_FD = 12, JR_NU = 18, JR_Z = 19, JR_W = 20, JR_T = 21,  // persistent state (22 rows)
+  JR_JQ = 22, JR_LB = 24, JR_UB = 25,                                             // per-instance problem data
+  JR_H = 26, JR_P = 47, JR_UD = 53, JR_DINV = 59, JR_R = 60,                      // backward -> forward workspace (35 rows)
+  JR_ROWS = 61
+};
+enum : int { TR_Y = 0, TR_ATY = 6, TR_B = 12, TR_ATB = 18, TR_ROWS = 24 };        // rows of a task block
+enum : int { PR_H = 0, PR_F = 27, PR_ROWS = 33 };                                 // rows of a pending-accumulator block
+enum : int { GR_MU = 0, GR_BINF = 1, GR_CTL = 2, GR_RES = 3, GR_CARRY = 7, GR_NORMS = 21, GR_ROWS = 47 };  // globals
+
+struct Offs {
+  int glob, joint0, task0, pend0;  // first row of the globals, of joint 1, of task 0, of pending slot 0
+  int prv, drv;                    // debug: primal / dual residual vectors (7 nb rows each)
+  int rows;                        // rows per tile record
+};
+
 struct ModelC {
   int nj, nb, nc, npend;
-  int max_iter, pad;
+  int max_iter, bounds_per_instance;
+  Offs off;
   double rho, mu0, mu_scale, tol_abs, tol_rel, tol_pinf, tol_dinf, tol_tail, Hv_inf;
   JointC j[kMaxJoints];
   TaskC t[kMaxTasks];
@@ -58,30 +81,29 @@ struct Carry {
 constexpr int kCarryRows = 14;
 
 struct StateP {
-  int cap;   // row stride (slots)
-  int n;     // slots in use
-  // persistent per-instance state (22 nb + 12 nc rows)
-  double *v, *f, *F, *nu, *z, *w, *T, *y, *Aty;
-  // per-instance problem data
-  double *jq, *b, *Atb, *binf, *lbv, *ubv;
-  // per-instance control + results
-  double *mu, *res;   // res: primal_residual, dual_residual, tol_primal, tol_dual
-  int *status, *iter;
-  // workspace written by the backward sweep and read by the forward sweep (35 nb rows + pending slots)
-  double *H, *p, *UDinv, *Dinv, *r, *pendH, *pendF;
-  double *carry;      // [kCarryRows][cap] (step-by-step interface only)
-  // debug mirrors of reference members
-  double *norms, *prv, *drv;
-  int *n_active;
+  double* arena;      // tile records
+  int n;              // slots in use (instances)
+  const int* list;    // optional compaction list: thread k works on slot list[k]
+  const int* n_list;  // device-resident length of `list`
+  int* n_active;      // device counter: instances still active after this launch
 };
 
-__constant__ ModelC c_model;  // single translation unit (loik_solver.cu)
+// Constant memory is per module: kConstSlots solvers can have kernels in flight concurrently (one slot each).
+constexpr int kConstSlots = 2;
+__constant__ ModelC c_models[kConstSlots];  // single translation unit (loik_solver.cu)
 
 #define LOIK_DEV __device__ __forceinline__
 
 __host__ __device__ __forceinline__ constexpr int si(int i, int j) { return i <= j ? (i * (5 - i)) / 2 + j : (j * (5 - j)) / 2 + i; }
-LOIK_DEV double ld(const double* base, int row, int cap, int s) { return base[(size_t)row * cap + s]; }
-LOIK_DEV void st(double* base, int row, int cap, int s, double x) { base[(size_t)row * cap + s] = x; }
+// T = this thread's lane inside its tile record; row r lives at T[r * 32].
+LOIK_DEV double* tile_ptr(const StateP& S, const ModelC& c_model, int s) { return S.arena + ((size_t)(s >> 5) * c_model.off.rows) * 32 + (s & 31); }
+LOIK_DEV double ld(const double* P, int row) { return P[row * 32]; }
+LOIK_DEV void st(double* P, int row, double x) { P[row * 32] = x; }
+// block base pointers: computed once per joint step, rows inside a block are immediates
+LOIK_DEV double* joint_blk(double* T, const Offs& O, int ji) { return T + (size_t)(O.joint0 + JR_ROWS * ji) * 32; }
+LOIK_DEV double* task_blk(double* T, const Offs& O, int k) { return T + (size_t)(O.task0 + TR_ROWS * k) * 32; }
+LOIK_DEV double* pend_blk(double* T, const Offs& O, int k) { return T + (size_t)(O.pend0 + PR_ROWS * k) * 32; }
+LOIK_DEV double* glob_blk(double* T, const Offs& O) { return T + (size_t)O.glob * 32; }
 LOIK_DEV double amax(double m, double x) { return fmax(m, fabs(x)); }
 
 // liMi = jointPlacements[i] * M_i(q)   (FwdPassInit, hxx:263-264).  (a, b) = (sin q, cos q) for
@@ -276,30 +298,32 @@ LOIK_DEV void actinv_motion(const double (&R)[9], const double (&t)[3], const do
 // instruction, so one warp keeps tens of 256 B requests in flight (the compiler cannot hoist a load
 // above a store to a possibly-aliasing row, so interleaving them would serialise on DRAM latency).
 // ---------------------------------------------------------------------------------------------
-LOIK_DEV double ldc(const double* base, int row, int cap, int s) { return __ldg(base + (size_t)row * cap + s); }  // read-only data
+LOIK_DEV double ldc(const double* T, int row) { return __ldg(T + row * 32); }  // read-only data
 
 // ---------------------------------------------------------------------------------------------
 // Backward sweep: FwdPass1 (hxx:290-338) fused into BwdPassOptimizedVisitor (hxx:345-354, algo :31-81).
 // Leaves for the forward sweep, per joint: H_i and p_i (accumulated over the subtree, un-projected,
 // = His[i]/pis[i] after the reference's BwdPass), UDinv_i, Dinv_i, r_i.
 // ---------------------------------------------------------------------------------------------
-LOIK_DEV void sweep_backward(const StateP& S, const int s, const double mu, const double mu_eq) {
-  const int cap = S.cap, nb = c_model.nb;
+LOIK_DEV void sweep_backward(const ModelC& c_model, double* __restrict__ T, const double mu, const double mu_eq) {
+  const Offs& O = c_model.off;
+  const int nb = c_model.nb;
   const double rho = c_model.rho;
   double cA[6], cB[9], cD[6], cp[6];  // contribution carried from child i+1
   bool have_carry = false;
   for (int i = nb; i >= 1; --i) {
     const JointC& J = c_model.j[i];
-    const int ji = i - 1;
+    double* Pj = joint_blk(T, O, i - 1);
     // ---- load phase
     double vold[6], aty[6], atb[6];
-    const double w_i = ld(S.w, ji, cap, s), z_i = ld(S.z, ji, cap, s);
-    const double qa = ldc(S.jq, 2 * ji, cap, s), qb = ldc(S.jq, 2 * ji + 1, cap, s);
+    const double w_i = ld(Pj, JR_W), z_i = ld(Pj, JR_Z);
+    const double qa = ldc(Pj, JR_JQ), qb = ldc(Pj, JR_JQ + 1);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) vold[c] = ld(S.v, 6 * ji + c, cap, s);
+    for (int c = 0; c < 6; ++c) vold[c] = ld(Pj, JR_V + c);
     if (J.task >= 0) {
+      const double* Pk = task_blk(T, O, J.task);
 #pragma unroll
-      for (int c = 0; c < 6; ++c) { aty[c] = ld(S.Aty, 6 * J.task + c, cap, s); atb[c] = ldc(S.Atb, 6 * J.task + c, cap, s); }
+      for (int c = 0; c < 6; ++c) { aty[c] = ld(Pk, TR_ATY + c); atb[c] = ldc(Pk, TR_ATB + c); }
     }
     // ---- FwdPass1: H_i = rho I + Href_i (:304-306); p_i = -rho v_prev_i - Hv_i (:310-313).  v still holds the
     // previous iterate here, which is the reference's vis_prev (UpdatePrev, data hxx:192-197).
@@ -322,11 +346,11 @@ LOIK_DEV void sweep_backward(const StateP& S, const int s, const double mu, cons
     }
     // children's contributions: His[parent] += SE3actOn(...), pis[parent] += liMi.act(...) (:66,:74)
     if (J.pend >= 0) {
-      const int r0 = 27 * J.pend;
+      const double* Pp = pend_blk(T, O, J.pend);
 #pragma unroll
-      for (int c = 0; c < 6; ++c) { A[c] += ld(S.pendH, r0 + c, cap, s); D[c] += ld(S.pendH, r0 + 15 + c, cap, s); p[c] += ld(S.pendH, r0 + 21 + c, cap, s); }
+      for (int c = 0; c < 6; ++c) { A[c] += ld(Pp, PR_H + c); D[c] += ld(Pp, PR_H + 15 + c); p[c] += ld(Pp, PR_H + 21 + c); }
 #pragma unroll
-      for (int c = 0; c < 9; ++c) B[c] += ld(S.pendH, r0 + 6 + c, cap, s);
+      for (int c = 0; c < 9; ++c) B[c] += ld(Pp, PR_H + 6 + c);
     }
     if (have_carry) {
 #pragma unroll
@@ -344,11 +368,11 @@ LOIK_DEV void sweep_backward(const StateP& S, const int s, const double mu, cons
     const double ri = (w_i - mu * z_i) + St_dot(J, p);
     // ---- store phase 1: hand H_i, p_i, UDinv_i, Dinv_i, r_i to the forward sweep
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { st(S.H, 21 * ji + c, cap, s, A[c]); st(S.H, 21 * ji + 15 + c, cap, s, D[c]); st(S.p, 6 * ji + c, cap, s, p[c]); st(S.UDinv, 6 * ji + c, cap, s, UD[c]); }
+    for (int c = 0; c < 6; ++c) { st(Pj, JR_H + c, A[c]); st(Pj, JR_H + 15 + c, D[c]); st(Pj, JR_P + c, p[c]); st(Pj, JR_UD + c, UD[c]); }
 #pragma unroll
-    for (int c = 0; c < 9; ++c) st(S.H, 21 * ji + 6 + c, cap, s, B[c]);
-    st(S.Dinv, ji, cap, s, Dinv);
-    st(S.r, ji, cap, s, ri);
+    for (int c = 0; c < 9; ++c) st(Pj, JR_H + 6 + c, B[c]);
+    st(Pj, JR_DINV, Dinv);
+    st(Pj, JR_R, ri);
     have_carry = false;
     if (J.parent > 0) {
       // projection: H -= UDinv U^T (calc_aba update_I, :63), p -= UDinv r_i (:71-73)
@@ -369,20 +393,20 @@ LOIK_DEV void sweep_backward(const StateP& S, const int s, const double mu, cons
       if (J.carry) {
         have_carry = true;
       } else {
-        const int r0 = 27 * J.ppend;
+        double* Pp = pend_blk(T, O, J.ppend);
         if (!J.pfirst) {  // read-modify-write of the parent's pending slot: all loads first
           double oH[27];
 #pragma unroll
-          for (int c = 0; c < 27; ++c) oH[c] = ld(S.pendH, r0 + c, cap, s);
+          for (int c = 0; c < 27; ++c) oH[c] = ld(Pp, PR_H + c);
 #pragma unroll
           for (int c = 0; c < 6; ++c) { cA[c] += oH[c]; cD[c] += oH[15 + c]; cp[c] += oH[21 + c]; }
 #pragma unroll
           for (int c = 0; c < 9; ++c) cB[c] += oH[6 + c];
         }
 #pragma unroll
-        for (int c = 0; c < 6; ++c) { st(S.pendH, r0 + c, cap, s, cA[c]); st(S.pendH, r0 + 15 + c, cap, s, cD[c]); st(S.pendH, r0 + 21 + c, cap, s, cp[c]); }
+        for (int c = 0; c < 6; ++c) { st(Pp, PR_H + c, cA[c]); st(Pp, PR_H + 15 + c, cD[c]); st(Pp, PR_H + 21 + c, cp[c]); }
 #pragma unroll
-        for (int c = 0; c < 9; ++c) st(S.pendH, r0 + 6 + c, cap, s, cB[c]);
+        for (int c = 0; c < 9; ++c) st(Pp, PR_H + 6 + c, cB[c]);
       }
     }
   }
@@ -393,8 +417,9 @@ LOIK_DEV void sweep_backward(const StateP& S, const int s, const double mu, cons
 // DualUpdate (:404-461) + ComputePrimalResiduals (:494-503), joint by joint, root to leaves.
 // ---------------------------------------------------------------------------------------------
 template <bool DEBUG>
-LOIK_DEV void sweep_forward(const StateP& S, const int s, const double mu, const double mu_eq, Carry& cy) {
-  const int cap = S.cap, nb = c_model.nb;
+LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const double mu, const double mu_eq, Carry& cy) {
+  const Offs& O = c_model.off;
+  const int nb = c_model.nb;
   cy.nu_inf = cy.dfis_inf = cy.dvis_inf = cy.dnu_inf = cy.dz_inf = cy.dyis_inf = cy.dw_inf = cy.Av_inf = 0.0;
   cy.bTdy_p = cy.bTdy_m = cy.ubdw_p = cy.lbdw_m = cy.pres_task = cy.pres_slack = 0.0;
   const double inv_mu = 1.0 / mu;
@@ -402,14 +427,15 @@ LOIK_DEV void sweep_forward(const StateP& S, const int s, const double mu, const
   for (int i = 1; i <= nb; ++i) {
     const JointC& J = c_model.j[i];
     const int ji = i - 1;
+    double* Pj = joint_blk(T, O, ji);
     // ---- load phase A: what nu_i, v_i and the dof update need
     double vin[6], UD[6], vold[6];
-    const double qa = ldc(S.jq, 2 * ji, cap, s), qb = ldc(S.jq, 2 * ji + 1, cap, s);
-    const double Dinv = ld(S.Dinv, ji, cap, s), ri = ld(S.r, ji, cap, s);
-    const double w_old = ld(S.w, ji, cap, s), nu_old = ld(S.nu, ji, cap, s), z_old = ld(S.z, ji, cap, s);
-    const double lb = S.lbv ? ldc(S.lbv, ji, cap, s) : J.lb, ub = S.ubv ? ldc(S.ubv, ji, cap, s) : J.ub;
+    const double qa = ldc(Pj, JR_JQ), qb = ldc(Pj, JR_JQ + 1);
+    const double Dinv = ld(Pj, JR_DINV), ri = ld(Pj, JR_R);
+    const double w_old = ld(Pj, JR_W), nu_old = ld(Pj, JR_NU), z_old = ld(Pj, JR_Z);
+    const double lb = c_model.bounds_per_instance ? ldc(Pj, JR_LB) : J.lb, ub = c_model.bounds_per_instance ? ldc(Pj, JR_UB) : J.ub;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { UD[c] = ld(S.UDinv, 6 * ji + c, cap, s); vold[c] = ld(S.v, 6 * ji + c, cap, s); }
+    for (int c = 0; c < 6; ++c) { UD[c] = ld(Pj, JR_UD + c); vold[c] = ld(Pj, JR_V + c); }
     if (J.parent == 0) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) vin[c] = 0.0;
@@ -417,8 +443,9 @@ LOIK_DEV void sweep_forward(const StateP& S, const int s, const double mu, const
 #pragma unroll
       for (int c = 0; c < 6; ++c) vin[c] = vprev[c];
     } else {
+      const double* Pq = joint_blk(T, O, J.parent - 1);
 #pragma unroll
-      for (int c = 0; c < 6; ++c) vin[c] = ld(S.v, 6 * (J.parent - 1) + c, cap, s);
+      for (int c = 0; c < 6; ++c) vin[c] = ld(Pq, JR_V + c);
     }
     // ---- maths A
     double R[9], t[3], v[6];
@@ -452,11 +479,11 @@ LOIK_DEV void sweep_forward(const StateP& S, const int s, const double mu, const
       double fold[6], p[6], A[6], B[9], D[6], f[6];
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
-        fold[c] = ld(S.f, 6 * ji + c, cap, s); p[c] = ld(S.p, 6 * ji + c, cap, s);
-        A[c] = ld(S.H, 21 * ji + c, cap, s); D[c] = ld(S.H, 21 * ji + 15 + c, cap, s);
+        fold[c] = ld(Pj, JR_F + c); p[c] = ld(Pj, JR_P + c);
+        A[c] = ld(Pj, JR_H + c); D[c] = ld(Pj, JR_H + 15 + c);
       }
 #pragma unroll
-      for (int c = 0; c < 9; ++c) B[c] = ld(S.H, 21 * ji + 6 + c, cap, s);
+      for (int c = 0; c < 9; ++c) B[c] = ld(Pj, JR_H + 6 + c);
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         f[a] = A[si(a, 0)] * v[0] + A[si(a, 1)] * v[1] + A[si(a, 2)] * v[2] + B[3 * a] * v[3] + B[3 * a + 1] * v[4] + B[3 * a + 2] * v[5] + p[a];
@@ -466,18 +493,18 @@ LOIK_DEV void sweep_forward(const StateP& S, const int s, const double mu, const
       for (int c = 0; c < 6; ++c) cy.dfis_inf = amax(cy.dfis_inf, f[c] - fold[c]);
       // ---- store phase
 #pragma unroll
-      for (int c = 0; c < 6; ++c) { st(S.v, 6 * ji + c, cap, s, v[c]); st(S.f, 6 * ji + c, cap, s, f[c]); }
+      for (int c = 0; c < 6; ++c) { st(Pj, JR_V + c, v[c]); st(Pj, JR_F + c, f[c]); }
     }
-    st(S.nu, ji, cap, s, nu);
-    st(S.z, ji, cap, s, z);
-    st(S.w, ji, cap, s, w_old + dw);
-    if (DEBUG) st(S.prv, 6 * nb + ji, cap, s, rp);
+    st(Pj, JR_NU, nu);
+    st(Pj, JR_Z, z);
+    st(Pj, JR_W, w_old + dw);
+    if (DEBUG) st(T, O.prv + 6 * nb + ji, rp);
     if (J.task >= 0) {  // DualUpdate for the task on this joint (:410-451)
-      const int k = J.task;
-      const TaskC& K = c_model.t[k];
+      const TaskC& K = c_model.t[J.task];
+      double* Pk = task_blk(T, O, J.task);
       double y[6], bk[6], yk[6];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) { bk[c] = ldc(S.b, 6 * k + c, cap, s); yk[c] = ld(S.y, 6 * k + c, cap, s); }
+      for (int c = 0; c < 6; ++c) { bk[c] = ldc(Pk, TR_B + c); yk[c] = ld(Pk, TR_Y + c); }
       double plus = 0.0, minus = 0.0;
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
@@ -490,15 +517,15 @@ LOIK_DEV void sweep_forward(const StateP& S, const int s, const double mu, const
         cy.pres_task = amax(cy.pres_task, e);
         plus += bk[a] * fmax(dy, 0.0);
         minus += bk[a] * fmin(dy, 0.0);
-        if (DEBUG) st(S.prv, 6 * ji + a, cap, s, e);
+        if (DEBUG) st(T, O.prv + 6 * ji + a, e);
       }
       cy.bTdy_p += plus;
       cy.bTdy_m += minus;
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
-        st(S.y, 6 * k + a, cap, s, y[a]);
+        st(Pk, TR_Y + a, y[a]);
         // Aty = A^T y (:425)
-        st(S.Aty, 6 * k + a, cap, s, K.A[a] * y[0] + K.A[6 + a] * y[1] + K.A[12 + a] * y[2] + K.A[18 + a] * y[3] + K.A[24 + a] * y[4] + K.A[30 + a] * y[5]);
+        st(Pk, TR_ATY + a, K.A[a] * y[0] + K.A[6 + a] * y[1] + K.A[12 + a] * y[2] + K.A[18 + a] * y[3] + K.A[24 + a] * y[4] + K.A[30 + a] * y[5]);
       }
     }
   }
@@ -514,41 +541,36 @@ struct Resid {
 // set F_c = Aty" choreography (:364,:370,:438-439) reduces to: F_old is what is in memory, F_new is rebuilt.
 // ---------------------------------------------------------------------------------------------
 template <bool DEBUG>
-LOIK_DEV void sweep_residual(const StateP& S, const int s, Resid& rs) {
-  const int cap = S.cap, nb = c_model.nb;
+LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resid& rs) {
+  const Offs& O = c_model.off;
+  const int nb = c_model.nb;
   rs.dres_v = rs.dres_nu = rs.Hrefv_inf = rs.F_inf = rs.T_inf = rs.dF_inf = rs.dT_inf = 0.0;
   double cF[6];
   bool have_carry = false;
   for (int i = nb; i >= 1; --i) {
     const JointC& J = c_model.j[i];
     const int ji = i - 1;
+    double* Pj = joint_blk(T, O, ji);
     // ---- load phase
-    double f[6], F[6], v[6], Fold[6], pF[6], oF[6];
-    const double w_i = ld(S.w, ji, cap, s), T_old = ld(S.T, ji, cap, s);
-    const double qa = ldc(S.jq, 2 * ji, cap, s), qb = ldc(S.jq, 2 * ji + 1, cap, s);
+    double f[6], F[6], v[6], Fold[6];
+    const double w_i = ld(Pj, JR_W), T_old = ld(Pj, JR_T);
+    const double qa = ldc(Pj, JR_JQ), qb = ldc(Pj, JR_JQ + 1);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { f[c] = ld(S.f, 6 * ji + c, cap, s); v[c] = ld(S.v, 6 * ji + c, cap, s); Fold[c] = ld(S.F, 6 * ji + c, cap, s); }
+    for (int c = 0; c < 6; ++c) { f[c] = ld(Pj, JR_F + c); v[c] = ld(Pj, JR_V + c); Fold[c] = ld(Pj, JR_FD + c); }
     if (J.task >= 0) {
+      const double* Pk = task_blk(T, O, J.task);
 #pragma unroll
-      for (int c = 0; c < 6; ++c) F[c] = ld(S.Aty, 6 * J.task + c, cap, s);  // (:438-439)
+      for (int c = 0; c < 6; ++c) F[c] = ld(Pk, TR_ATY + c);  // (:438-439)
     } else {
 #pragma unroll
       for (int c = 0; c < 6; ++c) F[c] = 0.0;  // (:370)
     }
     if (J.pend >= 0) {
+      const double* Pp = pend_blk(T, O, J.pend);
 #pragma unroll
-      for (int c = 0; c < 6; ++c) pF[c] = ld(S.pendF, 6 * J.pend + c, cap, s);
-    }
-    const bool rmw = J.parent > 0 && !J.carry && !J.pfirst;
-    if (rmw) {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) oF[c] = ld(S.pendF, 6 * J.ppend + c, cap, s);
+      for (int c = 0; c < 6; ++c) F[c] += ld(Pp, PR_F + c);
     }
     // ---- maths
-    if (J.pend >= 0) {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) F[c] += pF[c];
-    }
     if (have_carry) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) F[c] += cF[c];
@@ -571,17 +593,17 @@ LOIK_DEV void sweep_residual(const StateP& S, const int s, Resid& rs) {
       rs.dres_v = amax(rs.dres_v, rd[c]);
     }
     // Stf_plus_w (:231-236) and its delta (:471,:482-483)
-    const double T = St_dot(J, f) + w_i;
-    rs.T_inf = amax(rs.T_inf, T);
-    rs.dT_inf = amax(rs.dT_inf, T - T_old);
+    const double Tn = St_dot(J, f) + w_i;
+    rs.T_inf = amax(rs.T_inf, Tn);
+    rs.dT_inf = amax(rs.dT_inf, Tn - T_old);
     // ---- store phase
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      st(S.F, 6 * ji + c, cap, s, F[c]);
-      if (DEBUG) st(S.drv, 6 * ji + c, cap, s, rd[c]);
+      st(Pj, JR_FD + c, F[c]);
+      if (DEBUG) st(T, O.drv + 6 * ji + c, rd[c]);
     }
-    st(S.T, ji, cap, s, T);
-    if (DEBUG) st(S.drv, 6 * nb + ji, cap, s, T);
+    st(Pj, JR_T, Tn);
+    if (DEBUG) st(T, O.drv + 6 * nb + ji, Tn);
     have_carry = false;
     if (J.parent > 0) {  // fis_diff_plus_Aty[parent] += liMi.act(f_i) (:212)
       double R[9], t[3];
@@ -590,40 +612,45 @@ LOIK_DEV void sweep_residual(const StateP& S, const int s, Resid& rs) {
       if (J.carry) {
         have_carry = true;
       } else {
-        if (rmw) {
+        double* Pp = pend_blk(T, O, J.ppend);
+        if (!J.pfirst) {
+          double oF[6];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) oF[c] = ld(Pp, PR_F + c);
 #pragma unroll
           for (int c = 0; c < 6; ++c) cF[c] += oF[c];
         }
 #pragma unroll
-        for (int c = 0; c < 6; ++c) st(S.pendF, 6 * J.ppend + c, cap, s, cF[c]);
+        for (int c = 0; c < 6; ++c) st(Pp, PR_F + c, cF[c]);
       }
     }
   }
   rs.dres_nu = rs.T_inf;  // dual_residual_vec[6nb:] = Stf_plus_w (:484)
 }
+
 // ---------------------------------------------------------------------------------------------
 // CheckConvergence (hxx:540-565) + CheckFeasibility (:572-606) + UpdateMu (:613-641) + the loop control
 // of Solve() (hpp:377-454) and InfeasibilityTailSolve() (hpp:271-319), per instance.
 // `fixed`: stopping disabled (throughput mode).  Returns the new status; updates mu.
 // ---------------------------------------------------------------------------------------------
 template <bool DEBUG>
-LOIK_DEV int decide(const StateP& S, const int s, const int status, const int it, const bool fixed, const Carry& cy,
+LOIK_DEV int decide(const ModelC& c_model, double* __restrict__ T, const int status, const int it, const bool fixed, const Carry& cy,
                     const Resid& rs, double& mu) {
-  const int cap = S.cap;
   const ModelC& M = c_model;
+  double* G = glob_blk(T, M.off);
   const double pres = fmax(cy.pres_task, cy.pres_slack);  // (:498)
   const double dres = fmax(rs.dres_v, rs.dres_nu);        // (:517)
-  st(S.res, 0, cap, s, pres);
-  st(S.res, 1, cap, s, dres);
+  st(G, GR_RES + 0, pres);
+  st(G, GR_RES + 1, dres);
   int ns = status;
   double dyqp = 0.0, ATdy = 0.0, ubp = 0.0, lbm = 0.0, c1 = 0.0, c2 = 0.0;
   double dx = fmax(cy.dvis_inf, cy.dnu_inf);
   if (status == ST_RUNNING) {
-    const double binf = ld(S.binf, 0, cap, s);
+    const double binf = ld(G, GR_BINF);
     const double tol_p = M.tol_abs + M.tol_rel * fmax(fmax(cy.Av_inf, cy.nu_inf), fmax(binf, cy.nu_inf));            // (:544-546)
     const double tol_d = M.tol_abs + M.tol_rel * fmax(fmax(rs.Hrefv_inf, fmax(rs.F_inf, rs.T_inf)), M.Hv_inf);      // (:548-552)
-    st(S.res, 2, cap, s, tol_p);
-    st(S.res, 3, cap, s, tol_d);
+    st(G, GR_RES + 2, tol_p);
+    st(G, GR_RES + 3, tol_d);
     const bool converged = (pres < tol_p) && (dres < tol_d);                                                        // (:555)
     bool infeasible = false;
     if (it > 1) {                                                                                                   // (hpp:425-427)
@@ -653,17 +680,17 @@ LOIK_DEV int decide(const StateP& S, const int s, const int status, const int it
     else ns = ST_INFEASIBLE_DONE;
   }
   if (DEBUG) {
-    double* N = S.norms;
-    st(N, 0, cap, s, cy.bTdy_p); st(N, 1, cap, s, cy.bTdy_m); st(N, 2, cap, s, cy.Av_inf); st(N, 3, cap, s, cy.nu_inf);
-    st(N, 4, cap, s, rs.Hrefv_inf); st(N, 5, cap, s, rs.F_inf); st(N, 6, cap, s, rs.T_inf); st(N, 7, cap, s, rs.dF_inf);
-    st(N, 8, cap, s, rs.dT_inf); st(N, 9, cap, s, cy.dvis_inf); st(N, 10, cap, s, cy.dnu_inf); st(N, 11, cap, s, cy.dz_inf);
-    st(N, 12, cap, s, cy.dfis_inf); st(N, 13, cap, s, cy.dyis_inf); st(N, 14, cap, s, cy.dw_inf);
-    st(N, 15, cap, s, cy.pres_task); st(N, 16, cap, s, cy.pres_slack); st(N, 17, cap, s, rs.dres_v); st(N, 18, cap, s, rs.dres_nu);
+    const int N = GR_NORMS;
+    st(G, N + 0, cy.bTdy_p); st(G, N + 1, cy.bTdy_m); st(G, N + 2, cy.Av_inf); st(G, N + 3, cy.nu_inf);
+    st(G, N + 4, rs.Hrefv_inf); st(G, N + 5, rs.F_inf); st(G, N + 6, rs.T_inf); st(G, N + 7, rs.dF_inf);
+    st(G, N + 8, rs.dT_inf); st(G, N + 9, cy.dvis_inf); st(G, N + 10, cy.dnu_inf); st(G, N + 11, cy.dz_inf);
+    st(G, N + 12, cy.dfis_inf); st(G, N + 13, cy.dyis_inf); st(G, N + 14, cy.dw_inf);
+    st(G, N + 15, cy.pres_task); st(G, N + 16, cy.pres_slack); st(G, N + 17, rs.dres_v); st(G, N + 18, rs.dres_nu);
     if (status == ST_RUNNING && it > 1) {
-      st(N, 19, cap, s, dyqp); st(N, 20, cap, s, ATdy); st(N, 21, cap, s, ubp); st(N, 22, cap, s, lbm);
-      st(N, 23, cap, s, c1); st(N, 24, cap, s, c2);
+      st(G, N + 19, dyqp); st(G, N + 20, ATdy); st(G, N + 21, ubp); st(G, N + 22, lbm);
+      st(G, N + 23, c1); st(G, N + 24, c2);
     }
-    if (status == ST_TAIL || it > 1) st(N, 25, cap, s, dx);
+    if (status == ST_TAIL || it > 1) st(G, N + 25, dx);
   }
   return ns;
 }

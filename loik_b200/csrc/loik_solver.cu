@@ -17,129 +17,197 @@
 
 namespace loik {
 
-
-constexpr int kBlock = 128;
+constexpr int kBlock = 64;  // threads per CTA of the sweep kernels (2 warps = 2 tiles)
 
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
 
+LOIK_DEV int2 ld_ctl(const ModelC& c_model, const double* T) { return *reinterpret_cast<const int2*>(T + (size_t)(c_model.off.glob + GR_CTL) * 32); }
+LOIK_DEV void st_ctl(const ModelC& c_model, double* T, int status, int iter) { *reinterpret_cast<int2*>(T + (size_t)(c_model.off.glob + GR_CTL) * 32) = make_int2(status, iter); }
+
 // One launch = up to `iters` ADMM iterations of every active instance (all three sweeps + decisions
 // fused; instances are independent so no grid-wide synchronisation is needed between iterations).
+// Dense mode: thread k = slot k.  List mode: thread k = slot list[k] for k < *n_list (compacted
+// still-active instances; the grid is sized for the worst case and surplus CTAs exit at once).
 template <bool DEBUG, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) k_iterate(const StateP S, const int iters, const int fixed) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kBlock, MINB) k_iterate(const StateP S, const int slot, const int iters, const int fixed) {
+  const ModelC& c_model = c_models[slot];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  int s = -1;
+  if (S.list) {
+    if (k < *S.n_list) s = S.list[k];
+  } else if (k < S.n) {
+    s = k;
+  }
   bool active = false;
-  if (s < S.n) {
-    int status = S.status[s];
+  if (s >= 0) {
+    double* T = tile_ptr(S, c_model, s);
+    const int2 ctl = ld_ctl(c_model, T);
+    int status = ctl.x;
     if (status < ST_CONVERGED) {
-      int it = S.iter[s];
-      double mu = S.mu[s];
-      for (int k = 0; k < iters; ++k) {
+      int it = ctl.y;
+      double mu = ld(glob_blk(T, c_model.off), GR_MU);
+      for (int n = 0; n < iters; ++n) {
         ++it;
         const double mu_eq = c_model.mu_scale * mu;
-        sweep_backward(S, s, mu, mu_eq);
+        sweep_backward(c_model, T, mu, mu_eq);
         Carry cy;
-        sweep_forward<DEBUG>(S, s, mu, mu_eq, cy);
+        sweep_forward<DEBUG>(c_model, T, mu, mu_eq, cy);
         Resid rs;
-        sweep_residual<DEBUG>(S, s, rs);
-        status = decide<DEBUG>(S, s, status, it, fixed != 0, cy, rs, mu);
+        sweep_residual<DEBUG>(c_model, T, rs);
+        status = decide<DEBUG>(c_model, T, status, it, fixed != 0, cy, rs, mu);
         if (status >= ST_CONVERGED) break;
       }
-      S.status[s] = status;
-      S.iter[s] = it;
-      S.mu[s] = mu;
+      st_ctl(c_model, T, status, it);
+      st(glob_blk(T, c_model.off), GR_MU, mu);
       active = status < ST_CONVERGED;
     }
   }
-  const unsigned m = __ballot_sync(0xffffffffu, active);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(S.n_active, __popc(m));
+  if (S.n_active) {
+    const unsigned m = __ballot_sync(0xffffffffu, active);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(S.n_active, __popc(m));
+  }
 }
 
-// Step-by-step interface: the same sweeps, one per launch, scalars handed over through S.carry.
-__global__ void __launch_bounds__(kBlock) k_step_backward(const StateP S) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= S.n || S.status[s] >= ST_CONVERGED) return;
-  const double mu = S.mu[s];
-  sweep_backward(S, s, mu, c_model.mu_scale * mu);
+// Compaction: append the slots that are still active to list_out (order inside a CTA is preserved so
+// neighbouring instances stay neighbours).  Input is the previous list, or all slots when list_in == nullptr.
+__global__ void __launch_bounds__(256) k_compact(const StateP S, const int slot, const int* __restrict__ list_in, const int* __restrict__ n_in,
+                                                 int* __restrict__ list_out, int* __restrict__ n_out) {
+  const ModelC& c_model = c_models[slot];
+  __shared__ int warp_cnt[8];
+  __shared__ int block_base;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int limit = list_in ? *n_in : S.n;
+  int s = -1;
+  if (k < limit) s = list_in ? list_in[k] : k;
+  bool active = false;
+  if (s >= 0) active = ld_ctl(c_model, tile_ptr(S, c_model, s)).x < ST_CONVERGED;
+  const unsigned m = __ballot_sync(0xffffffffu, active);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) warp_cnt[wid] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) { const int c = warp_cnt[w]; warp_cnt[w] = tot; tot += c; }
+    block_base = tot ? atomicAdd(n_out, tot) : 0;
+  }
+  __syncthreads();
+  if (active) list_out[block_base + warp_cnt[wid] + __popc(m & ((1u << lane) - 1))] = s;
 }
-__global__ void __launch_bounds__(kBlock) k_step_forward(const StateP S) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= S.n || S.status[s] >= ST_CONVERGED) return;
-  const double mu = S.mu[s];
-  Carry cy;
-  sweep_forward<true>(S, s, mu, c_model.mu_scale * mu, cy);
-  const double* c = reinterpret_cast<const double*>(&cy);
-  for (int k = 0; k < kCarryRows; ++k) st(S.carry, k, S.cap, s, c[k]);
-  // ComputePrimalResiduals (hxx:494-503)
-  st(S.res, 0, S.cap, s, fmax(cy.pres_task, cy.pres_slack));
-  st(S.norms, 15, S.cap, s, cy.pres_task);
-  st(S.norms, 16, S.cap, s, cy.pres_slack);
-}
-__global__ void __launch_bounds__(kBlock) k_step_residual(const StateP S, const int fixed) {
+
+// Step-by-step interface: the same sweeps, one per launch, scalars handed over through the carry rows.
+__global__ void __launch_bounds__(kBlock) k_step_backward(const StateP S, const int slot) {
+  const ModelC& c_model = c_models[slot];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
-  int status = S.status[s];
+  double* T = tile_ptr(S, c_model, s);
+  if (ld_ctl(c_model, T).x >= ST_CONVERGED) return;
+  const double mu = ld(glob_blk(T, c_model.off), GR_MU);
+  sweep_backward(c_model, T, mu, c_model.mu_scale * mu);
+}
+__global__ void __launch_bounds__(kBlock) k_step_forward(const StateP S, const int slot) {
+  const ModelC& c_model = c_models[slot];
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S.n) return;
+  double* T = tile_ptr(S, c_model, s);
+  if (ld_ctl(c_model, T).x >= ST_CONVERGED) return;
+  double* G = glob_blk(T, c_model.off);
+  const double mu = ld(G, GR_MU);
+  Carry cy;
+  sweep_forward<true>(c_model, T, mu, c_model.mu_scale * mu, cy);
+  const double* c = reinterpret_cast<const double*>(&cy);
+  for (int k = 0; k < kCarryRows; ++k) st(G, GR_CARRY + k, c[k]);
+  // ComputePrimalResiduals (hxx:494-503)
+  st(G, GR_RES + 0, fmax(cy.pres_task, cy.pres_slack));
+  st(G, GR_NORMS + 15, cy.pres_task);
+  st(G, GR_NORMS + 16, cy.pres_slack);
+}
+__global__ void __launch_bounds__(kBlock) k_step_residual(const StateP S, const int slot, const int fixed) {
+  const ModelC& c_model = c_models[slot];
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S.n) return;
+  double* T = tile_ptr(S, c_model, s);
+  const int2 ctl = ld_ctl(c_model, T);
+  int status = ctl.x;
   if (status >= ST_CONVERGED) return;
+  double* G = glob_blk(T, c_model.off);
   Carry cy;
   double* c = reinterpret_cast<double*>(&cy);
-  for (int k = 0; k < kCarryRows; ++k) c[k] = ld(S.carry, k, S.cap, s);
+  for (int k = 0; k < kCarryRows; ++k) c[k] = ld(G, GR_CARRY + k);
   Resid rs;
-  sweep_residual<true>(S, s, rs);
-  double mu = S.mu[s];
-  const int it = S.iter[s] + 1;
-  status = decide<true>(S, s, status, it, fixed != 0, cy, rs, mu);
-  S.status[s] = status;
-  S.iter[s] = it;
-  S.mu[s] = mu;
+  sweep_residual<true>(c_model, T, rs);
+  double mu = ld(G, GR_MU);
+  const int it = ctl.y + 1;
+  status = decide<true>(c_model, T, status, it, fixed != 0, cy, rs, mu);
+  st_ctl(c_model, T, status, it);
+  st(G, GR_MU, mu);
 }
 
 enum : int { RST_WZ = 1, RST_NU = 2, RST_VFF = 4, RST_YATY = 8, RST_SOLVER = 16 };
 
 // ik_id_data_.Reset / ResetRecursion (data hxx:114-154) + ResetSolver (hpp:168-186)
-__global__ void k_reset(const StateP S, const int flags) {
+__global__ void k_reset(const StateP S, const int slot, const int flags) {
+  const ModelC& c_model = c_models[slot];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
-  const int cap = S.cap, nb = c_model.nb, nc = c_model.nc;
-  if (flags & RST_WZ)
-    for (int r = 0; r < nb; ++r) { st(S.w, r, cap, s, 0.0); st(S.z, r, cap, s, 0.0); }
-  if (flags & RST_NU)
-    for (int r = 0; r < nb; ++r) st(S.nu, r, cap, s, 0.0);
-  if (flags & RST_VFF)
-    for (int r = 0; r < 6 * nb; ++r) { st(S.v, r, cap, s, 0.0); st(S.f, r, cap, s, 0.0); st(S.F, r, cap, s, 0.0); }
+  double* T = tile_ptr(S, c_model, s);
+  const Offs& O = c_model.off;
+  const int nb = c_model.nb, nc = c_model.nc;
+  for (int j = 0; j < nb; ++j) {
+    double* Pj = joint_blk(T, O, j);
+    if (flags & RST_WZ) { st(Pj, JR_W, 0.0); st(Pj, JR_Z, 0.0); }
+    if (flags & RST_NU) st(Pj, JR_NU, 0.0);
+    if (flags & RST_VFF)
+      for (int c = 0; c < 6; ++c) { st(Pj, JR_V + c, 0.0); st(Pj, JR_F + c, 0.0); st(Pj, JR_FD + c, 0.0); }
+  }
   if (flags & RST_YATY)
-    for (int r = 0; r < 6 * nc; ++r) { st(S.y, r, cap, s, 0.0); st(S.Aty, r, cap, s, 0.0); }
+    for (int k = 0; k < nc; ++k) {
+      double* Pk = task_blk(T, O, k);
+      for (int c = 0; c < 6; ++c) { st(Pk, TR_Y + c, 0.0); st(Pk, TR_ATY + c, 0.0); }
+    }
   if (flags & RST_SOLVER) {
-    S.status[s] = ST_RUNNING;
-    S.iter[s] = 0;
-    S.mu[s] = c_model.mu0;
+    st_ctl(c_model, T, ST_RUNNING, 0);
+    st(glob_blk(T, O), GR_MU, c_model.mu0);
   }
 }
 
 // FwdPassInit (hxx:253-283): the q-dependent part of liMi, kept as (sin q, cos q) / (q, 0) per joint.
-// q is batch-major [n][nq].
-__global__ void k_set_q(const StateP S, const double* __restrict__ q) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= S.n) return;
+// q is batch-major [n][nq]; it is staged through shared memory so both the read and the write coalesce.
+__global__ void __launch_bounds__(kBlock) k_set_q(const StateP S, const int slot, const double* __restrict__ q) {
+  const ModelC& c_model = c_models[slot];
+  extern __shared__ double sh[];
   const int nb = c_model.nb;
+  const int s0 = blockIdx.x * blockDim.x;
+  const int cnt = min((int)blockDim.x, S.n - s0);
+  for (int e = threadIdx.x; e < cnt * nb; e += blockDim.x) sh[e] = q[(size_t)s0 * nb + e];
+  __syncthreads();
+  const int s = s0 + threadIdx.x;
+  if (s >= S.n) return;
+  double* T = tile_ptr(S, c_model, s);
   for (int i = 1; i <= nb; ++i) {
     const int jt = c_model.j[i].jtype;
-    const double qi = q[(size_t)s * nb + (i - 1)];
+    const double qi = sh[threadIdx.x * nb + (i - 1)];
     double a, b;
     if (jt <= 2 || jt == 6) sincos(qi, &a, &b);
     else { a = qi; b = 0.0; }
-    st(S.jq, 2 * (i - 1), S.cap, s, a);
-    st(S.jq, 2 * (i - 1) + 1, S.cap, s, b);
+    double* Pj = joint_blk(T, c_model.off, i - 1);
+    st(Pj, JR_JQ, a);
+    st(Pj, JR_JQ + 1, b);
   }
 }
 
 // UpdateEqConstraints (ik-id-description-optimized.hpp:127-171), per-instance part: b, Atb = A^T b, |b|inf.
 // task < 0: all tasks, bis_inf_norm reset; task >= 0: UpdateEqConstraint for that slot (:178-218), norm only grows.
-__global__ void k_set_b(const StateP S, const double* __restrict__ b, const int per_instance, const int task) {
+__global__ void k_set_b(const StateP S, const int slot, const double* __restrict__ b, const int per_instance, const int task) {
+  const ModelC& c_model = c_models[slot];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
-  const int nc = c_model.nc, cap = S.cap;
-  double binf = task < 0 ? 0.0 : ld(S.binf, 0, cap, s);
+  double* T = tile_ptr(S, c_model, s);
+  const Offs& O = c_model.off;
+  const int nc = c_model.nc;
+  double* G = glob_blk(T, O);
+  double binf = task < 0 ? 0.0 : ld(G, GR_BINF);
   const int k0 = task < 0 ? 0 : task, k1 = task < 0 ? nc : task + 1;
   for (int k = k0; k < k1; ++k) {
     double bk[6];
@@ -147,61 +215,72 @@ __global__ void k_set_b(const StateP S, const double* __restrict__ b, const int 
       const size_t src = task < 0 ? (per_instance ? ((size_t)s * nc + k) * 6 + a : (size_t)k * 6 + a)
                                   : (per_instance ? (size_t)s * 6 + a : (size_t)a);
       bk[a] = b[src];
-      st(S.b, 6 * k + a, cap, s, bk[a]);
+      st(task_blk(T, O, k), TR_B + a, bk[a]);
       binf = fmax(binf, fabs(bk[a]));
     }
     const double* A = c_model.t[k].A;
     for (int a = 0; a < 6; ++a) {
       double acc = 0.0;
       for (int r = 0; r < 6; ++r) acc += A[6 * r + a] * bk[r];
-      st(S.Atb, 6 * k + a, cap, s, acc);
+      st(task_blk(T, O, k), TR_ATB + a, acc);
     }
   }
-  st(S.binf, 0, cap, s, binf);
+  st(G, GR_BINF, binf);
 }
 
-__global__ void k_set_bounds(const StateP S, const double* __restrict__ lb, const double* __restrict__ ub) {
+__global__ void k_set_bounds(const StateP S, const int slot, const double* __restrict__ lb, const double* __restrict__ ub) {
+  const ModelC& c_model = c_models[slot];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
+  double* T = tile_ptr(S, c_model, s);
   const int nb = c_model.nb;
   for (int r = 0; r < nb; ++r) {
-    st(S.lbv, r, S.cap, s, lb[(size_t)s * nb + r]);
-    st(S.ubv, r, S.cap, s, ub[(size_t)s * nb + r]);
+    double* Pj = joint_blk(T, c_model.off, r);
+    st(Pj, JR_LB, lb[(size_t)s * nb + r]);
+    st(Pj, JR_UB, ub[(size_t)s * nb + r]);
   }
 }
 
-// batch-major gather of `rows` SoA rows: dst[s][k] = src[map ? map[k] : k][s]
-__global__ void k_gather(const double* __restrict__ src, const int cap, const int n, const int rows,
-                         const int* __restrict__ map, double* __restrict__ dst) {
+// batch-major gather of `nrows` rows: dst[s][k] = tile(s)[map[k]][lane(s)]  (map = absolute row indices).
+__global__ void __launch_bounds__(256) k_gather(const StateP S, const int slot, const int nrows, const int* __restrict__ map,
+                                                double* __restrict__ dst) {
+  const ModelC& c_model = c_models[slot];
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)n * rows) return;
-  const int s = (int)(idx / rows), k = (int)(idx % rows);
-  const int r = map ? map[k] : k;
-  dst[idx] = r < 0 ? 0.0 : src[(size_t)r * cap + s];
+  if (idx >= (size_t)S.n * nrows) return;
+  const int s = (int)(idx / nrows), k = (int)(idx % nrows);
+  dst[idx] = tile_ptr(S, c_model, s)[(size_t)map[k] * 32];
 }
-__global__ void k_gather_limi(const StateP S, double* __restrict__ dst) {
+__global__ void k_gather_limi(const StateP S, const int slot, double* __restrict__ dst) {
+  const ModelC& c_model = c_models[slot];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
+  const double* T = tile_ptr(S, c_model, s);
   const int nb = c_model.nb;
   for (int i = 1; i <= nb; ++i) {
     double R[9], t[3];
-    make_xf(c_model.j[i], ld(S.jq, 2 * (i - 1), S.cap, s), ld(S.jq, 2 * (i - 1) + 1, S.cap, s), R, t);
+    const double* Pj = joint_blk(const_cast<double*>(T), c_model.off, i - 1);
+    make_xf(c_model.j[i], ld(Pj, JR_JQ), ld(Pj, JR_JQ + 1), R, t);
     double* o = dst + ((size_t)s * nb + (i - 1)) * 12;
     for (int c = 0; c < 9; ++c) o[c] = R[c];
     for (int c = 0; c < 3; ++c) o[9 + c] = t[c];
   }
 }
-__global__ void k_status_flags(const StateP S, int* __restrict__ dst) {
+// which: 0 = iteration count, 1 = status flags (bit0 converged, bit1 primal infeasible, bit2 max_iter)
+__global__ void k_gather_ctl(const StateP S, const int slot, const int which, int* __restrict__ dst) {
+  const ModelC& c_model = c_models[slot];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
-  const int stt = S.status[s];
-  dst[s] = (stt == ST_CONVERGED ? 1 : 0) | ((stt == ST_TAIL || stt == ST_INFEASIBLE_DONE) ? 2 : 0) | (stt == ST_MAXITER ? 4 : 0);
+  const int2 c = ld_ctl(c_model, tile_ptr(S, c_model, s));
+  const int stt = c.x;
+  dst[s] = which == 0 ? c.y
+                      : ((stt == ST_CONVERGED ? 1 : 0) | ((stt == ST_TAIL || stt == ST_INFEASIBLE_DONE) ? 2 : 0) | (stt == ST_MAXITER ? 4 : 0));
 }
 // out[0..2] = #converged, #infeasible, #maxiter; out[3] = sum iters
-__global__ void k_stats(const StateP S, unsigned long long* __restrict__ out) {
+__global__ void k_stats(const StateP S, const int slot, unsigned long long* __restrict__ out) {
+  const ModelC& c_model = c_models[slot];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   int stt = -1, it = 0;
-  if (s < S.n) { stt = S.status[s]; it = S.iter[s]; }
+  if (s < S.n) { const int2 c = ld_ctl(c_model, tile_ptr(S, c_model, s)); stt = c.x; it = c.y; }
   const unsigned c = __ballot_sync(0xffffffffu, stt == ST_CONVERGED);
   const unsigned f = __ballot_sync(0xffffffffu, stt == ST_TAIL || stt == ST_INFEASIBLE_DONE);
   const unsigned m = __ballot_sync(0xffffffffu, stt == ST_MAXITER);
@@ -234,65 +313,66 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 struct loik_solver {
-  int device = 0, batch = 0, cap = 0;
+  int device = 0, batch = 0, ntiles = 0;
   int nj = 0, nb = 0, nc = 0, npend = 0;
   loik_params prm{};
-  ModelC mc{};          // host copy of the constant block
-  bool const_dirty = true;
+  ModelC mc{};          // host copy of this solver's constant block
+  ModelC mc_uploaded{}; // what was last written to the constant slot
+  bool uploaded_once = false;
+  int slot = 0;         // constant-memory slot (kConstSlots solvers can be in flight concurrently)
   bool problem_set = false;
   bool debug = false;
-  bool bounds_per_instance = false;
-  double* arena = nullptr;  // one allocation for every double row
-  size_t arena_rows = 0;
-  int* iarena = nullptr;    // status, iter
-  int* d_n_active = nullptr;
+  double* arena = nullptr;  // tile records
+  int* d_lists = nullptr;   // two compaction lists of `batch` ints
+  int* d_counts = nullptr;  // [0],[1]: list lengths (ping-pong); [2]: n_active
   unsigned long long* d_stats = nullptr;
-  int* h_n_active = nullptr;  // pinned
+  int* h_counts = nullptr;  // pinned
   unsigned long long* h_stats = nullptr;
   int* d_map = nullptr;  // gather map scratch (<= 36*64 ints)
   StateP S{};
-  double *lbv = nullptr, *ubv = nullptr;
+  cudaEvent_t ev_done = nullptr;  // recorded after the last kernel that reads this solver's constants
   // staging
   void* h_stage = nullptr; size_t h_stage_bytes = 0;
   void* d_stage = nullptr; size_t d_stage_bytes = 0;
   int64_t launches = 0;
   int64_t sweeps = 0;
-  int chunk_it = 0;  // iterations issued in the current solve
-  int minb = 3;
+  int minb = 0;
+  int last_list = -1;  // index of the list holding the most recent compaction, -1 = none
+  int sweeps_in_solve = 0;
 };
 
-static uint64_t g_const_owner = 0;  // which solver's ModelC currently sits in c_model
-static uint64_t g_next_id = 1;
-struct SolverId { uint64_t id; };
-static std::vector<std::pair<loik_solver*, uint64_t>> g_ids;
-static uint64_t solver_id(loik_solver* h) {
-  for (auto& p : g_ids) if (p.first == h) return p.second;
-  g_ids.emplace_back(h, g_next_id++);
-  return g_ids.back().second;
-}
+// Constant memory is a per-module resource: c_model[slot] is owned by one solver at a time.
+static loik_solver* g_slot_owner[kConstSlots] = {nullptr};
+static int g_next_slot = 0;
 
+// Make sure c_model[h->slot] holds h->mc before kernels of `h` are enqueued on `st`.  If another solver's
+// kernels may still be reading the slot, wait for them first (stream-ordered, no host block).
 static int upload_consts(loik_solver* h, cudaStream_t st) {
-  const uint64_t id = solver_id(h);
-  if (h->const_dirty || g_const_owner != id) {
-    CK(cudaMemcpyToSymbolAsync(c_model, &h->mc, sizeof(ModelC), 0, cudaMemcpyHostToDevice, st));
-    h->const_dirty = false;
-    g_const_owner = id;
-  }
+  loik_solver* owner = g_slot_owner[h->slot];
+  const bool same = owner == h && h->uploaded_once && std::memcmp(&h->mc, &h->mc_uploaded, sizeof(ModelC)) == 0;
+  if (same) return LOIK_OK;
+  if (owner && owner != h && owner->ev_done) CK(cudaStreamWaitEvent(st, owner->ev_done, 0));
+  h->mc_uploaded = h->mc;  // stable host copy for the async transfer
+  CK(cudaMemcpyToSymbolAsync(c_models, &h->mc_uploaded, sizeof(ModelC), (size_t)h->slot * sizeof(ModelC), cudaMemcpyHostToDevice, st));
+  h->uploaded_once = true;
+  g_slot_owner[h->slot] = h;
   return LOIK_OK;
 }
+static void mark_done(loik_solver* h, cudaStream_t st) { cudaEventRecord(h->ev_done, st); }
 
-static inline int grid_for(int n) { return (n + kBlock - 1) / kBlock; }
+static inline int grid_for(int n, int block = kBlock) { return (n + block - 1) / block; }
 
-// One place that launches the fused iteration kernel.  `minb` (resident CTAs per SM the kernel is
-// compiled for: 2 -> <=255 regs, 3 -> <=168, 4 -> <=128) is a tuning knob (env LOIK_MINB).
-static void launch_iterate(loik_solver* h, cudaStream_t st, int iters, int fixed) {
+// One place that launches the fused iteration kernel.  `minb` = resident CTAs (of 64 threads) per SM the
+// kernel is compiled for: 4 -> <=255 regs/thread, 6 -> <=168, 8 -> <=128 (tuning knob, env LOIK_MINB).
+static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S, int iters, int fixed) {
   const int g = grid_for(h->batch);
-#define LOIK_LAUNCH(DBG, MB) k_iterate<DBG, MB><<<g, kBlock, 0, st>>>(h->S, iters, fixed)
-  if (h->debug) { LOIK_LAUNCH(true, 2); }
-  else if (h->minb == 2) { LOIK_LAUNCH(false, 2); }
-  else if (h->minb == 3) { LOIK_LAUNCH(false, 3); }
-  else { LOIK_LAUNCH(false, 4); }
+#define LOIK_LAUNCH(DBG, MB) k_iterate<DBG, MB><<<g, kBlock, 0, st>>>(S, h->slot, iters, fixed)
+  if (h->debug) { LOIK_LAUNCH(true, 4); }
+  else if (h->minb == 4) { LOIK_LAUNCH(false, 4); }
+  else if (h->minb == 6) { LOIK_LAUNCH(false, 6); }
+  else { LOIK_LAUNCH(false, 8); }
 #undef LOIK_LAUNCH
+  h->launches++;
 }
 
 static int ensure_stage(loik_solver* h, size_t bytes) {
@@ -360,9 +440,11 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LOIK_ERR_CUDA, "loik_create: no CUDA device (libloik_b200 has no CPU fallback)");
   CK(cudaSetDevice(device));
   loik_solver* h = new loik_solver();
-  h->device = device; h->batch = batch; h->cap = (batch + 31) / 32 * 32;
+  h->device = device; h->batch = batch; h->ntiles = (batch + 31) / 32;
   h->nj = nj; h->nb = nj - 1; h->nc = params->num_eq_c; h->prm = *params;
-  if (const char* e = std::getenv("LOIK_MINB")) { const int v = std::atoi(e); if (v >= 2 && v <= 4) h->minb = v; }
+  h->slot = g_next_slot; g_next_slot = (g_next_slot + 1) % kConstSlots;
+  h->minb = 4;
+  if (const char* e = std::getenv("LOIK_MINB")) { const int v = std::atoi(e); if (v == 4 || v == 6 || v == 8) h->minb = v; }
   ModelC& M = h->mc;
   std::memset(&M, 0, sizeof(M));
   M.nj = nj; M.nb = nj - 1; M.nc = h->nc;
@@ -386,36 +468,29 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   }
   for (int i = 1; i < nj; ++i) M.j[i].pend = pend[i];
   M.npend = npend; h->npend = npend;
-  // device memory: one arena of rows
-  const int nb = h->nb, nc = std::max(h->nc, 1), cap = h->cap;
-  size_t rows = 0;
-  auto take = [&](size_t r) { size_t o = rows; rows += r; return o; };
-  const size_t o_v = take(6 * nb), o_f = take(6 * nb), o_F = take(6 * nb), o_nu = take(nb), o_z = take(nb), o_w = take(nb), o_T = take(nb);
-  const size_t o_y = take(6 * nc), o_Aty = take(6 * nc), o_jq = take(2 * nb), o_b = take(6 * nc), o_Atb = take(6 * nc), o_binf = take(1);
-  const size_t o_lb = take(nb), o_ub = take(nb), o_mu = take(1), o_res = take(4);
-  const size_t o_H = take(21 * nb), o_p = take(6 * nb), o_UD = take(6 * nb), o_Di = take(nb), o_r = take(nb);
-  const size_t o_pH = take(27 * std::max(npend, 1)), o_pF = take(6 * std::max(npend, 1));
-  const size_t o_cy = take(kCarryRows), o_norms = take(LOIK_NUM_NORMS), o_prv = take(7 * nb), o_drv = take(7 * nb);
-  h->arena_rows = rows;
-  if (cudaMalloc(&h->arena, rows * cap * sizeof(double)) != cudaSuccess) { delete h; return fail(LOIK_ERR_CUDA, "loik_create: cudaMalloc failed"); }
-  cudaMemset(h->arena, 0, rows * cap * sizeof(double));
-  cudaMalloc(&h->iarena, 2 * (size_t)cap * sizeof(int));
-  cudaMemset(h->iarena, 0, 2 * (size_t)cap * sizeof(int));
-  cudaMalloc(&h->d_n_active, sizeof(int));
+  // tile record layout: [globals | joint blocks | task blocks | pending blocks | debug vectors]
+  const int nb = h->nb, nc = std::max(h->nc, 1);
+  Offs& O = M.off;
+  int rows = 0;
+  O.glob = rows; rows += GR_ROWS;
+  O.joint0 = rows; rows += JR_ROWS * nb;
+  O.task0 = rows; rows += TR_ROWS * nc;
+  O.pend0 = rows; rows += PR_ROWS * std::max(npend, 1);
+  O.prv = rows; rows += 7 * nb;
+  O.drv = rows; rows += 7 * nb;
+  O.rows = rows;
+  const size_t arena_doubles = (size_t)h->ntiles * rows * 32;
+  if (cudaMalloc(&h->arena, arena_doubles * sizeof(double)) != cudaSuccess) { delete h; return fail(LOIK_ERR_CUDA, "loik_create: cudaMalloc failed"); }
+  cudaMemset(h->arena, 0, arena_doubles * sizeof(double));
+  cudaMalloc(&h->d_lists, 2 * (size_t)batch * sizeof(int));
+  cudaMalloc(&h->d_counts, 4 * sizeof(int));
+  cudaMemset(h->d_counts, 0, 4 * sizeof(int));
   cudaMalloc(&h->d_stats, 4 * sizeof(unsigned long long));
-  cudaMalloc(&h->d_map, 36 * LOIK_MAX_JOINTS * sizeof(int));
-  cudaMallocHost(&h->h_n_active, sizeof(int));
+  cudaMalloc(&h->d_map, 64 * LOIK_MAX_JOINTS * sizeof(int));
+  cudaMallocHost(&h->h_counts, 4 * sizeof(int));
   cudaMallocHost(&h->h_stats, 4 * sizeof(unsigned long long));
-  auto P = [&](size_t o) { return h->arena + o * cap; };
-  StateP& S = h->S;
-  S.cap = cap; S.n = batch;
-  S.v = P(o_v); S.f = P(o_f); S.F = P(o_F); S.nu = P(o_nu); S.z = P(o_z); S.w = P(o_w); S.T = P(o_T); S.y = P(o_y); S.Aty = P(o_Aty);
-  S.jq = P(o_jq); S.b = P(o_b); S.Atb = P(o_Atb); S.binf = P(o_binf); S.lbv = nullptr; S.ubv = nullptr;
-  h->lbv = P(o_lb); h->ubv = P(o_ub);
-  S.mu = P(o_mu); S.res = P(o_res); S.status = h->iarena; S.iter = h->iarena + cap;
-  S.H = P(o_H); S.p = P(o_p); S.UDinv = P(o_UD); S.Dinv = P(o_Di); S.r = P(o_r); S.pendH = P(o_pH); S.pendF = P(o_pF);
-  S.carry = P(o_cy); S.norms = P(o_norms); S.prv = P(o_prv); S.drv = P(o_drv);
-  S.n_active = h->d_n_active;
+  cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
+  h->S.arena = h->arena; h->S.n = batch; h->S.list = nullptr; h->S.n_list = nullptr; h->S.n_active = nullptr;
   if (cudaGetLastError() != cudaSuccess) { loik_destroy(h); return fail(LOIK_ERR_CUDA, "loik_create: allocation failed"); }
   *out = h;
   return LOIK_OK;
@@ -424,20 +499,23 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
 void loik_destroy(loik_solver* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaFree(h->arena); cudaFree(h->iarena); cudaFree(h->d_n_active); cudaFree(h->d_stats); cudaFree(h->d_map);
-  cudaFreeHost(h->h_n_active); cudaFreeHost(h->h_stats);
+  cudaDeviceSynchronize();
+  cudaFree(h->arena); cudaFree(h->d_lists); cudaFree(h->d_counts); cudaFree(h->d_stats); cudaFree(h->d_map);
+  cudaFreeHost(h->h_counts); cudaFreeHost(h->h_stats);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->d_stage) cudaFree(h->d_stage);
-  for (size_t i = 0; i < g_ids.size(); ++i)
-    if (g_ids[i].first == h) { if (g_const_owner == g_ids[i].second) g_const_owner = 0; g_ids.erase(g_ids.begin() + i); break; }
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
+  for (int i = 0; i < kConstSlots; ++i) if (g_slot_owner[i] == h) g_slot_owner[i] = nullptr;
   delete h;
 }
 
 static int launch_reset(loik_solver* h, int flags, cudaStream_t st) {
   int rc = upload_consts(h, st);
   if (rc) return rc;
-  k_reset<<<grid_for(h->batch), kBlock, 0, st>>>(h->S, flags);
+  k_reset<<<grid_for(h->batch, 128), 128, 0, st>>>(h->S, h->slot, flags);
   h->launches++;
+  h->last_list = -1;
+  h->sweeps_in_solve = 0;
   CK(cudaGetLastError());
   return LOIK_OK;
 }
@@ -454,6 +532,7 @@ static int set_problem_consts(loik_solver* h, const double* H_ref, const double*
   for (int i = 0; i < 6; ++i) { Hv[i] = 0; for (int j = 0; j < 6; ++j) Hv[i] += H_ref[6 * i + j] * v_ref[j]; }
   double hv_inf = 0; for (int i = 0; i < 6; ++i) hv_inf = std::max(hv_inf, std::fabs(Hv[i]));
   M.Hv_inf = hv_inf;  // = |Hv[0]|inf (ik-id-description-optimized.hpp:95)
+  M.bounds_per_instance = bounds_shared ? 0 : 1;
   for (int i = 1; i < h->nj; ++i) {
     JointC& J = M.j[i];
     sym_blocks(H_ref, J.HrA, J.HrB, J.HrD);
@@ -475,7 +554,6 @@ static int set_problem_consts(loik_solver* h, const double* H_ref, const double*
       for (int j = 0; j < 6; ++j) { double s = 0; for (int r = 0; r < 6; ++r) s += T.A[6 * r + i] * T.A[6 * r + j]; AtA[6 * i + j] = s; }
     sym_blocks(AtA, T.AtA_A, T.AtA_B, T.AtA_D);
   }
-  h->const_dirty = true;
   return LOIK_OK;
 }
 
@@ -489,7 +567,7 @@ int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const 
   const size_t q_bytes = (size_t)B * nb * sizeof(double);
   const size_t b_bytes = (size_t)(b_per_instance ? B : 1) * nc * 6 * sizeof(double);
   const size_t bd_bytes = (size_t)(bounds_per_instance ? B : 1) * nb * sizeof(double);
-  // shared bounds / shared b are small: read them on the host when they are host pointers
+  // shared bounds are small: read them on the host (they go to constant memory)
   std::vector<double> lbh(nb), ubh(nb);
   if (!bounds_per_instance) {
     if (loc == LOIK_HOST) { std::memcpy(lbh.data(), lb, bd_bytes); std::memcpy(ubh.data(), ub, bd_bytes); }
@@ -510,25 +588,24 @@ int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const 
   }
   // ik_id_data_.Reset(warm_start) + ResetSolver() + FwdPassInit's y/Aty wipe (hpp:346-359, hxx:270-278)
   const int flags = RST_SOLVER | (h->prm.warm_start ? 0 : (RST_WZ | RST_NU | RST_VFF | RST_YATY));
-  k_reset<<<grid_for(B), kBlock, 0, st>>>(h->S, flags);
-  k_set_q<<<grid_for(B), kBlock, 0, st>>>(h->S, (const double*)dq);
+  k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->S, h->slot, flags);
+  k_set_q<<<grid_for(B), kBlock, kBlock * nb * sizeof(double), st>>>(h->S, h->slot, (const double*)dq);
   h->launches += 2;
-  if (nc > 0) { k_set_b<<<grid_for(B), kBlock, 0, st>>>(h->S, (const double*)db, b_per_instance, -1); h->launches++; }
-  h->bounds_per_instance = bounds_per_instance != 0;
+  h->last_list = -1;
+  if (nc > 0) { k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->S, h->slot, (const double*)db, b_per_instance, -1); h->launches++; }
   if (bounds_per_instance) {
-    h->S.lbv = h->lbv; h->S.ubv = h->ubv;
-    k_set_bounds<<<grid_for(B), kBlock, 0, st>>>(h->S, (const double*)dlb, (const double*)dub);
+    k_set_bounds<<<grid_for(B, 128), 128, 0, st>>>(h->S, h->slot, (const double*)dlb, (const double*)dub);
     h->launches++;
-  } else {
-    h->S.lbv = nullptr; h->S.ubv = nullptr;
   }
   CK(cudaGetLastError());
+  mark_done(h, st);
   if (loc == LOIK_HOST) CK(cudaStreamSynchronize(st));  // the staging buffer may be reused by the next call
   h->problem_set = true;
   return LOIK_OK;
 }
 
 int loik_update_references(loik_solver* h, const double* H_refs, const double* v_refs, void* stream) {
+  (void)stream;
   if (!h || !H_refs || !v_refs) return fail(LOIK_ERR_INVALID, "loik_update_references: null argument");
   ModelC& M = h->mc;
   for (int i = 0; i < h->nj; ++i) {
@@ -538,31 +615,54 @@ int loik_update_references(loik_solver* h, const double* H_refs, const double* v
     if (n > M.Hv_inf) M.Hv_inf = n;  // only grows (ik-id-description-optimized.hpp:115-117)
     if (i >= 1) { sym_blocks(H_refs + 36 * i, M.j[i].HrA, M.j[i].HrB, M.j[i].HrD); for (int a = 0; a < 6; ++a) M.j[i].Hv[a] = Hv[a]; }
   }
-  h->const_dirty = true;
   return LOIK_OK;
 }
 
-// the main loop of Solve() (hpp:377-454) over the whole batch: launches fused iteration kernels until no
-// instance is active.  `chunk` iterations per launch; the active counter is read back after every launch.
-static int run_loop(loik_solver* h, cudaStream_t st, int max_sweeps, bool fixed) {
+// Compact the still-active instances into the other list.  Everything stays on the stream.
+static int compact(loik_solver* h, cudaStream_t st) {
+  const int B = h->batch;
+  const int in = h->last_list, outi = in < 0 ? 0 : 1 - in;
+  int* list_out = h->d_lists + (size_t)outi * B;
+  CK(cudaMemsetAsync(h->d_counts + outi, 0, sizeof(int), st));
+  k_compact<<<grid_for(B, 256), 256, 0, st>>>(h->S, h->slot, in < 0 ? nullptr : h->d_lists + (size_t)in * B,
+                                              in < 0 ? nullptr : h->d_counts + in, list_out, h->d_counts + outi);
+  h->launches++;
+  h->last_list = outi;
+  return LOIK_OK;
+}
+
+// The main loop of Solve() (hpp:377-454) over the whole batch, enqueued as a fixed schedule of launches with NO
+// host round trip: a few dense sweeps while (almost) every instance is active, then compaction + list-mode
+// launches of geometrically growing iteration counts.  Per-instance loop control lives on the device, so
+// finished instances are frozen and launches past global convergence find an empty list.  `budget` = ADMM
+// iterations any instance may still need (max_iter for a fresh solve).
+static int run_schedule(loik_solver* h, cudaStream_t st, int budget) {
   int rc = upload_consts(h, st);
   if (rc) return rc;
   const int B = h->batch;
   int done = 0;
-  while (done < max_sweeps) {
-    const int chunk = std::min(fixed ? max_sweeps : 4, max_sweeps - done);
-    CK(cudaMemsetAsync(h->d_n_active, 0, sizeof(int), st));
-    launch_iterate(h, st, chunk, fixed ? 1 : 0);
-    h->launches++;
-    h->sweeps += chunk;
-    done += chunk;
-    if (!fixed) {
-      CK(cudaMemcpyAsync(h->h_n_active, h->d_n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      if (*h->h_n_active == 0) break;
-    }
+  // dense phase
+  const int dense = std::min(budget, 3);
+  if (dense > 0) {
+    launch_iterate(h, st, h->S, dense, 0);
+    h->sweeps += dense; done += dense;
   }
+  int chunk = 1, reps = 0;
+  while (done < budget) {
+    rc = compact(h, st);
+    if (rc) return rc;
+    StateP S = h->S;
+    S.list = h->d_lists + (size_t)h->last_list * B;
+    S.n_list = h->d_counts + h->last_list;
+    const int c = std::min(chunk, budget - done);
+    launch_iterate(h, st, S, c, 0);
+    h->sweeps += c; done += c;
+    if (++reps == 2) { reps = 0; if (chunk < 64) chunk *= 2; }
+  }
+  // leave the number of still-active instances (0 after a complete schedule) in d_counts[2]
+  CK(cudaMemsetAsync(h->d_counts + 2, 0, sizeof(int), st));
   CK(cudaGetLastError());
+  mark_done(h, st);
   return LOIK_OK;
 }
 
@@ -573,34 +673,41 @@ int loik_reset_recursion(loik_solver* h, void* stream) {
   return launch_reset(h, RST_WZ | RST_VFF | RST_YATY | RST_SOLVER, (cudaStream_t)stream);
 }
 
+static int check_strategy(loik_solver* h) {
+  if (h->prm.mu_update_strat != LOIK_MU_DEFAULT)
+    return fail(LOIK_ERR_UNSUPPORTED, "[FirstOrderLoikOptimizedTpl::UpdateMu]: mu update strategy not yet implemented");
+  return LOIK_OK;
+}
+
 int loik_solve(loik_solver* h, void* stream) {
   if (!h) return fail(LOIK_ERR_INVALID, "null handle");
   if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_solve: call loik_solve_init first");
-  if (h->prm.mu_update_strat != LOIK_MU_DEFAULT)
-    return fail(LOIK_ERR_UNSUPPORTED, "[FirstOrderLoikOptimizedTpl::UpdateMu]: mu update strategy not yet implemented");
+  int rc = check_strategy(h);
+  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
-  int rc = launch_reset(h, RST_WZ | RST_VFF | RST_YATY | RST_SOLVER, st);  // ResetRecursion + ResetSolver (hpp:370-374)
+  rc = launch_reset(h, RST_WZ | RST_VFF | RST_YATY | RST_SOLVER, st);  // ResetRecursion + ResetSolver (hpp:370-374)
   if (rc) return rc;
   if (h->prm.max_iter < 2) return LOIK_OK;
-  return run_loop(h, st, h->prm.max_iter, false);
+  return run_schedule(h, st, h->prm.max_iter);
 }
 
 int loik_solve_full(loik_solver* h, const double* q, const double* H_ref, const double* v_ref, int32_t n_ids,
                     const int32_t* ids, const double* A, const double* b, int32_t b_per_instance, const double* lb,
                     const double* ub, int32_t bounds_per_instance, int32_t loc, void* stream) {
-  if (h && h->prm.mu_update_strat != LOIK_MU_DEFAULT)
-    return fail(LOIK_ERR_UNSUPPORTED, "[FirstOrderLoikOptimizedTpl::UpdateMu]: mu update strategy not yet implemented");
+  if (h) { int rc = check_strategy(h); if (rc) return rc; }
   int rc = loik_solve_init(h, q, H_ref, v_ref, n_ids, ids, A, b, b_per_instance, lb, ub, bounds_per_instance, loc, stream);
   if (rc) return rc;
   if (h->prm.max_iter < 2) return LOIK_OK;
-  return run_loop(h, (cudaStream_t)stream, h->prm.max_iter, false);
+  return run_schedule(h, (cudaStream_t)stream, h->prm.max_iter);
 }
 
 int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double* Ai, const double* bi,
                     int32_t b_per_instance, int32_t loc, void* stream) {
   if (!h || !q || !Ai || !bi) return fail(LOIK_ERR_INVALID, "loik_solve_task: null argument");
   if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_solve_task: call loik_solve_init first");
+  int rc = check_strategy(h);
+  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
   ModelC& M = h->mc;
@@ -614,24 +721,24 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
   for (int i = 0; i < 6; ++i)
     for (int j = 0; j < 6; ++j) { double s = 0; for (int r = 0; r < 6; ++r) s += T.A[6 * r + i] * T.A[6 * r + j]; AtA[6 * i + j] = s; }
   sym_blocks(AtA, T.AtA_A, T.AtA_B, T.AtA_D);
-  h->const_dirty = true;
   const int B = h->batch, nb = h->nb;
   const size_t q_bytes = (size_t)B * nb * sizeof(double), b_bytes = (size_t)(b_per_instance ? B : 1) * 6 * sizeof(double);
-  int rc;
   if (loc == LOIK_HOST) { rc = ensure_stage(h, q_bytes + b_bytes + 64); if (rc) return rc; }
   rc = upload_consts(h, st); if (rc) return rc;
   const void *dq, *db;
   rc = to_device(h, q, q_bytes, loc, 0, st, &dq); if (rc) return rc;
   rc = to_device(h, bi, b_bytes, loc, q_bytes, st, &db); if (rc) return rc;
   const int flags = RST_SOLVER | (h->prm.warm_start ? 0 : (RST_WZ | RST_NU | RST_VFF | RST_YATY));
-  k_reset<<<grid_for(B), kBlock, 0, st>>>(h->S, flags);
-  k_set_b<<<grid_for(B), kBlock, 0, st>>>(h->S, (const double*)db, b_per_instance, k);
-  k_set_q<<<grid_for(B), kBlock, 0, st>>>(h->S, (const double*)dq);
+  k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->S, h->slot, flags);
+  k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->S, h->slot, (const double*)db, b_per_instance, k);
+  k_set_q<<<grid_for(B), kBlock, kBlock * nb * sizeof(double), st>>>(h->S, h->slot, (const double*)dq);
   h->launches += 3;
+  h->last_list = -1;
   CK(cudaGetLastError());
+  mark_done(h, st);
   if (loc == LOIK_HOST) CK(cudaStreamSynchronize(st));
   if (h->prm.max_iter < 2) return LOIK_OK;
-  return run_loop(h, st, h->prm.max_iter, false);
+  return run_schedule(h, st, h->prm.max_iter);
 }
 
 int loik_iterate_fixed(loik_solver* h, int32_t iters, int32_t reset, void* stream) {
@@ -642,20 +749,22 @@ int loik_iterate_fixed(loik_solver* h, int32_t iters, int32_t reset, void* strea
   if (reset) { int rc = launch_reset(h, RST_WZ | RST_VFF | RST_YATY | RST_SOLVER, st); if (rc) return rc; }
   int rc = upload_consts(h, st);
   if (rc) return rc;
-  // one launch per iteration: this is the quantity the roofline is quoted on
-  for (int i = 0; i < iters; ++i) {
-    launch_iterate(h, st, 1, 1);
-  }
-  h->launches += iters; h->sweeps += iters;
+  // one launch per iteration, dense: this is the quantity the roofline is quoted on
+  for (int i = 0; i < iters; ++i) launch_iterate(h, st, h->S, 1, 1);
+  h->sweeps += iters;
   CK(cudaGetLastError());
+  mark_done(h, st);
   return LOIK_OK;
 }
 
+// ---- chunked solve for the batch-sharded multi-GPU driver: the caller interleaves chunks with the all-reduce of
+// the active count (loik_active_count_device_ptr) and stops when the global count is zero.
 int loik_solve_begin(loik_solver* h, void* stream) {
   if (!h) return fail(LOIK_ERR_INVALID, "null handle");
   if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_solve_begin: call loik_solve_init first");
+  int rc = check_strategy(h);
+  if (rc) return rc;
   CK(cudaSetDevice(h->device));
-  h->chunk_it = 0;
   return launch_reset(h, RST_WZ | RST_VFF | RST_YATY | RST_SOLVER, (cudaStream_t)stream);
 }
 int loik_solve_chunk(loik_solver* h, int32_t iters, void* stream) {
@@ -664,16 +773,26 @@ int loik_solve_chunk(loik_solver* h, int32_t iters, void* stream) {
   CK(cudaSetDevice(h->device));
   int rc = upload_consts(h, st);
   if (rc) return rc;
-  CK(cudaMemsetAsync(h->d_n_active, 0, sizeof(int), st));
-  launch_iterate(h, st, iters, 0);
-  h->launches++; h->sweeps += iters; h->chunk_it += iters;
+  const int B = h->batch;
+  StateP S = h->S;
+  if (h->last_list >= 0 || h->sweeps_in_solve >= 3) {  // dense for the first sweeps, compacted afterwards
+    rc = compact(h, st);
+    if (rc) return rc;
+    S.list = h->d_lists + (size_t)h->last_list * B;
+    S.n_list = h->d_counts + h->last_list;
+  }
+  CK(cudaMemsetAsync(h->d_counts + 2, 0, sizeof(int), st));
+  S.n_active = h->d_counts + 2;
+  launch_iterate(h, st, S, iters, 0);
+  h->sweeps += iters; h->sweeps_in_solve += iters;
   CK(cudaGetLastError());
+  mark_done(h, st);
   return LOIK_OK;
 }
 int loik_solve_end(loik_solver* h, void* stream) { (void)h; (void)stream; return LOIK_OK; }
 int loik_active_count_device_ptr(loik_solver* h, void** dev_ptr) {
   if (!h || !dev_ptr) return fail(LOIK_ERR_INVALID, "null argument");
-  *dev_ptr = h->d_n_active;
+  *dev_ptr = h->d_counts + 2;
   return LOIK_OK;
 }
 
@@ -686,13 +805,14 @@ int loik_step(loik_solver* h, int32_t step_id, void* stream) {
   if (rc) return rc;
   const int g = grid_for(h->batch);
   switch (step_id) {
-    case LOIK_STEP_BACKWARD: k_step_backward<<<g, kBlock, 0, st>>>(h->S); break;
-    case LOIK_STEP_FORWARD: k_step_forward<<<g, kBlock, 0, st>>>(h->S); break;
-    case LOIK_STEP_RESIDUAL: k_step_residual<<<g, kBlock, 0, st>>>(h->S, 0); h->sweeps++; break;
+    case LOIK_STEP_BACKWARD: k_step_backward<<<g, kBlock, 0, st>>>(h->S, h->slot); break;
+    case LOIK_STEP_FORWARD: k_step_forward<<<g, kBlock, 0, st>>>(h->S, h->slot); break;
+    case LOIK_STEP_RESIDUAL: k_step_residual<<<g, kBlock, 0, st>>>(h->S, h->slot, 0); h->sweeps++; break;
     default: return fail(LOIK_ERR_INVALID, "loik_step: unknown step id");
   }
   h->launches++;
   CK(cudaGetLastError());
+  mark_done(h, st);
   return LOIK_OK;
 }
 
@@ -708,33 +828,34 @@ int loik_get(loik_solver* h, int32_t field, void* dst, int32_t loc, void* stream
   CK(cudaSetDevice(h->device));
   int rc = upload_consts(h, st);
   if (rc) return rc;
-  const int B = h->batch, nb = h->nb, nc = h->nc, cap = h->cap;
-  const StateP& S = h->S;
-  const double* src = nullptr;
+  const int B = h->batch, nb = h->nb, nc = h->nc;
+  const Offs& O = h->mc.off;
   int rows = 0;
   std::vector<int> map;
   bool is_int = false;
+  auto per_joint = [&](int jr, int width) { for (int j = 0; j < nb; ++j) for (int c = 0; c < width; ++c) map.push_back(O.joint0 + JR_ROWS * j + jr + c); };
+  auto per_task = [&](int tr) { for (int k = 0; k < nc; ++k) for (int c = 0; c < 6; ++c) map.push_back(O.task0 + TR_ROWS * k + tr + c); };
+  auto span = [&](int r0, int n) { for (int c = 0; c < n; ++c) map.push_back(r0 + c); };
   switch (field) {
-    case LOIK_F_Z: src = S.z; rows = nb; break;
-    case LOIK_F_NU: src = S.nu; rows = nb; break;
-    case LOIK_F_W: src = S.w; rows = nb; break;
-    case LOIK_F_Y: src = S.y; rows = 6 * nc; break;
-    case LOIK_F_V: src = S.v; rows = 6 * nb; break;
-    case LOIK_F_F: src = S.f; rows = 6 * nb; break;
-    case LOIK_F_ATY: src = S.Aty; rows = 6 * nc; break;
-    case LOIK_F_FDPA: src = S.F; rows = 6 * nb; break;
-    case LOIK_F_STF_PLUS_W: src = S.T; rows = nb; break;
-    case LOIK_F_P: src = S.p; rows = 6 * nb; break;
-    case LOIK_F_UDINV: src = S.UDinv; rows = 6 * nb; break;
-    case LOIK_F_DINV: src = S.Dinv; rows = nb; break;
-    case LOIK_F_R: src = S.r; rows = nb; break;
-    case LOIK_F_MU: src = S.mu; rows = 1; break;
-    case LOIK_F_RESIDUALS: src = S.res; rows = 4; break;
-    case LOIK_F_NORMS: src = S.norms; rows = LOIK_NUM_NORMS; break;
-    case LOIK_F_PRIMAL_RES_VEC: src = S.prv; rows = 7 * nb; break;
-    case LOIK_F_DUAL_RES_VEC: src = S.drv; rows = 7 * nb; break;
-    case LOIK_F_H: {  // expand the 21 stored scalars of each joint to a full symmetric 6x6
-      src = S.H; rows = 36 * nb; map.resize(rows);
+    case LOIK_F_Z: per_joint(JR_Z, 1); break;
+    case LOIK_F_NU: per_joint(JR_NU, 1); break;
+    case LOIK_F_W: per_joint(JR_W, 1); break;
+    case LOIK_F_Y: per_task(TR_Y); break;
+    case LOIK_F_V: per_joint(JR_V, 6); break;
+    case LOIK_F_F: per_joint(JR_F, 6); break;
+    case LOIK_F_ATY: per_task(TR_ATY); break;
+    case LOIK_F_FDPA: per_joint(JR_FD, 6); break;
+    case LOIK_F_STF_PLUS_W: per_joint(JR_T, 1); break;
+    case LOIK_F_P: per_joint(JR_P, 6); break;
+    case LOIK_F_UDINV: per_joint(JR_UD, 6); break;
+    case LOIK_F_DINV: per_joint(JR_DINV, 1); break;
+    case LOIK_F_R: per_joint(JR_R, 1); break;
+    case LOIK_F_MU: span(O.glob + GR_MU, 1); break;
+    case LOIK_F_RESIDUALS: span(O.glob + GR_RES, 4); break;
+    case LOIK_F_NORMS: span(O.glob + GR_NORMS, LOIK_NUM_NORMS); break;
+    case LOIK_F_PRIMAL_RES_VEC: span(O.prv, 7 * nb); break;
+    case LOIK_F_DUAL_RES_VEC: span(O.drv, 7 * nb); break;
+    case LOIK_F_H:  // expand the 21 stored scalars of each joint to a full symmetric 6x6
       for (int j = 0; j < nb; ++j)
         for (int a = 0; a < 6; ++a)
           for (int c = 0; c < 6; ++c) {
@@ -743,31 +864,30 @@ int loik_get(loik_solver* h, int32_t field, void* dst, int32_t loc, void* stream
             else if (a >= 3 && c >= 3) r = 15 + si(a - 3, c - 3);
             else if (a < 3) r = 6 + 3 * a + (c - 3);
             else r = 6 + 3 * c + (a - 3);
-            map[36 * j + 6 * a + c] = 21 * j + r;
+            map.push_back(O.joint0 + JR_ROWS * j + JR_H + r);
           }
       break;
-    }
     case LOIK_F_LIMI: rows = 12 * nb; break;
     case LOIK_F_ITER: case LOIK_F_STATUS: is_int = true; rows = 1; break;
     default: return fail(LOIK_ERR_INVALID, "loik_get: unknown field");
   }
+  if (!map.empty()) rows = (int)map.size();
   const size_t bytes = (size_t)B * rows * (is_int ? sizeof(int) : sizeof(double));
   void* ddst = dst;
   if (loc == LOIK_HOST) { rc = ensure_stage(h, bytes); if (rc) return rc; ddst = h->d_stage; }
   if (field == LOIK_F_LIMI) {
-    k_gather_limi<<<grid_for(B), kBlock, 0, st>>>(S, (double*)ddst);
-  } else if (field == LOIK_F_ITER) {
-    CK(cudaMemcpyAsync(ddst, S.iter, bytes, cudaMemcpyDeviceToDevice, st));
-  } else if (field == LOIK_F_STATUS) {
-    k_status_flags<<<grid_for(B), kBlock, 0, st>>>(S, (int*)ddst);
+    k_gather_limi<<<grid_for(B, 128), 128, 0, st>>>(h->S, h->slot, (double*)ddst);
+  } else if (is_int) {
+    k_gather_ctl<<<grid_for(B, 128), 128, 0, st>>>(h->S, h->slot, field == LOIK_F_ITER ? 0 : 1, (int*)ddst);
   } else {
-    const int* dmap = nullptr;
-    if (!map.empty()) { CK(cudaMemcpyAsync(h->d_map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); dmap = h->d_map; }
+    CK(cudaMemcpyAsync(h->d_map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // `map` is a local
     const size_t total = (size_t)B * rows;
-    k_gather<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, cap, B, rows, dmap, (double*)ddst);
+    k_gather<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->S, h->slot, rows, h->d_map, (double*)ddst);
   }
   h->launches++;
   CK(cudaGetLastError());
+  mark_done(h, st);
   if (loc == LOIK_HOST) {
     CK(cudaMemcpyAsync(h->h_stage, ddst, bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -779,8 +899,11 @@ int loik_get(loik_solver* h, int32_t field, void* dst, int32_t loc, void* stream
 int loik_get_stats(loik_solver* h, int64_t out[5]) {
   if (!h || !out) return fail(LOIK_ERR_INVALID, "null argument");
   CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  int rc = upload_consts(h, 0);
+  if (rc) return rc;
   CK(cudaMemset(h->d_stats, 0, 4 * sizeof(unsigned long long)));
-  k_stats<<<grid_for(h->cap), kBlock>>>(h->S, h->d_stats);
+  k_stats<<<grid_for(h->ntiles * 32, 128), 128>>>(h->S, h->slot, h->d_stats);
   h->launches++;
   CK(cudaMemcpy(h->h_stats, h->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 4; ++i) out[i] = (int64_t)h->h_stats[i];
@@ -790,10 +913,10 @@ int loik_get_stats(loik_solver* h, int64_t out[5]) {
 
 int64_t loik_launch_count(loik_solver* h) { return h ? h->launches : 0; }
 
-int loik_set_max_iter(loik_solver* h, int32_t m) { if (!h) return LOIK_ERR_INVALID; h->prm.max_iter = m; h->mc.max_iter = m; h->const_dirty = true; return LOIK_OK; }
-int loik_set_rho(loik_solver* h, double rho) { if (!h) return LOIK_ERR_INVALID; h->prm.rho = rho; h->mc.rho = rho; h->const_dirty = true; return LOIK_OK; }
-int loik_set_mu(loik_solver* h, double mu) { if (!h) return LOIK_ERR_INVALID; h->prm.mu = mu; h->mc.mu0 = mu; h->const_dirty = true; return LOIK_OK; }
-int loik_set_tol_tail_solve(loik_solver* h, double tol) { if (!h) return LOIK_ERR_INVALID; h->prm.tol_tail_solve = tol; h->mc.tol_tail = tol; h->const_dirty = true; return LOIK_OK; }
+int loik_set_max_iter(loik_solver* h, int32_t m) { if (!h) return LOIK_ERR_INVALID; h->prm.max_iter = m; h->mc.max_iter = m; return LOIK_OK; }
+int loik_set_rho(loik_solver* h, double rho) { if (!h) return LOIK_ERR_INVALID; h->prm.rho = rho; h->mc.rho = rho; return LOIK_OK; }
+int loik_set_mu(loik_solver* h, double mu) { if (!h) return LOIK_ERR_INVALID; h->prm.mu = mu; h->mc.mu0 = mu; return LOIK_OK; }
+int loik_set_tol_tail_solve(loik_solver* h, double tol) { if (!h) return LOIK_ERR_INVALID; h->prm.tol_tail_solve = tol; h->mc.tol_tail = tol; return LOIK_OK; }
 int loik_set_warm_start(loik_solver* h, int32_t ws) { if (!h) return LOIK_ERR_INVALID; h->prm.warm_start = ws; return LOIK_OK; }
 
 }  // extern "C"
