@@ -37,6 +37,7 @@ WORKLOADS = {  # BASELINE.json configs[1..3]: (robot, per-GPU batch)
     "talos": ("talos", 16384),
 }
 FIXED_ITERS = 50
+METRIC = "IK solves/sec (batch, device-timed)"
 
 
 def algorithmic_bytes_per_instance_iteration(n, nc):
@@ -161,10 +162,11 @@ def run_reference(args, rank, world):
     total = sum(times)
     value = per_step * len(times) / total
     sample = f"{per_step} of {batch} instances per step, {cores} threads, one solver per thread (CPU restatement of loik-loid-optimized; reference not buildable offline)"
-    line = {"impl": "reference", "metric": "IK solves/sec (batch)", "value": value, "unit": "IK solves/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "IK solves/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{robot} batch {batch}", "robot": robot, "batch_per_gpu": batch, "max_iter": params["max_iter"]},
+            "config": {"workload": f"{robot} batch {batch} per GPU (BASELINE.json configs)", "robot": robot, "n_dof": model.nb,
+                       "n_tasks": len(pb["ids"]), "batch_per_gpu": batch, "max_iter": params["max_iter"]},
             "cpu_baseline": {"value": value, "unit": "IK solves/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "IK solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -173,11 +175,13 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="loik_b200", choices=["loik_b200", "reference"])
     ap.add_argument("--workload", default="panda", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config's)")
+    ap.add_argument("--pipeline", type=int, default=4,
+                    help="solver handles (each on its own stream) kept in flight; step i uses handle i %% depth")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -190,8 +194,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from loik_b200 import solver as lk
     from loik_b200 import sharded
+    from loik_b200 import solver as lk
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
@@ -205,37 +209,34 @@ def main():
     n, nc = model.nb, len(robots.TASK_JOINTS[robot])
     pb = problems.random_batch(model, batch, seed=0, first_index=rank * batch)  # this rank's shard of the global batch
     params = problems.bench_params(nc)
-    S = lk.make_solver(model, params, batch, device=local_rank)
-    drv = sharded.ShardedSolver(S, world)
+    D = max(1, args.pipeline)
+    solvers = [lk.make_solver(model, params, batch, device=local_rank) for _ in range(D)]
+    drivers = [sharded.ShardedSolver(S, world) for S in solvers]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(D)]
 
     # resident inputs (value) and pinned host inputs/outputs (e2e)
     q_d = torch.as_tensor(pb["q"], device=dev)
     b_d = torch.as_tensor(pb["bis"], device=dev)
     q_h = torch.as_tensor(pb["q"]).pin_memory()
     b_h = torch.as_tensor(pb["bis"]).pin_memory()
-    z_d = torch.empty(batch, n, dtype=torch.float64, device=dev)
-    it_d = torch.empty(batch, dtype=torch.int32, device=dev)
-    z_h = torch.empty(batch, n, dtype=torch.float64).pin_memory()
-    it_h = torch.empty(batch, dtype=torch.int32).pin_memory()
-    q_d2 = torch.empty_like(q_d)
-    b_d2 = torch.empty_like(b_d)
+    z_h = [torch.empty(batch, n, dtype=torch.float64).pin_memory() for _ in range(D)]
+    it_h = [torch.empty(batch, dtype=torch.int32).pin_memory() for _ in range(D)]
+    prob = (pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"])
 
-    def init_resident():
-        S.SolveInit(q_d, pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], b_d, pb["lb"], pb["ub"])
+    def step_resident(i):
+        k = i % D
+        with torch.cuda.stream(streams[k]):
+            drivers[k].solve()
 
-    def step_resident():
-        drv.solve()
-
-    def step_e2e():
-        q_d2.copy_(q_h, non_blocking=True)
-        b_d2.copy_(b_h, non_blocking=True)
-        S.SolveInit(q_d2, pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], b_d2, pb["lb"], pb["ub"])
-        drv.solve()
-        S.get(lk.F_Z, out=z_d)
-        S.get(lk.F_ITER, out=it_d)
-        z_h.copy_(z_d, non_blocking=True)
-        it_h.copy_(it_d, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    def step_e2e(i):
+        # the reference-facing call sequence with HOST buffers: SolveInit(q, ..., b, ...) -> Solve() -> read z, iter
+        k = i % D
+        S = solvers[k]
+        with torch.cuda.stream(streams[k]):
+            S.SolveInit(q_h, prob[0], prob[1], prob[2], prob[3], b_h, pb["lb"], pb["ub"])  # pinned host -> HBM inside
+            drivers[k].solve()
+            S.get(lk.F_Z, out=z_h[k])        # HBM -> pinned host inside
+            S.get(lk.F_ITER, out=it_h[k])
 
     def barrier():
         torch.cuda.synchronize()
@@ -246,35 +247,46 @@ def main():
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
+        cur = torch.cuda.current_stream()
+        e0.record(cur)
+        for st in streams:
+            st.wait_event(e0)
+        for i in range(steps):
+            fn(i)
+        for st in streams:
+            done = torch.cuda.Event()
+            done.record(st)
+            cur.wait_event(done)
+        e1.record(cur)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    init_resident()
-    for _ in range(args.warmup):
-        step_resident()
-    launches0 = S.launch_count()
+    for S in solvers:
+        S.SolveInit(q_d, prob[0], prob[1], prob[2], prob[3], b_d, pb["lb"], pb["ub"])
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    launches0 = sum(S.launch_count() for S in solvers)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms_total = timed(step_resident, args.steps)
-    launches = S.launch_count() - launches0
-    stats = S.stats()
+    launches = sum(S.launch_count() for S in solvers) - launches0
+    stats = solvers[0].stats()
     mean_iters = stats["total_iters"] / batch
-    sweeps_per_solve = None
+    # latency of one un-pipelined solve (one handle, one stream)
+    ms_single = timed(lambda i: step_resident(0), 3) / 3
 
-    # fixed-iteration mode: the roofline kernel (one launch = one ADMM iteration of the whole batch)
-    S.IterateFixed(3)
+    # fixed-iteration mode: the roofline kernel (one launch = one ADMM iteration of the whole batch, all active)
+    S0 = solvers[0]
+    S0.IterateFixed(3)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    S.IterateFixed(FIXED_ITERS)
+    S0.IterateFixed(FIXED_ITERS)
     e1.record()
     barrier()
     ms_fixed = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -283,8 +295,8 @@ def main():
     ms_iter = float(ms_fixed.item()) / FIXED_ITERS
 
     # e2e
-    for _ in range(2):
-        step_e2e()
+    for i in range(max(2, D)):
+        step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -295,28 +307,42 @@ def main():
         value = world * batch * args.steps / (ms_total * 1e-3)
         e2e_v = world * batch * args.steps / (ms_e2e * 1e-3)
         line = {
-            "metric": "IK solves/sec (batch, device-timed)", "value": value, "unit": "IK solves/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "IK solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{robot} batch {batch} per GPU (BASELINE.json configs)", "robot": robot, "n_dof": n,
                        "n_tasks": nc, "batch_per_gpu": batch, "global_batch": world * batch, "max_iter": params["max_iter"],
                        "l2": "inputs larger than L2: per-iteration working set %.0f MB" % (bpi * batch / 2 ** 20),
-                       "parallelism": f"batch-sharded x{world}", "mean_iters_per_solve": mean_iters},
+                       "parallelism": f"batch-sharded x{world}", "pipeline_depth": D,
+                       "pipeline": "step i runs on solver handle i % depth (own HBM state, own stream): the latency-bound "
+                                   "tail of one batch overlaps the bulk of the next",
+                       "mean_iters_per_solve": mean_iters},
+            "ms_per_solve_unpipelined": ms_single,
             "iters_per_s": world * batch / (ms_iter * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "peak_source": how, "kernel": "k_iterate (1 ADMM iteration / launch, all instances active)",
+                         "traffic": None, "peak_source": how,
+                         "kernel": "k_iterate (1 ADMM iteration / launch, all instances active)",
                          "algorithmic_bytes_per_launch": bpi * batch, "us_per_launch": ms_iter * 1e3,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_v, "unit": "IK solves/s", "h2d_bytes_per_step": int(q_h.numel() * 8 + b_h.numel() * 8),
-                    "d2h_bytes_per_step": int(z_h.numel() * 8 + it_h.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(z_h[0].numel() * 8 + it_h[0].numel() * 4), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks,
             "solve_stats": {k: int(v) for k, v in stats.items()},
         }
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                with open(traffic_file) as f:
+                    line["roofline"]["traffic"] = json.load(f).get(robot)
+            except Exception:
+                pass
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(model, pb, params, lib=native_oracle_lib())
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))
+    for S in solvers:
+        S.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -18,8 +18,9 @@
  *   - Batched arrays are batch-major (instance-major): q[batch][nq], b[batch][nc][6], z[batch][nv] ...
  *     i.e. one contiguous row per problem instance, exactly what a caller looping over reference
  *     solver objects would hold.  The library keeps its own joint-major SoA copy in HBM.
- *   - Every pointer argument may be a HOST pointer or a DEVICE pointer; `loc` says which
- *     (LOIK_HOST / LOIK_DEVICE).  Host buffers are staged through the library's pinned buffers.
+ *   - Every batched pointer argument may be a HOST pointer or a DEVICE pointer; `loc` says which
+ *     (LOIK_HOST / LOIK_DEVICE / LOIK_HOST_PINNED).  Pageable host buffers are staged through the library's
+ *     pinned buffers and the call synchronizes; device and page-locked buffers are fully asynchronous.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work of a call
  *     is enqueued on it; calls that return data to HOST memory synchronize that stream before returning.
  *   - Not thread-safe per handle (same as the reference: one solver+data pair per thread).
@@ -47,7 +48,9 @@ extern "C" {
 enum { LOIK_JOINT_RX = 0, LOIK_JOINT_RY, LOIK_JOINT_RZ, LOIK_JOINT_PX, LOIK_JOINT_PY, LOIK_JOINT_PZ,
        LOIK_JOINT_RU, LOIK_JOINT_PU };
 
-enum { LOIK_HOST = 0, LOIK_DEVICE = 1 };
+/* where a caller buffer lives: pageable host memory (staged + synchronous), device memory (asynchronous),
+ * or page-locked host memory (asynchronous DMA; the caller synchronizes the stream before reusing / reading it) */
+enum { LOIK_HOST = 0, LOIK_DEVICE = 1, LOIK_HOST_PINNED = 2 };
 
 /* error codes */
 enum { LOIK_OK = 0, LOIK_ERR_INVALID = -1, LOIK_ERR_CUDA = -2, LOIK_ERR_UNSUPPORTED = -3, LOIK_ERR_STATE = -4 };
@@ -133,7 +136,8 @@ typedef enum loik_step_id {
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
 /* FirstOrderLoikOptimizedTpl ctor (hpp:129-162) + IkIdDataTypeOptimizedTpl ctor (data hxx:40-104).
- * Copies the model (the reference holds `Model model_;` by value, hpp:762).  `device` = CUDA ordinal. */
+ * Copies the model (the reference holds `Model model_;` by value, hpp:762).  `device` = CUDA ordinal.
+ * Any number of solvers may be alive and have work in flight on different streams at the same time. */
 LOIK_API int loik_create(const loik_model_desc* model, const loik_params* params, int32_t batch, int32_t device,
                          loik_solver** out);
 LOIK_API void loik_destroy(loik_solver* h);
@@ -147,8 +151,9 @@ LOIK_API const char* loik_last_error(void);
  *   task_joint_ids [nc] joint ids carrying a task (distinct, in 1..njoints-1), shared by the batch
  *   A        [nc][36] shared by the batch
  *   b        [batch][nc][6] if b_per_instance else [nc][6]
- *   lb, ub   [batch][nv] if bounds_per_instance else [nv]
- * H_ref, v_ref, task_joint_ids, A are always HOST pointers (small, batch-uniform); `loc` applies to q, b, lb, ub. */
+ *   lb, ub   [batch][nv] if bounds_per_instance else [nv] (HOST)
+ * H_ref, v_ref, task_joint_ids, A and batch-shared lb/ub are always HOST pointers (small, batch-uniform: they
+ * travel to the kernels in the parameter block); `loc` applies to q, b and per-instance lb/ub. */
 LOIK_API int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const double* v_ref, int32_t n_ids,
                              const int32_t* task_joint_ids, const double* A, const double* b, int32_t b_per_instance,
                              const double* lb, const double* ub, int32_t bounds_per_instance, int32_t loc, void* stream);
@@ -159,7 +164,9 @@ LOIK_API int loik_update_references(loik_solver* h, const double* H_refs, const 
 
 /* ---- solving --------------------------------------------------------------------------------- */
 /* Solve()  (hpp:368-455): ResetRecursion + ResetSolver + main loop, every instance to its own
- * convergence / infeasibility tail / max_iter. */
+ * convergence / infeasibility tail / max_iter.  ASYNCHRONOUS: the whole solve is enqueued on `stream` as a fixed
+ * schedule of launches (loop control is per instance, on the device); results are valid once the stream has
+ * been synchronized or through a later loik_get on the same stream. */
 LOIK_API int loik_solve(loik_solver* h, void* stream);
 /* Solve(q, H_ref, v_ref, ids, Ais, bis, lb, ub)  (hpp:475-580) = SolveInit + main loop (no ResetRecursion). */
 LOIK_API int loik_solve_full(loik_solver* h, const double* q, const double* H_ref, const double* v_ref, int32_t n_ids,
@@ -191,6 +198,10 @@ LOIK_API int loik_get(loik_solver* h, int32_t field, void* dst, int32_t loc, voi
 /* Aggregates of the last solve: out[0] = #converged, out[1] = #primal infeasible, out[2] = #stopped at
  * max_iter, out[3] = sum of per-instance iteration counts, out[4] = ADMM sweeps launched (kernel iterations). */
 LOIK_API int loik_get_stats(loik_solver* h, int64_t out[5]);
+/* Same aggregates, asynchronously: enqueues the reduction on `stream` and returns a device pointer to 4 int64
+ * {#converged, #primal infeasible, #stopped at max_iter, sum of iteration counts} -- the buffer the batch-sharded
+ * multi-GPU driver all-reduces (NCCL SUM) for the global stopping-criterion outcome. */
+LOIK_API int loik_reduce_stats(loik_solver* h, void* stream, void** dev_ptr);
 /* Number of CUDA kernels this handle has launched so far (bench.py's gpu_launches). */
 LOIK_API int64_t loik_launch_count(loik_solver* h);
 

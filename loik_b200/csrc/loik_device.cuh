@@ -83,14 +83,16 @@ constexpr int kCarryRows = 14;
 struct StateP {
   double* arena;      // tile records
   int n;              // slots in use (instances)
+  const int* n_dev;   // if set: device-resident slot count (a packed arena), overrides n
   const int* list;    // optional compaction list: thread k works on slot list[k]
   const int* n_list;  // device-resident length of `list`
   int* n_active;      // device counter: instances still active after this launch
 };
 
-// Constant memory is per module: kConstSlots solvers can have kernels in flight concurrently (one slot each).
-constexpr int kConstSlots = 2;
-__constant__ ModelC c_models[kConstSlots];  // single translation unit (loik_solver.cu)
+// The batch-uniform block (model, problem constants, hyper-parameters) is passed to every kernel BY VALUE as a
+// __grid_constant__ parameter: it lands in the constant bank (uniform LDC reads, like a __constant__ symbol) but is
+// private to the launch, so any number of solvers can have kernels in flight on different streams concurrently
+// (a __constant__ symbol is a per-module singleton; a device buffer read with LDG measured 1.8x slower).
 
 #define LOIK_DEV __device__ __forceinline__
 

@@ -31,13 +31,12 @@ LOIK_DEV void st_ctl(const ModelC& c_model, double* T, int status, int iter) { *
 // Dense mode: thread k = slot k.  List mode: thread k = slot list[k] for k < *n_list (compacted
 // still-active instances; the grid is sized for the worst case and surplus CTAs exit at once).
 template <bool DEBUG, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) k_iterate(const StateP S, const int slot, const int iters, const int fixed) {
-  const ModelC& c_model = c_models[slot];
+__global__ void __launch_bounds__(kBlock, MINB) k_iterate(const __grid_constant__ ModelC c_model, const StateP S, const int iters, const int fixed) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   int s = -1;
   if (S.list) {
     if (k < *S.n_list) s = S.list[k];
-  } else if (k < S.n) {
+  } else if (k < (S.n_dev ? *S.n_dev : S.n)) {
     s = k;
   }
   bool active = false;
@@ -72,13 +71,12 @@ __global__ void __launch_bounds__(kBlock, MINB) k_iterate(const StateP S, const 
 
 // Compaction: append the slots that are still active to list_out (order inside a CTA is preserved so
 // neighbouring instances stay neighbours).  Input is the previous list, or all slots when list_in == nullptr.
-__global__ void __launch_bounds__(256) k_compact(const StateP S, const int slot, const int* __restrict__ list_in, const int* __restrict__ n_in,
+__global__ void __launch_bounds__(256) k_compact(const __grid_constant__ ModelC c_model, const StateP S, const int* __restrict__ list_in, const int* __restrict__ n_in,
                                                  int* __restrict__ list_out, int* __restrict__ n_out) {
-  const ModelC& c_model = c_models[slot];
   __shared__ int warp_cnt[8];
   __shared__ int block_base;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int limit = list_in ? *n_in : S.n;
+  const int limit = list_in ? *n_in : (S.n_dev ? *S.n_dev : S.n);
   int s = -1;
   if (k < limit) s = list_in ? list_in[k] : k;
   bool active = false;
@@ -96,9 +94,84 @@ __global__ void __launch_bounds__(256) k_compact(const StateP S, const int slot,
   if (active) list_out[block_base + warp_cnt[wid] + __popc(m & ((1u << lane) - 1))] = s;
 }
 
+// Physical re-packing: move the still-active instances listed in `list` (slots of arena X) to the dense prefix
+// 0..count-1 of arena Y, so the following sweeps run on full tiles with coalesced rows again.  Only the rows that
+// survive an iteration travel (state, problem data, control); the backward->forward workspace is rebuilt every sweep.
+// origin_y[k] = the instance's slot in the home arena.
+__global__ void __launch_bounds__(128) k_repack(const __grid_constant__ ModelC c_model, const StateP X, const int* __restrict__ list,
+                                                const int* __restrict__ count, const int* __restrict__ origin_x,
+                                                const StateP Y, int* __restrict__ origin_y) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= *count) return;
+  const int src = list[k];
+  const Offs& O = c_model.off;
+  const double* Ts = tile_ptr(X, c_model, src);
+  double* Td = tile_ptr(Y, c_model, k);
+  origin_y[k] = origin_x ? origin_x[src] : src;
+  {
+    const double* Gs = glob_blk(const_cast<double*>(Ts), O);
+    double* Gd = glob_blk(Td, O);
+#pragma unroll
+    for (int r = 0; r < GR_CARRY; ++r) st(Gd, r, ld(Gs, r));  // mu, binf, ctl, res
+  }
+  const int nb = c_model.nb, nc = c_model.nc;
+  for (int j = 0; j < nb; ++j) {
+    const double* Ps = joint_blk(const_cast<double*>(Ts), O, j);
+    double* Pd = joint_blk(Td, O, j);
+    double tmp[JR_H];
+#pragma unroll
+    for (int r = 0; r < JR_H; ++r) tmp[r] = ld(Ps, r);  // state + problem data (26 rows)
+#pragma unroll
+    for (int r = 0; r < JR_H; ++r) st(Pd, r, tmp[r]);
+  }
+  for (int t = 0; t < nc; ++t) {
+    const double* Ps = task_blk(const_cast<double*>(Ts), O, t);
+    double* Pd = task_blk(Td, O, t);
+    double tmp[TR_ROWS];
+#pragma unroll
+    for (int r = 0; r < TR_ROWS; ++r) tmp[r] = ld(Ps, r);
+#pragma unroll
+    for (int r = 0; r < TR_ROWS; ++r) st(Pd, r, tmp[r]);
+  }
+}
+
+// Retire: copy the results of the instances that finished inside packed arena X back to their home slots.
+// all != 0: every slot (end of the schedule), else only the finished ones (the active ones moved on).
+__global__ void __launch_bounds__(128) k_retire(const __grid_constant__ ModelC c_model, const StateP X, const int* __restrict__ origin_x,
+                                                const StateP Home, const int all) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= *X.n_dev) return;
+  const Offs& O = c_model.off;
+  const double* Ts = tile_ptr(X, c_model, k);
+  if (!all && ld_ctl(c_model, Ts).x < ST_CONVERGED) return;
+  double* Td = tile_ptr(Home, c_model, origin_x[k]);
+  {
+    const double* Gs = glob_blk(const_cast<double*>(Ts), O);
+    double* Gd = glob_blk(Td, O);
+#pragma unroll
+    for (int r = 0; r < GR_CARRY; ++r)
+      if (r != GR_BINF) st(Gd, r, ld(Gs, r));
+  }
+  const int nb = c_model.nb, nc = c_model.nc;
+  for (int j = 0; j < nb; ++j) {
+    const double* Ps = joint_blk(const_cast<double*>(Ts), O, j);
+    double* Pd = joint_blk(Td, O, j);
+    double tmp[JR_JQ];
+#pragma unroll
+    for (int r = 0; r < JR_JQ; ++r) tmp[r] = ld(Ps, r);  // v, f, F, nu, z, w, T (22 rows)
+#pragma unroll
+    for (int r = 0; r < JR_JQ; ++r) st(Pd, r, tmp[r]);
+  }
+  for (int t = 0; t < nc; ++t) {
+    const double* Ps = task_blk(const_cast<double*>(Ts), O, t);
+    double* Pd = task_blk(Td, O, t);
+#pragma unroll
+    for (int r = 0; r < TR_B; ++r) st(Pd, r, ld(Ps, r));  // y, Aty
+  }
+}
+
 // Step-by-step interface: the same sweeps, one per launch, scalars handed over through the carry rows.
-__global__ void __launch_bounds__(kBlock) k_step_backward(const StateP S, const int slot) {
-  const ModelC& c_model = c_models[slot];
+__global__ void __launch_bounds__(kBlock) k_step_backward(const __grid_constant__ ModelC c_model, const StateP S) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
   double* T = tile_ptr(S, c_model, s);
@@ -106,8 +179,7 @@ __global__ void __launch_bounds__(kBlock) k_step_backward(const StateP S, const 
   const double mu = ld(glob_blk(T, c_model.off), GR_MU);
   sweep_backward(c_model, T, mu, c_model.mu_scale * mu);
 }
-__global__ void __launch_bounds__(kBlock) k_step_forward(const StateP S, const int slot) {
-  const ModelC& c_model = c_models[slot];
+__global__ void __launch_bounds__(kBlock) k_step_forward(const __grid_constant__ ModelC c_model, const StateP S) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
   double* T = tile_ptr(S, c_model, s);
@@ -123,8 +195,7 @@ __global__ void __launch_bounds__(kBlock) k_step_forward(const StateP S, const i
   st(G, GR_NORMS + 15, cy.pres_task);
   st(G, GR_NORMS + 16, cy.pres_slack);
 }
-__global__ void __launch_bounds__(kBlock) k_step_residual(const StateP S, const int slot, const int fixed) {
-  const ModelC& c_model = c_models[slot];
+__global__ void __launch_bounds__(kBlock) k_step_residual(const __grid_constant__ ModelC c_model, const StateP S, const int fixed) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
   double* T = tile_ptr(S, c_model, s);
@@ -147,8 +218,7 @@ __global__ void __launch_bounds__(kBlock) k_step_residual(const StateP S, const 
 enum : int { RST_WZ = 1, RST_NU = 2, RST_VFF = 4, RST_YATY = 8, RST_SOLVER = 16 };
 
 // ik_id_data_.Reset / ResetRecursion (data hxx:114-154) + ResetSolver (hpp:168-186)
-__global__ void k_reset(const StateP S, const int slot, const int flags) {
-  const ModelC& c_model = c_models[slot];
+__global__ void k_reset(const __grid_constant__ ModelC c_model, const StateP S, const int flags) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
   double* T = tile_ptr(S, c_model, s);
@@ -174,8 +244,7 @@ __global__ void k_reset(const StateP S, const int slot, const int flags) {
 
 // FwdPassInit (hxx:253-283): the q-dependent part of liMi, kept as (sin q, cos q) / (q, 0) per joint.
 // q is batch-major [n][nq]; it is staged through shared memory so both the read and the write coalesce.
-__global__ void __launch_bounds__(kBlock) k_set_q(const StateP S, const int slot, const double* __restrict__ q) {
-  const ModelC& c_model = c_models[slot];
+__global__ void __launch_bounds__(kBlock) k_set_q(const __grid_constant__ ModelC c_model, const StateP S, const double* __restrict__ q) {
   extern __shared__ double sh[];
   const int nb = c_model.nb;
   const int s0 = blockIdx.x * blockDim.x;
@@ -199,8 +268,7 @@ __global__ void __launch_bounds__(kBlock) k_set_q(const StateP S, const int slot
 
 // UpdateEqConstraints (ik-id-description-optimized.hpp:127-171), per-instance part: b, Atb = A^T b, |b|inf.
 // task < 0: all tasks, bis_inf_norm reset; task >= 0: UpdateEqConstraint for that slot (:178-218), norm only grows.
-__global__ void k_set_b(const StateP S, const int slot, const double* __restrict__ b, const int per_instance, const int task) {
-  const ModelC& c_model = c_models[slot];
+__global__ void k_set_b(const __grid_constant__ ModelC c_model, const StateP S, const double* __restrict__ b, const int per_instance, const int task) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
   double* T = tile_ptr(S, c_model, s);
@@ -228,8 +296,7 @@ __global__ void k_set_b(const StateP S, const int slot, const double* __restrict
   st(G, GR_BINF, binf);
 }
 
-__global__ void k_set_bounds(const StateP S, const int slot, const double* __restrict__ lb, const double* __restrict__ ub) {
-  const ModelC& c_model = c_models[slot];
+__global__ void k_set_bounds(const __grid_constant__ ModelC c_model, const StateP S, const double* __restrict__ lb, const double* __restrict__ ub) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
   double* T = tile_ptr(S, c_model, s);
@@ -242,16 +309,14 @@ __global__ void k_set_bounds(const StateP S, const int slot, const double* __res
 }
 
 // batch-major gather of `nrows` rows: dst[s][k] = tile(s)[map[k]][lane(s)]  (map = absolute row indices).
-__global__ void __launch_bounds__(256) k_gather(const StateP S, const int slot, const int nrows, const int* __restrict__ map,
+__global__ void __launch_bounds__(256) k_gather(const __grid_constant__ ModelC c_model, const StateP S, const int nrows, const int* __restrict__ map,
                                                 double* __restrict__ dst) {
-  const ModelC& c_model = c_models[slot];
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)S.n * nrows) return;
   const int s = (int)(idx / nrows), k = (int)(idx % nrows);
   dst[idx] = tile_ptr(S, c_model, s)[(size_t)map[k] * 32];
 }
-__global__ void k_gather_limi(const StateP S, const int slot, double* __restrict__ dst) {
-  const ModelC& c_model = c_models[slot];
+__global__ void k_gather_limi(const __grid_constant__ ModelC c_model, const StateP S, double* __restrict__ dst) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
   const double* T = tile_ptr(S, c_model, s);
@@ -266,8 +331,7 @@ __global__ void k_gather_limi(const StateP S, const int slot, double* __restrict
   }
 }
 // which: 0 = iteration count, 1 = status flags (bit0 converged, bit1 primal infeasible, bit2 max_iter)
-__global__ void k_gather_ctl(const StateP S, const int slot, const int which, int* __restrict__ dst) {
-  const ModelC& c_model = c_models[slot];
+__global__ void k_gather_ctl(const __grid_constant__ ModelC c_model, const StateP S, const int which, int* __restrict__ dst) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
   const int2 c = ld_ctl(c_model, tile_ptr(S, c_model, s));
@@ -276,8 +340,7 @@ __global__ void k_gather_ctl(const StateP S, const int slot, const int which, in
                       : ((stt == ST_CONVERGED ? 1 : 0) | ((stt == ST_TAIL || stt == ST_INFEASIBLE_DONE) ? 2 : 0) | (stt == ST_MAXITER ? 4 : 0));
 }
 // out[0..2] = #converged, #infeasible, #maxiter; out[3] = sum iters
-__global__ void k_stats(const StateP S, const int slot, unsigned long long* __restrict__ out) {
-  const ModelC& c_model = c_models[slot];
+__global__ void k_stats(const __grid_constant__ ModelC c_model, const StateP S, unsigned long long* __restrict__ out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   int stt = -1, it = 0;
   if (s < S.n) { const int2 c = ld_ctl(c_model, tile_ptr(S, c_model, s)); stt = c.x; it = c.y; }
@@ -317,48 +380,33 @@ struct loik_solver {
   int nj = 0, nb = 0, nc = 0, npend = 0;
   loik_params prm{};
   ModelC mc{};          // host copy of this solver's constant block
-  ModelC mc_uploaded{}; // what was last written to the constant slot
-  bool uploaded_once = false;
-  int slot = 0;         // constant-memory slot (kConstSlots solvers can be in flight concurrently)
   bool problem_set = false;
   bool debug = false;
   double* arena = nullptr;  // tile records
   int* d_lists = nullptr;   // two compaction lists of `batch` ints
+  double* scratch[2] = {nullptr, nullptr};  // packed arenas (allocated at the first solve)
+  int* d_origin = nullptr;  // [2][batch] home slot of every packed slot
   int* d_counts = nullptr;  // [0],[1]: list lengths (ping-pong); [2]: n_active
   unsigned long long* d_stats = nullptr;
   int* h_counts = nullptr;  // pinned
   unsigned long long* h_stats = nullptr;
-  int* d_map = nullptr;  // gather map scratch (<= 36*64 ints)
+  int* d_map = nullptr;  // row maps of every loik_field (built once)
+  int map_off[32] = {0}, map_len[32] = {0};
   StateP S{};
-  cudaEvent_t ev_done = nullptr;  // recorded after the last kernel that reads this solver's constants
   // staging
   void* h_stage = nullptr; size_t h_stage_bytes = 0;
   void* d_stage = nullptr; size_t d_stage_bytes = 0;
   int64_t launches = 0;
   int64_t sweeps = 0;
   int minb = 0;
+  int dense_sweeps = 4;  // sweeps on the home arena before the first re-pack (env LOIK_DENSE)
   int last_list = -1;  // index of the list holding the most recent compaction, -1 = none
   int sweeps_in_solve = 0;
 };
 
-// Constant memory is a per-module resource: c_model[slot] is owned by one solver at a time.
-static loik_solver* g_slot_owner[kConstSlots] = {nullptr};
-static int g_next_slot = 0;
-
-// Make sure c_model[h->slot] holds h->mc before kernels of `h` are enqueued on `st`.  If another solver's
-// kernels may still be reading the slot, wait for them first (stream-ordered, no host block).
-static int upload_consts(loik_solver* h, cudaStream_t st) {
-  loik_solver* owner = g_slot_owner[h->slot];
-  const bool same = owner == h && h->uploaded_once && std::memcmp(&h->mc, &h->mc_uploaded, sizeof(ModelC)) == 0;
-  if (same) return LOIK_OK;
-  if (owner && owner != h && owner->ev_done) CK(cudaStreamWaitEvent(st, owner->ev_done, 0));
-  h->mc_uploaded = h->mc;  // stable host copy for the async transfer
-  CK(cudaMemcpyToSymbolAsync(c_models, &h->mc_uploaded, sizeof(ModelC), (size_t)h->slot * sizeof(ModelC), cudaMemcpyHostToDevice, st));
-  h->uploaded_once = true;
-  g_slot_owner[h->slot] = h;
-  return LOIK_OK;
-}
-static void mark_done(loik_solver* h, cudaStream_t st) { cudaEventRecord(h->ev_done, st); }
+// The batch-uniform block travels with every launch as a kernel parameter: nothing to upload.
+static int upload_consts(loik_solver*, cudaStream_t) { return LOIK_OK; }
+static void mark_done(loik_solver*, cudaStream_t) {}
 
 static inline int grid_for(int n, int block = kBlock) { return (n + block - 1) / block; }
 
@@ -366,7 +414,7 @@ static inline int grid_for(int n, int block = kBlock) { return (n + block - 1) /
 // kernel is compiled for: 4 -> <=255 regs/thread, 6 -> <=168, 8 -> <=128 (tuning knob, env LOIK_MINB).
 static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S, int iters, int fixed) {
   const int g = grid_for(h->batch);
-#define LOIK_LAUNCH(DBG, MB) k_iterate<DBG, MB><<<g, kBlock, 0, st>>>(S, h->slot, iters, fixed)
+#define LOIK_LAUNCH(DBG, MB) k_iterate<DBG, MB><<<g, kBlock, 0, st>>>(h->mc, S, iters, fixed)
   if (h->debug) { LOIK_LAUNCH(true, 4); }
   else if (h->minb == 4) { LOIK_LAUNCH(false, 4); }
   else if (h->minb == 6) { LOIK_LAUNCH(false, 6); }
@@ -375,8 +423,8 @@ static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S, int
   h->launches++;
 }
 
-static int ensure_stage(loik_solver* h, size_t bytes) {
-  if (bytes > h->h_stage_bytes) {
+static int ensure_stage(loik_solver* h, size_t bytes, bool need_host) {
+  if (need_host && bytes > h->h_stage_bytes) {
     if (h->h_stage) cudaFreeHost(h->h_stage);
     h->h_stage = nullptr; h->h_stage_bytes = 0;
     CK(cudaMallocHost(&h->h_stage, bytes));
@@ -395,6 +443,11 @@ static int ensure_stage(loik_solver* h, size_t bytes) {
 // pinned staging area first so the H2D copy is a true async DMA; `off` lets several inputs share it.
 static int to_device(loik_solver* h, const void* src, size_t bytes, int loc, size_t off, cudaStream_t st, const void** out) {
   if (loc == LOIK_DEVICE) { *out = src; return LOIK_OK; }
+  if (loc == LOIK_HOST_PINNED) {  // caller's buffer is page-locked: DMA straight from it, no host-side copy, no sync
+    CK(cudaMemcpyAsync((char*)h->d_stage + off, src, bytes, cudaMemcpyHostToDevice, st));
+    *out = (char*)h->d_stage + off;
+    return LOIK_OK;
+  }
   std::memcpy((char*)h->h_stage + off, src, bytes);
   CK(cudaMemcpyAsync((char*)h->d_stage + off, (char*)h->h_stage + off, bytes, cudaMemcpyHostToDevice, st));
   *out = (char*)h->d_stage + off;
@@ -442,8 +495,8 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   loik_solver* h = new loik_solver();
   h->device = device; h->batch = batch; h->ntiles = (batch + 31) / 32;
   h->nj = nj; h->nb = nj - 1; h->nc = params->num_eq_c; h->prm = *params;
-  h->slot = g_next_slot; g_next_slot = (g_next_slot + 1) % kConstSlots;
   h->minb = 4;
+  if (const char* e = std::getenv("LOIK_DENSE")) { const int v = std::atoi(e); if (v >= 0) h->dense_sweeps = v; }
   if (const char* e = std::getenv("LOIK_MINB")) { const int v = std::atoi(e); if (v == 4 || v == 6 || v == 8) h->minb = v; }
   ModelC& M = h->mc;
   std::memset(&M, 0, sizeof(M));
@@ -486,10 +539,56 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   cudaMalloc(&h->d_counts, 4 * sizeof(int));
   cudaMemset(h->d_counts, 0, 4 * sizeof(int));
   cudaMalloc(&h->d_stats, 4 * sizeof(unsigned long long));
-  cudaMalloc(&h->d_map, 64 * LOIK_MAX_JOINTS * sizeof(int));
+  {  // row maps of the gettable fields: field -> absolute rows of the tile record, in output order
+    std::vector<int> all;
+    const int ncq = h->nc;
+    auto per_joint = [&](std::vector<int>& m, int jr, int width) { for (int j = 0; j < nb; ++j) for (int c = 0; c < width; ++c) m.push_back(O.joint0 + JR_ROWS * j + jr + c); };
+    auto per_task = [&](std::vector<int>& m, int tr) { for (int k = 0; k < ncq; ++k) for (int c = 0; c < 6; ++c) m.push_back(O.task0 + TR_ROWS * k + tr + c); };
+    auto span = [&](std::vector<int>& m, int r0, int n) { for (int c = 0; c < n; ++c) m.push_back(r0 + c); };
+    for (int field = 0; field <= LOIK_F_DUAL_RES_VEC; ++field) {
+      std::vector<int> m;
+      switch (field) {
+        case LOIK_F_Z: per_joint(m, JR_Z, 1); break;
+        case LOIK_F_NU: per_joint(m, JR_NU, 1); break;
+        case LOIK_F_W: per_joint(m, JR_W, 1); break;
+        case LOIK_F_Y: per_task(m, TR_Y); break;
+        case LOIK_F_V: per_joint(m, JR_V, 6); break;
+        case LOIK_F_F: per_joint(m, JR_F, 6); break;
+        case LOIK_F_ATY: per_task(m, TR_ATY); break;
+        case LOIK_F_FDPA: per_joint(m, JR_FD, 6); break;
+        case LOIK_F_STF_PLUS_W: per_joint(m, JR_T, 1); break;
+        case LOIK_F_P: per_joint(m, JR_P, 6); break;
+        case LOIK_F_UDINV: per_joint(m, JR_UD, 6); break;
+        case LOIK_F_DINV: per_joint(m, JR_DINV, 1); break;
+        case LOIK_F_R: per_joint(m, JR_R, 1); break;
+        case LOIK_F_MU: span(m, O.glob + GR_MU, 1); break;
+        case LOIK_F_RESIDUALS: span(m, O.glob + GR_RES, 4); break;
+        case LOIK_F_NORMS: span(m, O.glob + GR_NORMS, LOIK_NUM_NORMS); break;
+        case LOIK_F_PRIMAL_RES_VEC: span(m, O.prv, 7 * nb); break;
+        case LOIK_F_DUAL_RES_VEC: span(m, O.drv, 7 * nb); break;
+        case LOIK_F_H:  // expand the 21 stored scalars of each joint to a full symmetric 6x6
+          for (int j = 0; j < nb; ++j)
+            for (int a = 0; a < 6; ++a)
+              for (int c = 0; c < 6; ++c) {
+                int r;
+                if (a < 3 && c < 3) r = si(a, c);
+                else if (a >= 3 && c >= 3) r = 15 + si(a - 3, c - 3);
+                else if (a < 3) r = 6 + 3 * a + (c - 3);
+                else r = 6 + 3 * c + (a - 3);
+                m.push_back(O.joint0 + JR_ROWS * j + JR_H + r);
+              }
+          break;
+        default: break;
+      }
+      h->map_off[field] = (int)all.size();
+      h->map_len[field] = (int)m.size();
+      all.insert(all.end(), m.begin(), m.end());
+    }
+    cudaMalloc(&h->d_map, std::max<size_t>(all.size(), 1) * sizeof(int));
+    cudaMemcpy(h->d_map, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice);
+  }
   cudaMallocHost(&h->h_counts, 4 * sizeof(int));
   cudaMallocHost(&h->h_stats, 4 * sizeof(unsigned long long));
-  cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
   h->S.arena = h->arena; h->S.n = batch; h->S.list = nullptr; h->S.n_list = nullptr; h->S.n_active = nullptr;
   if (cudaGetLastError() != cudaSuccess) { loik_destroy(h); return fail(LOIK_ERR_CUDA, "loik_create: allocation failed"); }
   *out = h;
@@ -500,19 +599,17 @@ void loik_destroy(loik_solver* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  cudaFree(h->arena); cudaFree(h->d_lists); cudaFree(h->d_counts); cudaFree(h->d_stats); cudaFree(h->d_map);
+  cudaFree(h->arena); cudaFree(h->scratch[0]); cudaFree(h->scratch[1]); cudaFree(h->d_origin); cudaFree(h->d_lists); cudaFree(h->d_counts); cudaFree(h->d_stats); cudaFree(h->d_map);
   cudaFreeHost(h->h_counts); cudaFreeHost(h->h_stats);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->d_stage) cudaFree(h->d_stage);
-  if (h->ev_done) cudaEventDestroy(h->ev_done);
-  for (int i = 0; i < kConstSlots; ++i) if (g_slot_owner[i] == h) g_slot_owner[i] = nullptr;
   delete h;
 }
 
 static int launch_reset(loik_solver* h, int flags, cudaStream_t st) {
   int rc = upload_consts(h, st);
   if (rc) return rc;
-  k_reset<<<grid_for(h->batch, 128), 128, 0, st>>>(h->S, h->slot, flags);
+  k_reset<<<grid_for(h->batch, 128), 128, 0, st>>>(h->mc, h->S, flags);
   h->launches++;
   h->last_list = -1;
   h->sweeps_in_solve = 0;
@@ -567,15 +664,11 @@ int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const 
   const size_t q_bytes = (size_t)B * nb * sizeof(double);
   const size_t b_bytes = (size_t)(b_per_instance ? B : 1) * nc * 6 * sizeof(double);
   const size_t bd_bytes = (size_t)(bounds_per_instance ? B : 1) * nb * sizeof(double);
-  // shared bounds are small: read them on the host (they go to constant memory)
-  std::vector<double> lbh(nb), ubh(nb);
-  if (!bounds_per_instance) {
-    if (loc == LOIK_HOST) { std::memcpy(lbh.data(), lb, bd_bytes); std::memcpy(ubh.data(), ub, bd_bytes); }
-    else { CK(cudaMemcpyAsync(lbh.data(), lb, bd_bytes, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(ubh.data(), ub, bd_bytes, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
-  }
-  int rc = set_problem_consts(h, H_ref, v_ref, n_ids, ids, A, lbh.data(), ubh.data(), !bounds_per_instance);
+  if (loc != LOIK_HOST && loc != LOIK_DEVICE && loc != LOIK_HOST_PINNED) return fail(LOIK_ERR_INVALID, "loik_solve_init: bad loc");
+  // batch-shared bounds are batch-uniform data like H_ref: always host pointers, they travel in the kernel parameter block
+  int rc = set_problem_consts(h, H_ref, v_ref, n_ids, ids, A, lb, ub, !bounds_per_instance);
   if (rc) return rc;
-  if (loc == LOIK_HOST) { rc = ensure_stage(h, q_bytes + b_bytes + 2 * bd_bytes + 64); if (rc) return rc; }
+  if (loc != LOIK_DEVICE) { rc = ensure_stage(h, q_bytes + b_bytes + 2 * bd_bytes + 64, loc == LOIK_HOST); if (rc) return rc; }
   rc = upload_consts(h, st);
   if (rc) return rc;
   const void *dq, *db = nullptr, *dlb = nullptr, *dub = nullptr;
@@ -588,13 +681,13 @@ int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const 
   }
   // ik_id_data_.Reset(warm_start) + ResetSolver() + FwdPassInit's y/Aty wipe (hpp:346-359, hxx:270-278)
   const int flags = RST_SOLVER | (h->prm.warm_start ? 0 : (RST_WZ | RST_NU | RST_VFF | RST_YATY));
-  k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->S, h->slot, flags);
-  k_set_q<<<grid_for(B), kBlock, kBlock * nb * sizeof(double), st>>>(h->S, h->slot, (const double*)dq);
+  k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, flags);
+  k_set_q<<<grid_for(B), kBlock, kBlock * nb * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);
   h->launches += 2;
   h->last_list = -1;
-  if (nc > 0) { k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->S, h->slot, (const double*)db, b_per_instance, -1); h->launches++; }
+  if (nc > 0) { k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)db, b_per_instance, -1); h->launches++; }
   if (bounds_per_instance) {
-    k_set_bounds<<<grid_for(B, 128), 128, 0, st>>>(h->S, h->slot, (const double*)dlb, (const double*)dub);
+    k_set_bounds<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)dlb, (const double*)dub);
     h->launches++;
   }
   CK(cudaGetLastError());
@@ -624,7 +717,7 @@ static int compact(loik_solver* h, cudaStream_t st) {
   const int in = h->last_list, outi = in < 0 ? 0 : 1 - in;
   int* list_out = h->d_lists + (size_t)outi * B;
   CK(cudaMemsetAsync(h->d_counts + outi, 0, sizeof(int), st));
-  k_compact<<<grid_for(B, 256), 256, 0, st>>>(h->S, h->slot, in < 0 ? nullptr : h->d_lists + (size_t)in * B,
+  k_compact<<<grid_for(B, 256), 256, 0, st>>>(h->mc, h->S, in < 0 ? nullptr : h->d_lists + (size_t)in * B,
                                               in < 0 ? nullptr : h->d_counts + in, list_out, h->d_counts + outi);
   h->launches++;
   h->last_list = outi;
@@ -632,37 +725,54 @@ static int compact(loik_solver* h, cudaStream_t st) {
 }
 
 // The main loop of Solve() (hpp:377-454) over the whole batch, enqueued as a fixed schedule of launches with NO
-// host round trip: a few dense sweeps while (almost) every instance is active, then compaction + list-mode
-// launches of geometrically growing iteration counts.  Per-instance loop control lives on the device, so
-// finished instances are frozen and launches past global convergence find an empty list.  `budget` = ADMM
-// iterations any instance may still need (max_iter for a fresh solve).
+// host round trip.  Per-instance loop control lives on the device (finished instances are frozen), so the
+// schedule only has to cover `budget` = max_iter sweeps.
+//   1. a few dense sweeps on the home arena while (almost) every instance is active;
+//   2. then, repeatedly: compact the still-active slots, physically re-pack them into the dense prefix of a
+//      scratch arena (full tiles, coalesced rows), retire the finished ones to their home slots, and sweep the
+//      packed arena for a geometrically growing number of iterations;
+//   3. retire whatever is left.  Launches past global convergence find a zero count and exit at once.
+static int ensure_scratch(loik_solver* h) {
+  if (h->scratch[0]) return LOIK_OK;
+  const size_t bytes = (size_t)h->ntiles * h->mc.off.rows * 32 * sizeof(double);
+  for (int i = 0; i < 2; ++i) CK(cudaMalloc(&h->scratch[i], bytes));
+  CK(cudaMalloc(&h->d_origin, 2 * (size_t)h->batch * sizeof(int)));
+  return LOIK_OK;
+}
+
 static int run_schedule(loik_solver* h, cudaStream_t st, int budget) {
-  int rc = upload_consts(h, st);
+  int rc = ensure_scratch(h);
   if (rc) return rc;
   const int B = h->batch;
   int done = 0;
-  // dense phase
-  const int dense = std::min(budget, 3);
+  const int dense = std::min(budget, h->dense_sweeps);
   if (dense > 0) {
     launch_iterate(h, st, h->S, dense, 0);
     h->sweeps += dense; done += dense;
   }
+  int cur = -1;  // -1 = home arena, else scratch index
+  StateP X = h->S;
   int chunk = 1, reps = 0;
   while (done < budget) {
-    rc = compact(h, st);
-    if (rc) return rc;
-    StateP S = h->S;
-    S.list = h->d_lists + (size_t)h->last_list * B;
-    S.n_list = h->d_counts + h->last_list;
+    const int y = cur < 0 ? 0 : 1 - cur;
+    int* list = h->d_lists;  // one list suffices: it is consumed by the re-pack right away
+    CK(cudaMemsetAsync(h->d_counts + y, 0, sizeof(int), st));
+    k_compact<<<grid_for(B, 256), 256, 0, st>>>(h->mc, X, nullptr, nullptr, list, h->d_counts + y);
+    StateP Y = h->S;
+    Y.arena = h->scratch[y]; Y.n_dev = h->d_counts + y;
+    const int* origin_x = cur < 0 ? nullptr : h->d_origin + (size_t)cur * B;
+    k_repack<<<grid_for(B, 128), 128, 0, st>>>(h->mc, X, list, h->d_counts + y, origin_x, Y, h->d_origin + (size_t)y * B);
+    h->launches += 2;
+    if (cur >= 0) { k_retire<<<grid_for(B, 128), 128, 0, st>>>(h->mc, X, origin_x, h->S, 0); h->launches++; }
+    cur = y; X = Y;
     const int c = std::min(chunk, budget - done);
-    launch_iterate(h, st, S, c, 0);
+    launch_iterate(h, st, X, c, 0);
     h->sweeps += c; done += c;
     if (++reps == 2) { reps = 0; if (chunk < 64) chunk *= 2; }
   }
-  // leave the number of still-active instances (0 after a complete schedule) in d_counts[2]
-  CK(cudaMemsetAsync(h->d_counts + 2, 0, sizeof(int), st));
+  if (cur >= 0) { k_retire<<<grid_for(B, 128), 128, 0, st>>>(h->mc, X, h->d_origin + (size_t)cur * B, h->S, 1); h->launches++; }
+  CK(cudaMemsetAsync(h->d_counts + 2, 0, sizeof(int), st));  // nothing is active after a complete schedule
   CK(cudaGetLastError());
-  mark_done(h, st);
   return LOIK_OK;
 }
 
@@ -723,15 +833,15 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
   sym_blocks(AtA, T.AtA_A, T.AtA_B, T.AtA_D);
   const int B = h->batch, nb = h->nb;
   const size_t q_bytes = (size_t)B * nb * sizeof(double), b_bytes = (size_t)(b_per_instance ? B : 1) * 6 * sizeof(double);
-  if (loc == LOIK_HOST) { rc = ensure_stage(h, q_bytes + b_bytes + 64); if (rc) return rc; }
+  if (loc != LOIK_DEVICE) { rc = ensure_stage(h, q_bytes + b_bytes + 64, loc == LOIK_HOST); if (rc) return rc; }
   rc = upload_consts(h, st); if (rc) return rc;
   const void *dq, *db;
   rc = to_device(h, q, q_bytes, loc, 0, st, &dq); if (rc) return rc;
   rc = to_device(h, bi, b_bytes, loc, q_bytes, st, &db); if (rc) return rc;
   const int flags = RST_SOLVER | (h->prm.warm_start ? 0 : (RST_WZ | RST_NU | RST_VFF | RST_YATY));
-  k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->S, h->slot, flags);
-  k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->S, h->slot, (const double*)db, b_per_instance, k);
-  k_set_q<<<grid_for(B), kBlock, kBlock * nb * sizeof(double), st>>>(h->S, h->slot, (const double*)dq);
+  k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, flags);
+  k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)db, b_per_instance, k);
+  k_set_q<<<grid_for(B), kBlock, kBlock * nb * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);
   h->launches += 3;
   h->last_list = -1;
   CK(cudaGetLastError());
@@ -805,9 +915,9 @@ int loik_step(loik_solver* h, int32_t step_id, void* stream) {
   if (rc) return rc;
   const int g = grid_for(h->batch);
   switch (step_id) {
-    case LOIK_STEP_BACKWARD: k_step_backward<<<g, kBlock, 0, st>>>(h->S, h->slot); break;
-    case LOIK_STEP_FORWARD: k_step_forward<<<g, kBlock, 0, st>>>(h->S, h->slot); break;
-    case LOIK_STEP_RESIDUAL: k_step_residual<<<g, kBlock, 0, st>>>(h->S, h->slot, 0); h->sweeps++; break;
+    case LOIK_STEP_BACKWARD: k_step_backward<<<g, kBlock, 0, st>>>(h->mc, h->S); break;
+    case LOIK_STEP_FORWARD: k_step_forward<<<g, kBlock, 0, st>>>(h->mc, h->S); break;
+    case LOIK_STEP_RESIDUAL: k_step_residual<<<g, kBlock, 0, st>>>(h->mc, h->S, 0); h->sweeps++; break;
     default: return fail(LOIK_ERR_INVALID, "loik_step: unknown step id");
   }
   h->launches++;
@@ -830,60 +940,20 @@ int loik_get(loik_solver* h, int32_t field, void* dst, int32_t loc, void* stream
   if (rc) return rc;
   const int B = h->batch, nb = h->nb, nc = h->nc;
   const Offs& O = h->mc.off;
-  int rows = 0;
-  std::vector<int> map;
-  bool is_int = false;
-  auto per_joint = [&](int jr, int width) { for (int j = 0; j < nb; ++j) for (int c = 0; c < width; ++c) map.push_back(O.joint0 + JR_ROWS * j + jr + c); };
-  auto per_task = [&](int tr) { for (int k = 0; k < nc; ++k) for (int c = 0; c < 6; ++c) map.push_back(O.task0 + TR_ROWS * k + tr + c); };
-  auto span = [&](int r0, int n) { for (int c = 0; c < n; ++c) map.push_back(r0 + c); };
-  switch (field) {
-    case LOIK_F_Z: per_joint(JR_Z, 1); break;
-    case LOIK_F_NU: per_joint(JR_NU, 1); break;
-    case LOIK_F_W: per_joint(JR_W, 1); break;
-    case LOIK_F_Y: per_task(TR_Y); break;
-    case LOIK_F_V: per_joint(JR_V, 6); break;
-    case LOIK_F_F: per_joint(JR_F, 6); break;
-    case LOIK_F_ATY: per_task(TR_ATY); break;
-    case LOIK_F_FDPA: per_joint(JR_FD, 6); break;
-    case LOIK_F_STF_PLUS_W: per_joint(JR_T, 1); break;
-    case LOIK_F_P: per_joint(JR_P, 6); break;
-    case LOIK_F_UDINV: per_joint(JR_UD, 6); break;
-    case LOIK_F_DINV: per_joint(JR_DINV, 1); break;
-    case LOIK_F_R: per_joint(JR_R, 1); break;
-    case LOIK_F_MU: span(O.glob + GR_MU, 1); break;
-    case LOIK_F_RESIDUALS: span(O.glob + GR_RES, 4); break;
-    case LOIK_F_NORMS: span(O.glob + GR_NORMS, LOIK_NUM_NORMS); break;
-    case LOIK_F_PRIMAL_RES_VEC: span(O.prv, 7 * nb); break;
-    case LOIK_F_DUAL_RES_VEC: span(O.drv, 7 * nb); break;
-    case LOIK_F_H:  // expand the 21 stored scalars of each joint to a full symmetric 6x6
-      for (int j = 0; j < nb; ++j)
-        for (int a = 0; a < 6; ++a)
-          for (int c = 0; c < 6; ++c) {
-            int r;
-            if (a < 3 && c < 3) r = si(a, c);
-            else if (a >= 3 && c >= 3) r = 15 + si(a - 3, c - 3);
-            else if (a < 3) r = 6 + 3 * a + (c - 3);
-            else r = 6 + 3 * c + (a - 3);
-            map.push_back(O.joint0 + JR_ROWS * j + JR_H + r);
-          }
-      break;
-    case LOIK_F_LIMI: rows = 12 * nb; break;
-    case LOIK_F_ITER: case LOIK_F_STATUS: is_int = true; rows = 1; break;
-    default: return fail(LOIK_ERR_INVALID, "loik_get: unknown field");
-  }
-  if (!map.empty()) rows = (int)map.size();
+  if (field < 0 || field > LOIK_F_DUAL_RES_VEC) return fail(LOIK_ERR_INVALID, "loik_get: unknown field");
+  const bool is_int = field == LOIK_F_ITER || field == LOIK_F_STATUS;
+  const int rows = is_int ? 1 : (field == LOIK_F_LIMI ? 12 * nb : h->map_len[field]);
+  (void)nc; (void)O;
   const size_t bytes = (size_t)B * rows * (is_int ? sizeof(int) : sizeof(double));
   void* ddst = dst;
-  if (loc == LOIK_HOST) { rc = ensure_stage(h, bytes); if (rc) return rc; ddst = h->d_stage; }
+  if (loc != LOIK_DEVICE) { rc = ensure_stage(h, bytes, loc == LOIK_HOST); if (rc) return rc; ddst = h->d_stage; }
   if (field == LOIK_F_LIMI) {
-    k_gather_limi<<<grid_for(B, 128), 128, 0, st>>>(h->S, h->slot, (double*)ddst);
+    k_gather_limi<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (double*)ddst);
   } else if (is_int) {
-    k_gather_ctl<<<grid_for(B, 128), 128, 0, st>>>(h->S, h->slot, field == LOIK_F_ITER ? 0 : 1, (int*)ddst);
+    k_gather_ctl<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, field == LOIK_F_ITER ? 0 : 1, (int*)ddst);
   } else {
-    CK(cudaMemcpyAsync(h->d_map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));  // `map` is a local
     const size_t total = (size_t)B * rows;
-    k_gather<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->S, h->slot, rows, h->d_map, (double*)ddst);
+    k_gather<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->mc, h->S, rows, h->d_map + h->map_off[field], (double*)ddst);
   }
   h->launches++;
   CK(cudaGetLastError());
@@ -892,6 +962,8 @@ int loik_get(loik_solver* h, int32_t field, void* dst, int32_t loc, void* stream
     CK(cudaMemcpyAsync(h->h_stage, ddst, bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     std::memcpy(dst, h->h_stage, bytes);
+  } else if (loc == LOIK_HOST_PINNED) {
+    CK(cudaMemcpyAsync(dst, ddst, bytes, cudaMemcpyDeviceToHost, st));  // caller synchronizes the stream before reading
   }
   return LOIK_OK;
 }
@@ -903,11 +975,23 @@ int loik_get_stats(loik_solver* h, int64_t out[5]) {
   int rc = upload_consts(h, 0);
   if (rc) return rc;
   CK(cudaMemset(h->d_stats, 0, 4 * sizeof(unsigned long long)));
-  k_stats<<<grid_for(h->ntiles * 32, 128), 128>>>(h->S, h->slot, h->d_stats);
+  k_stats<<<grid_for(h->ntiles * 32, 128), 128>>>(h->mc, h->S, h->d_stats);
   h->launches++;
   CK(cudaMemcpy(h->h_stats, h->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 4; ++i) out[i] = (int64_t)h->h_stats[i];
   out[4] = h->sweeps;
+  return LOIK_OK;
+}
+
+int loik_reduce_stats(loik_solver* h, void* stream, void** dev_ptr) {
+  if (!h || !dev_ptr) return fail(LOIK_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), st));
+  k_stats<<<grid_for(h->ntiles * 32, 128), 128, 0, st>>>(h->mc, h->S, h->d_stats);
+  h->launches++;
+  CK(cudaGetLastError());
+  *dev_ptr = h->d_stats;
   return LOIK_OK;
 }
 

@@ -1,21 +1,24 @@
 """Batch-sharded multi-GPU driver.
 
 Problem instances are independent, so each rank (one process per GPU, torchrun) owns a contiguous slice of
-the global batch and runs the same kernels on it; no tensor ever crosses NVLink.  The only collective is the
-all-reduce (SUM) of the still-active instance count that decides the *global* stop: one int32 per chunk of
-ADMM iterations.  Converged instances are frozen on device, so running a few extra sweeps past a rank's own
-convergence never changes a result.
+the global batch and runs the same kernels on it; no tensor ever crosses NVLink.  Loop control is per
+instance and lives on the device (converged instances are frozen), so a rank never has to wait for another
+rank's instances.  The only collective is ONE all-reduce (SUM) per solve of four int64 -- the global stopping-
+criterion outcome {#converged, #primal infeasible, #stopped at max_iter, total iterations} -- which every rank
+needs to report the same global status.  A chunked variant (`solve_chunked`) that all-reduces the still-active
+count every few sweeps and stops all ranks as soon as the global count reaches zero is kept for callers that
+want the early global exit.
 """
 from __future__ import annotations
 
 import torch
 
 
-class _DevInt:
-    """Zero-copy view of the library's device-resident active counter."""
+class _DevArray:
+    """Zero-copy view of a device buffer owned by the library."""
 
-    def __init__(self, ptr: int):
-        self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 def shard_range(global_batch: int, rank: int, world: int) -> tuple[int, int]:
@@ -25,38 +28,40 @@ def shard_range(global_batch: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def global_stop(active_local: torch.Tensor, world: int) -> int:
-    """SUM all-reduce of the active count; returns the global number of still-active instances."""
+def all_reduce_sum(t: torch.Tensor, world: int) -> torch.Tensor:
     if world > 1:
         import torch.distributed as dist
-        dist.all_reduce(active_local, op=dist.ReduceOp.SUM)
-    return int(active_local.item())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
 
 
 class ShardedSolver:
-    def __init__(self, solver, world: int, chunk: int = 4):
+    def __init__(self, solver, world: int, chunk: int = 8):
         self.S, self.world, self.chunk = solver, world, chunk
         self._active = None
+        self._stats = None
 
-    def solve(self) -> int:
-        """Solve() on every rank's shard; returns the number of ADMM sweeps launched."""
+    def solve(self) -> torch.Tensor:
+        """Solve() on this rank's shard (asynchronous) + the single all-reduce of the global outcome.
+        Returns a device tensor of 4 int64 (global counts); reading it synchronizes."""
         S = self.S
-        if self.world == 1:
-            S.Solve()
-            return 0
+        S.Solve()
+        ptr = S.reduce_stats_ptr()
+        if self._stats is None:
+            self._stats = torch.as_tensor(_DevArray(ptr, 4, "<i8"), device=f"cuda:{S.device}")
+        return all_reduce_sum(self._stats, self.world)
+
+    def solve_chunked(self) -> int:
+        """Chunks of ADMM sweeps interleaved with the all-reduce of the active count; global early exit."""
+        S = self.S
         if self._active is None:
-            self._active = torch.as_tensor(_DevInt(S.active_count_ptr()), device=f"cuda:{S.device}")
+            self._active = torch.as_tensor(_DevArray(S.active_count_ptr(), 1, "<i4"), device=f"cuda:{S.device}")
         S.SolveBegin()
-        done = 0
-        limit = self.max_iter
+        done, limit = 0, int(S.max_iter)
         while done < limit:
             k = min(self.chunk, limit - done)
             S.SolveChunk(k)
             done += k
-            if global_stop(self._active, self.world) == 0:
+            if int(all_reduce_sum(self._active, self.world).item()) == 0:
                 break
         return done
-
-    @property
-    def max_iter(self) -> int:
-        return int(self.S.max_iter)

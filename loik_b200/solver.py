@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libloik_b200.so")
 _lib = None
 
-LOIK_HOST, LOIK_DEVICE = 0, 1
+LOIK_HOST, LOIK_DEVICE, LOIK_HOST_PINNED = 0, 1, 2
 
 # loik_field (include/loik_b200.h)
 (F_Z, F_NU, F_W, F_Y, F_V, F_F, F_ATY, F_FDPA, F_STF_PLUS_W, F_H, F_P, F_UDINV, F_DINV, F_R, F_LIMI, F_MU, F_ITER,
@@ -38,7 +38,7 @@ NORM_NAMES = ["bT_delta_y_plus", "bT_delta_y_minus", "Av_inf_norm", "nu_inf_norm
 
 EXPORTS = ["loik_abi_version", "loik_last_error", "loik_create", "loik_destroy", "loik_solve_init",
            "loik_update_references", "loik_solve", "loik_solve_full", "loik_solve_task", "loik_iterate_fixed",
-           "loik_reset_recursion", "loik_step", "loik_set_debug", "loik_get", "loik_get_stats", "loik_launch_count",
+           "loik_reset_recursion", "loik_step", "loik_set_debug", "loik_get", "loik_get_stats", "loik_reduce_stats", "loik_launch_count",
            "loik_set_max_iter", "loik_set_rho", "loik_set_mu", "loik_set_tol_tail_solve", "loik_set_warm_start",
            "loik_active_count_device_ptr", "loik_solve_begin", "loik_solve_chunk", "loik_solve_end"]
 
@@ -85,6 +85,7 @@ def load_library(path: str | None = None):
     lib.loik_set_debug.argtypes = [vp, i32]
     lib.loik_get.argtypes = [vp, i32, vp, i32, vp]
     lib.loik_get_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.loik_reduce_stats.argtypes = [vp, vp, C.POINTER(vp)]
     lib.loik_launch_count.argtypes = [vp]
     lib.loik_launch_count.restype = C.c_int64
     lib.loik_set_max_iter.argtypes = [vp, i32]
@@ -126,7 +127,7 @@ class _Buf:
                 x = x.to(want).contiguous()
             self.obj = x
             self.ptr = x.data_ptr()
-            self.loc = LOIK_DEVICE if x.is_cuda else LOIK_HOST
+            self.loc = LOIK_DEVICE if x.is_cuda else (LOIK_HOST_PINNED if x.is_pinned() else LOIK_HOST)
             self.shape = tuple(x.shape)
         else:
             a = np.ascontiguousarray(x, dtype=dtype)
@@ -217,14 +218,8 @@ class FirstOrderLoikOptimized:
         if len(locs) != 1:
             raise RuntimeError("q, bis (and per-instance bounds) must all be host arrays or all be CUDA tensors")
         loc = locs.pop()
-        if not bd_per and lbb.loc != LOIK_HOST:
-            import torch
+        if not bd_per and lbb.loc == LOIK_DEVICE:  # batch-shared bounds are always read on the host
             lbb, ubb = _Buf(lbb.obj.cpu().numpy()), _Buf(ubb.obj.cpu().numpy())
-        if not bd_per and loc == LOIK_DEVICE:
-            # shared bounds are read on the host by the library when loc==HOST; give it device copies otherwise
-            import torch
-            lbb = _Buf(torch.as_tensor(lbb.obj, device=f"cuda:{self.device}"))
-            ubb = _Buf(torch.as_tensor(ubb.obj, device=f"cuda:{self.device}"))
         keep = (qb, H, vr, ids, A, bb, lbb, ubb)
         args = (qb.ptr, H.ptr, vr.ptr, int(ids.shape[0]), ids.ctypes.data, A.ptr, bb.ptr, b_per, lbb.ptr, ubb.ptr,
                 bd_per, loc, _current_stream())
@@ -387,6 +382,12 @@ class FirstOrderLoikOptimized:
         out = (C.c_int64 * 5)()
         self._check(self._lib.loik_get_stats(self._h, out))
         return dict(converged=out[0], primal_infeasible=out[1], max_iter=out[2], total_iters=out[3], sweeps=out[4])
+
+    def reduce_stats_ptr(self) -> int:
+        """Enqueue the status reduction on the current stream; device pointer to 4 int64 (see loik_reduce_stats)."""
+        p = C.c_void_p()
+        self._check(self._lib.loik_reduce_stats(self._h, _current_stream(), C.byref(p)))
+        return int(p.value)
 
     def launch_count(self) -> int:
         return int(self._lib.loik_launch_count(self._h))

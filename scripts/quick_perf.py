@@ -44,3 +44,33 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def pipelined(name="panda", depths=(1, 2, 4, 8)):
+    """Throughput with D solver handles in flight on D streams (tail of one batch overlaps the bulk of the next)."""
+    model = robots.get_robot(name)
+    B = int(os.environ.get("BATCH", {"panda": 65536, "ur10": 262144, "talos": 16384}[name]))
+    pb = problems.random_batch(model, B, seed=0)
+    nc = len(pb["ids"])
+    for D in depths:
+        Ss = [lk.make_solver(model, problems.bench_params(nc), B) for _ in range(D)]
+        streams = [torch.cuda.Stream() for _ in range(D)]
+        for S in Ss:
+            S.SolveInit(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
+        torch.cuda.synchronize()
+        steps = 4 * D
+        for rep in range(2):
+            t0 = time.perf_counter()
+            for i in range(steps):
+                with torch.cuda.stream(streams[i % D]):
+                    Ss[i % D].Solve()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        print(f"{name} pipeline depth {D}: {dt/steps*1e3:.3f} ms/solve, {B*steps/dt/1e6:.2f} M solves/s")
+        for S in Ss:
+            S.close()
+
+
+if __name__ == "__main__" and os.environ.get("PIPE"):
+    for nm in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["panda"]):
+        pipelined(nm)
