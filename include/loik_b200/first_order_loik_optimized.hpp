@@ -1,0 +1,188 @@
+// first_order_loik_optimized.hpp -- header-only C++ facade over the C ABI of libloik_b200.so with the shape of
+// loik::FirstOrderLoikOptimizedTpl<double> (/root/reference/include/loik/loik-loid-optimized.hpp:22): same
+// constructor argument order (:129-134), same SolveInit / Solve() / Solve(q,...) / Solve(q, c_id, Ai, bi) entry points
+// (:335-338, :368, :475-478, :596-597), same getters (task-solver-base.hpp:87-141), same failure mode (C ABI error codes
+// are re-thrown as std::runtime_error with the reference's messages).
+//
+// Differences, all forced by batching: vectors carry a leading batch dimension (row-major, one row per instance),
+// the caller-owned IkIdData of the reference lives in HBM inside the handle (read it back with z(), nu(), w() ...),
+// and the model is the flat table `loik_b200::Model` below.  With Pinocchio available, `loik_b200::Model` is filled
+// from a pinocchio::Model by `from_pinocchio()` (compile with -DLOIK_B200_WITH_PINOCCHIO; not compilable in the
+// offline build container, reviewed by eye -- SURVEY.md section 7 step 10).
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../loik_b200.h"
+
+#ifdef LOIK_B200_WITH_PINOCCHIO
+#include <pinocchio/multibody/model.hpp>
+#endif
+
+namespace loik_b200 {
+
+enum ADMMPenaltyUpdateStrat { DEFAULT = LOIK_MU_DEFAULT, OSQP = LOIK_MU_OSQP, MAXEIGENVALUE = LOIK_MU_MAXEIGENVALUE };
+
+// What the hot path reads from pinocchio::Model (loik-loid-optimized.hxx:46-47,258-265).
+struct Model {
+  int njoints = 0;  // incl. universe
+  int nv = 0;
+  std::vector<int32_t> parents, joint_types;
+  std::vector<double> joint_axes;   // [njoints][3]
+  std::vector<double> placement_R;  // [njoints][9] row-major
+  std::vector<double> placement_p;  // [njoints][3]
+};
+
+#ifdef LOIK_B200_WITH_PINOCCHIO
+// pinocchio::Model -> flat tables.  Only 1-DoF revolute / prismatic joints (aligned or unaligned) are supported.
+inline Model from_pinocchio(const pinocchio::Model& m) {
+  Model out;
+  out.njoints = m.njoints; out.nv = m.nv;
+  out.parents.assign(m.njoints, 0); out.joint_types.assign(m.njoints, 0);
+  out.joint_axes.assign(3 * m.njoints, 0.0); out.placement_R.assign(9 * m.njoints, 0.0); out.placement_p.assign(3 * m.njoints, 0.0);
+  for (int i = 0; i < m.njoints; ++i) {
+    out.parents[i] = static_cast<int32_t>(m.parents[i]);
+    const auto& M = m.jointPlacements[i];
+    for (int r = 0; r < 3; ++r) { out.placement_p[3 * i + r] = M.translation()[r]; for (int c = 0; c < 3; ++c) out.placement_R[9 * i + 3 * r + c] = M.rotation()(r, c); }
+    if (i == 0) { out.joint_axes[2] = 1.0; continue; }
+    const std::string s = m.joints[i].shortname();
+    double ax[3] = {0, 0, 0};
+    int code = -1;
+    if (s == "JointModelRX") { code = LOIK_JOINT_RX; ax[0] = 1; }
+    else if (s == "JointModelRY") { code = LOIK_JOINT_RY; ax[1] = 1; }
+    else if (s == "JointModelRZ") { code = LOIK_JOINT_RZ; ax[2] = 1; }
+    else if (s == "JointModelPX") { code = LOIK_JOINT_PX; ax[0] = 1; }
+    else if (s == "JointModelPY") { code = LOIK_JOINT_PY; ax[1] = 1; }
+    else if (s == "JointModelPZ") { code = LOIK_JOINT_PZ; ax[2] = 1; }
+    else if (s == "JointModelRevoluteUnaligned") {
+      code = LOIK_JOINT_RU;
+      const auto& a = boost::get<pinocchio::JointModelRevoluteUnaligned>(m.joints[i].toVariant()).axis;
+      ax[0] = a[0]; ax[1] = a[1]; ax[2] = a[2];
+    } else if (s == "JointModelPrismaticUnaligned") {
+      code = LOIK_JOINT_PU;
+      const auto& a = boost::get<pinocchio::JointModelPrismaticUnaligned>(m.joints[i].toVariant()).axis;
+      ax[0] = a[0]; ax[1] = a[1]; ax[2] = a[2];
+    } else {
+      throw std::runtime_error("loik_b200::from_pinocchio: unsupported joint type " + s);
+    }
+    if (m.joints[i].idx_v() != i - 1 || m.joints[i].idx_q() != i - 1)
+      throw std::runtime_error("loik_b200::from_pinocchio: only models with idx_q == idx_v == joint_id - 1 are supported");
+    out.joint_types[i] = code;
+    for (int c = 0; c < 3; ++c) out.joint_axes[3 * i + c] = ax[c];
+  }
+  return out;
+}
+#endif
+
+class FirstOrderLoikOptimized {
+ public:
+  // loik-loid-optimized.hpp:129-134 (+ batch, device; ik_id_data lives in the handle)
+  FirstOrderLoikOptimized(int max_iter, double tol_abs, double tol_rel, double tol_primal_inf, double tol_dual_inf, double rho,
+                          double mu, double mu_equality_scale_factor, ADMMPenaltyUpdateStrat mu_update_strat, int num_eq_c,
+                          int eq_c_dim, const Model& model, int batch, bool warm_start, double tol_tail_solve, bool verbose,
+                          bool logging, int device = 0, void* stream = nullptr)
+      : model_(model), batch_(batch), nc_(num_eq_c), stream_(stream) {
+    loik_model_desc md{model_.njoints, model_.parents.data(), model_.joint_types.data(), model_.joint_axes.data(),
+                       model_.placement_R.data(), model_.placement_p.data()};
+    loik_params p{max_iter, tol_abs, tol_rel, tol_primal_inf, tol_dual_inf, rho, mu, mu_equality_scale_factor,
+                  static_cast<int32_t>(mu_update_strat), num_eq_c, eq_c_dim, warm_start ? 1 : 0, tol_tail_solve,
+                  verbose ? 1 : 0, logging ? 1 : 0};
+    check(loik_create(&md, &p, batch, device, &h_));
+  }
+  ~FirstOrderLoikOptimized() { loik_destroy(h_); }
+  FirstOrderLoikOptimized(const FirstOrderLoikOptimized&) = delete;
+  FirstOrderLoikOptimized& operator=(const FirstOrderLoikOptimized&) = delete;
+
+  // SolveInit(q, H_ref, v_ref, ids, Ais, bis, lb, ub)  (hpp:335-338).  q [batch][nq]; bis [batch][nc][6]; lb/ub [nv].
+  void SolveInit(const std::vector<double>& q, const std::vector<double>& H_ref, const std::vector<double>& v_ref,
+                 const std::vector<int32_t>& active_task_constraint_ids, const std::vector<double>& Ais,
+                 const std::vector<double>& bis, const std::vector<double>& lb, const std::vector<double>& ub) {
+    validate(active_task_constraint_ids, Ais, bis, lb, ub);
+    check(loik_solve_init(h_, q.data(), H_ref.data(), v_ref.data(), (int32_t)active_task_constraint_ids.size(),
+                          active_task_constraint_ids.data(), Ais.data(), bis.data(), per_instance(bis), lb.data(), ub.data(), 0,
+                          LOIK_HOST, stream_));
+  }
+  void Solve() { check(loik_solve(h_, stream_)); }  // hpp:368
+  void Solve(const std::vector<double>& q, const std::vector<double>& H_ref, const std::vector<double>& v_ref,
+             const std::vector<int32_t>& active_task_constraint_ids, const std::vector<double>& Ais,
+             const std::vector<double>& bis, const std::vector<double>& lb, const std::vector<double>& ub) {  // hpp:475-478
+    validate(active_task_constraint_ids, Ais, bis, lb, ub);
+    check(loik_solve_full(h_, q.data(), H_ref.data(), v_ref.data(), (int32_t)active_task_constraint_ids.size(),
+                          active_task_constraint_ids.data(), Ais.data(), bis.data(), per_instance(bis), lb.data(), ub.data(), 0,
+                          LOIK_HOST, stream_));
+  }
+  // Solve(q, c_id, Ai, bi)  (hpp:596-597): bi [batch][6] or [6]
+  void Solve(const std::vector<double>& q, int c_id, const std::vector<double>& Ai, const std::vector<double>& bi) {
+    check(loik_solve_task(h_, q.data(), c_id, Ai.data(), bi.data(), bi.size() == (size_t)batch_ * 6 && batch_ > 1 ? 1 : 0, LOIK_HOST,
+                          stream_));
+  }
+
+  // results: ik_id_data.z / nu / w / yis / vis / fis of the reference, batch-major
+  std::vector<double> z() const { return get(LOIK_F_Z, model_.nv); }
+  std::vector<double> nu() const { return get(LOIK_F_NU, model_.nv); }
+  std::vector<double> w() const { return get(LOIK_F_W, model_.nv); }
+  std::vector<double> yis() const { return get(LOIK_F_Y, 6 * nc_); }
+  std::vector<double> vis() const { return get(LOIK_F_V, 6 * (model_.njoints - 1)); }
+  std::vector<double> fis() const { return get(LOIK_F_F, 6 * (model_.njoints - 1)); }
+  // getters of IkIdSolverBaseTpl (task-solver-base.hpp:87-141), one value per instance
+  std::vector<int32_t> get_iter() const { return geti(LOIK_F_ITER); }
+  std::vector<double> get_mu() const { return get(LOIK_F_MU, 1); }
+  std::vector<double> get_primal_residual() const { return column(0); }
+  std::vector<double> get_dual_residual() const { return column(1); }
+  std::vector<double> get_tol_primal() const { return column(2); }
+  std::vector<double> get_tol_dual() const { return column(3); }
+  std::vector<bool> get_convergence_status() const { return flag(1); }
+  std::vector<bool> get_primal_infeasibility_status() const { return flag(2); }
+  std::vector<bool> get_dual_infeasibility_status() const { return std::vector<bool>(batch_, false); }  // never evaluated by the optimized path
+  void set_max_iter(int m) { check(loik_set_max_iter(h_, m)); }
+  void set_rho(double r) { check(loik_set_rho(h_, r)); }
+  void set_mu(double m) { check(loik_set_mu(h_, m)); }
+  void set_tol_tail_solve(double t) { check(loik_set_tol_tail_solve(h_, t)); }
+  loik_solver* handle() const { return h_; }
+
+ private:
+  static void check(int rc) {
+    if (rc != LOIK_OK) throw std::runtime_error(loik_last_error());
+  }
+  int per_instance(const std::vector<double>& bis) const { return bis.size() == (size_t)batch_ * nc_ * 6 && batch_ > 1 ? 1 : 0; }
+  void validate(const std::vector<int32_t>& ids, const std::vector<double>& Ais, const std::vector<double>& bis,
+                const std::vector<double>& lb, const std::vector<double>& ub) const {
+    // ik-id-description-optimized.hpp:132-134, :328-335
+    if (Ais.size() != ids.size() * 36 || (bis.size() != ids.size() * 6 && bis.size() != (size_t)batch_ * ids.size() * 6))
+      throw std::runtime_error("[IkProblemFormulation::UpdateEqConstraints]: task_constraint_ids, Ais, and bis have different size !!!");
+    if (lb.size() != ub.size())
+      throw std::runtime_error("[IkProblemFormulation::UpdateIneqConstraints]: lower bound and upper bound have different dimensions!!!");
+    if ((int)lb.size() != model_.nv)
+      throw std::runtime_error("IkProblemFormulation::UpdateIneqConstraints]: inequality constraint dimension has changed, this is not supported currently!!!");
+  }
+  std::vector<double> get(int field, int width) const {
+    std::vector<double> out((size_t)batch_ * width);
+    check(loik_get(h_, field, out.data(), LOIK_HOST, stream_));
+    return out;
+  }
+  std::vector<int32_t> geti(int field) const {
+    std::vector<int32_t> out(batch_);
+    check(loik_get(h_, field, out.data(), LOIK_HOST, stream_));
+    return out;
+  }
+  std::vector<double> column(int c) const {
+    auto r = get(LOIK_F_RESIDUALS, 4);
+    std::vector<double> out(batch_);
+    for (int i = 0; i < batch_; ++i) out[i] = r[4 * i + c];
+    return out;
+  }
+  std::vector<bool> flag(int bit) const {
+    auto s = geti(LOIK_F_STATUS);
+    std::vector<bool> out(batch_);
+    for (int i = 0; i < batch_; ++i) out[i] = (s[i] & bit) != 0;
+    return out;
+  }
+  Model model_;
+  int batch_, nc_;
+  void* stream_;
+  loik_solver* h_ = nullptr;
+};
+
+}  // namespace loik_b200
