@@ -28,6 +28,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# The pipelined solver handles each own a stream (+ a high-priority one); with the default of 8 hardware queues
+# streams alias and serialise.  Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from loik_b200 import problems, robots  # noqa: E402
 
@@ -180,7 +183,7 @@ def main():
     ap.add_argument("--impl", default="loik_b200", choices=["loik_b200", "reference"])
     ap.add_argument("--workload", default="panda", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config's)")
-    ap.add_argument("--pipeline", type=int, default=4,
+    ap.add_argument("--pipeline", type=int, default=16,
                     help="solver handles (each on its own stream) kept in flight; step i uses handle i %% depth")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -209,7 +212,10 @@ def main():
     n, nc = model.nb, len(robots.TASK_JOINTS[robot])
     pb = problems.random_batch(model, batch, seed=0, first_index=rank * batch)  # this rank's shard of the global batch
     params = problems.bench_params(nc)
-    D = max(1, args.pipeline)
+    # each handle owns a home arena + two re-pack arenas; keep the pipeline within ~60 GB of HBM
+    rows_est = 48 + 61 * n + 24 * nc + 33 + 14 * n
+    bytes_per_handle = 3 * ((batch + 31) // 32) * rows_est * 256
+    D = max(1, min(args.pipeline, int(60e9 // bytes_per_handle)))
     solvers = [lk.make_solver(model, params, batch, device=local_rank) for _ in range(D)]
     drivers = [sharded.ShardedSolver(S, world) for S in solvers]
     streams = [torch.cuda.Stream(device=dev) for _ in range(D)]

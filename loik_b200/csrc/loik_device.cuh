@@ -301,6 +301,15 @@ LOIK_DEV void actinv_motion(const double (&R)[9], const double (&t)[3], const do
 // above a store to a possibly-aliasing row, so interleaving them would serialise on DRAM latency).
 // ---------------------------------------------------------------------------------------------
 LOIK_DEV double ldc(const double* T, int row) { return __ldg(T + row * 32); }  // read-only data
+// Software prefetch of the NEXT joint step's rows into L2, issued at the top of the current step: the sweeps are
+// chains of dependent steps, each starting with a batch of loads, and with 8 resident warps per SM the DRAM
+// latency of that batch is exposed; a prefetch costs no register and turns it into an L2 hit.
+LOIK_DEV void pf(const double* P, int row) { asm volatile("prefetch.global.L2 [%0];" ::"l"(P + row * 32)); }
+template <int N>
+LOIK_DEV void pf_rows(const double* P, int row0) {
+#pragma unroll
+  for (int c = 0; c < N; ++c) pf(P, row0 + c);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Backward sweep: FwdPass1 (hxx:290-338) fused into BwdPassOptimizedVisitor (hxx:345-354, algo :31-81).
@@ -316,6 +325,14 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, double* __restrict__ T, cons
   for (int i = nb; i >= 1; --i) {
     const JointC& J = c_model.j[i];
     double* Pj = joint_blk(T, O, i - 1);
+    if (i > 1) {
+      const double* Pn = joint_blk(T, O, i - 2);
+      pf_rows<6>(Pn, JR_V); pf(Pn, JR_W); pf(Pn, JR_Z); pf_rows<2>(Pn, JR_JQ);
+      const int kt = c_model.j[i - 1].task;
+      if (kt >= 0) { const double* Pk = task_blk(T, O, kt); pf_rows<6>(Pk, TR_ATY); pf_rows<6>(Pk, TR_ATB); }
+    } else {
+      pf_rows<6>(Pj, JR_F); pf(Pj, JR_NU);  // first rows of the forward sweep that this sweep has not touched
+    }
     // ---- load phase
     double vold[6], aty[6], atb[6];
     const double w_i = ld(Pj, JR_W), z_i = ld(Pj, JR_Z);
@@ -430,6 +447,13 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const
     const JointC& J = c_model.j[i];
     const int ji = i - 1;
     double* Pj = joint_blk(T, O, ji);
+    if (i < nb) {
+      const double* Pn = joint_blk(T, O, ji + 1);
+      pf_rows<6>(Pn, JR_V); pf_rows<6>(Pn, JR_F); pf(Pn, JR_NU); pf(Pn, JR_Z); pf(Pn, JR_W); pf_rows<2>(Pn, JR_JQ);
+      if (nb > 16) pf_rows<35>(Pn, JR_H);  // long trees: the workspace written by the backward sweep has left L2 by now
+      const int kt = c_model.j[i + 1].task;
+      if (kt >= 0) { const double* Pk = task_blk(T, O, kt); pf_rows<6>(Pk, TR_B); pf_rows<6>(Pk, TR_Y); }
+    }
     // ---- load phase A: what nu_i, v_i and the dof update need
     double vin[6], UD[6], vold[6];
     const double qa = ldc(Pj, JR_JQ), qb = ldc(Pj, JR_JQ + 1);
@@ -553,6 +577,10 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resi
     const JointC& J = c_model.j[i];
     const int ji = i - 1;
     double* Pj = joint_blk(T, O, ji);
+    if (i > 1) {
+      const double* Pn = joint_blk(T, O, ji - 1);
+      pf_rows<6>(Pn, JR_FD); pf(Pn, JR_T);
+    }
     // ---- load phase
     double f[6], F[6], v[6], Fold[6];
     const double w_i = ld(Pj, JR_W), T_old = ld(Pj, JR_T);

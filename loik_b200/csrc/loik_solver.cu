@@ -98,10 +98,14 @@ __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ ModelC 
 // 0..count-1 of arena Y, so the following sweeps run on full tiles with coalesced rows again.  Only the rows that
 // survive an iteration travel (state, problem data, control); the backward->forward workspace is rebuilt every sweep.
 // origin_y[k] = the instance's slot in the home arena.
+LOIK_DEV void retire_one(const ModelC& c_model, const StateP& X, const int* __restrict__ origin_x, const StateP& Home, int k, int all);
+
 __global__ void __launch_bounds__(128) k_repack(const __grid_constant__ ModelC c_model, const StateP X, const int* __restrict__ list,
                                                 const int* __restrict__ count, const int* __restrict__ origin_x,
-                                                const StateP Y, int* __restrict__ origin_y) {
+                                                const StateP Y, int* __restrict__ origin_y, const StateP Home, const int retire) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  // fused k_retire: slot k of X, if it finished inside X, goes home (X is a packed arena, never the home arena)
+  if (retire && k < *X.n_dev) retire_one(c_model, X, origin_x, Home, k, 0);
   if (k >= *count) return;
   const int src = list[k];
   const Offs& O = c_model.off;
@@ -141,6 +145,10 @@ __global__ void __launch_bounds__(128) k_retire(const __grid_constant__ ModelC c
                                                 const StateP Home, const int all) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= *X.n_dev) return;
+  retire_one(c_model, X, origin_x, Home, k, all);
+}
+
+LOIK_DEV void retire_one(const ModelC& c_model, const StateP& X, const int* __restrict__ origin_x, const StateP& Home, int k, int all) {
   const Offs& O = c_model.off;
   const double* Ts = tile_ptr(X, c_model, k);
   if (!all && ld_ctl(c_model, Ts).x < ST_CONVERGED) return;
@@ -400,7 +408,20 @@ struct loik_solver {
   int64_t sweeps = 0;
   int minb = 0;
   int dense_sweeps = 4;  // sweeps on the home arena before the first re-pack (env LOIK_DENSE)
+  int sched_reps = 2;      // re-pack rounds per chunk size (env LOIK_REPS)
+  double sched_growth = 2.0;  // chunk growth factor (env LOIK_GROWTH)
   int last_list = -1;  // index of the list holding the most recent compaction, -1 = none
+  // CUDA-graph cache of (reset +) the launch schedule: one graph launch per solve instead of ~60 kernel launches
+  cudaGraphExec_t g_exec = nullptr;
+  ModelC g_mc{};
+  int g_flags = -1, g_budget = -1, g_dense = -1;
+  int64_t g_launches = 0, g_sweeps = 0;
+  bool use_graph = true;
+  // the latency-bound tail rounds run on a high-priority stream so their few CTAs are dispatched ahead of the
+  // bulk kernels of other solvers sharing the GPU
+  cudaStream_t hi_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int hi_after = 8;  // sweeps after which the schedule moves to the high-priority stream (env LOIK_HI_AFTER, <0: never)
   int sweeps_in_solve = 0;
 };
 
@@ -497,6 +518,10 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   h->nj = nj; h->nb = nj - 1; h->nc = params->num_eq_c; h->prm = *params;
   h->minb = 4;
   if (const char* e = std::getenv("LOIK_DENSE")) { const int v = std::atoi(e); if (v >= 0) h->dense_sweeps = v; }
+  if (const char* e = std::getenv("LOIK_NO_GRAPH")) { if (std::atoi(e) != 0) h->use_graph = false; }
+  if (const char* e = std::getenv("LOIK_HI_AFTER")) h->hi_after = std::atoi(e);
+  if (const char* e = std::getenv("LOIK_REPS")) { const int v = std::atoi(e); if (v >= 1) h->sched_reps = v; }
+  if (const char* e = std::getenv("LOIK_GROWTH")) { const double v = std::atof(e); if (v >= 1.0) h->sched_growth = v; }
   if (const char* e = std::getenv("LOIK_MINB")) { const int v = std::atoi(e); if (v == 4 || v == 6 || v == 8) h->minb = v; }
   ModelC& M = h->mc;
   std::memset(&M, 0, sizeof(M));
@@ -587,6 +612,13 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
     cudaMalloc(&h->d_map, std::max<size_t>(all.size(), 1) * sizeof(int));
     cudaMemcpy(h->d_map, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice);
   }
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&h->hi_stream, cudaStreamNonBlocking, hi);
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+  }
   cudaMallocHost(&h->h_counts, 4 * sizeof(int));
   cudaMallocHost(&h->h_stats, 4 * sizeof(unsigned long long));
   h->S.arena = h->arena; h->S.n = batch; h->S.list = nullptr; h->S.n_list = nullptr; h->S.n_active = nullptr;
@@ -600,6 +632,10 @@ void loik_destroy(loik_solver* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   cudaFree(h->arena); cudaFree(h->scratch[0]); cudaFree(h->scratch[1]); cudaFree(h->d_origin); cudaFree(h->d_lists); cudaFree(h->d_counts); cudaFree(h->d_stats); cudaFree(h->d_map);
+  if (h->g_exec) cudaGraphExecDestroy(h->g_exec);
+  if (h->hi_stream) cudaStreamDestroy(h->hi_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaFreeHost(h->h_counts); cudaFreeHost(h->h_stats);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->d_stage) cudaFree(h->d_stage);
@@ -740,9 +776,11 @@ static int ensure_scratch(loik_solver* h) {
   return LOIK_OK;
 }
 
-static int run_schedule(loik_solver* h, cudaStream_t st, int budget) {
+static int run_schedule(loik_solver* h, cudaStream_t st0, int budget) {
   int rc = ensure_scratch(h);
   if (rc) return rc;
+  cudaStream_t st = st0;
+  bool forked = false;
   const int B = h->batch;
   int done = 0;
   const int dense = std::min(budget, h->dense_sweeps);
@@ -754,6 +792,12 @@ static int run_schedule(loik_solver* h, cudaStream_t st, int budget) {
   StateP X = h->S;
   int chunk = 1, reps = 0;
   while (done < budget) {
+    if (!forked && h->hi_after >= 0 && done >= h->hi_after && h->hi_stream) {  // tail rounds: high-priority stream
+      CK(cudaEventRecord(h->ev_fork, st0));
+      CK(cudaStreamWaitEvent(h->hi_stream, h->ev_fork, 0));
+      st = h->hi_stream;
+      forked = true;
+    }
     const int y = cur < 0 ? 0 : 1 - cur;
     int* list = h->d_lists;  // one list suffices: it is consumed by the re-pack right away
     CK(cudaMemsetAsync(h->d_counts + y, 0, sizeof(int), st));
@@ -761,18 +805,58 @@ static int run_schedule(loik_solver* h, cudaStream_t st, int budget) {
     StateP Y = h->S;
     Y.arena = h->scratch[y]; Y.n_dev = h->d_counts + y;
     const int* origin_x = cur < 0 ? nullptr : h->d_origin + (size_t)cur * B;
-    k_repack<<<grid_for(B, 128), 128, 0, st>>>(h->mc, X, list, h->d_counts + y, origin_x, Y, h->d_origin + (size_t)y * B);
+    k_repack<<<grid_for(B, 128), 128, 0, st>>>(h->mc, X, list, h->d_counts + y, origin_x, Y, h->d_origin + (size_t)y * B, h->S, cur >= 0 ? 1 : 0);
     h->launches += 2;
-    if (cur >= 0) { k_retire<<<grid_for(B, 128), 128, 0, st>>>(h->mc, X, origin_x, h->S, 0); h->launches++; }
     cur = y; X = Y;
     const int c = std::min(chunk, budget - done);
     launch_iterate(h, st, X, c, 0);
     h->sweeps += c; done += c;
-    if (++reps == 2) { reps = 0; if (chunk < 64) chunk *= 2; }
+    if (++reps == h->sched_reps) { reps = 0; if (chunk < 64) chunk = std::max(chunk + 1, (int)(chunk * h->sched_growth)); }
   }
   if (cur >= 0) { k_retire<<<grid_for(B, 128), 128, 0, st>>>(h->mc, X, h->d_origin + (size_t)cur * B, h->S, 1); h->launches++; }
   CK(cudaMemsetAsync(h->d_counts + 2, 0, sizeof(int), st));  // nothing is active after a complete schedule
+  if (forked) {
+    CK(cudaEventRecord(h->ev_join, h->hi_stream));
+    CK(cudaStreamWaitEvent(st0, h->ev_join, 0));
+  }
   CK(cudaGetLastError());
+  return LOIK_OK;
+}
+
+// (reset +) schedule, replayed from a CUDA graph when the stream can be captured (any stream but the legacy default
+// one).  The graph is re-captured when the parameter block, the reset flags or the iteration budget change.
+static int solve_scheduled(loik_solver* h, cudaStream_t st, int reset_flags, int budget) {
+  int rc = ensure_scratch(h);
+  if (rc) return rc;
+  const bool graphable = h->use_graph && st != nullptr && st != cudaStreamLegacy && !h->debug;
+  if (!graphable) {
+    if (reset_flags) { rc = launch_reset(h, reset_flags, st); if (rc) return rc; }
+    h->last_list = -1; h->sweeps_in_solve = 0;
+    return budget >= 1 ? run_schedule(h, st, budget) : LOIK_OK;
+  }
+  const bool valid = h->g_exec && h->g_flags == reset_flags && h->g_budget == budget && h->g_dense == h->dense_sweeps &&
+                     std::memcmp(&h->g_mc, &h->mc, sizeof(ModelC)) == 0;
+  if (!valid) {
+    if (h->g_exec) { cudaGraphExecDestroy(h->g_exec); h->g_exec = nullptr; }
+    const int64_t l0 = h->launches, s0 = h->sweeps;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    rc = LOIK_OK;
+    if (reset_flags) rc = launch_reset(h, reset_flags, st);
+    if (!rc && budget >= 1) rc = run_schedule(h, st, budget);
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(LOIK_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&h->g_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { h->g_exec = nullptr; return fail(LOIK_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+    h->g_mc = h->mc; h->g_flags = reset_flags; h->g_budget = budget; h->g_dense = h->dense_sweeps;
+    h->g_launches = h->launches - l0; h->g_sweeps = h->sweeps - s0;
+    h->launches = l0; h->sweeps = s0;  // counted per replay below
+  }
+  CK(cudaGraphLaunch(h->g_exec, st));
+  h->launches += h->g_launches; h->sweeps += h->g_sweeps;
+  h->last_list = -1; h->sweeps_in_solve = 0;
   return LOIK_OK;
 }
 
@@ -796,10 +880,8 @@ int loik_solve(loik_solver* h, void* stream) {
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
-  rc = launch_reset(h, RST_WZ | RST_VFF | RST_YATY | RST_SOLVER, st);  // ResetRecursion + ResetSolver (hpp:370-374)
-  if (rc) return rc;
-  if (h->prm.max_iter < 2) return LOIK_OK;
-  return run_schedule(h, st, h->prm.max_iter);
+  // ResetRecursion + ResetSolver (hpp:370-374), then the main loop
+  return solve_scheduled(h, st, RST_WZ | RST_VFF | RST_YATY | RST_SOLVER, h->prm.max_iter < 2 ? 0 : h->prm.max_iter);
 }
 
 int loik_solve_full(loik_solver* h, const double* q, const double* H_ref, const double* v_ref, int32_t n_ids,
@@ -809,7 +891,7 @@ int loik_solve_full(loik_solver* h, const double* q, const double* H_ref, const 
   int rc = loik_solve_init(h, q, H_ref, v_ref, n_ids, ids, A, b, b_per_instance, lb, ub, bounds_per_instance, loc, stream);
   if (rc) return rc;
   if (h->prm.max_iter < 2) return LOIK_OK;
-  return run_schedule(h, (cudaStream_t)stream, h->prm.max_iter);
+  return solve_scheduled(h, (cudaStream_t)stream, 0, h->prm.max_iter);
 }
 
 int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double* Ai, const double* bi,
@@ -848,7 +930,7 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
   mark_done(h, st);
   if (loc == LOIK_HOST) CK(cudaStreamSynchronize(st));
   if (h->prm.max_iter < 2) return LOIK_OK;
-  return run_schedule(h, st, h->prm.max_iter);
+  return solve_scheduled(h, st, 0, h->prm.max_iter);
 }
 
 int loik_iterate_fixed(loik_solver* h, int32_t iters, int32_t reset, void* stream) {

@@ -46,7 +46,7 @@ if __name__ == "__main__":
     main()
 
 
-def pipelined(name="panda", depths=(1, 2, 4, 8)):
+def pipelined(name="panda", depths=tuple(int(x) for x in os.environ.get("DEPTHS", "1,2,4,8").split(","))):
     """Throughput with D solver handles in flight on D streams (tail of one batch overlaps the bulk of the next)."""
     model = robots.get_robot(name)
     B = int(os.environ.get("BATCH", {"panda": 65536, "ur10": 262144, "talos": 16384}[name]))
