@@ -325,10 +325,13 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, double* __restrict__ T, cons
   for (int i = nb; i >= 1; --i) {
     const JointC& J = c_model.j[i];
     double* Pj = joint_blk(T, O, i - 1);
-    if (i > 1) {
-      const double* Pn = joint_blk(T, O, i - 2);
+#ifndef LOIK_PFD
+#define LOIK_PFD 1
+#endif
+    if (i > LOIK_PFD) {
+      const double* Pn = joint_blk(T, O, i - 1 - LOIK_PFD);
       pf_rows<6>(Pn, JR_V); pf(Pn, JR_W); pf(Pn, JR_Z); pf_rows<2>(Pn, JR_JQ);
-      const int kt = c_model.j[i - 1].task;
+      const int kt = c_model.j[i - LOIK_PFD].task;
       if (kt >= 0) { const double* Pk = task_blk(T, O, kt); pf_rows<6>(Pk, TR_ATY); pf_rows<6>(Pk, TR_ATB); }
     } else {
       pf_rows<6>(Pj, JR_F); pf(Pj, JR_NU);  // first rows of the forward sweep that this sweep has not touched
@@ -447,11 +450,11 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const
     const JointC& J = c_model.j[i];
     const int ji = i - 1;
     double* Pj = joint_blk(T, O, ji);
-    if (i < nb) {
-      const double* Pn = joint_blk(T, O, ji + 1);
+    if (i + LOIK_PFD <= nb) {
+      const double* Pn = joint_blk(T, O, ji + LOIK_PFD);
       pf_rows<6>(Pn, JR_V); pf_rows<6>(Pn, JR_F); pf(Pn, JR_NU); pf(Pn, JR_Z); pf(Pn, JR_W); pf_rows<2>(Pn, JR_JQ);
       if (nb > 16) pf_rows<35>(Pn, JR_H);  // long trees: the workspace written by the backward sweep has left L2 by now
-      const int kt = c_model.j[i + 1].task;
+      const int kt = c_model.j[i + LOIK_PFD].task;
       if (kt >= 0) { const double* Pk = task_blk(T, O, kt); pf_rows<6>(Pk, TR_B); pf_rows<6>(Pk, TR_Y); }
     }
     // ---- load phase A: what nu_i, v_i and the dof update need
@@ -577,8 +580,8 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resi
     const JointC& J = c_model.j[i];
     const int ji = i - 1;
     double* Pj = joint_blk(T, O, ji);
-    if (i > 1) {
-      const double* Pn = joint_blk(T, O, ji - 1);
+    if (i > LOIK_PFD) {
+      const double* Pn = joint_blk(T, O, ji - LOIK_PFD);
       pf_rows<6>(Pn, JR_FD); pf(Pn, JR_T);
     }
     // ---- load phase
