@@ -108,7 +108,8 @@ typedef enum loik_field {
   LOIK_F_NORMS,        /* [LOIK_NUM_NORMS] the running norms / sums of IkIdDataTypeOptimized + feasibility scalars
                           (only maintained when loik_set_debug(h,1)); order: loik_norm_index */
   LOIK_F_PRIMAL_RES_VEC, /* [6nb+nv] get_primal_residual_vec() (debug mode only) */
-  LOIK_F_DUAL_RES_VEC    /* [6nb+nv] get_dual_residual_vec()   (debug mode only) */
+  LOIK_F_DUAL_RES_VEC,   /* [6nb+nv] get_dual_residual_vec()   (debug mode only) */
+  LOIK_F_Q               /* [nq]     the configuration the kinematics (liMi) were last initialised with */
 } loik_field;
 
 /* index into LOIK_F_NORMS (names = members of IkIdDataTypeOptimizedTpl, loik-loid-data-optimized.hpp:259-329,
@@ -174,9 +175,14 @@ LOIK_API int loik_solve_full(loik_solver* h, const double* q, const double* H_re
                              const double* lb, const double* ub, int32_t bounds_per_instance, int32_t loc, void* stream);
 /* Solve(q, c_id, Ai, bi)  (hpp:596-695): tailored / trajectory-tracking form: Reset(warm_start), ResetSolver,
  * UpdateEqConstraint(c_id, Ai, bi), FwdPassInit(q), main loop.  Ai [36] HOST; q [batch][nq], bi [batch][6]
- * (or [6] if !b_per_instance) at `loc`. */
+ * (or [6] if !b_per_instance) at `loc`.  q == NULL keeps the device-resident configuration (see loik_integrate). */
 LOIK_API int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double* Ai, const double* bi,
                              int32_t b_per_instance, int32_t loc, void* stream);
+
+/* Outer IK loop on the device (the step after the hot path; README.md:5 of the reference: "differential IK ... to be
+ * integrated"): q <- q + dt * z (pinocchio::integrate for 1-DoF joints) and FwdPassInit(q) (hxx:253-283) for every
+ * instance.  Follow with loik_solve_task(h, NULL, c_id, Ai, bi, ...) for the next target.  Not a reference entry point. */
+LOIK_API int loik_integrate(loik_solver* h, double dt, void* stream);
 
 /* Fixed-iteration mode for throughput measurement: ResetRecursion + ResetSolver, then exactly `iters`
  * ADMM iterations on every instance with stopping disabled (convergence/feasibility still evaluated,

@@ -50,9 +50,9 @@ struct TaskC {
 //   [ globals | joint 1 | joint 2 | ... | task 0 | ... | pending slots | debug vectors ]
 enum : int {  // rows of a joint block
   JR_V = 0, JR_F = 6, JR_FD = 12, JR_NU = 18, JR_Z = 19, JR_W = 20, JR_T = 21,  // persistent state (22 rows)
-  JR_JQ = 22, JR_LB = 24, JR_UB = 25,                                             // per-instance problem data
-  JR_H = 26, JR_P = 47, JR_UD = 53, JR_DINV = 59, JR_R = 60,                      // backward -> forward workspace (35 rows)
-  JR_ROWS = 61
+  JR_JQ = 22, JR_LB = 24, JR_UB = 25, JR_Q = 26,                                  // per-instance problem data (5 rows)
+  JR_H = 27, JR_P = 48, JR_UD = 54, JR_DINV = 60, JR_R = 61,                      // backward -> forward workspace (35 rows)
+  JR_ROWS = 62
 };
 enum : int { TR_Y = 0, TR_ATY = 6, TR_B = 12, TR_ATB = 18, TR_ROWS = 24 };        // rows of a task block
 enum : int { PR_H = 0, PR_F = 27, PR_ROWS = 33 };                                 // rows of a pending-accumulator block

@@ -32,13 +32,11 @@ LOIK_DEV void st_ctl(const ModelC& c_model, double* T, int status, int iter) { *
 // still-active instances; the grid is sized for the worst case and surplus CTAs exit at once).
 template <bool DEBUG, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) k_iterate(const __grid_constant__ ModelC c_model, const StateP S, const int iters, const int fixed) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  int s = -1;
-  if (S.list) {
-    if (k < *S.n_list) s = S.list[k];
-  } else if (k < (S.n_dev ? *S.n_dev : S.n)) {
-    s = k;
-  }
+  const int limit = S.list ? *S.n_list : (S.n_dev ? *S.n_dev : S.n);
+  const int stride = gridDim.x * blockDim.x;
+  // grid-stride over the slots: late rounds are launched with a small grid (the count lives on the device)
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k - (int)threadIdx.x % 32 < limit; k += stride) {
+  const int s = k < limit ? (S.list ? S.list[k] : k) : -1;
   bool active = false;
   if (s >= 0) {
     double* T = tile_ptr(S, c_model, s);
@@ -66,6 +64,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_iterate(const __grid_constant_
   if (S.n_active) {
     const unsigned m = __ballot_sync(0xffffffffu, active);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(S.n_active, __popc(m));
+  }
   }
 }
 
@@ -271,6 +270,27 @@ __global__ void __launch_bounds__(kBlock) k_set_q(const __grid_constant__ ModelC
     double* Pj = joint_blk(T, c_model.off, i - 1);
     st(Pj, JR_JQ, a);
     st(Pj, JR_JQ + 1, b);
+    st(Pj, JR_Q, qi);
+  }
+}
+
+// Outer IK loop: q <- q + dt * z for 1-DoF joints (pinocchio::integrate), followed by
+// FwdPassInit of the new configuration (hxx:253-283), all on the device.
+__global__ void __launch_bounds__(128) k_integrate(const __grid_constant__ ModelC c_model, const StateP S, const double dt) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S.n) return;
+  double* T = tile_ptr(S, c_model, s);
+  const int nb = c_model.nb;
+  for (int i = 1; i <= nb; ++i) {
+    double* Pj = joint_blk(T, c_model.off, i - 1);
+    const int jt = c_model.j[i].jtype;
+    const double qi = ld(Pj, JR_Q) + dt * ld(Pj, JR_Z);
+    double a, b;
+    if (jt <= 2 || jt == 6) sincos(qi, &a, &b);
+    else { a = qi; b = 0.0; }
+    st(Pj, JR_Q, qi);
+    st(Pj, JR_JQ, a);
+    st(Pj, JR_JQ + 1, b);
   }
 }
 
@@ -421,6 +441,7 @@ struct loik_solver {
   // bulk kernels of other solvers sharing the GPU
   cudaStream_t hi_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int small_after = 1 << 30, small_grid = 296;  // late rounds: at most small_grid CTAs, grid-stride (env LOIK_SMALL_AFTER / LOIK_SMALL_GRID)
   int hi_after = 8;  // sweeps after which the schedule moves to the high-priority stream (env LOIK_HI_AFTER, <0: never)
   int sweeps_in_solve = 0;
 };
@@ -433,8 +454,9 @@ static inline int grid_for(int n, int block = kBlock) { return (n + block - 1) /
 
 // One place that launches the fused iteration kernel.  `minb` = resident CTAs (of 64 threads) per SM the
 // kernel is compiled for: 4 -> <=255 regs/thread, 6 -> <=168, 8 -> <=128 (tuning knob, env LOIK_MINB).
-static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S, int iters, int fixed) {
-  const int g = grid_for(h->batch);
+static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S, int iters, int fixed, int max_ctas = 0) {
+  int g = grid_for(h->batch);
+  if (max_ctas > 0) g = std::min(g, max_ctas);
 #define LOIK_LAUNCH(DBG, MB) k_iterate<DBG, MB><<<g, kBlock, 0, st>>>(h->mc, S, iters, fixed)
   if (h->debug) { LOIK_LAUNCH(true, 4); }
   else if (h->minb == 4) { LOIK_LAUNCH(false, 4); }
@@ -519,6 +541,8 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   h->minb = 4;
   if (const char* e = std::getenv("LOIK_DENSE")) { const int v = std::atoi(e); if (v >= 0) h->dense_sweeps = v; }
   if (const char* e = std::getenv("LOIK_NO_GRAPH")) { if (std::atoi(e) != 0) h->use_graph = false; }
+  if (const char* e = std::getenv("LOIK_SMALL_AFTER")) h->small_after = std::atoi(e);
+  if (const char* e = std::getenv("LOIK_SMALL_GRID")) h->small_grid = std::atoi(e);
   if (const char* e = std::getenv("LOIK_HI_AFTER")) h->hi_after = std::atoi(e);
   if (const char* e = std::getenv("LOIK_REPS")) { const int v = std::atoi(e); if (v >= 1) h->sched_reps = v; }
   if (const char* e = std::getenv("LOIK_GROWTH")) { const double v = std::atof(e); if (v >= 1.0) h->sched_growth = v; }
@@ -570,7 +594,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
     auto per_joint = [&](std::vector<int>& m, int jr, int width) { for (int j = 0; j < nb; ++j) for (int c = 0; c < width; ++c) m.push_back(O.joint0 + JR_ROWS * j + jr + c); };
     auto per_task = [&](std::vector<int>& m, int tr) { for (int k = 0; k < ncq; ++k) for (int c = 0; c < 6; ++c) m.push_back(O.task0 + TR_ROWS * k + tr + c); };
     auto span = [&](std::vector<int>& m, int r0, int n) { for (int c = 0; c < n; ++c) m.push_back(r0 + c); };
-    for (int field = 0; field <= LOIK_F_DUAL_RES_VEC; ++field) {
+    for (int field = 0; field <= LOIK_F_Q; ++field) {
       std::vector<int> m;
       switch (field) {
         case LOIK_F_Z: per_joint(m, JR_Z, 1); break;
@@ -591,6 +615,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
         case LOIK_F_NORMS: span(m, O.glob + GR_NORMS, LOIK_NUM_NORMS); break;
         case LOIK_F_PRIMAL_RES_VEC: span(m, O.prv, 7 * nb); break;
         case LOIK_F_DUAL_RES_VEC: span(m, O.drv, 7 * nb); break;
+        case LOIK_F_Q: per_joint(m, JR_Q, 1); break;
         case LOIK_F_H:  // expand the 21 stored scalars of each joint to a full symmetric 6x6
           for (int j = 0; j < nb; ++j)
             for (int a = 0; a < 6; ++a)
@@ -809,7 +834,7 @@ static int run_schedule(loik_solver* h, cudaStream_t st0, int budget) {
     h->launches += 2;
     cur = y; X = Y;
     const int c = std::min(chunk, budget - done);
-    launch_iterate(h, st, X, c, 0);
+    launch_iterate(h, st, X, c, 0, done >= h->small_after ? h->small_grid : 0);
     h->sweeps += c; done += c;
     if (++reps == h->sched_reps) { reps = 0; if (chunk < 64) chunk = std::max(chunk + 1, (int)(chunk * h->sched_growth)); }
   }
@@ -896,7 +921,7 @@ int loik_solve_full(loik_solver* h, const double* q, const double* H_ref, const 
 
 int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double* Ai, const double* bi,
                     int32_t b_per_instance, int32_t loc, void* stream) {
-  if (!h || !q || !Ai || !bi) return fail(LOIK_ERR_INVALID, "loik_solve_task: null argument");
+  if (!h || !Ai || !bi) return fail(LOIK_ERR_INVALID, "loik_solve_task: null argument");
   if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_solve_task: call loik_solve_init first");
   int rc = check_strategy(h);
   if (rc) return rc;
@@ -917,13 +942,13 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
   const size_t q_bytes = (size_t)B * nb * sizeof(double), b_bytes = (size_t)(b_per_instance ? B : 1) * 6 * sizeof(double);
   if (loc != LOIK_DEVICE) { rc = ensure_stage(h, q_bytes + b_bytes + 64, loc == LOIK_HOST); if (rc) return rc; }
   rc = upload_consts(h, st); if (rc) return rc;
-  const void *dq, *db;
-  rc = to_device(h, q, q_bytes, loc, 0, st, &dq); if (rc) return rc;
+  const void *dq = nullptr, *db;
+  if (q) { rc = to_device(h, q, q_bytes, loc, 0, st, &dq); if (rc) return rc; }
   rc = to_device(h, bi, b_bytes, loc, q_bytes, st, &db); if (rc) return rc;
   const int flags = RST_SOLVER | (h->prm.warm_start ? 0 : (RST_WZ | RST_NU | RST_VFF | RST_YATY));
   k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, flags);
   k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)db, b_per_instance, k);
-  k_set_q<<<grid_for(B), kBlock, kBlock * nb * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);
+  if (q) k_set_q<<<grid_for(B), kBlock, kBlock * nb * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);  // else: keep the device-resident q (loik_integrate)
   h->launches += 3;
   h->last_list = -1;
   CK(cudaGetLastError());
@@ -931,6 +956,17 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
   if (loc == LOIK_HOST) CK(cudaStreamSynchronize(st));
   if (h->prm.max_iter < 2) return LOIK_OK;
   return solve_scheduled(h, st, 0, h->prm.max_iter);
+}
+
+int loik_integrate(loik_solver* h, double dt, void* stream) {
+  if (!h) return fail(LOIK_ERR_INVALID, "null handle");
+  if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_integrate: call loik_solve_init first");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  k_integrate<<<grid_for(h->batch, 128), 128, 0, st>>>(h->mc, h->S, dt);
+  h->launches++;
+  CK(cudaGetLastError());
+  return LOIK_OK;
 }
 
 int loik_iterate_fixed(loik_solver* h, int32_t iters, int32_t reset, void* stream) {
@@ -1022,7 +1058,7 @@ int loik_get(loik_solver* h, int32_t field, void* dst, int32_t loc, void* stream
   if (rc) return rc;
   const int B = h->batch, nb = h->nb, nc = h->nc;
   const Offs& O = h->mc.off;
-  if (field < 0 || field > LOIK_F_DUAL_RES_VEC) return fail(LOIK_ERR_INVALID, "loik_get: unknown field");
+  if (field < 0 || field > LOIK_F_Q) return fail(LOIK_ERR_INVALID, "loik_get: unknown field");
   const bool is_int = field == LOIK_F_ITER || field == LOIK_F_STATUS;
   const int rows = is_int ? 1 : (field == LOIK_F_LIMI ? 12 * nb : h->map_len[field]);
   (void)nc; (void)O;

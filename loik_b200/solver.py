@@ -25,7 +25,7 @@ LOIK_HOST, LOIK_DEVICE, LOIK_HOST_PINNED = 0, 1, 2
 
 # loik_field (include/loik_b200.h)
 (F_Z, F_NU, F_W, F_Y, F_V, F_F, F_ATY, F_FDPA, F_STF_PLUS_W, F_H, F_P, F_UDINV, F_DINV, F_R, F_LIMI, F_MU, F_ITER,
- F_STATUS, F_RESIDUALS, F_NORMS, F_PRIMAL_RES_VEC, F_DUAL_RES_VEC) = range(22)
+ F_STATUS, F_RESIDUALS, F_NORMS, F_PRIMAL_RES_VEC, F_DUAL_RES_VEC, F_Q) = range(23)
 STEP_BACKWARD, STEP_FORWARD, STEP_RESIDUAL = range(3)
 
 NORM_NAMES = ["bT_delta_y_plus", "bT_delta_y_minus", "Av_inf_norm", "nu_inf_norm", "Href_v_inf_norm",
@@ -37,7 +37,7 @@ NORM_NAMES = ["bT_delta_y_plus", "bT_delta_y_minus", "Av_inf_norm", "nu_inf_norm
               "primal_infeasibility_cond_1", "primal_infeasibility_cond_2", "delta_x_qp_inf_norm"]
 
 EXPORTS = ["loik_abi_version", "loik_last_error", "loik_create", "loik_destroy", "loik_solve_init",
-           "loik_update_references", "loik_solve", "loik_solve_full", "loik_solve_task", "loik_iterate_fixed",
+           "loik_update_references", "loik_solve", "loik_solve_full", "loik_solve_task", "loik_integrate", "loik_iterate_fixed",
            "loik_reset_recursion", "loik_step", "loik_set_debug", "loik_get", "loik_get_stats", "loik_reduce_stats", "loik_launch_count",
            "loik_set_max_iter", "loik_set_rho", "loik_set_mu", "loik_set_tol_tail_solve", "loik_set_warm_start",
            "loik_active_count_device_ptr", "loik_solve_begin", "loik_solve_chunk", "loik_solve_end"]
@@ -80,6 +80,7 @@ def load_library(path: str | None = None):
     lib.loik_solve.argtypes = [vp, vp]
     lib.loik_solve_task.argtypes = [vp, dp, i32, dp, dp, i32, i32, vp]
     lib.loik_iterate_fixed.argtypes = [vp, i32, i32, vp]
+    lib.loik_integrate.argtypes = [vp, C.c_double, vp]
     lib.loik_reset_recursion.argtypes = [vp, vp]
     lib.loik_step.argtypes = [vp, i32, vp]
     lib.loik_set_debug.argtypes = [vp, i32]
@@ -237,8 +238,13 @@ class FirstOrderLoikOptimized:
             self._check(self._lib.loik_solve_full(self._h, *a))
         elif len(args) == 4:
             q, c_id, Ai, bi = args
-            qb, Ab, bb = _Buf(q), _Buf(np.asarray(Ai, np.float64).reshape(36)), _Buf(bi)
+            Ab, bb = _Buf(np.asarray(Ai, np.float64).reshape(36)), _Buf(bi)
             b_per = int(int(np.prod(bb.shape)) == self.batch * 6 and (self.batch > 1 or len(bb.shape) == 2))
+            if q is None:  # keep the device-resident configuration (after Integrate)
+                self._check(self._lib.loik_solve_task(self._h, None, int(c_id), Ab.ptr, bb.ptr, b_per, bb.loc,
+                                                      _current_stream()))
+                return
+            qb = _Buf(q)
             if qb.loc != bb.loc:
                 raise RuntimeError("q and bi must both be host arrays or both be CUDA tensors")
             self._check(self._lib.loik_solve_task(self._h, qb.ptr, int(c_id), Ab.ptr, bb.ptr, b_per, qb.loc,
@@ -267,6 +273,10 @@ class FirstOrderLoikOptimized:
     def StepResidual(self):
         """ComputeDualResiduals + CheckConvergence + CheckFeasibility + UpdateMu + loop control."""
         self._check(self._lib.loik_step(self._h, STEP_RESIDUAL, _current_stream()))
+
+    def Integrate(self, dt):
+        """q <- q + dt * z and FwdPassInit(q) on the device (outer IK loop)."""
+        self._check(self._lib.loik_integrate(self._h, float(dt), _current_stream()))
 
     def IterateFixed(self, iters, reset=True):
         self._check(self._lib.loik_iterate_fixed(self._h, int(iters), int(bool(reset)), _current_stream()))
@@ -308,7 +318,7 @@ class FirstOrderLoikOptimized:
         return {F_Z: (nb,), F_NU: (nb,), F_W: (nb,), F_Y: (nc, 6), F_V: (nb, 6), F_F: (nb, 6), F_ATY: (nc, 6),
                 F_FDPA: (nb, 6), F_STF_PLUS_W: (nb,), F_H: (nb, 6, 6), F_P: (nb, 6), F_UDINV: (nb, 6), F_DINV: (nb,),
                 F_R: (nb,), F_LIMI: (nb, 12), F_MU: (), F_ITER: (), F_STATUS: (), F_RESIDUALS: (4,),
-                F_NORMS: (len(NORM_NAMES),), F_PRIMAL_RES_VEC: (7 * nb,), F_DUAL_RES_VEC: (7 * nb,)}[field]
+                F_NORMS: (len(NORM_NAMES),), F_PRIMAL_RES_VEC: (7 * nb,), F_DUAL_RES_VEC: (7 * nb,), F_Q: (nb,)}[field]
 
     def get(self, field, out=None):
         """Copy a per-instance field of the whole batch out: numpy array [B, ...] (or into a CUDA tensor)."""
@@ -337,6 +347,7 @@ class FirstOrderLoikOptimized:
     Dinv = property(lambda self: self.get(F_DINV))
     r = property(lambda self: self.get(F_R))
     liMi = property(lambda self: self.get(F_LIMI))
+    q = property(lambda self: self.get(F_Q))
 
     def get_iter(self):
         return self.get(F_ITER)

@@ -6,8 +6,8 @@ name = sys.argv[1] if len(sys.argv) > 1 else "panda"
 B = int(os.environ.get("BATCH", 65536))
 model = robots.get_robot(name)
 pb = problems.random_batch(model, B, seed=0)
-for max_iter in (5, 9, 17, 33, 65, 200):
-    for D in (1, 8):
+for max_iter in (5, 6, 7, 9, 13, 17, 33, 65, 200):
+    for D in (16,):
         P = problems.bench_params(len(pb["ids"]), max_iter=max_iter)
         Ss = [lk.make_solver(model, P, B) for _ in range(D)]
         st = [torch.cuda.Stream() for _ in range(D)]

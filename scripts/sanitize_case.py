@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Small end-to-end case for compute-sanitizer (memcheck / racecheck / initcheck / synccheck)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from loik_b200 import problems, robots, solver as lk  # noqa: E402
+
+for name, B in (("panda9", 100), ("talos", 70)):
+    model = robots.get_robot(name)
+    pb = problems.random_batch(model, B, seed=0)
+    S = lk.make_solver(model, problems.bench_params(len(pb["ids"]), max_iter=40), B)
+    S.SolveInit(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
+    S.Solve()
+    z = S.z
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        S.Solve()          # graph path
+        side.synchronize()
+        assert np.array_equal(S.z, z)
+    S.Integrate(0.01)
+    S.Solve(None, int(pb["ids"][0]), pb["Ais"][0], pb["bis"][:, 0])
+    S.set_debug(True)
+    S.ResetRecursion(); S.StepBackward(); S.StepForward(); S.StepResidual()
+    _ = S.His, S.norms(), S.liMi, S.stats()
+    S.close()
+    print(name, "ok")

@@ -34,7 +34,7 @@ def test_enums_match_header():
     assert len(names) == len(solver.NORM_NAMES)
     body = src[src.index("typedef enum loik_field"):src.index("} loik_field")]
     fields = re.findall(r"^\s*(LOIK_F_\w+)", body, flags=re.M)
-    assert len(fields) == 22 and fields[solver.F_RESIDUALS] == "LOIK_F_RESIDUALS" and fields[solver.F_Z] == "LOIK_F_Z"
+    assert len(fields) == 23 and fields[solver.F_RESIDUALS] == "LOIK_F_RESIDUALS" and fields[solver.F_Z] == "LOIK_F_Z"
 
 
 def test_no_cpu_fallback_without_gpu():

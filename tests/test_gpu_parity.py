@@ -374,3 +374,34 @@ def test_graph_replay_on_side_stream_matches_direct_launches():
     np.testing.assert_array_equal(it2, G0.get_iter())
     assert it2.max() <= 20
     G0.close(); G1.close()
+
+
+def test_outer_ik_loop_on_device():
+    """integrate q <- q + dt z on the device, then the tailored Solve for the next target,
+    against the same sequence driven through the oracle (user-side integration + Solve(q, c_id, Ai, bi))."""
+    model = robots.panda()
+    B = 256
+    pb = problems.random_batch(model, B, seed=12)
+    nxt = problems.random_batch(model, B, seed=13)
+    params = dict(problems.bench_params(1), warm_start=True)
+    c_id, A, dt = int(pb["ids"][0]), pb["Ais"][0], 0.05
+    G = _gpu(model, params, B)
+    G.Solve(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
+    z0 = G.z
+    G.Integrate(dt)
+    np.testing.assert_allclose(G.q, pb["q"] + dt * z0, rtol=0, atol=1e-15)
+    b1 = 0.5 * (pb["bis"][:, 0] + nxt["bis"][:, 0])
+    G.Solve(None, c_id, A, b1)
+    z1, it1, mu1 = G.z, G.get_iter(), G.get_mu()
+    bad = 0
+    for i in range(B):
+        o = _oracle(model, params)
+        o.Solve(*instance(pb, i))
+        q1 = pb["q"][i] + dt * o.z
+        o.Solve(q1, c_id, A, b1[i])
+        if o.get_iter() != it1[i] or o.get_mu() != mu1[i]:
+            bad += 1
+            continue
+        assert rel_inf(z1[i], o.z) < 1e-6
+    assert bad <= 1
+    G.close()
