@@ -23,6 +23,8 @@ namespace loik {
 
 constexpr int kMaxJoints = 64;
 constexpr int kMaxTasks = 8;
+constexpr int kMaxPin = 6;    // children per joint that are not carried in registers
+constexpr int kMaxSeg = 16;   // chains of the tree that can be swept by different warps
 
 // status of an instance (per-instance loop control of Solve()/InfeasibilityTailSolve())
 enum : int { ST_RUNNING = 0, ST_TAIL = 1, ST_CONVERGED = 2, ST_INFEASIBLE_DONE = 3, ST_MAXITER = 4 };
@@ -32,11 +34,11 @@ struct JointC {
   double HrA[6], HrB[9], HrD[6];    // problem_.H_refs_[i] as blocks LL (sym), LA, AA (sym)
   double Hv[6];                     // problem_.Hv[i] = H_ref v_ref
   double lb, ub;                    // problem_.lb_/ub_ for this joint's dof (when shared by the batch)
-  int parent, jtype, task, pend;    // task: slot of the task on this joint or -1; pend: own pending slot or -1
-  int carry;                        // contribution to the parent travels in registers (parent == i-1)
-  int pfirst;                       // first non-carried contribution into the parent's pending slot ('=' not '+=')
-  int ppend;                        // the parent's pending slot (when !carry && parent > 0)
-  int pad;
+  int parent, jtype, task;          // task: slot of the task on this joint or -1
+  int carry;                        // contribution to the parent travels in registers (parent == i-1, only child)
+  int pout;                         // else (parent > 0): the pending block this joint writes its contribution to
+  int npin;                         // number of children that hand their contribution over through a pending block
+  int pin[kMaxPin];                 // those blocks (one per tree edge: single writer, no read-modify-write)
 };
 
 struct TaskC {
@@ -64,9 +66,16 @@ struct Offs {
   int rows;                        // rows per tile record
 };
 
+// A segment = a maximal chain lo..hi (parent(i) == i-1, single child) of the tree.  Segments only exchange data
+// through pending blocks / the parent's v row, so different warps can sweep them; `blevel` / `flevel` order them
+// (children before parents on the way down to the root, parents before children on the way out).
+struct SegC { short lo, hi, bwarp, blevel, fwarp, flevel; };
+
 struct ModelC {
   int nj, nb, nc, npend;
   int max_iter, bounds_per_instance;
+  int nseg, nblevel, nflevel, nwarp;
+  SegC seg[kMaxSeg];
   Offs off;
   double rho, mu0, mu_scale, tol_abs, tol_rel, tol_pinf, tol_dinf, tol_tail, Hv_inf;
   JointC j[kMaxJoints];
@@ -316,24 +325,21 @@ LOIK_DEV void pf_rows(const double* P, int row0) {
 // Leaves for the forward sweep, per joint: H_i and p_i (accumulated over the subtree, un-projected,
 // = His[i]/pis[i] after the reference's BwdPass), UDinv_i, Dinv_i, r_i.
 // ---------------------------------------------------------------------------------------------
-LOIK_DEV void sweep_backward(const ModelC& c_model, double* __restrict__ T, const double mu, const double mu_eq) {
+LOIK_DEV void sweep_backward(const ModelC& c_model, double* __restrict__ T, const double mu, const double mu_eq,
+                             const int lo, const int hi) {
   const Offs& O = c_model.off;
-  const int nb = c_model.nb;
   const double rho = c_model.rho;
   double cA[6], cB[9], cD[6], cp[6];  // contribution carried from child i+1
   bool have_carry = false;
-  for (int i = nb; i >= 1; --i) {
+  for (int i = hi; i >= lo; --i) {
     const JointC& J = c_model.j[i];
     double* Pj = joint_blk(T, O, i - 1);
-#ifndef LOIK_PFD
-#define LOIK_PFD 1
-#endif
-    if (i > LOIK_PFD) {
-      const double* Pn = joint_blk(T, O, i - 1 - LOIK_PFD);
+    if (i > lo) {
+      const double* Pn = joint_blk(T, O, i - 2);
       pf_rows<6>(Pn, JR_V); pf(Pn, JR_W); pf(Pn, JR_Z); pf_rows<2>(Pn, JR_JQ);
-      const int kt = c_model.j[i - LOIK_PFD].task;
+      const int kt = c_model.j[i - 1].task;
       if (kt >= 0) { const double* Pk = task_blk(T, O, kt); pf_rows<6>(Pk, TR_ATY); pf_rows<6>(Pk, TR_ATB); }
-    } else {
+    } else if (i == 1) {
       pf_rows<6>(Pj, JR_F); pf(Pj, JR_NU);  // first rows of the forward sweep that this sweep has not touched
     }
     // ---- load phase
@@ -367,8 +373,8 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, double* __restrict__ T, cons
       for (int c = 0; c < 6; ++c) p[c] += aty[c] - mu_eq * atb[c];
     }
     // children's contributions: His[parent] += SE3actOn(...), pis[parent] += liMi.act(...) (:66,:74)
-    if (J.pend >= 0) {
-      const double* Pp = pend_blk(T, O, J.pend);
+    for (int n = 0; n < J.npin; ++n) {
+      const double* Pp = pend_blk(T, O, J.pin[n]);
 #pragma unroll
       for (int c = 0; c < 6; ++c) { A[c] += ld(Pp, PR_H + c); D[c] += ld(Pp, PR_H + 15 + c); p[c] += ld(Pp, PR_H + 21 + c); }
 #pragma unroll
@@ -415,16 +421,7 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, double* __restrict__ T, cons
       if (J.carry) {
         have_carry = true;
       } else {
-        double* Pp = pend_blk(T, O, J.ppend);
-        if (!J.pfirst) {  // read-modify-write of the parent's pending slot: all loads first
-          double oH[27];
-#pragma unroll
-          for (int c = 0; c < 27; ++c) oH[c] = ld(Pp, PR_H + c);
-#pragma unroll
-          for (int c = 0; c < 6; ++c) { cA[c] += oH[c]; cD[c] += oH[15 + c]; cp[c] += oH[21 + c]; }
-#pragma unroll
-          for (int c = 0; c < 9; ++c) cB[c] += oH[6 + c];
-        }
+        double* Pp = pend_blk(T, O, J.pout);
 #pragma unroll
         for (int c = 0; c < 6; ++c) { st(Pp, PR_H + c, cA[c]); st(Pp, PR_H + 15 + c, cD[c]); st(Pp, PR_H + 21 + c, cp[c]); }
 #pragma unroll
@@ -438,23 +435,27 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, double* __restrict__ T, cons
 // Forward sweep: FwdPass2OptimizedVisitor (hxx:361-377, algo :102-163) + BoxProj (:384-397) +
 // DualUpdate (:404-461) + ComputePrimalResiduals (:494-503), joint by joint, root to leaves.
 // ---------------------------------------------------------------------------------------------
-template <bool DEBUG>
-LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const double mu, const double mu_eq, Carry& cy) {
-  const Offs& O = c_model.off;
-  const int nb = c_model.nb;
+LOIK_DEV void zero(Carry& cy) {
   cy.nu_inf = cy.dfis_inf = cy.dvis_inf = cy.dnu_inf = cy.dz_inf = cy.dyis_inf = cy.dw_inf = cy.Av_inf = 0.0;
   cy.bTdy_p = cy.bTdy_m = cy.ubdw_p = cy.lbdw_m = cy.pres_task = cy.pres_slack = 0.0;
+}
+// Accumulates into `cy` (the caller zeroes it once per iteration).
+template <bool DEBUG>
+LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const double mu, const double mu_eq, Carry& cy,
+                            const int lo, const int hi) {
+  const Offs& O = c_model.off;
+  const int nb = c_model.nb;
   const double inv_mu = 1.0 / mu;
   double vprev[6] = {0, 0, 0, 0, 0, 0};  // v of joint i-1
-  for (int i = 1; i <= nb; ++i) {
+  for (int i = lo; i <= hi; ++i) {
     const JointC& J = c_model.j[i];
     const int ji = i - 1;
     double* Pj = joint_blk(T, O, ji);
-    if (i + LOIK_PFD <= nb) {
-      const double* Pn = joint_blk(T, O, ji + LOIK_PFD);
+    if (i < hi) {
+      const double* Pn = joint_blk(T, O, ji + 1);
       pf_rows<6>(Pn, JR_V); pf_rows<6>(Pn, JR_F); pf(Pn, JR_NU); pf(Pn, JR_Z); pf(Pn, JR_W); pf_rows<2>(Pn, JR_JQ);
       if (nb > 16) pf_rows<35>(Pn, JR_H);  // long trees: the workspace written by the backward sweep has left L2 by now
-      const int kt = c_model.j[i + LOIK_PFD].task;
+      const int kt = c_model.j[i + 1].task;
       if (kt >= 0) { const double* Pk = task_blk(T, O, kt); pf_rows<6>(Pk, TR_B); pf_rows<6>(Pk, TR_Y); }
     }
     // ---- load phase A: what nu_i, v_i and the dof update need
@@ -468,7 +469,7 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const
     if (J.parent == 0) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) vin[c] = 0.0;
-    } else if (J.parent == i - 1) {
+    } else if (J.parent == i - 1 && i > lo) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) vin[c] = vprev[c];
     } else {
@@ -569,19 +570,20 @@ struct Resid {
 // leaves to root.  F = fis_diff_plus_Aty, T = Stf_plus_w.  The reference's "copy F to delta_F, zero F,
 // set F_c = Aty" choreography (:364,:370,:438-439) reduces to: F_old is what is in memory, F_new is rebuilt.
 // ---------------------------------------------------------------------------------------------
+LOIK_DEV void zero(Resid& rs) { rs.dres_v = rs.dres_nu = rs.Hrefv_inf = rs.F_inf = rs.T_inf = rs.dF_inf = rs.dT_inf = 0.0; }
+// Accumulates into `rs` (the caller zeroes it once per iteration and sets dres_nu = T_inf at the end, hxx:484).
 template <bool DEBUG>
-LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resid& rs) {
+LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resid& rs, const int lo, const int hi) {
   const Offs& O = c_model.off;
   const int nb = c_model.nb;
-  rs.dres_v = rs.dres_nu = rs.Hrefv_inf = rs.F_inf = rs.T_inf = rs.dF_inf = rs.dT_inf = 0.0;
   double cF[6];
   bool have_carry = false;
-  for (int i = nb; i >= 1; --i) {
+  for (int i = hi; i >= lo; --i) {
     const JointC& J = c_model.j[i];
     const int ji = i - 1;
     double* Pj = joint_blk(T, O, ji);
-    if (i > LOIK_PFD) {
-      const double* Pn = joint_blk(T, O, ji - LOIK_PFD);
+    if (i > lo) {
+      const double* Pn = joint_blk(T, O, ji - 1);
       pf_rows<6>(Pn, JR_FD); pf(Pn, JR_T);
     }
     // ---- load phase
@@ -598,8 +600,8 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resi
 #pragma unroll
       for (int c = 0; c < 6; ++c) F[c] = 0.0;  // (:370)
     }
-    if (J.pend >= 0) {
-      const double* Pp = pend_blk(T, O, J.pend);
+    for (int n = 0; n < J.npin; ++n) {
+      const double* Pp = pend_blk(T, O, J.pin[n]);
 #pragma unroll
       for (int c = 0; c < 6; ++c) F[c] += ld(Pp, PR_F + c);
     }
@@ -645,20 +647,12 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resi
       if (J.carry) {
         have_carry = true;
       } else {
-        double* Pp = pend_blk(T, O, J.ppend);
-        if (!J.pfirst) {
-          double oF[6];
-#pragma unroll
-          for (int c = 0; c < 6; ++c) oF[c] = ld(Pp, PR_F + c);
-#pragma unroll
-          for (int c = 0; c < 6; ++c) cF[c] += oF[c];
-        }
+        double* Pp = pend_blk(T, O, J.pout);
 #pragma unroll
         for (int c = 0; c < 6; ++c) st(Pp, PR_F + c, cF[c]);
       }
     }
   }
-  rs.dres_nu = rs.T_inf;  // dual_residual_vec[6nb:] = Stf_plus_w (:484)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -666,15 +660,18 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resi
 // of Solve() (hpp:377-454) and InfeasibilityTailSolve() (hpp:271-319), per instance.
 // `fixed`: stopping disabled (throughput mode).  Returns the new status; updates mu.
 // ---------------------------------------------------------------------------------------------
+// `writer`: this thread stores the per-instance results (one warp per tile does when several warps share it).
 template <bool DEBUG>
 LOIK_DEV int decide(const ModelC& c_model, double* __restrict__ T, const int status, const int it, const bool fixed, const Carry& cy,
-                    const Resid& rs, double& mu) {
+                    const Resid& rs, double& mu, const bool writer = true) {
   const ModelC& M = c_model;
   double* G = glob_blk(T, M.off);
   const double pres = fmax(cy.pres_task, cy.pres_slack);  // (:498)
-  const double dres = fmax(rs.dres_v, rs.dres_nu);        // (:517)
-  st(G, GR_RES + 0, pres);
-  st(G, GR_RES + 1, dres);
+  const double dres = fmax(rs.dres_v, rs.T_inf);          // (:517); dual_residual_vec[6nb:] = Stf_plus_w (:484)
+  if (writer) {
+    st(G, GR_RES + 0, pres);
+    st(G, GR_RES + 1, dres);
+  }
   int ns = status;
   double dyqp = 0.0, ATdy = 0.0, ubp = 0.0, lbm = 0.0, c1 = 0.0, c2 = 0.0;
   double dx = fmax(cy.dvis_inf, cy.dnu_inf);
@@ -682,8 +679,10 @@ LOIK_DEV int decide(const ModelC& c_model, double* __restrict__ T, const int sta
     const double binf = ld(G, GR_BINF);
     const double tol_p = M.tol_abs + M.tol_rel * fmax(fmax(cy.Av_inf, cy.nu_inf), fmax(binf, cy.nu_inf));            // (:544-546)
     const double tol_d = M.tol_abs + M.tol_rel * fmax(fmax(rs.Hrefv_inf, fmax(rs.F_inf, rs.T_inf)), M.Hv_inf);      // (:548-552)
-    st(G, GR_RES + 2, tol_p);
-    st(G, GR_RES + 3, tol_d);
+    if (writer) {
+      st(G, GR_RES + 2, tol_p);
+      st(G, GR_RES + 3, tol_d);
+    }
     const bool converged = (pres < tol_p) && (dres < tol_d);                                                        // (:555)
     bool infeasible = false;
     if (it > 1) {                                                                                                   // (hpp:425-427)
@@ -712,13 +711,13 @@ LOIK_DEV int decide(const ModelC& c_model, double* __restrict__ T, const int sta
     if (dx >= M.tol_tail || cy.dz_inf >= M.tol_tail) ns = (it >= M.max_iter) ? ST_INFEASIBLE_DONE : ST_TAIL;
     else ns = ST_INFEASIBLE_DONE;
   }
-  if (DEBUG) {
+  if (DEBUG && writer) {
     const int N = GR_NORMS;
     st(G, N + 0, cy.bTdy_p); st(G, N + 1, cy.bTdy_m); st(G, N + 2, cy.Av_inf); st(G, N + 3, cy.nu_inf);
     st(G, N + 4, rs.Hrefv_inf); st(G, N + 5, rs.F_inf); st(G, N + 6, rs.T_inf); st(G, N + 7, rs.dF_inf);
     st(G, N + 8, rs.dT_inf); st(G, N + 9, cy.dvis_inf); st(G, N + 10, cy.dnu_inf); st(G, N + 11, cy.dz_inf);
     st(G, N + 12, cy.dfis_inf); st(G, N + 13, cy.dyis_inf); st(G, N + 14, cy.dw_inf);
-    st(G, N + 15, cy.pres_task); st(G, N + 16, cy.pres_slack); st(G, N + 17, rs.dres_v); st(G, N + 18, rs.dres_nu);
+    st(G, N + 15, cy.pres_task); st(G, N + 16, cy.pres_slack); st(G, N + 17, rs.dres_v); st(G, N + 18, rs.T_inf);
     if (status == ST_RUNNING && it > 1) {
       st(G, N + 19, dyqp); st(G, N + 20, ATdy); st(G, N + 21, ubp); st(G, N + 22, lbm);
       st(G, N + 23, c1); st(G, N + 24, c2);

@@ -45,14 +45,17 @@ __global__ void __launch_bounds__(kBlock, MINB) k_iterate(const __grid_constant_
     if (status < ST_CONVERGED) {
       int it = ctl.y;
       double mu = ld(glob_blk(T, c_model.off), GR_MU);
+      const int nb = c_model.nb;
       for (int n = 0; n < iters; ++n) {
         ++it;
         const double mu_eq = c_model.mu_scale * mu;
-        sweep_backward(c_model, T, mu, mu_eq);
+        sweep_backward(c_model, T, mu, mu_eq, 1, nb);
         Carry cy;
-        sweep_forward<DEBUG>(c_model, T, mu, mu_eq, cy);
+        zero(cy);
+        sweep_forward<DEBUG>(c_model, T, mu, mu_eq, cy, 1, nb);
         Resid rs;
-        sweep_residual<DEBUG>(c_model, T, rs);
+        zero(rs);
+        sweep_residual<DEBUG>(c_model, T, rs, 1, nb);
         status = decide<DEBUG>(c_model, T, status, it, fixed != 0, cy, rs, mu);
         if (status >= ST_CONVERGED) break;
       }
@@ -65,6 +68,106 @@ __global__ void __launch_bounds__(kBlock, MINB) k_iterate(const __grid_constant_
     const unsigned m = __ballot_sync(0xffffffffu, active);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(S.n_active, __popc(m));
   }
+  }
+}
+
+// Segment-parallel variant for branching trees: one CTA = one tile of 32 instances, NW warps.  Warp w sweeps the
+// chains (segments) of the tree assigned to it; chains only exchange data through pending blocks / the parent's v
+// row in HBM/L2, ordered by CTA barriers between the levels of the segment DAG.  The running norms are combined
+// through shared memory in a fixed warp order, after which every warp takes the same decisions redundantly.
+template <bool DEBUG, int NW>
+__global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
+    k_iterate_seg(const __grid_constant__ ModelC c_model, const StateP S, const int iters, const int fixed) {
+  constexpr int NP = kCarryRows + 7;
+  __shared__ double part[NW][NP][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int limit = S.list ? *S.n_list : (S.n_dev ? *S.n_dev : S.n);
+  for (int tile = blockIdx.x; tile * 32 < limit; tile += gridDim.x) {
+    const int k = tile * 32 + lane;
+    const int s = k < limit ? (S.list ? S.list[k] : k) : -1;
+    double* T = nullptr;
+    int status = ST_CONVERGED, it = 0;
+    double mu = 0.0;
+    if (s >= 0) {
+      T = tile_ptr(S, c_model, s);
+      const int2 ctl = ld_ctl(c_model, T);
+      status = ctl.x; it = ctl.y;
+      mu = ld(glob_blk(T, c_model.off), GR_MU);
+    }
+    const bool was_active = status < ST_CONVERGED;
+    for (int n = 0; n < iters; ++n) {
+      const bool alive = status < ST_CONVERGED;
+      if (!__any_sync(0xffffffffu, alive)) break;  // identical in every warp of the CTA (same lanes, same decisions)
+      const double mu_eq = c_model.mu_scale * mu;
+      Carry cy;
+      Resid rs;
+      zero(cy);
+      zero(rs);
+      for (int lv = 0; lv < c_model.nblevel; ++lv) {
+        if (alive)
+          for (int g = 0; g < c_model.nseg; ++g)
+            if (c_model.seg[g].bwarp == w && c_model.seg[g].blevel == lv) sweep_backward(c_model, T, mu, mu_eq, c_model.seg[g].lo, c_model.seg[g].hi);
+        __syncthreads();
+      }
+      for (int lv = 0; lv < c_model.nflevel; ++lv) {
+        if (alive)
+          for (int g = 0; g < c_model.nseg; ++g)
+            if (c_model.seg[g].fwarp == w && c_model.seg[g].flevel == lv) sweep_forward<DEBUG>(c_model, T, mu, mu_eq, cy, c_model.seg[g].lo, c_model.seg[g].hi);
+        __syncthreads();
+      }
+      for (int lv = 0; lv < c_model.nblevel; ++lv) {
+        if (alive)
+          for (int g = 0; g < c_model.nseg; ++g)
+            if (c_model.seg[g].bwarp == w && c_model.seg[g].blevel == lv) sweep_residual<DEBUG>(c_model, T, rs, c_model.seg[g].lo, c_model.seg[g].hi);
+        __syncthreads();
+      }
+      {  // combine the per-warp partial norms / sums
+        const double* c = reinterpret_cast<const double*>(&cy);
+        const double* r = reinterpret_cast<const double*>(&rs);
+#pragma unroll
+        for (int q = 0; q < kCarryRows; ++q) part[w][q][lane] = c[q];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) part[w][kCarryRows + q][lane] = r[q];
+      }
+      __syncthreads();
+      {
+        double* c = reinterpret_cast<double*>(&cy);
+        double* r = reinterpret_cast<double*>(&rs);
+#pragma unroll
+        for (int q = 0; q < kCarryRows; ++q) {
+          const bool is_sum = q >= 8 && q <= 11;  // bTdy_p, bTdy_m, ubdw_p, lbdw_m are sums, the rest are inf-norms
+          double acc = part[0][q][lane];
+#pragma unroll
+          for (int ww = 1; ww < NW; ++ww) acc = is_sum ? acc + part[ww][q][lane] : fmax(acc, part[ww][q][lane]);
+          c[q] = acc;
+        }
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+          double acc = part[0][kCarryRows + q][lane];
+#pragma unroll
+          for (int ww = 1; ww < NW; ++ww) acc = fmax(acc, part[ww][kCarryRows + q][lane]);
+          r[q] = acc;
+        }
+      }
+      if (alive) {
+        ++it;
+        status = decide<DEBUG>(c_model, T, status, it, fixed != 0, cy, rs, mu, w == 0);
+      }
+      __syncthreads();  // part[] is rewritten in the next iteration
+    }
+    bool active = false;
+    if (was_active) {
+      if (w == 0) {
+        st_ctl(c_model, T, status, it);
+        st(glob_blk(T, c_model.off), GR_MU, mu);
+      }
+      active = status < ST_CONVERGED;
+    }
+    if (S.n_active && w == 0) {
+      const unsigned m = __ballot_sync(0xffffffffu, active);
+      if (lane == 0 && m) atomicAdd(S.n_active, __popc(m));
+    }
+    __syncthreads();  // the next tile's first sweeps must not overtake this tile's result stores of warp 0
   }
 }
 
@@ -184,7 +287,7 @@ __global__ void __launch_bounds__(kBlock) k_step_backward(const __grid_constant_
   double* T = tile_ptr(S, c_model, s);
   if (ld_ctl(c_model, T).x >= ST_CONVERGED) return;
   const double mu = ld(glob_blk(T, c_model.off), GR_MU);
-  sweep_backward(c_model, T, mu, c_model.mu_scale * mu);
+  sweep_backward(c_model, T, mu, c_model.mu_scale * mu, 1, c_model.nb);
 }
 __global__ void __launch_bounds__(kBlock) k_step_forward(const __grid_constant__ ModelC c_model, const StateP S) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -194,7 +297,8 @@ __global__ void __launch_bounds__(kBlock) k_step_forward(const __grid_constant__
   double* G = glob_blk(T, c_model.off);
   const double mu = ld(G, GR_MU);
   Carry cy;
-  sweep_forward<true>(c_model, T, mu, c_model.mu_scale * mu, cy);
+  zero(cy);
+  sweep_forward<true>(c_model, T, mu, c_model.mu_scale * mu, cy, 1, c_model.nb);
   const double* c = reinterpret_cast<const double*>(&cy);
   for (int k = 0; k < kCarryRows; ++k) st(G, GR_CARRY + k, c[k]);
   // ComputePrimalResiduals (hxx:494-503)
@@ -214,7 +318,8 @@ __global__ void __launch_bounds__(kBlock) k_step_residual(const __grid_constant_
   double* c = reinterpret_cast<double*>(&cy);
   for (int k = 0; k < kCarryRows; ++k) c[k] = ld(G, GR_CARRY + k);
   Resid rs;
-  sweep_residual<true>(c_model, T, rs);
+  zero(rs);
+  sweep_residual<true>(c_model, T, rs, 1, c_model.nb);
   double mu = ld(G, GR_MU);
   const int it = ctl.y + 1;
   status = decide<true>(c_model, T, status, it, fixed != 0, cy, rs, mu);
@@ -457,6 +562,17 @@ static inline int grid_for(int n, int block = kBlock) { return (n + block - 1) /
 static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S, int iters, int fixed, int max_ctas = 0) {
   int g = grid_for(h->batch);
   if (max_ctas > 0) g = std::min(g, max_ctas);
+  if (h->mc.nwarp > 1 && !h->debug) {  // segment-parallel: one CTA (nwarp warps) per tile
+    int gt = h->ntiles;
+    if (max_ctas > 0) gt = std::min(gt, max_ctas);
+    switch (h->mc.nwarp) {
+      case 2: k_iterate_seg<false, 2><<<gt, 64, 0, st>>>(h->mc, S, iters, fixed); break;
+      case 3: k_iterate_seg<false, 3><<<gt, 96, 0, st>>>(h->mc, S, iters, fixed); break;
+      default: k_iterate_seg<false, 4><<<gt, 128, 0, st>>>(h->mc, S, iters, fixed); break;
+    }
+    h->launches++;
+    return;
+  }
 #define LOIK_LAUNCH(DBG, MB) k_iterate<DBG, MB><<<g, kBlock, 0, st>>>(h->mc, S, iters, fixed)
   if (h->debug) { LOIK_LAUNCH(true, 4); }
   else if (h->minb == 4) { LOIK_LAUNCH(false, 4); }
@@ -553,23 +669,81 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   M.max_iter = params->max_iter; M.rho = params->rho; M.mu0 = params->mu; M.mu_scale = params->mu_equality_scale_factor;
   M.tol_abs = params->tol_abs; M.tol_rel = params->tol_rel; M.tol_pinf = params->tol_primal_inf; M.tol_dinf = params->tol_dual_inf;
   M.tol_tail = params->tol_tail_solve;
-  // tree bookkeeping: which contributions travel in registers (parent == i-1) and which go through a pending slot
-  std::vector<int> pend(nj, -1);
+  // tree bookkeeping.  A child's contribution to its parent travels in registers when the parent is the next joint
+  // swept and has no other child; every other edge gets its own pending block (single writer, no read-modify-write).
+  // Maximal register-carried chains are the segments that different warps can sweep (k_iterate_seg).
+  std::vector<int> nchild(nj, 0);
+  for (int i = 1; i < nj; ++i) nchild[model->parents[i]]++;
   int npend = 0;
-  for (int i = nj - 1; i >= 1; --i) {
+  for (int i = 1; i < nj; ++i) {
     JointC& J = M.j[i];
     J.parent = model->parents[i]; J.jtype = model->joint_types[i]; J.task = -1;
     for (int c = 0; c < 9; ++c) J.plR[c] = model->placement_R[9 * i + c];
     for (int c = 0; c < 3; ++c) { J.plp[c] = model->placement_p[3 * i + c]; J.axis[c] = model->joint_axes[3 * i + c]; }
-    J.carry = (J.parent > 0 && J.parent == i - 1) ? 1 : 0;
-    J.pfirst = 0; J.ppend = -1;
+    J.carry = (J.parent > 0 && J.parent == i - 1 && nchild[J.parent] == 1) ? 1 : 0;
+    J.pout = -1; J.npin = 0;
+  }
+  for (int i = 1; i < nj; ++i) {
+    JointC& J = M.j[i];
     if (J.parent > 0 && !J.carry) {
-      if (pend[J.parent] < 0) { pend[J.parent] = npend++; J.pfirst = 1; }
-      J.ppend = pend[J.parent];
+      JointC& P = M.j[J.parent];
+      if (P.npin >= kMaxPin) { delete h; return fail(LOIK_ERR_UNSUPPORTED, "loik_create: a joint has more branching children than kMaxPin"); }
+      J.pout = npend;
+      P.pin[P.npin++] = npend;
+      ++npend;
     }
   }
-  for (int i = 1; i < nj; ++i) M.j[i].pend = pend[i];
   M.npend = npend; h->npend = npend;
+  {
+    std::vector<int> seg_of(nj, -1), lo, hi;
+    for (int i = 1; i < nj; ++i) {
+      if (!M.j[i].carry) { lo.push_back(i); hi.push_back(i); }
+      else hi.back() = i;
+      seg_of[i] = (int)lo.size() - 1;
+    }
+    const int ns = (int)lo.size();
+    M.nseg = 1; M.nwarp = 1; M.nblevel = 1; M.nflevel = 1;
+    M.seg[0] = SegC{1, (short)(nj - 1), 0, 0, 0, 0};
+    bool want = ns >= 2 && ns <= kMaxSeg;
+    if (const char* e = std::getenv("LOIK_SEG")) want = want && std::atoi(e) != 0;
+    if (want) {
+      std::vector<int> fl(ns, 0), bl(ns, 0), par(ns, -1);
+      for (int g = 0; g < ns; ++g) {
+        const int p = M.j[lo[g]].parent;
+        if (p > 0) { par[g] = seg_of[p]; fl[g] = fl[par[g]] + 1; }
+      }
+      for (int g = ns - 1; g >= 0; --g)
+        if (par[g] >= 0) bl[par[g]] = std::max(bl[par[g]], bl[g] + 1);
+      int nbl = 0, nfl = 0, width = 1;
+      for (int g = 0; g < ns; ++g) { nbl = std::max(nbl, bl[g] + 1); nfl = std::max(nfl, fl[g] + 1); }
+      for (int lv = 0; lv < std::max(nbl, nfl); ++lv) {
+        int cb = 0, cf = 0;
+        for (int g = 0; g < ns; ++g) { cb += bl[g] == lv; cf += fl[g] == lv; }
+        width = std::max(width, std::max(cb, cf));
+      }
+      const int NW = std::min(4, width);
+      if (NW >= 2) {
+        M.nseg = ns; M.nwarp = NW; M.nblevel = nbl; M.nflevel = nfl;
+        // longest-processing-time-first assignment of the segments of every level to the warps
+        auto assign = [&](const std::vector<int>& level, int nlev, bool backward) {
+          for (int lv = 0; lv < nlev; ++lv) {
+            std::vector<int> ids;
+            for (int g = 0; g < ns; ++g) if (level[g] == lv) ids.push_back(g);
+            std::sort(ids.begin(), ids.end(), [&](int a, int b) { return (hi[a] - lo[a]) > (hi[b] - lo[b]); });
+            std::vector<int> load(NW, 0);
+            for (int g : ids) {
+              const int wmin = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+              load[wmin] += hi[g] - lo[g] + 1;
+              if (backward) M.seg[g].bwarp = (short)wmin; else M.seg[g].fwarp = (short)wmin;
+            }
+          }
+        };
+        for (int g = 0; g < ns; ++g) { M.seg[g].lo = (short)lo[g]; M.seg[g].hi = (short)hi[g]; M.seg[g].blevel = (short)bl[g]; M.seg[g].flevel = (short)fl[g]; }
+        assign(bl, nbl, true);
+        assign(fl, nfl, false);
+      }
+    }
+  }
   // tile record layout: [globals | joint blocks | task blocks | pending blocks | debug vectors]
   const int nb = h->nb, nc = std::max(h->nc, 1);
   Offs& O = M.off;
