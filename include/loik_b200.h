@@ -122,6 +122,7 @@ typedef enum loik_norm_index {
   LOIK_N_PRIMAL_RES_TASK, LOIK_N_PRIMAL_RES_SLACK, LOIK_N_DUAL_RES_V, LOIK_N_DUAL_RES_NU,
   LOIK_N_DELTA_Y_QP_INF, LOIK_N_AT_DELTA_Y_QP_INF, LOIK_N_UB_T_DELTA_Y_PLUS, LOIK_N_LB_T_DELTA_Y_MINUS,
   LOIK_N_PINF_COND_1, LOIK_N_PINF_COND_2, LOIK_N_DELTA_X_QP_INF,
+  LOIK_N_CONVERGED, LOIK_N_PRIMAL_INFEASIBLE, /* flags raised by the per-method steps (LOIK_STEP_CHECK_*) */
   LOIK_NUM_NORMS
 } loik_norm_index;
 
@@ -131,8 +132,21 @@ typedef enum loik_norm_index {
 typedef enum loik_step_id {
   LOIK_STEP_BACKWARD = 0, /* UpdatePrev + ResetInfNorms + FwdPass1 + BwdPassOptimizedVisitor      (hxx:290-354) */
   LOIK_STEP_FORWARD,      /* FwdPass2OptimizedVisitor + BoxProj + DualUpdate + ComputePrimalResiduals (hxx:361-503) */
-  LOIK_STEP_RESIDUAL      /* ComputeDualResiduals + CheckConvergence + CheckFeasibility + UpdateMu
+  LOIK_STEP_RESIDUAL,     /* ComputeDualResiduals + CheckConvergence + CheckFeasibility + UpdateMu
                              + the loop-control of Solve()/InfeasibilityTailSolve()               (hxx:510-641) */
+  /* the reference's public methods one by one (hpp:192-264).  They ignore / do not advance the loop control, keep the
+   * running norms in LOIK_F_NORMS and need loik_set_debug(h, 1). */
+  LOIK_STEP_UPDATE_PREV,       /* ik_id_data_.UpdatePrev(): nothing to do (the sweeps read old values before overwriting) */
+  LOIK_STEP_RESET_INF_NORMS,   /* ik_id_data_.ResetInfNorms()    (data hxx:165-182) */
+  LOIK_STEP_FWD_PASS1,         /* FwdPass1()                     (hxx:290-338): His, pis, r = w - mu z */
+  LOIK_STEP_BWD_PASS,          /* BwdPassOptimizedVisitor()      (hxx:345-354) */
+  LOIK_STEP_FWD_PASS2,         /* FwdPass2OptimizedVisitor()     (hxx:361-377) */
+  LOIK_STEP_BOX_PROJ,          /* BoxProj()                      (hxx:384-397) */
+  LOIK_STEP_DUAL_UPDATE,       /* DualUpdate()                   (hxx:404-461) */
+  LOIK_STEP_COMPUTE_RESIDUALS, /* ComputeResiduals()             (hxx:529-533) */
+  LOIK_STEP_CHECK_CONVERGENCE, /* CheckConvergence()             (hxx:540-565) */
+  LOIK_STEP_CHECK_FEASIBILITY, /* CheckFeasibility()             (hxx:572-606) */
+  LOIK_STEP_UPDATE_MU          /* UpdateMu()                     (hxx:613-641) */
 } loik_step_id;
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
@@ -190,9 +204,11 @@ LOIK_API int loik_integrate(loik_solver* h, double dt, void* stream);
 LOIK_API int loik_iterate_fixed(loik_solver* h, int32_t iters, int32_t reset, void* stream);
 
 /* ---- step-by-step interface (parity tests) ---------------------------------------------------- */
+/* FwdPassInit(q)  (hxx:253-283) alone: q [batch][nq] at `loc`. */
+LOIK_API int loik_fwd_pass_init(loik_solver* h, const double* q, int32_t loc, void* stream);
 /* ik_id_data_.ResetRecursion() + ResetSolver(): what Solve() does before its loop (hpp:370-374). */
 LOIK_API int loik_reset_recursion(loik_solver* h, void* stream);
-/* One fused step of the current iteration on every still-active instance. */
+/* One step of the current iteration on every instance (the fused ones: on every still-active instance). */
 LOIK_API int loik_step(loik_solver* h, int32_t step_id, void* stream);
 /* Keep the reference's running norms, feasibility scalars and residual vectors readable (slower). */
 LOIK_API int loik_set_debug(loik_solver* h, int32_t on);

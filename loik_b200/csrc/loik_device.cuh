@@ -58,7 +58,7 @@ enum : int {  // rows of a joint block
 };
 enum : int { TR_Y = 0, TR_ATY = 6, TR_B = 12, TR_ATB = 18, TR_ROWS = 24 };        // rows of a task block
 enum : int { PR_H = 0, PR_F = 27, PR_ROWS = 33 };                                 // rows of a pending-accumulator block
-enum : int { GR_MU = 0, GR_BINF = 1, GR_CTL = 2, GR_RES = 3, GR_CARRY = 7, GR_NORMS = 21, GR_ROWS = 47 };  // globals
+enum : int { GR_MU = 0, GR_BINF = 1, GR_CTL = 2, GR_RES = 3, GR_CARRY = 7, GR_NORMS = 21, GR_ROWS = 49 };  // globals (norms: 28 rows)
 
 struct Offs {
   int glob, joint0, task0, pend0;  // first row of the globals, of joint 1, of task 0, of pending slot 0
@@ -725,6 +725,186 @@ LOIK_DEV int decide(const ModelC& c_model, double* __restrict__ T, const int sta
     if (status == ST_TAIL || it > 1) st(G, N + 25, dx);
   }
   return ns;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The reference's public per-step methods one by one (loik-loid-optimized.hpp:192-264), for tests that drive the
+// solver the way tests/loik-loid.cpp:340-478 does.  They work on the home arena, ignore the loop-control status and
+// keep the reference's running norms in the GR_NORMS rows (index = loik_norm_index).  Same device maths as the
+// fused sweeps; the production path never calls them.
+// ---------------------------------------------------------------------------------------------
+enum : int { N_BTDY_P = 0, N_BTDY_M, N_AV, N_NU, N_HREFV, N_F, N_T, N_DF, N_DT, N_DVIS, N_DNU, N_DZ, N_DFIS, N_DYIS, N_DW,
+             N_PRES_TASK, N_PRES_SLACK, N_DRES_V, N_DRES_NU, N_DYQP, N_ATDY, N_UBP, N_LBM, N_C1, N_C2, N_DX, N_CONVERGED,
+             N_PINFEASIBLE };
+
+// ResetInfNorms (data hxx:165-182)
+LOIK_DEV void fine_reset_inf_norms(const ModelC& M, double* __restrict__ T) {
+  double* G = glob_blk(T, M.off);
+  for (int k = 0; k <= N_DW; ++k) st(G, GR_NORMS + k, 0.0);
+  st(G, GR_CARRY + 10, 0.0);  // ub^T max(delta_w, 0)
+  st(G, GR_CARRY + 11, 0.0);  // lb^T min(delta_w, 0)
+}
+// FwdPass1 (hxx:290-338): His, pis (rows JR_H / JR_P), r = w - mu_ineq z (row JR_R); R = mu_ineq is implicit
+LOIK_DEV void fine_fwdpass1(const ModelC& M, double* __restrict__ T, const double mu, const double mu_eq) {
+  const Offs& O = M.off;
+  for (int i = 1; i <= M.nb; ++i) {
+    const JointC& J = M.j[i];
+    double* Pj = joint_blk(T, O, i - 1);
+    double A[6], B[9], D[6], p[6];
+    for (int c = 0; c < 6; ++c) { p[c] = -M.rho * ld(Pj, JR_V + c) - J.Hv[c]; A[c] = J.HrA[c]; D[c] = J.HrD[c]; }
+    for (int c = 0; c < 9; ++c) B[c] = J.HrB[c];
+    A[0] += M.rho; A[3] += M.rho; A[5] += M.rho; D[0] += M.rho; D[3] += M.rho; D[5] += M.rho;
+    if (J.task >= 0) {
+      const TaskC& K = M.t[J.task];
+      const double* Pk = task_blk(T, O, J.task);
+      for (int c = 0; c < 6; ++c) { A[c] += mu_eq * K.AtA_A[c]; D[c] += mu_eq * K.AtA_D[c]; p[c] += ld(Pk, TR_ATY + c) - mu_eq * ld(Pk, TR_ATB + c); }
+      for (int c = 0; c < 9; ++c) B[c] += mu_eq * K.AtA_B[c];
+    }
+    const double r0 = ld(Pj, JR_W) - mu * ld(Pj, JR_Z);
+    for (int c = 0; c < 6; ++c) { st(Pj, JR_H + c, A[c]); st(Pj, JR_H + 15 + c, D[c]); st(Pj, JR_P + c, p[c]); }
+    for (int c = 0; c < 9; ++c) st(Pj, JR_H + 6 + c, B[c]);
+    st(Pj, JR_R, r0);
+  }
+}
+// FwdPass2OptimizedVisitor (hxx:361-377, algo :102-163)
+LOIK_DEV void fine_fwdpass2(const ModelC& M, double* __restrict__ T) {
+  const Offs& O = M.off;
+  double* G = glob_blk(T, O);
+  double nu_inf = ld(G, GR_NORMS + N_NU), dfis = ld(G, GR_NORMS + N_DFIS), hrefv = ld(G, GR_NORMS + N_HREFV), dvis = ld(G, GR_NORMS + N_DVIS);
+  double dnu = 0.0;
+  for (int i = 1; i <= M.nb; ++i) {
+    const JointC& J = M.j[i];
+    double* Pj = joint_blk(T, O, i - 1);
+    double vin[6], R[9], t[3], v[6];
+    for (int c = 0; c < 6; ++c) vin[c] = J.parent == 0 ? 0.0 : ld(joint_blk(T, O, J.parent - 1), JR_V + c);
+    make_xf(J, ld(Pj, JR_JQ), ld(Pj, JR_JQ + 1), R, t);
+    actinv_motion(R, t, vin, v);
+    double acc = 0.0;
+    for (int c = 0; c < 6; ++c) acc += ld(Pj, JR_UD + c) * v[c];
+    const double nu = -acc - ld(Pj, JR_DINV) * ld(Pj, JR_R);
+    nu_inf = amax(nu_inf, nu);
+    S_axpy(J, nu, v);
+    double A[6], B[9], D[6];
+    for (int c = 0; c < 6; ++c) { A[c] = ld(Pj, JR_H + c); D[c] = ld(Pj, JR_H + 15 + c); }
+    for (int c = 0; c < 9; ++c) B[c] = ld(Pj, JR_H + 6 + c);
+    double f[6], Hrv[6];
+    for (int a = 0; a < 3; ++a) {
+      f[a] = A[si(a, 0)] * v[0] + A[si(a, 1)] * v[1] + A[si(a, 2)] * v[2] + B[3 * a] * v[3] + B[3 * a + 1] * v[4] + B[3 * a + 2] * v[5] + ld(Pj, JR_P + a);
+      f[3 + a] = B[a] * v[0] + B[3 + a] * v[1] + B[6 + a] * v[2] + D[si(a, 0)] * v[3] + D[si(a, 1)] * v[4] + D[si(a, 2)] * v[5] + ld(Pj, JR_P + 3 + a);
+      Hrv[a] = J.HrA[si(a, 0)] * v[0] + J.HrA[si(a, 1)] * v[1] + J.HrA[si(a, 2)] * v[2] + J.HrB[3 * a] * v[3] + J.HrB[3 * a + 1] * v[4] + J.HrB[3 * a + 2] * v[5];
+      Hrv[3 + a] = J.HrB[a] * v[0] + J.HrB[3 + a] * v[1] + J.HrB[6 + a] * v[2] + J.HrD[si(a, 0)] * v[3] + J.HrD[si(a, 1)] * v[4] + J.HrD[si(a, 2)] * v[5];
+    }
+    for (int c = 0; c < 6; ++c) {
+      dvis = amax(dvis, v[c] - ld(Pj, JR_V + c));
+      dfis = amax(dfis, f[c] - ld(Pj, JR_F + c));
+      hrefv = amax(hrefv, Hrv[c]);
+    }
+    dnu = amax(dnu, nu - ld(Pj, JR_NU));
+    for (int c = 0; c < 6; ++c) { st(Pj, JR_V + c, v[c]); st(Pj, JR_F + c, f[c]); }
+    st(Pj, JR_NU, nu);
+  }
+  st(G, GR_NORMS + N_NU, nu_inf); st(G, GR_NORMS + N_DFIS, dfis); st(G, GR_NORMS + N_HREFV, hrefv);
+  st(G, GR_NORMS + N_DVIS, dvis); st(G, GR_NORMS + N_DNU, dnu);
+}
+// BoxProj (hxx:384-397)
+LOIK_DEV void fine_boxproj(const ModelC& M, double* __restrict__ T, const double mu) {
+  const Offs& O = M.off;
+  double* G = glob_blk(T, O);
+  double dz = 0.0, slack = 0.0;
+  for (int i = 1; i <= M.nb; ++i) {
+    const JointC& J = M.j[i];
+    double* Pj = joint_blk(T, O, i - 1);
+    const double lb = M.bounds_per_instance ? ld(Pj, JR_LB) : J.lb, ub = M.bounds_per_instance ? ld(Pj, JR_UB) : J.ub;
+    const double nu = ld(Pj, JR_NU);
+    const double z = fmin(ub, fmax(lb, nu + (1.0 / mu) * ld(Pj, JR_W)));
+    dz = amax(dz, z - ld(Pj, JR_Z));
+    slack = amax(slack, nu - z);
+    st(Pj, JR_Z, z);
+    st(T, O.prv + 6 * M.nb + (i - 1), nu - z);
+  }
+  st(G, GR_NORMS + N_DZ, dz);
+  st(G, GR_NORMS + N_PRES_SLACK, slack);
+}
+// DualUpdate (hxx:404-461)
+LOIK_DEV void fine_dualupdate(const ModelC& M, double* __restrict__ T, const double mu, const double mu_eq) {
+  const Offs& O = M.off;
+  double* G = glob_blk(T, O);
+  double dyis = ld(G, GR_NORMS + N_DYIS), Av_inf = ld(G, GR_NORMS + N_AV), bp = ld(G, GR_NORMS + N_BTDY_P), bm = ld(G, GR_NORMS + N_BTDY_M);
+  double ptask = 0.0;
+  for (int k = 0; k < M.nc; ++k) {
+    const TaskC& K = M.t[k];
+    double* Pk = task_blk(T, O, k);
+    const double* Pj = joint_blk(T, O, K.joint - 1);
+    double v[6], y[6], plus = 0.0, minus = 0.0;
+    for (int c = 0; c < 6; ++c) v[c] = ld(Pj, JR_V + c);
+    for (int a = 0; a < 6; ++a) {
+      const double Av = K.A[6 * a] * v[0] + K.A[6 * a + 1] * v[1] + K.A[6 * a + 2] * v[2] + K.A[6 * a + 3] * v[3] + K.A[6 * a + 4] * v[4] + K.A[6 * a + 5] * v[5];
+      const double bi = ld(Pk, TR_B + a), e = Av - bi, dy = mu_eq * e;
+      y[a] = ld(Pk, TR_Y + a) + dy;
+      dyis = amax(dyis, dy); Av_inf = amax(Av_inf, Av); ptask = amax(ptask, e);
+      plus += bi * fmax(dy, 0.0); minus += bi * fmin(dy, 0.0);
+      st(T, O.prv + 6 * (K.joint - 1) + a, e);
+    }
+    bp += plus; bm += minus;
+    for (int a = 0; a < 6; ++a) {
+      st(Pk, TR_Y + a, y[a]);
+      st(Pk, TR_ATY + a, K.A[a] * y[0] + K.A[6 + a] * y[1] + K.A[12 + a] * y[2] + K.A[18 + a] * y[3] + K.A[24 + a] * y[4] + K.A[30 + a] * y[5]);
+    }
+  }
+  double dw_inf = 0.0, ubdw = 0.0, lbdw = 0.0;
+  for (int i = 1; i <= M.nb; ++i) {
+    const JointC& J = M.j[i];
+    double* Pj = joint_blk(T, O, i - 1);
+    const double lb = M.bounds_per_instance ? ld(Pj, JR_LB) : J.lb, ub = M.bounds_per_instance ? ld(Pj, JR_UB) : J.ub;
+    const double dw = mu * (ld(Pj, JR_NU) - ld(Pj, JR_Z));
+    st(Pj, JR_W, ld(Pj, JR_W) + dw);
+    dw_inf = amax(dw_inf, dw);
+    ubdw += ub * fmax(dw, 0.0); lbdw += lb * fmin(dw, 0.0);
+  }
+  st(G, GR_NORMS + N_DYIS, dyis); st(G, GR_NORMS + N_AV, Av_inf); st(G, GR_NORMS + N_BTDY_P, bp); st(G, GR_NORMS + N_BTDY_M, bm);
+  st(G, GR_NORMS + N_PRES_TASK, ptask); st(G, GR_NORMS + N_DW, dw_inf);
+  st(G, GR_CARRY + 10, ubdw); st(G, GR_CARRY + 11, lbdw);
+}
+// ComputeResiduals (hxx:529-533)
+LOIK_DEV void fine_compute_residuals(const ModelC& M, double* __restrict__ T) {
+  double* G = glob_blk(T, M.off);
+  st(G, GR_RES + 0, fmax(ld(G, GR_NORMS + N_PRES_TASK), ld(G, GR_NORMS + N_PRES_SLACK)));
+  Resid rs;
+  zero(rs);
+  sweep_residual<true>(M, T, rs, 1, M.nb);
+  st(G, GR_NORMS + N_F, rs.F_inf); st(G, GR_NORMS + N_T, rs.T_inf); st(G, GR_NORMS + N_DF, rs.dF_inf); st(G, GR_NORMS + N_DT, rs.dT_inf);
+  st(G, GR_NORMS + N_DRES_V, rs.dres_v); st(G, GR_NORMS + N_DRES_NU, rs.T_inf);
+  st(G, GR_RES + 1, fmax(rs.dres_v, rs.T_inf));
+}
+// CheckConvergence (hxx:540-565)
+LOIK_DEV void fine_check_convergence(const ModelC& M, double* __restrict__ T) {
+  double* G = glob_blk(T, M.off);
+  const double nu_inf = ld(G, GR_NORMS + N_NU);
+  const double tol_p = M.tol_abs + M.tol_rel * fmax(fmax(ld(G, GR_NORMS + N_AV), nu_inf), fmax(ld(G, GR_BINF), nu_inf));
+  const double tol_d = M.tol_abs + M.tol_rel * fmax(fmax(ld(G, GR_NORMS + N_HREFV), fmax(ld(G, GR_NORMS + N_F), ld(G, GR_NORMS + N_T))), M.Hv_inf);
+  st(G, GR_RES + 2, tol_p); st(G, GR_RES + 3, tol_d);
+  if (ld(G, GR_RES + 0) < tol_p && ld(G, GR_RES + 1) < tol_d) st(G, GR_NORMS + N_CONVERGED, 1.0);
+}
+// CheckFeasibility (hxx:572-606)
+LOIK_DEV void fine_check_feasibility(const ModelC& M, double* __restrict__ T) {
+  double* G = glob_blk(T, M.off);
+  const double dyqp = fmax(ld(G, GR_NORMS + N_DFIS), fmax(ld(G, GR_NORMS + N_DYIS), ld(G, GR_NORMS + N_DW)));
+  const double ATdy = fmax(ld(G, GR_NORMS + N_DF), ld(G, GR_NORMS + N_DT));
+  const bool c1 = ATdy <= M.tol_pinf * dyqp;
+  const double ubp = ld(G, GR_NORMS + N_BTDY_P) + ld(G, GR_CARRY + 10), lbm = ld(G, GR_NORMS + N_BTDY_M) + ld(G, GR_CARRY + 11);
+  const bool c2 = (ubp + lbm) <= M.tol_pinf * dyqp;
+  st(G, GR_NORMS + N_DYQP, dyqp); st(G, GR_NORMS + N_ATDY, ATdy); st(G, GR_NORMS + N_UBP, ubp); st(G, GR_NORMS + N_LBM, lbm);
+  st(G, GR_NORMS + N_C1, c1 ? 1.0 : 0.0); st(G, GR_NORMS + N_C2, c2 ? 1.0 : 0.0);
+  if (c1 && c2) st(G, GR_NORMS + N_PINFEASIBLE, 1.0);
+  st(G, GR_NORMS + N_DX, fmax(ld(G, GR_NORMS + N_DVIS), ld(G, GR_NORMS + N_DNU)));
+}
+// UpdateMu (hxx:613-641)
+LOIK_DEV void fine_update_mu(const ModelC& M, double* __restrict__ T) {
+  double* G = glob_blk(T, M.off);
+  const double pres = ld(G, GR_RES + 0), dres = ld(G, GR_RES + 1);
+  double mu = ld(G, GR_MU);
+  if (pres > 10 * dres) mu *= 10; else if (dres > 10 * pres) mu *= 0.1;
+  st(G, GR_MU, mu);
 }
 
 }  // namespace loik

@@ -327,6 +327,27 @@ __global__ void __launch_bounds__(kBlock) k_step_residual(const __grid_constant_
   st(G, GR_MU, mu);
 }
 
+// The reference's public methods one by one (LOIK_STEP_UPDATE_PREV ... LOIK_STEP_UPDATE_MU), every instance.
+__global__ void __launch_bounds__(kBlock) k_fine(const __grid_constant__ ModelC c_model, const StateP S, const int which) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S.n) return;
+  double* T = tile_ptr(S, c_model, s);
+  const double mu = ld(glob_blk(T, c_model.off), GR_MU), mu_eq = c_model.mu_scale * mu;
+  switch (which) {
+    case LOIK_STEP_RESET_INF_NORMS: fine_reset_inf_norms(c_model, T); break;
+    case LOIK_STEP_FWD_PASS1: fine_fwdpass1(c_model, T, mu, mu_eq); break;
+    case LOIK_STEP_BWD_PASS: sweep_backward(c_model, T, mu, mu_eq, 1, c_model.nb); break;
+    case LOIK_STEP_FWD_PASS2: fine_fwdpass2(c_model, T); break;
+    case LOIK_STEP_BOX_PROJ: fine_boxproj(c_model, T, mu); break;
+    case LOIK_STEP_DUAL_UPDATE: fine_dualupdate(c_model, T, mu, mu_eq); break;
+    case LOIK_STEP_COMPUTE_RESIDUALS: fine_compute_residuals(c_model, T); break;
+    case LOIK_STEP_CHECK_CONVERGENCE: fine_check_convergence(c_model, T); break;
+    case LOIK_STEP_CHECK_FEASIBILITY: fine_check_feasibility(c_model, T); break;
+    case LOIK_STEP_UPDATE_MU: fine_update_mu(c_model, T); break;
+    default: break;
+  }
+}
+
 enum : int { RST_WZ = 1, RST_NU = 2, RST_VFF = 4, RST_YATY = 8, RST_SOLVER = 16 };
 
 // ik_id_data_.Reset / ResetRecursion (data hxx:114-154) + ResetSolver (hpp:168-186)
@@ -351,6 +372,8 @@ __global__ void k_reset(const __grid_constant__ ModelC c_model, const StateP S, 
   if (flags & RST_SOLVER) {
     st_ctl(c_model, T, ST_RUNNING, 0);
     st(glob_blk(T, O), GR_MU, c_model.mu0);
+    st(glob_blk(T, O), GR_NORMS + N_CONVERGED, 0.0);
+    st(glob_blk(T, O), GR_NORMS + N_PINFEASIBLE, 0.0);
   }
 }
 
@@ -1059,6 +1082,23 @@ static int solve_scheduled(loik_solver* h, cudaStream_t st, int reset_flags, int
   return LOIK_OK;
 }
 
+int loik_fwd_pass_init(loik_solver* h, const double* q, int32_t loc, void* stream) {
+  if (!h || !q) return fail(LOIK_ERR_INVALID, "loik_fwd_pass_init: null argument");
+  if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_fwd_pass_init: call loik_solve_init first");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  const size_t q_bytes = (size_t)h->batch * h->nb * sizeof(double);
+  int rc;
+  if (loc != LOIK_DEVICE) { rc = ensure_stage(h, q_bytes + 64, loc == LOIK_HOST); if (rc) return rc; }
+  const void* dq;
+  rc = to_device(h, q, q_bytes, loc, 0, st, &dq); if (rc) return rc;
+  k_set_q<<<grid_for(h->batch), kBlock, kBlock * h->nb * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (loc == LOIK_HOST) CK(cudaStreamSynchronize(st));
+  return LOIK_OK;
+}
+
 int loik_reset_recursion(loik_solver* h, void* stream) {
   if (!h) return fail(LOIK_ERR_INVALID, "null handle");
   if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_reset_recursion: call loik_solve_init first");
@@ -1210,6 +1250,13 @@ int loik_step(loik_solver* h, int32_t step_id, void* stream) {
     case LOIK_STEP_BACKWARD: k_step_backward<<<g, kBlock, 0, st>>>(h->mc, h->S); break;
     case LOIK_STEP_FORWARD: k_step_forward<<<g, kBlock, 0, st>>>(h->mc, h->S); break;
     case LOIK_STEP_RESIDUAL: k_step_residual<<<g, kBlock, 0, st>>>(h->mc, h->S, 0); h->sweeps++; break;
+    case LOIK_STEP_UPDATE_PREV: return LOIK_OK;  // the sweeps read the previous iterate before overwriting it
+    case LOIK_STEP_RESET_INF_NORMS: case LOIK_STEP_FWD_PASS1: case LOIK_STEP_BWD_PASS: case LOIK_STEP_FWD_PASS2:
+    case LOIK_STEP_BOX_PROJ: case LOIK_STEP_DUAL_UPDATE: case LOIK_STEP_COMPUTE_RESIDUALS: case LOIK_STEP_CHECK_CONVERGENCE:
+    case LOIK_STEP_CHECK_FEASIBILITY: case LOIK_STEP_UPDATE_MU:
+      if (!h->debug) return fail(LOIK_ERR_STATE, "loik_step: the per-method steps need loik_set_debug(h, 1)");
+      k_fine<<<g, kBlock, 0, st>>>(h->mc, h->S, step_id);
+      break;
     default: return fail(LOIK_ERR_INVALID, "loik_step: unknown step id");
   }
   h->launches++;

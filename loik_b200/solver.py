@@ -26,7 +26,9 @@ LOIK_HOST, LOIK_DEVICE, LOIK_HOST_PINNED = 0, 1, 2
 # loik_field (include/loik_b200.h)
 (F_Z, F_NU, F_W, F_Y, F_V, F_F, F_ATY, F_FDPA, F_STF_PLUS_W, F_H, F_P, F_UDINV, F_DINV, F_R, F_LIMI, F_MU, F_ITER,
  F_STATUS, F_RESIDUALS, F_NORMS, F_PRIMAL_RES_VEC, F_DUAL_RES_VEC, F_Q) = range(23)
-STEP_BACKWARD, STEP_FORWARD, STEP_RESIDUAL = range(3)
+(STEP_BACKWARD, STEP_FORWARD, STEP_RESIDUAL, STEP_UPDATE_PREV, STEP_RESET_INF_NORMS, STEP_FWD_PASS1, STEP_BWD_PASS,
+ STEP_FWD_PASS2, STEP_BOX_PROJ, STEP_DUAL_UPDATE, STEP_COMPUTE_RESIDUALS, STEP_CHECK_CONVERGENCE, STEP_CHECK_FEASIBILITY,
+ STEP_UPDATE_MU) = range(14)
 
 NORM_NAMES = ["bT_delta_y_plus", "bT_delta_y_minus", "Av_inf_norm", "nu_inf_norm", "Href_v_inf_norm",
               "fis_diff_plus_Aty_inf_norm", "Stf_plus_w_inf_norm", "delta_fis_diff_plus_Aty_inf_norm",
@@ -34,11 +36,12 @@ NORM_NAMES = ["bT_delta_y_plus", "bT_delta_y_minus", "Av_inf_norm", "nu_inf_norm
               "delta_fis_inf_norm", "delta_yis_inf_norm", "delta_w_inf_norm", "primal_residual_task",
               "primal_residual_slack", "dual_residual_v", "dual_residual_nu", "delta_y_qp_inf_norm",
               "A_qp_T_delta_y_qp_inf_norm", "ub_qp_T_delta_y_qp_plus", "lb_qp_T_delta_y_qp_minus",
-              "primal_infeasibility_cond_1", "primal_infeasibility_cond_2", "delta_x_qp_inf_norm"]
+              "primal_infeasibility_cond_1", "primal_infeasibility_cond_2", "delta_x_qp_inf_norm", "converged",
+              "primal_infeasible"]
 
 EXPORTS = ["loik_abi_version", "loik_last_error", "loik_create", "loik_destroy", "loik_solve_init",
            "loik_update_references", "loik_solve", "loik_solve_full", "loik_solve_task", "loik_integrate", "loik_iterate_fixed",
-           "loik_reset_recursion", "loik_step", "loik_set_debug", "loik_get", "loik_get_stats", "loik_reduce_stats", "loik_launch_count",
+           "loik_fwd_pass_init", "loik_reset_recursion", "loik_step", "loik_set_debug", "loik_get", "loik_get_stats", "loik_reduce_stats", "loik_launch_count",
            "loik_set_max_iter", "loik_set_rho", "loik_set_mu", "loik_set_tol_tail_solve", "loik_set_warm_start",
            "loik_active_count_device_ptr", "loik_solve_begin", "loik_solve_chunk", "loik_solve_end"]
 
@@ -82,6 +85,7 @@ def load_library(path: str | None = None):
     lib.loik_iterate_fixed.argtypes = [vp, i32, i32, vp]
     lib.loik_integrate.argtypes = [vp, C.c_double, vp]
     lib.loik_reset_recursion.argtypes = [vp, vp]
+    lib.loik_fwd_pass_init.argtypes = [vp, dp, i32, vp]
     lib.loik_step.argtypes = [vp, i32, vp]
     lib.loik_set_debug.argtypes = [vp, i32]
     lib.loik_get.argtypes = [vp, i32, vp, i32, vp]
@@ -277,6 +281,47 @@ class FirstOrderLoikOptimized:
     def Integrate(self, dt):
         """q <- q + dt * z and FwdPassInit(q) on the device (outer IK loop)."""
         self._check(self._lib.loik_integrate(self._h, float(dt), _current_stream()))
+
+    # ---- the reference's public per-step methods, one by one (loik-loid-optimized.hpp:192-264); need set_debug(True)
+    def _fine(self, step):
+        self._check(self._lib.loik_step(self._h, step, _current_stream()))
+
+    def FwdPassInit(self, q):
+        qb = _Buf(q)
+        self._check(self._lib.loik_fwd_pass_init(self._h, qb.ptr, qb.loc, _current_stream()))
+
+    def UpdatePrev(self):
+        self._fine(STEP_UPDATE_PREV)
+
+    def ResetInfNorms(self):
+        self._fine(STEP_RESET_INF_NORMS)
+
+    def FwdPass1(self):
+        self._fine(STEP_FWD_PASS1)
+
+    def BwdPassOptimizedVisitor(self):
+        self._fine(STEP_BWD_PASS)
+
+    def FwdPass2OptimizedVisitor(self):
+        self._fine(STEP_FWD_PASS2)
+
+    def BoxProj(self):
+        self._fine(STEP_BOX_PROJ)
+
+    def DualUpdate(self):
+        self._fine(STEP_DUAL_UPDATE)
+
+    def ComputeResiduals(self):
+        self._fine(STEP_COMPUTE_RESIDUALS)
+
+    def CheckConvergence(self):
+        self._fine(STEP_CHECK_CONVERGENCE)
+
+    def CheckFeasibility(self):
+        self._fine(STEP_CHECK_FEASIBILITY)
+
+    def UpdateMu(self):
+        self._fine(STEP_UPDATE_MU)
 
     def IterateFixed(self, iters, reset=True):
         self._check(self._lib.loik_iterate_fixed(self._h, int(iters), int(bool(reset)), _current_stream()))

@@ -405,3 +405,40 @@ def test_outer_ik_loop_on_device():
         assert rel_inf(z1[i], o.z) < 1e-6
     assert bad <= 1
     G.close()
+
+
+def test_update_references_per_joint():
+    """problem_.UpdateReferences(H_refs, v_refs) (ik-id-description-optimized.hpp:103-121): per-joint symmetric weights and
+    reference velocities after SolveInit, against the oracle driven the same way."""
+    model = robots.panda(fingers=True)
+    B = 96
+    rng = np.random.default_rng(21)
+    pb = problems.random_batch(model, B, seed=14)
+    H_refs = np.zeros((model.nj, 6, 6))
+    v_refs = 0.05 * rng.normal(size=(model.nj, 6))
+    for i in range(model.nj):
+        M = rng.normal(size=(6, 6))
+        H_refs[i] = np.eye(6) * rng.uniform(0.5, 2.0) + 0.05 * (M + M.T)
+    params = problems.bench_params(1, max_iter=60)
+    G = _gpu(model, params, B)
+    _solve_init(G, pb)
+    G.UpdateReferences(H_refs, v_refs)
+    G.Solve()
+    z, it, mu = G.z, G.get_iter(), G.get_mu()
+    bad = 0
+    for i in range(B):
+        o = _oracle(model, params)
+        o.SolveInit(*instance(pb, i))
+        o.UpdateReferences(H_refs, v_refs)
+        o.Solve()
+        if o.get_iter() != it[i] or o.get_mu() != mu[i]:
+            bad += 1
+            continue
+        assert rel_inf(z[i], o.z) < 1e-6, i
+    assert bad == 0
+    with pytest.raises(RuntimeError, match="symmetric"):
+        Hn = H_refs.copy(); Hn[2, 0, 1] += 0.3
+        G.UpdateReferences(Hn, v_refs)
+    with pytest.raises(RuntimeError, match="wrong size"):
+        G.UpdateReferences(H_refs[:-1], v_refs[:-1])
+    G.close()
