@@ -270,15 +270,15 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # clocks / throttle reasons are sampled from the warm-up to the end of the last timed region
     for S in solvers:
         S.SolveInit(q_d, prob[0], prob[1], prob[2], prob[3], b_d, pb["lb"], pb["ub"])
     for i in range(max(args.warmup, D)):  # every handle allocates its re-pack arenas and captures its graph once
         step_resident(i)
     barrier()
     launches0 = sum(S.launch_count() for S in solvers)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ms_total = timed(step_resident, args.steps)
     launches = sum(S.launch_count() for S in solvers) - launches0
     stats = solvers[0].stats()
