@@ -58,5 +58,8 @@ def random_batch(model: RobotModel, batch: int, seed: int = 0, task_joints=None,
         e = min(hi, (blk + 1) * BLK)
         q[s - lo:e - lo] = model.q_min + uq[s - blk * BLK:e - blk * BLK] * (model.q_max - model.q_min)
         b[s - lo:e - lo] = (2.0 * ub_[s - blk * BLK:e - blk * BLK] - 1.0) * b_scale
+    if model.has_free_flyer:  # q[3:7] of the root joint is a unit quaternion (x, y, z, w)
+        quat = q[:, 3:7]
+        quat /= np.linalg.norm(quat, axis=1, keepdims=True)
     return dict(q=q, H_ref=np.eye(6), v_ref=np.zeros(6), ids=np.asarray(task_joints, np.int32),
                 Ais=np.tile(np.eye(6), (nc, 1, 1)), bis=b, lb=-model.v_max.copy(), ub=model.v_max.copy())

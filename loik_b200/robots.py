@@ -14,8 +14,9 @@ Joint type codes (shared with ``include/loik_b200.h`` and ``oracle/loik_oracle.c
     3,4,5  prismatic along +x,+y,+z  (JointModelPX/PY/PZ)
     6      revolute, unaligned axis  (JointModelRevoluteUnaligned)
     7      prismatic, unaligned axis (JointModelPrismaticUnaligned)
+    8      free-flyer (JointModelFreeFlyer, nq = 7, nv = 6) -- supported as the root joint (joint 1, parent 0) only
 
-All joints are 1-DoF, so ``idx_q = idx_v = joint_id - 1`` and ``nq = nv = nb``.
+1-DoF joints have ``nq = nv = 1``; ``idx_q`` / ``idx_v`` follow pinocchio (cumulative over the joints in id order).
 """
 from __future__ import annotations
 
@@ -24,7 +25,7 @@ import math
 
 import numpy as np
 
-RX, RY, RZ, PX, PY, PZ, RU, PU = range(8)
+RX, RY, RZ, PX, PY, PZ, RU, PU, FF = range(9)
 _AXES = {"x": (1.0, 0.0, 0.0), "y": (0.0, 1.0, 0.0), "z": (0.0, 0.0, 1.0)}
 
 
@@ -61,21 +62,38 @@ class RobotModel:
         return self.nj - 1
 
     @property
+    def has_free_flyer(self) -> bool:
+        return self.nj > 1 and int(self.jtype[1]) == FF
+
+    @property
     def nv(self) -> int:
-        return self.nj - 1
+        return self.nj - 1 + (5 if self.has_free_flyer else 0)
 
     @property
     def nq(self) -> int:
-        return self.nj - 1
+        return self.nj - 1 + (6 if self.has_free_flyer else 0)
+
+    def nv_joint(self, i: int) -> int:
+        return 6 if int(self.jtype[i]) == FF else 1
+
+    def idx_v(self, i: int) -> int:
+        return (i - 1) + (5 if (self.has_free_flyer and i > 1) else 0)
+
+    def idx_q(self, i: int) -> int:
+        return (i - 1) + (6 if (self.has_free_flyer and i > 1) else 0)
 
     def neutral(self) -> np.ndarray:
-        return np.zeros(self.nq)
+        q = np.zeros(self.nq)
+        if self.has_free_flyer:
+            q[6] = 1.0  # unit quaternion (x, y, z, w)
+        return q
 
     def validate(self) -> None:
         assert self.parent[0] == 0
         for i in range(1, self.nj):
             assert 0 <= self.parent[i] < i, "joints must be numbered parent < child"
-            assert 0 <= self.jtype[i] <= PU
+            assert 0 <= self.jtype[i] <= FF
+            assert self.jtype[i] != FF or (i == 1 and self.parent[i] == 0), "free-flyer only as the root joint"
             assert abs(np.linalg.norm(self.axis[i]) - 1.0) < 1e-12
             R = self.placement_R[i]
             assert np.allclose(R @ R.T, np.eye(3), atol=1e-12)
@@ -93,6 +111,16 @@ def _build(name, joints) -> RobotModel:
     qmin, qmax, vmax, names = [], [], [], ["universe"]
     for i, (jn, par, jt, ax, xyz, rpy, lo, hi, vm) in enumerate(joints, start=1):
         parent[i] = par
+        if jt == "FF":
+            jtype[i] = FF
+            axis[i] = (0.0, 0.0, 1.0)
+            R[i] = rpy_to_matrix(*rpy)
+            p[i] = xyz
+            qmin += [-1.0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0]   # position box; the quaternion part is normalised by the samplers
+            qmax += [1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0]
+            vmax += [vm] * 6
+            names.append(jn)
+            continue
         if isinstance(ax, str):
             a = np.array(_AXES[ax])
             code = {"x": 0, "y": 1, "z": 2}[ax] + (0 if jt == "R" else 3)
@@ -155,13 +183,18 @@ def ur10() -> RobotModel:
     return _build("ur10", J)
 
 
-def talos() -> RobotModel:
-    """Talos humanoid, fixed base, 32 revolute joints, five branches.
+def talos(floating: bool = False) -> RobotModel:
+    """Talos humanoid, 32 revolute joints, five branches; fixed base as in the reference fixture
+    (`tests/loik-loid.cpp:110-111`), or ``floating=True``: a free-flyer root joint (nv = 38).
 
-    Topology is the structural part (joint 0 has three children, joint 14 three);
+    Topology is the structural part (the base has three children, torso_2 three);
     link offsets are plausible synthetic values.
     """
     J = []
+    base = 0
+    if floating:
+        J.append(("root_joint", 0, "FF", None, (0, 0, 0), (0, 0, 0), None, None, 2.0))
+        base = 1
 
     def leg(side, sgn, root_parent):
         base = len(J)
@@ -173,10 +206,10 @@ def talos() -> RobotModel:
             par = root_parent if k == 0 else base + k
             J.append((f"leg_{side}_{k+1}_joint", par, "R", ax[k], xyz[k], (0, 0, 0), lim[k][0], lim[k][1], vm[k]))
 
-    leg("left", +1.0, 0)          # joints 1..6
-    leg("right", -1.0, 0)         # joints 7..12
-    J.append(("torso_1_joint", 0, "R", "z", (0, 0, 0.0722), (0, 0, 0), -1.26, 1.26, 5.4))     # 13
-    J.append(("torso_2_joint", 13, "R", "y", (0, 0, 0), (0, 0, 0), -0.23, 0.73, 5.4))         # 14
+    leg("left", +1.0, base)       # joints 1..6   (+1 each with a floating base)
+    leg("right", -1.0, base)      # joints 7..12
+    J.append(("torso_1_joint", base, "R", "z", (0, 0, 0.0722), (0, 0, 0), -1.26, 1.26, 5.4))          # 13
+    J.append(("torso_2_joint", 13 + base, "R", "y", (0, 0, 0), (0, 0, 0), -0.23, 0.73, 5.4))          # 14
 
     def arm(side, sgn):
         base = len(J)
@@ -187,15 +220,16 @@ def talos() -> RobotModel:
         vm = [2.7, 3.66, 4.58, 4.58, 1.95, 1.76, 1.76, 1.0]
         names = [f"arm_{side}_{k+1}_joint" for k in range(7)] + [f"gripper_{side}_joint"]
         for k in range(8):
-            par = 14 if k == 0 else base + k
+            par = torso2 if k == 0 else base + k
             J.append((names[k], par, "R", ax[k], xyz[k], (0, 0, 0), lim[k][0], lim[k][1], vm[k]))
 
+    torso2 = 14 + base
     arm("left", +1.0)             # joints 15..22
     arm("right", -1.0)            # joints 23..30
-    J.append(("head_1_joint", 14, "R", "y", (0, 0, 0.316), (0, 0, 0), -0.21, 0.79, 3.0))      # 31
-    J.append(("head_2_joint", 31, "R", "z", (0.039, 0, 0), (0, 0, 0), -1.31, 1.31, 3.0))      # 32
-    m = _build("talos", J)
-    assert m.nj == 33
+    J.append(("head_1_joint", torso2, "R", "y", (0, 0, 0.316), (0, 0, 0), -0.21, 0.79, 3.0))          # 31
+    J.append(("head_2_joint", 31 + base, "R", "z", (0.039, 0, 0), (0, 0, 0), -1.31, 1.31, 3.0))       # 32
+    m = _build("talos_ff" if floating else "talos", J)
+    assert m.nj == 33 + base
     return m
 
 
@@ -217,10 +251,10 @@ def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0
     return _build(f"random{nb}_s{seed}", J)
 
 
-ROBOTS = {"panda": panda, "panda9": lambda: panda(True), "ur10": ur10, "talos": talos}
+ROBOTS = {"panda": panda, "panda9": lambda: panda(True), "ur10": ur10, "talos": talos, "talos_ff": lambda: talos(True)}
 
 # End-effector task joints used by the BASELINE.json configs.
-TASK_JOINTS = {"panda": [7], "panda9": [7], "ur10": [6], "talos": [21, 29]}
+TASK_JOINTS = {"panda": [7], "panda9": [7], "ur10": [6], "talos": [21, 29], "talos_ff": [22, 30]}
 
 
 def get_robot(name: str) -> RobotModel:

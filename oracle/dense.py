@@ -38,6 +38,8 @@ def dual_action_matrix(R, t):
 
 
 def joint_subspace(jtype, axis):
+    if jtype == 8:  # free-flyer
+        return np.eye(6)
     S = np.zeros((6, 1))
     if jtype <= 2:
         S[3 + jtype, 0] = 1.0
@@ -51,7 +53,14 @@ def joint_subspace(jtype, axis):
 
 
 def joint_transform(jtype, axis, q):
-    """jmodel.calc -> jdata.M(): (R, p)."""
+    """jmodel.calc -> jdata.M(): (R, p).  q: scalar for 1-DoF joints, (x, y, z, qx, qy, qz, qw) for the free-flyer."""
+    if jtype == 8:
+        x, y, z, w = q[3:7]
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        return R, np.asarray(q[:3], float).copy()
+    q = float(np.asarray(q).reshape(-1)[0])
     if jtype <= 2:
         a = np.eye(3)[jtype]
         rev = True
@@ -130,7 +139,8 @@ class FirstOrderLoik:
     def FwdPassInit(self, q):
         mdl = self.model
         for i in range(1, self.nj):
-            MR, Mp = joint_transform(int(mdl.jtype[i]), mdl.axis[i], q[i - 1])
+            iq = mdl.idx_q(i)
+            MR, Mp = joint_transform(int(mdl.jtype[i]), mdl.axis[i], q[iq:iq + (7 if int(mdl.jtype[i]) == 8 else 1)])
             R = mdl.placement_R[i] @ MR
             p = mdl.placement_p[i] + mdl.placement_R[i] @ Mp
             self.liMi[i] = (R, p)
@@ -158,7 +168,8 @@ class FirstOrderLoik:
             r0 = (i - 1) * 6
             self.P_qp[r0:r0 + 6, r0:r0 + 6] = self.H_refs[i]
             self.q_qp[r0:r0 + 6] = -self.H_refs[i].T @ self.v_refs[i]
-            self.A_qp[r0:r0 + 6, 6 * nb + (i - 1):6 * nb + i] = self.S[i]
+            iv, nvj = self.model.idx_v(i), self.model.nv_joint(i)
+            self.A_qp[r0:r0 + 6, 6 * nb + iv:6 * nb + iv + nvj] = self.S[i]
             par = int(self.model.parent[i])
             if par > 0:
                 # iMo * oMp as action matrices (ik-id-description.hpp:458)
@@ -199,8 +210,9 @@ class FirstOrderLoik:
     # ---- loik-loid.hxx:39-76 ------------------------------------------------------------------
     def FwdPass1(self):
         for i in range(1, self.nj):
-            self.Ris[i] = self.mu_ineq * np.eye(1)
-            self.ris[i] = self.w[i - 1:i] - self.mu_ineq * self.z[i - 1:i]
+            iv, nvj = self.model.idx_v(i), self.model.nv_joint(i)
+            self.Ris[i] = self.mu_ineq * np.eye(nvj)
+            self.ris[i] = self.w[iv:iv + nvj] - self.mu_ineq * self.z[iv:iv + nvj]
             self.His[i] = self.rho * np.eye(6) + self.H_refs[i]
             self.pis[i] = -self.rho * self.vis_prev[i] - self.H_refs[i].T @ self.v_refs[i]
         for k, c in enumerate(self.task_ids):
@@ -231,7 +243,8 @@ class FirstOrderLoik:
             vp = np.linalg.inv(action_matrix(R, t)) @ self.vis[par]
             Hi, pi, Si = self.His[i], self.pis[i], self.S[i]
             nu_i = -self.Di_invs[i] @ (Si.T @ (Hi @ vp + pi) + self.ris[i])
-            self.nu[i - 1] = nu_i[0]
+            iv, nvj = self.model.idx_v(i), self.model.nv_joint(i)
+            self.nu[iv:iv + nvj] = nu_i
             self.vis[i] = vp + (Si @ nu_i)
             self.fis[i] = Hi @ self.vis[i] + pi
 
@@ -358,9 +371,10 @@ def kkt_report(model, liMi, task_ids, Ais, bis, H_ref, v_ref, lb, ub, v, nu, z, 
     for i in range(1, nj):
         par = int(model.parent[i])
         R, t = liMi[i]
-        S = joint_subspace(int(model.jtype[i]), model.axis[i])[:, 0]
+        S = joint_subspace(int(model.jtype[i]), model.axis[i])
+        iv, nvj = model.idx_v(i), model.nv_joint(i)
         vp = np.linalg.inv(action_matrix(R, t)) @ (v[par] if par > 0 else np.zeros(6))
-        kin = max(kin, np.abs(-v[i] + vp + S * nu[i - 1]).max())
+        kin = max(kin, np.abs(-v[i] + vp + S @ nu[iv:iv + nvj]).max())
         stat_v[i] += H_ref @ (v[i] - v_ref) - f[i]
         if par > 0:
             stat_v[par] += dual_action_matrix(R, t) @ f[i]
@@ -369,7 +383,8 @@ def kkt_report(model, liMi, task_ids, Ais, bis, H_ref, v_ref, lb, ub, v, nu, z, 
         A = np.asarray(Ais[k]).reshape(6, 6)
         stat_v[c] += A.T @ y[k]
         task = max(task, np.abs(A @ v[c] - bis[k]).max())
-    stat_nu = np.array([joint_subspace(int(model.jtype[i]), model.axis[i])[:, 0] @ f[i] + w[i - 1] for i in range(1, nj)])
+    stat_nu = np.concatenate([joint_subspace(int(model.jtype[i]), model.axis[i]).T @ f[i]
+                              + w[model.idx_v(i):model.idx_v(i) + model.nv_joint(i)] for i in range(1, nj)])
     out["kinematics"] = kin
     out["task"] = task
     out["stationarity_v"] = np.abs(stat_v[1:]).max()

@@ -30,12 +30,13 @@
 
 #define LO_API __attribute__((visibility("default")))
 
-enum { JT_RX = 0, JT_RY, JT_RZ, JT_PX, JT_PY, JT_PZ, JT_RU, JT_PU };
+enum { JT_RX = 0, JT_RY, JT_RZ, JT_PX, JT_PY, JT_PZ, JT_RU, JT_PU, JT_FF };
 
 typedef struct lo_solver {
   /* ---- model (what the hot path reads from pinocchio::Model) ---- */
-  int nj, nb, nv, nc;
+  int nj, nb, nv, nq, nc;
   int *parent, *jtype;
+  int *nvj, *idxv, *idxq; /* jmodel.nv(), jmodel.idx_v(), jmodel.idx_q() */
   double *axis;      /* [nj*3] */
   double *plR, *plp; /* jointPlacements */
   /* ---- IkIdSolverBaseTpl (task-solver-base.hpp:146-170) ---- */
@@ -69,7 +70,7 @@ typedef struct lo_solver {
   double fis_diff_plus_Aty_inf_norm, Stf_plus_w_inf_norm, delta_fis_diff_plus_Aty_inf_norm;
   double delta_Stf_plus_w_inf_norm, delta_vis_inf_norm, delta_nu_inf_norm, delta_z_inf_norm;
   double delta_fis_inf_norm, delta_yis_inf_norm, delta_w_inf_norm;
-  /* pinocchio JointData: S (6), U (6), Dinv (1), UDinv (6) per joint */
+  /* pinocchio JointData per joint: S (6 x nvj), U (6 x nvj), Dinv (nvj x nvj), UDinv (6 x nvj); row-major, row stride 6 */
   double *jS, *jU, *jDinv, *jUDinv;
   /* history (LoikSolverInfo, loik-loid-optimized.hpp:47-127) -- always recorded here */
   int hist_len, hist_cap;
@@ -179,23 +180,31 @@ static void se3_act_on(const double *R, const double *t, const double *I, double
 }
 
 /* P4: jdata.S() for 1-DoF joints: S = [0;axis] (revolute) or [axis;0] (prismatic) */
-static void joint_S(int jt, const double *axis, double *S) {
-  memset(S, 0, 6 * sizeof(double));
+static void joint_S(int jt, const double *axis, double *S) { /* S[6*row + col], col < nvj */
+  memset(S, 0, 36 * sizeof(double));
   switch (jt) {
-    case JT_RX: case JT_RY: case JT_RZ: S[3 + jt] = 1.0; break;
-    case JT_PX: case JT_PY: case JT_PZ: S[jt - 3] = 1.0; break;
-    case JT_RU: S[3] = axis[0]; S[4] = axis[1]; S[5] = axis[2]; break;
-    default: S[0] = axis[0]; S[1] = axis[1]; S[2] = axis[2]; break;
+    case JT_RX: case JT_RY: case JT_RZ: S[6 * (3 + jt)] = 1.0; break;
+    case JT_PX: case JT_PY: case JT_PZ: S[6 * (jt - 3)] = 1.0; break;
+    case JT_RU: S[18] = axis[0]; S[24] = axis[1]; S[30] = axis[2]; break;
+    case JT_PU: S[0] = axis[0]; S[6] = axis[1]; S[12] = axis[2]; break;
+    default: for (int k = 0; k < 6; ++k) S[7 * k] = 1.0; break; /* free-flyer: identity */
   }
 }
 
 /* P5: jmodel.calc(jdata, q) -> jdata.M(): revolute M = (Rot(axis,q), 0), prismatic M = (I, axis q).
  * Axis-aligned revolute joints fill exact 0/1 entries (pinocchio TransformRevoluteTpl); the unaligned
  * one uses pinocchio's toRotationMatrix(axis, cos, sin): R = c I + s [a]x + (1-c) a a^T. */
-static void joint_M(int jt, const double *axis, double q, double *MR, double *Mp) {
+static void joint_M(int jt, const double *axis, const double *qv, double *MR, double *Mp) {
+  const double q = qv[0];
   for (int i = 0; i < 9; ++i) MR[i] = (i % 4 == 0) ? 1.0 : 0.0;
   Mp[0] = Mp[1] = Mp[2] = 0.0;
-  if (jt <= JT_RZ) {
+  if (jt == JT_FF) { /* q = (x, y, z, qx, qy, qz, qw): M = (R(quat), p) */
+    const double x = qv[3], y = qv[4], z = qv[5], w = qv[6];
+    MR[0] = 1 - 2 * (y * y + z * z); MR[1] = 2 * (x * y - z * w);     MR[2] = 2 * (x * z + y * w);
+    MR[3] = 2 * (x * y + z * w);     MR[4] = 1 - 2 * (x * x + z * z); MR[5] = 2 * (y * z - x * w);
+    MR[6] = 2 * (x * z - y * w);     MR[7] = 2 * (y * z + x * w);     MR[8] = 1 - 2 * (x * x + y * y);
+    Mp[0] = qv[0]; Mp[1] = qv[1]; Mp[2] = qv[2];
+  } else if (jt <= JT_RZ) {
     double s = sin(q), c = cos(q);
     int a = (jt + 1) % 3, b = (jt + 2) % 3; /* rotation in the (a,b) plane */
     MR[3 * a + a] = c; MR[3 * a + b] = -s;
@@ -213,19 +222,65 @@ static void joint_M(int jt, const double *axis, double q, double *MR, double *Mp
   }
 }
 
-/* P1: JointModel*::calc_aba(jdata, armature, I, update_I) (call site hxx:60-63).
- * U = I S; Dinv = 1/(S^T U + armature); UDinv = U Dinv; if update_I: I -= UDinv U^T. */
-static void joint_calc_aba(lo_solver *s, int i, double armature, double *I, int update_I) {
-  const double *S = s->jS + 6 * i;
-  double *U = s->jU + 6 * i, *UDinv = s->jUDinv + 6 * i;
-  mat6_vec(I, S, U);
-  double StU = 0.0;
-  for (int k = 0; k < 6; ++k) StU += S[k] * U[k];
-  s->jDinv[i] = 1.0 / (StU + armature);
-  for (int k = 0; k < 6; ++k) UDinv[k] = U[k] * s->jDinv[i];
+/* inverse of a small SPD matrix (n <= 6, row stride 6) by Cholesky: pinocchio's PerformStYSInversion does
+ * Dinv.setIdentity(); StU.llt().solveInPlace(Dinv) */
+static void spd_inverse(const double *A, int n, double *Ainv) {
+  double L[36] = {0}, Li[36] = {0};
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double sum = A[6 * i + j];
+      for (int k = 0; k < j; ++k) sum -= L[6 * i + k] * L[6 * j + k];
+      L[6 * i + j] = (i == j) ? sqrt(sum) : sum / L[6 * j + j];
+    }
+  for (int c = 0; c < n; ++c) /* Li = L^-1 by forward substitution */
+    for (int i = 0; i < n; ++i) {
+      double sum = (i == c) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) sum -= L[6 * i + k] * Li[6 * k + c];
+      Li[6 * i + c] = sum / L[6 * i + i];
+    }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double sum = 0.0;
+      for (int k = 0; k < n; ++k) sum += Li[6 * k + i] * Li[6 * k + j];
+      Ainv[6 * i + j] = sum;
+    }
+}
+
+/* P1: JointModel*::calc_aba(jdata, armature, I, update_I) (call site hxx:60-63), generic form:
+ * U = I S; StU = S^T U + diag(armature); Dinv = StU^-1; UDinv = U Dinv; if update_I: I -= UDinv U^T.
+ * For a 1-DoF aligned joint this is pinocchio's U = I.col(k), Dinv = 1/(I(k,k) + armature). */
+static void joint_calc_aba(lo_solver *s, int i, const double *armature, double *I, int update_I) {
+  const int n = s->nvj[i];
+  const double *S = s->jS + 36 * i;
+  double *U = s->jU + 36 * i, *UDinv = s->jUDinv + 36 * i, *Dinv = s->jDinv + 36 * i;
+  double StU[36] = {0};
+  for (int a = 0; a < 6; ++a)
+    for (int c = 0; c < n; ++c) {
+      double sum = 0.0;
+      for (int k = 0; k < 6; ++k) sum += I[6 * a + k] * S[6 * k + c];
+      U[6 * a + c] = sum;
+    }
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < n; ++c) {
+      double sum = 0.0;
+      for (int k = 0; k < 6; ++k) sum += S[6 * k + r] * U[6 * k + c];
+      StU[6 * r + c] = sum + (r == c ? armature[r] : 0.0);
+    }
+  if (n == 1) Dinv[0] = 1.0 / StU[0];
+  else spd_inverse(StU, n, Dinv);
+  for (int a = 0; a < 6; ++a)
+    for (int c = 0; c < n; ++c) {
+      double sum = 0.0;
+      for (int k = 0; k < n; ++k) sum += U[6 * a + k] * Dinv[6 * k + c];
+      UDinv[6 * a + c] = sum;
+    }
   if (update_I)
     for (int a = 0; a < 6; ++a)
-      for (int b = 0; b < 6; ++b) I[6 * a + b] -= UDinv[a] * U[b];
+      for (int b = 0; b < 6; ++b) {
+        double sum = 0.0;
+        for (int k = 0; k < n; ++k) sum += UDinv[6 * a + k] * U[6 * b + k];
+        I[6 * a + b] -= sum;
+      }
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -243,9 +298,16 @@ LO_API lo_solver *lo_create(int nj, const int *parent, const int *jtype, const d
                             int mu_update_strat, int num_eq_c, int eq_c_dim, int warm_start, double tol_tail_solve) {
   if (eq_c_dim != 6 || nj < 2 || num_eq_c < 0) return NULL;
   lo_solver *s = (lo_solver *)calloc(1, sizeof(lo_solver));
-  s->nj = nj; s->nb = nj - 1; s->nv = nj - 1; s->nc = num_eq_c;
+  s->nj = nj; s->nb = nj - 1; s->nc = num_eq_c;
   s->parent = (int *)calloc(nj, sizeof(int)); s->jtype = (int *)calloc(nj, sizeof(int));
   memcpy(s->parent, parent, nj * sizeof(int)); memcpy(s->jtype, jtype, nj * sizeof(int));
+  s->nvj = (int *)calloc(nj, sizeof(int)); s->idxv = (int *)calloc(nj, sizeof(int)); s->idxq = (int *)calloc(nj, sizeof(int));
+  s->nv = 0; s->nq = 0;
+  for (int i = 1; i < nj; ++i) {
+    s->idxv[i] = s->nv; s->idxq[i] = s->nq;
+    s->nvj[i] = (jtype[i] == JT_FF) ? 6 : 1;
+    s->nv += s->nvj[i]; s->nq += (jtype[i] == JT_FF) ? 7 : 1;
+  }
   s->axis = dalloc(3 * nj); memcpy(s->axis, axis, 3 * nj * sizeof(double));
   s->plR = dalloc(9 * nj); memcpy(s->plR, plR, 9 * nj * sizeof(double));
   s->plp = dalloc(3 * nj); memcpy(s->plp, plp, 3 * nj * sizeof(double));
@@ -272,8 +334,8 @@ LO_API lo_solver *lo_create(int nj, const int *parent, const int *jtype, const d
   s->Aty = dalloc(6 * nc); s->fis_diff_plus_Aty = dalloc(6 * nj); s->delta_fis_diff_plus_Aty = dalloc(6 * nj);
   s->Href_v = dalloc(6 * nj); s->Av_minus_b = dalloc(6 * nc);
   s->Stf_plus_w = dalloc(s->nv); s->delta_Stf_plus_w = dalloc(s->nv);
-  s->jS = dalloc(6 * nj); s->jU = dalloc(6 * nj); s->jDinv = dalloc(nj); s->jUDinv = dalloc(6 * nj);
-  for (int i = 1; i < nj; ++i) joint_S(s->jtype[i], s->axis + 3 * i, s->jS + 6 * i);
+  s->jS = dalloc(36 * nj); s->jU = dalloc(36 * nj); s->jDinv = dalloc(36 * nj); s->jUDinv = dalloc(36 * nj);
+  for (int i = 1; i < nj; ++i) joint_S(s->jtype[i], s->axis + 3 * i, s->jS + 36 * i);
   s->hist_cap = max_iter + 2; s->hist_mu = dalloc(s->hist_cap); s->hist_pres = dalloc(s->hist_cap);
   s->hist_dres = dalloc(s->hist_cap);
   problem_reset(s);
@@ -283,7 +345,7 @@ LO_API lo_solver *lo_create(int nj, const int *parent, const int *jtype, const d
 
 LO_API void lo_destroy(lo_solver *s) {
   if (!s) return;
-  void *ptrs[] = {s->parent, s->jtype, s->axis, s->plR, s->plp, s->primal_residual_vec, s->dual_residual_vec, s->H_refs,
+  void *ptrs[] = {s->nvj, s->idxv, s->idxq, s->parent, s->jtype, s->axis, s->plR, s->plp, s->primal_residual_vec, s->dual_residual_vec, s->H_refs,
                   s->v_refs, s->Hv, s->task_ids, s->Ais, s->bis, s->AtA, s->Atb, s->lb, s->ub, s->oMi_R, s->oMi_p,
                   s->liMi_R, s->liMi_p, s->nu, s->nu_prev, s->vis, s->vis_prev, s->His, s->His_aba, s->pis, s->pis_aba,
                   s->R, s->r, s->fis, s->delta_fis, s->yis, s->delta_yis, s->w, s->delta_w, s->z, s->z_prev, s->Aty,
@@ -433,7 +495,7 @@ LO_API void lo_fwd_pass_init(lo_solver *s, const double *q) {
   for (int i = 1; i < s->nj; ++i) {
     double MR[9], Mp[3], t[3];
     int par = s->parent[i];
-    joint_M(s->jtype[i], s->axis + 3 * i, q[i - 1], MR, Mp);
+    joint_M(s->jtype[i], s->axis + 3 * i, q + s->idxq[i], MR, Mp);
     /* liMi = jointPlacements[i] * M : (R1 R2, p1 + R1 p2) */
     m3mul(s->plR + 9 * i, MR, s->liMi_R + 9 * i);
     for (int a = 0; a < 3; ++a)
@@ -484,16 +546,20 @@ LO_API void lo_bwd_pass(lo_solver *s) {
   for (int i = s->nj - 1; i > 0; --i) {
     int par = s->parent[i];
     double *Hi_aba = s->His_aba + 36 * i, *pi_aba = s->pis_aba + 6 * i;
-    const double *pi = s->pis + 6 * i, *S = s->jS + 6 * i;
+    const double *pi = s->pis + 6 * i, *S = s->jS + 36 * i;
+    const int n = s->nvj[i], iv = s->idxv[i];
     double tmp36[36], tmp6[6];
-    joint_calc_aba(s, i, s->R[i - 1], Hi_aba, par > 0);                                   /* :60-63 */
+    joint_calc_aba(s, i, s->R + iv, Hi_aba, par > 0);                                     /* :60-63 */
     se3_act_on(s->liMi_R + 9 * i, s->liMi_p + 3 * i, Hi_aba, tmp36);                      /* :66 */
     for (int a = 0; a < 36; ++a) s->His_aba[36 * par + a] += tmp36[a];
     memcpy(s->His + 36 * par, s->His_aba + 36 * par, 36 * sizeof(double));                /* :67 */
-    double Stp = 0.0;
-    for (int a = 0; a < 6; ++a) Stp += S[a] * pi[a];
-    s->r[i - 1] += Stp;                                                                   /* :70 */
-    for (int a = 0; a < 6; ++a) pi_aba[a] -= s->jUDinv[6 * i + a] * s->r[i - 1];          /* :71-73 */
+    for (int c = 0; c < n; ++c) {
+      double Stp = 0.0;
+      for (int a = 0; a < 6; ++a) Stp += S[6 * a + c] * pi[a];
+      s->r[iv + c] += Stp;                                                                /* :70 */
+    }
+    for (int a = 0; a < 6; ++a)
+      for (int c = 0; c < n; ++c) pi_aba[a] -= s->jUDinv[36 * i + 6 * a + c] * s->r[iv + c]; /* :71-73 */
     se3_act_force(s->liMi_R + 9 * i, s->liMi_p + 3 * i, pi_aba, tmp6);                    /* :74 */
     for (int a = 0; a < 6; ++a) s->pis[6 * par + a] += tmp6[a];
     memcpy(s->pis_aba + 6 * par, s->pis + 6 * par, 6 * sizeof(double));                   /* :75 */
@@ -505,16 +571,21 @@ LO_API void lo_fwd_pass2(lo_solver *s) {
   memcpy(s->delta_fis_diff_plus_Aty, s->fis_diff_plus_Aty, 6 * s->nj * sizeof(double));   /* :364 */
   for (int i = 1; i < s->nj; ++i) {
     int par = s->parent[i];
-    const double *Hi = s->His + 36 * i, *pi = s->pis + 6 * i, *S = s->jS + 6 * i;
+    const double *Hi = s->His + 36 * i, *pi = s->pis + 6 * i, *S = s->jS + 36 * i;
+    const int nj_ = s->nvj[i], iv = s->idxv[i];
     double vp[6], Hv6[6], d[6], n;
     se3_actinv_motion(s->liMi_R + 9 * i, s->liMi_p + 3 * i, s->vis + 6 * par, vp);        /* :125 */
-    double acc = 0.0;
-    for (int a = 0; a < 6; ++a) acc += s->jUDinv[6 * i + a] * vp[a];
-    s->nu[i - 1] = -acc - s->jDinv[i] * s->r[i - 1];                                      /* :127 */
-    n = fabs(s->nu[i - 1]);
+    for (int c = 0; c < nj_; ++c) {
+      double acc = 0.0, dr = 0.0;
+      for (int a = 0; a < 6; ++a) acc += s->jUDinv[36 * i + 6 * a + c] * vp[a];
+      for (int k = 0; k < nj_; ++k) dr += s->jDinv[36 * i + 6 * c + k] * s->r[iv + k];
+      s->nu[iv + c] = -acc - dr;                                                          /* :127 */
+    }
+    n = infn(s->nu + iv, nj_);
     if (n > s->nu_inf_norm) s->nu_inf_norm = n;                                           /* :129-131 */
     for (int a = 0; a < 6; ++a) s->vis[6 * i + a] = vp[a];
-    for (int a = 0; a < 6; ++a) s->vis[6 * i + a] += S[a] * s->nu[i - 1];                 /* :133-134 */
+    for (int a = 0; a < 6; ++a)
+      for (int c = 0; c < nj_; ++c) s->vis[6 * i + a] += S[6 * a + c] * s->nu[iv + c];    /* :133-134 */
     memcpy(s->delta_fis + 6 * i, s->fis + 6 * i, 6 * sizeof(double));                     /* :137 */
     mat6_vec(Hi, s->vis + 6 * i, Hv6);
     for (int a = 0; a < 6; ++a) s->fis[6 * i + a] = Hv6[a] + pi[a];                       /* :139-140 */
@@ -588,7 +659,8 @@ static void lo_bwd_pass2(lo_solver *s) {
   memcpy(s->delta_Stf_plus_w, s->Stf_plus_w, s->nv * sizeof(double));                     /* :471 */
   for (int i = s->nj - 1; i > 0; --i) {
     int par = s->parent[i];
-    const double *fi = s->fis + 6 * i, *S = s->jS + 6 * i;
+    const double *fi = s->fis + 6 * i, *S = s->jS + 36 * i;
+    const int nj_ = s->nvj[i], iv = s->idxv[i];
     double t6[6], n;
     for (int a = 0; a < 6; ++a) s->fis_diff_plus_Aty[6 * i + a] += -fi[a];                /* :210 */
     se3_act_force(s->liMi_R + 9 * i, s->liMi_p + 3 * i, fi, t6);
@@ -601,10 +673,12 @@ static void lo_bwd_pass2(lo_solver *s) {
     if (n > s->fis_diff_plus_Aty_inf_norm) s->fis_diff_plus_Aty_inf_norm = n;             /* :223-225 */
     for (int a = 0; a < 6; ++a)
       s->dual_residual_vec[6 * (i - 1) + a] = s->Href_v[6 * i + a] - s->Hv[6 * i + a] + s->fis_diff_plus_Aty[6 * i + a];
-    double Stf = 0.0;
-    for (int a = 0; a < 6; ++a) Stf += S[a] * fi[a];
-    s->Stf_plus_w[i - 1] = Stf + s->w[i - 1];                                             /* :231 */
-    n = fabs(s->Stf_plus_w[i - 1]);
+    for (int c = 0; c < nj_; ++c) {
+      double Stf = 0.0;
+      for (int a = 0; a < 6; ++a) Stf += S[6 * a + c] * fi[a];
+      s->Stf_plus_w[iv + c] = Stf + s->w[iv + c];                                         /* :231 */
+    }
+    n = infn(s->Stf_plus_w + iv, nj_);
     if (n > s->Stf_plus_w_inf_norm) s->Stf_plus_w_inf_norm = n;
   }
   double m = 0.0;
@@ -779,8 +853,8 @@ LO_API double *lo_array(lo_solver *s, const char *field, int *n) {
   FIELD("z_prev", s->z_prev, nv) FIELD("Aty", s->Aty, 6 * nc) FIELD("fis_diff_plus_Aty", s->fis_diff_plus_Aty, 6 * nj)
   FIELD("delta_fis_diff_plus_Aty", s->delta_fis_diff_plus_Aty, 6 * nj) FIELD("Href_v", s->Href_v, 6 * nj)
   FIELD("Av_minus_b", s->Av_minus_b, 6 * nc) FIELD("Stf_plus_w", s->Stf_plus_w, nv)
-  FIELD("delta_Stf_plus_w", s->delta_Stf_plus_w, nv) FIELD("U", s->jU, 6 * nj) FIELD("Dinv", s->jDinv, nj)
-  FIELD("UDinv", s->jUDinv, 6 * nj) FIELD("S", s->jS, 6 * nj)
+  FIELD("delta_Stf_plus_w", s->delta_Stf_plus_w, nv) FIELD("U_full", s->jU, 36 * nj) FIELD("Dinv_full", s->jDinv, 36 * nj)
+  FIELD("UDinv_full", s->jUDinv, 36 * nj) FIELD("S_full", s->jS, 36 * nj)
   FIELD("primal_residual_vec", s->primal_residual_vec, 6 * s->nb + nv)
   FIELD("dual_residual_vec", s->dual_residual_vec, 6 * s->nb + nv)
   FIELD("Hv", s->Hv, 6 * nj) FIELD("H_refs", s->H_refs, 36 * nj) FIELD("AtA", s->AtA, 36 * nc) FIELD("Atb", s->Atb, 6 * nc)
@@ -835,15 +909,16 @@ typedef struct {
 
 static void *batch_worker(void *arg) {
   lo_batch_job *j = (lo_batch_job *)arg;
-  int nv = j->nj - 1, nc = j->nc;
+  int nc = j->nc;
   lo_solver *s = lo_create(j->nj, j->parent, j->jtype, j->axis, j->plR, j->plp, j->max_iter, j->tol_abs, j->tol_rel,
                            j->tol_primal_inf, j->tol_dual_inf, j->rho, j->mu, j->mu_eq_scale, j->strat, nc, 6, 0, j->tol_tail);
+  const int nv = s->nv, nq = s->nq;
   long tot = 0;
   for (int b = j->lo; b < j->hi; ++b) {
     const double *bis = j->b_per_instance ? j->bis + (size_t)b * 6 * nc : j->bis;
     const double *lb = j->bounds_per_instance ? j->lb + (size_t)b * nv : j->lb;
     const double *ub = j->bounds_per_instance ? j->ub + (size_t)b * nv : j->ub;
-    lo_solve_init(s, j->q + (size_t)b * nv, j->H_ref, j->v_ref, nc, j->ids, j->Ais, bis, lb, ub);
+    lo_solve_init(s, j->q + (size_t)b * nq, j->H_ref, j->v_ref, nc, j->ids, j->Ais, bis, lb, ub);
     if (j->mode == 0) {
       lo_solve(s);
     } else {

@@ -99,8 +99,10 @@ FIXTURE_PARAMS = dict(max_iter=2, tol_abs=1e-3, tol_rel=1e-3, tol_primal_inf=1e-
                       tol_tail_solve=1e-1)
 
 _SHAPES6 = {"vis", "vis_prev", "pis", "pis_aba", "fis", "delta_fis", "fis_diff_plus_Aty", "delta_fis_diff_plus_Aty",
-            "Href_v", "U", "UDinv", "S", "Hv", "yis", "delta_yis", "Aty", "Av_minus_b", "Atb"}
-_SHAPES36 = {"His", "His_aba", "H_refs", "AtA"}
+            "Href_v", "Hv", "yis", "delta_yis", "Aty", "Av_minus_b", "Atb"}
+_SHAPES36 = {"His", "His_aba", "H_refs", "AtA", "U_full", "UDinv_full", "S_full", "Dinv_full"}
+# pinocchio JointData of 1-DoF joints: U / UDinv / S are the first column, Dinv the (0,0) entry of the per-joint blocks
+_FIRST_COL = {"U": "U_full", "UDinv": "UDinv_full", "S": "S_full"}
 
 
 class FirstOrderLoikOptimized:
@@ -223,6 +225,10 @@ class FirstOrderLoikOptimized:
 
     # ---- state access (the reference exposes these as public IkIdData members / getters) ----
     def array(self, name) -> np.ndarray:
+        if name in _FIRST_COL:
+            return self.array(_FIRST_COL[name])[:, :, 0].copy()
+        if name == "Dinv":
+            return self.array("Dinv_full")[:, 0, 0].copy()
         n = C.c_int(0)
         ptr = self._lib.lo_array(self._h, name.encode(), C.byref(n))
         if not ptr:

@@ -442,3 +442,41 @@ def test_update_references_per_joint():
     with pytest.raises(RuntimeError, match="wrong size"):
         G.UpdateReferences(H_refs[:-1], v_refs[:-1])
     G.close()
+
+
+@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "panda9"])
+def test_against_committed_golden_fixtures(name):
+    """CUDA path vs tests/golden/random_*.npz (frozen oracle-pair outputs, scripts/make_golden.py) -- no oracle call."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"random_{name}.npz"))
+    model = robots.get_robot(name)
+    n = int(g["n"])
+    pb = problems.random_batch(model, n, seed=int(g["seed"]))
+    params = problems.bench_params(len(pb["ids"]))
+    G = _gpu(model, params, n)
+    _solve_init(G, pb)
+    G.Solve()
+    np.testing.assert_array_equal(G.get_iter(), g["iter"])
+    np.testing.assert_array_equal(G.get_mu(), g["mu"])
+    np.testing.assert_array_equal(G.get_convergence_status(), g["converged"])
+    np.testing.assert_array_equal(G.get_primal_infeasibility_status(), g["primal_infeasible"])
+    z, nu, w, y = G.z, G.nu, G.w, G.yis
+    for i in range(n):
+        assert rel_inf(z[i], g["z"][i]) < 1e-6 and rel_inf(nu[i], g["nu"][i]) < 1e-6
+        assert rel_inf(w[i], g["w"][i]) < 1e-6 and rel_inf(y[i], g["yis"][i]) < 1e-6
+    G.close()
+
+
+@pytest.mark.parametrize("name", ["talos", "panda", "ur10"])
+def test_fixture_golden_on_gpu(name):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"fixture_{name}.npz"))
+    model = robots.get_robot(name)
+    pr = problems.fixture_problem(model, float(g["bound"]))
+    G = _gpu(model, dict(problems.FIXTURE_PARAMS, max_iter=int(g["max_iter"])), 1)
+    G.Solve(pr["q"][None], pr["H_ref"], pr["v_ref"], pr["ids"], pr["Ais"], pr["bis"][None], pr["lb"], pr["ub"])
+    assert int(G.get_iter()[0]) == int(g["iter"]) and float(G.get_mu()[0]) == float(g["mu"])
+    assert bool(G.get_convergence_status()[0]) == bool(g["converged"])
+    assert bool(G.get_primal_infeasibility_status()[0]) == bool(g["primal_infeasible"])
+    assert rel_inf(G.z[0], g["z"]) < 1e-6 and rel_inf(G.w[0], g["w"]) < 1e-6 and rel_inf(G.vis[0], g["vis"][1:]) < 1e-6
+    G.close()

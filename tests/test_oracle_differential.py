@@ -47,14 +47,17 @@ def step_once_and_compare(A, B, model, it, what):
     check_abs_or_rel(B.His_aba[1:], B.His[1:], TOL, what + " FwdPass1 His_aba")
     check_abs_or_rel(B.pis[1:], A.pis[1:], TOL, what + " FwdPass1 pis")
     for i in range(1, model.nj):
-        check_abs_or_rel(B.R[i - 1], A.Ris[i][0, 0], TOL, what + " R")
-        check_abs_or_rel(B.r[i - 1], A.ris[i][0], TOL, what + " r")
+        iv, n = model.idx_v(i), model.nv_joint(i)
+        check_abs_or_rel(B.R[iv:iv + n], np.diag(A.Ris[i]), TOL, what + " R")
+        check_abs_or_rel(B.r[iv:iv + n], A.ris[i], TOL, what + " r")
     A.BwdPass()
     B.BwdPassOptimizedVisitor()
     check_abs_or_rel(B.His[1:], A.His[1:], TOL, what + " BwdPass His")
     check_abs_or_rel(B.pis[1:], A.pis[1:], TOL, what + " BwdPass pis")
+    Dfull = B.Dinv_full
     for i in range(1, model.nj):  # D^-1 and the projector agree with calc_aba's Dinv / UDinv
-        check_abs_or_rel(B.Dinv[i], A.Di_invs[i][0, 0], TOL, what + " Dinv")
+        n = model.nv_joint(i)
+        check_abs_or_rel(Dfull[i][:n, :n], A.Di_invs[i], TOL, what + " Dinv")
     A.FwdPass2()
     B.FwdPass2OptimizedVisitor()
     check_abs_or_rel(B.nu, A.nu, TOL, what + " FwdPass2 nu")
@@ -99,7 +102,7 @@ def step_once_and_compare(A, B, model, it, what):
     assert A.mu == B.get_mu(), what + " mu"
 
 
-ROBOT_CASES = [("talos", 1.0), ("panda", 1.0), ("panda9", 2.0), ("ur10", 1.0)]
+ROBOT_CASES = [("talos", 1.0), ("panda", 1.0), ("panda9", 2.0), ("ur10", 1.0), ("talos_ff", 1.0)]
 
 
 @pytest.mark.parametrize("name,bound", ROBOT_CASES)
@@ -133,7 +136,7 @@ def test_component_wise_random_trees(seed):
         step_once_and_compare(A, B, model, it, f"tree{seed} it{it}")
 
 
-@pytest.mark.parametrize("name,bound", [("talos", 2.0), ("panda", 2.0), ("ur10", 2.0)])
+@pytest.mark.parametrize("name,bound", [("talos", 2.0), ("panda", 2.0), ("ur10", 2.0), ("talos_ff", 2.0)])
 def test_optimized_correctness_end_to_end(name, bound):
     """tests/loik-loid.cpp:559-671 -- max_iter = 8, bounds +-2: SolveInit + Solve() == dense Solve(args)."""
     model = robots.get_robot(name)
@@ -151,12 +154,12 @@ def test_optimized_correctness_end_to_end(name, bound):
     check_abs_or_rel(B.get_primal_residual(), A.primal_residual, TOL, "primal_residual")
 
 
-@pytest.mark.parametrize("name", ["panda", "ur10", "talos"])
+@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "talos_ff"])
 def test_end_to_end_random_instances(name):
     """Full solves (max_iter = 200) on seeded random instances of the BASELINE configs: same iterates, same
     iteration count, same mu history, same flags."""
     model = robots.get_robot(name)
-    n = 6 if name == "talos" else 12
+    n = 6 if name.startswith("talos") else 12
     pb = problems.random_batch(model, n, seed=7)
     params = problems.bench_params(len(pb["ids"]), max_iter=60)
     for i in range(n):
