@@ -24,7 +24,8 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work of a call
  *     is enqueued on it; calls that return data to HOST memory synchronize that stream before returning.
  *   - Not thread-safe per handle (same as the reference: one solver+data pair per thread).
- *   - 1-DoF joints only (revolute / prismatic, aligned or unaligned): idx_q = idx_v = joint_id - 1.
+ *   - Joints: 1-DoF revolute / prismatic (aligned or unaligned) anywhere, a free-flyer as the root joint; idx_q / idx_v
+ *     are cumulative in joint-id order as in pinocchio (nq = nv = njoints-1 without a free-flyer, +6 / +5 with one).
  */
 #ifndef LOIK_B200_H_
 #define LOIK_B200_H_
@@ -46,7 +47,8 @@ extern "C" {
 
 /* joint type codes: pinocchio JointModelRX/RY/RZ, PX/PY/PZ, RevoluteUnaligned, PrismaticUnaligned */
 enum { LOIK_JOINT_RX = 0, LOIK_JOINT_RY, LOIK_JOINT_RZ, LOIK_JOINT_PX, LOIK_JOINT_PY, LOIK_JOINT_PZ,
-       LOIK_JOINT_RU, LOIK_JOINT_PU };
+       LOIK_JOINT_RU, LOIK_JOINT_PU,
+       LOIK_JOINT_FF /* JointModelFreeFlyer (nq 7 = x y z qx qy qz qw, nv 6): as the root joint (joint 1, parent 0) only */ };
 
 /* where a caller buffer lives: pageable host memory (staged + synchronous), device memory (asynchronous),
  * or page-locked host memory (asynchronous DMA; the caller synchronizes the stream before reusing / reading it) */

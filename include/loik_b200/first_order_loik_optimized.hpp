@@ -64,11 +64,14 @@ inline Model from_pinocchio(const pinocchio::Model& m) {
       code = LOIK_JOINT_PU;
       const auto& a = boost::get<pinocchio::JointModelPrismaticUnaligned>(m.joints[i].toVariant()).axis;
       ax[0] = a[0]; ax[1] = a[1]; ax[2] = a[2];
+    } else if (s == "JointModelFreeFlyer" && i == 1 && m.parents[i] == 0) {
+      code = LOIK_JOINT_FF; ax[2] = 1;
     } else {
       throw std::runtime_error("loik_b200::from_pinocchio: unsupported joint type " + s);
     }
-    if (m.joints[i].idx_v() != i - 1 || m.joints[i].idx_q() != i - 1)
-      throw std::runtime_error("loik_b200::from_pinocchio: only models with idx_q == idx_v == joint_id - 1 are supported");
+    const bool ff = m.joints[1].shortname() == "JointModelFreeFlyer";
+    if (m.joints[i].idx_v() != (i - 1) + ((ff && i > 1) ? 5 : 0) || m.joints[i].idx_q() != (i - 1) + ((ff && i > 1) ? 6 : 0))
+      throw std::runtime_error("loik_b200::from_pinocchio: unexpected idx_q / idx_v layout");
     out.joint_types[i] = code;
     for (int c = 0; c < 3; ++c) out.joint_axes[3 * i + c] = ax[c];
   }

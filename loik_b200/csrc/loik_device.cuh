@@ -35,6 +35,7 @@ struct JointC {
   double Hv[6];                     // problem_.Hv[i] = H_ref v_ref
   double lb, ub;                    // problem_.lb_/ub_ for this joint's dof (when shared by the batch)
   int parent, jtype, task;          // task: slot of the task on this joint or -1
+  int idxv, idxq;                   // jmodel.idx_v(), jmodel.idx_q()
   int carry;                        // contribution to the parent travels in registers (parent == i-1, only child)
   int pout;                         // else (parent > 0): the pending block this joint writes its contribution to
   int npin;                         // number of children that hand their contribution over through a pending block
@@ -60,9 +61,17 @@ enum : int { TR_Y = 0, TR_ATY = 6, TR_B = 12, TR_ATB = 18, TR_ROWS = 24 };      
 enum : int { PR_H = 0, PR_F = 27, PR_ROWS = 33 };                                 // rows of a pending-accumulator block
 enum : int { GR_MU = 0, GR_BINF = 1, GR_CTL = 2, GR_RES = 3, GR_CARRY = 7, GR_NORMS = 21, GR_ROWS = 49 };  // globals (norms: 28 rows)
 
+// Free-flyer root joint (JointModelFreeFlyer, nv = 6): its 6-vector quantities (v, f, F, H, p) use the rows of joint
+// block 1 like every joint; what is per-dof (6 instead of 1) lives in this extra block.
+enum : int { FR_NU = 0, FR_Z = 6, FR_W = 12, FR_T = 18,   // state (24 rows)
+             FR_LB = 24, FR_UB = 30, FR_Q = 36,          // problem data (19 rows): bounds, q = (x y z qx qy qz qw)
+             FR_DINV = 43, FR_R = 64,                    // workspace: Dinv (21, symmetric 6x6 packed), r (6)
+             FR_ROWS = 70 };
+
 struct Offs {
   int glob, joint0, task0, pend0;  // first row of the globals, of joint 1, of task 0, of pending slot 0
-  int prv, drv;                    // debug: primal / dual residual vectors (7 nb rows each)
+  int ff0;                         // first row of the free-flyer block (when the model has one)
+  int prv, drv;                    // debug: primal / dual residual vectors (6 nb + nv rows each)
   int rows;                        // rows per tile record
 };
 
@@ -75,6 +84,8 @@ struct ModelC {
   int nj, nb, nc, npend;
   int max_iter, bounds_per_instance;
   int nseg, nblevel, nflevel, nwarp;
+  int has_ff, nv, nq, pad0;        // joint 1 is a free-flyer; model.nv, model.nq
+  double fflb[6], ffub[6];         // its bounds when shared by the batch
   SegC seg[kMaxSeg];
   Offs off;
   double rho, mu0, mu_scale, tol_abs, tol_rel, tol_pinf, tol_dinf, tol_tail, Hv_inf;
@@ -115,6 +126,8 @@ LOIK_DEV double* joint_blk(double* T, const Offs& O, int ji) { return T + (size_
 LOIK_DEV double* task_blk(double* T, const Offs& O, int k) { return T + (size_t)(O.task0 + TR_ROWS * k) * 32; }
 LOIK_DEV double* pend_blk(double* T, const Offs& O, int k) { return T + (size_t)(O.pend0 + PR_ROWS * k) * 32; }
 LOIK_DEV double* glob_blk(double* T, const Offs& O) { return T + (size_t)O.glob * 32; }
+LOIK_DEV double* ff_blk(double* T, const Offs& O) { return T + (size_t)O.ff0 * 32; }
+__host__ __device__ __forceinline__ constexpr int s6(int i, int j) { return i <= j ? i * 6 - (i * (i - 1)) / 2 + (j - i) : j * 6 - (j * (j - 1)) / 2 + (i - j); }
 LOIK_DEV double amax(double m, double x) { return fmax(m, fabs(x)); }
 
 // liMi = jointPlacements[i] * M_i(q)   (FwdPassInit, hxx:263-264).  (a, b) = (sin q, cos q) for
@@ -528,7 +541,7 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const
     st(Pj, JR_NU, nu);
     st(Pj, JR_Z, z);
     st(Pj, JR_W, w_old + dw);
-    if (DEBUG) st(T, O.prv + 6 * nb + ji, rp);
+    if (DEBUG) st(T, O.prv + 6 * nb + J.idxv, rp);
     if (J.task >= 0) {  // DualUpdate for the task on this joint (:410-451)
       const TaskC& K = c_model.t[J.task];
       double* Pk = task_blk(T, O, J.task);
@@ -638,7 +651,7 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resi
       if (DEBUG) st(T, O.drv + 6 * ji + c, rd[c]);
     }
     st(Pj, JR_T, Tn);
-    if (DEBUG) st(T, O.drv + 6 * nb + ji, Tn);
+    if (DEBUG) st(T, O.drv + 6 * nb + J.idxv, Tn);
     have_carry = false;
     if (J.parent > 0) {  // fis_diff_plus_Aty[parent] += liMi.act(f_i) (:212)
       double R[9], t[3];
@@ -652,6 +665,204 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resi
         for (int c = 0; c < 6; ++c) st(Pp, PR_F + c, cF[c]);
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Free-flyer root joint (joint 1, parent = universe; S = I6, nv = 6): the three sweeps' steps for it.  calc_aba
+// (P1, general form): U = H, Dinv = (H + mu_ineq I)^-1 (Cholesky), no projection / propagation (nothing above the
+// root is ever read); v_parent = 0 so nu = -Dinv r and v = nu.  The regular sweeps then run over joints 2..nb.
+// ---------------------------------------------------------------------------------------------
+LOIK_DEV void spd6_inverse(double (&M)[36], double (&Minv)[21]) {  // M: full symmetric 6x6, overwritten by its Cholesky factor
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      double sum = M[6 * i + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) sum -= M[6 * i + k] * M[6 * j + k];
+      M[6 * i + j] = (i == j) ? sqrt(sum) : sum / M[6 * j + j];
+    }
+  double Li[36];  // L^-1 (lower triangular)
+#pragma unroll
+  for (int c = 0; c < 6; ++c)
+#pragma unroll
+    for (int i = c; i < 6; ++i) {
+      double sum = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = c; k < i; ++k) sum -= M[6 * i + k] * Li[6 * k + c];
+      Li[6 * i + c] = sum / M[6 * i + i];
+    }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = i; j < 6; ++j) {
+      double sum = 0.0;
+#pragma unroll
+      for (int k = j; k < 6; ++k) sum += Li[6 * k + i] * Li[6 * k + j];
+      Minv[s6(i, j)] = sum;
+    }
+}
+
+LOIK_DEV void ff_backward(const ModelC& c_model, double* __restrict__ T, const double mu, const double mu_eq) {
+  const Offs& O = c_model.off;
+  const JointC& J = c_model.j[1];
+  double* Pj = joint_blk(T, O, 0);
+  double* Pf = ff_blk(T, O);
+  const double rho = c_model.rho;
+  double A[6], B[9], D[6], p[6], w[6], z[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) { p[c] = -rho * ld(Pj, JR_V + c) - J.Hv[c]; A[c] = J.HrA[c]; D[c] = J.HrD[c]; w[c] = ld(Pf, FR_W + c); z[c] = ld(Pf, FR_Z + c); }
+#pragma unroll
+  for (int c = 0; c < 9; ++c) B[c] = J.HrB[c];
+  A[0] += rho; A[3] += rho; A[5] += rho; D[0] += rho; D[3] += rho; D[5] += rho;
+  if (J.task >= 0) {
+    const TaskC& K = c_model.t[J.task];
+    const double* Pk = task_blk(T, O, J.task);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { A[c] += mu_eq * K.AtA_A[c]; D[c] += mu_eq * K.AtA_D[c]; p[c] += ld(Pk, TR_ATY + c) - mu_eq * ldc(Pk, TR_ATB + c); }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) B[c] += mu_eq * K.AtA_B[c];
+  }
+  for (int n = 0; n < J.npin; ++n) {
+    const double* Pp = pend_blk(T, O, J.pin[n]);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { A[c] += ld(Pp, PR_H + c); D[c] += ld(Pp, PR_H + 15 + c); p[c] += ld(Pp, PR_H + 21 + c); }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) B[c] += ld(Pp, PR_H + 6 + c);
+  }
+  double Mx[36], Dinv[21];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      Mx[6 * a + b] = A[si(a, b)]; Mx[6 * (3 + a) + 3 + b] = D[si(a, b)];
+      Mx[6 * a + 3 + b] = B[3 * a + b]; Mx[6 * (3 + b) + a] = B[3 * a + b];
+    }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) Mx[7 * c] += mu;  // armature R = mu_ineq (hxx:294-295)
+  spd6_inverse(Mx, Dinv);
+#pragma unroll
+  for (int c = 0; c < 6; ++c) { st(Pj, JR_H + c, A[c]); st(Pj, JR_H + 15 + c, D[c]); st(Pj, JR_P + c, p[c]); st(Pf, FR_R + c, (w[c] - mu * z[c]) + p[c]); }
+#pragma unroll
+  for (int c = 0; c < 9; ++c) st(Pj, JR_H + 6 + c, B[c]);
+#pragma unroll
+  for (int c = 0; c < 21; ++c) st(Pf, FR_DINV + c, Dinv[c]);
+}
+
+template <bool DEBUG>
+LOIK_DEV void ff_forward(const ModelC& c_model, double* __restrict__ T, const double mu, const double mu_eq, Carry& cy) {
+  const Offs& O = c_model.off;
+  const JointC& J = c_model.j[1];
+  const int nb = c_model.nb;
+  double* Pj = joint_blk(T, O, 0);
+  double* Pf = ff_blk(T, O);
+  const double inv_mu = 1.0 / mu;
+  double Dinv[21], r[6], A[6], B[9], D[6], p[6], vold[6], fold[6], v[6], f[6];
+#pragma unroll
+  for (int c = 0; c < 21; ++c) Dinv[c] = ld(Pf, FR_DINV + c);
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    r[c] = ld(Pf, FR_R + c); A[c] = ld(Pj, JR_H + c); D[c] = ld(Pj, JR_H + 15 + c); p[c] = ld(Pj, JR_P + c);
+    vold[c] = ld(Pj, JR_V + c); fold[c] = ld(Pj, JR_F + c);
+  }
+#pragma unroll
+  for (int c = 0; c < 9; ++c) B[c] = ld(Pj, JR_H + 6 + c);
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {  // nu = -UDinv^T vp - Dinv r with vp = 0 (:127); v = vp + S nu = nu (:133-134)
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc += Dinv[s6(c, k)] * r[k];
+    v[c] = -acc;
+    cy.nu_inf = amax(cy.nu_inf, v[c]);
+    cy.dvis_inf = amax(cy.dvis_inf, v[c] - vold[c]);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    f[a] = A[si(a, 0)] * v[0] + A[si(a, 1)] * v[1] + A[si(a, 2)] * v[2] + B[3 * a] * v[3] + B[3 * a + 1] * v[4] + B[3 * a + 2] * v[5] + p[a];
+    f[3 + a] = B[a] * v[0] + B[3 + a] * v[1] + B[6 + a] * v[2] + D[si(a, 0)] * v[3] + D[si(a, 1)] * v[4] + D[si(a, 2)] * v[5] + p[3 + a];
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    cy.dfis_inf = amax(cy.dfis_inf, f[c] - fold[c]);
+    const double lb = c_model.bounds_per_instance ? ldc(Pf, FR_LB + c) : c_model.fflb[c];
+    const double ub = c_model.bounds_per_instance ? ldc(Pf, FR_UB + c) : c_model.ffub[c];
+    const double nu = v[c], w_old = ld(Pf, FR_W + c);
+    cy.dnu_inf = amax(cy.dnu_inf, nu - ld(Pf, FR_NU + c));
+    const double z = fmin(ub, fmax(lb, nu + inv_mu * w_old));
+    cy.dz_inf = amax(cy.dz_inf, z - ld(Pf, FR_Z + c));
+    const double rp = nu - z;
+    cy.pres_slack = amax(cy.pres_slack, rp);
+    const double dw = mu * rp;
+    cy.dw_inf = amax(cy.dw_inf, dw);
+    cy.ubdw_p += ub * fmax(dw, 0.0);
+    cy.lbdw_m += lb * fmin(dw, 0.0);
+    st(Pj, JR_V + c, v[c]); st(Pj, JR_F + c, f[c]);
+    st(Pf, FR_NU + c, nu); st(Pf, FR_Z + c, z); st(Pf, FR_W + c, w_old + dw);
+    if (DEBUG) st(T, O.prv + 6 * nb + c, rp);
+  }
+  if (J.task >= 0) {  // DualUpdate for a task on the root joint (:410-451)
+    const TaskC& K = c_model.t[J.task];
+    double* Pk = task_blk(T, O, J.task);
+    double y[6], plus = 0.0, minus = 0.0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const double Av = K.A[6 * a] * v[0] + K.A[6 * a + 1] * v[1] + K.A[6 * a + 2] * v[2] + K.A[6 * a + 3] * v[3] + K.A[6 * a + 4] * v[4] + K.A[6 * a + 5] * v[5];
+      const double bi = ldc(Pk, TR_B + a), e = Av - bi, dy = mu_eq * e;
+      y[a] = ld(Pk, TR_Y + a) + dy;
+      cy.dyis_inf = amax(cy.dyis_inf, dy); cy.Av_inf = amax(cy.Av_inf, Av); cy.pres_task = amax(cy.pres_task, e);
+      plus += bi * fmax(dy, 0.0); minus += bi * fmin(dy, 0.0);
+      if (DEBUG) st(T, O.prv + a, e);
+    }
+    cy.bTdy_p += plus; cy.bTdy_m += minus;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      st(Pk, TR_Y + a, y[a]);
+      st(Pk, TR_ATY + a, K.A[a] * y[0] + K.A[6 + a] * y[1] + K.A[12 + a] * y[2] + K.A[18 + a] * y[3] + K.A[24 + a] * y[4] + K.A[30 + a] * y[5]);
+    }
+  }
+}
+
+template <bool DEBUG>
+LOIK_DEV void ff_residual(const ModelC& c_model, double* __restrict__ T, Resid& rs) {
+  const Offs& O = c_model.off;
+  const JointC& J = c_model.j[1];
+  const int nb = c_model.nb;
+  double* Pj = joint_blk(T, O, 0);
+  double* Pf = ff_blk(T, O);
+  double f[6], v[6], F[6], Fold[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) { f[c] = ld(Pj, JR_F + c); v[c] = ld(Pj, JR_V + c); Fold[c] = ld(Pj, JR_FD + c); F[c] = 0.0; }
+  if (J.task >= 0) {
+    const double* Pk = task_blk(T, O, J.task);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) F[c] = ld(Pk, TR_ATY + c);
+  }
+  for (int n = 0; n < J.npin; ++n) {
+    const double* Pp = pend_blk(T, O, J.pin[n]);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) F[c] += ld(Pp, PR_F + c);
+  }
+  double Hrv[6];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    Hrv[a] = J.HrA[si(a, 0)] * v[0] + J.HrA[si(a, 1)] * v[1] + J.HrA[si(a, 2)] * v[2] + J.HrB[3 * a] * v[3] + J.HrB[3 * a + 1] * v[4] + J.HrB[3 * a + 2] * v[5];
+    Hrv[3 + a] = J.HrB[a] * v[0] + J.HrB[3 + a] * v[1] + J.HrB[6 + a] * v[2] + J.HrD[si(a, 0)] * v[3] + J.HrD[si(a, 1)] * v[4] + J.HrD[si(a, 2)] * v[5];
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    F[c] += -f[c];
+    rs.dF_inf = amax(rs.dF_inf, F[c] - Fold[c]);
+    rs.F_inf = amax(rs.F_inf, F[c]);
+    rs.Hrefv_inf = amax(rs.Hrefv_inf, Hrv[c]);
+    const double rd = Hrv[c] - J.Hv[c] + F[c];
+    rs.dres_v = amax(rs.dres_v, rd);
+    const double Tn = f[c] + ld(Pf, FR_W + c);  // S^T f + w with S = I (:231)
+    rs.T_inf = amax(rs.T_inf, Tn);
+    rs.dT_inf = amax(rs.dT_inf, Tn - ld(Pf, FR_T + c));
+    st(Pj, JR_FD + c, F[c]);
+    st(Pf, FR_T + c, Tn);
+    if (DEBUG) { st(T, O.drv + c, rd); st(T, O.drv + 6 * nb + c, Tn); }
   }
 }
 
@@ -820,7 +1031,7 @@ LOIK_DEV void fine_boxproj(const ModelC& M, double* __restrict__ T, const double
     dz = amax(dz, z - ld(Pj, JR_Z));
     slack = amax(slack, nu - z);
     st(Pj, JR_Z, z);
-    st(T, O.prv + 6 * M.nb + (i - 1), nu - z);
+    st(T, O.prv + 6 * M.nb + J.idxv, nu - z);
   }
   st(G, GR_NORMS + N_DZ, dz);
   st(G, GR_NORMS + N_PRES_SLACK, slack);

@@ -49,13 +49,17 @@ __global__ void __launch_bounds__(kBlock, MINB) k_iterate(const __grid_constant_
       for (int n = 0; n < iters; ++n) {
         ++it;
         const double mu_eq = c_model.mu_scale * mu;
-        sweep_backward(c_model, T, mu, mu_eq, 1, nb);
+        const int lo = c_model.has_ff ? 2 : 1;  // a free-flyer root joint is handled outside the joint loops
+        sweep_backward(c_model, T, mu, mu_eq, lo, nb);
+        if (c_model.has_ff) ff_backward(c_model, T, mu, mu_eq);
         Carry cy;
         zero(cy);
-        sweep_forward<DEBUG>(c_model, T, mu, mu_eq, cy, 1, nb);
+        if (c_model.has_ff) ff_forward<DEBUG>(c_model, T, mu, mu_eq, cy);
+        sweep_forward<DEBUG>(c_model, T, mu, mu_eq, cy, lo, nb);
         Resid rs;
         zero(rs);
-        sweep_residual<DEBUG>(c_model, T, rs, 1, nb);
+        sweep_residual<DEBUG>(c_model, T, rs, lo, nb);
+        if (c_model.has_ff) ff_residual<DEBUG>(c_model, T, rs);
         status = decide<DEBUG>(c_model, T, status, it, fixed != 0, cy, rs, mu);
         if (status >= ST_CONVERGED) break;
       }
@@ -106,19 +110,28 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
       for (int lv = 0; lv < c_model.nblevel; ++lv) {
         if (alive)
           for (int g = 0; g < c_model.nseg; ++g)
-            if (c_model.seg[g].bwarp == w && c_model.seg[g].blevel == lv) sweep_backward(c_model, T, mu, mu_eq, c_model.seg[g].lo, c_model.seg[g].hi);
+            if (c_model.seg[g].bwarp == w && c_model.seg[g].blevel == lv) {
+              if (c_model.has_ff && c_model.seg[g].lo == 1) ff_backward(c_model, T, mu, mu_eq);
+              else sweep_backward(c_model, T, mu, mu_eq, c_model.seg[g].lo, c_model.seg[g].hi);
+            }
         __syncthreads();
       }
       for (int lv = 0; lv < c_model.nflevel; ++lv) {
         if (alive)
           for (int g = 0; g < c_model.nseg; ++g)
-            if (c_model.seg[g].fwarp == w && c_model.seg[g].flevel == lv) sweep_forward<DEBUG>(c_model, T, mu, mu_eq, cy, c_model.seg[g].lo, c_model.seg[g].hi);
+            if (c_model.seg[g].fwarp == w && c_model.seg[g].flevel == lv) {
+              if (c_model.has_ff && c_model.seg[g].lo == 1) ff_forward<DEBUG>(c_model, T, mu, mu_eq, cy);
+              else sweep_forward<DEBUG>(c_model, T, mu, mu_eq, cy, c_model.seg[g].lo, c_model.seg[g].hi);
+            }
         __syncthreads();
       }
       for (int lv = 0; lv < c_model.nblevel; ++lv) {
         if (alive)
           for (int g = 0; g < c_model.nseg; ++g)
-            if (c_model.seg[g].bwarp == w && c_model.seg[g].blevel == lv) sweep_residual<DEBUG>(c_model, T, rs, c_model.seg[g].lo, c_model.seg[g].hi);
+            if (c_model.seg[g].bwarp == w && c_model.seg[g].blevel == lv) {
+              if (c_model.has_ff && c_model.seg[g].lo == 1) ff_residual<DEBUG>(c_model, T, rs);
+              else sweep_residual<DEBUG>(c_model, T, rs, c_model.seg[g].lo, c_model.seg[g].hi);
+            }
         __syncthreads();
       }
       {  // combine the per-warp partial norms / sums
@@ -230,6 +243,11 @@ __global__ void __launch_bounds__(128) k_repack(const __grid_constant__ ModelC c
 #pragma unroll
     for (int r = 0; r < JR_H; ++r) st(Pd, r, tmp[r]);
   }
+  if (c_model.has_ff) {
+    const double* Ps = ff_blk(const_cast<double*>(Ts), O);
+    double* Pd = ff_blk(Td, O);
+    for (int r = 0; r < FR_DINV; ++r) st(Pd, r, ld(Ps, r));  // state + problem data
+  }
   for (int t = 0; t < nc; ++t) {
     const double* Ps = task_blk(const_cast<double*>(Ts), O, t);
     double* Pd = task_blk(Td, O, t);
@@ -272,6 +290,11 @@ LOIK_DEV void retire_one(const ModelC& c_model, const StateP& X, const int* __re
 #pragma unroll
     for (int r = 0; r < JR_JQ; ++r) st(Pd, r, tmp[r]);
   }
+  if (c_model.has_ff) {
+    const double* Ps = ff_blk(const_cast<double*>(Ts), O);
+    double* Pd = ff_blk(Td, O);
+    for (int r = 0; r < FR_LB; ++r) st(Pd, r, ld(Ps, r));  // nu, z, w, T
+  }
   for (int t = 0; t < nc; ++t) {
     const double* Ps = task_blk(const_cast<double*>(Ts), O, t);
     double* Pd = task_blk(Td, O, t);
@@ -287,7 +310,8 @@ __global__ void __launch_bounds__(kBlock) k_step_backward(const __grid_constant_
   double* T = tile_ptr(S, c_model, s);
   if (ld_ctl(c_model, T).x >= ST_CONVERGED) return;
   const double mu = ld(glob_blk(T, c_model.off), GR_MU);
-  sweep_backward(c_model, T, mu, c_model.mu_scale * mu, 1, c_model.nb);
+  sweep_backward(c_model, T, mu, c_model.mu_scale * mu, c_model.has_ff ? 2 : 1, c_model.nb);
+  if (c_model.has_ff) ff_backward(c_model, T, mu, c_model.mu_scale * mu);
 }
 __global__ void __launch_bounds__(kBlock) k_step_forward(const __grid_constant__ ModelC c_model, const StateP S) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -298,7 +322,8 @@ __global__ void __launch_bounds__(kBlock) k_step_forward(const __grid_constant__
   const double mu = ld(G, GR_MU);
   Carry cy;
   zero(cy);
-  sweep_forward<true>(c_model, T, mu, c_model.mu_scale * mu, cy, 1, c_model.nb);
+  if (c_model.has_ff) ff_forward<true>(c_model, T, mu, c_model.mu_scale * mu, cy);
+  sweep_forward<true>(c_model, T, mu, c_model.mu_scale * mu, cy, c_model.has_ff ? 2 : 1, c_model.nb);
   const double* c = reinterpret_cast<const double*>(&cy);
   for (int k = 0; k < kCarryRows; ++k) st(G, GR_CARRY + k, c[k]);
   // ComputePrimalResiduals (hxx:494-503)
@@ -319,7 +344,8 @@ __global__ void __launch_bounds__(kBlock) k_step_residual(const __grid_constant_
   for (int k = 0; k < kCarryRows; ++k) c[k] = ld(G, GR_CARRY + k);
   Resid rs;
   zero(rs);
-  sweep_residual<true>(c_model, T, rs, 1, c_model.nb);
+  sweep_residual<true>(c_model, T, rs, c_model.has_ff ? 2 : 1, c_model.nb);
+  if (c_model.has_ff) ff_residual<true>(c_model, T, rs);
   double mu = ld(G, GR_MU);
   const int it = ctl.y + 1;
   status = decide<true>(c_model, T, status, it, fixed != 0, cy, rs, mu);
@@ -364,6 +390,13 @@ __global__ void k_reset(const __grid_constant__ ModelC c_model, const StateP S, 
     if (flags & RST_VFF)
       for (int c = 0; c < 6; ++c) { st(Pj, JR_V + c, 0.0); st(Pj, JR_F + c, 0.0); st(Pj, JR_FD + c, 0.0); }
   }
+  if (c_model.has_ff) {
+    double* Pf = ff_blk(T, O);
+    for (int c = 0; c < 6; ++c) {
+      if (flags & RST_WZ) { st(Pf, FR_W + c, 0.0); st(Pf, FR_Z + c, 0.0); }
+      if (flags & RST_NU) st(Pf, FR_NU + c, 0.0);
+    }
+  }
   if (flags & RST_YATY)
     for (int k = 0; k < nc; ++k) {
       double* Pk = task_blk(T, O, k);
@@ -381,17 +414,19 @@ __global__ void k_reset(const __grid_constant__ ModelC c_model, const StateP S, 
 // q is batch-major [n][nq]; it is staged through shared memory so both the read and the write coalesce.
 __global__ void __launch_bounds__(kBlock) k_set_q(const __grid_constant__ ModelC c_model, const StateP S, const double* __restrict__ q) {
   extern __shared__ double sh[];
-  const int nb = c_model.nb;
+  const int nb = c_model.nb, nq = c_model.nq;
   const int s0 = blockIdx.x * blockDim.x;
   const int cnt = min((int)blockDim.x, S.n - s0);
-  for (int e = threadIdx.x; e < cnt * nb; e += blockDim.x) sh[e] = q[(size_t)s0 * nb + e];
+  for (int e = threadIdx.x; e < cnt * nq; e += blockDim.x) sh[e] = q[(size_t)s0 * nq + e];
   __syncthreads();
   const int s = s0 + threadIdx.x;
   if (s >= S.n) return;
   double* T = tile_ptr(S, c_model, s);
-  for (int i = 1; i <= nb; ++i) {
+  if (c_model.has_ff)  // the root pose does not enter the velocity-level problem (nothing above the root is read); keep q
+    for (int c = 0; c < 7; ++c) st(ff_blk(T, c_model.off), FR_Q + c, sh[threadIdx.x * nq + c]);
+  for (int i = c_model.has_ff ? 2 : 1; i <= nb; ++i) {
     const int jt = c_model.j[i].jtype;
-    const double qi = sh[threadIdx.x * nb + (i - 1)];
+    const double qi = sh[threadIdx.x * nq + c_model.j[i].idxq];
     double a, b;
     if (jt <= 2 || jt == 6) sincos(qi, &a, &b);
     else { a = qi; b = 0.0; }
@@ -456,11 +491,13 @@ __global__ void k_set_bounds(const __grid_constant__ ModelC c_model, const State
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
   double* T = tile_ptr(S, c_model, s);
-  const int nb = c_model.nb;
-  for (int r = 0; r < nb; ++r) {
-    double* Pj = joint_blk(T, c_model.off, r);
-    st(Pj, JR_LB, lb[(size_t)s * nb + r]);
-    st(Pj, JR_UB, ub[(size_t)s * nb + r]);
+  const int nb = c_model.nb, nv = c_model.nv;
+  if (c_model.has_ff)
+    for (int c = 0; c < 6; ++c) { st(ff_blk(T, c_model.off), FR_LB + c, lb[(size_t)s * nv + c]); st(ff_blk(T, c_model.off), FR_UB + c, ub[(size_t)s * nv + c]); }
+  for (int i = c_model.has_ff ? 2 : 1; i <= nb; ++i) {
+    double* Pj = joint_blk(T, c_model.off, i - 1);
+    st(Pj, JR_LB, lb[(size_t)s * nv + c_model.j[i].idxv]);
+    st(Pj, JR_UB, ub[(size_t)s * nv + c_model.j[i].idxv]);
   }
 }
 
@@ -470,14 +507,26 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ ModelC c
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)S.n * nrows) return;
   const int s = (int)(idx / nrows), k = (int)(idx % nrows);
-  dst[idx] = tile_ptr(S, c_model, s)[(size_t)map[k] * 32];
+  dst[idx] = map[k] < 0 ? 0.0 : tile_ptr(S, c_model, s)[(size_t)map[k] * 32];
 }
 __global__ void k_gather_limi(const __grid_constant__ ModelC c_model, const StateP S, double* __restrict__ dst) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
   const double* T = tile_ptr(S, c_model, s);
   const int nb = c_model.nb;
-  for (int i = 1; i <= nb; ++i) {
+  if (c_model.has_ff) {  // liMi[1] = jointPlacement * (R(quat), p)
+    const double* Pf = ff_blk(const_cast<double*>(T), c_model.off);
+    const double x = ld(Pf, FR_Q + 3), y = ld(Pf, FR_Q + 4), z = ld(Pf, FR_Q + 5), w = ld(Pf, FR_Q + 6);
+    const double M[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w), 1 - 2 * (x * x + z * z),
+                         2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+    const double* P = c_model.j[1].plR;
+    double* o = dst + (size_t)s * nb * 12;
+    for (int a = 0; a < 3; ++a) {
+      for (int b = 0; b < 3; ++b) o[3 * a + b] = P[3 * a] * M[b] + P[3 * a + 1] * M[3 + b] + P[3 * a + 2] * M[6 + b];
+      o[9 + a] = c_model.j[1].plp[a] + P[3 * a] * ld(Pf, FR_Q) + P[3 * a + 1] * ld(Pf, FR_Q + 1) + P[3 * a + 2] * ld(Pf, FR_Q + 2);
+    }
+  }
+  for (int i = c_model.has_ff ? 2 : 1; i <= nb; ++i) {
     double R[9], t[3];
     const double* Pj = joint_blk(const_cast<double*>(T), c_model.off, i - 1);
     make_xf(c_model.j[i], ld(Pj, JR_JQ), ld(Pj, JR_JQ + 1), R, t);
@@ -533,7 +582,7 @@ static int fail(int code, const std::string& msg) {
 
 struct loik_solver {
   int device = 0, batch = 0, ntiles = 0;
-  int nj = 0, nb = 0, nc = 0, npend = 0;
+  int nj = 0, nb = 0, nc = 0, npend = 0, nv = 0, nq = 0;
   loik_params prm{};
   ModelC mc{};          // host copy of this solver's constant block
   bool problem_set = false;
@@ -669,7 +718,10 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   if (batch < 1) return fail(LOIK_ERR_INVALID, "loik_create: batch must be >= 1");
   for (int i = 1; i < nj; ++i) {
     if (model->parents[i] < 0 || model->parents[i] >= i) return fail(LOIK_ERR_INVALID, "loik_create: parents[i] must be < i");
-    if (model->joint_types[i] < 0 || model->joint_types[i] > LOIK_JOINT_PU) return fail(LOIK_ERR_UNSUPPORTED, "loik_create: only 1-DoF revolute/prismatic joints are supported");
+    if (model->joint_types[i] < 0 || model->joint_types[i] > LOIK_JOINT_FF)
+      return fail(LOIK_ERR_UNSUPPORTED, "loik_create: unsupported joint type (1-DoF revolute/prismatic joints and a free-flyer root are supported)");
+    if (model->joint_types[i] == LOIK_JOINT_FF && !(i == 1 && model->parents[i] == 0))
+      return fail(LOIK_ERR_UNSUPPORTED, "loik_create: a free-flyer joint is supported as the root joint (joint 1, parent 0) only");
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LOIK_ERR_CUDA, "loik_create: no CUDA device (libloik_b200 has no CPU fallback)");
@@ -677,6 +729,8 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   loik_solver* h = new loik_solver();
   h->device = device; h->batch = batch; h->ntiles = (batch + 31) / 32;
   h->nj = nj; h->nb = nj - 1; h->nc = params->num_eq_c; h->prm = *params;
+  const bool has_ff = model->joint_types[1] == LOIK_JOINT_FF;
+  h->nv = nj - 1 + (has_ff ? 5 : 0); h->nq = nj - 1 + (has_ff ? 6 : 0);
   h->minb = 4;
   if (const char* e = std::getenv("LOIK_DENSE")) { const int v = std::atoi(e); if (v >= 0) h->dense_sweeps = v; }
   if (const char* e = std::getenv("LOIK_NO_GRAPH")) { if (std::atoi(e) != 0) h->use_graph = false; }
@@ -689,6 +743,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   ModelC& M = h->mc;
   std::memset(&M, 0, sizeof(M));
   M.nj = nj; M.nb = nj - 1; M.nc = h->nc;
+  M.has_ff = has_ff ? 1 : 0; M.nv = h->nv; M.nq = h->nq;
   M.max_iter = params->max_iter; M.rho = params->rho; M.mu0 = params->mu; M.mu_scale = params->mu_equality_scale_factor;
   M.tol_abs = params->tol_abs; M.tol_rel = params->tol_rel; M.tol_pinf = params->tol_primal_inf; M.tol_dinf = params->tol_dual_inf;
   M.tol_tail = params->tol_tail_solve;
@@ -703,8 +758,11 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
     J.parent = model->parents[i]; J.jtype = model->joint_types[i]; J.task = -1;
     for (int c = 0; c < 9; ++c) J.plR[c] = model->placement_R[9 * i + c];
     for (int c = 0; c < 3; ++c) { J.plp[c] = model->placement_p[3 * i + c]; J.axis[c] = model->joint_axes[3 * i + c]; }
-    J.carry = (J.parent > 0 && J.parent == i - 1 && nchild[J.parent] == 1) ? 1 : 0;
+    // (edges into a free-flyer root always go through a pending block: it is handled outside the joint loops)
+    J.carry = (J.parent > 0 && J.parent == i - 1 && nchild[J.parent] == 1 && model->joint_types[J.parent] != LOIK_JOINT_FF) ? 1 : 0;
     J.pout = -1; J.npin = 0;
+    J.idxv = (i - 1) + ((has_ff && i > 1) ? 5 : 0);
+    J.idxq = (i - 1) + ((has_ff && i > 1) ? 6 : 0);
   }
   for (int i = 1; i < nj; ++i) {
     JointC& J = M.j[i];
@@ -775,8 +833,9 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   O.joint0 = rows; rows += JR_ROWS * nb;
   O.task0 = rows; rows += TR_ROWS * nc;
   O.pend0 = rows; rows += PR_ROWS * std::max(npend, 1);
-  O.prv = rows; rows += 7 * nb;
-  O.drv = rows; rows += 7 * nb;
+  O.ff0 = rows; rows += has_ff ? FR_ROWS : 0;
+  O.prv = rows; rows += 6 * nb + h->nv;
+  O.drv = rows; rows += 6 * nb + h->nv;
   O.rows = rows;
   const size_t arena_doubles = (size_t)h->ntiles * rows * 32;
   if (cudaMalloc(&h->arena, arena_doubles * sizeof(double)) != cudaSuccess) { delete h; return fail(LOIK_ERR_CUDA, "loik_create: cudaMalloc failed"); }
@@ -789,30 +848,45 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
     std::vector<int> all;
     const int ncq = h->nc;
     auto per_joint = [&](std::vector<int>& m, int jr, int width) { for (int j = 0; j < nb; ++j) for (int c = 0; c < width; ++c) m.push_back(O.joint0 + JR_ROWS * j + jr + c); };
+    // one row per dof: the free-flyer root contributes 6 rows of its own block (fr < 0: no such quantity -> zeros)
+    auto per_dof = [&](std::vector<int>& m, int jr, int fr) {
+      for (int j = 0; j < nb; ++j) {
+        if (has_ff && j == 0) { for (int c = 0; c < 6; ++c) m.push_back(fr < 0 ? -1 : O.ff0 + fr + c); }
+        else m.push_back(O.joint0 + JR_ROWS * j + jr);
+      }
+    };
+    auto per_joint_noff = [&](std::vector<int>& m, int jr, int width) {
+      for (int j = 0; j < nb; ++j) for (int c = 0; c < width; ++c) m.push_back((has_ff && j == 0) ? -1 : O.joint0 + JR_ROWS * j + jr + c);
+    };
     auto per_task = [&](std::vector<int>& m, int tr) { for (int k = 0; k < ncq; ++k) for (int c = 0; c < 6; ++c) m.push_back(O.task0 + TR_ROWS * k + tr + c); };
     auto span = [&](std::vector<int>& m, int r0, int n) { for (int c = 0; c < n; ++c) m.push_back(r0 + c); };
     for (int field = 0; field <= LOIK_F_Q; ++field) {
       std::vector<int> m;
       switch (field) {
-        case LOIK_F_Z: per_joint(m, JR_Z, 1); break;
-        case LOIK_F_NU: per_joint(m, JR_NU, 1); break;
-        case LOIK_F_W: per_joint(m, JR_W, 1); break;
+        case LOIK_F_Z: per_dof(m, JR_Z, FR_Z); break;
+        case LOIK_F_NU: per_dof(m, JR_NU, FR_NU); break;
+        case LOIK_F_W: per_dof(m, JR_W, FR_W); break;
         case LOIK_F_Y: per_task(m, TR_Y); break;
         case LOIK_F_V: per_joint(m, JR_V, 6); break;
         case LOIK_F_F: per_joint(m, JR_F, 6); break;
         case LOIK_F_ATY: per_task(m, TR_ATY); break;
         case LOIK_F_FDPA: per_joint(m, JR_FD, 6); break;
-        case LOIK_F_STF_PLUS_W: per_joint(m, JR_T, 1); break;
+        case LOIK_F_STF_PLUS_W: per_dof(m, JR_T, FR_T); break;
         case LOIK_F_P: per_joint(m, JR_P, 6); break;
-        case LOIK_F_UDINV: per_joint(m, JR_UD, 6); break;
-        case LOIK_F_DINV: per_joint(m, JR_DINV, 1); break;
-        case LOIK_F_R: per_joint(m, JR_R, 1); break;
+        case LOIK_F_UDINV: per_joint_noff(m, JR_UD, 6); break;  // (zeros for a free-flyer root: its UDinv never enters the solution)
+        case LOIK_F_DINV: per_joint_noff(m, JR_DINV, 1); break;
+        case LOIK_F_R: per_dof(m, JR_R, FR_R); break;
         case LOIK_F_MU: span(m, O.glob + GR_MU, 1); break;
         case LOIK_F_RESIDUALS: span(m, O.glob + GR_RES, 4); break;
         case LOIK_F_NORMS: span(m, O.glob + GR_NORMS, LOIK_NUM_NORMS); break;
-        case LOIK_F_PRIMAL_RES_VEC: span(m, O.prv, 7 * nb); break;
-        case LOIK_F_DUAL_RES_VEC: span(m, O.drv, 7 * nb); break;
-        case LOIK_F_Q: per_joint(m, JR_Q, 1); break;
+        case LOIK_F_PRIMAL_RES_VEC: span(m, O.prv, 6 * nb + h->nv); break;
+        case LOIK_F_DUAL_RES_VEC: span(m, O.drv, 6 * nb + h->nv); break;
+        case LOIK_F_Q:
+          for (int j = 0; j < nb; ++j) {
+            if (has_ff && j == 0) { for (int c = 0; c < 7; ++c) m.push_back(O.ff0 + FR_Q + c); }
+            else m.push_back(O.joint0 + JR_ROWS * j + JR_Q);
+          }
+          break;
         case LOIK_F_H:  // expand the 21 stored scalars of each joint to a full symmetric 6x6
           for (int j = 0; j < nb; ++j)
             for (int a = 0; a < 6; ++a)
@@ -888,12 +962,13 @@ static int set_problem_consts(loik_solver* h, const double* H_ref, const double*
   double hv_inf = 0; for (int i = 0; i < 6; ++i) hv_inf = std::max(hv_inf, std::fabs(Hv[i]));
   M.Hv_inf = hv_inf;  // = |Hv[0]|inf (ik-id-description-optimized.hpp:95)
   M.bounds_per_instance = bounds_shared ? 0 : 1;
+  if (M.has_ff && bounds_shared) for (int c = 0; c < 6; ++c) { M.fflb[c] = lb[c]; M.ffub[c] = ub[c]; }
   for (int i = 1; i < h->nj; ++i) {
     JointC& J = M.j[i];
     sym_blocks(H_ref, J.HrA, J.HrB, J.HrD);
     for (int c = 0; c < 6; ++c) J.Hv[c] = Hv[c];
     J.task = -1;
-    if (bounds_shared) { J.lb = lb[i - 1]; J.ub = ub[i - 1]; }
+    if (bounds_shared) { J.lb = lb[J.idxv]; J.ub = ub[J.idxv]; }
   }
   for (int k = 0; k < n_ids; ++k) {
     const int c = ids[k];
@@ -918,10 +993,10 @@ int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const 
   if (!h || !q || !H_ref || !v_ref || !lb || !ub || (n_ids > 0 && (!ids || !A || !b))) return fail(LOIK_ERR_INVALID, "loik_solve_init: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
-  const int B = h->batch, nb = h->nb, nc = h->nc;
-  const size_t q_bytes = (size_t)B * nb * sizeof(double);
+  const int B = h->batch, nc = h->nc;
+  const size_t q_bytes = (size_t)B * h->nq * sizeof(double);
   const size_t b_bytes = (size_t)(b_per_instance ? B : 1) * nc * 6 * sizeof(double);
-  const size_t bd_bytes = (size_t)(bounds_per_instance ? B : 1) * nb * sizeof(double);
+  const size_t bd_bytes = (size_t)(bounds_per_instance ? B : 1) * h->nv * sizeof(double);
   if (loc != LOIK_HOST && loc != LOIK_DEVICE && loc != LOIK_HOST_PINNED) return fail(LOIK_ERR_INVALID, "loik_solve_init: bad loc");
   // batch-shared bounds are batch-uniform data like H_ref: always host pointers, they travel in the kernel parameter block
   int rc = set_problem_consts(h, H_ref, v_ref, n_ids, ids, A, lb, ub, !bounds_per_instance);
@@ -940,7 +1015,7 @@ int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const 
   // ik_id_data_.Reset(warm_start) + ResetSolver() + FwdPassInit's y/Aty wipe (hpp:346-359, hxx:270-278)
   const int flags = RST_SOLVER | (h->prm.warm_start ? 0 : (RST_WZ | RST_NU | RST_VFF | RST_YATY));
   k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, flags);
-  k_set_q<<<grid_for(B), kBlock, kBlock * nb * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);
+  k_set_q<<<grid_for(B), kBlock, kBlock * h->nq * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);
   h->launches += 2;
   h->last_list = -1;
   if (nc > 0) { k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)db, b_per_instance, -1); h->launches++; }
@@ -1087,12 +1162,12 @@ int loik_fwd_pass_init(loik_solver* h, const double* q, int32_t loc, void* strea
   if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_fwd_pass_init: call loik_solve_init first");
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
-  const size_t q_bytes = (size_t)h->batch * h->nb * sizeof(double);
+  const size_t q_bytes = (size_t)h->batch * h->nq * sizeof(double);
   int rc;
   if (loc != LOIK_DEVICE) { rc = ensure_stage(h, q_bytes + 64, loc == LOIK_HOST); if (rc) return rc; }
   const void* dq;
   rc = to_device(h, q, q_bytes, loc, 0, st, &dq); if (rc) return rc;
-  k_set_q<<<grid_for(h->batch), kBlock, kBlock * h->nb * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);
+  k_set_q<<<grid_for(h->batch), kBlock, kBlock * h->nq * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);
   h->launches++;
   CK(cudaGetLastError());
   if (loc == LOIK_HOST) CK(cudaStreamSynchronize(st));
@@ -1152,8 +1227,8 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
   for (int i = 0; i < 6; ++i)
     for (int j = 0; j < 6; ++j) { double s = 0; for (int r = 0; r < 6; ++r) s += T.A[6 * r + i] * T.A[6 * r + j]; AtA[6 * i + j] = s; }
   sym_blocks(AtA, T.AtA_A, T.AtA_B, T.AtA_D);
-  const int B = h->batch, nb = h->nb;
-  const size_t q_bytes = (size_t)B * nb * sizeof(double), b_bytes = (size_t)(b_per_instance ? B : 1) * 6 * sizeof(double);
+  const int B = h->batch;
+  const size_t q_bytes = (size_t)B * h->nq * sizeof(double), b_bytes = (size_t)(b_per_instance ? B : 1) * 6 * sizeof(double);
   if (loc != LOIK_DEVICE) { rc = ensure_stage(h, q_bytes + b_bytes + 64, loc == LOIK_HOST); if (rc) return rc; }
   rc = upload_consts(h, st); if (rc) return rc;
   const void *dq = nullptr, *db;
@@ -1162,7 +1237,7 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
   const int flags = RST_SOLVER | (h->prm.warm_start ? 0 : (RST_WZ | RST_NU | RST_VFF | RST_YATY));
   k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, flags);
   k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)db, b_per_instance, k);
-  if (q) k_set_q<<<grid_for(B), kBlock, kBlock * nb * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);  // else: keep the device-resident q (loik_integrate)
+  if (q) k_set_q<<<grid_for(B), kBlock, kBlock * h->nq * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);  // else: keep the device-resident q (loik_integrate)
   h->launches += 3;
   h->last_list = -1;
   CK(cudaGetLastError());
@@ -1175,6 +1250,7 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
 int loik_integrate(loik_solver* h, double dt, void* stream) {
   if (!h) return fail(LOIK_ERR_INVALID, "null handle");
   if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_integrate: call loik_solve_init first");
+  if (h->mc.has_ff) return fail(LOIK_ERR_UNSUPPORTED, "loik_integrate: free-flyer root joints are not supported yet (SE3 exponential)");
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
   k_integrate<<<grid_for(h->batch, 128), 128, 0, st>>>(h->mc, h->S, dt);
@@ -1255,6 +1331,7 @@ int loik_step(loik_solver* h, int32_t step_id, void* stream) {
     case LOIK_STEP_BOX_PROJ: case LOIK_STEP_DUAL_UPDATE: case LOIK_STEP_COMPUTE_RESIDUALS: case LOIK_STEP_CHECK_CONVERGENCE:
     case LOIK_STEP_CHECK_FEASIBILITY: case LOIK_STEP_UPDATE_MU:
       if (!h->debug) return fail(LOIK_ERR_STATE, "loik_step: the per-method steps need loik_set_debug(h, 1)");
+      if (h->mc.has_ff) return fail(LOIK_ERR_UNSUPPORTED, "loik_step: the per-method steps do not support a free-flyer root (use the fused steps)");
       k_fine<<<g, kBlock, 0, st>>>(h->mc, h->S, step_id);
       break;
     default: return fail(LOIK_ERR_INVALID, "loik_step: unknown step id");

@@ -359,11 +359,12 @@ class FirstOrderLoikOptimized:
         self._check(self._lib.loik_set_warm_start(self._h, int(bool(ws))))
 
     def _field_shape(self, field):
-        nb, nc = self.model.nb, self.nc
-        return {F_Z: (nb,), F_NU: (nb,), F_W: (nb,), F_Y: (nc, 6), F_V: (nb, 6), F_F: (nb, 6), F_ATY: (nc, 6),
-                F_FDPA: (nb, 6), F_STF_PLUS_W: (nb,), F_H: (nb, 6, 6), F_P: (nb, 6), F_UDINV: (nb, 6), F_DINV: (nb,),
-                F_R: (nb,), F_LIMI: (nb, 12), F_MU: (), F_ITER: (), F_STATUS: (), F_RESIDUALS: (4,),
-                F_NORMS: (len(NORM_NAMES),), F_PRIMAL_RES_VEC: (7 * nb,), F_DUAL_RES_VEC: (7 * nb,), F_Q: (nb,)}[field]
+        nb, nc, nv, nq = self.model.nb, self.nc, self.model.nv, self.model.nq
+        return {F_Z: (nv,), F_NU: (nv,), F_W: (nv,), F_Y: (nc, 6), F_V: (nb, 6), F_F: (nb, 6), F_ATY: (nc, 6),
+                F_FDPA: (nb, 6), F_STF_PLUS_W: (nv,), F_H: (nb, 6, 6), F_P: (nb, 6), F_UDINV: (nb, 6), F_DINV: (nb,),
+                F_R: (nv,), F_LIMI: (nb, 12), F_MU: (), F_ITER: (), F_STATUS: (), F_RESIDUALS: (4,),
+                F_NORMS: (len(NORM_NAMES),), F_PRIMAL_RES_VEC: (6 * nb + nv,), F_DUAL_RES_VEC: (6 * nb + nv,),
+                F_Q: (nq,)}[field]
 
     def get(self, field, out=None):
         """Copy a per-instance field of the whole batch out: numpy array [B, ...] (or into a CUDA tensor)."""

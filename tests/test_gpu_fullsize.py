@@ -14,7 +14,7 @@ from tests.helpers import ctor_kwargs, rel_inf
 
 pytestmark = pytest.mark.gpu
 
-FULL = [("panda", 65536), ("ur10", 262144), ("talos", 16384)]
+FULL = [("panda", 65536), ("ur10", 262144), ("talos", 16384), ("talos_ff", 8192)]
 
 
 def _gpu(model, params, batch):
@@ -51,7 +51,7 @@ def test_full_size_sample_vs_oracle_and_properties(name, B):
     assert (np.abs(r["z"] - pb["lb"])[lo] < 5e-2).all()
     # (1) seeded sample against the oracle
     rng = np.random.default_rng(1)
-    idx = np.sort(rng.choice(B, size=768 if name != "talos" else 256, replace=False))
+    idx = np.sort(rng.choice(B, size=768 if not name.startswith("talos") else 256, replace=False))
     sub = dict(pb, q=pb["q"][idx], bis=pb["bis"][idx])
     ref = recursion.batch_solve(model, params, sub["q"], sub["H_ref"], sub["v_ref"], sub["ids"], sub["Ais"], sub["bis"], sub["lb"],
                                 sub["ub"], nthreads=8)

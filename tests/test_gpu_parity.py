@@ -64,8 +64,9 @@ def _compare_steps(model, params, pb, n_iters, what):
         for i, o in enumerate(O):
             check_abs_or_rel(H[i], o.His[1:], STEP_TOL, tag + " His")
             check_abs_or_rel(p[i], o.pis[1:], STEP_TOL, tag + " pis")
-            check_abs_or_rel(UD[i], o.UDinv[1:], STEP_TOL, tag + " UDinv")
-            check_abs_or_rel(Di[i], o.Dinv[1:], STEP_TOL, tag + " Dinv")
+            k0 = 1 if model.has_free_flyer else 0  # the root free-flyer's 6x6 UDinv / Dinv are not exposed per joint
+            check_abs_or_rel(UD[i][k0:], o.UDinv[1 + k0:], STEP_TOL, tag + " UDinv")
+            check_abs_or_rel(Di[i][k0:], o.Dinv[1 + k0:], STEP_TOL, tag + " Dinv")
             check_abs_or_rel(r[i], o.r, STEP_TOL, tag + " r")
         # ---- forward: FwdPass2 + BoxProj + DualUpdate (+ primal residuals)
         for o in O:
@@ -130,7 +131,7 @@ def test_component_wise_fixture(name, bound):
     _compare_steps(model, dict(problems.FIXTURE_PARAMS, max_iter=200), pb, 3, name)
 
 
-@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "panda9"])
+@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "panda9", "talos_ff"])
 def test_component_wise_random_batch(name):
     model = robots.get_robot(name)
     pb = problems.random_batch(model, 40, seed=11)
@@ -186,7 +187,7 @@ def test_end_to_end_fixture(name, bound):
     _compare_solves(model, dict(problems.FIXTURE_PARAMS, max_iter=8), pb, name + " fixture")
 
 
-@pytest.mark.parametrize("name,B", [("panda", 4096), ("ur10", 4096), ("talos", 1024), ("panda9", 1024)])
+@pytest.mark.parametrize("name,B", [("panda", 4096), ("ur10", 4096), ("talos", 1024), ("panda9", 1024), ("talos_ff", 1024)])
 def test_end_to_end_random_batch(name, B):
     """Full solves (max_iter = 200) of the BASELINE configs at a size the oracle finishes in seconds."""
     model = robots.get_robot(name)
@@ -480,3 +481,49 @@ def test_fixture_golden_on_gpu(name):
     assert bool(G.get_primal_infeasibility_status()[0]) == bool(g["primal_infeasible"])
     assert rel_inf(G.z[0], g["z"]) < 1e-6 and rel_inf(G.w[0], g["w"]) < 1e-6 and rel_inf(G.vis[0], g["vis"][1:]) < 1e-6
     G.close()
+
+
+def test_free_flyer_root_joint():
+    """SURVEY.md section 8(f) rank 4 (first step): a JointModelFreeFlyer root (nq 7, nv 6; floating-base Talos, nv = 38),
+    per-instance bounds, a task on the root joint itself, sub-batch invariance and the unsupported corners."""
+    model = robots.talos(floating=True)
+    B = 200
+    pb = problems.random_batch(model, B, seed=31)
+    rng = np.random.default_rng(5)
+    ub = model.v_max[None] * rng.uniform(0.2, 1.0, size=(B, model.nv))
+    ids = np.array([1, 22, 30], np.int32)                     # root joint + both wrists
+    pb = dict(pb, ids=ids, Ais=np.tile(np.eye(6), (3, 1, 1)), bis=rng.uniform(-0.3, 0.3, size=(B, 3, 6)), lb=-ub, ub=ub)
+    params = problems.bench_params(3, max_iter=80)
+    G = _gpu(model, params, B)
+    _solve_init(G, pb)
+    G.Solve()
+    z, nu, w, y, it, mu = G.z, G.nu, G.w, G.yis, G.get_iter(), G.get_mu()
+    assert z.shape == (B, 38) and G.q.shape == (B, 39)
+    np.testing.assert_array_equal(G.q, pb["q"])
+    bad = 0
+    for i in range(B):
+        o = _oracle(model, params)
+        o.SolveInit(pb["q"][i], pb["H_ref"], pb["v_ref"], ids, pb["Ais"], pb["bis"][i], -ub[i], ub[i])
+        o.Solve()
+        if o.get_iter() != it[i] or o.get_mu() != mu[i]:
+            bad += 1
+            continue
+        assert rel_inf(z[i], o.z) < 1e-6 and rel_inf(nu[i], o.nu) < 1e-6 and rel_inf(w[i], o.w) < 1e-6
+        assert rel_inf(y[i], o.yis) < 1e-6
+    assert bad <= 1
+    G2 = _gpu(model, params, 37)
+    sub = dict(pb, q=pb["q"][50:87], bis=pb["bis"][50:87], lb=pb["lb"][50:87], ub=pb["ub"][50:87])
+    _solve_init(G2, sub)
+    G2.Solve()
+    np.testing.assert_array_equal(G2.z, z[50:87])
+    with pytest.raises(RuntimeError, match="free-flyer"):
+        G.Integrate(0.01)
+    G.set_debug(True)
+    with pytest.raises(RuntimeError, match="free-flyer"):
+        G.FwdPass1()
+    G.close(); G2.close()
+    from loik_b200 import solver
+    bad_model = robots.talos(floating=True)
+    bad_model.jtype = bad_model.jtype.copy(); bad_model.jtype[5] = robots.FF
+    with pytest.raises(RuntimeError, match="root joint"):
+        solver.make_solver(bad_model, params, 4)
