@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from loik_b200 import problems, robots, solver as lk
 name = sys.argv[1] if len(sys.argv) > 1 else "panda"
 D = int(os.environ.get("DEPTH", 16))
-B = int(os.environ.get("BATCH", {"panda": 65536, "ur10": 262144, "talos": 16384}[name]))
+B = int(os.environ.get("BATCH", {"panda": 65536, "ur10": 262144, "talos": 16384, "talos_ff": 16384}[name]))
 model = robots.get_robot(name)
 pb = problems.random_batch(model, B, seed=0)
 P = problems.bench_params(len(pb["ids"]))

@@ -13,7 +13,7 @@ from loik_b200 import problems, robots, solver as lk  # noqa: E402
 
 def main():
     names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["panda"]
-    batches = {"panda": 65536, "ur10": 262144, "talos": 16384}
+    batches = {"panda": 65536, "ur10": 262144, "talos": 16384, "talos_ff": 16384}
     for name in names:
         model = robots.get_robot(name)
         B = int(os.environ.get("BATCH", batches[name]))
@@ -49,7 +49,7 @@ if __name__ == "__main__":
 def pipelined(name="panda", depths=tuple(int(x) for x in os.environ.get("DEPTHS", "1,2,4,8").split(","))):
     """Throughput with D solver handles in flight on D streams (tail of one batch overlaps the bulk of the next)."""
     model = robots.get_robot(name)
-    B = int(os.environ.get("BATCH", {"panda": 65536, "ur10": 262144, "talos": 16384}[name]))
+    B = int(os.environ.get("BATCH", {"panda": 65536, "ur10": 262144, "talos": 16384, "talos_ff": 16384}[name]))
     pb = problems.random_batch(model, B, seed=0)
     nc = len(pb["ids"])
     for D in depths:
