@@ -128,7 +128,44 @@ LOIK_DEV double* pend_blk(double* T, const Offs& O, int k) { return T + (size_t)
 LOIK_DEV double* glob_blk(double* T, const Offs& O) { return T + (size_t)O.glob * 32; }
 LOIK_DEV double* ff_blk(double* T, const Offs& O) { return T + (size_t)O.ff0 * 32; }
 __host__ __device__ __forceinline__ constexpr int s6(int i, int j) { return i <= j ? i * 6 - (i * (i - 1)) / 2 + (j - i) : j * 6 - (j * (j - 1)) / 2 + (i - j); }
-LOIK_DEV double amax(double m, double x) { return fmax(m, fabs(x)); }
+// Running inf-norms and the box projection are compare + select: sm_100a has no fp64 min/max instruction, and
+// fmax()/fmin() expand to DSETP + FSEL + SEL + a NaN-quieting LOP3 + register-pair shuffles (8-9 instructions each,
+// ~30 % of the dynamic instructions of an iteration with ~54 norm updates per joint).  Same values as fmax/fmin for
+// ordered operands; a NaN second operand is ignored like fmax/fmin do (the comparison is false) and the running
+// norms (first operand) never hold one.
+LOIK_DEV double dmax(double a, double b) { return b > a ? b : a; }
+LOIK_DEV double dmin(double a, double b) { return b < a ? b : a; }
+#ifndef LOIK_AMAX_VARIANT
+#define LOIK_AMAX_VARIANT 3
+#endif
+#if LOIK_AMAX_VARIANT == 1
+LOIK_DEV double amax(double m, double x) { const double a = fabs(x); return a > m ? a : m; }
+#else
+LOIK_DEV double amax(double m, double x) {  // max(m, |x|): |x| is a sign-bit mask on the high word, not an fp64 operation
+  const bool gt = fabs(x) > m;
+  const int hi = gt ? (__double2hiint(x) & 0x7fffffff) : __double2hiint(m);
+  const int lo = gt ? __double2loint(x) : __double2loint(m);
+  return __hiloint2double(hi, lo);
+}
+#endif
+// max(m, |x_0|, ..., |x_5|).  max is exactly associative, so the order of the comparisons does not change the value;
+// variant 3 uses a tree (depth 4 instead of a serial chain of 6 dependent compare-selects).
+LOIK_DEV double absmax2(double a, double b) {
+  const bool gt = fabs(a) > fabs(b);
+  const int hi = (gt ? __double2hiint(a) : __double2hiint(b)) & 0x7fffffff;
+  const int lo = gt ? __double2loint(a) : __double2loint(b);
+  return __hiloint2double(hi, lo);
+}
+LOIK_DEV double amax6(double m, const double (&x)[6]) {
+#if LOIK_AMAX_VARIANT == 3
+  const double a = absmax2(x[0], x[1]), b = absmax2(x[2], x[3]), c = absmax2(x[4], x[5]);
+  return dmax(dmax(m, a), dmax(b, c));
+#else
+#pragma unroll
+  for (int c = 0; c < 6; ++c) m = amax(m, x[c]);
+  return m;
+#endif
+}
 
 // liMi = jointPlacements[i] * M_i(q)   (FwdPassInit, hxx:263-264).  (a, b) = (sin q, cos q) for
 // revolute joints, (q, -) for prismatic ones.
@@ -501,21 +538,22 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const
     const double nu = -acc - Dinv * ri;
     cy.nu_inf = amax(cy.nu_inf, nu);  // (:129-131)
     S_axpy(J, nu, v);                 // v_i = vp + S nu_i (:133-134)
+    {                                 // delta_vis_inf_norm vs the previous iterate (:156-158)
+      double dv[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {     // delta_vis_inf_norm vs the previous iterate (:156-158)
-      cy.dvis_inf = amax(cy.dvis_inf, v[c] - vold[c]);
-      vprev[c] = v[c];
+      for (int c = 0; c < 6; ++c) { dv[c] = v[c] - vold[c]; vprev[c] = v[c]; }
+      cy.dvis_inf = amax6(cy.dvis_inf, dv);
     }
     // this joint's dof: delta_nu (:375), BoxProj (:388-394), w update (:454-458), CheckFeasibility's dot products (:588,590)
     cy.dnu_inf = amax(cy.dnu_inf, nu - nu_old);
-    const double z = fmin(ub, fmax(lb, nu + inv_mu * w_old));
+    const double z = dmin(ub, dmax(lb, nu + inv_mu * w_old));
     cy.dz_inf = amax(cy.dz_inf, z - z_old);
     const double rp = nu - z;
     cy.pres_slack = amax(cy.pres_slack, rp);
     const double dw = mu * rp;
     cy.dw_inf = amax(cy.dw_inf, dw);
-    cy.ubdw_p += ub * fmax(dw, 0.0);
-    cy.lbdw_m += lb * fmin(dw, 0.0);
+    cy.ubdw_p += ub * dmax(dw, 0.0);
+    cy.lbdw_m += lb * dmin(dw, 0.0);
     // ---- load phase B: f_i = H_i v_i + p_i (:139-140), delta_fis (:137-146).  Issued before the stores of
     // phase A so the requests overlap the maths above.
     {
@@ -532,8 +570,12 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const
         f[a] = A[si(a, 0)] * v[0] + A[si(a, 1)] * v[1] + A[si(a, 2)] * v[2] + B[3 * a] * v[3] + B[3 * a + 1] * v[4] + B[3 * a + 2] * v[5] + p[a];
         f[3 + a] = B[a] * v[0] + B[3 + a] * v[1] + B[6 + a] * v[2] + D[si(a, 0)] * v[3] + D[si(a, 1)] * v[4] + D[si(a, 2)] * v[5] + p[3 + a];
       }
+      {
+        double df[6];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) cy.dfis_inf = amax(cy.dfis_inf, f[c] - fold[c]);
+        for (int c = 0; c < 6; ++c) df[c] = f[c] - fold[c];
+        cy.dfis_inf = amax6(cy.dfis_inf, df);
+      }
       // ---- store phase
 #pragma unroll
       for (int c = 0; c < 6; ++c) { st(Pj, JR_V + c, v[c]); st(Pj, JR_F + c, f[c]); }
@@ -558,8 +600,8 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const
         cy.dyis_inf = amax(cy.dyis_inf, dy);
         cy.Av_inf = amax(cy.Av_inf, Av);
         cy.pres_task = amax(cy.pres_task, e);
-        plus += bk[a] * fmax(dy, 0.0);
-        minus += bk[a] * fmin(dy, 0.0);
+        plus += bk[a] * dmax(dy, 0.0);
+        minus += bk[a] * dmin(dy, 0.0);
         if (DEBUG) st(T, O.prv + 6 * ji + a, e);
       }
       cy.bTdy_p += plus;
@@ -632,13 +674,17 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resi
       Hrv[a] = J.HrA[si(a, 0)] * v[0] + J.HrA[si(a, 1)] * v[1] + J.HrA[si(a, 2)] * v[2] + J.HrB[3 * a] * v[3] + J.HrB[3 * a + 1] * v[4] + J.HrB[3 * a + 2] * v[5];
       Hrv[3 + a] = J.HrB[a] * v[0] + J.HrB[3 + a] * v[1] + J.HrB[6 + a] * v[2] + J.HrD[si(a, 0)] * v[3] + J.HrD[si(a, 1)] * v[4] + J.HrD[si(a, 2)] * v[5];
     }
+    {
+      double dF[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      rs.dF_inf = amax(rs.dF_inf, F[c] - Fold[c]);  // (:215-220)
-      rs.F_inf = amax(rs.F_inf, F[c]);              // (:223-225)
-      rs.Hrefv_inf = amax(rs.Hrefv_inf, Hrv[c]);
-      rd[c] = Hrv[c] - J.Hv[c] + F[c];              // (:228)
-      rs.dres_v = amax(rs.dres_v, rd[c]);
+      for (int c = 0; c < 6; ++c) {
+        dF[c] = F[c] - Fold[c];
+        rd[c] = Hrv[c] - J.Hv[c] + F[c];            // (:228)
+      }
+      rs.dF_inf = amax6(rs.dF_inf, dF);             // (:215-220)
+      rs.F_inf = amax6(rs.F_inf, F);                // (:223-225)
+      rs.Hrefv_inf = amax6(rs.Hrefv_inf, Hrv);
+      rs.dres_v = amax6(rs.dres_v, rd);
     }
     // Stf_plus_w (:231-236) and its delta (:471,:482-483)
     const double Tn = St_dot(J, f) + w_i;
@@ -789,14 +835,14 @@ LOIK_DEV void ff_forward(const ModelC& c_model, double* __restrict__ T, const do
     const double ub = c_model.bounds_per_instance ? ldc(Pf, FR_UB + c) : c_model.ffub[c];
     const double nu = v[c], w_old = ld(Pf, FR_W + c);
     cy.dnu_inf = amax(cy.dnu_inf, nu - ld(Pf, FR_NU + c));
-    const double z = fmin(ub, fmax(lb, nu + inv_mu * w_old));
+    const double z = dmin(ub, dmax(lb, nu + inv_mu * w_old));
     cy.dz_inf = amax(cy.dz_inf, z - ld(Pf, FR_Z + c));
     const double rp = nu - z;
     cy.pres_slack = amax(cy.pres_slack, rp);
     const double dw = mu * rp;
     cy.dw_inf = amax(cy.dw_inf, dw);
-    cy.ubdw_p += ub * fmax(dw, 0.0);
-    cy.lbdw_m += lb * fmin(dw, 0.0);
+    cy.ubdw_p += ub * dmax(dw, 0.0);
+    cy.lbdw_m += lb * dmin(dw, 0.0);
     st(Pj, JR_V + c, v[c]); st(Pj, JR_F + c, f[c]);
     st(Pf, FR_NU + c, nu); st(Pf, FR_Z + c, z); st(Pf, FR_W + c, w_old + dw);
     if (DEBUG) st(T, O.prv + 6 * nb + c, rp);
@@ -811,7 +857,7 @@ LOIK_DEV void ff_forward(const ModelC& c_model, double* __restrict__ T, const do
       const double bi = ldc(Pk, TR_B + a), e = Av - bi, dy = mu_eq * e;
       y[a] = ld(Pk, TR_Y + a) + dy;
       cy.dyis_inf = amax(cy.dyis_inf, dy); cy.Av_inf = amax(cy.Av_inf, Av); cy.pres_task = amax(cy.pres_task, e);
-      plus += bi * fmax(dy, 0.0); minus += bi * fmin(dy, 0.0);
+      plus += bi * dmax(dy, 0.0); minus += bi * dmin(dy, 0.0);
       if (DEBUG) st(T, O.prv + a, e);
     }
     cy.bTdy_p += plus; cy.bTdy_m += minus;
@@ -877,19 +923,19 @@ LOIK_DEV int decide(const ModelC& c_model, double* __restrict__ T, const int sta
                     const Resid& rs, double& mu, const bool writer = true) {
   const ModelC& M = c_model;
   double* G = glob_blk(T, M.off);
-  const double pres = fmax(cy.pres_task, cy.pres_slack);  // (:498)
-  const double dres = fmax(rs.dres_v, rs.T_inf);          // (:517); dual_residual_vec[6nb:] = Stf_plus_w (:484)
+  const double pres = dmax(cy.pres_task, cy.pres_slack);  // (:498)
+  const double dres = dmax(rs.dres_v, rs.T_inf);          // (:517); dual_residual_vec[6nb:] = Stf_plus_w (:484)
   if (writer) {
     st(G, GR_RES + 0, pres);
     st(G, GR_RES + 1, dres);
   }
   int ns = status;
   double dyqp = 0.0, ATdy = 0.0, ubp = 0.0, lbm = 0.0, c1 = 0.0, c2 = 0.0;
-  double dx = fmax(cy.dvis_inf, cy.dnu_inf);
+  double dx = dmax(cy.dvis_inf, cy.dnu_inf);
   if (status == ST_RUNNING) {
     const double binf = ld(G, GR_BINF);
-    const double tol_p = M.tol_abs + M.tol_rel * fmax(fmax(cy.Av_inf, cy.nu_inf), fmax(binf, cy.nu_inf));            // (:544-546)
-    const double tol_d = M.tol_abs + M.tol_rel * fmax(fmax(rs.Hrefv_inf, fmax(rs.F_inf, rs.T_inf)), M.Hv_inf);      // (:548-552)
+    const double tol_p = M.tol_abs + M.tol_rel * dmax(dmax(cy.Av_inf, cy.nu_inf), dmax(binf, cy.nu_inf));            // (:544-546)
+    const double tol_d = M.tol_abs + M.tol_rel * dmax(dmax(rs.Hrefv_inf, dmax(rs.F_inf, rs.T_inf)), M.Hv_inf);      // (:548-552)
     if (writer) {
       st(G, GR_RES + 2, tol_p);
       st(G, GR_RES + 3, tol_d);
@@ -897,8 +943,8 @@ LOIK_DEV int decide(const ModelC& c_model, double* __restrict__ T, const int sta
     const bool converged = (pres < tol_p) && (dres < tol_d);                                                        // (:555)
     bool infeasible = false;
     if (it > 1) {                                                                                                   // (hpp:425-427)
-      dyqp = fmax(cy.dfis_inf, fmax(cy.dyis_inf, cy.dw_inf));                                                       // (:576-578)
-      ATdy = fmax(rs.dF_inf, rs.dT_inf);                                                                            // (:580-581)
+      dyqp = dmax(cy.dfis_inf, dmax(cy.dyis_inf, cy.dw_inf));                                                       // (:576-578)
+      ATdy = dmax(rs.dF_inf, rs.dT_inf);                                                                            // (:580-581)
       const bool cond1 = ATdy <= M.tol_pinf * dyqp;                                                                 // (:583-584)
       ubp = cy.bTdy_p + cy.ubdw_p;                                                                                  // (:587-588)
       lbm = cy.bTdy_m + cy.lbdw_m;                                                                                  // (:589-590)
@@ -1027,7 +1073,7 @@ LOIK_DEV void fine_boxproj(const ModelC& M, double* __restrict__ T, const double
     double* Pj = joint_blk(T, O, i - 1);
     const double lb = M.bounds_per_instance ? ld(Pj, JR_LB) : J.lb, ub = M.bounds_per_instance ? ld(Pj, JR_UB) : J.ub;
     const double nu = ld(Pj, JR_NU);
-    const double z = fmin(ub, fmax(lb, nu + (1.0 / mu) * ld(Pj, JR_W)));
+    const double z = dmin(ub, dmax(lb, nu + (1.0 / mu) * ld(Pj, JR_W)));
     dz = amax(dz, z - ld(Pj, JR_Z));
     slack = amax(slack, nu - z);
     st(Pj, JR_Z, z);
@@ -1053,7 +1099,7 @@ LOIK_DEV void fine_dualupdate(const ModelC& M, double* __restrict__ T, const dou
       const double bi = ld(Pk, TR_B + a), e = Av - bi, dy = mu_eq * e;
       y[a] = ld(Pk, TR_Y + a) + dy;
       dyis = amax(dyis, dy); Av_inf = amax(Av_inf, Av); ptask = amax(ptask, e);
-      plus += bi * fmax(dy, 0.0); minus += bi * fmin(dy, 0.0);
+      plus += bi * dmax(dy, 0.0); minus += bi * dmin(dy, 0.0);
       st(T, O.prv + 6 * (K.joint - 1) + a, e);
     }
     bp += plus; bm += minus;
@@ -1070,7 +1116,7 @@ LOIK_DEV void fine_dualupdate(const ModelC& M, double* __restrict__ T, const dou
     const double dw = mu * (ld(Pj, JR_NU) - ld(Pj, JR_Z));
     st(Pj, JR_W, ld(Pj, JR_W) + dw);
     dw_inf = amax(dw_inf, dw);
-    ubdw += ub * fmax(dw, 0.0); lbdw += lb * fmin(dw, 0.0);
+    ubdw += ub * dmax(dw, 0.0); lbdw += lb * dmin(dw, 0.0);
   }
   st(G, GR_NORMS + N_DYIS, dyis); st(G, GR_NORMS + N_AV, Av_inf); st(G, GR_NORMS + N_BTDY_P, bp); st(G, GR_NORMS + N_BTDY_M, bm);
   st(G, GR_NORMS + N_PRES_TASK, ptask); st(G, GR_NORMS + N_DW, dw_inf);
@@ -1079,35 +1125,35 @@ LOIK_DEV void fine_dualupdate(const ModelC& M, double* __restrict__ T, const dou
 // ComputeResiduals (hxx:529-533)
 LOIK_DEV void fine_compute_residuals(const ModelC& M, double* __restrict__ T) {
   double* G = glob_blk(T, M.off);
-  st(G, GR_RES + 0, fmax(ld(G, GR_NORMS + N_PRES_TASK), ld(G, GR_NORMS + N_PRES_SLACK)));
+  st(G, GR_RES + 0, dmax(ld(G, GR_NORMS + N_PRES_TASK), ld(G, GR_NORMS + N_PRES_SLACK)));
   Resid rs;
   zero(rs);
   sweep_residual<true>(M, T, rs, 1, M.nb);
   st(G, GR_NORMS + N_F, rs.F_inf); st(G, GR_NORMS + N_T, rs.T_inf); st(G, GR_NORMS + N_DF, rs.dF_inf); st(G, GR_NORMS + N_DT, rs.dT_inf);
   st(G, GR_NORMS + N_DRES_V, rs.dres_v); st(G, GR_NORMS + N_DRES_NU, rs.T_inf);
-  st(G, GR_RES + 1, fmax(rs.dres_v, rs.T_inf));
+  st(G, GR_RES + 1, dmax(rs.dres_v, rs.T_inf));
 }
 // CheckConvergence (hxx:540-565)
 LOIK_DEV void fine_check_convergence(const ModelC& M, double* __restrict__ T) {
   double* G = glob_blk(T, M.off);
   const double nu_inf = ld(G, GR_NORMS + N_NU);
-  const double tol_p = M.tol_abs + M.tol_rel * fmax(fmax(ld(G, GR_NORMS + N_AV), nu_inf), fmax(ld(G, GR_BINF), nu_inf));
-  const double tol_d = M.tol_abs + M.tol_rel * fmax(fmax(ld(G, GR_NORMS + N_HREFV), fmax(ld(G, GR_NORMS + N_F), ld(G, GR_NORMS + N_T))), M.Hv_inf);
+  const double tol_p = M.tol_abs + M.tol_rel * dmax(dmax(ld(G, GR_NORMS + N_AV), nu_inf), dmax(ld(G, GR_BINF), nu_inf));
+  const double tol_d = M.tol_abs + M.tol_rel * dmax(dmax(ld(G, GR_NORMS + N_HREFV), dmax(ld(G, GR_NORMS + N_F), ld(G, GR_NORMS + N_T))), M.Hv_inf);
   st(G, GR_RES + 2, tol_p); st(G, GR_RES + 3, tol_d);
   if (ld(G, GR_RES + 0) < tol_p && ld(G, GR_RES + 1) < tol_d) st(G, GR_NORMS + N_CONVERGED, 1.0);
 }
 // CheckFeasibility (hxx:572-606)
 LOIK_DEV void fine_check_feasibility(const ModelC& M, double* __restrict__ T) {
   double* G = glob_blk(T, M.off);
-  const double dyqp = fmax(ld(G, GR_NORMS + N_DFIS), fmax(ld(G, GR_NORMS + N_DYIS), ld(G, GR_NORMS + N_DW)));
-  const double ATdy = fmax(ld(G, GR_NORMS + N_DF), ld(G, GR_NORMS + N_DT));
+  const double dyqp = dmax(ld(G, GR_NORMS + N_DFIS), dmax(ld(G, GR_NORMS + N_DYIS), ld(G, GR_NORMS + N_DW)));
+  const double ATdy = dmax(ld(G, GR_NORMS + N_DF), ld(G, GR_NORMS + N_DT));
   const bool c1 = ATdy <= M.tol_pinf * dyqp;
   const double ubp = ld(G, GR_NORMS + N_BTDY_P) + ld(G, GR_CARRY + 10), lbm = ld(G, GR_NORMS + N_BTDY_M) + ld(G, GR_CARRY + 11);
   const bool c2 = (ubp + lbm) <= M.tol_pinf * dyqp;
   st(G, GR_NORMS + N_DYQP, dyqp); st(G, GR_NORMS + N_ATDY, ATdy); st(G, GR_NORMS + N_UBP, ubp); st(G, GR_NORMS + N_LBM, lbm);
   st(G, GR_NORMS + N_C1, c1 ? 1.0 : 0.0); st(G, GR_NORMS + N_C2, c2 ? 1.0 : 0.0);
   if (c1 && c2) st(G, GR_NORMS + N_PINFEASIBLE, 1.0);
-  st(G, GR_NORMS + N_DX, fmax(ld(G, GR_NORMS + N_DVIS), ld(G, GR_NORMS + N_DNU)));
+  st(G, GR_NORMS + N_DX, dmax(ld(G, GR_NORMS + N_DVIS), ld(G, GR_NORMS + N_DNU)));
 }
 // UpdateMu (hxx:613-641)
 LOIK_DEV void fine_update_mu(const ModelC& M, double* __restrict__ T) {

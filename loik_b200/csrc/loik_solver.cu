@@ -151,14 +151,14 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
           const bool is_sum = q >= 8 && q <= 11;  // bTdy_p, bTdy_m, ubdw_p, lbdw_m are sums, the rest are inf-norms
           double acc = part[0][q][lane];
 #pragma unroll
-          for (int ww = 1; ww < NW; ++ww) acc = is_sum ? acc + part[ww][q][lane] : fmax(acc, part[ww][q][lane]);
+          for (int ww = 1; ww < NW; ++ww) acc = is_sum ? acc + part[ww][q][lane] : dmax(acc, part[ww][q][lane]);
           c[q] = acc;
         }
 #pragma unroll
         for (int q = 0; q < 7; ++q) {
           double acc = part[0][kCarryRows + q][lane];
 #pragma unroll
-          for (int ww = 1; ww < NW; ++ww) acc = fmax(acc, part[ww][kCarryRows + q][lane]);
+          for (int ww = 1; ww < NW; ++ww) acc = dmax(acc, part[ww][kCarryRows + q][lane]);
           r[q] = acc;
         }
       }
@@ -802,7 +802,8 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
         for (int g = 0; g < ns; ++g) { cb += bl[g] == lv; cf += fl[g] == lv; }
         width = std::max(width, std::max(cb, cf));
       }
-      const int NW = std::min(4, width);
+      int NW = std::min(4, width);
+      if (const char* e = std::getenv("LOIK_NWARP")) NW = std::max(1, std::min(NW, std::atoi(e)));  // tuning knob: warps per tile
       if (NW >= 2) {
         M.nseg = ns; M.nwarp = NW; M.nblevel = nbl; M.nflevel = nfl;
         // longest-processing-time-first assignment of the segments of every level to the warps

@@ -65,7 +65,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("LOIK_B200_LIB") or LIB_PATH  # LOIK_B200_LIB: A/B builds of the same ABI (development)
     if not os.path.exists(p):
         raise RuntimeError(f"{p} is missing: build it with `python -m loik_b200.build` "
                            f"(libloik_b200 has no CPU fallback)")
