@@ -107,6 +107,17 @@ struct StateP {
   const int* list;    // optional compaction list: thread k works on slot list[k]
   const int* n_list;  // device-resident length of `list`
   int* n_active;      // device counter: instances still active after this launch
+  // Migrating launch (the re-pack fused into the iteration): thread k < *n_list reads the instance in slot list[k]
+  // of `arena` during its first iteration and writes everything to slot k of `dst` (dense prefix, full tiles),
+  // where it then stays for the rest of the launch.  Survivors of the launch claim the slots of the next launch in
+  // next_list / next_count; instances that finish copy their results to their slot of `home` (origin_* = home slot of
+  // a packed slot; origin_src == nullptr: `arena` is the home arena).
+  double* dst;
+  const int* origin_src;
+  int* origin_dst;
+  int* next_list;
+  int* next_count;
+  double* home;
 };
 
 // The batch-uniform block (model, problem constants, hyper-parameters) is passed to every kernel BY VALUE as a
@@ -359,7 +370,7 @@ LOIK_DEV void actinv_motion(const double (&R)[9], const double (&t)[3], const do
 // instruction, so one warp keeps tens of 256 B requests in flight (the compiler cannot hoist a load
 // above a store to a possibly-aliasing row, so interleaving them would serialise on DRAM latency).
 // ---------------------------------------------------------------------------------------------
-LOIK_DEV double ldc(const double* T, int row) { return __ldg(T + row * 32); }  // read-only data
+LOIK_DEV double ldc(const double* T, int row) { return __ldg(T + row * 32); }  // read-only data (never a row this launch writes)
 // Software prefetch of the NEXT joint step's rows into L2, issued at the top of the current step: the sweeps are
 // chains of dependent steps, each starting with a batch of loads, and with 8 resident warps per SM the DRAM
 // latency of that batch is exposed; a prefetch costs no register and turns it into an L2 hit.
@@ -375,33 +386,48 @@ LOIK_DEV void pf_rows(const double* P, int row0) {
 // Leaves for the forward sweep, per joint: H_i and p_i (accumulated over the subtree, un-projected,
 // = His[i]/pis[i] after the reference's BwdPass), UDinv_i, Dinv_i, r_i.
 // ---------------------------------------------------------------------------------------------
-LOIK_DEV void sweep_backward(const ModelC& c_model, double* __restrict__ T, const double mu, const double mu_eq,
-                             const int lo, const int hi) {
+// Every sweep takes two tile pointers: Ts, where the previous iterate and the per-instance problem data are read, and
+// Td, where everything is written (and where what this iteration has already written is read back).  Ts == Td except
+// in the first iteration of a migrating launch, whose backward sweep also carries the problem data rows over
+// (`migrate`), so that the forward and residual sweeps read them from Td.
+LOIK_DEV void sweep_backward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq,
+                             const int lo, const int hi, const bool migrate = false) {
   const Offs& O = c_model.off;
   const double rho = c_model.rho;
   double cA[6], cB[9], cD[6], cp[6];  // contribution carried from child i+1
   bool have_carry = false;
   for (int i = hi; i >= lo; --i) {
     const JointC& J = c_model.j[i];
-    double* Pj = joint_blk(T, O, i - 1);
+    double* Pj = joint_blk(Td, O, i - 1);
+    const double* Ps = joint_blk(const_cast<double*>(Ts), O, i - 1);
     if (i > lo) {
-      const double* Pn = joint_blk(T, O, i - 2);
+      const double* Pn = joint_blk(const_cast<double*>(Ts), O, i - 2);
       pf_rows<6>(Pn, JR_V); pf(Pn, JR_W); pf(Pn, JR_Z); pf_rows<2>(Pn, JR_JQ);
       const int kt = c_model.j[i - 1].task;
-      if (kt >= 0) { const double* Pk = task_blk(T, O, kt); pf_rows<6>(Pk, TR_ATY); pf_rows<6>(Pk, TR_ATB); }
+      if (kt >= 0) { const double* Pk = task_blk(const_cast<double*>(Ts), O, kt); pf_rows<6>(Pk, TR_ATY); pf_rows<6>(Pk, TR_ATB); }
     } else if (i == 1) {
-      pf_rows<6>(Pj, JR_F); pf(Pj, JR_NU);  // first rows of the forward sweep that this sweep has not touched
+      pf_rows<6>(Ps, JR_F); pf(Ps, JR_NU);  // first rows of the forward sweep that this sweep has not touched
     }
     // ---- load phase
     double vold[6], aty[6], atb[6];
-    const double w_i = ld(Pj, JR_W), z_i = ld(Pj, JR_Z);
-    const double qa = ldc(Pj, JR_JQ), qb = ldc(Pj, JR_JQ + 1);
+    const double w_i = ld(Ps, JR_W), z_i = ld(Ps, JR_Z);
+    const double qa = ldc(Ps, JR_JQ), qb = ldc(Ps, JR_JQ + 1);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) vold[c] = ld(Pj, JR_V + c);
+    for (int c = 0; c < 6; ++c) vold[c] = ld(Ps, JR_V + c);
     if (J.task >= 0) {
-      const double* Pk = task_blk(T, O, J.task);
+      const double* Pk = task_blk(const_cast<double*>(Ts), O, J.task);
 #pragma unroll
       for (int c = 0; c < 6; ++c) { aty[c] = ld(Pk, TR_ATY + c); atb[c] = ldc(Pk, TR_ATB + c); }
+    }
+    double cst[3] = {0, 0, 0}, tb[6] = {0, 0, 0, 0, 0, 0};  // migrating: the problem data rows travel with the instance
+    if (migrate) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) cst[c] = ldc(Ps, JR_LB + c);  // lb, ub, q
+      if (J.task >= 0) {
+        const double* Pk = task_blk(const_cast<double*>(Ts), O, J.task);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) tb[c] = ldc(Pk, TR_B + c);
+      }
     }
     // ---- FwdPass1: H_i = rho I + Href_i (:304-306); p_i = -rho v_prev_i - Hv_i (:310-313).  v still holds the
     // previous iterate here, which is the reference's vis_prev (UpdatePrev, data hxx:192-197).
@@ -424,7 +450,7 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, double* __restrict__ T, cons
     }
     // children's contributions: His[parent] += SE3actOn(...), pis[parent] += liMi.act(...) (:66,:74)
     for (int n = 0; n < J.npin; ++n) {
-      const double* Pp = pend_blk(T, O, J.pin[n]);
+      const double* Pp = pend_blk(Td, O, J.pin[n]);
 #pragma unroll
       for (int c = 0; c < 6; ++c) { A[c] += ld(Pp, PR_H + c); D[c] += ld(Pp, PR_H + 15 + c); p[c] += ld(Pp, PR_H + 21 + c); }
 #pragma unroll
@@ -451,6 +477,16 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, double* __restrict__ T, cons
     for (int c = 0; c < 9; ++c) st(Pj, JR_H + 6 + c, B[c]);
     st(Pj, JR_DINV, Dinv);
     st(Pj, JR_R, ri);
+    if (migrate) {
+      st(Pj, JR_JQ, qa); st(Pj, JR_JQ + 1, qb);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) st(Pj, JR_LB + c, cst[c]);
+      if (J.task >= 0) {
+        double* Pk = task_blk(Td, O, J.task);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { st(Pk, TR_B + c, tb[c]); st(Pk, TR_ATB + c, atb[c]); }
+      }
+    }
     have_carry = false;
     if (J.parent > 0) {
       // projection: H -= UDinv U^T (calc_aba update_I, :63), p -= UDinv r_i (:71-73)
@@ -471,7 +507,7 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, double* __restrict__ T, cons
       if (J.carry) {
         have_carry = true;
       } else {
-        double* Pp = pend_blk(T, O, J.pout);
+        double* Pp = pend_blk(Td, O, J.pout);
 #pragma unroll
         for (int c = 0; c < 6; ++c) { st(Pp, PR_H + c, cA[c]); st(Pp, PR_H + 15 + c, cD[c]); st(Pp, PR_H + 21 + c, cp[c]); }
 #pragma unroll
@@ -491,7 +527,7 @@ LOIK_DEV void zero(Carry& cy) {
 }
 // Accumulates into `cy` (the caller zeroes it once per iteration).
 template <bool DEBUG>
-LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const double mu, const double mu_eq, Carry& cy,
+LOIK_DEV void sweep_forward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, Carry& cy,
                             const int lo, const int hi) {
   const Offs& O = c_model.off;
   const int nb = c_model.nb;
@@ -500,22 +536,24 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const
   for (int i = lo; i <= hi; ++i) {
     const JointC& J = c_model.j[i];
     const int ji = i - 1;
-    double* Pj = joint_blk(T, O, ji);
+    double* Pj = joint_blk(Td, O, ji);
+    const double* Ps = joint_blk(const_cast<double*>(Ts), O, ji);
     if (i < hi) {
-      const double* Pn = joint_blk(T, O, ji + 1);
-      pf_rows<6>(Pn, JR_V); pf_rows<6>(Pn, JR_F); pf(Pn, JR_NU); pf(Pn, JR_Z); pf(Pn, JR_W); pf_rows<2>(Pn, JR_JQ);
-      if (nb > 16) pf_rows<35>(Pn, JR_H);  // long trees: the workspace written by the backward sweep has left L2 by now
+      const double* Pn = joint_blk(const_cast<double*>(Ts), O, ji + 1);
+      const double* Pnd = joint_blk(Td, O, ji + 1);
+      pf_rows<6>(Pn, JR_V); pf_rows<6>(Pn, JR_F); pf(Pn, JR_NU); pf(Pn, JR_Z); pf(Pn, JR_W); pf_rows<2>(Pnd, JR_JQ);
+      if (nb > 16) pf_rows<35>(Pnd, JR_H);  // long trees: the workspace written by the backward sweep has left L2 by now
       const int kt = c_model.j[i + 1].task;
-      if (kt >= 0) { const double* Pk = task_blk(T, O, kt); pf_rows<6>(Pk, TR_B); pf_rows<6>(Pk, TR_Y); }
+      if (kt >= 0) { pf_rows<6>(task_blk(Td, O, kt), TR_B); pf_rows<6>(task_blk(const_cast<double*>(Ts), O, kt), TR_Y); }
     }
     // ---- load phase A: what nu_i, v_i and the dof update need
     double vin[6], UD[6], vold[6];
-    const double qa = ldc(Pj, JR_JQ), qb = ldc(Pj, JR_JQ + 1);
+    const double qa = ld(Pj, JR_JQ), qb = ld(Pj, JR_JQ + 1);
     const double Dinv = ld(Pj, JR_DINV), ri = ld(Pj, JR_R);
-    const double w_old = ld(Pj, JR_W), nu_old = ld(Pj, JR_NU), z_old = ld(Pj, JR_Z);
-    const double lb = c_model.bounds_per_instance ? ldc(Pj, JR_LB) : J.lb, ub = c_model.bounds_per_instance ? ldc(Pj, JR_UB) : J.ub;
+    const double w_old = ld(Ps, JR_W), nu_old = ld(Ps, JR_NU), z_old = ld(Ps, JR_Z);
+    const double lb = c_model.bounds_per_instance ? ld(Pj, JR_LB) : J.lb, ub = c_model.bounds_per_instance ? ld(Pj, JR_UB) : J.ub;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { UD[c] = ld(Pj, JR_UD + c); vold[c] = ld(Pj, JR_V + c); }
+    for (int c = 0; c < 6; ++c) { UD[c] = ld(Pj, JR_UD + c); vold[c] = ld(Ps, JR_V + c); }
     if (J.parent == 0) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) vin[c] = 0.0;
@@ -523,7 +561,7 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const
 #pragma unroll
       for (int c = 0; c < 6; ++c) vin[c] = vprev[c];
     } else {
-      const double* Pq = joint_blk(T, O, J.parent - 1);
+      const double* Pq = joint_blk(Td, O, J.parent - 1);  // the parent's new v (this sweep)
 #pragma unroll
       for (int c = 0; c < 6; ++c) vin[c] = ld(Pq, JR_V + c);
     }
@@ -560,7 +598,7 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const
       double fold[6], p[6], A[6], B[9], D[6], f[6];
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
-        fold[c] = ld(Pj, JR_F + c); p[c] = ld(Pj, JR_P + c);
+        fold[c] = ld(Ps, JR_F + c); p[c] = ld(Pj, JR_P + c);
         A[c] = ld(Pj, JR_H + c); D[c] = ld(Pj, JR_H + 15 + c);
       }
 #pragma unroll
@@ -583,13 +621,14 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const
     st(Pj, JR_NU, nu);
     st(Pj, JR_Z, z);
     st(Pj, JR_W, w_old + dw);
-    if (DEBUG) st(T, O.prv + 6 * nb + J.idxv, rp);
+    if (DEBUG) st(Td, O.prv + 6 * nb + J.idxv, rp);
     if (J.task >= 0) {  // DualUpdate for the task on this joint (:410-451)
       const TaskC& K = c_model.t[J.task];
-      double* Pk = task_blk(T, O, J.task);
+      double* Pk = task_blk(Td, O, J.task);
+      const double* Pks = task_blk(const_cast<double*>(Ts), O, J.task);
       double y[6], bk[6], yk[6];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) { bk[c] = ldc(Pk, TR_B + c); yk[c] = ld(Pk, TR_Y + c); }
+      for (int c = 0; c < 6; ++c) { bk[c] = ld(Pk, TR_B + c); yk[c] = ld(Pks, TR_Y + c); }
       double plus = 0.0, minus = 0.0;
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
@@ -602,7 +641,7 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, double* __restrict__ T, const
         cy.pres_task = amax(cy.pres_task, e);
         plus += bk[a] * dmax(dy, 0.0);
         minus += bk[a] * dmin(dy, 0.0);
-        if (DEBUG) st(T, O.prv + 6 * ji + a, e);
+        if (DEBUG) st(Td, O.prv + 6 * ji + a, e);
       }
       cy.bTdy_p += plus;
       cy.bTdy_m += minus;
@@ -628,7 +667,7 @@ struct Resid {
 LOIK_DEV void zero(Resid& rs) { rs.dres_v = rs.dres_nu = rs.Hrefv_inf = rs.F_inf = rs.T_inf = rs.dF_inf = rs.dT_inf = 0.0; }
 // Accumulates into `rs` (the caller zeroes it once per iteration and sets dres_nu = T_inf at the end, hxx:484).
 template <bool DEBUG>
-LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resid& rs, const int lo, const int hi) {
+LOIK_DEV void sweep_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs, const int lo, const int hi) {
   const Offs& O = c_model.off;
   const int nb = c_model.nb;
   double cF[6];
@@ -636,19 +675,20 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resi
   for (int i = hi; i >= lo; --i) {
     const JointC& J = c_model.j[i];
     const int ji = i - 1;
-    double* Pj = joint_blk(T, O, ji);
+    double* Pj = joint_blk(Td, O, ji);
+    const double* Ps = joint_blk(const_cast<double*>(Ts), O, ji);
     if (i > lo) {
-      const double* Pn = joint_blk(T, O, ji - 1);
+      const double* Pn = joint_blk(const_cast<double*>(Ts), O, ji - 1);
       pf_rows<6>(Pn, JR_FD); pf(Pn, JR_T);
     }
     // ---- load phase
     double f[6], F[6], v[6], Fold[6];
-    const double w_i = ld(Pj, JR_W), T_old = ld(Pj, JR_T);
-    const double qa = ldc(Pj, JR_JQ), qb = ldc(Pj, JR_JQ + 1);
+    const double w_i = ld(Pj, JR_W), T_old = ld(Ps, JR_T);
+    const double qa = ld(Pj, JR_JQ), qb = ld(Pj, JR_JQ + 1);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { f[c] = ld(Pj, JR_F + c); v[c] = ld(Pj, JR_V + c); Fold[c] = ld(Pj, JR_FD + c); }
+    for (int c = 0; c < 6; ++c) { f[c] = ld(Pj, JR_F + c); v[c] = ld(Pj, JR_V + c); Fold[c] = ld(Ps, JR_FD + c); }
     if (J.task >= 0) {
-      const double* Pk = task_blk(T, O, J.task);
+      const double* Pk = task_blk(Td, O, J.task);
 #pragma unroll
       for (int c = 0; c < 6; ++c) F[c] = ld(Pk, TR_ATY + c);  // (:438-439)
     } else {
@@ -656,7 +696,7 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resi
       for (int c = 0; c < 6; ++c) F[c] = 0.0;  // (:370)
     }
     for (int n = 0; n < J.npin; ++n) {
-      const double* Pp = pend_blk(T, O, J.pin[n]);
+      const double* Pp = pend_blk(Td, O, J.pin[n]);
 #pragma unroll
       for (int c = 0; c < 6; ++c) F[c] += ld(Pp, PR_F + c);
     }
@@ -694,10 +734,10 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resi
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       st(Pj, JR_FD + c, F[c]);
-      if (DEBUG) st(T, O.drv + 6 * ji + c, rd[c]);
+      if (DEBUG) st(Td, O.drv + 6 * ji + c, rd[c]);
     }
     st(Pj, JR_T, Tn);
-    if (DEBUG) st(T, O.drv + 6 * nb + J.idxv, Tn);
+    if (DEBUG) st(Td, O.drv + 6 * nb + J.idxv, Tn);
     have_carry = false;
     if (J.parent > 0) {  // fis_diff_plus_Aty[parent] += liMi.act(f_i) (:212)
       double R[9], t[3];
@@ -706,7 +746,7 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, double* __restrict__ T, Resi
       if (J.carry) {
         have_carry = true;
       } else {
-        double* Pp = pend_blk(T, O, J.pout);
+        double* Pp = pend_blk(Td, O, J.pout);
 #pragma unroll
         for (int c = 0; c < 6; ++c) st(Pp, PR_F + c, cF[c]);
       }
@@ -750,28 +790,38 @@ LOIK_DEV void spd6_inverse(double (&M)[36], double (&Minv)[21]) {  // M: full sy
     }
 }
 
-LOIK_DEV void ff_backward(const ModelC& c_model, double* __restrict__ T, const double mu, const double mu_eq) {
+LOIK_DEV void ff_backward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, const bool migrate = false) {
   const Offs& O = c_model.off;
   const JointC& J = c_model.j[1];
-  double* Pj = joint_blk(T, O, 0);
-  double* Pf = ff_blk(T, O);
+  double* Pj = joint_blk(Td, O, 0);
+  double* Pf = ff_blk(Td, O);
+  const double* Pjs = joint_blk(const_cast<double*>(Ts), O, 0);
+  const double* Pfs = ff_blk(const_cast<double*>(Ts), O);
   const double rho = c_model.rho;
   double A[6], B[9], D[6], p[6], w[6], z[6];
+  if (migrate) {  // the problem data rows travel with the instance
+    for (int c = FR_LB; c < FR_DINV; ++c) st(Pf, c, ldc(Pfs, c));
+    if (J.task >= 0) {
+      const double* Pks = task_blk(const_cast<double*>(Ts), O, J.task);
+      double* Pk = task_blk(Td, O, J.task);
+      for (int c = 0; c < 12; ++c) st(Pk, TR_B + c, ldc(Pks, TR_B + c));
+    }
+  }
 #pragma unroll
-  for (int c = 0; c < 6; ++c) { p[c] = -rho * ld(Pj, JR_V + c) - J.Hv[c]; A[c] = J.HrA[c]; D[c] = J.HrD[c]; w[c] = ld(Pf, FR_W + c); z[c] = ld(Pf, FR_Z + c); }
+  for (int c = 0; c < 6; ++c) { p[c] = -rho * ld(Pjs, JR_V + c) - J.Hv[c]; A[c] = J.HrA[c]; D[c] = J.HrD[c]; w[c] = ld(Pfs, FR_W + c); z[c] = ld(Pfs, FR_Z + c); }
 #pragma unroll
   for (int c = 0; c < 9; ++c) B[c] = J.HrB[c];
   A[0] += rho; A[3] += rho; A[5] += rho; D[0] += rho; D[3] += rho; D[5] += rho;
   if (J.task >= 0) {
     const TaskC& K = c_model.t[J.task];
-    const double* Pk = task_blk(T, O, J.task);
+    const double* Pk = task_blk(const_cast<double*>(Ts), O, J.task);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { A[c] += mu_eq * K.AtA_A[c]; D[c] += mu_eq * K.AtA_D[c]; p[c] += ld(Pk, TR_ATY + c) - mu_eq * ldc(Pk, TR_ATB + c); }
+    for (int c = 0; c < 6; ++c) { A[c] += mu_eq * K.AtA_A[c]; D[c] += mu_eq * K.AtA_D[c]; p[c] += ld(Pk, TR_ATY + c) - mu_eq * ld(Pk, TR_ATB + c); }
 #pragma unroll
     for (int c = 0; c < 9; ++c) B[c] += mu_eq * K.AtA_B[c];
   }
   for (int n = 0; n < J.npin; ++n) {
-    const double* Pp = pend_blk(T, O, J.pin[n]);
+    const double* Pp = pend_blk(Td, O, J.pin[n]);
 #pragma unroll
     for (int c = 0; c < 6; ++c) { A[c] += ld(Pp, PR_H + c); D[c] += ld(Pp, PR_H + 15 + c); p[c] += ld(Pp, PR_H + 21 + c); }
 #pragma unroll
@@ -797,12 +847,14 @@ LOIK_DEV void ff_backward(const ModelC& c_model, double* __restrict__ T, const d
 }
 
 template <bool DEBUG>
-LOIK_DEV void ff_forward(const ModelC& c_model, double* __restrict__ T, const double mu, const double mu_eq, Carry& cy) {
+LOIK_DEV void ff_forward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, Carry& cy) {
   const Offs& O = c_model.off;
   const JointC& J = c_model.j[1];
   const int nb = c_model.nb;
-  double* Pj = joint_blk(T, O, 0);
-  double* Pf = ff_blk(T, O);
+  double* Pj = joint_blk(Td, O, 0);
+  double* Pf = ff_blk(Td, O);
+  const double* Pjs = joint_blk(const_cast<double*>(Ts), O, 0);
+  const double* Pfs = ff_blk(const_cast<double*>(Ts), O);
   const double inv_mu = 1.0 / mu;
   double Dinv[21], r[6], A[6], B[9], D[6], p[6], vold[6], fold[6], v[6], f[6];
 #pragma unroll
@@ -810,7 +862,7 @@ LOIK_DEV void ff_forward(const ModelC& c_model, double* __restrict__ T, const do
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     r[c] = ld(Pf, FR_R + c); A[c] = ld(Pj, JR_H + c); D[c] = ld(Pj, JR_H + 15 + c); p[c] = ld(Pj, JR_P + c);
-    vold[c] = ld(Pj, JR_V + c); fold[c] = ld(Pj, JR_F + c);
+    vold[c] = ld(Pjs, JR_V + c); fold[c] = ld(Pjs, JR_F + c);
   }
 #pragma unroll
   for (int c = 0; c < 9; ++c) B[c] = ld(Pj, JR_H + 6 + c);
@@ -831,12 +883,12 @@ LOIK_DEV void ff_forward(const ModelC& c_model, double* __restrict__ T, const do
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     cy.dfis_inf = amax(cy.dfis_inf, f[c] - fold[c]);
-    const double lb = c_model.bounds_per_instance ? ldc(Pf, FR_LB + c) : c_model.fflb[c];
-    const double ub = c_model.bounds_per_instance ? ldc(Pf, FR_UB + c) : c_model.ffub[c];
-    const double nu = v[c], w_old = ld(Pf, FR_W + c);
-    cy.dnu_inf = amax(cy.dnu_inf, nu - ld(Pf, FR_NU + c));
+    const double lb = c_model.bounds_per_instance ? ld(Pf, FR_LB + c) : c_model.fflb[c];
+    const double ub = c_model.bounds_per_instance ? ld(Pf, FR_UB + c) : c_model.ffub[c];
+    const double nu = v[c], w_old = ld(Pfs, FR_W + c);
+    cy.dnu_inf = amax(cy.dnu_inf, nu - ld(Pfs, FR_NU + c));
     const double z = dmin(ub, dmax(lb, nu + inv_mu * w_old));
-    cy.dz_inf = amax(cy.dz_inf, z - ld(Pf, FR_Z + c));
+    cy.dz_inf = amax(cy.dz_inf, z - ld(Pfs, FR_Z + c));
     const double rp = nu - z;
     cy.pres_slack = amax(cy.pres_slack, rp);
     const double dw = mu * rp;
@@ -845,20 +897,21 @@ LOIK_DEV void ff_forward(const ModelC& c_model, double* __restrict__ T, const do
     cy.lbdw_m += lb * dmin(dw, 0.0);
     st(Pj, JR_V + c, v[c]); st(Pj, JR_F + c, f[c]);
     st(Pf, FR_NU + c, nu); st(Pf, FR_Z + c, z); st(Pf, FR_W + c, w_old + dw);
-    if (DEBUG) st(T, O.prv + 6 * nb + c, rp);
+    if (DEBUG) st(Td, O.prv + 6 * nb + c, rp);
   }
   if (J.task >= 0) {  // DualUpdate for a task on the root joint (:410-451)
     const TaskC& K = c_model.t[J.task];
-    double* Pk = task_blk(T, O, J.task);
+    double* Pk = task_blk(Td, O, J.task);
+    const double* Pks = task_blk(const_cast<double*>(Ts), O, J.task);
     double y[6], plus = 0.0, minus = 0.0;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
       const double Av = K.A[6 * a] * v[0] + K.A[6 * a + 1] * v[1] + K.A[6 * a + 2] * v[2] + K.A[6 * a + 3] * v[3] + K.A[6 * a + 4] * v[4] + K.A[6 * a + 5] * v[5];
-      const double bi = ldc(Pk, TR_B + a), e = Av - bi, dy = mu_eq * e;
-      y[a] = ld(Pk, TR_Y + a) + dy;
+      const double bi = ld(Pk, TR_B + a), e = Av - bi, dy = mu_eq * e;
+      y[a] = ld(Pks, TR_Y + a) + dy;
       cy.dyis_inf = amax(cy.dyis_inf, dy); cy.Av_inf = amax(cy.Av_inf, Av); cy.pres_task = amax(cy.pres_task, e);
       plus += bi * dmax(dy, 0.0); minus += bi * dmin(dy, 0.0);
-      if (DEBUG) st(T, O.prv + a, e);
+      if (DEBUG) st(Td, O.prv + a, e);
     }
     cy.bTdy_p += plus; cy.bTdy_m += minus;
 #pragma unroll
@@ -870,22 +923,24 @@ LOIK_DEV void ff_forward(const ModelC& c_model, double* __restrict__ T, const do
 }
 
 template <bool DEBUG>
-LOIK_DEV void ff_residual(const ModelC& c_model, double* __restrict__ T, Resid& rs) {
+LOIK_DEV void ff_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs) {
   const Offs& O = c_model.off;
   const JointC& J = c_model.j[1];
   const int nb = c_model.nb;
-  double* Pj = joint_blk(T, O, 0);
-  double* Pf = ff_blk(T, O);
+  double* Pj = joint_blk(Td, O, 0);
+  double* Pf = ff_blk(Td, O);
+  const double* Pjs = joint_blk(const_cast<double*>(Ts), O, 0);
+  const double* Pfs = ff_blk(const_cast<double*>(Ts), O);
   double f[6], v[6], F[6], Fold[6];
 #pragma unroll
-  for (int c = 0; c < 6; ++c) { f[c] = ld(Pj, JR_F + c); v[c] = ld(Pj, JR_V + c); Fold[c] = ld(Pj, JR_FD + c); F[c] = 0.0; }
+  for (int c = 0; c < 6; ++c) { f[c] = ld(Pj, JR_F + c); v[c] = ld(Pj, JR_V + c); Fold[c] = ld(Pjs, JR_FD + c); F[c] = 0.0; }
   if (J.task >= 0) {
-    const double* Pk = task_blk(T, O, J.task);
+    const double* Pk = task_blk(Td, O, J.task);
 #pragma unroll
     for (int c = 0; c < 6; ++c) F[c] = ld(Pk, TR_ATY + c);
   }
   for (int n = 0; n < J.npin; ++n) {
-    const double* Pp = pend_blk(T, O, J.pin[n]);
+    const double* Pp = pend_blk(Td, O, J.pin[n]);
 #pragma unroll
     for (int c = 0; c < 6; ++c) F[c] += ld(Pp, PR_F + c);
   }
@@ -905,10 +960,10 @@ LOIK_DEV void ff_residual(const ModelC& c_model, double* __restrict__ T, Resid& 
     rs.dres_v = amax(rs.dres_v, rd);
     const double Tn = f[c] + ld(Pf, FR_W + c);  // S^T f + w with S = I (:231)
     rs.T_inf = amax(rs.T_inf, Tn);
-    rs.dT_inf = amax(rs.dT_inf, Tn - ld(Pf, FR_T + c));
+    rs.dT_inf = amax(rs.dT_inf, Tn - ld(Pfs, FR_T + c));
     st(Pj, JR_FD + c, F[c]);
     st(Pf, FR_T + c, Tn);
-    if (DEBUG) { st(T, O.drv + c, rd); st(T, O.drv + 6 * nb + c, Tn); }
+    if (DEBUG) { st(Td, O.drv + c, rd); st(Td, O.drv + 6 * nb + c, Tn); }
   }
 }
 
@@ -1128,7 +1183,7 @@ LOIK_DEV void fine_compute_residuals(const ModelC& M, double* __restrict__ T) {
   st(G, GR_RES + 0, dmax(ld(G, GR_NORMS + N_PRES_TASK), ld(G, GR_NORMS + N_PRES_SLACK)));
   Resid rs;
   zero(rs);
-  sweep_residual<true>(M, T, rs, 1, M.nb);
+  sweep_residual<true>(M, T, T, rs, 1, M.nb);
   st(G, GR_NORMS + N_F, rs.F_inf); st(G, GR_NORMS + N_T, rs.T_inf); st(G, GR_NORMS + N_DF, rs.dF_inf); st(G, GR_NORMS + N_DT, rs.dT_inf);
   st(G, GR_NORMS + N_DRES_V, rs.dres_v); st(G, GR_NORMS + N_DRES_NU, rs.T_inf);
   st(G, GR_RES + 1, dmax(rs.dres_v, rs.T_inf));

@@ -26,10 +26,69 @@ constexpr int kBlock = 64;  // threads per CTA of the sweep kernels (2 warps = 2
 LOIK_DEV int2 ld_ctl(const ModelC& c_model, const double* T) { return *reinterpret_cast<const int2*>(T + (size_t)(c_model.off.glob + GR_CTL) * 32); }
 LOIK_DEV void st_ctl(const ModelC& c_model, double* T, int status, int iter) { *reinterpret_cast<int2*>(T + (size_t)(c_model.off.glob + GR_CTL) * 32) = make_int2(status, iter); }
 
+LOIK_DEV double* tile_of(double* arena, const ModelC& c_model, int s) { return arena + ((size_t)(s >> 5) * c_model.off.rows) * 32 + (s & 31); }
+
+// Results of a finished instance go from its packed slot (tile pointer Ts) to its home slot (Th): the state rows
+// only (v, f, F, nu, z, w, T | y, Aty | mu, control, residuals); problem data and workspace stay behind.
+LOIK_DEV void retire_rows(const ModelC& c_model, const double* Ts, double* Th) {
+  const Offs& O = c_model.off;
+  {
+    const double* Gs = glob_blk(const_cast<double*>(Ts), O);
+    double* Gd = glob_blk(Th, O);
+#pragma unroll
+    for (int r = 0; r < GR_CARRY; ++r)
+      if (r != GR_BINF) st(Gd, r, ld(Gs, r));
+  }
+  const int nb = c_model.nb, nc = c_model.nc;
+  for (int j = 0; j < nb; ++j) {
+    const double* Ps = joint_blk(const_cast<double*>(Ts), O, j);
+    double* Pd = joint_blk(Th, O, j);
+    double tmp[JR_JQ];
+#pragma unroll
+    for (int r = 0; r < JR_JQ; ++r) tmp[r] = ld(Ps, r);  // v, f, F, nu, z, w, T (22 rows)
+#pragma unroll
+    for (int r = 0; r < JR_JQ; ++r) st(Pd, r, tmp[r]);
+  }
+  if (c_model.has_ff) {
+    const double* Ps = ff_blk(const_cast<double*>(Ts), O);
+    double* Pd = ff_blk(Th, O);
+    for (int r = 0; r < FR_LB; ++r) st(Pd, r, ld(Ps, r));  // nu, z, w, T
+  }
+  for (int t = 0; t < nc; ++t) {
+    const double* Ps = task_blk(const_cast<double*>(Ts), O, t);
+    double* Pd = task_blk(Th, O, t);
+#pragma unroll
+    for (int r = 0; r < TR_B; ++r) st(Pd, r, ld(Ps, r));  // y, Aty
+  }
+}
+
+// First iteration of a migrating launch: the rows of the globals block that no sweep rewrites travel here.
+LOIK_DEV void migrate_globals(const ModelC& c_model, const double* Ts, double* Td) {
+  const double* Gs = glob_blk(const_cast<double*>(Ts), c_model.off);
+  double* Gd = glob_blk(Td, c_model.off);
+  st(Gd, GR_BINF, ld(Gs, GR_BINF));
+#pragma unroll
+  for (int r = 0; r < 4; ++r) st(Gd, GR_RES + r, ld(Gs, GR_RES + r));
+}
+
+// Survivors of a launch claim the slots of the next one (order inside a warp is preserved, so neighbours stay
+// neighbours and the gather of the next launch's first iteration stays mostly coalesced).
+LOIK_DEV void claim_next(const StateP& S, const bool active, const int slot_now) {
+  const unsigned m = __ballot_sync(0xffffffffu, active);
+  if (!m) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(S.next_count, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (active) S.next_list[base + __popc(m & ((1u << lane) - 1))] = slot_now;
+}
+
 // One launch = up to `iters` ADMM iterations of every active instance (all three sweeps + decisions
 // fused; instances are independent so no grid-wide synchronisation is needed between iterations).
 // Dense mode: thread k = slot k.  List mode: thread k = slot list[k] for k < *n_list (compacted
-// still-active instances; the grid is sized for the worst case and surplus CTAs exit at once).
+// still-active instances; the grid is sized for the worst case and surplus CTAs exit at once), in place, or --
+// migrating launch, S.dst set -- read there during the first iteration and written to slot k of S.dst: the physical
+// re-pack of the still-active instances into full tiles costs no pass of its own.
 template <bool DEBUG, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) k_iterate(const __grid_constant__ ModelC c_model, const StateP S, const int iters, const int fixed) {
   const int limit = S.list ? *S.n_list : (S.n_dev ? *S.n_dev : S.n);
@@ -39,39 +98,49 @@ __global__ void __launch_bounds__(kBlock, MINB) k_iterate(const __grid_constant_
   const int s = k < limit ? (S.list ? S.list[k] : k) : -1;
   bool active = false;
   if (s >= 0) {
-    double* T = tile_ptr(S, c_model, s);
-    const int2 ctl = ld_ctl(c_model, T);
+    const bool MIG = S.dst != nullptr;
+    double* Td = MIG ? tile_of(S.dst, c_model, k) : tile_ptr(S, c_model, s);
+    const double* Ts = MIG ? tile_ptr(S, c_model, s) : Td;
+    const int2 ctl = ld_ctl(c_model, Ts);
     int status = ctl.x;
     if (status < ST_CONVERGED) {
       int it = ctl.y;
-      double mu = ld(glob_blk(T, c_model.off), GR_MU);
+      double mu = ld(glob_blk(const_cast<double*>(Ts), c_model.off), GR_MU);
       const int nb = c_model.nb;
+      bool migrate = MIG;  // the first iteration of a migrating launch reads at Ts and writes at Td
+      if (MIG) { migrate_globals(c_model, Ts, Td); S.origin_dst[k] = S.origin_src ? S.origin_src[s] : s; }
       for (int n = 0; n < iters; ++n) {
         ++it;
         const double mu_eq = c_model.mu_scale * mu;
         const int lo = c_model.has_ff ? 2 : 1;  // a free-flyer root joint is handled outside the joint loops
-        sweep_backward(c_model, T, mu, mu_eq, lo, nb);
-        if (c_model.has_ff) ff_backward(c_model, T, mu, mu_eq);
+        sweep_backward(c_model, Ts, Td, mu, mu_eq, lo, nb, migrate);
+        if (c_model.has_ff) ff_backward(c_model, Ts, Td, mu, mu_eq, migrate);
         Carry cy;
         zero(cy);
-        if (c_model.has_ff) ff_forward<DEBUG>(c_model, T, mu, mu_eq, cy);
-        sweep_forward<DEBUG>(c_model, T, mu, mu_eq, cy, lo, nb);
+        if (c_model.has_ff) ff_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy);
+        sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, lo, nb);
         Resid rs;
         zero(rs);
-        sweep_residual<DEBUG>(c_model, T, rs, lo, nb);
-        if (c_model.has_ff) ff_residual<DEBUG>(c_model, T, rs);
-        status = decide<DEBUG>(c_model, T, status, it, fixed != 0, cy, rs, mu);
+        sweep_residual<DEBUG>(c_model, Ts, Td, rs, lo, nb);
+        if (c_model.has_ff) ff_residual<DEBUG>(c_model, Ts, Td, rs);
+        status = decide<DEBUG>(c_model, Td, status, it, fixed != 0, cy, rs, mu);
+        Ts = Td; migrate = false;
         if (status >= ST_CONVERGED) break;
       }
-      st_ctl(c_model, T, status, it);
-      st(glob_blk(T, c_model.off), GR_MU, mu);
+      st_ctl(c_model, Td, status, it);
+      st(glob_blk(Td, c_model.off), GR_MU, mu);
       active = status < ST_CONVERGED;
+      if (!active && S.home) {  // finished away from home: the results go to the home slot now
+        const int* origin = MIG ? S.origin_dst : S.origin_src;
+        if (origin) retire_rows(c_model, Td, tile_of(S.home, c_model, origin[MIG ? k : s]));
+      }
     }
   }
   if (S.n_active) {
     const unsigned m = __ballot_sync(0xffffffffu, active);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(S.n_active, __popc(m));
   }
+  if (S.next_list) claim_next(S, active, S.dst ? k : s);
   }
 }
 
@@ -86,19 +155,23 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
   __shared__ double part[NW][NP][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int limit = S.list ? *S.n_list : (S.n_dev ? *S.n_dev : S.n);
+  const bool MIG = S.dst != nullptr;
   for (int tile = blockIdx.x; tile * 32 < limit; tile += gridDim.x) {
     const int k = tile * 32 + lane;
     const int s = k < limit ? (S.list ? S.list[k] : k) : -1;
-    double* T = nullptr;
+    double* Td = nullptr;
     int status = ST_CONVERGED, it = 0;
     double mu = 0.0;
+    if (s >= 0) Td = MIG ? tile_of(S.dst, c_model, k) : tile_ptr(S, c_model, s);
+    const double* Ts = (MIG && s >= 0) ? tile_ptr(S, c_model, s) : Td;  // (first iteration of a migrating launch)
     if (s >= 0) {
-      T = tile_ptr(S, c_model, s);
-      const int2 ctl = ld_ctl(c_model, T);
+      const int2 ctl = ld_ctl(c_model, Ts);
       status = ctl.x; it = ctl.y;
-      mu = ld(glob_blk(T, c_model.off), GR_MU);
+      mu = ld(glob_blk(const_cast<double*>(Ts), c_model.off), GR_MU);
     }
     const bool was_active = status < ST_CONVERGED;
+    bool migrate = MIG;
+    if (MIG && was_active && w == 0) { migrate_globals(c_model, Ts, Td); S.origin_dst[k] = S.origin_src ? S.origin_src[s] : s; }
     for (int n = 0; n < iters; ++n) {
       const bool alive = status < ST_CONVERGED;
       if (!__any_sync(0xffffffffu, alive)) break;  // identical in every warp of the CTA (same lanes, same decisions)
@@ -111,8 +184,8 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
         if (alive)
           for (int g = 0; g < c_model.nseg; ++g)
             if (c_model.seg[g].bwarp == w && c_model.seg[g].blevel == lv) {
-              if (c_model.has_ff && c_model.seg[g].lo == 1) ff_backward(c_model, T, mu, mu_eq);
-              else sweep_backward(c_model, T, mu, mu_eq, c_model.seg[g].lo, c_model.seg[g].hi);
+              if (c_model.has_ff && c_model.seg[g].lo == 1) ff_backward(c_model, Ts, Td, mu, mu_eq, migrate);
+              else sweep_backward(c_model, Ts, Td, mu, mu_eq, c_model.seg[g].lo, c_model.seg[g].hi, migrate);
             }
         __syncthreads();
       }
@@ -120,8 +193,8 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
         if (alive)
           for (int g = 0; g < c_model.nseg; ++g)
             if (c_model.seg[g].fwarp == w && c_model.seg[g].flevel == lv) {
-              if (c_model.has_ff && c_model.seg[g].lo == 1) ff_forward<DEBUG>(c_model, T, mu, mu_eq, cy);
-              else sweep_forward<DEBUG>(c_model, T, mu, mu_eq, cy, c_model.seg[g].lo, c_model.seg[g].hi);
+              if (c_model.has_ff && c_model.seg[g].lo == 1) ff_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy);
+              else sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, c_model.seg[g].lo, c_model.seg[g].hi);
             }
         __syncthreads();
       }
@@ -129,8 +202,8 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
         if (alive)
           for (int g = 0; g < c_model.nseg; ++g)
             if (c_model.seg[g].bwarp == w && c_model.seg[g].blevel == lv) {
-              if (c_model.has_ff && c_model.seg[g].lo == 1) ff_residual<DEBUG>(c_model, T, rs);
-              else sweep_residual<DEBUG>(c_model, T, rs, c_model.seg[g].lo, c_model.seg[g].hi);
+              if (c_model.has_ff && c_model.seg[g].lo == 1) ff_residual<DEBUG>(c_model, Ts, Td, rs);
+              else sweep_residual<DEBUG>(c_model, Ts, Td, rs, c_model.seg[g].lo, c_model.seg[g].hi);
             }
         __syncthreads();
       }
@@ -164,21 +237,30 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
       }
       if (alive) {
         ++it;
-        status = decide<DEBUG>(c_model, T, status, it, fixed != 0, cy, rs, mu, w == 0);
+        status = decide<DEBUG>(c_model, Td, status, it, fixed != 0, cy, rs, mu, w == 0);
       }
+      Ts = Td; migrate = false;
       __syncthreads();  // part[] is rewritten in the next iteration
     }
     bool active = false;
     if (was_active) {
-      if (w == 0) {
-        st_ctl(c_model, T, status, it);
-        st(glob_blk(T, c_model.off), GR_MU, mu);
-      }
       active = status < ST_CONVERGED;
+      if (w == 0) {
+        st_ctl(c_model, Td, status, it);
+        st(glob_blk(Td, c_model.off), GR_MU, mu);
+        // (the last iteration's stores of the other warps are ordered before this by the barrier that ends it)
+        if (!active && S.home) {
+          const int* origin = MIG ? S.origin_dst : S.origin_src;
+          if (origin) retire_rows(c_model, Td, tile_of(S.home, c_model, origin[MIG ? k : s]));
+        }
+      }
     }
-    if (S.n_active && w == 0) {
-      const unsigned m = __ballot_sync(0xffffffffu, active);
-      if (lane == 0 && m) atomicAdd(S.n_active, __popc(m));
+    if (w == 0) {
+      if (S.n_active) {
+        const unsigned m = __ballot_sync(0xffffffffu, active);
+        if (lane == 0 && m) atomicAdd(S.n_active, __popc(m));
+      }
+      if (S.next_list) claim_next(S, active, S.dst ? k : s);
     }
     __syncthreads();  // the next tile's first sweeps must not overtake this tile's result stores of warp 0
   }
@@ -209,100 +291,6 @@ __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ ModelC 
   if (active) list_out[block_base + warp_cnt[wid] + __popc(m & ((1u << lane) - 1))] = s;
 }
 
-// Physical re-packing: move the still-active instances listed in `list` (slots of arena X) to the dense prefix
-// 0..count-1 of arena Y, so the following sweeps run on full tiles with coalesced rows again.  Only the rows that
-// survive an iteration travel (state, problem data, control); the backward->forward workspace is rebuilt every sweep.
-// origin_y[k] = the instance's slot in the home arena.
-LOIK_DEV void retire_one(const ModelC& c_model, const StateP& X, const int* __restrict__ origin_x, const StateP& Home, int k, int all);
-
-__global__ void __launch_bounds__(128) k_repack(const __grid_constant__ ModelC c_model, const StateP X, const int* __restrict__ list,
-                                                const int* __restrict__ count, const int* __restrict__ origin_x,
-                                                const StateP Y, int* __restrict__ origin_y, const StateP Home, const int retire) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  // fused k_retire: slot k of X, if it finished inside X, goes home (X is a packed arena, never the home arena)
-  if (retire && k < *X.n_dev) retire_one(c_model, X, origin_x, Home, k, 0);
-  if (k >= *count) return;
-  const int src = list[k];
-  const Offs& O = c_model.off;
-  const double* Ts = tile_ptr(X, c_model, src);
-  double* Td = tile_ptr(Y, c_model, k);
-  origin_y[k] = origin_x ? origin_x[src] : src;
-  {
-    const double* Gs = glob_blk(const_cast<double*>(Ts), O);
-    double* Gd = glob_blk(Td, O);
-#pragma unroll
-    for (int r = 0; r < GR_CARRY; ++r) st(Gd, r, ld(Gs, r));  // mu, binf, ctl, res
-  }
-  const int nb = c_model.nb, nc = c_model.nc;
-  for (int j = 0; j < nb; ++j) {
-    const double* Ps = joint_blk(const_cast<double*>(Ts), O, j);
-    double* Pd = joint_blk(Td, O, j);
-    double tmp[JR_H];
-#pragma unroll
-    for (int r = 0; r < JR_H; ++r) tmp[r] = ld(Ps, r);  // state + problem data (26 rows)
-#pragma unroll
-    for (int r = 0; r < JR_H; ++r) st(Pd, r, tmp[r]);
-  }
-  if (c_model.has_ff) {
-    const double* Ps = ff_blk(const_cast<double*>(Ts), O);
-    double* Pd = ff_blk(Td, O);
-    for (int r = 0; r < FR_DINV; ++r) st(Pd, r, ld(Ps, r));  // state + problem data
-  }
-  for (int t = 0; t < nc; ++t) {
-    const double* Ps = task_blk(const_cast<double*>(Ts), O, t);
-    double* Pd = task_blk(Td, O, t);
-    double tmp[TR_ROWS];
-#pragma unroll
-    for (int r = 0; r < TR_ROWS; ++r) tmp[r] = ld(Ps, r);
-#pragma unroll
-    for (int r = 0; r < TR_ROWS; ++r) st(Pd, r, tmp[r]);
-  }
-}
-
-// Retire: copy the results of the instances that finished inside packed arena X back to their home slots.
-// all != 0: every slot (end of the schedule), else only the finished ones (the active ones moved on).
-__global__ void __launch_bounds__(128) k_retire(const __grid_constant__ ModelC c_model, const StateP X, const int* __restrict__ origin_x,
-                                                const StateP Home, const int all) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= *X.n_dev) return;
-  retire_one(c_model, X, origin_x, Home, k, all);
-}
-
-LOIK_DEV void retire_one(const ModelC& c_model, const StateP& X, const int* __restrict__ origin_x, const StateP& Home, int k, int all) {
-  const Offs& O = c_model.off;
-  const double* Ts = tile_ptr(X, c_model, k);
-  if (!all && ld_ctl(c_model, Ts).x < ST_CONVERGED) return;
-  double* Td = tile_ptr(Home, c_model, origin_x[k]);
-  {
-    const double* Gs = glob_blk(const_cast<double*>(Ts), O);
-    double* Gd = glob_blk(Td, O);
-#pragma unroll
-    for (int r = 0; r < GR_CARRY; ++r)
-      if (r != GR_BINF) st(Gd, r, ld(Gs, r));
-  }
-  const int nb = c_model.nb, nc = c_model.nc;
-  for (int j = 0; j < nb; ++j) {
-    const double* Ps = joint_blk(const_cast<double*>(Ts), O, j);
-    double* Pd = joint_blk(Td, O, j);
-    double tmp[JR_JQ];
-#pragma unroll
-    for (int r = 0; r < JR_JQ; ++r) tmp[r] = ld(Ps, r);  // v, f, F, nu, z, w, T (22 rows)
-#pragma unroll
-    for (int r = 0; r < JR_JQ; ++r) st(Pd, r, tmp[r]);
-  }
-  if (c_model.has_ff) {
-    const double* Ps = ff_blk(const_cast<double*>(Ts), O);
-    double* Pd = ff_blk(Td, O);
-    for (int r = 0; r < FR_LB; ++r) st(Pd, r, ld(Ps, r));  // nu, z, w, T
-  }
-  for (int t = 0; t < nc; ++t) {
-    const double* Ps = task_blk(const_cast<double*>(Ts), O, t);
-    double* Pd = task_blk(Td, O, t);
-#pragma unroll
-    for (int r = 0; r < TR_B; ++r) st(Pd, r, ld(Ps, r));  // y, Aty
-  }
-}
-
 // Step-by-step interface: the same sweeps, one per launch, scalars handed over through the carry rows.
 __global__ void __launch_bounds__(kBlock) k_step_backward(const __grid_constant__ ModelC c_model, const StateP S) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,8 +298,8 @@ __global__ void __launch_bounds__(kBlock) k_step_backward(const __grid_constant_
   double* T = tile_ptr(S, c_model, s);
   if (ld_ctl(c_model, T).x >= ST_CONVERGED) return;
   const double mu = ld(glob_blk(T, c_model.off), GR_MU);
-  sweep_backward(c_model, T, mu, c_model.mu_scale * mu, c_model.has_ff ? 2 : 1, c_model.nb);
-  if (c_model.has_ff) ff_backward(c_model, T, mu, c_model.mu_scale * mu);
+  sweep_backward(c_model, T, T, mu, c_model.mu_scale * mu, c_model.has_ff ? 2 : 1, c_model.nb);
+  if (c_model.has_ff) ff_backward(c_model, T, T, mu, c_model.mu_scale * mu);
 }
 __global__ void __launch_bounds__(kBlock) k_step_forward(const __grid_constant__ ModelC c_model, const StateP S) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -322,8 +310,8 @@ __global__ void __launch_bounds__(kBlock) k_step_forward(const __grid_constant__
   const double mu = ld(G, GR_MU);
   Carry cy;
   zero(cy);
-  if (c_model.has_ff) ff_forward<true>(c_model, T, mu, c_model.mu_scale * mu, cy);
-  sweep_forward<true>(c_model, T, mu, c_model.mu_scale * mu, cy, c_model.has_ff ? 2 : 1, c_model.nb);
+  if (c_model.has_ff) ff_forward<true>(c_model, T, T, mu, c_model.mu_scale * mu, cy);
+  sweep_forward<true>(c_model, T, T, mu, c_model.mu_scale * mu, cy, c_model.has_ff ? 2 : 1, c_model.nb);
   const double* c = reinterpret_cast<const double*>(&cy);
   for (int k = 0; k < kCarryRows; ++k) st(G, GR_CARRY + k, c[k]);
   // ComputePrimalResiduals (hxx:494-503)
@@ -344,8 +332,8 @@ __global__ void __launch_bounds__(kBlock) k_step_residual(const __grid_constant_
   for (int k = 0; k < kCarryRows; ++k) c[k] = ld(G, GR_CARRY + k);
   Resid rs;
   zero(rs);
-  sweep_residual<true>(c_model, T, rs, c_model.has_ff ? 2 : 1, c_model.nb);
-  if (c_model.has_ff) ff_residual<true>(c_model, T, rs);
+  sweep_residual<true>(c_model, T, T, rs, c_model.has_ff ? 2 : 1, c_model.nb);
+  if (c_model.has_ff) ff_residual<true>(c_model, T, T, rs);
   double mu = ld(G, GR_MU);
   const int it = ctl.y + 1;
   status = decide<true>(c_model, T, status, it, fixed != 0, cy, rs, mu);
@@ -362,7 +350,7 @@ __global__ void __launch_bounds__(kBlock) k_fine(const __grid_constant__ ModelC 
   switch (which) {
     case LOIK_STEP_RESET_INF_NORMS: fine_reset_inf_norms(c_model, T); break;
     case LOIK_STEP_FWD_PASS1: fine_fwdpass1(c_model, T, mu, mu_eq); break;
-    case LOIK_STEP_BWD_PASS: sweep_backward(c_model, T, mu, mu_eq, 1, c_model.nb); break;
+    case LOIK_STEP_BWD_PASS: sweep_backward(c_model, T, T, mu, mu_eq, 1, c_model.nb); break;
     case LOIK_STEP_FWD_PASS2: fine_fwdpass2(c_model, T); break;
     case LOIK_STEP_BOX_PROJ: fine_boxproj(c_model, T, mu); break;
     case LOIK_STEP_DUAL_UPDATE: fine_dualupdate(c_model, T, mu, mu_eq); break;
@@ -620,6 +608,7 @@ struct loik_solver {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int small_after = 1 << 30, small_grid = 296;  // late rounds: at most small_grid CTAs, grid-stride (env LOIK_SMALL_AFTER / LOIK_SMALL_GRID)
   int hi_after = 8;  // sweeps after which the schedule moves to the high-priority stream (env LOIK_HI_AFTER, <0: never)
+  int seg_after = 32;  // sweeps after which a branching tree is swept by the segment-parallel kernel (env LOIK_SEG_AFTER)
   int sweeps_in_solve = 0;
 };
 
@@ -631,10 +620,13 @@ static inline int grid_for(int n, int block = kBlock) { return (n + block - 1) /
 
 // One place that launches the fused iteration kernel.  `minb` = resident CTAs (of 64 threads) per SM the
 // kernel is compiled for: 4 -> <=255 regs/thread, 6 -> <=168, 8 -> <=128 (tuning knob, env LOIK_MINB).
-static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S, int iters, int fixed, int max_ctas = 0) {
+// `seg`: use the segment-parallel kernel (several warps per tile) when the tree branches.  It shortens the critical
+// path of a sweep (latency) but spends 2-3.5x the warp-slot time of the one-warp-per-tile kernel per iteration, so
+// the schedule switches to it only for the late rounds, when few tiles are left and latency is all that matters.
+static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S, int iters, int fixed, int max_ctas = 0, bool seg = true) {
   int g = grid_for(h->batch);
   if (max_ctas > 0) g = std::min(g, max_ctas);
-  if (h->mc.nwarp > 1 && !h->debug) {  // segment-parallel: one CTA (nwarp warps) per tile
+  if (seg && h->mc.nwarp > 1 && !h->debug) {  // segment-parallel: one CTA (nwarp warps) per tile
     int gt = h->ntiles;
     if (max_ctas > 0) gt = std::min(gt, max_ctas);
     switch (h->mc.nwarp) {
@@ -737,6 +729,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   if (const char* e = std::getenv("LOIK_SMALL_AFTER")) h->small_after = std::atoi(e);
   if (const char* e = std::getenv("LOIK_SMALL_GRID")) h->small_grid = std::atoi(e);
   if (const char* e = std::getenv("LOIK_HI_AFTER")) h->hi_after = std::atoi(e);
+  if (const char* e = std::getenv("LOIK_SEG_AFTER")) h->seg_after = std::atoi(e);
   if (const char* e = std::getenv("LOIK_REPS")) { const int v = std::atoi(e); if (v >= 1) h->sched_reps = v; }
   if (const char* e = std::getenv("LOIK_GROWTH")) { const double v = std::atof(e); if (v >= 1.0) h->sched_growth = v; }
   if (const char* e = std::getenv("LOIK_MINB")) { const int v = std::atoi(e); if (v == 4 || v == 6 || v == 8) h->minb = v; }
@@ -1061,11 +1054,13 @@ static int compact(loik_solver* h, cudaStream_t st) {
 // The main loop of Solve() (hpp:377-454) over the whole batch, enqueued as a fixed schedule of launches with NO
 // host round trip.  Per-instance loop control lives on the device (finished instances are frozen), so the
 // schedule only has to cover `budget` = max_iter sweeps.
-//   1. a few dense sweeps on the home arena while (almost) every instance is active;
-//   2. then, repeatedly: compact the still-active slots, physically re-pack them into the dense prefix of a
-//      scratch arena (full tiles, coalesced rows), retire the finished ones to their home slots, and sweep the
-//      packed arena for a geometrically growing number of iterations;
-//   3. retire whatever is left.  Launches past global convergence find a zero count and exit at once.
+//   1. a few dense sweeps on the home arena while (almost) every instance is active; the survivors claim the
+//      slots of the next launch (claim_next);
+//   2. then a sequence of MIGRATING launches of 1,1,2,2,4,4,... iterations: each reads its instances where the
+//      previous launch left them and writes them, from its first iteration on, to the dense prefix of the other
+//      scratch arena (full tiles, coalesced rows) -- the physical re-pack costs no pass of its own; an instance that
+//      finishes copies its results to its home slot on the spot (retire_rows), survivors claim the next slots.
+//   Launches past global convergence find a zero count and exit at once.
 static int ensure_scratch(loik_solver* h) {
   if (h->scratch[0]) return LOIK_OK;
   const size_t bytes = (size_t)h->ntiles * h->mc.off.rows * 32 * sizeof(double);
@@ -1081,13 +1076,19 @@ static int run_schedule(loik_solver* h, cudaStream_t st0, int budget) {
   bool forked = false;
   const int B = h->batch;
   int done = 0;
+  int li = 0;  // list / count that the NEXT launch reads
   const int dense = std::min(budget, h->dense_sweeps);
+  StateP X = h->S;  // where the instances of the next launch live: the home arena first
+  X.list = nullptr; X.n_list = nullptr;
   if (dense > 0) {
-    launch_iterate(h, st, h->S, dense, 0);
+    CK(cudaMemsetAsync(h->d_counts + li, 0, sizeof(int), st));
+    StateP P = h->S;
+    P.next_list = h->d_lists + (size_t)li * B; P.next_count = h->d_counts + li;
+    launch_iterate(h, st, P, dense, 0, 0, h->seg_after <= 0);
     h->sweeps += dense; done += dense;
+    X.list = P.next_list; X.n_list = P.next_count;
   }
   int cur = -1;  // -1 = home arena, else scratch index
-  StateP X = h->S;
   int chunk = 1, reps = 0;
   while (done < budget) {
     if (!forked && h->hi_after >= 0 && done >= h->hi_after && h->hi_stream) {  // tail rounds: high-priority stream
@@ -1097,21 +1098,25 @@ static int run_schedule(loik_solver* h, cudaStream_t st0, int budget) {
       forked = true;
     }
     const int y = cur < 0 ? 0 : 1 - cur;
-    int* list = h->d_lists;  // one list suffices: it is consumed by the re-pack right away
-    CK(cudaMemsetAsync(h->d_counts + y, 0, sizeof(int), st));
-    k_compact<<<grid_for(B, 256), 256, 0, st>>>(h->mc, X, nullptr, nullptr, list, h->d_counts + y);
-    StateP Y = h->S;
-    Y.arena = h->scratch[y]; Y.n_dev = h->d_counts + y;
-    const int* origin_x = cur < 0 ? nullptr : h->d_origin + (size_t)cur * B;
-    k_repack<<<grid_for(B, 128), 128, 0, st>>>(h->mc, X, list, h->d_counts + y, origin_x, Y, h->d_origin + (size_t)y * B, h->S, cur >= 0 ? 1 : 0);
-    h->launches += 2;
-    cur = y; X = Y;
     const int c = std::min(chunk, budget - done);
-    launch_iterate(h, st, X, c, 0, done >= h->small_after ? h->small_grid : 0);
+    StateP P = X;
+    P.dst = h->scratch[y];
+    P.origin_src = cur < 0 ? nullptr : h->d_origin + (size_t)cur * B;
+    P.origin_dst = h->d_origin + (size_t)y * B;
+    P.home = h->S.arena;
+    P.n_active = nullptr;
+    int* nlist = nullptr; int* ncount = nullptr;
+    if (done + c < budget) {
+      CK(cudaMemsetAsync(h->d_counts + (1 - li), 0, sizeof(int), st));
+      nlist = h->d_lists + (size_t)(1 - li) * B; ncount = h->d_counts + (1 - li);
+    }
+    P.next_list = nlist; P.next_count = ncount;
+    launch_iterate(h, st, P, c, 0, done >= h->small_after ? h->small_grid : 0, done >= h->seg_after);
     h->sweeps += c; done += c;
+    X = h->S; X.arena = h->scratch[y]; X.list = nlist; X.n_list = ncount;
+    cur = y; li = 1 - li;
     if (++reps == h->sched_reps) { reps = 0; if (chunk < 64) chunk = std::max(chunk + 1, (int)(chunk * h->sched_growth)); }
   }
-  if (cur >= 0) { k_retire<<<grid_for(B, 128), 128, 0, st>>>(h->mc, X, h->d_origin + (size_t)cur * B, h->S, 1); h->launches++; }
   CK(cudaMemsetAsync(h->d_counts + 2, 0, sizeof(int), st));  // nothing is active after a complete schedule
   if (forked) {
     CK(cudaEventRecord(h->ev_join, h->hi_stream));
@@ -1269,7 +1274,7 @@ int loik_iterate_fixed(loik_solver* h, int32_t iters, int32_t reset, void* strea
   int rc = upload_consts(h, st);
   if (rc) return rc;
   // one launch per iteration, dense: this is the quantity the roofline is quoted on
-  for (int i = 0; i < iters; ++i) launch_iterate(h, st, h->S, 1, 1);
+  for (int i = 0; i < iters; ++i) launch_iterate(h, st, h->S, 1, 1, 0, h->seg_after <= 0);  // the kernel the bulk of a solve runs
   h->sweeps += iters;
   CK(cudaGetLastError());
   mark_done(h, st);
