@@ -178,12 +178,12 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=16)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="loik_b200", choices=["loik_b200", "reference"])
     ap.add_argument("--workload", default="panda", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config's)")
-    ap.add_argument("--pipeline", type=int, default=16,
+    ap.add_argument("--pipeline", type=int, default=32,
                     help="solver handles (each on its own stream) kept in flight; step i uses handle i %% depth")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
