@@ -89,8 +89,9 @@ LOIK_DEV void claim_next(const StateP& S, const bool active, const int slot_now)
 // still-active instances; the grid is sized for the worst case and surplus CTAs exit at once), in place, or --
 // migrating launch, S.dst set -- read there during the first iteration and written to slot k of S.dst: the physical
 // re-pack of the still-active instances into full tiles costs no pass of its own.
+// MINB = resident CTAs per SM the kernel is compiled for -> register cap 65536 / (64 MINB), rounded down to 8
 template <bool DEBUG, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) k_iterate(const __grid_constant__ ModelC c_model, const StateP S, const int iters, const int fixed) {
+__global__ void __launch_bounds__(kBlock) __maxnreg__(MINB <= 4 ? 255 : (65536 / (kBlock * MINB)) / 8 * 8) k_iterate(const __grid_constant__ ModelC c_model, const StateP S, const int iters, const int fixed) {
   const int limit = S.list ? *S.n_list : (S.n_dev ? *S.n_dev : S.n);
   const int stride = gridDim.x * blockDim.x;
   // grid-stride over the slots: late rounds are launched with a small grid (the count lives on the device)
@@ -640,6 +641,7 @@ static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S, int
 #define LOIK_LAUNCH(DBG, MB) k_iterate<DBG, MB><<<g, kBlock, 0, st>>>(h->mc, S, iters, fixed)
   if (h->debug) { LOIK_LAUNCH(true, 4); }
   else if (h->minb == 4) { LOIK_LAUNCH(false, 4); }
+  else if (h->minb == 5) { LOIK_LAUNCH(false, 5); }
   else if (h->minb == 6) { LOIK_LAUNCH(false, 6); }
   else { LOIK_LAUNCH(false, 8); }
 #undef LOIK_LAUNCH
@@ -732,7 +734,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   if (const char* e = std::getenv("LOIK_SEG_AFTER")) h->seg_after = std::atoi(e);
   if (const char* e = std::getenv("LOIK_REPS")) { const int v = std::atoi(e); if (v >= 1) h->sched_reps = v; }
   if (const char* e = std::getenv("LOIK_GROWTH")) { const double v = std::atof(e); if (v >= 1.0) h->sched_growth = v; }
-  if (const char* e = std::getenv("LOIK_MINB")) { const int v = std::atoi(e); if (v == 4 || v == 6 || v == 8) h->minb = v; }
+  if (const char* e = std::getenv("LOIK_MINB")) { const int v = std::atoi(e); if (v == 4 || v == 5 || v == 6 || v == 8) h->minb = v; }
   ModelC& M = h->mc;
   std::memset(&M, 0, sizeof(M));
   M.nj = nj; M.nb = nj - 1; M.nc = h->nc;
