@@ -42,6 +42,7 @@ inline Model from_pinocchio(const pinocchio::Model& m) {
   out.njoints = m.njoints; out.nv = m.nv;
   out.parents.assign(m.njoints, 0); out.joint_types.assign(m.njoints, 0);
   out.joint_axes.assign(3 * m.njoints, 0.0); out.placement_R.assign(9 * m.njoints, 0.0); out.placement_p.assign(3 * m.njoints, 0.0);
+  int idx_q = 0;  // cumulative, as pinocchio lays q out
   for (int i = 0; i < m.njoints; ++i) {
     out.parents[i] = static_cast<int32_t>(m.parents[i]);
     const auto& M = m.jointPlacements[i];
@@ -66,12 +67,20 @@ inline Model from_pinocchio(const pinocchio::Model& m) {
       ax[0] = a[0]; ax[1] = a[1]; ax[2] = a[2];
     } else if (s == "JointModelFreeFlyer" && i == 1 && m.parents[i] == 0) {
       code = LOIK_JOINT_FF; ax[2] = 1;
+    } else if (s == "JointModelRUBX") { code = LOIK_JOINT_RUBX; ax[0] = 1; }
+    else if (s == "JointModelRUBY") { code = LOIK_JOINT_RUBY; ax[1] = 1; }
+    else if (s == "JointModelRUBZ") { code = LOIK_JOINT_RUBZ; ax[2] = 1; }
+    else if (s == "JointModelRevoluteUnboundedUnaligned") {
+      code = LOIK_JOINT_RUBU;
+      const auto& a = boost::get<pinocchio::JointModelRevoluteUnboundedUnaligned>(m.joints[i].toVariant()).axis;
+      ax[0] = a[0]; ax[1] = a[1]; ax[2] = a[2];
     } else {
       throw std::runtime_error("loik_b200::from_pinocchio: unsupported joint type " + s);
     }
     const bool ff = m.joints[1].shortname() == "JointModelFreeFlyer";
-    if (m.joints[i].idx_v() != (i - 1) + ((ff && i > 1) ? 5 : 0) || m.joints[i].idx_q() != (i - 1) + ((ff && i > 1) ? 6 : 0))
+    if (m.joints[i].idx_v() != (i - 1) + ((ff && i > 1) ? 5 : 0) || m.joints[i].idx_q() != idx_q)
       throw std::runtime_error("loik_b200::from_pinocchio: unexpected idx_q / idx_v layout");
+    idx_q += m.joints[i].nq();
     out.joint_types[i] = code;
     for (int c = 0; c < 3; ++c) out.joint_axes[3 * i + c] = ax[c];
   }

@@ -40,6 +40,7 @@ struct JointC {
   int pout;                         // else (parent > 0): the pending block this joint writes its contribution to
   int npin;                         // number of children that hand their contribution over through a pending block
   int pin[kMaxPin];                 // those blocks (one per tree edge: single writer, no read-modify-write)
+  int qkind, pad;                   // how q parametrises the joint: 0 = one scalar, 1 = (cos, sin) (unbounded revolute)
 };
 
 struct TaskC {

@@ -417,7 +417,8 @@ __global__ void __launch_bounds__(kBlock) k_set_q(const __grid_constant__ ModelC
     const int jt = c_model.j[i].jtype;
     const double qi = sh[threadIdx.x * nq + c_model.j[i].idxq];
     double a, b;
-    if (jt <= 2 || jt == 6) sincos(qi, &a, &b);
+    if (c_model.j[i].qkind == 1) { b = qi; a = sh[threadIdx.x * nq + c_model.j[i].idxq + 1]; }  // q = (cos, sin), used as given (JointModelRevoluteUnbounded*::calc)
+    else if (jt <= 2 || jt == 6) sincos(qi, &a, &b);
     else { a = qi; b = 0.0; }
     double* Pj = joint_blk(T, c_model.off, i - 1);
     st(Pj, JR_JQ, a);
@@ -436,6 +437,20 @@ __global__ void __launch_bounds__(128) k_integrate(const __grid_constant__ Model
   for (int i = 1; i <= nb; ++i) {
     double* Pj = joint_blk(T, c_model.off, i - 1);
     const int jt = c_model.j[i].jtype;
+    if (c_model.j[i].qkind == 1) {
+      // SpecialOrthogonalOperationTpl<2>::integrate_impl: rotate (cos, sin) by omega = dt z, then the first-order
+      // renormalisation out *= (3 - |out|^2) / 2
+      const double ca = ld(Pj, JR_JQ + 1), sa = ld(Pj, JR_JQ);
+      double so, co;
+      sincos(dt * ld(Pj, JR_Z), &so, &co);
+      double c = co * ca - so * sa, s_ = so * ca + co * sa;
+      const double k = (3.0 - (c * c + s_ * s_)) / 2.0;
+      c *= k; s_ *= k;
+      st(Pj, JR_Q, c);
+      st(Pj, JR_JQ, s_);
+      st(Pj, JR_JQ + 1, c);
+      continue;
+    }
     const double qi = ld(Pj, JR_Q) + dt * ld(Pj, JR_Z);
     double a, b;
     if (jt <= 2 || jt == 6) sincos(qi, &a, &b);
@@ -712,7 +727,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   if (batch < 1) return fail(LOIK_ERR_INVALID, "loik_create: batch must be >= 1");
   for (int i = 1; i < nj; ++i) {
     if (model->parents[i] < 0 || model->parents[i] >= i) return fail(LOIK_ERR_INVALID, "loik_create: parents[i] must be < i");
-    if (model->joint_types[i] < 0 || model->joint_types[i] > LOIK_JOINT_FF)
+    if (model->joint_types[i] < 0 || model->joint_types[i] > LOIK_JOINT_RUBU)
       return fail(LOIK_ERR_UNSUPPORTED, "loik_create: unsupported joint type (1-DoF revolute/prismatic joints and a free-flyer root are supported)");
     if (model->joint_types[i] == LOIK_JOINT_FF && !(i == 1 && model->parents[i] == 0))
       return fail(LOIK_ERR_UNSUPPORTED, "loik_create: a free-flyer joint is supported as the root joint (joint 1, parent 0) only");
@@ -724,7 +739,10 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   h->device = device; h->batch = batch; h->ntiles = (batch + 31) / 32;
   h->nj = nj; h->nb = nj - 1; h->nc = params->num_eq_c; h->prm = *params;
   const bool has_ff = model->joint_types[1] == LOIK_JOINT_FF;
-  h->nv = nj - 1 + (has_ff ? 5 : 0); h->nq = nj - 1 + (has_ff ? 6 : 0);
+  auto unbounded = [&](int i) { return model->joint_types[i] >= LOIK_JOINT_RUBX && model->joint_types[i] <= LOIK_JOINT_RUBU; };
+  h->nv = nj - 1 + (has_ff ? 5 : 0);
+  h->nq = 0;
+  for (int i = 1; i < nj; ++i) h->nq += model->joint_types[i] == LOIK_JOINT_FF ? 7 : (unbounded(i) ? 2 : 1);
   h->minb = 4;
   if (const char* e = std::getenv("LOIK_DENSE")) { const int v = std::atoi(e); if (v >= 0) h->dense_sweeps = v; }
   if (const char* e = std::getenv("LOIK_NO_GRAPH")) { if (std::atoi(e) != 0) h->use_graph = false; }
@@ -747,7 +765,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   // Maximal register-carried chains are the segments that different warps can sweep (k_iterate_seg).
   std::vector<int> nchild(nj, 0);
   for (int i = 1; i < nj; ++i) nchild[model->parents[i]]++;
-  int npend = 0;
+  int npend = 0, idxq = 0;
   for (int i = 1; i < nj; ++i) {
     JointC& J = M.j[i];
     J.parent = model->parents[i]; J.jtype = model->joint_types[i]; J.task = -1;
@@ -757,7 +775,10 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
     J.carry = (J.parent > 0 && J.parent == i - 1 && nchild[J.parent] == 1 && model->joint_types[J.parent] != LOIK_JOINT_FF) ? 1 : 0;
     J.pout = -1; J.npin = 0;
     J.idxv = (i - 1) + ((has_ff && i > 1) ? 5 : 0);
-    J.idxq = (i - 1) + ((has_ff && i > 1) ? 6 : 0);
+    J.idxq = idxq; idxq += model->joint_types[i] == LOIK_JOINT_FF ? 7 : (unbounded(i) ? 2 : 1);
+    J.qkind = unbounded(i) ? 1 : 0;
+    // an unbounded revolute joint is its bounded twin everywhere but in how q enters (k_set_q, k_integrate, the q getter)
+    if (unbounded(i)) J.jtype = model->joint_types[i] == LOIK_JOINT_RUBU ? LOIK_JOINT_RU : model->joint_types[i] - LOIK_JOINT_RUBX;
   }
   for (int i = 1; i < nj; ++i) {
     JointC& J = M.j[i];
@@ -880,6 +901,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
         case LOIK_F_Q:
           for (int j = 0; j < nb; ++j) {
             if (has_ff && j == 0) { for (int c = 0; c < 7; ++c) m.push_back(O.ff0 + FR_Q + c); }
+            else if (M.j[j + 1].qkind == 1) { m.push_back(O.joint0 + JR_ROWS * j + JR_JQ + 1); m.push_back(O.joint0 + JR_ROWS * j + JR_JQ); }  // (cos, sin)
             else m.push_back(O.joint0 + JR_ROWS * j + JR_Q);
           }
           break;

@@ -61,5 +61,9 @@ def random_batch(model: RobotModel, batch: int, seed: int = 0, task_joints=None,
     if model.has_free_flyer:  # q[3:7] of the root joint is a unit quaternion (x, y, z, w)
         quat = q[:, 3:7]
         quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    for i in range(1, model.nj):
+        if model.is_unbounded(i):  # (cos, sin) of an unbounded revolute joint
+            cs = q[:, model.idx_q(i):model.idx_q(i) + 2]
+            cs /= np.linalg.norm(cs, axis=1, keepdims=True)
     return dict(q=q, H_ref=np.eye(6), v_ref=np.zeros(6), ids=np.asarray(task_joints, np.int32),
                 Ais=np.tile(np.eye(6), (nc, 1, 1)), bis=b, lb=-model.v_max.copy(), ub=model.v_max.copy())

@@ -15,8 +15,10 @@ Joint type codes (shared with ``include/loik_b200.h`` and ``oracle/loik_oracle.c
     6      revolute, unaligned axis  (JointModelRevoluteUnaligned)
     7      prismatic, unaligned axis (JointModelPrismaticUnaligned)
     8      free-flyer (JointModelFreeFlyer, nq = 7, nv = 6) -- supported as the root joint (joint 1, parent 0) only
+    9,10,11 unbounded revolute about +x,+y,+z (JointModelRUBX/RUBY/RUBZ: URDF ``continuous`` joints; nq = 2, q = (cos, sin))
+    12     unbounded revolute, unaligned axis (JointModelRevoluteUnboundedUnaligned, nq = 2)
 
-1-DoF joints have ``nq = nv = 1``; ``idx_q`` / ``idx_v`` follow pinocchio (cumulative over the joints in id order).
+Other 1-DoF joints have ``nq = nv = 1``; ``idx_q`` / ``idx_v`` follow pinocchio (cumulative over the joints in id order).
 """
 from __future__ import annotations
 
@@ -25,7 +27,7 @@ import math
 
 import numpy as np
 
-RX, RY, RZ, PX, PY, PZ, RU, PU, FF = range(9)
+RX, RY, RZ, PX, PY, PZ, RU, PU, FF, RUBX, RUBY, RUBZ, RUBU = range(13)
 _AXES = {"x": (1.0, 0.0, 0.0), "y": (0.0, 1.0, 0.0), "z": (0.0, 0.0, 1.0)}
 
 
@@ -67,32 +69,74 @@ class RobotModel:
 
     @property
     def nv(self) -> int:
-        return self.nj - 1 + (5 if self.has_free_flyer else 0)
+        return sum(self.nv_joint(i) for i in range(1, self.nj))
 
     @property
     def nq(self) -> int:
-        return self.nj - 1 + (6 if self.has_free_flyer else 0)
+        return sum(self.nq_joint(i) for i in range(1, self.nj))
 
     def nv_joint(self, i: int) -> int:
         return 6 if int(self.jtype[i]) == FF else 1
 
+    def nq_joint(self, i: int) -> int:
+        jt = int(self.jtype[i])
+        return 7 if jt == FF else (2 if RUBX <= jt <= RUBU else 1)
+
     def idx_v(self, i: int) -> int:
-        return (i - 1) + (5 if (self.has_free_flyer and i > 1) else 0)
+        return sum(self.nv_joint(k) for k in range(1, i))
 
     def idx_q(self, i: int) -> int:
-        return (i - 1) + (6 if (self.has_free_flyer and i > 1) else 0)
+        return sum(self.nq_joint(k) for k in range(1, i))
+
+    def is_unbounded(self, i: int) -> bool:
+        return RUBX <= int(self.jtype[i]) <= RUBU
 
     def neutral(self) -> np.ndarray:
         q = np.zeros(self.nq)
         if self.has_free_flyer:
             q[6] = 1.0  # unit quaternion (x, y, z, w)
+        for i in range(1, self.nj):
+            if self.is_unbounded(i):
+                q[self.idx_q(i)] = 1.0  # (cos, sin) = (1, 0)
         return q
+
+    def normalize(self, q: np.ndarray) -> np.ndarray:
+        """pinocchio::normalize: unit quaternion of a free-flyer, unit (cos, sin) of the unbounded revolute joints."""
+        q = np.array(q, np.float64)
+        if self.has_free_flyer:
+            q[..., 3:7] /= np.linalg.norm(q[..., 3:7], axis=-1, keepdims=True)
+        for i in range(1, self.nj):
+            if self.is_unbounded(i):
+                iq = self.idx_q(i)
+                q[..., iq:iq + 2] /= np.linalg.norm(q[..., iq:iq + 2], axis=-1, keepdims=True)
+        return q
+
+    def integrate(self, q: np.ndarray, v: np.ndarray) -> np.ndarray:
+        """pinocchio::integrate(model, q, v) for the joint types the device-side outer loop supports: q + v for the
+        vector-space joints, the SO(2) update of JointModelRevoluteUnbounded* (rotate (cos, sin) by v, then the
+        first-order renormalisation ``out *= (3 - |out|^2) / 2``).  ``q`` is [..., nq], ``v`` is [..., nv]."""
+        q = np.asarray(q, np.float64)
+        v = np.asarray(v, np.float64)
+        out = np.empty_like(q)
+        for i in range(1, self.nj):
+            iq, iv = self.idx_q(i), self.idx_v(i)
+            if int(self.jtype[i]) == FF:
+                raise NotImplementedError("integrate: free-flyer (SE3 exponential) is not supported")
+            if self.is_unbounded(i):
+                ca, sa, om = q[..., iq], q[..., iq + 1], v[..., iv]
+                co, so = np.cos(om), np.sin(om)
+                c, s_ = co * ca - so * sa, so * ca + co * sa
+                k = (3.0 - (c * c + s_ * s_)) / 2.0
+                out[..., iq], out[..., iq + 1] = c * k, s_ * k
+            else:
+                out[..., iq] = q[..., iq] + v[..., iv]
+        return out
 
     def validate(self) -> None:
         assert self.parent[0] == 0
         for i in range(1, self.nj):
             assert 0 <= self.parent[i] < i, "joints must be numbered parent < child"
-            assert 0 <= self.jtype[i] <= FF
+            assert 0 <= self.jtype[i] <= RUBU
             assert self.jtype[i] != FF or (i == 1 and self.parent[i] == 0), "free-flyer only as the root joint"
             assert abs(np.linalg.norm(self.axis[i]) - 1.0) < 1e-12
             R = self.placement_R[i]
@@ -123,17 +167,21 @@ def _build(name, joints) -> RobotModel:
             continue
         if isinstance(ax, str):
             a = np.array(_AXES[ax])
-            code = {"x": 0, "y": 1, "z": 2}[ax] + (0 if jt == "R" else 3)
+            code = {"x": 0, "y": 1, "z": 2}[ax] + {"R": 0, "P": 3, "C": RUBX}[jt]
         else:
             a = np.asarray(ax, np.float64)
             a = a / np.linalg.norm(a)
-            code = RU if jt == "R" else PU
+            code = {"R": RU, "P": PU, "C": RUBU}[jt]
         jtype[i] = code
         axis[i] = a
         R[i] = rpy_to_matrix(*rpy)
         p[i] = xyz
-        qmin.append(lo)
-        qmax.append(hi)
+        if jt == "C":  # URDF `continuous`: q = (cos, sin); the samplers draw both in [-1, 1] and normalise the pair
+            qmin += [-1.0, -1.0]
+            qmax += [1.0, 1.0]
+        else:
+            qmin.append(lo)
+            qmax.append(hi)
         vmax.append(vm)
         names.append(jn)
     m = RobotModel(name, parent, jtype, axis, R, p, np.array(qmin), np.array(qmax), np.array(vmax), names)
@@ -169,8 +217,9 @@ def panda(fingers: bool = False) -> RobotModel:
     return _build("panda9" if fingers else "panda", J)
 
 
-def ur10() -> RobotModel:
-    """UR10, 6-DoF serial chain (BASELINE.json "UR10 6-DoF")."""
+def ur10(continuous: bool = False) -> RobotModel:
+    """UR10, 6-DoF serial chain (BASELINE.json "UR10 6-DoF").  ``continuous=True``: shoulder pan and wrist 3 as URDF
+    ``continuous`` joints (pinocchio JointModelRUBZ / RUBY, nq = 8), the way the e-series wrist 3 is modelled."""
     tp = 2 * math.pi
     J = [
         ("shoulder_pan_joint", 0, "R", "z", (0, 0, 0.1273), (0, 0, 0), -tp, tp, 2.16),
@@ -180,7 +229,10 @@ def ur10() -> RobotModel:
         ("wrist_2_joint", 4, "R", "z", (0, 0.1149, 0), (0, 0, 0), -tp, tp, 3.2),
         ("wrist_3_joint", 5, "R", "y", (0, 0, 0.1157), (0, 0, 0), -tp, tp, 3.2),
     ]
-    return _build("ur10", J)
+    if continuous:
+        J[0] = J[0][:2] + ("C",) + J[0][3:]
+        J[5] = J[5][:2] + ("C",) + J[5][3:]
+    return _build("ur10c" if continuous else "ur10", J)
 
 
 def talos(floating: bool = False) -> RobotModel:
@@ -233,13 +285,16 @@ def talos(floating: bool = False) -> RobotModel:
     return m
 
 
-def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0.3, prismatic: float = 0.25) -> RobotModel:
+def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0.3, prismatic: float = 0.25,
+                continuous: float = 0.0) -> RobotModel:
     """Seeded random kinematic tree covering every joint type (parity stress tests)."""
     rng = np.random.default_rng(seed)
     J = []
     for i in range(1, nb + 1):
         par = i - 1 if (i == 1 or rng.random() > branching) else int(rng.integers(0, i))
         kind = "P" if rng.random() < prismatic else "R"
+        if continuous > 0.0 and kind == "R" and rng.random() < continuous:
+            kind = "C"
         if rng.random() < unaligned:
             ax = rng.normal(size=3)
         else:
@@ -248,13 +303,14 @@ def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0
         rpy = tuple(rng.uniform(-math.pi, math.pi, size=3))
         lo, hi = (-0.3, 0.3) if kind == "P" else (-2.5, 2.5)
         J.append((f"j{i}", par, kind, ax, xyz, rpy, lo, hi, float(rng.uniform(1.0, 4.0))))
-    return _build(f"random{nb}_s{seed}", J)
+    return _build(f"random{nb}_s{seed}" + ("c" if continuous > 0.0 else ""), J)
 
 
-ROBOTS = {"panda": panda, "panda9": lambda: panda(True), "ur10": ur10, "talos": talos, "talos_ff": lambda: talos(True)}
+ROBOTS = {"panda": panda, "panda9": lambda: panda(True), "ur10": ur10, "ur10c": lambda: ur10(True), "talos": talos,
+          "talos_ff": lambda: talos(True)}
 
 # End-effector task joints used by the BASELINE.json configs.
-TASK_JOINTS = {"panda": [7], "panda9": [7], "ur10": [6], "talos": [21, 29], "talos_ff": [22, 30]}
+TASK_JOINTS = {"panda": [7], "panda9": [7], "ur10": [6], "ur10c": [6], "talos": [21, 29], "talos_ff": [22, 30]}
 
 
 def get_robot(name: str) -> RobotModel:

@@ -40,6 +40,8 @@ def dual_action_matrix(R, t):
 def joint_subspace(jtype, axis):
     if jtype == 8:  # free-flyer
         return np.eye(6)
+    if 9 <= jtype <= 12:  # unbounded revolute: the subspace of RX/RY/RZ/RU
+        jtype = jtype - 9 if jtype < 12 else 6
     S = np.zeros((6, 1))
     if jtype <= 2:
         S[3 + jtype, 0] = 1.0
@@ -60,6 +62,11 @@ def joint_transform(jtype, axis, q):
                       [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
                       [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
         return R, np.asarray(q[:3], float).copy()
+    if 9 <= jtype <= 12:  # JointModelRevoluteUnbounded*: q = (cos, sin), used as given
+        c, s_ = float(q[0]), float(q[1])
+        a = np.eye(3)[jtype - 9] if jtype < 12 else np.asarray(axis, float)
+        K = skew(a)
+        return np.eye(3) + s_ * K + (1.0 - c) * (K @ K), np.zeros(3)
     q = float(np.asarray(q).reshape(-1)[0])
     if jtype <= 2:
         a = np.eye(3)[jtype]
@@ -140,7 +147,7 @@ class FirstOrderLoik:
         mdl = self.model
         for i in range(1, self.nj):
             iq = mdl.idx_q(i)
-            MR, Mp = joint_transform(int(mdl.jtype[i]), mdl.axis[i], q[iq:iq + (7 if int(mdl.jtype[i]) == 8 else 1)])
+            MR, Mp = joint_transform(int(mdl.jtype[i]), mdl.axis[i], q[iq:iq + mdl.nq_joint(i)])
             R = mdl.placement_R[i] @ MR
             p = mdl.placement_p[i] + mdl.placement_R[i] @ Mp
             self.liMi[i] = (R, p)

@@ -30,7 +30,7 @@
 
 #define LO_API __attribute__((visibility("default")))
 
-enum { JT_RX = 0, JT_RY, JT_RZ, JT_PX, JT_PY, JT_PZ, JT_RU, JT_PU, JT_FF };
+enum { JT_RX = 0, JT_RY, JT_RZ, JT_PX, JT_PY, JT_PZ, JT_RU, JT_PU, JT_FF, JT_RUBX, JT_RUBY, JT_RUBZ, JT_RUBU };
 
 typedef struct lo_solver {
   /* ---- model (what the hot path reads from pinocchio::Model) ---- */
@@ -184,8 +184,9 @@ static void joint_S(int jt, const double *axis, double *S) { /* S[6*row + col], 
   memset(S, 0, 36 * sizeof(double));
   switch (jt) {
     case JT_RX: case JT_RY: case JT_RZ: S[6 * (3 + jt)] = 1.0; break;
+    case JT_RUBX: case JT_RUBY: case JT_RUBZ: S[6 * (3 + jt - JT_RUBX)] = 1.0; break; /* same subspace as RX/RY/RZ */
     case JT_PX: case JT_PY: case JT_PZ: S[6 * (jt - 3)] = 1.0; break;
-    case JT_RU: S[18] = axis[0]; S[24] = axis[1]; S[30] = axis[2]; break;
+    case JT_RU: case JT_RUBU: S[18] = axis[0]; S[24] = axis[1]; S[30] = axis[2]; break;
     case JT_PU: S[0] = axis[0]; S[6] = axis[1]; S[12] = axis[2]; break;
     default: for (int k = 0; k < 6; ++k) S[7 * k] = 1.0; break; /* free-flyer: identity */
   }
@@ -198,6 +199,21 @@ static void joint_M(int jt, const double *axis, const double *qv, double *MR, do
   const double q = qv[0];
   for (int i = 0; i < 9; ++i) MR[i] = (i % 4 == 0) ? 1.0 : 0.0;
   Mp[0] = Mp[1] = Mp[2] = 0.0;
+  if (jt >= JT_RUBX && jt <= JT_RUBU) { /* JointModelRevoluteUnbounded*::calc: ca = q[0], sa = q[1], no sin/cos call */
+    const double c = qv[0], s = qv[1];
+    if (jt != JT_RUBU) {
+      const int k = jt - JT_RUBX, a = (k + 1) % 3, b = (k + 2) % 3;
+      MR[3 * a + a] = c; MR[3 * a + b] = -s;
+      MR[3 * b + a] = s; MR[3 * b + b] = c;
+    } else {
+      const double *a = axis;
+      const double v = 1.0 - c;
+      MR[0] = c + v * a[0] * a[0];        MR[1] = v * a[0] * a[1] - s * a[2]; MR[2] = v * a[0] * a[2] + s * a[1];
+      MR[3] = v * a[1] * a[0] + s * a[2]; MR[4] = c + v * a[1] * a[1];        MR[5] = v * a[1] * a[2] - s * a[0];
+      MR[6] = v * a[2] * a[0] - s * a[1]; MR[7] = v * a[2] * a[1] + s * a[0]; MR[8] = c + v * a[2] * a[2];
+    }
+    return;
+  }
   if (jt == JT_FF) { /* q = (x, y, z, qx, qy, qz, qw): M = (R(quat), p) */
     const double x = qv[3], y = qv[4], z = qv[5], w = qv[6];
     MR[0] = 1 - 2 * (y * y + z * z); MR[1] = 2 * (x * y - z * w);     MR[2] = 2 * (x * z + y * w);
@@ -306,7 +322,7 @@ LO_API lo_solver *lo_create(int nj, const int *parent, const int *jtype, const d
   for (int i = 1; i < nj; ++i) {
     s->idxv[i] = s->nv; s->idxq[i] = s->nq;
     s->nvj[i] = (jtype[i] == JT_FF) ? 6 : 1;
-    s->nv += s->nvj[i]; s->nq += (jtype[i] == JT_FF) ? 7 : 1;
+    s->nv += s->nvj[i]; s->nq += (jtype[i] == JT_FF) ? 7 : ((jtype[i] >= JT_RUBX && jtype[i] <= JT_RUBU) ? 2 : 1);
   }
   s->axis = dalloc(3 * nj); memcpy(s->axis, axis, 3 * nj * sizeof(double));
   s->plR = dalloc(9 * nj); memcpy(s->plR, plR, 9 * nj * sizeof(double));

@@ -44,7 +44,7 @@ def main():
                  primal_infeasible=B.get_primal_infeasibility_status(), primal_residual=B.get_primal_residual(),
                  dual_residual=B.get_dual_residual())
     # 2. seeded random instances of the BASELINE configs, full solves (max_iter = 200)
-    for name, n in (("panda", 48), ("ur10", 48), ("talos", 16), ("panda9", 16)):
+    for name, n in (("panda", 48), ("ur10", 48), ("talos", 16), ("panda9", 16), ("ur10c", 32)):
         model = robots.get_robot(name)
         pb = problems.random_batch(model, n, seed=1234)
         params = problems.bench_params(len(pb["ids"]))

@@ -131,22 +131,23 @@ def test_component_wise_fixture(name, bound):
     _compare_steps(model, dict(problems.FIXTURE_PARAMS, max_iter=200), pb, 3, name)
 
 
-@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "panda9", "talos_ff"])
+@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "panda9", "talos_ff", "ur10c"])
 def test_component_wise_random_batch(name):
     model = robots.get_robot(name)
     pb = problems.random_batch(model, 40, seed=11)
     _compare_steps(model, problems.bench_params(len(pb["ids"])), pb, 4, name)
 
 
-@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
-def test_component_wise_random_trees(seed):
-    """Every joint type, random branching, non-identity A and H_ref, non-zero v_ref, two tasks."""
-    model = robots.random_tree(10 + 3 * seed, seed)
+@pytest.mark.parametrize("seed,continuous", [(0, 0.0), (1, 0.0), (2, 0.0), (3, 0.0), (4, 0.0), (5, 0.0), (6, 0.5), (7, 0.5), (8, 1.0)])
+def test_component_wise_random_trees(seed, continuous):
+    """Every joint type (incl. unbounded revolute, q = (cos, sin)), random branching, non-identity A and H_ref, non-zero
+    v_ref, two tasks."""
+    model = robots.random_tree(10 + 3 * min(seed, 5), seed, continuous=continuous)
     rng = np.random.default_rng(100 + seed)
     B = 33
     ids = np.array(sorted(rng.choice(np.arange(1, model.nj), size=2, replace=False)), np.int32)
     Hs = rng.normal(size=(6, 6))
-    pb = dict(q=rng.uniform(model.q_min, model.q_max, size=(B, model.nq)), H_ref=np.eye(6) + 0.1 * (Hs + Hs.T),
+    pb = dict(q=model.normalize(rng.uniform(model.q_min, model.q_max, size=(B, model.nq))), H_ref=np.eye(6) + 0.1 * (Hs + Hs.T),
               v_ref=0.1 * rng.normal(size=6), ids=ids,
               Ais=np.stack([np.eye(6) + 0.3 * rng.normal(size=(6, 6)) for _ in range(2)]),
               bis=rng.uniform(-0.5, 0.5, size=(B, 2, 6)), lb=-model.v_max, ub=model.v_max)
@@ -187,7 +188,8 @@ def test_end_to_end_fixture(name, bound):
     _compare_solves(model, dict(problems.FIXTURE_PARAMS, max_iter=8), pb, name + " fixture")
 
 
-@pytest.mark.parametrize("name,B", [("panda", 4096), ("ur10", 4096), ("talos", 1024), ("panda9", 1024), ("talos_ff", 1024)])
+@pytest.mark.parametrize("name,B", [("panda", 4096), ("ur10", 4096), ("talos", 1024), ("panda9", 1024), ("talos_ff", 1024),
+                                    ("ur10c", 2048)])
 def test_end_to_end_random_batch(name, B):
     """Full solves (max_iter = 200) of the BASELINE configs at a size the oracle finishes in seconds."""
     model = robots.get_robot(name)
@@ -408,6 +410,39 @@ def test_outer_ik_loop_on_device():
     G.close()
 
 
+def test_outer_ik_loop_unbounded_revolute():
+    """The same outer loop on a robot with URDF `continuous` joints (JointModelRUBZ / RUBY, q = (cos, sin)): the
+    device-side integration is pinocchio's SO(2) update (rotate, first-order renormalise), checked against
+    RobotModel.integrate, and the q getter returns (cos, sin) pairs."""
+    model = robots.get_robot("ur10c")
+    B = 192
+    pb = problems.random_batch(model, B, seed=31)
+    nxt = problems.random_batch(model, B, seed=32)
+    params = dict(problems.bench_params(1), warm_start=True)
+    c_id, A, dt = int(pb["ids"][0]), pb["Ais"][0], 0.05
+    G = _gpu(model, params, B)
+    G.Solve(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
+    np.testing.assert_array_equal(G.q, pb["q"])
+    z0 = G.z
+    G.Integrate(dt)
+    q1 = model.integrate(pb["q"], dt * z0)
+    np.testing.assert_allclose(G.q, q1, rtol=0, atol=2e-15)
+    b1 = 0.5 * (pb["bis"][:, 0] + nxt["bis"][:, 0])
+    G.Solve(None, c_id, A, b1)
+    z1, it1, mu1 = G.z, G.get_iter(), G.get_mu()
+    bad = 0
+    for i in range(B):
+        o = _oracle(model, params)
+        o.Solve(*instance(pb, i))
+        o.Solve(model.integrate(pb["q"][i], dt * o.z), c_id, A, b1[i])
+        if o.get_iter() != it1[i] or o.get_mu() != mu1[i]:
+            bad += 1
+            continue
+        assert rel_inf(z1[i], o.z) < 1e-6
+    assert bad <= 1
+    G.close()
+
+
 def test_update_references_per_joint():
     """problem_.UpdateReferences(H_refs, v_refs) (ik-id-description-optimized.hpp:103-121): per-joint symmetric weights and
     reference velocities after SolveInit, against the oracle driven the same way."""
@@ -445,7 +480,7 @@ def test_update_references_per_joint():
     G.close()
 
 
-@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "panda9"])
+@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "panda9", "ur10c"])
 def test_against_committed_golden_fixtures(name):
     """CUDA path vs tests/golden/random_*.npz (frozen oracle-pair outputs, scripts/make_golden.py) -- no oracle call."""
     import os

@@ -102,7 +102,7 @@ def step_once_and_compare(A, B, model, it, what):
     assert A.mu == B.get_mu(), what + " mu"
 
 
-ROBOT_CASES = [("talos", 1.0), ("panda", 1.0), ("panda9", 2.0), ("ur10", 1.0), ("talos_ff", 1.0)]
+ROBOT_CASES = [("talos", 1.0), ("panda", 1.0), ("panda9", 2.0), ("ur10", 1.0), ("talos_ff", 1.0), ("ur10c", 1.0)]
 
 
 @pytest.mark.parametrize("name,bound", ROBOT_CASES)
@@ -118,17 +118,19 @@ def test_optimized_correctness_component_wise(name, bound):
         step_once_and_compare(A, B, model, it, f"{name} it{it}")
 
 
-@pytest.mark.parametrize("seed", [0, 1, 2, 3])
-def test_component_wise_random_trees(seed):
-    """Same, on seeded random trees with every joint type (aligned/unaligned, revolute/prismatic, branching)."""
-    model = robots.random_tree(12, seed)
+@pytest.mark.parametrize("seed,continuous", [(0, 0.0), (1, 0.0), (2, 0.0), (3, 0.0), (4, 0.5), (5, 0.5), (6, 1.0)])
+def test_component_wise_random_trees(seed, continuous):
+    """Same, on seeded random trees with every joint type (aligned/unaligned, revolute/prismatic/unbounded revolute,
+    branching)."""
+    model = robots.random_tree(12, seed, continuous=continuous)
     rng = np.random.default_rng(100 + seed)
     params = dict(problems.FIXTURE_PARAMS, max_iter=2, num_eq_c=2)
     ids = np.array(sorted(rng.choice(np.arange(1, model.nj), size=2, replace=False)), np.int32)
     As = np.stack([np.eye(6) + 0.3 * rng.normal(size=(6, 6)) for _ in range(2)])
     Hs = rng.normal(size=(6, 6))
-    pr = dict(q=rng.uniform(model.q_min, model.q_max), H_ref=np.eye(6) + 0.1 * (Hs + Hs.T), v_ref=0.1 * rng.normal(size=6),
-              ids=ids, Ais=As, bis=rng.uniform(-0.5, 0.5, size=(2, 6)), lb=-model.v_max, ub=model.v_max)
+    pr = dict(q=model.normalize(rng.uniform(model.q_min, model.q_max)), H_ref=np.eye(6) + 0.1 * (Hs + Hs.T),
+              v_ref=0.1 * rng.normal(size=6), ids=ids, Ais=As, bis=rng.uniform(-0.5, 0.5, size=(2, 6)), lb=-model.v_max,
+              ub=model.v_max)
     A, B = make_pair(model, params)
     A.SolveInit(*prob_args(pr))
     B.SolveInit(*prob_args(pr))
@@ -136,7 +138,7 @@ def test_component_wise_random_trees(seed):
         step_once_and_compare(A, B, model, it, f"tree{seed} it{it}")
 
 
-@pytest.mark.parametrize("name,bound", [("talos", 2.0), ("panda", 2.0), ("ur10", 2.0), ("talos_ff", 2.0)])
+@pytest.mark.parametrize("name,bound", [("talos", 2.0), ("panda", 2.0), ("ur10", 2.0), ("talos_ff", 2.0), ("ur10c", 2.0)])
 def test_optimized_correctness_end_to_end(name, bound):
     """tests/loik-loid.cpp:559-671 -- max_iter = 8, bounds +-2: SolveInit + Solve() == dense Solve(args)."""
     model = robots.get_robot(name)
@@ -154,7 +156,7 @@ def test_optimized_correctness_end_to_end(name, bound):
     check_abs_or_rel(B.get_primal_residual(), A.primal_residual, TOL, "primal_residual")
 
 
-@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "talos_ff"])
+@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "talos_ff", "ur10c"])
 def test_end_to_end_random_instances(name):
     """Full solves (max_iter = 200) on seeded random instances of the BASELINE configs: same iterates, same
     iteration count, same mu history, same flags."""
@@ -265,3 +267,22 @@ def test_error_paths():
     Bo = recursion.FirstOrderLoikOptimized(model, **dict(kw, mu_update_strat=1, max_iter=5))
     with pytest.raises(RuntimeError):  # OSQP strategy throws (hxx:632-635)
         Bo.Solve(*prob_args(pr))
+
+
+def test_unbounded_revolute_equals_bounded_twin():
+    """JointModelRUB*: q = (cos, sin) used as given -- the solve equals the one of the bounded joint at the same angle
+    (same S, same M up to the rounding of sin/cos), and pinocchio's SO(2) integrate keeps (cos, sin) on the circle."""
+    m, m0 = robots.get_robot("ur10c"), robots.get_robot("ur10")
+    pb = problems.random_batch(m, 16, seed=5)
+    q0 = np.zeros((16, 6))
+    q0[:, 0] = np.arctan2(pb["q"][:, 1], pb["q"][:, 0]); q0[:, 1:5] = pb["q"][:, 2:6]; q0[:, 5] = np.arctan2(pb["q"][:, 7], pb["q"][:, 6])
+    P = problems.bench_params(1)
+    a = recursion.batch_solve(m, P, pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"], nthreads=1)
+    b = recursion.batch_solve(m0, P, q0, pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"], nthreads=1)
+    np.testing.assert_array_equal(a["iters"], b["iters"])
+    assert np.abs(a["z"] - b["z"]).max() < 1e-9
+    q1 = m.integrate(pb["q"], 0.05 * a["z"])
+    th = q0 + 0.05 * b["z"]
+    assert np.abs(q1[:, 0] - np.cos(th[:, 0])).max() < 1e-6 and np.abs(q1[:, 7] - np.sin(th[:, 5])).max() < 1e-6
+    assert np.abs(np.hypot(q1[:, 0], q1[:, 1]) - 1.0).max() < 1e-6
+    np.testing.assert_allclose(q1[:, 2:6], th[:, 1:5], rtol=0, atol=1e-15)
