@@ -1,0 +1,86 @@
+"""The kinematic conventions of the restated Pinocchio primitives (P3-P5 of SURVEY.md section 8(a)) against first
+principles.
+
+Both oracles (and the CUDA kernels) share the *restated* conventions of pinocchio 3.0.0 -- liMi = placement * M(q),
+body-frame spatial velocities ordered [linear; angular], v_i = liMi.actInv(v_parent) + S nu_i -- so agreement between
+them cannot expose a wrong convention.  This test can: the link velocities `vis` a solve returns must equal the body
+velocities obtained by *numerically differentiating an independent forward kinematics* (plain rotation matrices,
+written here, nothing imported from oracle/ or loik_b200/csrc) along the joint velocity `nu` the same solve returns.
+"""
+import numpy as np
+import pytest
+
+from loik_b200 import problems, robots
+from oracle import recursion
+from tests.helpers import ctor_kwargs
+
+
+def _rot(axis, th):
+    a = np.asarray(axis, float)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+
+
+def _fk(model, q):
+    """World placement (R, p) of every joint frame: oMi = oM_parent * jointPlacement_i * M_i(q_i)."""
+    R = [np.eye(3)] * model.nj
+    p = [np.zeros(3)] * model.nj
+    for i in range(1, model.nj):
+        jt, iq = int(model.jtype[i]), model.idx_q(i)
+        ax = np.eye(3)[jt % 3] if jt <= 5 else (np.eye(3)[jt - 9] if 9 <= jt <= 11 else model.axis[i])
+        if jt <= 2 or jt == 6:
+            Rj, pj = _rot(ax, q[iq]), np.zeros(3)
+        elif 9 <= jt <= 12:
+            Rj, pj = _rot(ax, np.arctan2(q[iq + 1], q[iq])), np.zeros(3)
+        else:
+            Rj, pj = np.eye(3), ax * q[iq]
+        par = int(model.parent[i])
+        Rl = model.placement_R[i] @ Rj
+        pl = model.placement_p[i] + model.placement_R[i] @ pj
+        R[i] = R[par] @ Rl
+        p[i] = p[par] + R[par] @ pl
+    return R, p
+
+
+def _body_velocities(model, q, nu, eps=1e-6):
+    """Central differences of the forward kinematics along nu, expressed in each joint's own frame, [linear; angular]."""
+    Rp, pp = _fk(model, model.integrate(q, eps * nu))
+    Rm, pm = _fk(model, model.integrate(q, -eps * nu))
+    R0, _ = _fk(model, q)
+    out = np.zeros((model.nj, 6))
+    for i in range(1, model.nj):
+        W = R0[i].T @ (Rp[i] - Rm[i]) / (2 * eps)          # R^T Rdot = [omega]x in the body frame
+        out[i, :3] = R0[i].T @ (pp[i] - pm[i]) / (2 * eps)
+        out[i, 3:] = [W[2, 1] - W[1, 2], W[0, 2] - W[2, 0], W[1, 0] - W[0, 1]]
+        out[i, 3:] *= 0.5
+    return out
+
+
+def _check(model, pr, what):
+    params = dict(problems.FIXTURE_PARAMS, max_iter=30, num_eq_c=len(pr["ids"]))
+    B = recursion.FirstOrderLoikOptimized(model, **ctor_kwargs(params))
+    B.Solve(pr["q"], pr["H_ref"], pr["v_ref"], pr["ids"], pr["Ais"], pr["bis"], pr["lb"], pr["ub"])
+    assert np.abs(B.nu).max() > 1e-3, what + ": degenerate solve"
+    fd = _body_velocities(model, np.asarray(pr["q"], float), B.nu)
+    err = np.abs(fd[1:] - B.vis[1:]).max()
+    assert err < 1e-6 * max(1.0, np.abs(B.vis).max()), f"{what}: link velocities differ from d/dt FK by {err:.2e}"
+
+
+@pytest.mark.parametrize("name", ["panda", "panda9", "ur10", "ur10c", "talos"])
+def test_link_velocities_are_time_derivatives_of_forward_kinematics(name):
+    model = robots.get_robot(name)
+    pb = problems.random_batch(model, 3, seed=41)
+    for k in range(3):
+        pr = dict(pb, q=pb["q"][k], bis=pb["bis"][k])
+        _check(model, pr, f"{name}[{k}]")
+
+
+@pytest.mark.parametrize("seed,continuous", [(0, 0.0), (1, 0.0), (2, 0.5), (3, 1.0)])
+def test_link_velocities_random_trees(seed, continuous):
+    """Every joint type (aligned / unaligned, revolute / prismatic / unbounded revolute), random placements, branching."""
+    model = robots.random_tree(11, seed, continuous=continuous)
+    rng = np.random.default_rng(500 + seed)
+    ids = np.array(sorted(rng.choice(np.arange(1, model.nj), size=2, replace=False)), np.int32)
+    pr = dict(q=model.normalize(rng.uniform(model.q_min, model.q_max)), H_ref=np.eye(6), v_ref=np.zeros(6), ids=ids,
+              Ais=np.tile(np.eye(6), (2, 1, 1)), bis=rng.uniform(-0.5, 0.5, size=(2, 6)), lb=-model.v_max, ub=model.v_max)
+    _check(model, pr, f"tree{seed}")
