@@ -994,3 +994,99 @@ LO_API long lo_batch_solve(int nj, const int *parent, const int *jtype, const do
   free(jobs); free(th);
   return tot;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* trajectory-tracking driver (the reference's real-time use, hpp:596-695; SURVEY.md 8(f) ranks  */
+/* 2-3): per instance one full Solve, then `steps` times { q <- integrate(q, dt z) (user side:  */
+/* pinocchio::integrate for 1-DoF joints); Solve(q, c_id, A, b_t) } with                          */
+/* b_t = (1 - t/steps) b0 + (t/steps) b1.  Outputs: final z and the iteration count of every step.*/
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  lo_batch_job base;
+  const double *bis1; double dt; int steps, warm, c_id;
+  int *step_iters; /* [batch][steps] */
+  double *q_out;   /* [batch][nq] */
+} lo_track_job;
+
+static void integrate_q(const lo_solver *s, double *q, const double *v, double dt) {
+  for (int i = 1; i < s->nj; ++i) {
+    const int jt = s->jtype[i], iq = s->idxq[i], iv = s->idxv[i];
+    if (jt >= JT_RUBX && jt <= JT_RUBU) { /* SpecialOrthogonalOperationTpl<2>::integrate_impl */
+      const double ca = q[iq], sa = q[iq + 1], om = dt * v[iv];
+      const double co = cos(om), so = sin(om);
+      double c = co * ca - so * sa, sn = so * ca + co * sa;
+      const double k = (3.0 - (c * c + sn * sn)) / 2.0;
+      q[iq] = c * k; q[iq + 1] = sn * k;
+    } else {
+      q[iq] += dt * v[iv];
+    }
+  }
+}
+
+static void *track_worker(void *arg) {
+  lo_track_job *t = (lo_track_job *)arg;
+  lo_batch_job *j = &t->base;
+  const int nc = j->nc;
+  lo_solver *s = lo_create(j->nj, j->parent, j->jtype, j->axis, j->plR, j->plp, j->max_iter, j->tol_abs, j->tol_rel,
+                           j->tol_primal_inf, j->tol_dual_inf, j->rho, j->mu, j->mu_eq_scale, j->strat, nc, 6, t->warm, j->tol_tail);
+  const int nv = s->nv, nq = s->nq;
+  double *q = (double *)malloc(nq * sizeof(double));
+  int slot = 0;
+  for (int k = 0; k < nc; ++k) if (j->ids[k] == t->c_id) slot = k;
+  long tot = 0;
+  for (int b = j->lo; b < j->hi; ++b) {
+    const double *b0 = j->bis + (size_t)b * 6 * nc, *b1 = t->bis1 + (size_t)b * 6 * nc;
+    memcpy(q, j->q + (size_t)b * nq, nq * sizeof(double));
+    s->warm_start = 0; /* a fresh solver object per instance: its first Solve starts from zero state */
+    lo_solve_full(s, q, j->H_ref, j->v_ref, nc, j->ids, j->Ais, b0, j->lb, j->ub);
+    s->warm_start = t->warm;
+    for (int st = 1; st <= t->steps; ++st) {
+      const double a = (double)st / t->steps;
+      double bt[6];
+      for (int c = 0; c < 6; ++c) bt[c] = (1.0 - a) * b0[6 * slot + c] + a * b1[6 * slot + c];
+      integrate_q(s, q, s->z, t->dt);
+      lo_solve_task(s, q, t->c_id, j->Ais + 36 * slot, bt);
+      tot += s->iter;
+      if (t->step_iters) t->step_iters[(size_t)b * t->steps + st - 1] = s->iter;
+    }
+    if (j->z) memcpy(j->z + (size_t)b * nv, s->z, nv * sizeof(double));
+    if (t->q_out) memcpy(t->q_out + (size_t)b * nq, q, nq * sizeof(double));
+  }
+  j->total_iters = tot;
+  free(q);
+  lo_destroy(s);
+  return NULL;
+}
+
+LO_API long lo_batch_track(int nj, const int *parent, const int *jtype, const double *axis, const double *plR, const double *plp,
+                           int max_iter, double tol_abs, double tol_rel, double tol_primal_inf, double tol_dual_inf, double rho,
+                           double mu, double mu_eq_scale, int strat, int nc, double tol_tail, int batch, const double *q,
+                           const double *H_ref, const double *v_ref, const int *ids, const double *Ais, const double *bis0,
+                           const double *bis1, const double *lb, const double *ub, int c_id, double dt, int steps, int warm,
+                           int nthreads, double *z, double *q_out, int *step_iters) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > batch) nthreads = batch > 0 ? batch : 1;
+  lo_track_job *jobs = (lo_track_job *)calloc(nthreads, sizeof(lo_track_job));
+  pthread_t *th = (pthread_t *)calloc(nthreads, sizeof(pthread_t));
+  for (int t = 0; t < nthreads; ++t) {
+    lo_batch_job *j = &jobs[t].base;
+    j->nj = nj; j->parent = parent; j->jtype = jtype; j->axis = axis; j->plR = plR; j->plp = plp;
+    j->max_iter = max_iter; j->tol_abs = tol_abs; j->tol_rel = tol_rel; j->tol_primal_inf = tol_primal_inf;
+    j->tol_dual_inf = tol_dual_inf; j->rho = rho; j->mu = mu; j->mu_eq_scale = mu_eq_scale; j->strat = strat; j->nc = nc;
+    j->tol_tail = tol_tail; j->q = q; j->H_ref = H_ref; j->v_ref = v_ref; j->ids = ids; j->Ais = Ais; j->bis = bis0;
+    j->lb = lb; j->ub = ub;
+    j->lo = (int)((long)batch * t / nthreads); j->hi = (int)((long)batch * (t + 1) / nthreads);
+    j->z = z;
+    jobs[t].bis1 = bis1; jobs[t].dt = dt; jobs[t].steps = steps; jobs[t].warm = warm; jobs[t].c_id = c_id;
+    jobs[t].step_iters = step_iters; jobs[t].q_out = q_out;
+    if (nthreads == 1) track_worker(&jobs[t]);
+    else pthread_create(&th[t], NULL, track_worker, &jobs[t]);
+  }
+  long tot = 0;
+  for (int t = 0; t < nthreads; ++t) {
+    if (nthreads > 1) pthread_join(th[t], NULL);
+    tot += jobs[t].base.total_iters;
+  }
+  free(jobs); free(th);
+  return tot;
+}

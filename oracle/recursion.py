@@ -308,3 +308,32 @@ def batch_solve(model, params: dict, q, H_ref, v_ref, ids, Ais, bis, lb, ub, *, 
                              g("status"), g("mu"))
     out["total_iters"] = int(tot)
     return out
+
+
+def batch_track(model, params: dict, q, H_ref, v_ref, ids, Ais, bis0, bis1, lb, ub, *, c_id, dt, steps, warm=True, nthreads=1,
+                lib=None):
+    """CPU baseline of the trajectory-tracking loop: per instance Solve(...), then `steps` times
+    { q <- integrate(q, dt z); Solve(q, c_id, A, b_t) }, b_t blending bis0 -> bis1 (lo_batch_track).
+    Returns dict(z [B,nv], q [B,nq], step_iters [B,steps], total_iters)."""
+    lib = lib or load()
+    q = _as_d(q)
+    B = q.shape[0]
+    nc = len(ids)
+    bis0, bis1, lb, ub = _as_d(bis0), _as_d(bis1), _as_d(lb), _as_d(ub)
+    ids = _as_i(ids)
+    H_ref, v_ref, Ais = _as_d(H_ref), _as_d(v_ref), _as_d(Ais)
+    k = [_as_i(model.parent), _as_i(model.jtype), _as_d(model.axis), _as_d(model.placement_R), _as_d(model.placement_p)]
+    out = dict(z=np.zeros((B, model.nv)), q=np.zeros((B, model.nq)), step_iters=np.zeros((B, steps), np.int32))
+    p = params
+    lib.lo_batch_track.restype = C.c_long
+    lib.lo_batch_track.argtypes = ([C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_int] + [C.c_double] * 7 + [C.c_int, C.c_int, C.c_double,
+                                   C.c_int, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_int, C.c_int,
+                                   C.c_int, _dp, _dp, _ip])
+    tot = lib.lo_batch_track(model.nj, _p(k[0]), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]), int(p["max_iter"]), p["tol_abs"],
+                             p["tol_rel"], p["tol_primal_inf"], p["tol_dual_inf"], p["rho"], p["mu"],
+                             p["mu_equality_scale_factor"], int(p.get("mu_update_strat", 0)), nc, p["tol_tail_solve"], B,
+                             _p(q), _p(H_ref), _p(v_ref), _p(ids), _p(Ais), _p(bis0), _p(bis1), _p(lb), _p(ub), int(c_id),
+                             float(dt), int(steps), int(bool(warm)), int(nthreads), _p(out["z"]), _p(out["q"]),
+                             _p(out["step_iters"]))
+    out["total_iters"] = int(tot)
+    return out

@@ -443,6 +443,38 @@ def test_outer_ik_loop_unbounded_revolute():
     G.close()
 
 
+@pytest.mark.parametrize("name,warm", [("panda", True), ("panda", False), ("ur10c", True)])
+def test_tracking_loop_vs_oracle(name, warm):
+    """The trajectory-tracking loop (full Solve, then T x { Integrate(dt); Solve(q on device, c_id, A, b_t) }) against
+    the oracle driven the same way (lo_batch_track): iteration count of every instance at the last step, final z, and
+    the integrated configuration."""
+    from oracle import recursion
+    model = robots.get_robot(name)
+    B, T, dt = 512, 6, 0.02
+    pb = problems.random_batch(model, B, seed=51)
+    nx = problems.random_batch(model, B, seed=52)
+    params = dict(problems.bench_params(1), warm_start=warm)
+    c_id, A = int(pb["ids"][0]), pb["Ais"][0]
+    G = _gpu(model, params, B)
+    G.Solve(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
+    for t in range(1, T + 1):
+        a = t / T
+        G.Integrate(dt)
+        G.Solve(None, c_id, A, (1.0 - a) * pb["bis"][:, 0] + a * nx["bis"][:, 0])
+    ref = recursion.batch_track(model, params, pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], nx["bis"], pb["lb"],
+                                pb["ub"], c_id=c_id, dt=dt, steps=T, warm=warm, nthreads=4)
+    same = G.get_iter() == ref["step_iters"][:, -1]
+    # a decision that flips on rounding at an earlier step changes the trajectory of that instance from there on
+    assert same.mean() >= 0.99, f"{(~same).sum()} of {B} instances ended with a different iteration count"
+    z, q = G.z, G.q
+    for i in np.nonzero(same)[0]:
+        if rel_inf(q[i], ref["q"][i]) < 1e-9:
+            assert rel_inf(z[i], ref["z"][i]) < 1e-6
+    close_q = np.array([rel_inf(q[i], ref["q"][i]) < 1e-9 for i in range(B)])
+    assert close_q.mean() >= 0.99
+    G.close()
+
+
 def test_update_references_per_joint():
     """problem_.UpdateReferences(H_refs, v_refs) (ik-id-description-optimized.hpp:103-121): per-joint symmetric weights and
     reference velocities after SolveInit, against the oracle driven the same way."""
