@@ -148,6 +148,49 @@ class FirstOrderLoikOptimized {
   std::vector<bool> get_convergence_status() const { return flag(1); }
   std::vector<bool> get_primal_infeasibility_status() const { return flag(2); }
   std::vector<bool> get_dual_infeasibility_status() const { return std::vector<bool>(batch_, false); }  // never evaluated by the optimized path
+  // the rest of the public surface the reference's tests drive (loik-loid-optimized.hpp:168-264, 698-755;
+  // tests/loik-loid.cpp:340-478): the per-step methods one by one and the feasibility scalars.  They need
+  // set_debug(true) (the production path fuses the steps and keeps no running norms) and work on every instance.
+  void set_debug(bool on) { check(loik_set_debug(h_, on ? 1 : 0)); }
+  void ResetSolver() { check(loik_reset_recursion(h_, stream_)); }  // Solve()'s ResetRecursion + ResetSolver (hpp:370-374)
+  void FwdPassInit(const std::vector<double>& q) { check(loik_fwd_pass_init(h_, q.data(), LOIK_HOST, stream_)); }
+  void UpdatePrev() { step(LOIK_STEP_UPDATE_PREV); }
+  void ResetInfNorms() { step(LOIK_STEP_RESET_INF_NORMS); }
+  void FwdPass1() { step(LOIK_STEP_FWD_PASS1); }
+  void BwdPassOptimizedVisitor() { step(LOIK_STEP_BWD_PASS); }
+  void FwdPass2OptimizedVisitor() { step(LOIK_STEP_FWD_PASS2); }
+  void BoxProj() { step(LOIK_STEP_BOX_PROJ); }
+  void DualUpdate() { step(LOIK_STEP_DUAL_UPDATE); }
+  void ComputeResiduals() { step(LOIK_STEP_COMPUTE_RESIDUALS); }
+  void CheckConvergence() { step(LOIK_STEP_CHECK_CONVERGENCE); }
+  void CheckFeasibility() { step(LOIK_STEP_CHECK_FEASIBILITY); }
+  void UpdateMu() { step(LOIK_STEP_UPDATE_MU); }
+  // problem_.UpdateReferences(H_refs, v_refs)  (ik-id-description-optimized.hpp:103-121): [njoints][36], [njoints][6]
+  void UpdateReferences(const std::vector<double>& H_refs, const std::vector<double>& v_refs) {
+    if (H_refs.size() != (size_t)model_.njoints * 36 || v_refs.size() != (size_t)model_.njoints * 6)
+      throw std::runtime_error("[IkProblemFormulation::UpdateReferences]: input arguments 'H_refs', 'v_refs' have wrong size!!");
+    check(loik_update_references(h_, H_refs.data(), v_refs.data(), stream_));
+  }
+  // outer IK loop on the device: q <- integrate(q, dt z), then Solve(c_id, Ai, bi) on the device-resident q
+  void Integrate(double dt) { check(loik_integrate(h_, dt, stream_)); }
+  void Solve(int c_id, const std::vector<double>& Ai, const std::vector<double>& bi) {
+    check(loik_solve_task(h_, nullptr, c_id, Ai.data(), bi.data(), bi.size() == (size_t)batch_ * 6 && batch_ > 1 ? 1 : 0, LOIK_HOST, stream_));
+  }
+  std::vector<double> His() const { return get(LOIK_F_H, 36 * (model_.njoints - 1)); }   // debug mode
+  std::vector<double> pis() const { return get(LOIK_F_P, 6 * (model_.njoints - 1)); }    // debug mode
+  std::vector<double> Aty() const { return get(LOIK_F_ATY, 6 * nc_); }
+  std::vector<double> get_primal_residual_vec() const { return get(LOIK_F_PRIMAL_RES_VEC, 6 * (model_.njoints - 1) + model_.nv); }
+  std::vector<double> get_dual_residual_vec() const { return get(LOIK_F_DUAL_RES_VEC, 6 * (model_.njoints - 1) + model_.nv); }
+  std::vector<double> get_dual_residual_v() const { return norm(LOIK_N_DUAL_RES_V); }
+  std::vector<double> get_dual_residual_nu() const { return norm(LOIK_N_DUAL_RES_NU); }
+  std::vector<double> get_delta_x_qp_inf_norm() const { return norm(LOIK_N_DELTA_X_QP_INF); }
+  std::vector<double> get_delta_z_qp_inf_norm() const { return norm(LOIK_N_DELTA_Z_INF); }
+  std::vector<double> get_delta_y_qp_inf_norm() const { return norm(LOIK_N_DELTA_Y_QP_INF); }
+  std::vector<double> get_A_qp_T_delta_y_qp_inf_norm() const { return norm(LOIK_N_AT_DELTA_Y_QP_INF); }
+  std::vector<double> get_ub_qp_T_delta_y_qp_plus() const { return norm(LOIK_N_UB_T_DELTA_Y_PLUS); }
+  std::vector<double> get_lb_qp_T_delta_y_qp_minus() const { return norm(LOIK_N_LB_T_DELTA_Y_MINUS); }
+  std::vector<bool> get_primal_infeasibility_cond_1() const { return normflag(LOIK_N_PINF_COND_1); }
+  std::vector<bool> get_primal_infeasibility_cond_2() const { return normflag(LOIK_N_PINF_COND_2); }
   void set_max_iter(int m) { check(loik_set_max_iter(h_, m)); }
   void set_rho(double r) { check(loik_set_rho(h_, r)); }
   void set_mu(double m) { check(loik_set_mu(h_, m)); }
@@ -183,6 +226,19 @@ class FirstOrderLoikOptimized {
     auto r = get(LOIK_F_RESIDUALS, 4);
     std::vector<double> out(batch_);
     for (int i = 0; i < batch_; ++i) out[i] = r[4 * i + c];
+    return out;
+  }
+  void step(int which) { check(loik_step(h_, which, stream_)); }
+  std::vector<double> norm(int idx) const {
+    auto r = get(LOIK_F_NORMS, LOIK_NUM_NORMS);
+    std::vector<double> out(batch_);
+    for (int i = 0; i < batch_; ++i) out[i] = r[(size_t)LOIK_NUM_NORMS * i + idx];
+    return out;
+  }
+  std::vector<bool> normflag(int idx) const {
+    auto r = norm(idx);
+    std::vector<bool> out(batch_);
+    for (int i = 0; i < batch_; ++i) out[i] = r[i] != 0.0;
     return out;
   }
   std::vector<bool> flag(int bit) const {
