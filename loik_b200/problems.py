@@ -58,8 +58,8 @@ def random_batch(model: RobotModel, batch: int, seed: int = 0, task_joints=None,
         e = min(hi, (blk + 1) * BLK)
         q[s - lo:e - lo] = model.q_min + uq[s - blk * BLK:e - blk * BLK] * (model.q_max - model.q_min)
         b[s - lo:e - lo] = (2.0 * ub_[s - blk * BLK:e - blk * BLK] - 1.0) * b_scale
-    if model.has_free_flyer:  # q[3:7] of the root joint is a unit quaternion (x, y, z, w)
-        quat = q[:, 3:7]
+    for a, b_ in model.quaternion_slices():  # unit quaternions (x, y, z, w) of free-flyer / spherical joints
+        quat = q[:, a:b_]
         quat /= np.linalg.norm(quat, axis=1, keepdims=True)
     for i in range(1, model.nj):
         if model.is_unbounded(i):  # (cos, sin) of an unbounded revolute joint

@@ -17,6 +17,9 @@ Joint type codes (shared with ``include/loik_b200.h`` and ``oracle/loik_oracle.c
     8      free-flyer (JointModelFreeFlyer, nq = 7, nv = 6) -- supported as the root joint (joint 1, parent 0) only
     9,10,11 unbounded revolute about +x,+y,+z (JointModelRUBX/RUBY/RUBZ: URDF ``continuous`` joints; nq = 2, q = (cos, sin))
     12     unbounded revolute, unaligned axis (JointModelRevoluteUnboundedUnaligned, nq = 2)
+    13     spherical (JointModelSpherical, nq = 4 = unit quaternion x y z w, nv = 3, S = [0; I3])      -- oracles only so far
+    14     translation (JointModelTranslation, nq = nv = 3, S = [I3; 0])                                 -- oracles only so far
+    (a free-flyer away from the root is likewise understood by both oracles, not yet by the CUDA kernels)
 
 Other 1-DoF joints have ``nq = nv = 1``; ``idx_q`` / ``idx_v`` follow pinocchio (cumulative over the joints in id order).
 """
@@ -27,7 +30,7 @@ import math
 
 import numpy as np
 
-RX, RY, RZ, PX, PY, PZ, RU, PU, FF, RUBX, RUBY, RUBZ, RUBU = range(13)
+RX, RY, RZ, PX, PY, PZ, RU, PU, FF, RUBX, RUBY, RUBZ, RUBU, SPH, TRA = range(15)
 _AXES = {"x": (1.0, 0.0, 0.0), "y": (0.0, 1.0, 0.0), "z": (0.0, 0.0, 1.0)}
 
 
@@ -65,7 +68,13 @@ class RobotModel:
 
     @property
     def has_free_flyer(self) -> bool:
+        """A free-flyer ROOT joint (the only multi-DoF joint the CUDA kernels take)."""
         return self.nj > 1 and int(self.jtype[1]) == FF
+
+    @property
+    def gpu_supported(self) -> bool:
+        return all(int(self.jtype[i]) not in (SPH, TRA) and (int(self.jtype[i]) != FF or (i == 1 and self.parent[i] == 0))
+                   for i in range(1, self.nj))
 
     @property
     def nv(self) -> int:
@@ -76,11 +85,23 @@ class RobotModel:
         return sum(self.nq_joint(i) for i in range(1, self.nj))
 
     def nv_joint(self, i: int) -> int:
-        return 6 if int(self.jtype[i]) == FF else 1
+        jt = int(self.jtype[i])
+        return 6 if jt == FF else (3 if jt in (SPH, TRA) else 1)
 
     def nq_joint(self, i: int) -> int:
         jt = int(self.jtype[i])
-        return 7 if jt == FF else (2 if RUBX <= jt <= RUBU else 1)
+        return {FF: 7, SPH: 4, TRA: 3}.get(jt, 2 if RUBX <= jt <= RUBU else 1)
+
+    def quaternion_slices(self):
+        """(start, stop) of every unit quaternion inside q (free-flyer: q[iq+3:iq+7], spherical: q[iq:iq+4])."""
+        out = []
+        for i in range(1, self.nj):
+            jt, iq = int(self.jtype[i]), self.idx_q(i)
+            if jt == FF:
+                out.append((iq + 3, iq + 7))
+            elif jt == SPH:
+                out.append((iq, iq + 4))
+        return out
 
     def idx_v(self, i: int) -> int:
         return sum(self.nv_joint(k) for k in range(1, i))
@@ -93,8 +114,8 @@ class RobotModel:
 
     def neutral(self) -> np.ndarray:
         q = np.zeros(self.nq)
-        if self.has_free_flyer:
-            q[6] = 1.0  # unit quaternion (x, y, z, w)
+        for a, b in self.quaternion_slices():
+            q[b - 1] = 1.0  # unit quaternion (x, y, z, w)
         for i in range(1, self.nj):
             if self.is_unbounded(i):
                 q[self.idx_q(i)] = 1.0  # (cos, sin) = (1, 0)
@@ -103,8 +124,8 @@ class RobotModel:
     def normalize(self, q: np.ndarray) -> np.ndarray:
         """pinocchio::normalize: unit quaternion of a free-flyer, unit (cos, sin) of the unbounded revolute joints."""
         q = np.array(q, np.float64)
-        if self.has_free_flyer:
-            q[..., 3:7] /= np.linalg.norm(q[..., 3:7], axis=-1, keepdims=True)
+        for a, b in self.quaternion_slices():
+            q[..., a:b] /= np.linalg.norm(q[..., a:b], axis=-1, keepdims=True)
         for i in range(1, self.nj):
             if self.is_unbounded(i):
                 iq = self.idx_q(i)
@@ -120,8 +141,11 @@ class RobotModel:
         out = np.empty_like(q)
         for i in range(1, self.nj):
             iq, iv = self.idx_q(i), self.idx_v(i)
-            if int(self.jtype[i]) == FF:
-                raise NotImplementedError("integrate: free-flyer (SE3 exponential) is not supported")
+            if int(self.jtype[i]) in (FF, SPH):
+                raise NotImplementedError("integrate: free-flyer / spherical joints (SE3 / SO3 exponential) are not supported")
+            if int(self.jtype[i]) == TRA:
+                out[..., iq:iq + 3] = q[..., iq:iq + 3] + v[..., iv:iv + 3]
+                continue
             if self.is_unbounded(i):
                 ca, sa, om = q[..., iq], q[..., iq + 1], v[..., iv]
                 co, so = np.cos(om), np.sin(om)
@@ -136,8 +160,7 @@ class RobotModel:
         assert self.parent[0] == 0
         for i in range(1, self.nj):
             assert 0 <= self.parent[i] < i, "joints must be numbered parent < child"
-            assert 0 <= self.jtype[i] <= RUBU
-            assert self.jtype[i] != FF or (i == 1 and self.parent[i] == 0), "free-flyer only as the root joint"
+            assert 0 <= self.jtype[i] <= TRA
             assert abs(np.linalg.norm(self.axis[i]) - 1.0) < 1e-12
             R = self.placement_R[i]
             assert np.allclose(R @ R.T, np.eye(3), atol=1e-12)
@@ -155,14 +178,15 @@ def _build(name, joints) -> RobotModel:
     qmin, qmax, vmax, names = [], [], [], ["universe"]
     for i, (jn, par, jt, ax, xyz, rpy, lo, hi, vm) in enumerate(joints, start=1):
         parent[i] = par
-        if jt == "FF":
-            jtype[i] = FF
+        if jt in ("FF", "S", "T"):
+            jtype[i] = {"FF": FF, "S": SPH, "T": TRA}[jt]
             axis[i] = (0.0, 0.0, 1.0)
             R[i] = rpy_to_matrix(*rpy)
             p[i] = xyz
-            qmin += [-1.0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0]   # position box; the quaternion part is normalised by the samplers
-            qmax += [1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0]
-            vmax += [vm] * 6
+            nqj, nvj = {"FF": (7, 6), "S": (4, 3), "T": (3, 3)}[jt]
+            qmin += [-1.0] * nqj   # position box; the quaternion part is normalised by the samplers
+            qmax += [1.0] * nqj
+            vmax += [vm] * nvj
             names.append(jn)
             continue
         if isinstance(ax, str):
@@ -286,7 +310,7 @@ def talos(floating: bool = False) -> RobotModel:
 
 
 def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0.3, prismatic: float = 0.25,
-                continuous: float = 0.0) -> RobotModel:
+                continuous: float = 0.0, multidof: float = 0.0) -> RobotModel:
     """Seeded random kinematic tree covering every joint type (parity stress tests)."""
     rng = np.random.default_rng(seed)
     J = []
@@ -295,6 +319,8 @@ def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0
         kind = "P" if rng.random() < prismatic else "R"
         if continuous > 0.0 and kind == "R" and rng.random() < continuous:
             kind = "C"
+        if multidof > 0.0 and rng.random() < multidof:  # spherical / translation / free-flyer anywhere in the tree
+            kind = ("S", "T", "FF")[int(rng.integers(0, 3))]
         if rng.random() < unaligned:
             ax = rng.normal(size=3)
         else:
@@ -303,7 +329,7 @@ def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0
         rpy = tuple(rng.uniform(-math.pi, math.pi, size=3))
         lo, hi = (-0.3, 0.3) if kind == "P" else (-2.5, 2.5)
         J.append((f"j{i}", par, kind, ax, xyz, rpy, lo, hi, float(rng.uniform(1.0, 4.0))))
-    return _build(f"random{nb}_s{seed}" + ("c" if continuous > 0.0 else ""), J)
+    return _build(f"random{nb}_s{seed}" + ("c" if continuous > 0.0 else "") + ("m" if multidof > 0.0 else ""), J)
 
 
 ROBOTS = {"panda": panda, "panda9": lambda: panda(True), "ur10": ur10, "ur10c": lambda: ur10(True), "talos": talos,

@@ -40,6 +40,10 @@ def dual_action_matrix(R, t):
 def joint_subspace(jtype, axis):
     if jtype == 8:  # free-flyer
         return np.eye(6)
+    if jtype == 13:  # spherical: S = [0; I3]
+        return np.vstack([np.zeros((3, 3)), np.eye(3)])
+    if jtype == 14:  # translation: S = [I3; 0]
+        return np.vstack([np.eye(3), np.zeros((3, 3))])
     if 9 <= jtype <= 12:  # unbounded revolute: the subspace of RX/RY/RZ/RU
         jtype = jtype - 9 if jtype < 12 else 6
     S = np.zeros((6, 1))
@@ -56,12 +60,14 @@ def joint_subspace(jtype, axis):
 
 def joint_transform(jtype, axis, q):
     """jmodel.calc -> jdata.M(): (R, p).  q: scalar for 1-DoF joints, (x, y, z, qx, qy, qz, qw) for the free-flyer."""
-    if jtype == 8:
-        x, y, z, w = q[3:7]
+    if jtype == 14:
+        return np.eye(3), np.asarray(q[:3], float).copy()
+    if jtype in (8, 13):
+        x, y, z, w = q[3:7] if jtype == 8 else q[0:4]
         R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
                       [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
                       [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
-        return R, np.asarray(q[:3], float).copy()
+        return R, (np.asarray(q[:3], float).copy() if jtype == 8 else np.zeros(3))
     if 9 <= jtype <= 12:  # JointModelRevoluteUnbounded*: q = (cos, sin), used as given
         c, s_ = float(q[0]), float(q[1])
         a = np.eye(3)[jtype - 9] if jtype < 12 else np.asarray(axis, float)

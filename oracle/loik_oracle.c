@@ -30,7 +30,9 @@
 
 #define LO_API __attribute__((visibility("default")))
 
-enum { JT_RX = 0, JT_RY, JT_RZ, JT_PX, JT_PY, JT_PZ, JT_RU, JT_PU, JT_FF, JT_RUBX, JT_RUBY, JT_RUBZ, JT_RUBU };
+enum { JT_RX = 0, JT_RY, JT_RZ, JT_PX, JT_PY, JT_PZ, JT_RU, JT_PU, JT_FF, JT_RUBX, JT_RUBY, JT_RUBZ, JT_RUBU, JT_SPH, JT_TRA };
+static int jt_nv(int jt) { return jt == JT_FF ? 6 : ((jt == JT_SPH || jt == JT_TRA) ? 3 : 1); }
+static int jt_nq(int jt) { return jt == JT_FF ? 7 : (jt == JT_SPH ? 4 : (jt == JT_TRA ? 3 : ((jt >= JT_RUBX && jt <= JT_RUBU) ? 2 : 1))); }
 
 typedef struct lo_solver {
   /* ---- model (what the hot path reads from pinocchio::Model) ---- */
@@ -188,6 +190,8 @@ static void joint_S(int jt, const double *axis, double *S) { /* S[6*row + col], 
     case JT_PX: case JT_PY: case JT_PZ: S[6 * (jt - 3)] = 1.0; break;
     case JT_RU: case JT_RUBU: S[18] = axis[0]; S[24] = axis[1]; S[30] = axis[2]; break;
     case JT_PU: S[0] = axis[0]; S[6] = axis[1]; S[12] = axis[2]; break;
+    case JT_SPH: for (int k = 0; k < 3; ++k) S[6 * (3 + k) + k] = 1.0; break; /* JointModelSpherical: S = [0; I3] */
+    case JT_TRA: for (int k = 0; k < 3; ++k) S[6 * k + k] = 1.0; break;       /* JointModelTranslation: S = [I3; 0] */
     default: for (int k = 0; k < 6; ++k) S[7 * k] = 1.0; break; /* free-flyer: identity */
   }
 }
@@ -214,12 +218,14 @@ static void joint_M(int jt, const double *axis, const double *qv, double *MR, do
     }
     return;
   }
-  if (jt == JT_FF) { /* q = (x, y, z, qx, qy, qz, qw): M = (R(quat), p) */
-    const double x = qv[3], y = qv[4], z = qv[5], w = qv[6];
+  if (jt == JT_TRA) { Mp[0] = qv[0]; Mp[1] = qv[1]; Mp[2] = qv[2]; return; }
+  if (jt == JT_FF || jt == JT_SPH) { /* q = (x, y, z, qx, qy, qz, qw): M = (R(quat), p); spherical: q = (qx, qy, qz, qw), p = 0 */
+    const int o = jt == JT_FF ? 3 : 0;
+    const double x = qv[o], y = qv[o + 1], z = qv[o + 2], w = qv[o + 3];
     MR[0] = 1 - 2 * (y * y + z * z); MR[1] = 2 * (x * y - z * w);     MR[2] = 2 * (x * z + y * w);
     MR[3] = 2 * (x * y + z * w);     MR[4] = 1 - 2 * (x * x + z * z); MR[5] = 2 * (y * z - x * w);
     MR[6] = 2 * (x * z - y * w);     MR[7] = 2 * (y * z + x * w);     MR[8] = 1 - 2 * (x * x + y * y);
-    Mp[0] = qv[0]; Mp[1] = qv[1]; Mp[2] = qv[2];
+    if (jt == JT_FF) { Mp[0] = qv[0]; Mp[1] = qv[1]; Mp[2] = qv[2]; }
   } else if (jt <= JT_RZ) {
     double s = sin(q), c = cos(q);
     int a = (jt + 1) % 3, b = (jt + 2) % 3; /* rotation in the (a,b) plane */
@@ -321,8 +327,8 @@ LO_API lo_solver *lo_create(int nj, const int *parent, const int *jtype, const d
   s->nv = 0; s->nq = 0;
   for (int i = 1; i < nj; ++i) {
     s->idxv[i] = s->nv; s->idxq[i] = s->nq;
-    s->nvj[i] = (jtype[i] == JT_FF) ? 6 : 1;
-    s->nv += s->nvj[i]; s->nq += (jtype[i] == JT_FF) ? 7 : ((jtype[i] >= JT_RUBX && jtype[i] <= JT_RUBU) ? 2 : 1);
+    s->nvj[i] = jt_nv(jtype[i]);
+    s->nv += s->nvj[i]; s->nq += jt_nq(jtype[i]);
   }
   s->axis = dalloc(3 * nj); memcpy(s->axis, axis, 3 * nj * sizeof(double));
   s->plR = dalloc(9 * nj); memcpy(s->plR, plR, 9 * nj * sizeof(double));
@@ -1017,9 +1023,9 @@ static void integrate_q(const lo_solver *s, double *q, const double *v, double d
       double c = co * ca - so * sa, sn = so * ca + co * sa;
       const double k = (3.0 - (c * c + sn * sn)) / 2.0;
       q[iq] = c * k; q[iq + 1] = sn * k;
-    } else {
-      q[iq] += dt * v[iv];
-    }
+    } else if (jt_nq(jt) == s->nvj[i]) { /* vector-space joints (1-DoF, translation) */
+      for (int k = 0; k < s->nvj[i]; ++k) q[iq + k] += dt * v[iv + k];
+    } /* free-flyer / spherical: the SE3 / SO3 exponential is not restated; the tracking driver is not used with them */
   }
 }
 

@@ -28,7 +28,15 @@ def _fk(model, q):
     for i in range(1, model.nj):
         jt, iq = int(model.jtype[i]), model.idx_q(i)
         ax = np.eye(3)[jt % 3] if jt <= 5 else (np.eye(3)[jt - 9] if 9 <= jt <= 11 else model.axis[i])
-        if jt <= 2 or jt == 6:
+        if jt in (8, 13):  # free-flyer (x y z | quaternion) / spherical (quaternion x y z w)
+            x, y, z, w = q[iq + 3:iq + 7] if jt == 8 else q[iq:iq + 4]
+            Rj = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                           [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                           [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+            pj = q[iq:iq + 3].copy() if jt == 8 else np.zeros(3)
+        elif jt == 14:
+            Rj, pj = np.eye(3), q[iq:iq + 3].copy()
+        elif jt <= 2 or jt == 6:
             Rj, pj = _rot(ax, q[iq]), np.zeros(3)
         elif 9 <= jt <= 12:
             Rj, pj = _rot(ax, np.arctan2(q[iq + 1], q[iq])), np.zeros(3)
@@ -42,10 +50,45 @@ def _fk(model, q):
     return R, p
 
 
+def _quat_mul(a, b):  # (x, y, z, w)
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def _move(model, q, v):
+    """q (+) v with the exact exponential maps, written here (body-frame velocities: q_R <- q_R * exp(omega),
+    p <- p + R v_lin for the free-flyer)."""
+    out = np.array(q, float)
+    for i in range(1, model.nj):
+        jt, iq, iv = int(model.jtype[i]), model.idx_q(i), model.idx_v(i)
+        if jt in (8, 13):
+            w = v[iv + 3:iv + 6] if jt == 8 else v[iv:iv + 3]
+            th = np.linalg.norm(w)
+            dq = np.append(np.sin(th / 2) * w / th, np.cos(th / 2)) if th > 0 else np.array([0, 0, 0, 1.0])
+            qs = slice(iq + 3, iq + 7) if jt == 8 else slice(iq, iq + 4)
+            if jt == 8:  # first order in |v| is all the finite difference needs
+                x, y, z, ww = q[qs]
+                R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * ww), 2 * (x * z + y * ww)],
+                              [2 * (x * y + z * ww), 1 - 2 * (x * x + z * z), 2 * (y * z - x * ww)],
+                              [2 * (x * z - y * ww), 2 * (y * z + x * ww), 1 - 2 * (x * x + y * y)]])
+                out[iq:iq + 3] = q[iq:iq + 3] + R @ v[iv:iv + 3]
+            out[qs] = _quat_mul(q[qs], dq)
+        elif jt == 14:
+            out[iq:iq + 3] = q[iq:iq + 3] + v[iv:iv + 3]
+        elif 9 <= jt <= 12:
+            th = np.arctan2(q[iq + 1], q[iq]) + v[iv]
+            out[iq], out[iq + 1] = np.cos(th), np.sin(th)
+        else:
+            out[iq] = q[iq] + v[iv]
+    return out
+
+
 def _body_velocities(model, q, nu, eps=1e-6):
     """Central differences of the forward kinematics along nu, expressed in each joint's own frame, [linear; angular]."""
-    Rp, pp = _fk(model, model.integrate(q, eps * nu))
-    Rm, pm = _fk(model, model.integrate(q, -eps * nu))
+    Rp, pp = _fk(model, _move(model, q, eps * nu))
+    Rm, pm = _fk(model, _move(model, q, -eps * nu))
     R0, _ = _fk(model, q)
     out = np.zeros((model.nj, 6))
     for i in range(1, model.nj):
@@ -66,7 +109,7 @@ def _check(model, pr, what):
     assert err < 1e-6 * max(1.0, np.abs(B.vis).max()), f"{what}: link velocities differ from d/dt FK by {err:.2e}"
 
 
-@pytest.mark.parametrize("name", ["panda", "panda9", "ur10", "ur10c", "talos"])
+@pytest.mark.parametrize("name", ["panda", "panda9", "ur10", "ur10c", "talos", "talos_ff"])
 def test_link_velocities_are_time_derivatives_of_forward_kinematics(name):
     model = robots.get_robot(name)
     pb = problems.random_batch(model, 3, seed=41)
@@ -75,10 +118,11 @@ def test_link_velocities_are_time_derivatives_of_forward_kinematics(name):
         _check(model, pr, f"{name}[{k}]")
 
 
-@pytest.mark.parametrize("seed,continuous", [(0, 0.0), (1, 0.0), (2, 0.5), (3, 1.0)])
-def test_link_velocities_random_trees(seed, continuous):
-    """Every joint type (aligned / unaligned, revolute / prismatic / unbounded revolute), random placements, branching."""
-    model = robots.random_tree(11, seed, continuous=continuous)
+@pytest.mark.parametrize("seed,continuous,multidof", [(0, 0.0, 0.0), (1, 0.0, 0.0), (2, 0.5, 0.0), (3, 1.0, 0.0), (4, 0.0, 0.4), (5, 0.3, 0.5)])
+def test_link_velocities_random_trees(seed, continuous, multidof):
+    """Every joint type (aligned / unaligned, revolute / prismatic / unbounded revolute / spherical / translation /
+    free-flyer anywhere), random placements, branching."""
+    model = robots.random_tree(11, seed, continuous=continuous, multidof=multidof)
     rng = np.random.default_rng(500 + seed)
     ids = np.array(sorted(rng.choice(np.arange(1, model.nj), size=2, replace=False)), np.int32)
     pr = dict(q=model.normalize(rng.uniform(model.q_min, model.q_max)), H_ref=np.eye(6), v_ref=np.zeros(6), ids=ids,

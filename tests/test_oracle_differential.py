@@ -118,11 +118,12 @@ def test_optimized_correctness_component_wise(name, bound):
         step_once_and_compare(A, B, model, it, f"{name} it{it}")
 
 
-@pytest.mark.parametrize("seed,continuous", [(0, 0.0), (1, 0.0), (2, 0.0), (3, 0.0), (4, 0.5), (5, 0.5), (6, 1.0)])
-def test_component_wise_random_trees(seed, continuous):
+@pytest.mark.parametrize("seed,continuous,multidof", [(0, 0.0, 0.0), (1, 0.0, 0.0), (2, 0.0, 0.0), (3, 0.0, 0.0), (4, 0.5, 0.0),
+                                                      (5, 0.5, 0.0), (6, 1.0, 0.0), (7, 0.0, 0.3), (8, 0.3, 0.3), (9, 0.0, 0.6)])
+def test_component_wise_random_trees(seed, continuous, multidof):
     """Same, on seeded random trees with every joint type (aligned/unaligned, revolute/prismatic/unbounded revolute,
-    branching)."""
-    model = robots.random_tree(12, seed, continuous=continuous)
+    and -- oracles only so far -- spherical / translation joints and free-flyers anywhere in the tree), branching."""
+    model = robots.random_tree(12, seed, continuous=continuous, multidof=multidof)
     rng = np.random.default_rng(100 + seed)
     params = dict(problems.FIXTURE_PARAMS, max_iter=2, num_eq_c=2)
     ids = np.array(sorted(rng.choice(np.arange(1, model.nj), size=2, replace=False)), np.int32)
