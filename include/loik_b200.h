@@ -48,9 +48,11 @@ extern "C" {
 /* joint type codes: pinocchio JointModelRX/RY/RZ, PX/PY/PZ, RevoluteUnaligned, PrismaticUnaligned */
 enum { LOIK_JOINT_RX = 0, LOIK_JOINT_RY, LOIK_JOINT_RZ, LOIK_JOINT_PX, LOIK_JOINT_PY, LOIK_JOINT_PZ,
        LOIK_JOINT_RU, LOIK_JOINT_PU,
-       LOIK_JOINT_FF, /* JointModelFreeFlyer (nq 7 = x y z qx qy qz qw, nv 6): as the root joint (joint 1, parent 0) only */
+       LOIK_JOINT_FF, /* JointModelFreeFlyer (nq 7 = x y z qx qy qz qw, nv 6), anywhere in the tree */
        /* JointModelRUBX/RUBY/RUBZ and JointModelRevoluteUnboundedUnaligned (URDF `continuous` joints): nq 2 = (cos, sin), nv 1 */
-       LOIK_JOINT_RUBX, LOIK_JOINT_RUBY, LOIK_JOINT_RUBZ, LOIK_JOINT_RUBU };
+       LOIK_JOINT_RUBX, LOIK_JOINT_RUBY, LOIK_JOINT_RUBZ, LOIK_JOINT_RUBU,
+       LOIK_JOINT_SPHERICAL,   /* JointModelSpherical (nq 4 = unit quaternion x y z w, nv 3, S = [0; I3]) */
+       LOIK_JOINT_TRANSLATION  /* JointModelTranslation (nq = nv = 3, S = [I3; 0]) */ };
 
 /* where a caller buffer lives: pageable host memory (staged + synchronous), device memory (asynchronous),
  * or page-locked host memory (asynchronous DMA; the caller synchronizes the stream before reusing / reading it) */

@@ -25,6 +25,7 @@ constexpr int kMaxJoints = 64;
 constexpr int kMaxTasks = 8;
 constexpr int kMaxPin = 6;    // children per joint that are not carried in registers
 constexpr int kMaxSeg = 16;   // chains of the tree that can be swept by different warps
+constexpr int kMaxMd = 8;     // multi-DoF joints (free-flyer, spherical, translation) per model
 
 // status of an instance (per-instance loop control of Solve()/InfeasibilityTailSolve())
 enum : int { ST_RUNNING = 0, ST_TAIL = 1, ST_CONVERGED = 2, ST_INFEASIBLE_DONE = 3, ST_MAXITER = 4 };
@@ -40,7 +41,9 @@ struct JointC {
   int pout;                         // else (parent > 0): the pending block this joint writes its contribution to
   int npin;                         // number of children that hand their contribution over through a pending block
   int pin[kMaxPin];                 // those blocks (one per tree edge: single writer, no read-modify-write)
-  int qkind, pad;                   // how q parametrises the joint: 0 = one scalar, 1 = (cos, sin) (unbounded revolute)
+  int qkind;                        // how q parametrises the joint: 0 = one scalar, 1 = (cos, sin) (unbounded revolute)
+  int nvj, sel0, mblk;              // multi-DoF joints: nv of the joint (3 / 6), first component S selects, index of its md block
+  int pad;
 };
 
 struct TaskC {
@@ -62,16 +65,19 @@ enum : int { TR_Y = 0, TR_ATY = 6, TR_B = 12, TR_ATB = 18, TR_ROWS = 24 };      
 enum : int { PR_H = 0, PR_F = 27, PR_ROWS = 33 };                                 // rows of a pending-accumulator block
 enum : int { GR_MU = 0, GR_BINF = 1, GR_CTL = 2, GR_RES = 3, GR_CARRY = 7, GR_NORMS = 21, GR_ROWS = 49 };  // globals (norms: 28 rows)
 
-// Free-flyer root joint (JointModelFreeFlyer, nv = 6): its 6-vector quantities (v, f, F, H, p) use the rows of joint
-// block 1 like every joint; what is per-dof (6 instead of 1) lives in this extra block.
+// Multi-DoF joints whose motion subspace selects components (JointModelFreeFlyer: S = I6, nq 7; JointModelSpherical:
+// S = [0; I3], nq 4; JointModelTranslation: S = [I3; 0], nq 3): their 6-vector quantities (v, f, F, H, p) use the rows of
+// their joint block like every joint; what is per-dof (K = 3 / 6 instead of 1) lives in an extra block per such joint
+// (sized for K = 6).
 enum : int { FR_NU = 0, FR_Z = 6, FR_W = 12, FR_T = 18,   // state (24 rows)
-             FR_LB = 24, FR_UB = 30, FR_Q = 36,          // problem data (19 rows): bounds, q = (x y z qx qy qz qw)
-             FR_DINV = 43, FR_R = 64,                    // workspace: Dinv (21, symmetric 6x6 packed), r (6)
-             FR_ROWS = 70 };
+             FR_LB = 24, FR_UB = 30, FR_Q = 36,          // problem data (19 rows): bounds, q (up to 7: x y z qx qy qz qw)
+             FR_XF = 43,                                 // liMi = placement * M(q): rotation (9, row-major), translation (3)
+             FR_DINV = 55, FR_R = 76, FR_UD = 82,        // workspace: Dinv (21, symmetric packed), r (6), UDinv (6 x K, [a][k])
+             FR_ROWS = 118 };
 
 struct Offs {
   int glob, joint0, task0, pend0;  // first row of the globals, of joint 1, of task 0, of pending slot 0
-  int ff0;                         // first row of the free-flyer block (when the model has one)
+  int ff0;                         // first row of the multi-DoF blocks (FR_ROWS each)
   int prv, drv;                    // debug: primal / dual residual vectors (6 nb + nv rows each)
   int rows;                        // rows per tile record
 };
@@ -80,14 +86,20 @@ struct Offs {
 // through pending blocks / the parent's v row, so different warps can sweep them; `blevel` / `flevel` order them
 // (children before parents on the way down to the root, parents before children on the way out).
 struct SegC { short lo, hi, bwarp, blevel, fwarp, flevel; };
+// A span = a maximal run lo..hi of consecutive 1-DoF joints, or one multi-DoF joint (lo == hi, md = its nv): the units
+// the one-warp-per-tile kernel sweeps, so that the multi-DoF steps stay out of the register-carried joint loops.
+struct SpanC { short lo, hi, md, pad; };
+constexpr int kMaxSpan = 2 * kMaxMd + 1;
 
 struct ModelC {
   int nj, nb, nc, npend;
   int max_iter, bounds_per_instance;
   int nseg, nblevel, nflevel, nwarp;
-  int has_ff, nv, nq, pad0;        // joint 1 is a free-flyer; model.nv, model.nq
-  double fflb[6], ffub[6];         // its bounds when shared by the batch
+  int nmd, nv, nq, pad0;           // number of multi-DoF joints; model.nv, model.nq
+  double mdlb[kMaxMd][6], mdub[kMaxMd][6];  // their bounds when shared by the batch
   SegC seg[kMaxSeg];
+  int nspan, pad1;
+  SpanC span[kMaxSpan];
   Offs off;
   double rho, mu0, mu_scale, tol_abs, tol_rel, tol_pinf, tol_dinf, tol_tail, Hv_inf;
   JointC j[kMaxJoints];
@@ -127,6 +139,7 @@ struct StateP {
 // (a __constant__ symbol is a per-module singleton; a device buffer read with LDG measured 1.8x slower).
 
 #define LOIK_DEV __device__ __forceinline__
+#define LOIK_DEV_CALL __device__ __noinline__  // rare paths kept out of the hot loops' register allocation
 
 __host__ __device__ __forceinline__ constexpr int si(int i, int j) { return i <= j ? (i * (5 - i)) / 2 + j : (j * (5 - j)) / 2 + i; }
 // T = this thread's lane inside its tile record; row r lives at T[r * 32].
@@ -138,7 +151,7 @@ LOIK_DEV double* joint_blk(double* T, const Offs& O, int ji) { return T + (size_
 LOIK_DEV double* task_blk(double* T, const Offs& O, int k) { return T + (size_t)(O.task0 + TR_ROWS * k) * 32; }
 LOIK_DEV double* pend_blk(double* T, const Offs& O, int k) { return T + (size_t)(O.pend0 + PR_ROWS * k) * 32; }
 LOIK_DEV double* glob_blk(double* T, const Offs& O) { return T + (size_t)O.glob * 32; }
-LOIK_DEV double* ff_blk(double* T, const Offs& O) { return T + (size_t)O.ff0 * 32; }
+LOIK_DEV double* md_blk(double* T, const Offs& O, int m) { return T + (size_t)(O.ff0 + FR_ROWS * m) * 32; }
 __host__ __device__ __forceinline__ constexpr int s6(int i, int j) { return i <= j ? i * 6 - (i * (i - 1)) / 2 + (j - i) : j * 6 - (j * (j - 1)) / 2 + (i - j); }
 // Running inf-norms and the box projection are compare + select: sm_100a has no fp64 min/max instruction, and
 // fmax()/fmin() expand to DSETP + FSEL + SEL + a NaN-quieting LOP3 + register-pair shuffles (8-9 instructions each,
@@ -756,50 +769,74 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, const double* Ts, double* Td
 }
 
 // ---------------------------------------------------------------------------------------------
-// Free-flyer root joint (joint 1, parent = universe; S = I6, nv = 6): the three sweeps' steps for it.  calc_aba
-// (P1, general form): U = H, Dinv = (H + mu_ineq I)^-1 (Cholesky), no projection / propagation (nothing above the
-// root is ever read); v_parent = 0 so nu = -Dinv r and v = nu.  The regular sweeps then run over joints 2..nb.
+// Multi-DoF joints (K = J.nvj dofs, S selects components sel0 .. sel0+K-1): the three sweeps' steps for one such joint,
+// called from inside the joint loops.  calc_aba (P1, general form): U = H S, StU = S^T U + mu_ineq I,
+// Dinv = StU^-1 (pinocchio: Cholesky, PerformStYSInversion), UDinv = U Dinv, and below a non-root joint
+// H -= UDinv U^T.  They never carry to / from a neighbour in registers: every edge into or out of them is a pending
+// block.  At the root (parent = universe) nothing above is read: no projection, v_parent = 0, nu = -Dinv r.
 // ---------------------------------------------------------------------------------------------
-LOIK_DEV void spd6_inverse(double (&M)[36], double (&Minv)[21]) {  // M: full symmetric 6x6, overwritten by its Cholesky factor
+template <int K>
+__host__ __device__ __forceinline__ constexpr int sk(int i, int j) { return i <= j ? i * K - (i * (i - 1)) / 2 + (j - i) : j * K - (j * (j - 1)) / 2 + (i - j); }
+
+template <int K>
+LOIK_DEV void spd_inverse(double (&M)[K * K], double (&Minv)[K * (K + 1) / 2]) {  // M: full symmetric KxK, overwritten by its Cholesky factor
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < K; ++i)
 #pragma unroll
     for (int j = 0; j <= i; ++j) {
-      double sum = M[6 * i + j];
+      double sum = M[K * i + j];
 #pragma unroll
-      for (int k = 0; k < j; ++k) sum -= M[6 * i + k] * M[6 * j + k];
-      M[6 * i + j] = (i == j) ? sqrt(sum) : sum / M[6 * j + j];
+      for (int k = 0; k < j; ++k) sum -= M[K * i + k] * M[K * j + k];
+      M[K * i + j] = (i == j) ? sqrt(sum) : sum / M[K * j + j];
     }
-  double Li[36];  // L^-1 (lower triangular)
+  double Li[K * K];  // L^-1 (lower triangular)
 #pragma unroll
-  for (int c = 0; c < 6; ++c)
+  for (int c = 0; c < K; ++c)
 #pragma unroll
-    for (int i = c; i < 6; ++i) {
+    for (int i = c; i < K; ++i) {
       double sum = (i == c) ? 1.0 : 0.0;
 #pragma unroll
-      for (int k = c; k < i; ++k) sum -= M[6 * i + k] * Li[6 * k + c];
-      Li[6 * i + c] = sum / M[6 * i + i];
+      for (int k = c; k < i; ++k) sum -= M[K * i + k] * Li[K * k + c];
+      Li[K * i + c] = sum / M[K * i + i];
     }
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < K; ++i)
 #pragma unroll
-    for (int j = i; j < 6; ++j) {
+    for (int j = i; j < K; ++j) {
       double sum = 0.0;
 #pragma unroll
-      for (int k = j; k < 6; ++k) sum += Li[6 * k + i] * Li[6 * k + j];
-      Minv[s6(i, j)] = sum;
+      for (int k = j; k < K; ++k) sum += Li[K * k + i] * Li[K * k + j];
+      Minv[sk<K>(i, j)] = sum;
     }
 }
+// element (a, b) of H = [[A, B], [B^T, D]]
+LOIK_DEV double Hel(const double (&A)[6], const double (&B)[9], const double (&D)[6], int a, int b) {
+  return a < 3 ? (b < 3 ? A[si(a, b)] : B[3 * a + (b - 3)]) : (b < 3 ? B[3 * b + (a - 3)] : D[si(a - 3, b - 3)]);
+}
+LOIK_DEV void Hsub(double (&A)[6], double (&B)[9], double (&D)[6], int a, int b, double x) {  // H(a, b) -= x, a <= b
+  if (b < 3) A[si(a, b)] -= x;
+  else if (a < 3) B[3 * a + (b - 3)] -= x;
+  else D[si(a - 3, b - 3)] -= x;
+}
+LOIK_DEV void md_load_xf(const double* Pf, double (&R)[9], double (&t)[3]) {
+#pragma unroll
+  for (int c = 0; c < 9; ++c) R[c] = ld(Pf, FR_XF + c);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) t[c] = ld(Pf, FR_XF + 9 + c);
+}
 
-LOIK_DEV void ff_backward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, const bool migrate = false) {
+template <int K>
+LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, const int i,
+                          const bool migrate) {
   const Offs& O = c_model.off;
-  const JointC& J = c_model.j[1];
-  double* Pj = joint_blk(Td, O, 0);
-  double* Pf = ff_blk(Td, O);
-  const double* Pjs = joint_blk(const_cast<double*>(Ts), O, 0);
-  const double* Pfs = ff_blk(const_cast<double*>(Ts), O);
+  const JointC& J = c_model.j[i];
+  const int s0 = J.sel0;
+  double* Pj = joint_blk(Td, O, i - 1);
+  double* Pf = md_blk(Td, O, J.mblk);
+  const double* Pjs = joint_blk(const_cast<double*>(Ts), O, i - 1);
+  const double* Pfs = md_blk(const_cast<double*>(Ts), O, J.mblk);
   const double rho = c_model.rho;
-  double A[6], B[9], D[6], p[6], w[6], z[6];
+  double A[6], B[9], D[6], p[6], w[K], z[K];
   if (migrate) {  // the problem data rows travel with the instance
     for (int c = FR_LB; c < FR_DINV; ++c) st(Pf, c, ldc(Pfs, c));
     if (J.task >= 0) {
@@ -809,17 +846,19 @@ LOIK_DEV void ff_backward(const ModelC& c_model, const double* Ts, double* Td, c
     }
   }
 #pragma unroll
-  for (int c = 0; c < 6; ++c) { p[c] = -rho * ld(Pjs, JR_V + c) - J.Hv[c]; A[c] = J.HrA[c]; D[c] = J.HrD[c]; w[c] = ld(Pfs, FR_W + c); z[c] = ld(Pfs, FR_Z + c); }
+  for (int c = 0; c < 6; ++c) { p[c] = -rho * ld(Pjs, JR_V + c) - J.Hv[c]; A[c] = J.HrA[c]; D[c] = J.HrD[c]; }
+#pragma unroll
+  for (int c = 0; c < K; ++c) { w[c] = ld(Pfs, FR_W + c); z[c] = ld(Pfs, FR_Z + c); }
 #pragma unroll
   for (int c = 0; c < 9; ++c) B[c] = J.HrB[c];
   A[0] += rho; A[3] += rho; A[5] += rho; D[0] += rho; D[3] += rho; D[5] += rho;
   if (J.task >= 0) {
-    const TaskC& K = c_model.t[J.task];
+    const TaskC& Kt = c_model.t[J.task];
     const double* Pk = task_blk(const_cast<double*>(Ts), O, J.task);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { A[c] += mu_eq * K.AtA_A[c]; D[c] += mu_eq * K.AtA_D[c]; p[c] += ld(Pk, TR_ATY + c) - mu_eq * ld(Pk, TR_ATB + c); }
+    for (int c = 0; c < 6; ++c) { A[c] += mu_eq * Kt.AtA_A[c]; D[c] += mu_eq * Kt.AtA_D[c]; p[c] += ld(Pk, TR_ATY + c) - mu_eq * ld(Pk, TR_ATB + c); }
 #pragma unroll
-    for (int c = 0; c < 9; ++c) B[c] += mu_eq * K.AtA_B[c];
+    for (int c = 0; c < 9; ++c) B[c] += mu_eq * Kt.AtA_B[c];
   }
   for (int n = 0; n < J.npin; ++n) {
     const double* Pp = pend_blk(Td, O, J.pin[n]);
@@ -828,54 +867,130 @@ LOIK_DEV void ff_backward(const ModelC& c_model, const double* Ts, double* Td, c
 #pragma unroll
     for (int c = 0; c < 9; ++c) B[c] += ld(Pp, PR_H + 6 + c);
   }
-  double Mx[36], Dinv[21];
+  double Mx[K * K], Dinv[K * (K + 1) / 2], r[K];
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
+  for (int a = 0; a < K; ++a)
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      Mx[6 * a + b] = A[si(a, b)]; Mx[6 * (3 + a) + 3 + b] = D[si(a, b)];
-      Mx[6 * a + 3 + b] = B[3 * a + b]; Mx[6 * (3 + b) + a] = B[3 * a + b];
-    }
+    for (int b = 0; b < K; ++b) Mx[K * a + b] = Hel(A, B, D, s0 + a, s0 + b);
 #pragma unroll
-  for (int c = 0; c < 6; ++c) Mx[7 * c] += mu;  // armature R = mu_ineq (hxx:294-295)
-  spd6_inverse(Mx, Dinv);
+  for (int c = 0; c < K; ++c) Mx[(K + 1) * c] += mu;  // armature R = mu_ineq (hxx:294-295)
+  spd_inverse<K>(Mx, Dinv);
 #pragma unroll
-  for (int c = 0; c < 6; ++c) { st(Pj, JR_H + c, A[c]); st(Pj, JR_H + 15 + c, D[c]); st(Pj, JR_P + c, p[c]); st(Pf, FR_R + c, (w[c] - mu * z[c]) + p[c]); }
+  for (int c = 0; c < K; ++c) r[c] = (w[c] - mu * z[c]) + p[s0 + c];  // r = w - mu z (:296) + S^T p (:70)
+#pragma unroll
+  for (int c = 0; c < 6; ++c) { st(Pj, JR_H + c, A[c]); st(Pj, JR_H + 15 + c, D[c]); st(Pj, JR_P + c, p[c]); }
 #pragma unroll
   for (int c = 0; c < 9; ++c) st(Pj, JR_H + 6 + c, B[c]);
 #pragma unroll
-  for (int c = 0; c < 21; ++c) st(Pf, FR_DINV + c, Dinv[c]);
+  for (int c = 0; c < K; ++c) st(Pf, FR_R + c, r[c]);
+#pragma unroll
+  for (int c = 0; c < K * (K + 1) / 2; ++c) st(Pf, FR_DINV + c, Dinv[c]);
+  if (J.parent > 0) {
+    // UDinv = U Dinv with U = H S (columns s0 .. s0+K-1 of H); H -= UDinv U^T (:63); p -= UDinv r (:71-73)
+    double UD[6][K];
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        double sum = 0.0;
+#pragma unroll
+        for (int l = 0; l < K; ++l) sum += Hel(A, B, D, a, s0 + l) * Dinv[sk<K>(l, k)];
+        UD[a][k] = sum;
+        st(Pf, FR_UD + K * a + k, sum);
+      }
+    double U[6][K];
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int k = 0; k < K; ++k) U[a][k] = Hel(A, B, D, a, s0 + k);
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = a; b < 6; ++b) {
+        if (a < 3 && b >= 3) continue;  // the LA block is general: done below
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) sum += UD[a][k] * U[b][k];
+        Hsub(A, B, D, a, b, sum);
+      }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 3; b < 6; ++b) {
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) sum += UD[a][k] * U[b][k];
+        B[3 * a + (b - 3)] -= sum;
+      }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double sum = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) sum += UD[a][k] * r[k];
+      p[a] -= sum;
+    }
+    double R[9], t[3], cA[6], cB[9], cD[6], cp[6];
+    md_load_xf(migrate ? Pfs : Pf, R, t);
+    congruence(R, t, A, B, D, cA, cB, cD);
+    act_force(R, t, p, cp);
+    double* Pp = pend_blk(Td, O, J.pout);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { st(Pp, PR_H + c, cA[c]); st(Pp, PR_H + 15 + c, cD[c]); st(Pp, PR_H + 21 + c, cp[c]); }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) st(Pp, PR_H + 6 + c, cB[c]);
+  }
 }
 
-template <bool DEBUG>
-LOIK_DEV void ff_forward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, Carry& cy) {
+template <bool DEBUG, int K>
+LOIK_DEV_CALL void md_forward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, Carry& cy, const int i) {
   const Offs& O = c_model.off;
-  const JointC& J = c_model.j[1];
-  const int nb = c_model.nb;
-  double* Pj = joint_blk(Td, O, 0);
-  double* Pf = ff_blk(Td, O);
-  const double* Pjs = joint_blk(const_cast<double*>(Ts), O, 0);
-  const double* Pfs = ff_blk(const_cast<double*>(Ts), O);
+  const JointC& J = c_model.j[i];
+  const int nb = c_model.nb, s0 = J.sel0;
+  double* Pj = joint_blk(Td, O, i - 1);
+  double* Pf = md_blk(Td, O, J.mblk);
+  const double* Pjs = joint_blk(const_cast<double*>(Ts), O, i - 1);
+  const double* Pfs = md_blk(const_cast<double*>(Ts), O, J.mblk);
   const double inv_mu = 1.0 / mu;
-  double Dinv[21], r[6], A[6], B[9], D[6], p[6], vold[6], fold[6], v[6], f[6];
+  double Dinv[K * (K + 1) / 2], r[K], A[6], B[9], D[6], p[6], vold[6], fold[6], v[6], f[6], nu[K];
 #pragma unroll
-  for (int c = 0; c < 21; ++c) Dinv[c] = ld(Pf, FR_DINV + c);
+  for (int c = 0; c < K * (K + 1) / 2; ++c) Dinv[c] = ld(Pf, FR_DINV + c);
+#pragma unroll
+  for (int c = 0; c < K; ++c) r[c] = ld(Pf, FR_R + c);
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
-    r[c] = ld(Pf, FR_R + c); A[c] = ld(Pj, JR_H + c); D[c] = ld(Pj, JR_H + 15 + c); p[c] = ld(Pj, JR_P + c);
+    A[c] = ld(Pj, JR_H + c); D[c] = ld(Pj, JR_H + 15 + c); p[c] = ld(Pj, JR_P + c);
     vold[c] = ld(Pjs, JR_V + c); fold[c] = ld(Pjs, JR_F + c);
   }
 #pragma unroll
   for (int c = 0; c < 9; ++c) B[c] = ld(Pj, JR_H + 6 + c);
+  if (J.parent > 0) {  // vi_parent = liMi.actInv(v_parent) (:125)
+    double R[9], t[3], vin[6];
+    md_load_xf(Pf, R, t);
+    const double* Pq = joint_blk(Td, O, J.parent - 1);
 #pragma unroll
-  for (int c = 0; c < 6; ++c) {  // nu = -UDinv^T vp - Dinv r with vp = 0 (:127); v = vp + S nu = nu (:133-134)
-    double acc = 0.0;
+    for (int c = 0; c < 6; ++c) vin[c] = ld(Pq, JR_V + c);
+    actinv_motion(R, t, vin, v);
+  } else {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) acc += Dinv[s6(c, k)] * r[k];
-    v[c] = -acc;
-    cy.nu_inf = amax(cy.nu_inf, v[c]);
-    cy.dvis_inf = amax(cy.dvis_inf, v[c] - vold[c]);
+    for (int c = 0; c < 6; ++c) v[c] = 0.0;
   }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {  // nu = -UDinv^T vp - Dinv r (:127)
+    double acc = 0.0;
+    if (J.parent > 0) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) acc += ld(Pf, FR_UD + K * a + k) * v[a];
+    }
+    double dr = 0.0;
+#pragma unroll
+    for (int l = 0; l < K; ++l) dr += Dinv[sk<K>(k, l)] * r[l];
+    nu[k] = -acc - dr;
+    cy.nu_inf = amax(cy.nu_inf, nu[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[s0 + k] += nu[k];  // v_i = vp + S nu (:133-134)
+#pragma unroll
+  for (int c = 0; c < 6; ++c) cy.dvis_inf = amax(cy.dvis_inf, v[c] - vold[c]);
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     f[a] = A[si(a, 0)] * v[0] + A[si(a, 1)] * v[1] + A[si(a, 2)] * v[2] + B[3 * a] * v[3] + B[3 * a + 1] * v[4] + B[3 * a + 2] * v[5] + p[a];
@@ -884,54 +999,57 @@ LOIK_DEV void ff_forward(const ModelC& c_model, const double* Ts, double* Td, co
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     cy.dfis_inf = amax(cy.dfis_inf, f[c] - fold[c]);
-    const double lb = c_model.bounds_per_instance ? ld(Pf, FR_LB + c) : c_model.fflb[c];
-    const double ub = c_model.bounds_per_instance ? ld(Pf, FR_UB + c) : c_model.ffub[c];
-    const double nu = v[c], w_old = ld(Pfs, FR_W + c);
-    cy.dnu_inf = amax(cy.dnu_inf, nu - ld(Pfs, FR_NU + c));
-    const double z = dmin(ub, dmax(lb, nu + inv_mu * w_old));
+    st(Pj, JR_V + c, v[c]); st(Pj, JR_F + c, f[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < K; ++c) {
+    const double lb = c_model.bounds_per_instance ? ld(Pf, FR_LB + c) : c_model.mdlb[J.mblk][c];
+    const double ub = c_model.bounds_per_instance ? ld(Pf, FR_UB + c) : c_model.mdub[J.mblk][c];
+    const double w_old = ld(Pfs, FR_W + c);
+    cy.dnu_inf = amax(cy.dnu_inf, nu[c] - ld(Pfs, FR_NU + c));
+    const double z = dmin(ub, dmax(lb, nu[c] + inv_mu * w_old));
     cy.dz_inf = amax(cy.dz_inf, z - ld(Pfs, FR_Z + c));
-    const double rp = nu - z;
+    const double rp = nu[c] - z;
     cy.pres_slack = amax(cy.pres_slack, rp);
     const double dw = mu * rp;
     cy.dw_inf = amax(cy.dw_inf, dw);
     cy.ubdw_p += ub * dmax(dw, 0.0);
     cy.lbdw_m += lb * dmin(dw, 0.0);
-    st(Pj, JR_V + c, v[c]); st(Pj, JR_F + c, f[c]);
-    st(Pf, FR_NU + c, nu); st(Pf, FR_Z + c, z); st(Pf, FR_W + c, w_old + dw);
-    if (DEBUG) st(Td, O.prv + 6 * nb + c, rp);
+    st(Pf, FR_NU + c, nu[c]); st(Pf, FR_Z + c, z); st(Pf, FR_W + c, w_old + dw);
+    if (DEBUG) st(Td, O.prv + 6 * nb + J.idxv + c, rp);
   }
-  if (J.task >= 0) {  // DualUpdate for a task on the root joint (:410-451)
-    const TaskC& K = c_model.t[J.task];
+  if (J.task >= 0) {  // DualUpdate for a task on this joint (:410-451)
+    const TaskC& Kt = c_model.t[J.task];
     double* Pk = task_blk(Td, O, J.task);
     const double* Pks = task_blk(const_cast<double*>(Ts), O, J.task);
     double y[6], plus = 0.0, minus = 0.0;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
-      const double Av = K.A[6 * a] * v[0] + K.A[6 * a + 1] * v[1] + K.A[6 * a + 2] * v[2] + K.A[6 * a + 3] * v[3] + K.A[6 * a + 4] * v[4] + K.A[6 * a + 5] * v[5];
+      const double Av = Kt.A[6 * a] * v[0] + Kt.A[6 * a + 1] * v[1] + Kt.A[6 * a + 2] * v[2] + Kt.A[6 * a + 3] * v[3] + Kt.A[6 * a + 4] * v[4] + Kt.A[6 * a + 5] * v[5];
       const double bi = ld(Pk, TR_B + a), e = Av - bi, dy = mu_eq * e;
       y[a] = ld(Pks, TR_Y + a) + dy;
       cy.dyis_inf = amax(cy.dyis_inf, dy); cy.Av_inf = amax(cy.Av_inf, Av); cy.pres_task = amax(cy.pres_task, e);
       plus += bi * dmax(dy, 0.0); minus += bi * dmin(dy, 0.0);
-      if (DEBUG) st(Td, O.prv + a, e);
+      if (DEBUG) st(Td, O.prv + 6 * (i - 1) + a, e);
     }
     cy.bTdy_p += plus; cy.bTdy_m += minus;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
       st(Pk, TR_Y + a, y[a]);
-      st(Pk, TR_ATY + a, K.A[a] * y[0] + K.A[6 + a] * y[1] + K.A[12 + a] * y[2] + K.A[18 + a] * y[3] + K.A[24 + a] * y[4] + K.A[30 + a] * y[5]);
+      st(Pk, TR_ATY + a, Kt.A[a] * y[0] + Kt.A[6 + a] * y[1] + Kt.A[12 + a] * y[2] + Kt.A[18 + a] * y[3] + Kt.A[24 + a] * y[4] + Kt.A[30 + a] * y[5]);
     }
   }
 }
 
-template <bool DEBUG>
-LOIK_DEV void ff_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs) {
+template <bool DEBUG, int K>
+LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs, const int i) {
   const Offs& O = c_model.off;
-  const JointC& J = c_model.j[1];
-  const int nb = c_model.nb;
-  double* Pj = joint_blk(Td, O, 0);
-  double* Pf = ff_blk(Td, O);
-  const double* Pjs = joint_blk(const_cast<double*>(Ts), O, 0);
-  const double* Pfs = ff_blk(const_cast<double*>(Ts), O);
+  const JointC& J = c_model.j[i];
+  const int nb = c_model.nb, s0 = J.sel0;
+  double* Pj = joint_blk(Td, O, i - 1);
+  double* Pf = md_blk(Td, O, J.mblk);
+  const double* Pjs = joint_blk(const_cast<double*>(Ts), O, i - 1);
+  const double* Pfs = md_blk(const_cast<double*>(Ts), O, J.mblk);
   double f[6], v[6], F[6], Fold[6];
 #pragma unroll
   for (int c = 0; c < 6; ++c) { f[c] = ld(Pj, JR_F + c); v[c] = ld(Pj, JR_V + c); Fold[c] = ld(Pjs, JR_FD + c); F[c] = 0.0; }
@@ -959,13 +1077,54 @@ LOIK_DEV void ff_residual(const ModelC& c_model, const double* Ts, double* Td, R
     rs.Hrefv_inf = amax(rs.Hrefv_inf, Hrv[c]);
     const double rd = Hrv[c] - J.Hv[c] + F[c];
     rs.dres_v = amax(rs.dres_v, rd);
-    const double Tn = f[c] + ld(Pf, FR_W + c);  // S^T f + w with S = I (:231)
+    st(Pj, JR_FD + c, F[c]);
+    if (DEBUG) st(Td, O.drv + 6 * (i - 1) + c, rd);
+  }
+#pragma unroll
+  for (int c = 0; c < K; ++c) {
+    const double Tn = f[s0 + c] + ld(Pf, FR_W + c);  // S^T f + w (:231)
     rs.T_inf = amax(rs.T_inf, Tn);
     rs.dT_inf = amax(rs.dT_inf, Tn - ld(Pfs, FR_T + c));
-    st(Pj, JR_FD + c, F[c]);
     st(Pf, FR_T + c, Tn);
-    if (DEBUG) { st(Td, O.drv + c, rd); st(Td, O.drv + 6 * nb + c, Tn); }
+    if (DEBUG) st(Td, O.drv + 6 * nb + J.idxv + c, Tn);
   }
+  if (J.parent > 0) {  // fis_diff_plus_Aty[parent] += liMi.act(f_i) (:212)
+    double R[9], t[3], cF[6];
+    md_load_xf(Pf, R, t);
+    act_force(R, t, f, cF);
+    double* Pp = pend_blk(Td, O, J.pout);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) st(Pp, PR_F + c, cF[c]);
+  }
+}
+
+// The three sweeps over the joints lo..hi, multi-DoF joints included (lo == hi for those).  The running norms travel
+// to the out-of-line multi-DoF steps through a local copy, so that they stay in registers in the joint loops.
+LOIK_DEV void span_backward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, const int lo,
+                            const int hi, const bool migrate) {
+  const int k = c_model.j[lo].nvj;
+  if (k == 1) sweep_backward(c_model, Ts, Td, mu, mu_eq, lo, hi, migrate);
+  else if (k == 3) md_backward<3>(c_model, Ts, Td, mu, mu_eq, lo, migrate);
+  else md_backward<6>(c_model, Ts, Td, mu, mu_eq, lo, migrate);
+}
+template <bool DEBUG>
+LOIK_DEV void span_forward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, Carry& cy,
+                           const int lo, const int hi) {
+  const int k = c_model.j[lo].nvj;
+  if (k == 1) { sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, lo, hi); return; }
+  Carry tmp = cy;
+  if (k == 3) md_forward<DEBUG, 3>(c_model, Ts, Td, mu, mu_eq, tmp, lo);
+  else md_forward<DEBUG, 6>(c_model, Ts, Td, mu, mu_eq, tmp, lo);
+  cy = tmp;
+}
+template <bool DEBUG>
+LOIK_DEV void span_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs, const int lo, const int hi) {
+  const int k = c_model.j[lo].nvj;
+  if (k == 1) { sweep_residual<DEBUG>(c_model, Ts, Td, rs, lo, hi); return; }
+  Resid tmp = rs;
+  if (k == 3) md_residual<DEBUG, 3>(c_model, Ts, Td, tmp, lo);
+  else md_residual<DEBUG, 6>(c_model, Ts, Td, tmp, lo);
+  rs = tmp;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -49,9 +49,9 @@ LOIK_DEV void retire_rows(const ModelC& c_model, const double* Ts, double* Th) {
 #pragma unroll
     for (int r = 0; r < JR_JQ; ++r) st(Pd, r, tmp[r]);
   }
-  if (c_model.has_ff) {
-    const double* Ps = ff_blk(const_cast<double*>(Ts), O);
-    double* Pd = ff_blk(Th, O);
+  for (int m = 0; m < c_model.nmd; ++m) {
+    const double* Ps = md_blk(const_cast<double*>(Ts), O, m);
+    double* Pd = md_blk(Th, O, m);
     for (int r = 0; r < FR_LB; ++r) st(Pd, r, ld(Ps, r));  // nu, z, w, T
   }
   for (int t = 0; t < nc; ++t) {
@@ -90,7 +90,9 @@ LOIK_DEV void claim_next(const StateP& S, const bool active, const int slot_now)
 // migrating launch, S.dst set -- read there during the first iteration and written to slot k of S.dst: the physical
 // re-pack of the still-active instances into full tiles costs no pass of its own.
 // MINB = resident CTAs per SM the kernel is compiled for -> register cap 65536 / (64 MINB), rounded down to 8
-template <bool DEBUG, int MINB>
+// MD: the model has multi-DoF joints (span-level dispatch, out-of-line steps); the 1-DoF-only instantiation is the
+// plain joint loops, untouched by that machinery (it is the kernel every BASELINE robot runs).
+template <bool DEBUG, int MINB, bool MD = false>
 __global__ void __launch_bounds__(kBlock) __maxnreg__(MINB <= 4 ? 255 : (65536 / (kBlock * MINB)) / 8 * 8) k_iterate(const __grid_constant__ ModelC c_model, const StateP S, const int iters, const int fixed) {
   const int limit = S.list ? *S.n_list : (S.n_dev ? *S.n_dev : S.n);
   const int stride = gridDim.x * blockDim.x;
@@ -107,23 +109,25 @@ __global__ void __launch_bounds__(kBlock) __maxnreg__(MINB <= 4 ? 255 : (65536 /
     if (status < ST_CONVERGED) {
       int it = ctl.y;
       double mu = ld(glob_blk(const_cast<double*>(Ts), c_model.off), GR_MU);
-      const int nb = c_model.nb;
       bool migrate = MIG;  // the first iteration of a migrating launch reads at Ts and writes at Td
       if (MIG) { migrate_globals(c_model, Ts, Td); S.origin_dst[k] = S.origin_src ? S.origin_src[s] : s; }
       for (int n = 0; n < iters; ++n) {
         ++it;
         const double mu_eq = c_model.mu_scale * mu;
-        const int lo = c_model.has_ff ? 2 : 1;  // a free-flyer root joint is handled outside the joint loops
-        sweep_backward(c_model, Ts, Td, mu, mu_eq, lo, nb, migrate);
-        if (c_model.has_ff) ff_backward(c_model, Ts, Td, mu, mu_eq, migrate);
         Carry cy;
-        zero(cy);
-        if (c_model.has_ff) ff_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy);
-        sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, lo, nb);
         Resid rs;
+        zero(cy);
         zero(rs);
-        sweep_residual<DEBUG>(c_model, Ts, Td, rs, lo, nb);
-        if (c_model.has_ff) ff_residual<DEBUG>(c_model, Ts, Td, rs);
+        if (MD) {
+          for (int g = c_model.nspan - 1; g >= 0; --g) span_backward(c_model, Ts, Td, mu, mu_eq, c_model.span[g].lo, c_model.span[g].hi, migrate);
+          for (int g = 0; g < c_model.nspan; ++g) span_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, c_model.span[g].lo, c_model.span[g].hi);
+          for (int g = c_model.nspan - 1; g >= 0; --g) span_residual<DEBUG>(c_model, Ts, Td, rs, c_model.span[g].lo, c_model.span[g].hi);
+        } else {
+          const int nb = c_model.nb;
+          sweep_backward(c_model, Ts, Td, mu, mu_eq, 1, nb, migrate);
+          sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, 1, nb);
+          sweep_residual<DEBUG>(c_model, Ts, Td, rs, 1, nb);
+        }
         status = decide<DEBUG>(c_model, Td, status, it, fixed != 0, cy, rs, mu);
         Ts = Td; migrate = false;
         if (status >= ST_CONVERGED) break;
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(kBlock) __maxnreg__(MINB <= 4 ? 255 : (65536 /
 // chains (segments) of the tree assigned to it; chains only exchange data through pending blocks / the parent's v
 // row in HBM/L2, ordered by CTA barriers between the levels of the segment DAG.  The running norms are combined
 // through shared memory in a fixed warp order, after which every warp takes the same decisions redundantly.
-template <bool DEBUG, int NW>
+template <bool DEBUG, int NW, bool MD = false>
 __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
     k_iterate_seg(const __grid_constant__ ModelC c_model, const StateP S, const int iters, const int fixed) {
   constexpr int NP = kCarryRows + 7;
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
         if (alive)
           for (int g = 0; g < c_model.nseg; ++g)
             if (c_model.seg[g].bwarp == w && c_model.seg[g].blevel == lv) {
-              if (c_model.has_ff && c_model.seg[g].lo == 1) ff_backward(c_model, Ts, Td, mu, mu_eq, migrate);
+              if (MD) span_backward(c_model, Ts, Td, mu, mu_eq, c_model.seg[g].lo, c_model.seg[g].hi, migrate);
               else sweep_backward(c_model, Ts, Td, mu, mu_eq, c_model.seg[g].lo, c_model.seg[g].hi, migrate);
             }
         __syncthreads();
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
         if (alive)
           for (int g = 0; g < c_model.nseg; ++g)
             if (c_model.seg[g].fwarp == w && c_model.seg[g].flevel == lv) {
-              if (c_model.has_ff && c_model.seg[g].lo == 1) ff_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy);
+              if (MD) span_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, c_model.seg[g].lo, c_model.seg[g].hi);
               else sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, c_model.seg[g].lo, c_model.seg[g].hi);
             }
         __syncthreads();
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
         if (alive)
           for (int g = 0; g < c_model.nseg; ++g)
             if (c_model.seg[g].bwarp == w && c_model.seg[g].blevel == lv) {
-              if (c_model.has_ff && c_model.seg[g].lo == 1) ff_residual<DEBUG>(c_model, Ts, Td, rs);
+              if (MD) span_residual<DEBUG>(c_model, Ts, Td, rs, c_model.seg[g].lo, c_model.seg[g].hi);
               else sweep_residual<DEBUG>(c_model, Ts, Td, rs, c_model.seg[g].lo, c_model.seg[g].hi);
             }
         __syncthreads();
@@ -299,8 +303,7 @@ __global__ void __launch_bounds__(kBlock) k_step_backward(const __grid_constant_
   double* T = tile_ptr(S, c_model, s);
   if (ld_ctl(c_model, T).x >= ST_CONVERGED) return;
   const double mu = ld(glob_blk(T, c_model.off), GR_MU);
-  sweep_backward(c_model, T, T, mu, c_model.mu_scale * mu, c_model.has_ff ? 2 : 1, c_model.nb);
-  if (c_model.has_ff) ff_backward(c_model, T, T, mu, c_model.mu_scale * mu);
+  for (int g = c_model.nspan - 1; g >= 0; --g) span_backward(c_model, T, T, mu, c_model.mu_scale * mu, c_model.span[g].lo, c_model.span[g].hi, false);
 }
 __global__ void __launch_bounds__(kBlock) k_step_forward(const __grid_constant__ ModelC c_model, const StateP S) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,8 +314,7 @@ __global__ void __launch_bounds__(kBlock) k_step_forward(const __grid_constant__
   const double mu = ld(G, GR_MU);
   Carry cy;
   zero(cy);
-  if (c_model.has_ff) ff_forward<true>(c_model, T, T, mu, c_model.mu_scale * mu, cy);
-  sweep_forward<true>(c_model, T, T, mu, c_model.mu_scale * mu, cy, c_model.has_ff ? 2 : 1, c_model.nb);
+  for (int g = 0; g < c_model.nspan; ++g) span_forward<true>(c_model, T, T, mu, c_model.mu_scale * mu, cy, c_model.span[g].lo, c_model.span[g].hi);
   const double* c = reinterpret_cast<const double*>(&cy);
   for (int k = 0; k < kCarryRows; ++k) st(G, GR_CARRY + k, c[k]);
   // ComputePrimalResiduals (hxx:494-503)
@@ -333,8 +335,7 @@ __global__ void __launch_bounds__(kBlock) k_step_residual(const __grid_constant_
   for (int k = 0; k < kCarryRows; ++k) c[k] = ld(G, GR_CARRY + k);
   Resid rs;
   zero(rs);
-  sweep_residual<true>(c_model, T, T, rs, c_model.has_ff ? 2 : 1, c_model.nb);
-  if (c_model.has_ff) ff_residual<true>(c_model, T, T, rs);
+  for (int g = c_model.nspan - 1; g >= 0; --g) span_residual<true>(c_model, T, T, rs, c_model.span[g].lo, c_model.span[g].hi);
   double mu = ld(G, GR_MU);
   const int it = ctl.y + 1;
   status = decide<true>(c_model, T, status, it, fixed != 0, cy, rs, mu);
@@ -379,8 +380,8 @@ __global__ void k_reset(const __grid_constant__ ModelC c_model, const StateP S, 
     if (flags & RST_VFF)
       for (int c = 0; c < 6; ++c) { st(Pj, JR_V + c, 0.0); st(Pj, JR_F + c, 0.0); st(Pj, JR_FD + c, 0.0); }
   }
-  if (c_model.has_ff) {
-    double* Pf = ff_blk(T, O);
+  for (int m = 0; m < c_model.nmd; ++m) {
+    double* Pf = md_blk(T, O, m);
     for (int c = 0; c < 6; ++c) {
       if (flags & RST_WZ) { st(Pf, FR_W + c, 0.0); st(Pf, FR_Z + c, 0.0); }
       if (flags & RST_NU) st(Pf, FR_NU + c, 0.0);
@@ -411,10 +412,30 @@ __global__ void __launch_bounds__(kBlock) k_set_q(const __grid_constant__ ModelC
   const int s = s0 + threadIdx.x;
   if (s >= S.n) return;
   double* T = tile_ptr(S, c_model, s);
-  if (c_model.has_ff)  // the root pose does not enter the velocity-level problem (nothing above the root is read); keep q
-    for (int c = 0; c < 7; ++c) st(ff_blk(T, c_model.off), FR_Q + c, sh[threadIdx.x * nq + c]);
-  for (int i = c_model.has_ff ? 2 : 1; i <= nb; ++i) {
+  for (int i = 1; i <= nb; ++i) {
     const int jt = c_model.j[i].jtype;
+    if (c_model.j[i].nvj > 1) {  // multi-DoF joint: keep q, liMi = placement * M(q) (hxx:263-264) into the md block
+      const JointC& J = c_model.j[i];
+      const double* qj = sh + threadIdx.x * nq + J.idxq;
+      double* Pf = md_blk(T, c_model.off, J.mblk);
+      const int nqj = jt == LOIK_JOINT_FF ? 7 : (jt == LOIK_JOINT_SPHERICAL ? 4 : 3);
+      for (int c = 0; c < nqj; ++c) st(Pf, FR_Q + c, qj[c]);
+      double M[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pq[3] = {0, 0, 0};
+      if (jt != LOIK_JOINT_TRANSLATION) {
+        const int o = jt == LOIK_JOINT_FF ? 3 : 0;
+        const double x = qj[o], y = qj[o + 1], z = qj[o + 2], w = qj[o + 3];
+        M[0] = 1 - 2 * (y * y + z * z); M[1] = 2 * (x * y - z * w); M[2] = 2 * (x * z + y * w);
+        M[3] = 2 * (x * y + z * w); M[4] = 1 - 2 * (x * x + z * z); M[5] = 2 * (y * z - x * w);
+        M[6] = 2 * (x * z - y * w); M[7] = 2 * (y * z + x * w); M[8] = 1 - 2 * (x * x + y * y);
+      }
+      if (jt != LOIK_JOINT_SPHERICAL) { pq[0] = qj[0]; pq[1] = qj[1]; pq[2] = qj[2]; }
+      const double* P = J.plR;
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) st(Pf, FR_XF + 3 * a + b, P[3 * a] * M[b] + P[3 * a + 1] * M[3 + b] + P[3 * a + 2] * M[6 + b]);
+        st(Pf, FR_XF + 9 + a, J.plp[a] + (P[3 * a] * pq[0] + P[3 * a + 1] * pq[1] + P[3 * a + 2] * pq[2]));
+      }
+      continue;
+    }
     const double qi = sh[threadIdx.x * nq + c_model.j[i].idxq];
     double a, b;
     if (c_model.j[i].qkind == 1) { b = qi; a = sh[threadIdx.x * nq + c_model.j[i].idxq + 1]; }  // q = (cos, sin), used as given (JointModelRevoluteUnbounded*::calc)
@@ -437,6 +458,14 @@ __global__ void __launch_bounds__(128) k_integrate(const __grid_constant__ Model
   for (int i = 1; i <= nb; ++i) {
     double* Pj = joint_blk(T, c_model.off, i - 1);
     const int jt = c_model.j[i].jtype;
+    if (c_model.j[i].nvj > 1) {  // translation joint (vector space): q += dt z, liMi translation = placement.p + placement.R q
+      const JointC& J = c_model.j[i];
+      double* Pf = md_blk(T, c_model.off, J.mblk);
+      double qn[3];
+      for (int c = 0; c < 3; ++c) { qn[c] = ld(Pf, FR_Q + c) + dt * ld(Pf, FR_Z + c); st(Pf, FR_Q + c, qn[c]); }
+      for (int a = 0; a < 3; ++a) st(Pf, FR_XF + 9 + a, J.plp[a] + (J.plR[3 * a] * qn[0] + J.plR[3 * a + 1] * qn[1] + J.plR[3 * a + 2] * qn[2]));
+      continue;
+    }
     if (c_model.j[i].qkind == 1) {
       // SpecialOrthogonalOperationTpl<2>::integrate_impl: rotate (cos, sin) by omega = dt z, then the first-order
       // renormalisation out *= (3 - |out|^2) / 2
@@ -496,9 +525,12 @@ __global__ void k_set_bounds(const __grid_constant__ ModelC c_model, const State
   if (s >= S.n) return;
   double* T = tile_ptr(S, c_model, s);
   const int nb = c_model.nb, nv = c_model.nv;
-  if (c_model.has_ff)
-    for (int c = 0; c < 6; ++c) { st(ff_blk(T, c_model.off), FR_LB + c, lb[(size_t)s * nv + c]); st(ff_blk(T, c_model.off), FR_UB + c, ub[(size_t)s * nv + c]); }
-  for (int i = c_model.has_ff ? 2 : 1; i <= nb; ++i) {
+  for (int i = 1; i <= nb; ++i) {
+    if (c_model.j[i].nvj > 1) {
+      double* Pf = md_blk(T, c_model.off, c_model.j[i].mblk);
+      for (int c = 0; c < c_model.j[i].nvj; ++c) { st(Pf, FR_LB + c, lb[(size_t)s * nv + c_model.j[i].idxv + c]); st(Pf, FR_UB + c, ub[(size_t)s * nv + c_model.j[i].idxv + c]); }
+      continue;
+    }
     double* Pj = joint_blk(T, c_model.off, i - 1);
     st(Pj, JR_LB, lb[(size_t)s * nv + c_model.j[i].idxv]);
     st(Pj, JR_UB, ub[(size_t)s * nv + c_model.j[i].idxv]);
@@ -518,22 +550,11 @@ __global__ void k_gather_limi(const __grid_constant__ ModelC c_model, const Stat
   if (s >= S.n) return;
   const double* T = tile_ptr(S, c_model, s);
   const int nb = c_model.nb;
-  if (c_model.has_ff) {  // liMi[1] = jointPlacement * (R(quat), p)
-    const double* Pf = ff_blk(const_cast<double*>(T), c_model.off);
-    const double x = ld(Pf, FR_Q + 3), y = ld(Pf, FR_Q + 4), z = ld(Pf, FR_Q + 5), w = ld(Pf, FR_Q + 6);
-    const double M[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w), 1 - 2 * (x * x + z * z),
-                         2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
-    const double* P = c_model.j[1].plR;
-    double* o = dst + (size_t)s * nb * 12;
-    for (int a = 0; a < 3; ++a) {
-      for (int b = 0; b < 3; ++b) o[3 * a + b] = P[3 * a] * M[b] + P[3 * a + 1] * M[3 + b] + P[3 * a + 2] * M[6 + b];
-      o[9 + a] = c_model.j[1].plp[a] + P[3 * a] * ld(Pf, FR_Q) + P[3 * a + 1] * ld(Pf, FR_Q + 1) + P[3 * a + 2] * ld(Pf, FR_Q + 2);
-    }
-  }
-  for (int i = c_model.has_ff ? 2 : 1; i <= nb; ++i) {
+  for (int i = 1; i <= nb; ++i) {
     double R[9], t[3];
     const double* Pj = joint_blk(const_cast<double*>(T), c_model.off, i - 1);
-    make_xf(c_model.j[i], ld(Pj, JR_JQ), ld(Pj, JR_JQ + 1), R, t);
+    if (c_model.j[i].nvj > 1) md_load_xf(md_blk(const_cast<double*>(T), c_model.off, c_model.j[i].mblk), R, t);
+    else make_xf(c_model.j[i], ld(Pj, JR_JQ), ld(Pj, JR_JQ + 1), R, t);
     double* o = dst + ((size_t)s * nb + (i - 1)) * 12;
     for (int c = 0; c < 9; ++c) o[c] = R[c];
     for (int c = 0; c < 3; ++c) o[9 + c] = t[c];
@@ -642,23 +663,31 @@ static inline int grid_for(int n, int block = kBlock) { return (n + block - 1) /
 static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S, int iters, int fixed, int max_ctas = 0, bool seg = true) {
   int g = grid_for(h->batch);
   if (max_ctas > 0) g = std::min(g, max_ctas);
+  const bool md = h->mc.nmd > 0;  // multi-DoF joints: the instantiations with the span-level dispatch
   if (seg && h->mc.nwarp > 1 && !h->debug) {  // segment-parallel: one CTA (nwarp warps) per tile
     int gt = h->ntiles;
     if (max_ctas > 0) gt = std::min(gt, max_ctas);
+#define LOIK_LAUNCH_SEG(NW_)                                                                       \
+  do {                                                                                             \
+    if (md) k_iterate_seg<false, NW_, true><<<gt, 32 * NW_, 0, st>>>(h->mc, S, iters, fixed);      \
+    else k_iterate_seg<false, NW_, false><<<gt, 32 * NW_, 0, st>>>(h->mc, S, iters, fixed);        \
+  } while (0)
     switch (h->mc.nwarp) {
-      case 2: k_iterate_seg<false, 2><<<gt, 64, 0, st>>>(h->mc, S, iters, fixed); break;
-      case 3: k_iterate_seg<false, 3><<<gt, 96, 0, st>>>(h->mc, S, iters, fixed); break;
-      default: k_iterate_seg<false, 4><<<gt, 128, 0, st>>>(h->mc, S, iters, fixed); break;
+      case 2: LOIK_LAUNCH_SEG(2); break;
+      case 3: LOIK_LAUNCH_SEG(3); break;
+      default: LOIK_LAUNCH_SEG(4); break;
     }
+#undef LOIK_LAUNCH_SEG
     h->launches++;
     return;
   }
-#define LOIK_LAUNCH(DBG, MB) k_iterate<DBG, MB><<<g, kBlock, 0, st>>>(h->mc, S, iters, fixed)
-  if (h->debug) { LOIK_LAUNCH(true, 4); }
-  else if (h->minb == 4) { LOIK_LAUNCH(false, 4); }
-  else if (h->minb == 5) { LOIK_LAUNCH(false, 5); }
-  else if (h->minb == 6) { LOIK_LAUNCH(false, 6); }
-  else { LOIK_LAUNCH(false, 8); }
+#define LOIK_LAUNCH(DBG, MB, MD_) k_iterate<DBG, MB, MD_><<<g, kBlock, 0, st>>>(h->mc, S, iters, fixed)
+  if (h->debug) { if (md) LOIK_LAUNCH(true, 4, true); else LOIK_LAUNCH(true, 4, false); }
+  else if (md) { LOIK_LAUNCH(false, 4, true); }
+  else if (h->minb == 4) { LOIK_LAUNCH(false, 4, false); }
+  else if (h->minb == 5) { LOIK_LAUNCH(false, 5, false); }
+  else if (h->minb == 6) { LOIK_LAUNCH(false, 6, false); }
+  else { LOIK_LAUNCH(false, 8, false); }
 #undef LOIK_LAUNCH
   h->launches++;
 }
@@ -727,10 +756,14 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   if (batch < 1) return fail(LOIK_ERR_INVALID, "loik_create: batch must be >= 1");
   for (int i = 1; i < nj; ++i) {
     if (model->parents[i] < 0 || model->parents[i] >= i) return fail(LOIK_ERR_INVALID, "loik_create: parents[i] must be < i");
-    if (model->joint_types[i] < 0 || model->joint_types[i] > LOIK_JOINT_RUBU)
-      return fail(LOIK_ERR_UNSUPPORTED, "loik_create: unsupported joint type (1-DoF revolute/prismatic joints and a free-flyer root are supported)");
-    if (model->joint_types[i] == LOIK_JOINT_FF && !(i == 1 && model->parents[i] == 0))
-      return fail(LOIK_ERR_UNSUPPORTED, "loik_create: a free-flyer joint is supported as the root joint (joint 1, parent 0) only");
+    if (model->joint_types[i] < 0 || model->joint_types[i] > LOIK_JOINT_TRANSLATION)
+      return fail(LOIK_ERR_UNSUPPORTED, "loik_create: unsupported joint type (1-DoF revolute/prismatic joints, free-flyer, spherical and translation joints are supported)");
+  }
+  auto nv_of = [&](int i) { const int t = model->joint_types[i]; return t == LOIK_JOINT_FF ? 6 : ((t == LOIK_JOINT_SPHERICAL || t == LOIK_JOINT_TRANSLATION) ? 3 : 1); };
+  {
+    int nmd = 0;
+    for (int i = 1; i < nj; ++i) nmd += nv_of(i) > 1;
+    if (nmd > kMaxMd) return fail(LOIK_ERR_UNSUPPORTED, "loik_create: more multi-DoF joints than kMaxMd");
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LOIK_ERR_CUDA, "loik_create: no CUDA device (libloik_b200 has no CPU fallback)");
@@ -738,11 +771,13 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   loik_solver* h = new loik_solver();
   h->device = device; h->batch = batch; h->ntiles = (batch + 31) / 32;
   h->nj = nj; h->nb = nj - 1; h->nc = params->num_eq_c; h->prm = *params;
-  const bool has_ff = model->joint_types[1] == LOIK_JOINT_FF;
   auto unbounded = [&](int i) { return model->joint_types[i] >= LOIK_JOINT_RUBX && model->joint_types[i] <= LOIK_JOINT_RUBU; };
-  h->nv = nj - 1 + (has_ff ? 5 : 0);
-  h->nq = 0;
-  for (int i = 1; i < nj; ++i) h->nq += model->joint_types[i] == LOIK_JOINT_FF ? 7 : (unbounded(i) ? 2 : 1);
+  auto nq_of = [&](int i) {
+    const int t = model->joint_types[i];
+    return t == LOIK_JOINT_FF ? 7 : (t == LOIK_JOINT_SPHERICAL ? 4 : (t == LOIK_JOINT_TRANSLATION ? 3 : (unbounded(i) ? 2 : 1)));
+  };
+  h->nv = 0; h->nq = 0;
+  for (int i = 1; i < nj; ++i) { h->nv += nv_of(i); h->nq += nq_of(i); }
   h->minb = 4;
   if (const char* e = std::getenv("LOIK_DENSE")) { const int v = std::atoi(e); if (v >= 0) h->dense_sweeps = v; }
   if (const char* e = std::getenv("LOIK_NO_GRAPH")) { if (std::atoi(e) != 0) h->use_graph = false; }
@@ -756,7 +791,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   ModelC& M = h->mc;
   std::memset(&M, 0, sizeof(M));
   M.nj = nj; M.nb = nj - 1; M.nc = h->nc;
-  M.has_ff = has_ff ? 1 : 0; M.nv = h->nv; M.nq = h->nq;
+  M.nv = h->nv; M.nq = h->nq;
   M.max_iter = params->max_iter; M.rho = params->rho; M.mu0 = params->mu; M.mu_scale = params->mu_equality_scale_factor;
   M.tol_abs = params->tol_abs; M.tol_rel = params->tol_rel; M.tol_pinf = params->tol_primal_inf; M.tol_dinf = params->tol_dual_inf;
   M.tol_tail = params->tol_tail_solve;
@@ -765,17 +800,18 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   // Maximal register-carried chains are the segments that different warps can sweep (k_iterate_seg).
   std::vector<int> nchild(nj, 0);
   for (int i = 1; i < nj; ++i) nchild[model->parents[i]]++;
-  int npend = 0, idxq = 0;
+  int npend = 0, idxq = 0, idxv = 0, nmd = 0;
   for (int i = 1; i < nj; ++i) {
     JointC& J = M.j[i];
     J.parent = model->parents[i]; J.jtype = model->joint_types[i]; J.task = -1;
     for (int c = 0; c < 9; ++c) J.plR[c] = model->placement_R[9 * i + c];
     for (int c = 0; c < 3; ++c) { J.plp[c] = model->placement_p[3 * i + c]; J.axis[c] = model->joint_axes[3 * i + c]; }
-    // (edges into a free-flyer root always go through a pending block: it is handled outside the joint loops)
-    J.carry = (J.parent > 0 && J.parent == i - 1 && nchild[J.parent] == 1 && model->joint_types[J.parent] != LOIK_JOINT_FF) ? 1 : 0;
+    // (every edge into or out of a multi-DoF joint goes through a pending block: those joints have their own step)
+    J.carry = (J.parent > 0 && J.parent == i - 1 && nchild[J.parent] == 1 && nv_of(J.parent) == 1 && nv_of(i) == 1) ? 1 : 0;
     J.pout = -1; J.npin = 0;
-    J.idxv = (i - 1) + ((has_ff && i > 1) ? 5 : 0);
-    J.idxq = idxq; idxq += model->joint_types[i] == LOIK_JOINT_FF ? 7 : (unbounded(i) ? 2 : 1);
+    J.nvj = nv_of(i); J.sel0 = model->joint_types[i] == LOIK_JOINT_SPHERICAL ? 3 : 0; J.mblk = J.nvj > 1 ? nmd++ : -1;
+    J.idxv = idxv; idxv += J.nvj;
+    J.idxq = idxq; idxq += nq_of(i);
     J.qkind = unbounded(i) ? 1 : 0;
     // an unbounded revolute joint is its bounded twin everywhere but in how q enters (k_set_q, k_integrate, the q getter)
     if (unbounded(i)) J.jtype = model->joint_types[i] == LOIK_JOINT_RUBU ? LOIK_JOINT_RU : model->joint_types[i] - LOIK_JOINT_RUBX;
@@ -790,7 +826,13 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
       ++npend;
     }
   }
-  M.npend = npend; h->npend = npend;
+  M.npend = npend; h->npend = npend; M.nmd = nmd;
+  M.nspan = 0;
+  for (int i = 1; i < nj; ++i) {
+    if (M.j[i].nvj > 1) M.span[M.nspan++] = SpanC{(short)i, (short)i, (short)M.j[i].nvj, 0};
+    else if (M.nspan > 0 && M.span[M.nspan - 1].md == 0) M.span[M.nspan - 1].hi = (short)i;
+    else M.span[M.nspan++] = SpanC{(short)i, (short)i, 0, 0};
+  }
   {
     std::vector<int> seg_of(nj, -1), lo, hi;
     for (int i = 1; i < nj; ++i) {
@@ -850,7 +892,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   O.joint0 = rows; rows += JR_ROWS * nb;
   O.task0 = rows; rows += TR_ROWS * nc;
   O.pend0 = rows; rows += PR_ROWS * std::max(npend, 1);
-  O.ff0 = rows; rows += has_ff ? FR_ROWS : 0;
+  O.ff0 = rows; rows += FR_ROWS * nmd;
   O.prv = rows; rows += 6 * nb + h->nv;
   O.drv = rows; rows += 6 * nb + h->nv;
   O.rows = rows;
@@ -868,12 +910,12 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
     // one row per dof: the free-flyer root contributes 6 rows of its own block (fr < 0: no such quantity -> zeros)
     auto per_dof = [&](std::vector<int>& m, int jr, int fr) {
       for (int j = 0; j < nb; ++j) {
-        if (has_ff && j == 0) { for (int c = 0; c < 6; ++c) m.push_back(fr < 0 ? -1 : O.ff0 + fr + c); }
+        if (M.j[j + 1].nvj > 1) { for (int c = 0; c < M.j[j + 1].nvj; ++c) m.push_back(fr < 0 ? -1 : O.ff0 + FR_ROWS * M.j[j + 1].mblk + fr + c); }
         else m.push_back(O.joint0 + JR_ROWS * j + jr);
       }
     };
     auto per_joint_noff = [&](std::vector<int>& m, int jr, int width) {
-      for (int j = 0; j < nb; ++j) for (int c = 0; c < width; ++c) m.push_back((has_ff && j == 0) ? -1 : O.joint0 + JR_ROWS * j + jr + c);
+      for (int j = 0; j < nb; ++j) for (int c = 0; c < width; ++c) m.push_back(M.j[j + 1].nvj > 1 ? -1 : O.joint0 + JR_ROWS * j + jr + c);
     };
     auto per_task = [&](std::vector<int>& m, int tr) { for (int k = 0; k < ncq; ++k) for (int c = 0; c < 6; ++c) m.push_back(O.task0 + TR_ROWS * k + tr + c); };
     auto span = [&](std::vector<int>& m, int r0, int n) { for (int c = 0; c < n; ++c) m.push_back(r0 + c); };
@@ -900,7 +942,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
         case LOIK_F_DUAL_RES_VEC: span(m, O.drv, 6 * nb + h->nv); break;
         case LOIK_F_Q:
           for (int j = 0; j < nb; ++j) {
-            if (has_ff && j == 0) { for (int c = 0; c < 7; ++c) m.push_back(O.ff0 + FR_Q + c); }
+            if (M.j[j + 1].nvj > 1) { for (int c = 0; c < nq_of(j + 1); ++c) m.push_back(O.ff0 + FR_ROWS * M.j[j + 1].mblk + FR_Q + c); }
             else if (M.j[j + 1].qkind == 1) { m.push_back(O.joint0 + JR_ROWS * j + JR_JQ + 1); m.push_back(O.joint0 + JR_ROWS * j + JR_JQ); }  // (cos, sin)
             else m.push_back(O.joint0 + JR_ROWS * j + JR_Q);
           }
@@ -980,7 +1022,10 @@ static int set_problem_consts(loik_solver* h, const double* H_ref, const double*
   double hv_inf = 0; for (int i = 0; i < 6; ++i) hv_inf = std::max(hv_inf, std::fabs(Hv[i]));
   M.Hv_inf = hv_inf;  // = |Hv[0]|inf (ik-id-description-optimized.hpp:95)
   M.bounds_per_instance = bounds_shared ? 0 : 1;
-  if (M.has_ff && bounds_shared) for (int c = 0; c < 6; ++c) { M.fflb[c] = lb[c]; M.ffub[c] = ub[c]; }
+  if (bounds_shared)
+    for (int i = 1; i < h->nj; ++i)
+      if (M.j[i].nvj > 1)
+        for (int c = 0; c < M.j[i].nvj; ++c) { M.mdlb[M.j[i].mblk][c] = lb[M.j[i].idxv + c]; M.mdub[M.j[i].mblk][c] = ub[M.j[i].idxv + c]; }
   for (int i = 1; i < h->nj; ++i) {
     JointC& J = M.j[i];
     sym_blocks(H_ref, J.HrA, J.HrB, J.HrD);
@@ -1280,7 +1325,9 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
 int loik_integrate(loik_solver* h, double dt, void* stream) {
   if (!h) return fail(LOIK_ERR_INVALID, "null handle");
   if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_integrate: call loik_solve_init first");
-  if (h->mc.has_ff) return fail(LOIK_ERR_UNSUPPORTED, "loik_integrate: free-flyer root joints are not supported yet (SE3 exponential)");
+  for (int i = 1; i < h->nj; ++i)
+    if (h->mc.j[i].nvj > 1 && h->mc.j[i].jtype != LOIK_JOINT_TRANSLATION)
+      return fail(LOIK_ERR_UNSUPPORTED, "loik_integrate: free-flyer / spherical joints are not supported yet (SE3 / SO3 exponential)");
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
   k_integrate<<<grid_for(h->batch, 128), 128, 0, st>>>(h->mc, h->S, dt);
@@ -1361,7 +1408,7 @@ int loik_step(loik_solver* h, int32_t step_id, void* stream) {
     case LOIK_STEP_BOX_PROJ: case LOIK_STEP_DUAL_UPDATE: case LOIK_STEP_COMPUTE_RESIDUALS: case LOIK_STEP_CHECK_CONVERGENCE:
     case LOIK_STEP_CHECK_FEASIBILITY: case LOIK_STEP_UPDATE_MU:
       if (!h->debug) return fail(LOIK_ERR_STATE, "loik_step: the per-method steps need loik_set_debug(h, 1)");
-      if (h->mc.has_ff) return fail(LOIK_ERR_UNSUPPORTED, "loik_step: the per-method steps do not support a free-flyer root (use the fused steps)");
+      if (h->mc.nmd > 0) return fail(LOIK_ERR_UNSUPPORTED, "loik_step: the per-method steps do not support multi-DoF joints (use the fused steps)");
       k_fine<<<g, kBlock, 0, st>>>(h->mc, h->S, step_id);
       break;
     default: return fail(LOIK_ERR_INVALID, "loik_step: unknown step id");

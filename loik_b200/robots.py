@@ -14,12 +14,12 @@ Joint type codes (shared with ``include/loik_b200.h`` and ``oracle/loik_oracle.c
     3,4,5  prismatic along +x,+y,+z  (JointModelPX/PY/PZ)
     6      revolute, unaligned axis  (JointModelRevoluteUnaligned)
     7      prismatic, unaligned axis (JointModelPrismaticUnaligned)
-    8      free-flyer (JointModelFreeFlyer, nq = 7, nv = 6) -- supported as the root joint (joint 1, parent 0) only
+    8      free-flyer (JointModelFreeFlyer, nq = 7 = x y z qx qy qz qw, nv = 6)
     9,10,11 unbounded revolute about +x,+y,+z (JointModelRUBX/RUBY/RUBZ: URDF ``continuous`` joints; nq = 2, q = (cos, sin))
     12     unbounded revolute, unaligned axis (JointModelRevoluteUnboundedUnaligned, nq = 2)
-    13     spherical (JointModelSpherical, nq = 4 = unit quaternion x y z w, nv = 3, S = [0; I3])      -- oracles only so far
-    14     translation (JointModelTranslation, nq = nv = 3, S = [I3; 0])                                 -- oracles only so far
-    (a free-flyer away from the root is likewise understood by both oracles, not yet by the CUDA kernels)
+    13     spherical (JointModelSpherical, nq = 4 = unit quaternion x y z w, nv = 3, S = [0; I3])
+    14     translation (JointModelTranslation, nq = nv = 3, S = [I3; 0])
+    (the multi-DoF types 8, 13, 14 may sit anywhere in the tree; the CUDA kernels take up to 8 of them per model)
 
 Other 1-DoF joints have ``nq = nv = 1``; ``idx_q`` / ``idx_v`` follow pinocchio (cumulative over the joints in id order).
 """
@@ -68,13 +68,8 @@ class RobotModel:
 
     @property
     def has_free_flyer(self) -> bool:
-        """A free-flyer ROOT joint (the only multi-DoF joint the CUDA kernels take)."""
+        """A free-flyer root joint (floating-base robots)."""
         return self.nj > 1 and int(self.jtype[1]) == FF
-
-    @property
-    def gpu_supported(self) -> bool:
-        return all(int(self.jtype[i]) not in (SPH, TRA) and (int(self.jtype[i]) != FF or (i == 1 and self.parent[i] == 0))
-                   for i in range(1, self.nj))
 
     @property
     def nv(self) -> int:
@@ -310,17 +305,19 @@ def talos(floating: bool = False) -> RobotModel:
 
 
 def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0.3, prismatic: float = 0.25,
-                continuous: float = 0.0, multidof: float = 0.0) -> RobotModel:
+                continuous: float = 0.0, multidof: float = 0.0, max_multidof: int = 8) -> RobotModel:
     """Seeded random kinematic tree covering every joint type (parity stress tests)."""
     rng = np.random.default_rng(seed)
     J = []
+    n_md = 0  # (the CUDA kernels take up to kMaxMd = 8 multi-DoF joints per model)
     for i in range(1, nb + 1):
         par = i - 1 if (i == 1 or rng.random() > branching) else int(rng.integers(0, i))
         kind = "P" if rng.random() < prismatic else "R"
         if continuous > 0.0 and kind == "R" and rng.random() < continuous:
             kind = "C"
-        if multidof > 0.0 and rng.random() < multidof:  # spherical / translation / free-flyer anywhere in the tree
+        if multidof > 0.0 and rng.random() < multidof and n_md < max_multidof:  # spherical / translation / free-flyer anywhere in the tree
             kind = ("S", "T", "FF")[int(rng.integers(0, 3))]
+            n_md += 1
         if rng.random() < unaligned:
             ax = rng.normal(size=3)
         else:

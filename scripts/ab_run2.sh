@@ -1,6 +1,4 @@
 #!/bin/bash
-mkdir -p gpurun_out
-echo "== pytest tracking"; timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "tracking or outer" 2>&1 | tail -5
-echo "== tracking warm"; timeout 300 python scripts/bench_tracking.py 2>&1 | tail -1 | tee gpurun_out/tracking_panda_warm.json
-echo "== tracking cold"; timeout 300 python scripts/bench_tracking.py --cold 2>&1 | tail -1 | tee gpurun_out/tracking_panda_cold.json
-echo "== tracking talos warm"; timeout 300 python scripts/bench_tracking.py --robot talos --batch 16384 --cpu-sample 1024 2>&1 | tail -1 | tee gpurun_out/tracking_talos_warm.json
+mkdir -p gpurun_out; export CUDA_DEVICE_MAX_CONNECTIONS=32
+echo "== pytest"; timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+echo "== perf"; PIPE=1 DEPTHS=32 timeout 300 python scripts/quick_perf.py panda,talos,talos_ff 2>&1 | grep -v "^ *$" | tail -9

@@ -64,9 +64,9 @@ def _compare_steps(model, params, pb, n_iters, what):
         for i, o in enumerate(O):
             check_abs_or_rel(H[i], o.His[1:], STEP_TOL, tag + " His")
             check_abs_or_rel(p[i], o.pis[1:], STEP_TOL, tag + " pis")
-            k0 = 1 if model.has_free_flyer else 0  # the root free-flyer's 6x6 UDinv / Dinv are not exposed per joint
-            check_abs_or_rel(UD[i][k0:], o.UDinv[1 + k0:], STEP_TOL, tag + " UDinv")
-            check_abs_or_rel(Di[i][k0:], o.Dinv[1 + k0:], STEP_TOL, tag + " Dinv")
+            one = np.array([model.nv_joint(j) == 1 for j in range(1, model.nj)])  # the K x K Dinv / 6 x K UDinv of multi-DoF joints are not exposed per joint
+            check_abs_or_rel(UD[i][one], o.UDinv[1:][one], STEP_TOL, tag + " UDinv")
+            check_abs_or_rel(Di[i][one], o.Dinv[1:][one], STEP_TOL, tag + " Dinv")
             check_abs_or_rel(r[i], o.r, STEP_TOL, tag + " r")
         # ---- forward: FwdPass2 + BoxProj + DualUpdate (+ primal residuals)
         for o in O:
@@ -586,11 +586,45 @@ def test_free_flyer_root_joint():
     with pytest.raises(RuntimeError, match="free-flyer"):
         G.Integrate(0.01)
     G.set_debug(True)
-    with pytest.raises(RuntimeError, match="free-flyer"):
+    with pytest.raises(RuntimeError, match="multi-DoF"):
         G.FwdPass1()
     G.close(); G2.close()
     from loik_b200 import solver
     bad_model = robots.talos(floating=True)
-    bad_model.jtype = bad_model.jtype.copy(); bad_model.jtype[5] = robots.FF
-    with pytest.raises(RuntimeError, match="root joint"):
+    bad_model.jtype = bad_model.jtype.copy(); bad_model.jtype[5] = 99
+    with pytest.raises(RuntimeError, match="unsupported joint type"):
         solver.make_solver(bad_model, params, 4)
+
+
+def _multidof_problem(model, B, seed):
+    rng = np.random.default_rng(300 + seed)
+    ids = np.array(sorted(rng.choice(np.arange(1, model.nj), size=2, replace=False)), np.int32)
+    Hs = rng.normal(size=(6, 6))
+    return dict(q=model.normalize(rng.uniform(model.q_min, model.q_max, size=(B, model.nq))), H_ref=np.eye(6) + 0.1 * (Hs + Hs.T),
+                v_ref=0.1 * rng.normal(size=6), ids=ids, Ais=np.stack([np.eye(6) + 0.3 * rng.normal(size=(6, 6)) for _ in range(2)]),
+                bis=rng.uniform(-0.5, 0.5, size=(B, 2, 6)), lb=-model.v_max, ub=model.v_max)
+
+
+@pytest.mark.parametrize("seed,multidof,continuous", [(0, 0.3, 0.0), (1, 0.3, 0.3), (2, 0.6, 0.0), (3, 1.0, 0.0), (4, 0.4, 0.0)])
+def test_multi_dof_joints_anywhere_step_by_step(seed, multidof, continuous):
+    """spherical / translation joints and free-flyers anywhere in a random tree (next to
+    every 1-DoF type), two tasks that may sit on the multi-DoF joints themselves: every fused step against the oracle."""
+    model = robots.random_tree(9 + seed, 40 + seed, continuous=continuous, multidof=multidof)
+    assert any(model.nv_joint(i) > 1 for i in range(1, model.nj))
+    pb = _multidof_problem(model, 33, seed)
+    _compare_steps(model, dict(problems.FIXTURE_PARAMS, max_iter=200, num_eq_c=2), pb, 3, f"mdtree{seed}")
+
+
+@pytest.mark.parametrize("seed,multidof", [(0, 0.3), (1, 0.5), (2, 1.0)])
+def test_multi_dof_joints_anywhere_full_solves(seed, multidof):
+    """Full solves (per-instance loop control, migrating launches, retire) on trees with multi-DoF joints; per-instance
+    bounds on one of them; the getters' per-dof layout (z, nu, w of 3- and 6-dof joints at idx_v)."""
+    model = robots.random_tree(10 + 2 * seed, 60 + seed, multidof=multidof)
+    B = 300
+    pb = _multidof_problem(model, B, 10 + seed)
+    if seed == 1:
+        rng = np.random.default_rng(7)
+        ub = model.v_max[None] * rng.uniform(0.3, 1.0, size=(B, model.nv))
+        pb = dict(pb, lb=-ub, ub=ub)
+    _compare_solves(model, dict(problems.FIXTURE_PARAMS, max_iter=120, num_eq_c=2, tol_abs=1e-3, tol_rel=1e-3), pb, f"mdsolve{seed}",
+                    max_diverged_frac=0.01)
