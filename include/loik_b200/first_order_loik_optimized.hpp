@@ -42,7 +42,7 @@ inline Model from_pinocchio(const pinocchio::Model& m) {
   out.njoints = m.njoints; out.nv = m.nv;
   out.parents.assign(m.njoints, 0); out.joint_types.assign(m.njoints, 0);
   out.joint_axes.assign(3 * m.njoints, 0.0); out.placement_R.assign(9 * m.njoints, 0.0); out.placement_p.assign(3 * m.njoints, 0.0);
-  int idx_q = 0;  // cumulative, as pinocchio lays q out
+  int idx_q = 0, idx_v = 0;  // cumulative, as pinocchio lays q and v out
   for (int i = 0; i < m.njoints; ++i) {
     out.parents[i] = static_cast<int32_t>(m.parents[i]);
     const auto& M = m.jointPlacements[i];
@@ -65,9 +65,10 @@ inline Model from_pinocchio(const pinocchio::Model& m) {
       code = LOIK_JOINT_PU;
       const auto& a = boost::get<pinocchio::JointModelPrismaticUnaligned>(m.joints[i].toVariant()).axis;
       ax[0] = a[0]; ax[1] = a[1]; ax[2] = a[2];
-    } else if (s == "JointModelFreeFlyer" && i == 1 && m.parents[i] == 0) {
-      code = LOIK_JOINT_FF; ax[2] = 1;
-    } else if (s == "JointModelRUBX") { code = LOIK_JOINT_RUBX; ax[0] = 1; }
+    } else if (s == "JointModelFreeFlyer") { code = LOIK_JOINT_FF; ax[2] = 1; }
+    else if (s == "JointModelSpherical") { code = LOIK_JOINT_SPHERICAL; ax[2] = 1; }
+    else if (s == "JointModelTranslation") { code = LOIK_JOINT_TRANSLATION; ax[2] = 1; }
+    else if (s == "JointModelRUBX") { code = LOIK_JOINT_RUBX; ax[0] = 1; }
     else if (s == "JointModelRUBY") { code = LOIK_JOINT_RUBY; ax[1] = 1; }
     else if (s == "JointModelRUBZ") { code = LOIK_JOINT_RUBZ; ax[2] = 1; }
     else if (s == "JointModelRevoluteUnboundedUnaligned") {
@@ -77,10 +78,10 @@ inline Model from_pinocchio(const pinocchio::Model& m) {
     } else {
       throw std::runtime_error("loik_b200::from_pinocchio: unsupported joint type " + s);
     }
-    const bool ff = m.joints[1].shortname() == "JointModelFreeFlyer";
-    if (m.joints[i].idx_v() != (i - 1) + ((ff && i > 1) ? 5 : 0) || m.joints[i].idx_q() != idx_q)
+    if (m.joints[i].idx_v() != idx_v || m.joints[i].idx_q() != idx_q)
       throw std::runtime_error("loik_b200::from_pinocchio: unexpected idx_q / idx_v layout");
     idx_q += m.joints[i].nq();
+    idx_v += m.joints[i].nv();
     out.joint_types[i] = code;
     for (int c = 0; c < 3; ++c) out.joint_axes[3 * i + c] = ax[c];
   }
