@@ -21,12 +21,14 @@
  * Layout conventions: spatial vectors are [linear(0:3); angular(3:6)] (pinocchio Motion/Force),
  * 6x6 matrices are row-major double[36], rotations row-major double[9].
  */
+#define _POSIX_C_SOURCE 200809L /* clock_gettime (lo_time_solve) */
 #include <math.h>
 #include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #define LO_API __attribute__((visibility("default")))
 
@@ -1095,4 +1097,17 @@ LO_API long lo_batch_track(int nj, const int *parent, const int *jtype, const do
   }
   free(jobs); free(th);
   return tot;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* the reference's own timing protocol (tests/loik-loid.cpp:987-1032): SolveInit once, then n x */
+/* Solve() on one thread.  Returns seconds; *iters_out = iterations of the last solve.          */
+/* ------------------------------------------------------------------------------------------ */
+LO_API double lo_time_solve(lo_solver *s, int n, int *iters_out) {
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int k = 0; k < n; ++k) lo_solve(s);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (iters_out) *iters_out = s->iter;
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
