@@ -649,9 +649,6 @@ struct loik_solver {
   int sweeps_in_solve = 0;
 };
 
-// The batch-uniform block travels with every launch as a kernel parameter: nothing to upload.
-static int upload_consts(loik_solver*, cudaStream_t) { return LOIK_OK; }
-static void mark_done(loik_solver*, cudaStream_t) {}
 
 static inline int grid_for(int n, int block = kBlock) { return (n + block - 1) / block; }
 
@@ -999,8 +996,6 @@ void loik_destroy(loik_solver* h) {
 }
 
 static int launch_reset(loik_solver* h, int flags, cudaStream_t st) {
-  int rc = upload_consts(h, st);
-  if (rc) return rc;
   k_reset<<<grid_for(h->batch, 128), 128, 0, st>>>(h->mc, h->S, flags);
   h->launches++;
   h->last_list = -1;
@@ -1065,8 +1060,6 @@ int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const 
   int rc = set_problem_consts(h, H_ref, v_ref, n_ids, ids, A, lb, ub, !bounds_per_instance);
   if (rc) return rc;
   if (loc != LOIK_DEVICE) { rc = ensure_stage(h, q_bytes + b_bytes + 2 * bd_bytes + 64, loc == LOIK_HOST); if (rc) return rc; }
-  rc = upload_consts(h, st);
-  if (rc) return rc;
   const void *dq, *db = nullptr, *dlb = nullptr, *dub = nullptr;
   size_t off = 0;
   rc = to_device(h, q, q_bytes, loc, off, st, &dq); if (rc) return rc; off += q_bytes;
@@ -1087,7 +1080,6 @@ int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const 
     h->launches++;
   }
   CK(cudaGetLastError());
-  mark_done(h, st);
   if (loc == LOIK_HOST) CK(cudaStreamSynchronize(st));  // the staging buffer may be reused by the next call
   h->problem_set = true;
   return LOIK_OK;
@@ -1305,7 +1297,6 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
   const int B = h->batch;
   const size_t q_bytes = (size_t)B * h->nq * sizeof(double), b_bytes = (size_t)(b_per_instance ? B : 1) * 6 * sizeof(double);
   if (loc != LOIK_DEVICE) { rc = ensure_stage(h, q_bytes + b_bytes + 64, loc == LOIK_HOST); if (rc) return rc; }
-  rc = upload_consts(h, st); if (rc) return rc;
   const void *dq = nullptr, *db;
   if (q) { rc = to_device(h, q, q_bytes, loc, 0, st, &dq); if (rc) return rc; }
   rc = to_device(h, bi, b_bytes, loc, q_bytes, st, &db); if (rc) return rc;
@@ -1316,7 +1307,6 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
   h->launches += 3;
   h->last_list = -1;
   CK(cudaGetLastError());
-  mark_done(h, st);
   if (loc == LOIK_HOST) CK(cudaStreamSynchronize(st));
   if (h->prm.max_iter < 2) return LOIK_OK;
   return solve_scheduled(h, st, 0, h->prm.max_iter);
@@ -1342,13 +1332,10 @@ int loik_iterate_fixed(loik_solver* h, int32_t iters, int32_t reset, void* strea
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
   if (reset) { int rc = launch_reset(h, RST_WZ | RST_VFF | RST_YATY | RST_SOLVER, st); if (rc) return rc; }
-  int rc = upload_consts(h, st);
-  if (rc) return rc;
   // one launch per iteration, dense: this is the quantity the roofline is quoted on
   for (int i = 0; i < iters; ++i) launch_iterate(h, st, h->S, 1, 1, 0, h->seg_after <= 0);  // the kernel the bulk of a solve runs
   h->sweeps += iters;
   CK(cudaGetLastError());
-  mark_done(h, st);
   return LOIK_OK;
 }
 
@@ -1366,8 +1353,7 @@ int loik_solve_chunk(loik_solver* h, int32_t iters, void* stream) {
   if (!h) return fail(LOIK_ERR_INVALID, "null handle");
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
-  int rc = upload_consts(h, st);
-  if (rc) return rc;
+  int rc = LOIK_OK;
   const int B = h->batch;
   StateP S = h->S;
   if (h->last_list >= 0 || h->sweeps_in_solve >= 3) {  // dense for the first sweeps, compacted afterwards
@@ -1381,7 +1367,6 @@ int loik_solve_chunk(loik_solver* h, int32_t iters, void* stream) {
   launch_iterate(h, st, S, iters, 0);
   h->sweeps += iters; h->sweeps_in_solve += iters;
   CK(cudaGetLastError());
-  mark_done(h, st);
   return LOIK_OK;
 }
 int loik_solve_end(loik_solver* h, void* stream) { (void)h; (void)stream; return LOIK_OK; }
@@ -1396,8 +1381,6 @@ int loik_step(loik_solver* h, int32_t step_id, void* stream) {
   if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_step: call loik_solve_init first");
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
-  int rc = upload_consts(h, st);
-  if (rc) return rc;
   const int g = grid_for(h->batch);
   switch (step_id) {
     case LOIK_STEP_BACKWARD: k_step_backward<<<g, kBlock, 0, st>>>(h->mc, h->S); break;
@@ -1415,7 +1398,6 @@ int loik_step(loik_solver* h, int32_t step_id, void* stream) {
   }
   h->launches++;
   CK(cudaGetLastError());
-  mark_done(h, st);
   return LOIK_OK;
 }
 
@@ -1429,8 +1411,7 @@ int loik_get(loik_solver* h, int32_t field, void* dst, int32_t loc, void* stream
   if (!h || !dst) return fail(LOIK_ERR_INVALID, "loik_get: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
-  int rc = upload_consts(h, st);
-  if (rc) return rc;
+  int rc = LOIK_OK;
   const int B = h->batch, nb = h->nb, nc = h->nc;
   const Offs& O = h->mc.off;
   if (field < 0 || field > LOIK_F_Q) return fail(LOIK_ERR_INVALID, "loik_get: unknown field");
@@ -1450,7 +1431,6 @@ int loik_get(loik_solver* h, int32_t field, void* dst, int32_t loc, void* stream
   }
   h->launches++;
   CK(cudaGetLastError());
-  mark_done(h, st);
   if (loc == LOIK_HOST) {
     CK(cudaMemcpyAsync(h->h_stage, ddst, bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1465,8 +1445,6 @@ int loik_get_stats(loik_solver* h, int64_t out[5]) {
   if (!h || !out) return fail(LOIK_ERR_INVALID, "null argument");
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
-  int rc = upload_consts(h, 0);
-  if (rc) return rc;
   CK(cudaMemset(h->d_stats, 0, 4 * sizeof(unsigned long long)));
   k_stats<<<grid_for(h->ntiles * 32, 128), 128>>>(h->mc, h->S, h->d_stats);
   h->launches++;
