@@ -11,8 +11,9 @@ synthetic batch BASELINE.json names; `value` = IK solves per second over all ran
 region.  `roofline` is quoted on the ADMM-iteration kernel in fixed-iteration mode (every instance active,
 one launch per iteration): algorithmic bytes per launch = 8*(143 n + 42 nc) * batch.
 
-For N > 1 (torchrun) the batch is sharded across ranks (weak scaling: per-GPU batch fixed); the only
-collective is the all-reduce of the still-active count that decides the global stop.
+For N > 1 (torchrun) the batch is sharded across ranks (weak scaling: per-GPU batch fixed); loop control is per
+instance on the device, and the only collective is one all-reduce of four int64 per solve: the global stopping-
+criterion outcome (#converged, #infeasible, #max_iter, total iterations).
 """
 from __future__ import annotations
 
