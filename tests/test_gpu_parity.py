@@ -628,3 +628,53 @@ def test_multi_dof_joints_anywhere_full_solves(seed, multidof):
         pb = dict(pb, lb=-ub, ub=ub)
     _compare_solves(model, dict(problems.FIXTURE_PARAMS, max_iter=120, num_eq_c=2, tol_abs=1e-3, tol_rel=1e-3), pb, f"mdsolve{seed}",
                     max_diverged_frac=0.01)
+
+
+def test_multi_dof_fwd_pass_init_and_integrate():
+    """FwdPassInit for multi-DoF joints (liMi = placement * M(q): quaternion of free-flyer / spherical joints, offset of
+    translation joints) against the oracle, the q getter layout, and the device-side integrate of a tree whose only
+    multi-DoF joints are translation joints (vector space) next to unbounded revolute ones."""
+    model = robots.random_tree(12, 77, multidof=0.5)
+    B = 40
+    pb = _multidof_problem(model, B, 3)
+    params = dict(problems.FIXTURE_PARAMS, max_iter=50, num_eq_c=2)
+    G = _gpu(model, params, B)
+    _solve_init(G, pb)
+    np.testing.assert_array_equal(G.q, pb["q"])
+    L = G.liMi
+    for i in range(0, B, 7):
+        o = _oracle(model, params)
+        o.SolveInit(*instance(pb, i))
+        np.testing.assert_allclose(L[i][:, :9].reshape(-1, 3, 3), o.liMi_R[1:], rtol=0, atol=1e-14)
+        np.testing.assert_allclose(L[i][:, 9:], o.liMi_p[1:], rtol=0, atol=1e-14)
+    with pytest.raises(RuntimeError, match="free-flyer / spherical"):
+        G.Integrate(0.01)
+    G.close()
+    # translation + unbounded revolute joints: integrate on the device == RobotModel.integrate, then a tailored solve
+    J = [("j1", 0, "R", "z", (0, 0, 0.1), (0, 0, 0), -2, 2, 2.0), ("t2", 1, "T", None, (0.1, 0, 0.2), (0.3, -0.2, 0.5), None, None, 1.5),
+         ("c3", 2, "C", "y", (0, 0.1, 0.1), (0, 0.4, 0), None, None, 2.0), ("j4", 3, "R", (1.0, 1.0, 0.0), (0.2, 0, 0), (0, 0, 0.7), -2, 2, 2.0),
+         ("t5", 2, "T", None, (0, -0.2, 0.1), (0, 0, 0), None, None, 1.0)]
+    model = robots._build("tra_tree", J)
+    pb = _multidof_problem(model, B, 4)
+    pb = dict(pb, ids=np.array([4, 5], np.int32))
+    params = dict(problems.bench_params(2), warm_start=True)
+    G = _gpu(model, params, B)
+    G.Solve(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
+    z0, dt = G.z, 0.03
+    G.Integrate(dt)
+    q1 = model.integrate(pb["q"], dt * z0)
+    np.testing.assert_allclose(G.q, q1, rtol=0, atol=2e-15)
+    b1 = 0.7 * pb["bis"][:, 0]
+    G.Solve(None, 4, pb["Ais"][0], b1)
+    z1, it1, mu1 = G.z, G.get_iter(), G.get_mu()
+    bad = 0
+    for i in range(B):
+        o = _oracle(model, params)
+        o.Solve(*instance(pb, i))
+        o.Solve(model.integrate(pb["q"][i], dt * o.z), 4, pb["Ais"][0], b1[i])
+        if o.get_iter() != it1[i] or o.get_mu() != mu1[i]:
+            bad += 1
+            continue
+        assert rel_inf(z1[i], o.z) < 1e-6
+    assert bad <= 1
+    G.close()
