@@ -458,12 +458,50 @@ __global__ void __launch_bounds__(128) k_integrate(const __grid_constant__ Model
   for (int i = 1; i <= nb; ++i) {
     double* Pj = joint_blk(T, c_model.off, i - 1);
     const int jt = c_model.j[i].jtype;
-    if (c_model.j[i].nvj > 1) {  // translation joint (vector space): q += dt z, liMi translation = placement.p + placement.R q
+    if (c_model.j[i].nvj > 1) {
+      // multi-DoF joints.  Translation (vector space): q += dt z.  Spherical / free-flyer
+      // (SpecialOrthogonalOperationTpl<3> / SpecialEuclideanOperationTpl<3>::integrate_impl): quat * exp3(omega), and
+      // p + R(quat) * [translation of exp6(v)], body-frame velocities, then quaternion::firstOrderNormalize.
+      // liMi = placement * M(q) (FR_XF) is rebuilt for the new configuration.
       const JointC& J = c_model.j[i];
       double* Pf = md_blk(T, c_model.off, J.mblk);
-      double qn[3];
-      for (int c = 0; c < 3; ++c) { qn[c] = ld(Pf, FR_Q + c) + dt * ld(Pf, FR_Z + c); st(Pf, FR_Q + c, qn[c]); }
-      for (int a = 0; a < 3; ++a) st(Pf, FR_XF + 9 + a, J.plp[a] + (J.plR[3 * a] * qn[0] + J.plR[3 * a + 1] * qn[1] + J.plR[3 * a + 2] * qn[2]));
+      double M[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pq[3] = {0, 0, 0};
+      if (jt == LOIK_JOINT_TRANSLATION) {
+        for (int c = 0; c < 3; ++c) { pq[c] = ld(Pf, FR_Q + c) + dt * ld(Pf, FR_Z + c); st(Pf, FR_Q + c, pq[c]); }
+      } else {
+        const int o = jt == LOIK_JOINT_FF ? 3 : 0;
+        const double w0 = dt * ld(Pf, FR_Z + o), w1 = dt * ld(Pf, FR_Z + o + 1), w2 = dt * ld(Pf, FR_Z + o + 2);
+        const double ax = ld(Pf, FR_Q + o), ay = ld(Pf, FR_Q + o + 1), az = ld(Pf, FR_Q + o + 2), aw = ld(Pf, FR_Q + o + 3);
+        const double th2 = w0 * w0 + w1 * w1 + w2 * w2, th = sqrt(th2);
+        const bool small = th < 1e-4;
+        const double k = small ? 0.5 - th2 / 48.0 : sin(th / 2) / th, cw = small ? 1.0 - th2 / 8.0 : cos(th / 2);
+        const double d0 = k * w0, d1 = k * w1, d2 = k * w2;
+        double r0 = aw * d0 + ax * cw + ay * d2 - az * d1, r1 = aw * d1 - ax * d2 + ay * cw + az * d0;
+        double r2 = aw * d2 + ax * d1 - ay * d0 + az * cw, r3 = aw * cw - ax * d0 - ay * d1 - az * d2;
+        if (jt == LOIK_JOINT_FF) {
+          const double v0 = dt * ld(Pf, FR_Z), v1 = dt * ld(Pf, FR_Z + 1), v2 = dt * ld(Pf, FR_Z + 2);
+          const double a_v = small ? 1.0 - th2 / 6.0 : sin(th) / th, a_wxv = small ? 0.5 - th2 / 24.0 : (1.0 - cos(th)) / th2;
+          const double a_w = (small ? 1.0 / 6.0 - th2 / 120.0 : (1.0 - a_v) / th2) * (w0 * v0 + w1 * v1 + w2 * v2);
+          const double p0 = a_v * v0 + a_w * w0 + a_wxv * (w1 * v2 - w2 * v1), p1 = a_v * v1 + a_w * w1 + a_wxv * (w2 * v0 - w0 * v2);
+          const double p2 = a_v * v2 + a_w * w2 + a_wxv * (w0 * v1 - w1 * v0);
+          const double Rq[9] = {1 - 2 * (ay * ay + az * az), 2 * (ax * ay - az * aw), 2 * (ax * az + ay * aw), 2 * (ax * ay + az * aw),
+                                1 - 2 * (ax * ax + az * az), 2 * (ay * az - ax * aw), 2 * (ax * az - ay * aw), 2 * (ay * az + ax * aw),
+                                1 - 2 * (ax * ax + ay * ay)};
+          for (int c = 0; c < 3; ++c) { pq[c] = ld(Pf, FR_Q + c) + (Rq[3 * c] * p0 + Rq[3 * c + 1] * p1 + Rq[3 * c + 2] * p2); st(Pf, FR_Q + c, pq[c]); }
+          if (r0 * ax + r1 * ay + r2 * az + r3 * aw < 0.0) { r0 = -r0; r1 = -r1; r2 = -r2; r3 = -r3; }
+        }
+        const double nrm = (3.0 - (r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3)) / 2.0;
+        const double x = r0 * nrm, y = r1 * nrm, z = r2 * nrm, w = r3 * nrm;
+        st(Pf, FR_Q + o, x); st(Pf, FR_Q + o + 1, y); st(Pf, FR_Q + o + 2, z); st(Pf, FR_Q + o + 3, w);
+        M[0] = 1 - 2 * (y * y + z * z); M[1] = 2 * (x * y - z * w); M[2] = 2 * (x * z + y * w);
+        M[3] = 2 * (x * y + z * w); M[4] = 1 - 2 * (x * x + z * z); M[5] = 2 * (y * z - x * w);
+        M[6] = 2 * (x * z - y * w); M[7] = 2 * (y * z + x * w); M[8] = 1 - 2 * (x * x + y * y);
+      }
+      const double* P = J.plR;
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) st(Pf, FR_XF + 3 * a + b, P[3 * a] * M[b] + P[3 * a + 1] * M[3 + b] + P[3 * a + 2] * M[6 + b]);
+        st(Pf, FR_XF + 9 + a, J.plp[a] + (P[3 * a] * pq[0] + P[3 * a + 1] * pq[1] + P[3 * a + 2] * pq[2]));
+      }
       continue;
     }
     if (c_model.j[i].qkind == 1) {
@@ -1315,9 +1353,6 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
 int loik_integrate(loik_solver* h, double dt, void* stream) {
   if (!h) return fail(LOIK_ERR_INVALID, "null handle");
   if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_integrate: call loik_solve_init first");
-  for (int i = 1; i < h->nj; ++i)
-    if (h->mc.j[i].nvj > 1 && h->mc.j[i].jtype != LOIK_JOINT_TRANSLATION)
-      return fail(LOIK_ERR_UNSUPPORTED, "loik_integrate: free-flyer / spherical joints are not supported yet (SE3 / SO3 exponential)");
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
   k_integrate<<<grid_for(h->batch, 128), 128, 0, st>>>(h->mc, h->S, dt);

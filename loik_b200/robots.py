@@ -43,6 +43,23 @@ def rpy_to_matrix(r: float, p: float, y: float) -> np.ndarray:
     return Rz @ Ry @ Rx
 
 
+def _quat_mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Hamilton product of quaternions stored (x, y, z, w), broadcasting over leading axes."""
+    ax, ay, az, aw = (a[..., k] for k in range(4))
+    bx, by, bz, bw = (b[..., k] for k in range(4))
+    return np.stack([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz], axis=-1)
+
+
+def _quat_rotate(qt: np.ndarray, p: np.ndarray) -> np.ndarray:
+    """R(q) p for a quaternion (x, y, z, w): the rotation matrix of joint_transform applied to p."""
+    x, y, z, w = (qt[..., k] for k in range(4))
+    R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+                  np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+                  np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], -2)
+    return np.einsum("...ij,...j->...i", R, p)
+
+
 @dataclasses.dataclass
 class RobotModel:
     """What the LoIK hot path needs from ``pinocchio::Model`` (joint 0 = universe)."""
@@ -128,20 +145,40 @@ class RobotModel:
         return q
 
     def integrate(self, q: np.ndarray, v: np.ndarray) -> np.ndarray:
-        """pinocchio::integrate(model, q, v) for the joint types the device-side outer loop supports: q + v for the
-        vector-space joints, the SO(2) update of JointModelRevoluteUnbounded* (rotate (cos, sin) by v, then the
-        first-order renormalisation ``out *= (3 - |out|^2) / 2``).  ``q`` is [..., nq], ``v`` is [..., nv]."""
+        """pinocchio::integrate(model, q, v): q + v for the vector-space joints; the SO(2) update of
+        JointModelRevoluteUnbounded* (rotate (cos, sin) by v, then the first-order renormalisation
+        ``out *= (3 - |out|^2) / 2``); quaternion * exp3(omega) for spherical joints and M * exp6(v) for free-flyers
+        (body-frame velocities, [linear; angular]), each followed by the same first-order renormalisation of the
+        quaternion.  ``q`` is [..., nq], ``v`` is [..., nv]."""
         q = np.asarray(q, np.float64)
         v = np.asarray(v, np.float64)
         out = np.empty_like(q)
         for i in range(1, self.nj):
-            iq, iv = self.idx_q(i), self.idx_v(i)
-            if int(self.jtype[i]) in (FF, SPH):
-                raise NotImplementedError("integrate: free-flyer / spherical joints (SE3 / SO3 exponential) are not supported")
-            if int(self.jtype[i]) == TRA:
+            iq, iv, jt = self.idx_q(i), self.idx_v(i), int(self.jtype[i])
+            if jt in (FF, SPH):
+                o = 3 if jt == FF else 0
+                w = v[..., iv + o:iv + o + 3]
+                quat = q[..., iq + o:iq + o + 4]
+                th2 = np.sum(w * w, axis=-1)
+                th = np.sqrt(th2)
+                small = th < 1e-4
+                ths = np.where(small, 1.0, th)
+                k = np.where(small, 0.5 - th2 / 48.0, np.sin(ths / 2) / ths)            # sin(th/2)/th
+                dq = np.concatenate([k[..., None] * w, np.where(small, 1.0 - th2 / 8.0, np.cos(ths / 2))[..., None]], axis=-1)
+                res = _quat_mul(quat, dq)
+                if jt == FF:
+                    vl = v[..., iv:iv + 3]
+                    a_v = np.where(small, 1.0 - th2 / 6.0, np.sin(ths) / ths)           # sin(th)/th
+                    a_wxv = np.where(small, 0.5 - th2 / 24.0, (1.0 - np.cos(ths)) / np.where(small, 1.0, th2))
+                    a_w = np.where(small, 1.0 / 6.0 - th2 / 120.0, (1.0 - a_v) / np.where(small, 1.0, th2)) * np.sum(w * vl, axis=-1)
+                    p = a_v[..., None] * vl + a_w[..., None] * w + a_wxv[..., None] * np.cross(w, vl)
+                    out[..., iq:iq + 3] = q[..., iq:iq + 3] + _quat_rotate(quat, p)
+                    res = np.where((np.sum(res * quat, axis=-1) < 0.0)[..., None], -res, res)
+                res = res * ((3.0 - np.sum(res * res, axis=-1)) / 2.0)[..., None]        # quaternion::firstOrderNormalize
+                out[..., iq + o:iq + o + 4] = res
+            elif jt == TRA:
                 out[..., iq:iq + 3] = q[..., iq:iq + 3] + v[..., iv:iv + 3]
-                continue
-            if self.is_unbounded(i):
+            elif self.is_unbounded(i):
                 ca, sa, om = q[..., iq], q[..., iq + 1], v[..., iv]
                 co, so = np.cos(om), np.sin(om)
                 c, s_ = co * ca - so * sa, so * ca + co * sa

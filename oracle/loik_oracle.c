@@ -1025,9 +1025,35 @@ static void integrate_q(const lo_solver *s, double *q, const double *v, double d
       double c = co * ca - so * sa, sn = so * ca + co * sa;
       const double k = (3.0 - (c * c + sn * sn)) / 2.0;
       q[iq] = c * k; q[iq + 1] = sn * k;
-    } else if (jt_nq(jt) == s->nvj[i]) { /* vector-space joints (1-DoF, translation) */
+    } else if (jt == JT_FF || jt == JT_SPH) {
+      /* SpecialOrthogonalOperationTpl<3> / SpecialEuclideanOperationTpl<3>::integrate_impl: quat * exp3(omega) (and
+       * p + R(quat) * [translation of exp6(v)]), body-frame velocities, then quaternion::firstOrderNormalize */
+      const int o = jt == JT_FF ? 3 : 0;
+      double w[3] = {dt * v[iv + o], dt * v[iv + o + 1], dt * v[iv + o + 2]};
+      double *qt = q + iq + o;
+      const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
+      const int small = th < 1e-4;
+      const double k = small ? 0.5 - th2 / 48.0 : sin(th / 2) / th, cw = small ? 1.0 - th2 / 8.0 : cos(th / 2);
+      const double d[4] = {k * w[0], k * w[1], k * w[2], cw};
+      const double ax = qt[0], ay = qt[1], az = qt[2], aw = qt[3];
+      double r[4] = {aw * d[0] + ax * d[3] + ay * d[2] - az * d[1], aw * d[1] - ax * d[2] + ay * d[3] + az * d[0],
+                     aw * d[2] + ax * d[1] - ay * d[0] + az * d[3], aw * d[3] - ax * d[0] - ay * d[1] - az * d[2]};
+      if (jt == JT_FF) {
+        const double vl[3] = {dt * v[iv], dt * v[iv + 1], dt * v[iv + 2]};
+        const double a_v = small ? 1.0 - th2 / 6.0 : sin(th) / th, a_wxv = small ? 0.5 - th2 / 24.0 : (1.0 - cos(th)) / th2;
+        const double a_w = (small ? 1.0 / 6.0 - th2 / 120.0 : (1.0 - a_v) / th2) * (w[0] * vl[0] + w[1] * vl[1] + w[2] * vl[2]);
+        double cr[3], p[3], MR[9], Mp[3];
+        cross3(w, vl, cr);
+        for (int c = 0; c < 3; ++c) p[c] = a_v * vl[c] + a_w * w[c] + a_wxv * cr[c];
+        joint_M(JT_SPH, NULL, qt, MR, Mp); /* R(quat) */
+        for (int c = 0; c < 3; ++c) q[iq + c] += MR[3 * c] * p[0] + MR[3 * c + 1] * p[1] + MR[3 * c + 2] * p[2];
+        if (r[0] * ax + r[1] * ay + r[2] * az + r[3] * aw < 0.0) for (int c = 0; c < 4; ++c) r[c] = -r[c];
+      }
+      const double nrm = (3.0 - (r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3])) / 2.0;
+      for (int c = 0; c < 4; ++c) qt[c] = r[c] * nrm;
+    } else { /* vector-space joints (1-DoF, translation) */
       for (int k = 0; k < s->nvj[i]; ++k) q[iq + k] += dt * v[iv + k];
-    } /* free-flyer / spherical: the SE3 / SO3 exponential is not restated; the tracking driver is not used with them */
+    }
   }
 }
 

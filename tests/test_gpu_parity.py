@@ -443,17 +443,17 @@ def test_outer_ik_loop_unbounded_revolute():
     G.close()
 
 
-@pytest.mark.parametrize("name,warm", [("panda", True), ("panda", False), ("ur10c", True)])
+@pytest.mark.parametrize("name,warm", [("panda", True), ("panda", False), ("ur10c", True), ("talos_ff", True)])
 def test_tracking_loop_vs_oracle(name, warm):
     """The trajectory-tracking loop (full Solve, then T x { Integrate(dt); Solve(q on device, c_id, A, b_t) }) against
     the oracle driven the same way (lo_batch_track): iteration count of every instance at the last step, final z, and
     the integrated configuration."""
     from oracle import recursion
     model = robots.get_robot(name)
-    B, T, dt = 512, 6, 0.02
+    B, T, dt = (512 if model.nb < 20 else 128), 6, 0.02
     pb = problems.random_batch(model, B, seed=51)
     nx = problems.random_batch(model, B, seed=52)
-    params = dict(problems.bench_params(1), warm_start=warm)
+    params = dict(problems.bench_params(len(pb["ids"])), warm_start=warm)
     c_id, A = int(pb["ids"][0]), pb["Ais"][0]
     G = _gpu(model, params, B)
     G.Solve(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
@@ -583,8 +583,8 @@ def test_free_flyer_root_joint():
     _solve_init(G2, sub)
     G2.Solve()
     np.testing.assert_array_equal(G2.z, z[50:87])
-    with pytest.raises(RuntimeError, match="free-flyer"):
-        G.Integrate(0.01)
+    G.Integrate(0.01)  # M * exp6(dt z) for the floating base (SpecialEuclideanOperationTpl<3>::integrate_impl)
+    np.testing.assert_allclose(G.q, model.integrate(pb["q"], 0.01 * z), rtol=0, atol=5e-15)
     G.set_debug(True)
     with pytest.raises(RuntimeError, match="multi-DoF"):
         G.FwdPass1()
@@ -647,8 +647,16 @@ def test_multi_dof_fwd_pass_init_and_integrate():
         o.SolveInit(*instance(pb, i))
         np.testing.assert_allclose(L[i][:, :9].reshape(-1, 3, 3), o.liMi_R[1:], rtol=0, atol=1e-14)
         np.testing.assert_allclose(L[i][:, 9:], o.liMi_p[1:], rtol=0, atol=1e-14)
-    with pytest.raises(RuntimeError, match="free-flyer / spherical"):
-        G.Integrate(0.01)
+    G.Solve()
+    zz = G.z
+    G.Integrate(0.05)  # quaternion * exp3 / M * exp6 for the spherical joints and free-flyers of the tree
+    np.testing.assert_allclose(G.q, model.integrate(pb["q"], 0.05 * zz), rtol=0, atol=5e-15)
+    L = G.liMi
+    for i in range(0, B, 9):
+        o = _oracle(model, params)
+        o.SolveInit(model.integrate(pb["q"][i], 0.05 * zz[i]), *instance(pb, i)[1:])
+        np.testing.assert_allclose(L[i][:, :9].reshape(-1, 3, 3), o.liMi_R[1:], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(L[i][:, 9:], o.liMi_p[1:], rtol=0, atol=1e-13)
     G.close()
     # translation + unbounded revolute joints: integrate on the device == RobotModel.integrate, then a tailored solve
     J = [("j1", 0, "R", "z", (0, 0, 0.1), (0, 0, 0), -2, 2, 2.0), ("t2", 1, "T", None, (0.1, 0, 0.2), (0.3, -0.2, 0.5), None, None, 1.5),

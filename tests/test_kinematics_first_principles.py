@@ -128,3 +128,43 @@ def test_link_velocities_random_trees(seed, continuous, multidof):
     pr = dict(q=model.normalize(rng.uniform(model.q_min, model.q_max)), H_ref=np.eye(6), v_ref=np.zeros(6), ids=ids,
               Ais=np.tile(np.eye(6), (2, 1, 1)), bis=rng.uniform(-0.5, 0.5, size=(2, 6)), lb=-model.v_max, ub=model.v_max)
     _check(model, pr, f"tree{seed}")
+
+
+def test_integrate_is_the_group_exponential():
+    """RobotModel.integrate / the oracle's tracking driver for free-flyer and spherical joints against the matrix
+    exponential (scipy.linalg.expm of the 4x4 twist / 3x3 skew matrix): M1 = M0 expm(v^), R1 = R0 expm(omega^)."""
+    import scipy.linalg as sl
+
+    def skew(a):
+        return np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+
+    def rq(q):
+        x, y, z, w = q
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+    J = [("ff", 0, "FF", None, (0, 0, 0), (0, 0, 0), None, None, 1.0), ("s", 1, "S", None, (0.1, 0, 0), (0, 0, 0), None, None, 1.0),
+         ("r", 2, "R", "z", (0, 0, 0.2), (0, 0, 0), -2, 2, 1.0)]
+    m = robots._build("ff_sph", J)
+    rng = np.random.default_rng(0)
+    for scale in (1e-7, 1e-3, 0.3, 2.0):
+        for _ in range(20):
+            q = m.normalize(rng.normal(size=m.nq))
+            v = scale * rng.normal(size=m.nv)
+            q1 = m.integrate(q, v)
+            M0 = np.eye(4); M0[:3, :3] = rq(q[3:7]); M0[:3, 3] = q[:3]
+            X = np.zeros((4, 4)); X[:3, :3] = skew(v[3:6]); X[:3, 3] = v[:3]
+            M1 = M0 @ sl.expm(X)
+            assert np.abs(rq(q1[3:7]) - M1[:3, :3]).max() < 1e-12 and np.abs(q1[:3] - M1[:3, 3]).max() < 1e-12
+            assert np.abs(rq(q1[7:11]) - rq(q[7:11]) @ sl.expm(skew(v[6:9]))).max() < 1e-12
+            assert abs(q1[11] - (q[11] + v[9])) < 1e-15
+    # the C tracking driver integrates the same way (one step, dt = 0.05): compare the configurations it ends with
+    B = 16
+    pb = dict(q=m.normalize(rng.normal(size=(B, m.nq))), H_ref=np.eye(6), v_ref=np.zeros(6), ids=np.array([3], np.int32),
+              Ais=np.eye(6)[None], bis=rng.uniform(-0.3, 0.3, size=(B, 1, 6)), lb=-m.v_max, ub=m.v_max)
+    params = dict(problems.bench_params(1), warm_start=True)
+    trk = recursion.batch_track(m, params, pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["bis"], pb["lb"],
+                                pb["ub"], c_id=3, dt=0.05, steps=1, warm=True)
+    full = recursion.batch_solve(m, params, pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
+    np.testing.assert_allclose(trk["q"], m.integrate(pb["q"], 0.05 * full["z"]), rtol=0, atol=1e-14)
