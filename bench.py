@@ -39,6 +39,7 @@ WORKLOADS = {  # BASELINE.json configs[1..3]: (robot, per-GPU batch)
     "panda": ("panda", 65536),
     "ur10": ("ur10", 262144),
     "talos": ("talos", 16384),
+    "talos_ff": ("talos_ff", 16384),  # floating base (free-flyer root, nv = 38): not a BASELINE config, SURVEY.md 8(f) rank 4
 }
 FIXED_ITERS = 50
 METRIC = "IK solves/sec (batch, device-timed)"

@@ -89,7 +89,9 @@ LOIK_DEV void claim_next(const StateP& S, const bool active, const int slot_now)
 // still-active instances; the grid is sized for the worst case and surplus CTAs exit at once), in place, or --
 // migrating launch, S.dst set -- read there during the first iteration and written to slot k of S.dst: the physical
 // re-pack of the still-active instances into full tiles costs no pass of its own.
-// MINB = resident CTAs per SM the kernel is compiled for -> register cap 65536 / (64 MINB), rounded down to 8
+// MINB = resident CTAs per SM the kernel is compiled for -> register cap 65536 / (64 MINB), rounded down to 8.  Only
+// MINB = 4 (255 registers) is instantiated: 5 / 6 / 8 CTAs per SM (200 / 168 / 128 registers) spill and were 1.3-1.6x
+// slower (profiles/r1_history.md).
 // MD: the model has multi-DoF joints (span-level dispatch, out-of-line steps); the 1-DoF-only instantiation is the
 // plain joint loops, untouched by that machinery (it is the kernel every BASELINE robot runs).
 template <bool DEBUG, int MINB, bool MD = false>
@@ -666,7 +668,6 @@ struct loik_solver {
   void* d_stage = nullptr; size_t d_stage_bytes = 0;
   int64_t launches = 0;
   int64_t sweeps = 0;
-  int minb = 0;
   int dense_sweeps = 4;  // sweeps on the home arena before the first re-pack (env LOIK_DENSE)
   int sched_reps = 2;      // re-pack rounds per chunk size (env LOIK_REPS)
   double sched_growth = 2.0;  // chunk growth factor (env LOIK_GROWTH)
@@ -690,8 +691,7 @@ struct loik_solver {
 
 static inline int grid_for(int n, int block = kBlock) { return (n + block - 1) / block; }
 
-// One place that launches the fused iteration kernel.  `minb` = resident CTAs (of 64 threads) per SM the
-// kernel is compiled for: 4 -> <=255 regs/thread, 6 -> <=168, 8 -> <=128 (tuning knob, env LOIK_MINB).
+// One place that launches the fused iteration kernel.
 // `seg`: use the segment-parallel kernel (several warps per tile) when the tree branches.  It shortens the critical
 // path of a sweep (latency) but spends 2-3.5x the warp-slot time of the one-warp-per-tile kernel per iteration, so
 // the schedule switches to it only for the late rounds, when few tiles are left and latency is all that matters.
@@ -719,10 +719,7 @@ static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S, int
 #define LOIK_LAUNCH(DBG, MB, MD_) k_iterate<DBG, MB, MD_><<<g, kBlock, 0, st>>>(h->mc, S, iters, fixed)
   if (h->debug) { if (md) LOIK_LAUNCH(true, 4, true); else LOIK_LAUNCH(true, 4, false); }
   else if (md) { LOIK_LAUNCH(false, 4, true); }
-  else if (h->minb == 4) { LOIK_LAUNCH(false, 4, false); }
-  else if (h->minb == 5) { LOIK_LAUNCH(false, 5, false); }
-  else if (h->minb == 6) { LOIK_LAUNCH(false, 6, false); }
-  else { LOIK_LAUNCH(false, 8, false); }
+  else { LOIK_LAUNCH(false, 4, false); }
 #undef LOIK_LAUNCH
   h->launches++;
 }
@@ -813,7 +810,6 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   };
   h->nv = 0; h->nq = 0;
   for (int i = 1; i < nj; ++i) { h->nv += nv_of(i); h->nq += nq_of(i); }
-  h->minb = 4;
   if (const char* e = std::getenv("LOIK_DENSE")) { const int v = std::atoi(e); if (v >= 0) h->dense_sweeps = v; }
   if (const char* e = std::getenv("LOIK_NO_GRAPH")) { if (std::atoi(e) != 0) h->use_graph = false; }
   if (const char* e = std::getenv("LOIK_SMALL_AFTER")) h->small_after = std::atoi(e);
@@ -822,7 +818,6 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   if (const char* e = std::getenv("LOIK_SEG_AFTER")) h->seg_after = std::atoi(e);
   if (const char* e = std::getenv("LOIK_REPS")) { const int v = std::atoi(e); if (v >= 1) h->sched_reps = v; }
   if (const char* e = std::getenv("LOIK_GROWTH")) { const double v = std::atof(e); if (v >= 1.0) h->sched_growth = v; }
-  if (const char* e = std::getenv("LOIK_MINB")) { const int v = std::atoi(e); if (v == 4 || v == 5 || v == 6 || v == 8) h->minb = v; }
   ModelC& M = h->mc;
   std::memset(&M, 0, sizeof(M));
   M.nj = nj; M.nb = nj - 1; M.nc = h->nc;

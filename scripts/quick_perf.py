@@ -27,8 +27,8 @@ def main():
         e0.record(); S.IterateFixed(50); e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / 50
         bpi = 8 * (143 * model.nb + 42 * nc)
-        print(f"{name} B={B} MINB={os.environ.get('LOIK_MINB','-')}: {us:.1f} us/iter, {B/us:.1f} M inst-it/s, "
-              f"{bpi*B/us/1e3:.0f} GB/s algorithmic = {bpi*B/us/1e3/6464.9:.3f} of HBM")
+        print(f"{name} B={B}: {us:.1f} us/iter, {B/us:.1f} M inst-it/s, "
+              f"{bpi*B/us/1e3:.0f} GB/s algorithmic = {bpi*B/us/1e3/6547.5:.3f} of HBM")
         for _ in range(2):
             S.Solve()
         torch.cuda.synchronize()
