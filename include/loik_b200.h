@@ -200,8 +200,9 @@ LOIK_API int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, cons
                              int32_t b_per_instance, int32_t loc, void* stream);
 
 /* Outer IK loop on the device (the step after the hot path; README.md:5 of the reference: "differential IK ... to be
- * integrated"): q <- q + dt * z (pinocchio::integrate for 1-DoF joints) and FwdPassInit(q) (hxx:253-283) for every
- * instance.  Follow with loik_solve_task(h, NULL, c_id, Ai, bi, ...) for the next target.  Not a reference entry point. */
+ * integrated"): q <- pinocchio::integrate(model, q, dt * z) -- q + dt z for vector-space joints, the SO(2) update of the
+ * unbounded revolute joints, quat * exp3 / M * exp6 with the first-order quaternion renormalisation for spherical joints
+ * and free-flyers -- and FwdPassInit(q) (hxx:253-283) for every instance.  Follow with loik_solve_task(h, NULL, c_id, Ai, bi, ...) for the next target.  Not a reference entry point. */
 LOIK_API int loik_integrate(loik_solver* h, double dt, void* stream);
 
 /* Fixed-iteration mode for throughput measurement: ResetRecursion + ResetSolver, then exactly `iters`
