@@ -55,3 +55,23 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("oracle-vs", "").lower() or f == "robots.py" or "import oracle" not in txt, f
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_model_validation_needs_no_gpu():
+    """loik_create validates the model before it touches CUDA: the reference-style error texts come back on any box."""
+    import numpy as np
+    from loik_b200 import problems, robots, solver
+    P = problems.bench_params(1)
+    m = robots.panda()
+    m.jtype = m.jtype.copy(); m.jtype[3] = 99
+    with pytest.raises(RuntimeError, match="unsupported joint type"):
+        solver.make_solver(m, P, 4)
+    m = robots.panda()
+    m.parent = m.parent.copy(); m.parent[2] = 5
+    with pytest.raises(RuntimeError, match="parents"):
+        solver.make_solver(m, P, 4)
+    many = robots._build("many_md", [(f"s{i}", i, "S", None, (0.1, 0, 0), (0, 0, 0), None, None, 1.0) for i in range(9)])
+    with pytest.raises(RuntimeError, match="multi-DoF"):
+        solver.make_solver(many, P, 4)
+    with pytest.raises(RuntimeError, match="equality constraint dimension is not 6"):
+        solver.make_solver(robots.panda(), dict(P, eq_c_dim=3), 4)
