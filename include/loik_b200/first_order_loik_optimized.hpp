@@ -68,6 +68,7 @@ inline Model from_pinocchio(const pinocchio::Model& m) {
     } else if (s == "JointModelFreeFlyer") { code = LOIK_JOINT_FF; ax[2] = 1; }
     else if (s == "JointModelSpherical") { code = LOIK_JOINT_SPHERICAL; ax[2] = 1; }
     else if (s == "JointModelTranslation") { code = LOIK_JOINT_TRANSLATION; ax[2] = 1; }
+    else if (s == "JointModelPlanar") { code = LOIK_JOINT_PLANAR; ax[2] = 1; }
     else if (s == "JointModelRUBX") { code = LOIK_JOINT_RUBX; ax[0] = 1; }
     else if (s == "JointModelRUBY") { code = LOIK_JOINT_RUBY; ax[1] = 1; }
     else if (s == "JointModelRUBZ") { code = LOIK_JOINT_RUBZ; ax[2] = 1; }

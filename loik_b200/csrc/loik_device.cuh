@@ -42,7 +42,7 @@ struct JointC {
   int npin;                         // number of children that hand their contribution over through a pending block
   int pin[kMaxPin];                 // those blocks (one per tree edge: single writer, no read-modify-write)
   int qkind;                        // how q parametrises the joint: 0 = one scalar, 1 = (cos, sin) (unbounded revolute)
-  int nvj, sel0, mblk;              // multi-DoF joints: nv of the joint (3 / 6), first component S selects, index of its md block
+  int nvj, sel0, mblk;              // multi-DoF joints: nv of the joint (3 / 6), the components S selects (4 bits each, dof k in bits 4k..4k+3), index of its md block
   int pad;
 };
 
@@ -769,7 +769,7 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, const double* Ts, double* Td
 }
 
 // ---------------------------------------------------------------------------------------------
-// Multi-DoF joints (K = J.nvj dofs, S selects components sel0 .. sel0+K-1): the three sweeps' steps for one such joint,
+// Multi-DoF joints (K = J.nvj dofs, S selects the components sel[0..K) packed in J.sel0): the three sweeps' steps for one such joint,
 // called from inside the joint loops.  calc_aba (P1, general form): U = H S, StU = S^T U + mu_ineq I,
 // Dinv = StU^-1 (pinocchio: Cholesky, PerformStYSInversion), UDinv = U Dinv, and below a non-root joint
 // H -= UDinv U^T.  They never carry to / from a neighbour in registers: every edge into or out of them is a pending
@@ -830,7 +830,9 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
                           const bool migrate) {
   const Offs& O = c_model.off;
   const JointC& J = c_model.j[i];
-  const int s0 = J.sel0;
+  int sel[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) sel[k] = (J.sel0 >> (4 * k)) & 7;
   double* Pj = joint_blk(Td, O, i - 1);
   double* Pf = md_blk(Td, O, J.mblk);
   const double* Pjs = joint_blk(const_cast<double*>(Ts), O, i - 1);
@@ -871,12 +873,12 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
 #pragma unroll
   for (int a = 0; a < K; ++a)
 #pragma unroll
-    for (int b = 0; b < K; ++b) Mx[K * a + b] = Hel(A, B, D, s0 + a, s0 + b);
+    for (int b = 0; b < K; ++b) Mx[K * a + b] = Hel(A, B, D, sel[a], sel[b]);
 #pragma unroll
   for (int c = 0; c < K; ++c) Mx[(K + 1) * c] += mu;  // armature R = mu_ineq (hxx:294-295)
   spd_inverse<K>(Mx, Dinv);
 #pragma unroll
-  for (int c = 0; c < K; ++c) r[c] = (w[c] - mu * z[c]) + p[s0 + c];  // r = w - mu z (:296) + S^T p (:70)
+  for (int c = 0; c < K; ++c) r[c] = (w[c] - mu * z[c]) + p[sel[c]];  // r = w - mu z (:296) + S^T p (:70)
 #pragma unroll
   for (int c = 0; c < 6; ++c) { st(Pj, JR_H + c, A[c]); st(Pj, JR_H + 15 + c, D[c]); st(Pj, JR_P + c, p[c]); }
 #pragma unroll
@@ -886,7 +888,7 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
 #pragma unroll
   for (int c = 0; c < K * (K + 1) / 2; ++c) st(Pf, FR_DINV + c, Dinv[c]);
   if (J.parent > 0) {
-    // UDinv = U Dinv with U = H S (columns s0 .. s0+K-1 of H); H -= UDinv U^T (:63); p -= UDinv r (:71-73)
+    // UDinv = U Dinv with U = H S (the selected columns of H); H -= UDinv U^T (:63); p -= UDinv r (:71-73)
     double UD[6][K];
 #pragma unroll
     for (int a = 0; a < 6; ++a)
@@ -894,7 +896,7 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
       for (int k = 0; k < K; ++k) {
         double sum = 0.0;
 #pragma unroll
-        for (int l = 0; l < K; ++l) sum += Hel(A, B, D, a, s0 + l) * Dinv[sk<K>(l, k)];
+        for (int l = 0; l < K; ++l) sum += Hel(A, B, D, a, sel[l]) * Dinv[sk<K>(l, k)];
         UD[a][k] = sum;
         st(Pf, FR_UD + K * a + k, sum);
       }
@@ -902,7 +904,7 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
-      for (int k = 0; k < K; ++k) U[a][k] = Hel(A, B, D, a, s0 + k);
+      for (int k = 0; k < K; ++k) U[a][k] = Hel(A, B, D, a, sel[k]);
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
@@ -945,7 +947,10 @@ template <bool DEBUG, int K>
 LOIK_DEV_CALL void md_forward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, Carry& cy, const int i) {
   const Offs& O = c_model.off;
   const JointC& J = c_model.j[i];
-  const int nb = c_model.nb, s0 = J.sel0;
+  const int nb = c_model.nb;
+  int sel[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) sel[k] = (J.sel0 >> (4 * k)) & 7;
   double* Pj = joint_blk(Td, O, i - 1);
   double* Pf = md_blk(Td, O, J.mblk);
   const double* Pjs = joint_blk(const_cast<double*>(Ts), O, i - 1);
@@ -988,7 +993,7 @@ LOIK_DEV_CALL void md_forward(const ModelC& c_model, const double* Ts, double* T
     cy.nu_inf = amax(cy.nu_inf, nu[k]);
   }
 #pragma unroll
-  for (int k = 0; k < K; ++k) v[s0 + k] += nu[k];  // v_i = vp + S nu (:133-134)
+  for (int k = 0; k < K; ++k) v[sel[k]] += nu[k];  // v_i = vp + S nu (:133-134)
 #pragma unroll
   for (int c = 0; c < 6; ++c) cy.dvis_inf = amax(cy.dvis_inf, v[c] - vold[c]);
 #pragma unroll
@@ -1045,7 +1050,10 @@ template <bool DEBUG, int K>
 LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs, const int i) {
   const Offs& O = c_model.off;
   const JointC& J = c_model.j[i];
-  const int nb = c_model.nb, s0 = J.sel0;
+  const int nb = c_model.nb;
+  int sel[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) sel[k] = (J.sel0 >> (4 * k)) & 7;
   double* Pj = joint_blk(Td, O, i - 1);
   double* Pf = md_blk(Td, O, J.mblk);
   const double* Pjs = joint_blk(const_cast<double*>(Ts), O, i - 1);
@@ -1082,7 +1090,7 @@ LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* 
   }
 #pragma unroll
   for (int c = 0; c < K; ++c) {
-    const double Tn = f[s0 + c] + ld(Pf, FR_W + c);  // S^T f + w (:231)
+    const double Tn = f[sel[c]] + ld(Pf, FR_W + c);  // S^T f + w (:231)
     rs.T_inf = amax(rs.T_inf, Tn);
     rs.dT_inf = amax(rs.dT_inf, Tn - ld(Pfs, FR_T + c));
     st(Pf, FR_T + c, Tn);

@@ -420,17 +420,20 @@ __global__ void __launch_bounds__(kBlock) k_set_q(const __grid_constant__ ModelC
       const JointC& J = c_model.j[i];
       const double* qj = sh + threadIdx.x * nq + J.idxq;
       double* Pf = md_blk(T, c_model.off, J.mblk);
-      const int nqj = jt == LOIK_JOINT_FF ? 7 : (jt == LOIK_JOINT_SPHERICAL ? 4 : 3);
+      const int nqj = jt == LOIK_JOINT_FF ? 7 : (jt == LOIK_JOINT_TRANSLATION ? 3 : 4);
       for (int c = 0; c < nqj; ++c) st(Pf, FR_Q + c, qj[c]);
       double M[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pq[3] = {0, 0, 0};
-      if (jt != LOIK_JOINT_TRANSLATION) {
+      if (jt == LOIK_JOINT_PLANAR) {  // JointModelPlanar::calc: R = Rz from (cos, sin) = (q[2], q[3]) as given, p = (x, y, 0)
+        M[0] = qj[2]; M[1] = -qj[3]; M[3] = qj[3]; M[4] = qj[2];
+        pq[0] = qj[0]; pq[1] = qj[1];
+      } else if (jt != LOIK_JOINT_TRANSLATION) {
         const int o = jt == LOIK_JOINT_FF ? 3 : 0;
         const double x = qj[o], y = qj[o + 1], z = qj[o + 2], w = qj[o + 3];
         M[0] = 1 - 2 * (y * y + z * z); M[1] = 2 * (x * y - z * w); M[2] = 2 * (x * z + y * w);
         M[3] = 2 * (x * y + z * w); M[4] = 1 - 2 * (x * x + z * z); M[5] = 2 * (y * z - x * w);
         M[6] = 2 * (x * z - y * w); M[7] = 2 * (y * z + x * w); M[8] = 1 - 2 * (x * x + y * y);
       }
-      if (jt != LOIK_JOINT_SPHERICAL) { pq[0] = qj[0]; pq[1] = qj[1]; pq[2] = qj[2]; }
+      if (jt == LOIK_JOINT_FF || jt == LOIK_JOINT_TRANSLATION) { pq[0] = qj[0]; pq[1] = qj[1]; pq[2] = qj[2]; }
       const double* P = J.plR;
       for (int a = 0; a < 3; ++a) {
         for (int b = 0; b < 3; ++b) st(Pf, FR_XF + 3 * a + b, P[3 * a] * M[b] + P[3 * a + 1] * M[3 + b] + P[3 * a + 2] * M[6 + b]);
@@ -470,6 +473,18 @@ __global__ void __launch_bounds__(128) k_integrate(const __grid_constant__ Model
       double M[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pq[3] = {0, 0, 0};
       if (jt == LOIK_JOINT_TRANSLATION) {
         for (int c = 0; c < 3; ++c) { pq[c] = ld(Pf, FR_Q + c) + dt * ld(Pf, FR_Z + c); st(Pf, FR_Q + c, pq[c]); }
+      } else if (jt == LOIK_JOINT_PLANAR) {
+        // SpecialEuclideanOperationTpl<2>::integrate_impl: (R0, t0) * exp(v): t = vcross - R vcross with vcross = (-vy, vx) / omega
+        const double c0 = ld(Pf, FR_Q + 2), s0 = ld(Pf, FR_Q + 3);
+        const double vx = dt * ld(Pf, FR_Z), vy = dt * ld(Pf, FR_Z + 1), om = dt * ld(Pf, FR_Z + 2);
+        double sv, cv;
+        sincos(om, &sv, &cv);
+        double tx = vx, ty = vy;
+        if (fabs(om) > 1e-14) { const double ax = -vy / om, ay = vx / om; tx = ax - (cv * ax - sv * ay); ty = ay - (sv * ax + cv * ay); }
+        pq[0] = ld(Pf, FR_Q) + (c0 * tx - s0 * ty); pq[1] = ld(Pf, FR_Q + 1) + (s0 * tx + c0 * ty);
+        const double c1 = c0 * cv - s0 * sv, s1 = s0 * cv + c0 * sv;
+        st(Pf, FR_Q, pq[0]); st(Pf, FR_Q + 1, pq[1]); st(Pf, FR_Q + 2, c1); st(Pf, FR_Q + 3, s1);
+        M[0] = c1; M[1] = -s1; M[3] = s1; M[4] = c1;
       } else {
         const int o = jt == LOIK_JOINT_FF ? 3 : 0;
         const double w0 = dt * ld(Pf, FR_Z + o), w1 = dt * ld(Pf, FR_Z + o + 1), w2 = dt * ld(Pf, FR_Z + o + 2);
@@ -788,10 +803,10 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   if (batch < 1) return fail(LOIK_ERR_INVALID, "loik_create: batch must be >= 1");
   for (int i = 1; i < nj; ++i) {
     if (model->parents[i] < 0 || model->parents[i] >= i) return fail(LOIK_ERR_INVALID, "loik_create: parents[i] must be < i");
-    if (model->joint_types[i] < 0 || model->joint_types[i] > LOIK_JOINT_TRANSLATION)
-      return fail(LOIK_ERR_UNSUPPORTED, "loik_create: unsupported joint type (1-DoF revolute/prismatic joints, free-flyer, spherical and translation joints are supported)");
+    if (model->joint_types[i] < 0 || model->joint_types[i] > LOIK_JOINT_PLANAR)
+      return fail(LOIK_ERR_UNSUPPORTED, "loik_create: unsupported joint type (1-DoF revolute/prismatic joints, free-flyer, spherical, translation and planar joints are supported)");
   }
-  auto nv_of = [&](int i) { const int t = model->joint_types[i]; return t == LOIK_JOINT_FF ? 6 : ((t == LOIK_JOINT_SPHERICAL || t == LOIK_JOINT_TRANSLATION) ? 3 : 1); };
+  auto nv_of = [&](int i) { const int t = model->joint_types[i]; return t == LOIK_JOINT_FF ? 6 : ((t == LOIK_JOINT_SPHERICAL || t == LOIK_JOINT_TRANSLATION || t == LOIK_JOINT_PLANAR) ? 3 : 1); };
   {
     int nmd = 0;
     for (int i = 1; i < nj; ++i) nmd += nv_of(i) > 1;
@@ -806,7 +821,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   auto unbounded = [&](int i) { return model->joint_types[i] >= LOIK_JOINT_RUBX && model->joint_types[i] <= LOIK_JOINT_RUBU; };
   auto nq_of = [&](int i) {
     const int t = model->joint_types[i];
-    return t == LOIK_JOINT_FF ? 7 : (t == LOIK_JOINT_SPHERICAL ? 4 : (t == LOIK_JOINT_TRANSLATION ? 3 : (unbounded(i) ? 2 : 1)));
+    return t == LOIK_JOINT_FF ? 7 : ((t == LOIK_JOINT_SPHERICAL || t == LOIK_JOINT_PLANAR) ? 4 : (t == LOIK_JOINT_TRANSLATION ? 3 : (unbounded(i) ? 2 : 1)));
   };
   h->nv = 0; h->nq = 0;
   for (int i = 1; i < nj; ++i) { h->nv += nv_of(i); h->nq += nq_of(i); }
@@ -839,7 +854,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
     // (every edge into or out of a multi-DoF joint goes through a pending block: those joints have their own step)
     J.carry = (J.parent > 0 && J.parent == i - 1 && nchild[J.parent] == 1 && nv_of(J.parent) == 1 && nv_of(i) == 1) ? 1 : 0;
     J.pout = -1; J.npin = 0;
-    J.nvj = nv_of(i); J.sel0 = model->joint_types[i] == LOIK_JOINT_SPHERICAL ? 3 : 0; J.mblk = J.nvj > 1 ? nmd++ : -1;
+    J.nvj = nv_of(i); J.sel0 = model->joint_types[i] == LOIK_JOINT_FF ? 0x543210 : (model->joint_types[i] == LOIK_JOINT_SPHERICAL ? 0x543 : (model->joint_types[i] == LOIK_JOINT_PLANAR ? 0x510 : 0x210)); J.mblk = J.nvj > 1 ? nmd++ : -1;
     J.idxv = idxv; idxv += J.nvj;
     J.idxq = idxq; idxq += nq_of(i);
     J.qkind = unbounded(i) ? 1 : 0;

@@ -61,9 +61,8 @@ def random_batch(model: RobotModel, batch: int, seed: int = 0, task_joints=None,
     for a, b_ in model.quaternion_slices():  # unit quaternions (x, y, z, w) of free-flyer / spherical joints
         quat = q[:, a:b_]
         quat /= np.linalg.norm(quat, axis=1, keepdims=True)
-    for i in range(1, model.nj):
-        if model.is_unbounded(i):  # (cos, sin) of an unbounded revolute joint
-            cs = q[:, model.idx_q(i):model.idx_q(i) + 2]
-            cs /= np.linalg.norm(cs, axis=1, keepdims=True)
+    for a, b_ in model.unit_pair_slices():  # (cos, sin) of unbounded revolute joints / of the heading of planar joints
+        cs = q[:, a:b_]
+        cs /= np.linalg.norm(cs, axis=1, keepdims=True)
     return dict(q=q, H_ref=np.eye(6), v_ref=np.zeros(6), ids=np.asarray(task_joints, np.int32),
                 Ais=np.tile(np.eye(6), (nc, 1, 1)), bis=b, lb=-model.v_max.copy(), ub=model.v_max.copy())

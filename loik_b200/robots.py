@@ -19,7 +19,8 @@ Joint type codes (shared with ``include/loik_b200.h`` and ``oracle/loik_oracle.c
     12     unbounded revolute, unaligned axis (JointModelRevoluteUnboundedUnaligned, nq = 2)
     13     spherical (JointModelSpherical, nq = 4 = unit quaternion x y z w, nv = 3, S = [0; I3])
     14     translation (JointModelTranslation, nq = nv = 3, S = [I3; 0])
-    (the multi-DoF types 8, 13, 14 may sit anywhere in the tree; the CUDA kernels take up to 8 of them per model)
+    15     planar (JointModelPlanar, nq = 4 = x y cos sin, nv = 3 = vx vy wz: S selects components 0, 1, 5)
+    (the multi-DoF types 8, 13, 14, 15 may sit anywhere in the tree; the CUDA kernels take up to 8 of them per model)
 
 Other 1-DoF joints have ``nq = nv = 1``; ``idx_q`` / ``idx_v`` follow pinocchio (cumulative over the joints in id order).
 """
@@ -30,7 +31,7 @@ import math
 
 import numpy as np
 
-RX, RY, RZ, PX, PY, PZ, RU, PU, FF, RUBX, RUBY, RUBZ, RUBU, SPH, TRA = range(15)
+RX, RY, RZ, PX, PY, PZ, RU, PU, FF, RUBX, RUBY, RUBZ, RUBU, SPH, TRA, PLA = range(16)
 _AXES = {"x": (1.0, 0.0, 0.0), "y": (0.0, 1.0, 0.0), "z": (0.0, 0.0, 1.0)}
 
 
@@ -98,11 +99,11 @@ class RobotModel:
 
     def nv_joint(self, i: int) -> int:
         jt = int(self.jtype[i])
-        return 6 if jt == FF else (3 if jt in (SPH, TRA) else 1)
+        return 6 if jt == FF else (3 if jt in (SPH, TRA, PLA) else 1)
 
     def nq_joint(self, i: int) -> int:
         jt = int(self.jtype[i])
-        return {FF: 7, SPH: 4, TRA: 3}.get(jt, 2 if RUBX <= jt <= RUBU else 1)
+        return {FF: 7, SPH: 4, TRA: 3, PLA: 4}.get(jt, 2 if RUBX <= jt <= RUBU else 1)
 
     def quaternion_slices(self):
         """(start, stop) of every unit quaternion inside q (free-flyer: q[iq+3:iq+7], spherical: q[iq:iq+4])."""
@@ -124,13 +125,22 @@ class RobotModel:
     def is_unbounded(self, i: int) -> bool:
         return RUBX <= int(self.jtype[i]) <= RUBU
 
+    def unit_pair_slices(self):
+        """(start, stop) of every (cos, sin) pair inside q: unbounded revolute joints, the heading of planar joints."""
+        out = []
+        for i in range(1, self.nj):
+            if self.is_unbounded(i):
+                out.append((self.idx_q(i), self.idx_q(i) + 2))
+            elif int(self.jtype[i]) == PLA:
+                out.append((self.idx_q(i) + 2, self.idx_q(i) + 4))
+        return out
+
     def neutral(self) -> np.ndarray:
         q = np.zeros(self.nq)
         for a, b in self.quaternion_slices():
             q[b - 1] = 1.0  # unit quaternion (x, y, z, w)
-        for i in range(1, self.nj):
-            if self.is_unbounded(i):
-                q[self.idx_q(i)] = 1.0  # (cos, sin) = (1, 0)
+        for a, b in self.unit_pair_slices():
+            q[a] = 1.0  # (cos, sin) = (1, 0)
         return q
 
     def normalize(self, q: np.ndarray) -> np.ndarray:
@@ -138,10 +148,8 @@ class RobotModel:
         q = np.array(q, np.float64)
         for a, b in self.quaternion_slices():
             q[..., a:b] /= np.linalg.norm(q[..., a:b], axis=-1, keepdims=True)
-        for i in range(1, self.nj):
-            if self.is_unbounded(i):
-                iq = self.idx_q(i)
-                q[..., iq:iq + 2] /= np.linalg.norm(q[..., iq:iq + 2], axis=-1, keepdims=True)
+        for a, b in self.unit_pair_slices():
+            q[..., a:b] /= np.linalg.norm(q[..., a:b], axis=-1, keepdims=True)
         return q
 
     def integrate(self, q: np.ndarray, v: np.ndarray) -> np.ndarray:
@@ -178,6 +186,19 @@ class RobotModel:
                 out[..., iq + o:iq + o + 4] = res
             elif jt == TRA:
                 out[..., iq:iq + 3] = q[..., iq:iq + 3] + v[..., iv:iv + 3]
+            elif jt == PLA:  # SpecialEuclideanOperationTpl<2>::integrate_impl: (R0, t0) * exp(v)
+                c0, s0 = q[..., iq + 2], q[..., iq + 3]
+                vx, vy, om = v[..., iv], v[..., iv + 1], v[..., iv + 2]
+                cv, sv = np.cos(om), np.sin(om)
+                big = np.abs(om) > 1e-14
+                oms = np.where(big, om, 1.0)
+                ax, ay = -vy / oms, vx / oms
+                tx = np.where(big, ax - (cv * ax - sv * ay), vx)
+                ty = np.where(big, ay - (sv * ax + cv * ay), vy)
+                out[..., iq] = q[..., iq] + (c0 * tx - s0 * ty)
+                out[..., iq + 1] = q[..., iq + 1] + (s0 * tx + c0 * ty)
+                out[..., iq + 2] = c0 * cv - s0 * sv
+                out[..., iq + 3] = s0 * cv + c0 * sv
             elif self.is_unbounded(i):
                 ca, sa, om = q[..., iq], q[..., iq + 1], v[..., iv]
                 co, so = np.cos(om), np.sin(om)
@@ -192,7 +213,7 @@ class RobotModel:
         assert self.parent[0] == 0
         for i in range(1, self.nj):
             assert 0 <= self.parent[i] < i, "joints must be numbered parent < child"
-            assert 0 <= self.jtype[i] <= TRA
+            assert 0 <= self.jtype[i] <= PLA
             assert abs(np.linalg.norm(self.axis[i]) - 1.0) < 1e-12
             R = self.placement_R[i]
             assert np.allclose(R @ R.T, np.eye(3), atol=1e-12)
@@ -210,12 +231,12 @@ def _build(name, joints) -> RobotModel:
     qmin, qmax, vmax, names = [], [], [], ["universe"]
     for i, (jn, par, jt, ax, xyz, rpy, lo, hi, vm) in enumerate(joints, start=1):
         parent[i] = par
-        if jt in ("FF", "S", "T"):
-            jtype[i] = {"FF": FF, "S": SPH, "T": TRA}[jt]
+        if jt in ("FF", "S", "T", "PL"):
+            jtype[i] = {"FF": FF, "S": SPH, "T": TRA, "PL": PLA}[jt]
             axis[i] = (0.0, 0.0, 1.0)
             R[i] = rpy_to_matrix(*rpy)
             p[i] = xyz
-            nqj, nvj = {"FF": (7, 6), "S": (4, 3), "T": (3, 3)}[jt]
+            nqj, nvj = {"FF": (7, 6), "S": (4, 3), "T": (3, 3), "PL": (4, 3)}[jt]
             qmin += [-1.0] * nqj   # position box; the quaternion part is normalised by the samplers
             qmax += [1.0] * nqj
             vmax += [vm] * nvj
@@ -353,7 +374,7 @@ def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0
         if continuous > 0.0 and kind == "R" and rng.random() < continuous:
             kind = "C"
         if multidof > 0.0 and rng.random() < multidof and n_md < max_multidof:  # spherical / translation / free-flyer anywhere in the tree
-            kind = ("S", "T", "FF")[int(rng.integers(0, 3))]
+            kind = ("S", "T", "FF", "PL")[int(rng.integers(0, 4))]
             n_md += 1
         if rng.random() < unaligned:
             ax = rng.normal(size=3)

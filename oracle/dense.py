@@ -44,6 +44,9 @@ def joint_subspace(jtype, axis):
         return np.vstack([np.zeros((3, 3)), np.eye(3)])
     if jtype == 14:  # translation: S = [I3; 0]
         return np.vstack([np.eye(3), np.zeros((3, 3))])
+    if jtype == 15:  # planar: (vx, vy, wz)
+        S = np.zeros((6, 3)); S[0, 0] = S[1, 1] = S[5, 2] = 1.0
+        return S
     if 9 <= jtype <= 12:  # unbounded revolute: the subspace of RX/RY/RZ/RU
         jtype = jtype - 9 if jtype < 12 else 6
     S = np.zeros((6, 1))
@@ -62,6 +65,9 @@ def joint_transform(jtype, axis, q):
     """jmodel.calc -> jdata.M(): (R, p).  q: scalar for 1-DoF joints, (x, y, z, qx, qy, qz, qw) for the free-flyer."""
     if jtype == 14:
         return np.eye(3), np.asarray(q[:3], float).copy()
+    if jtype == 15:  # planar: q = (x, y, cos, sin)
+        c, s_ = float(q[2]), float(q[3])
+        return np.array([[c, -s_, 0.0], [s_, c, 0.0], [0.0, 0.0, 1.0]]), np.array([float(q[0]), float(q[1]), 0.0])
     if jtype in (8, 13):
         x, y, z, w = q[3:7] if jtype == 8 else q[0:4]
         R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],

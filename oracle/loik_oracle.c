@@ -32,9 +32,9 @@
 
 #define LO_API __attribute__((visibility("default")))
 
-enum { JT_RX = 0, JT_RY, JT_RZ, JT_PX, JT_PY, JT_PZ, JT_RU, JT_PU, JT_FF, JT_RUBX, JT_RUBY, JT_RUBZ, JT_RUBU, JT_SPH, JT_TRA };
-static int jt_nv(int jt) { return jt == JT_FF ? 6 : ((jt == JT_SPH || jt == JT_TRA) ? 3 : 1); }
-static int jt_nq(int jt) { return jt == JT_FF ? 7 : (jt == JT_SPH ? 4 : (jt == JT_TRA ? 3 : ((jt >= JT_RUBX && jt <= JT_RUBU) ? 2 : 1))); }
+enum { JT_RX = 0, JT_RY, JT_RZ, JT_PX, JT_PY, JT_PZ, JT_RU, JT_PU, JT_FF, JT_RUBX, JT_RUBY, JT_RUBZ, JT_RUBU, JT_SPH, JT_TRA, JT_PLA };
+static int jt_nv(int jt) { return jt == JT_FF ? 6 : ((jt == JT_SPH || jt == JT_TRA || jt == JT_PLA) ? 3 : 1); }
+static int jt_nq(int jt) { return jt == JT_FF ? 7 : ((jt == JT_SPH || jt == JT_PLA) ? 4 : (jt == JT_TRA ? 3 : ((jt >= JT_RUBX && jt <= JT_RUBU) ? 2 : 1))); }
 
 typedef struct lo_solver {
   /* ---- model (what the hot path reads from pinocchio::Model) ---- */
@@ -194,6 +194,7 @@ static void joint_S(int jt, const double *axis, double *S) { /* S[6*row + col], 
     case JT_PU: S[0] = axis[0]; S[6] = axis[1]; S[12] = axis[2]; break;
     case JT_SPH: for (int k = 0; k < 3; ++k) S[6 * (3 + k) + k] = 1.0; break; /* JointModelSpherical: S = [0; I3] */
     case JT_TRA: for (int k = 0; k < 3; ++k) S[6 * k + k] = 1.0; break;       /* JointModelTranslation: S = [I3; 0] */
+    case JT_PLA: S[6 * 0 + 0] = 1.0; S[6 * 1 + 1] = 1.0; S[6 * 5 + 2] = 1.0; break; /* JointModelPlanar: (vx, vy, wz) */
     default: for (int k = 0; k < 6; ++k) S[7 * k] = 1.0; break; /* free-flyer: identity */
   }
 }
@@ -221,6 +222,11 @@ static void joint_M(int jt, const double *axis, const double *qv, double *MR, do
     return;
   }
   if (jt == JT_TRA) { Mp[0] = qv[0]; Mp[1] = qv[1]; Mp[2] = qv[2]; return; }
+  if (jt == JT_PLA) { /* JointModelPlanar::calc: rotation about z from (cos, sin) = (q[2], q[3]) as given, translation (x, y, 0) */
+    MR[0] = qv[2]; MR[1] = -qv[3]; MR[3] = qv[3]; MR[4] = qv[2];
+    Mp[0] = qv[0]; Mp[1] = qv[1];
+    return;
+  }
   if (jt == JT_FF || jt == JT_SPH) { /* q = (x, y, z, qx, qy, qz, qw): M = (R(quat), p); spherical: q = (qx, qy, qz, qw), p = 0 */
     const int o = jt == JT_FF ? 3 : 0;
     const double x = qv[o], y = qv[o + 1], z = qv[o + 2], w = qv[o + 3];
@@ -1051,6 +1057,13 @@ static void integrate_q(const lo_solver *s, double *q, const double *v, double d
       }
       const double nrm = (3.0 - (r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3])) / 2.0;
       for (int c = 0; c < 4; ++c) qt[c] = r[c] * nrm;
+    } else if (jt == JT_PLA) { /* SpecialEuclideanOperationTpl<2>::integrate_impl: (R0, t0) * exp(v) */
+      const double c0 = q[iq + 2], s0 = q[iq + 3], vx = dt * v[iv], vy = dt * v[iv + 1], om = dt * v[iv + 2];
+      const double cv = cos(om), sv = sin(om);
+      double tx = vx, ty = vy;
+      if (fabs(om) > 1e-14) { const double ax = -vy / om, ay = vx / om; tx = ax - (cv * ax - sv * ay); ty = ay - (sv * ax + cv * ay); }
+      q[iq] += c0 * tx - s0 * ty; q[iq + 1] += s0 * tx + c0 * ty;
+      q[iq + 2] = c0 * cv - s0 * sv; q[iq + 3] = s0 * cv + c0 * sv;
     } else { /* vector-space joints (1-DoF, translation) */
       for (int k = 0; k < s->nvj[i]; ++k) q[iq + k] += dt * v[iv + k];
     }

@@ -40,9 +40,10 @@ def _solve_init(G, pb):
     G.SolveInit(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
 
 
-def _compare_steps(model, params, pb, n_iters, what):
+def _compare_steps(model, params, pb, n_iters, what, tol=None):
     """Step-by-step: after each fused CUDA step compare every field the oracle exposes at the same point."""
     B = pb["q"].shape[0]
+    STEP_TOL = tol if tol is not None else globals()["STEP_TOL"]
     G = _gpu(model, params, B)
     G.set_debug(True)
     _solve_init(G, pb)
@@ -91,19 +92,19 @@ def _compare_steps(model, params, pb, n_iters, what):
         prv, drv = G.get_primal_residual_vec(), G.get_dual_residual_vec()
         for i, o in enumerate(O):
             fscale = max(1.0, np.abs(o.fis).max())
-            assert np.abs(F[i] - o.fis_diff_plus_Aty[1:]).max() < 1e-12 * fscale * 10, tag + " fis_diff_plus_Aty"
-            assert np.abs(T[i] - o.Stf_plus_w).max() < 1e-12 * fscale * 10, tag + " Stf_plus_w"
+            assert np.abs(F[i] - o.fis_diff_plus_Aty[1:]).max() < (STEP_TOL * 1e-2) * fscale * 10, tag + " fis_diff_plus_Aty"
+            assert np.abs(T[i] - o.Stf_plus_w).max() < (STEP_TOL * 1e-2) * fscale * 10, tag + " Stf_plus_w"
             check_abs_or_rel(prv[i], o.get_primal_residual_vec(), STEP_TOL, tag + " primal_residual_vec")
-            assert np.abs(drv[i] - o.get_dual_residual_vec()).max() < 1e-12 * fscale * 10, tag + " dual_residual_vec"
+            assert np.abs(drv[i] - o.get_dual_residual_vec()).max() < (STEP_TOL * 1e-2) * fscale * 10, tag + " dual_residual_vec"
             check_abs_or_rel(res[i, 0], o.get_primal_residual(), STEP_TOL, tag + " primal_residual")
-            assert abs(res[i, 1] - o.get_dual_residual()) < 1e-12 * fscale * 10, tag + " dual_residual"
+            assert abs(res[i, 1] - o.get_dual_residual()) < (STEP_TOL * 1e-2) * fscale * 10, tag + " dual_residual"
             check_abs_or_rel(res[i, 2], o.get_tol_primal(), STEP_TOL, tag + " tol_primal")
-            check_abs_or_rel(res[i, 3], o.get_tol_dual(), 1e-9, tag + " tol_dual")
+            check_abs_or_rel(res[i, 3], o.get_tol_dual(), max(1e-9, 10 * STEP_TOL), tag + " tol_dual")
             for nm in ("Av_inf_norm", "nu_inf_norm", "delta_vis_inf_norm", "delta_z_inf_norm", "delta_fis_inf_norm",
                        "delta_yis_inf_norm", "delta_w_inf_norm", "bT_delta_y_plus", "bT_delta_y_minus",
                        "primal_residual_task", "primal_residual_slack"):
                 ref = o.scalar(nm)
-                assert abs(nrm[nm][i] - ref) <= 1e-9 * max(1.0, abs(ref)) * (fscale if "fis" in nm else 1.0), f"{tag} {nm}"
+                assert abs(nrm[nm][i] - ref) <= max(1e-9, 10 * STEP_TOL) * max(1.0, abs(ref)) * (fscale if "fis" in nm else 1.0), f"{tag} {nm}"
             if it > 1:
                 assert bool(nrm["primal_infeasibility_cond_1"][i]) == o.get_primal_infeasibility_cond_1(), tag
                 assert bool(nrm["primal_infeasibility_cond_2"][i]) == o.get_primal_infeasibility_cond_2(), tag
@@ -612,7 +613,9 @@ def test_multi_dof_joints_anywhere_step_by_step(seed, multidof, continuous):
     model = robots.random_tree(9 + seed, 40 + seed, continuous=continuous, multidof=multidof)
     assert any(model.nv_joint(i) > 1 for i in range(1, model.nj))
     pb = _multidof_problem(model, 33, seed)
-    _compare_steps(model, dict(problems.FIXTURE_PARAMS, max_iter=200, num_eq_c=2), pb, 3, f"mdtree{seed}")
+    # several free-flyers in series: H - H (H + mu I)^-1 H below each of them is a difference of nearly equal matrices
+    # (mu = 1e-2 next to task weights of 1e2): rounding differences between two orders of evaluation reach a few 1e-10
+    _compare_steps(model, dict(problems.FIXTURE_PARAMS, max_iter=200, num_eq_c=2), pb, 3, f"mdtree{seed}", tol=5e-9)
 
 
 @pytest.mark.parametrize("seed,multidof", [(0, 0.3), (1, 0.5), (2, 1.0)])

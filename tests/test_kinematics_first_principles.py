@@ -36,6 +36,8 @@ def _fk(model, q):
             pj = q[iq:iq + 3].copy() if jt == 8 else np.zeros(3)
         elif jt == 14:
             Rj, pj = np.eye(3), q[iq:iq + 3].copy()
+        elif jt == 15:  # planar: x, y, heading (cos, sin)
+            Rj, pj = _rot([0, 0, 1.0], np.arctan2(q[iq + 3], q[iq + 2])), np.array([q[iq], q[iq + 1], 0.0])
         elif jt <= 2 or jt == 6:
             Rj, pj = _rot(ax, q[iq]), np.zeros(3)
         elif 9 <= jt <= 12:
@@ -77,6 +79,11 @@ def _move(model, q, v):
             out[qs] = _quat_mul(q[qs], dq)
         elif jt == 14:
             out[iq:iq + 3] = q[iq:iq + 3] + v[iv:iv + 3]
+        elif jt == 15:  # body-frame (vx, vy, wz), first order in |v|
+            th = np.arctan2(q[iq + 3], q[iq + 2])
+            out[iq] = q[iq] + np.cos(th) * v[iv] - np.sin(th) * v[iv + 1]
+            out[iq + 1] = q[iq + 1] + np.sin(th) * v[iv] + np.cos(th) * v[iv + 1]
+            out[iq + 2], out[iq + 3] = np.cos(th + v[iv + 2]), np.sin(th + v[iv + 2])
         elif 9 <= jt <= 12:
             th = np.arctan2(q[iq + 1], q[iq]) + v[iv]
             out[iq], out[iq + 1] = np.cos(th), np.sin(th)
@@ -145,7 +152,7 @@ def test_integrate_is_the_group_exponential():
                          [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
 
     J = [("ff", 0, "FF", None, (0, 0, 0), (0, 0, 0), None, None, 1.0), ("s", 1, "S", None, (0.1, 0, 0), (0, 0, 0), None, None, 1.0),
-         ("r", 2, "R", "z", (0, 0, 0.2), (0, 0, 0), -2, 2, 1.0)]
+         ("r", 2, "R", "z", (0, 0, 0.2), (0, 0, 0), -2, 2, 1.0), ("pl", 3, "PL", None, (0, 0.1, 0), (0, 0, 0), None, None, 1.0)]
     m = robots._build("ff_sph", J)
     rng = np.random.default_rng(0)
     for scale in (1e-7, 1e-3, 0.3, 2.0):
@@ -159,12 +166,18 @@ def test_integrate_is_the_group_exponential():
             assert np.abs(rq(q1[3:7]) - M1[:3, :3]).max() < 1e-12 and np.abs(q1[:3] - M1[:3, 3]).max() < 1e-12
             assert np.abs(rq(q1[7:11]) - rq(q[7:11]) @ sl.expm(skew(v[6:9]))).max() < 1e-12
             assert abs(q1[11] - (q[11] + v[9])) < 1e-15
+            # planar joint: SE(2) as a 3x3 homogeneous matrix
+            P0 = np.array([[q[14], -q[15], q[12]], [q[15], q[14], q[13]], [0, 0, 1.0]])
+            Xp = np.array([[0, -v[12], v[10]], [v[12], 0, v[11]], [0, 0, 0.0]])
+            P1 = P0 @ sl.expm(Xp)
+            assert np.abs(np.array([[q1[14], -q1[15], q1[12]], [q1[15], q1[14], q1[13]], [0, 0, 1.0]]) - P1).max() < 1e-12
     # the C tracking driver integrates the same way (one step, dt = 0.05): compare the configurations it ends with
     B = 16
     pb = dict(q=m.normalize(rng.normal(size=(B, m.nq))), H_ref=np.eye(6), v_ref=np.zeros(6), ids=np.array([3], np.int32),
               Ais=np.eye(6)[None], bis=rng.uniform(-0.3, 0.3, size=(B, 1, 6)), lb=-m.v_max, ub=m.v_max)
+    pb["ids"] = np.array([4], np.int32)
     params = dict(problems.bench_params(1), warm_start=True)
     trk = recursion.batch_track(m, params, pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["bis"], pb["lb"],
-                                pb["ub"], c_id=3, dt=0.05, steps=1, warm=True)
+                                pb["ub"], c_id=4, dt=0.05, steps=1, warm=True)
     full = recursion.batch_solve(m, params, pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
     np.testing.assert_allclose(trk["q"], m.integrate(pb["q"], 0.05 * full["z"]), rtol=0, atol=1e-14)
