@@ -146,6 +146,9 @@ __host__ __device__ __forceinline__ constexpr int si(int i, int j) { return i <=
 LOIK_DEV double* tile_ptr(const StateP& S, const ModelC& c_model, int s) { return S.arena + ((size_t)(s >> 5) * c_model.off.rows) * 32 + (s & 31); }
 LOIK_DEV double ld(const double* P, int row) { return P[row * 32]; }
 LOIK_DEV void st(double* P, int row, double x) { P[row * 32] = x; }
+// rows read once per iteration and rewritten by the same sweep (F = fis_diff_plus_Aty, T = Stf_plus_w): streaming hints
+LOIK_DEV double ld_cs(const double* P, int row) { return __ldcs(P + row * 32); }
+LOIK_DEV void st_cs(double* P, int row, double x) { __stcs(P + row * 32, x); }
 // block base pointers: computed once per joint step, rows inside a block are immediates
 LOIK_DEV double* joint_blk(double* T, const Offs& O, int ji) { return T + (size_t)(O.joint0 + JR_ROWS * ji) * 32; }
 LOIK_DEV double* task_blk(double* T, const Offs& O, int k) { return T + (size_t)(O.task0 + TR_ROWS * k) * 32; }
@@ -697,10 +700,10 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, const double* Ts, double* Td
     }
     // ---- load phase
     double f[6], F[6], v[6], Fold[6];
-    const double w_i = ld(Pj, JR_W), T_old = ld(Ps, JR_T);
+    const double w_i = ld(Pj, JR_W), T_old = ld_cs(Ps, JR_T);
     const double qa = ld(Pj, JR_JQ), qb = ld(Pj, JR_JQ + 1);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { f[c] = ld(Pj, JR_F + c); v[c] = ld(Pj, JR_V + c); Fold[c] = ld(Ps, JR_FD + c); }
+    for (int c = 0; c < 6; ++c) { f[c] = ld(Pj, JR_F + c); v[c] = ld(Pj, JR_V + c); Fold[c] = ld_cs(Ps, JR_FD + c); }
     if (J.task >= 0) {
       const double* Pk = task_blk(Td, O, J.task);
 #pragma unroll
@@ -747,10 +750,10 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, const double* Ts, double* Td
     // ---- store phase
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      st(Pj, JR_FD + c, F[c]);
+      st_cs(Pj, JR_FD + c, F[c]);
       if (DEBUG) st(Td, O.drv + 6 * ji + c, rd[c]);
     }
-    st(Pj, JR_T, Tn);
+    st_cs(Pj, JR_T, Tn);
     if (DEBUG) st(Td, O.drv + 6 * nb + J.idxv, Tn);
     have_carry = false;
     if (J.parent > 0) {  // fis_diff_plus_Aty[parent] += liMi.act(f_i) (:212)
