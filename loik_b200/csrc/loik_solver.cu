@@ -952,7 +952,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
     std::vector<int> all;
     const int ncq = h->nc;
     auto per_joint = [&](std::vector<int>& m, int jr, int width) { for (int j = 0; j < nb; ++j) for (int c = 0; c < width; ++c) m.push_back(O.joint0 + JR_ROWS * j + jr + c); };
-    // one row per dof: the free-flyer root contributes 6 rows of its own block (fr < 0: no such quantity -> zeros)
+    // one row per dof: a multi-DoF joint contributes nv rows of its own block (fr < 0: no such quantity -> zeros)
     auto per_dof = [&](std::vector<int>& m, int jr, int fr) {
       for (int j = 0; j < nb; ++j) {
         if (M.j[j + 1].nvj > 1) { for (int c = 0; c < M.j[j + 1].nvj; ++c) m.push_back(fr < 0 ? -1 : O.ff0 + FR_ROWS * M.j[j + 1].mblk + fr + c); }
@@ -977,7 +977,7 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
         case LOIK_F_FDPA: per_joint(m, JR_FD, 6); break;
         case LOIK_F_STF_PLUS_W: per_dof(m, JR_T, FR_T); break;
         case LOIK_F_P: per_joint(m, JR_P, 6); break;
-        case LOIK_F_UDINV: per_joint_noff(m, JR_UD, 6); break;  // (zeros for a free-flyer root: its UDinv never enters the solution)
+        case LOIK_F_UDINV: per_joint_noff(m, JR_UD, 6); break;  // (zeros for multi-DoF joints: their 6 x K UDinv / K x K Dinv are not exposed per joint)
         case LOIK_F_DINV: per_joint_noff(m, JR_DINV, 1); break;
         case LOIK_F_R: per_dof(m, JR_R, FR_R); break;
         case LOIK_F_MU: span(m, O.glob + GR_MU, 1); break;
