@@ -220,6 +220,14 @@ LOIK_API int loik_reset_recursion(loik_solver* h, void* stream);
 LOIK_API int loik_step(loik_solver* h, int32_t step_id, void* stream);
 /* Keep the reference's running norms, feasibility scalars and residual vectors readable (slower). */
 LOIK_API int loik_set_debug(loik_solver* h, int32_t on);
+/* The reference leaves the workspace of the last backward pass in the caller's data after Solve(): His, pis
+ * (ik_id_data, read by tests/loik-loid.cpp:597-615) and jdata.UDinv()/Dinv(), r.  A batched solve packs the
+ * still-active instances into dense tiles as it goes, and by default only the state rows of a finished instance
+ * return to its slot.  on != 0: the workspace rows return too (35 more rows per joint and solve, once), so
+ * LOIK_F_H / _P / _UDINV / _DINV / _R are valid after loik_solve*.  Off (default), loik_get of those fields after a
+ * solve fails with LOIK_ERR_STATE instead of returning stale rows; after the in-place steps (loik_step,
+ * loik_iterate_fixed, loik_solve_chunk) they are always valid. */
+LOIK_API int loik_set_keep_workspace(loik_solver* h, int32_t on);
 
 /* ---- results --------------------------------------------------------------------------------- */
 /* Copy a per-instance field of all `batch` instances to dst ([batch][field shape], batch-major).

@@ -154,6 +154,9 @@ class FirstOrderLoikOptimized {
   // tests/loik-loid.cpp:340-478): the per-step methods one by one and the feasibility scalars.  They need
   // set_debug(true) (the production path fuses the steps and keeps no running norms) and work on every instance.
   void set_debug(bool on) { check(loik_set_debug(h_, on ? 1 : 0)); }
+  // His() / pis() after Solve(), as the reference leaves them in ik_id_data (tests/loik-loid.cpp:597-615): opt-in, a
+  // finished instance then brings its backward-pass workspace home too (off: those getters throw after a solve)
+  void set_keep_workspace(bool on) { check(loik_set_keep_workspace(h_, on ? 1 : 0)); }
   void ResetSolver() { check(loik_reset_recursion(h_, stream_)); }  // Solve()'s ResetRecursion + ResetSolver (hpp:370-374)
   void FwdPassInit(const std::vector<double>& q) { check(loik_fwd_pass_init(h_, q.data(), LOIK_HOST, stream_)); }
   void UpdatePrev() { step(LOIK_STEP_UPDATE_PREV); }
@@ -178,8 +181,8 @@ class FirstOrderLoikOptimized {
   void Solve(int c_id, const std::vector<double>& Ai, const std::vector<double>& bi) {
     check(loik_solve_task(h_, nullptr, c_id, Ai.data(), bi.data(), bi.size() == (size_t)batch_ * 6 && batch_ > 1 ? 1 : 0, LOIK_HOST, stream_));
   }
-  std::vector<double> His() const { return get(LOIK_F_H, 36 * (model_.njoints - 1)); }   // debug mode
-  std::vector<double> pis() const { return get(LOIK_F_P, 6 * (model_.njoints - 1)); }    // debug mode
+  std::vector<double> His() const { return get(LOIK_F_H, 36 * (model_.njoints - 1)); }   // after the per-step methods, or after Solve() with set_keep_workspace(true)
+  std::vector<double> pis() const { return get(LOIK_F_P, 6 * (model_.njoints - 1)); }    // same
   std::vector<double> Aty() const { return get(LOIK_F_ATY, 6 * nc_); }
   std::vector<double> get_primal_residual_vec() const { return get(LOIK_F_PRIMAL_RES_VEC, 6 * (model_.njoints - 1) + model_.nv); }
   std::vector<double> get_dual_residual_vec() const { return get(LOIK_F_DUAL_RES_VEC, 6 * (model_.njoints - 1) + model_.nv); }

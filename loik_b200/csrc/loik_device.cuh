@@ -131,6 +131,7 @@ struct StateP {
   int* next_list;
   int* next_count;
   double* home;
+  int keep_ws;        // retiring instances also carry their backward->forward workspace home (loik_set_keep_workspace)
 };
 
 // The batch-uniform block (model, problem constants, hyper-parameters) is passed to every kernel BY VALUE as a

@@ -17,7 +17,10 @@
 
 namespace loik {
 
-constexpr int kBlock = 64;  // threads per CTA of the sweep kernels (2 warps = 2 tiles)
+#ifndef LOIK_KBLOCK
+#define LOIK_KBLOCK 64
+#endif
+constexpr int kBlock = LOIK_KBLOCK;  // threads per CTA of the sweep kernels (2 warps = 2 tiles)
 
 // ---------------------------------------------------------------------------------------------
 // kernels
@@ -59,6 +62,23 @@ LOIK_DEV void retire_rows(const ModelC& c_model, const double* Ts, double* Th) {
     double* Pd = task_blk(Th, O, t);
 #pragma unroll
     for (int r = 0; r < TR_B; ++r) st(Pd, r, ld(Ps, r));  // y, Aty
+  }
+}
+
+// Opt-in (loik_set_keep_workspace): the workspace of the last backward pass (His, pis, UDinv, Dinv, r -- what the
+// reference leaves in ik_id_data / jdata after Solve()) follows a retiring instance home too.  Out of line: a rare
+// path that must not take part in the register allocation of the sweeps.
+LOIK_DEV_CALL void retire_workspace(const ModelC& c_model, const double* Ts, double* Th) {
+  const Offs& O = c_model.off;
+  for (int j = 0; j < c_model.nb; ++j) {
+    const double* Ps = joint_blk(const_cast<double*>(Ts), O, j);
+    double* Pd = joint_blk(Th, O, j);
+    for (int r = JR_H; r < JR_ROWS; ++r) st(Pd, r, ld(Ps, r));
+  }
+  for (int m = 0; m < c_model.nmd; ++m) {
+    const double* Ps = md_blk(const_cast<double*>(Ts), O, m);
+    double* Pd = md_blk(Th, O, m);
+    for (int r = FR_DINV; r < FR_ROWS; ++r) st(Pd, r, ld(Ps, r));
   }
 }
 
@@ -139,7 +159,11 @@ __global__ void __launch_bounds__(kBlock) __maxnreg__(MINB <= 4 ? 255 : (65536 /
       active = status < ST_CONVERGED;
       if (!active && S.home) {  // finished away from home: the results go to the home slot now
         const int* origin = MIG ? S.origin_dst : S.origin_src;
-        if (origin) retire_rows(c_model, Td, tile_of(S.home, c_model, origin[MIG ? k : s]));
+        if (origin) {
+          double* Th = tile_of(S.home, c_model, origin[MIG ? k : s]);
+          retire_rows(c_model, Td, Th);
+          if (S.keep_ws) retire_workspace(c_model, Td, Th);
+        }
       }
     }
   }
@@ -258,7 +282,11 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
         // (the last iteration's stores of the other warps are ordered before this by the barrier that ends it)
         if (!active && S.home) {
           const int* origin = MIG ? S.origin_dst : S.origin_src;
-          if (origin) retire_rows(c_model, Td, tile_of(S.home, c_model, origin[MIG ? k : s]));
+          if (origin) {
+            double* Th = tile_of(S.home, c_model, origin[MIG ? k : s]);
+            retire_rows(c_model, Td, Th);
+            if (S.keep_ws) retire_workspace(c_model, Td, Th);
+          }
         }
       }
     }
@@ -667,6 +695,9 @@ struct loik_solver {
   ModelC mc{};          // host copy of this solver's constant block
   bool problem_set = false;
   bool debug = false;
+  // backward->forward workspace (His, pis, UDinv, Dinv, r) of the home arena is the last backward pass of every
+  // instance: true after in-place steps, false after a scheduled solve whose instances migrated without keep_ws
+  bool ws_valid = true;
   double* arena = nullptr;  // tile records
   int* d_lists = nullptr;   // two compaction lists of `batch` ints
   double* scratch[2] = {nullptr, nullptr};  // packed arenas (allocated at the first solve)
@@ -690,7 +721,7 @@ struct loik_solver {
   // CUDA-graph cache of (reset +) the launch schedule: one graph launch per solve instead of ~60 kernel launches
   cudaGraphExec_t g_exec = nullptr;
   ModelC g_mc{};
-  int g_flags = -1, g_budget = -1, g_dense = -1;
+  int g_flags = -1, g_budget = -1, g_dense = -1, g_keep = -1;
   int64_t g_launches = 0, g_sweeps = 0;
   bool use_graph = true;
   // the latency-bound tail rounds run on a high-priority stream so their few CTAs are dispatched ahead of the
@@ -1048,6 +1079,7 @@ static int launch_reset(loik_solver* h, int flags, cudaStream_t st) {
   h->launches++;
   h->last_list = -1;
   h->sweeps_in_solve = 0;
+  if (flags & RST_SOLVER) h->ws_valid = true;  // every instance is active again: the next backward pass rewrites all of it
   CK(cudaGetLastError());
   return LOIK_OK;
 }
@@ -1119,6 +1151,7 @@ int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const 
   // ik_id_data_.Reset(warm_start) + ResetSolver() + FwdPassInit's y/Aty wipe (hpp:346-359, hxx:270-278)
   const int flags = RST_SOLVER | (h->prm.warm_start ? 0 : (RST_WZ | RST_NU | RST_VFF | RST_YATY));
   k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, flags);
+  h->ws_valid = true;
   k_set_q<<<grid_for(B), kBlock, kBlock * h->nq * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);
   h->launches += 2;
   h->last_list = -1;
@@ -1237,7 +1270,7 @@ static int run_schedule(loik_solver* h, cudaStream_t st0, int budget) {
 
 // (reset +) schedule, replayed from a CUDA graph when the stream can be captured (any stream but the legacy default
 // one).  The graph is re-captured when the parameter block, the reset flags or the iteration budget change.
-static int solve_scheduled(loik_solver* h, cudaStream_t st, int reset_flags, int budget) {
+static int solve_scheduled_impl(loik_solver* h, cudaStream_t st, int reset_flags, int budget) {
   int rc = ensure_scratch(h);
   if (rc) return rc;
   const bool graphable = h->use_graph && st != nullptr && st != cudaStreamLegacy && !h->debug;
@@ -1246,7 +1279,7 @@ static int solve_scheduled(loik_solver* h, cudaStream_t st, int reset_flags, int
     h->last_list = -1; h->sweeps_in_solve = 0;
     return budget >= 1 ? run_schedule(h, st, budget) : LOIK_OK;
   }
-  const bool valid = h->g_exec && h->g_flags == reset_flags && h->g_budget == budget && h->g_dense == h->dense_sweeps &&
+  const bool valid = h->g_exec && h->g_flags == reset_flags && h->g_budget == budget && h->g_dense == h->dense_sweeps && h->g_keep == h->S.keep_ws &&
                      std::memcmp(&h->g_mc, &h->mc, sizeof(ModelC)) == 0;
   if (!valid) {
     if (h->g_exec) { cudaGraphExecDestroy(h->g_exec); h->g_exec = nullptr; }
@@ -1262,7 +1295,7 @@ static int solve_scheduled(loik_solver* h, cudaStream_t st, int reset_flags, int
     const cudaError_t ie = cudaGraphInstantiate(&h->g_exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ie != cudaSuccess) { h->g_exec = nullptr; return fail(LOIK_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
-    h->g_mc = h->mc; h->g_flags = reset_flags; h->g_budget = budget; h->g_dense = h->dense_sweeps;
+    h->g_mc = h->mc; h->g_flags = reset_flags; h->g_budget = budget; h->g_dense = h->dense_sweeps; h->g_keep = h->S.keep_ws;
     h->g_launches = h->launches - l0; h->g_sweeps = h->sweeps - s0;
     h->launches = l0; h->sweeps = s0;  // counted per replay below
   }
@@ -1270,6 +1303,14 @@ static int solve_scheduled(loik_solver* h, cudaStream_t st, int reset_flags, int
   h->launches += h->g_launches; h->sweeps += h->g_sweeps;
   h->last_list = -1; h->sweeps_in_solve = 0;
   return LOIK_OK;
+}
+
+static int solve_scheduled(loik_solver* h, cudaStream_t st, int reset_flags, int budget) {
+  const int rc = solve_scheduled_impl(h, st, reset_flags, budget);
+  // the dense sweeps run in place; instances that finish in the migrating launches after them only bring their
+  // workspace home with keep_ws
+  if (budget > h->dense_sweeps && !h->S.keep_ws) h->ws_valid = false;
+  return rc;
 }
 
 int loik_fwd_pass_init(loik_solver* h, const double* q, int32_t loc, void* stream) {
@@ -1350,6 +1391,7 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
   rc = to_device(h, bi, b_bytes, loc, q_bytes, st, &db); if (rc) return rc;
   const int flags = RST_SOLVER | (h->prm.warm_start ? 0 : (RST_WZ | RST_NU | RST_VFF | RST_YATY));
   k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, flags);
+  h->ws_valid = true;
   k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)db, b_per_instance, k);
   if (q) k_set_q<<<grid_for(B), kBlock, kBlock * h->nq * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);  // else: keep the device-resident q (loik_integrate)
   h->launches += 3;
@@ -1446,6 +1488,12 @@ int loik_step(loik_solver* h, int32_t step_id, void* stream) {
   return LOIK_OK;
 }
 
+int loik_set_keep_workspace(loik_solver* h, int32_t on) {
+  if (!h) return fail(LOIK_ERR_INVALID, "null handle");
+  h->S.keep_ws = on != 0;
+  return LOIK_OK;
+}
+
 int loik_set_debug(loik_solver* h, int32_t on) {
   if (!h) return fail(LOIK_ERR_INVALID, "null handle");
   h->debug = on != 0;
@@ -1461,6 +1509,10 @@ int loik_get(loik_solver* h, int32_t field, void* dst, int32_t loc, void* stream
   const Offs& O = h->mc.off;
   if (field < 0 || field > LOIK_F_Q) return fail(LOIK_ERR_INVALID, "loik_get: unknown field");
   const bool is_int = field == LOIK_F_ITER || field == LOIK_F_STATUS;
+  const bool is_ws = field == LOIK_F_H || field == LOIK_F_P || field == LOIK_F_UDINV || field == LOIK_F_DINV || field == LOIK_F_R;
+  if (is_ws && !h->ws_valid)
+    return fail(LOIK_ERR_STATE, "loik_get: the backward-pass workspace (His, pis, UDinv, Dinv, r) of the last solve was not kept; "
+                                "call loik_set_keep_workspace(h, 1) before solving");
   const int rows = is_int ? 1 : (field == LOIK_F_LIMI ? 12 * nb : h->map_len[field]);
   (void)nc; (void)O;
   const size_t bytes = (size_t)B * rows * (is_int ? sizeof(int) : sizeof(double));

@@ -41,7 +41,7 @@ NORM_NAMES = ["bT_delta_y_plus", "bT_delta_y_minus", "Av_inf_norm", "nu_inf_norm
 
 EXPORTS = ["loik_abi_version", "loik_last_error", "loik_create", "loik_destroy", "loik_solve_init",
            "loik_update_references", "loik_solve", "loik_solve_full", "loik_solve_task", "loik_integrate", "loik_iterate_fixed",
-           "loik_fwd_pass_init", "loik_reset_recursion", "loik_step", "loik_set_debug", "loik_get", "loik_get_stats", "loik_reduce_stats", "loik_launch_count",
+           "loik_fwd_pass_init", "loik_reset_recursion", "loik_step", "loik_set_debug", "loik_set_keep_workspace", "loik_get", "loik_get_stats", "loik_reduce_stats", "loik_launch_count",
            "loik_set_max_iter", "loik_set_rho", "loik_set_mu", "loik_set_tol_tail_solve", "loik_set_warm_start",
            "loik_active_count_device_ptr", "loik_solve_begin", "loik_solve_chunk", "loik_solve_end"]
 
@@ -88,6 +88,7 @@ def load_library(path: str | None = None):
     lib.loik_fwd_pass_init.argtypes = [vp, dp, i32, vp]
     lib.loik_step.argtypes = [vp, i32, vp]
     lib.loik_set_debug.argtypes = [vp, i32]
+    lib.loik_set_keep_workspace.argtypes = [vp, i32]
     lib.loik_get.argtypes = [vp, i32, vp, i32, vp]
     lib.loik_get_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.loik_reduce_stats.argtypes = [vp, vp, C.POINTER(vp)]
@@ -328,6 +329,12 @@ class FirstOrderLoikOptimized:
 
     def set_debug(self, on=True):
         self._check(self._lib.loik_set_debug(self._h, int(bool(on))))
+
+    def set_keep_workspace(self, on=True):
+        """His / pis / UDinv / Dinv / r of the last backward pass stay readable after Solve(), as the reference leaves
+        them in ik_id_data (tests/loik-loid.cpp:597-615); off, those getters raise after a solve instead of returning
+        stale rows."""
+        self._check(self._lib.loik_set_keep_workspace(self._h, int(bool(on))))
 
     # chunked solve for the multi-GPU driver
     def SolveBegin(self):
