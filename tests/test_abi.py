@@ -75,3 +75,17 @@ def test_model_validation_needs_no_gpu():
         solver.make_solver(many, P, 4)
     with pytest.raises(RuntimeError, match="equality constraint dimension is not 6"):
         solver.make_solver(robots.panda(), dict(P, eq_c_dim=3), 4)
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """The boundary is a C ABI: the header must compile on its own as C99 and as C++ (no CUDA / torch types)."""
+    import shutil
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    cases = [("gcc", "t.c", ["-std=c99", "-pedantic", "-Werror"]), ("g++", "t.cpp", ["-std=c++17", "-Werror"])]
+    for cc, fname, flags in cases:
+        if not shutil.which(cc):
+            pytest.skip(f"{cc} not installed")
+        src = tmp_path / fname
+        src.write_text('#include "loik_b200.h"\nint main(void) { loik_params p; loik_model_desc m; (void)p; (void)m; return (int)sizeof(loik_solver*) == 0; }\n')
+        subprocess.check_call([cc, *flags, "-Wall", "-fsyntax-only", "-I", inc, str(src)])
