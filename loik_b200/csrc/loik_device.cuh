@@ -389,10 +389,21 @@ LOIK_DEV void actinv_motion(const double (&R)[9], const double (&t)[3], const do
 // above a store to a possibly-aliasing row, so interleaving them would serialise on DRAM latency).
 // ---------------------------------------------------------------------------------------------
 LOIK_DEV double ldc(const double* T, int row) { return __ldg(T + row * 32); }  // read-only data (never a row this launch writes)
-// Software prefetch of the NEXT joint step's rows into L2, issued at the top of the current step: the sweeps are
-// chains of dependent steps, each starting with a batch of loads, and with 8 resident warps per SM the DRAM
-// latency of that batch is exposed; a prefetch costs no register and turns it into an L2 hit.
-LOIK_DEV void pf(const double* P, int row) { asm volatile("prefetch.global.L2 [%0];" ::"l"(P + row * 32)); }
+// Software prefetch of the NEXT joint step's rows, issued at the top of the current step: the sweeps are chains of
+// dependent steps, each starting with a batch of loads, and with 8 resident warps per SM the latency of that batch is
+// exposed; a prefetch costs no register.  Target L1 (CCTL.E.PF1), and cover the rows this iteration wrote one sweep
+// earlier as well (the backward sweep's workspace for the forward step, f / v / w for the residual step): they are
+// still in L2, but with several solves in flight an L2 hit is slow enough to matter -- pipelined Panda 67.5 -> 69.2 M
+// solves/s, UR10 110.7 -> 113.6 M, Talos 6.59 -> 6.73 M; a dense launch timed alone pays 2 % for the extra
+// instructions (84.3 -> 86.0 us).  L1 instead of L2 with the old coverage: no difference; the L1 carve-out alone: no
+// difference (profiles/r1_history.md).  -DLOIK_PF_BASIC = the old coverage, -DLOIK_PF_LEVEL=\"L2\" = the old target.
+#ifndef LOIK_PF_LEVEL
+#define LOIK_PF_LEVEL "L1"
+#endif
+#ifndef LOIK_PF_BASIC
+#define LOIK_PF_EXT 1
+#endif
+LOIK_DEV void pf(const double* P, int row) { asm volatile("prefetch.global." LOIK_PF_LEVEL " [%0];" ::"l"(P + row * 32)); }
 template <int N>
 LOIK_DEV void pf_rows(const double* P, int row0) {
 #pragma unroll
@@ -560,7 +571,12 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, const double* Ts, double* Td,
       const double* Pn = joint_blk(const_cast<double*>(Ts), O, ji + 1);
       const double* Pnd = joint_blk(Td, O, ji + 1);
       pf_rows<6>(Pn, JR_V); pf_rows<6>(Pn, JR_F); pf(Pn, JR_NU); pf(Pn, JR_Z); pf(Pn, JR_W); pf_rows<2>(Pnd, JR_JQ);
+#ifdef LOIK_PF_EXT
+      pf_rows<35>(Pnd, JR_H);  // (L1 prefetch: also what is still in L2)
+      if (c_model.bounds_per_instance) pf_rows<2>(Pnd, JR_LB);
+#else
       if (nb > 16) pf_rows<35>(Pnd, JR_H);  // long trees: the workspace written by the backward sweep has left L2 by now
+#endif
       const int kt = c_model.j[i + 1].task;
       if (kt >= 0) { pf_rows<6>(task_blk(Td, O, kt), TR_B); pf_rows<6>(task_blk(const_cast<double*>(Ts), O, kt), TR_Y); }
     }
@@ -698,6 +714,12 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, const double* Ts, double* Td
     if (i > lo) {
       const double* Pn = joint_blk(const_cast<double*>(Ts), O, ji - 1);
       pf_rows<6>(Pn, JR_FD); pf(Pn, JR_T);
+#ifdef LOIK_PF_EXT
+      const double* Pnd = joint_blk(Td, O, ji - 1);
+      pf_rows<6>(Pnd, JR_F); pf_rows<6>(Pnd, JR_V); pf(Pnd, JR_W); pf_rows<2>(Pnd, JR_JQ);
+      const int kt = c_model.j[i - 1].task;
+      if (kt >= 0) pf_rows<6>(task_blk(Td, O, kt), TR_ATY);
+#endif
     }
     // ---- load phase
     double f[6], F[6], v[6], Fold[6];

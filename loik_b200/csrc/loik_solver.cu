@@ -762,6 +762,16 @@ static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S, int
     h->launches++;
     return;
   }
+#if defined(LOIK_PF_EXT) || defined(LOIK_L1_CARVEOUT)  // (LOIK_PF_EXT: set in loik_device.cuh unless LOIK_PF_BASIC)
+  {  // all of the unified L1/shared array as L1 (k_iterate uses no shared memory)
+    static bool done[64] = {false};
+    if (h->device < 64 && !done[h->device]) {
+      done[h->device] = true;
+      cudaFuncSetAttribute(k_iterate<false, 4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+      cudaFuncSetAttribute(k_iterate<false, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    }
+  }
+#endif
 #define LOIK_LAUNCH(DBG, MB, MD_) k_iterate<DBG, MB, MD_><<<g, kBlock, 0, st>>>(h->mc, S, iters, fixed)
   if (h->debug) { if (md) LOIK_LAUNCH(true, 4, true); else LOIK_LAUNCH(true, 4, false); }
   else if (md) { LOIK_LAUNCH(false, 4, true); }
