@@ -20,7 +20,9 @@
  *     solver objects would hold.  The library keeps its own joint-major SoA copy in HBM.
  *   - Every batched pointer argument may be a HOST pointer or a DEVICE pointer; `loc` says which
  *     (LOIK_HOST / LOIK_DEVICE / LOIK_HOST_PINNED).  Pageable host buffers are staged through the library's
- *     pinned buffers and the call synchronizes; device and page-locked buffers are fully asynchronous.
+ *     pinned buffers and the call synchronizes; device and page-locked buffers are fully asynchronous: the caller
+ *     keeps a LOIK_HOST_PINNED / LOIK_DEVICE buffer alive and unmodified until `stream` has passed the call (inputs),
+ *     and synchronizes `stream` before reading a LOIK_HOST_PINNED output.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work of a call
  *     is enqueued on it; calls that return data to HOST memory synchronize that stream before returning.
  *   - Not thread-safe per handle (same as the reference: one solver+data pair per thread).
