@@ -165,6 +165,13 @@ typedef enum loik_step_id {
 LOIK_API int loik_create(const loik_model_desc* model, const loik_params* params, int32_t batch, int32_t device,
                          loik_solver** out);
 LOIK_API void loik_destroy(loik_solver* h);
+/* Host-side bookkeeping loik_create derives from the model, without touching CUDA (tests / diagnostics; not a reference
+ * entry point).  Writes to out[0..n): rows per tile record, #pending blocks, #segments, warps per tile of the
+ * segment-parallel kernel, #backward levels, #forward levels, #spans, #multi-DoF joints; then per joint 1..njoints-1
+ * {carry, pending block written (-1: none), #pending blocks read, multi-DoF block (-1: none)}; per segment {lo, hi,
+ * backward warp, backward level, forward warp, forward level}; per span {lo, hi, nv of a multi-DoF joint or 0}.
+ * Returns n, or < 0 (same validation and messages as loik_create; cap too small). */
+LOIK_API int32_t loik_model_layout(const loik_model_desc* model, const loik_params* params, int32_t* out, int32_t cap);
 LOIK_API const char* loik_last_error(void);
 
 /* ---- problem set-up -------------------------------------------------------------------------- */

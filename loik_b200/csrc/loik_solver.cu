@@ -832,7 +832,9 @@ extern "C" {
 int32_t loik_abi_version(void) { return 1; }
 const char* loik_last_error(void) { return g_err.c_str(); }
 
-int loik_create(const loik_model_desc* model, const loik_params* params, int32_t batch, int32_t device, loik_solver** out) {
+// `dry`: stop after the host-side part (validation, tree bookkeeping, tile-record layout) and hand back a handle that
+// owns no CUDA resource -- what loik_model_layout reports, so that this logic is testable on a box without a GPU.
+static int create_impl(const loik_model_desc* model, const loik_params* params, int32_t batch, int32_t device, loik_solver** out, bool dry) {
   if (!model || !params || !out) return fail(LOIK_ERR_INVALID, "loik_create: null argument");
   *out = nullptr;
   const int nj = model->njoints;
@@ -853,9 +855,6 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
     for (int i = 1; i < nj; ++i) nmd += nv_of(i) > 1;
     if (nmd > kMaxMd) return fail(LOIK_ERR_UNSUPPORTED, "loik_create: more multi-DoF joints than kMaxMd");
   }
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LOIK_ERR_CUDA, "loik_create: no CUDA device (libloik_b200 has no CPU fallback)");
-  CK(cudaSetDevice(device));
   loik_solver* h = new loik_solver();
   h->device = device; h->batch = batch; h->ntiles = (batch + 31) / 32;
   h->nj = nj; h->nb = nj - 1; h->nc = params->num_eq_c; h->prm = *params;
@@ -982,6 +981,13 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   O.prv = rows; rows += 6 * nb + h->nv;
   O.drv = rows; rows += 6 * nb + h->nv;
   O.rows = rows;
+  if (dry) { *out = h; return LOIK_OK; }
+  {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { delete h; return fail(LOIK_ERR_CUDA, "loik_create: no CUDA device (libloik_b200 has no CPU fallback)"); }
+    const cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete h; return fail(LOIK_ERR_CUDA, std::string("cudaSetDevice(device): ") + cudaGetErrorString(e)); }
+  }
   const size_t arena_doubles = (size_t)h->ntiles * rows * 32;
   if (cudaMalloc(&h->arena, arena_doubles * sizeof(double)) != cudaSuccess) { delete h; return fail(LOIK_ERR_CUDA, "loik_create: cudaMalloc failed"); }
   cudaMemset(h->arena, 0, arena_doubles * sizeof(double));
@@ -1067,6 +1073,26 @@ int loik_create(const loik_model_desc* model, const loik_params* params, int32_t
   if (cudaGetLastError() != cudaSuccess) { loik_destroy(h); return fail(LOIK_ERR_CUDA, "loik_create: allocation failed"); }
   *out = h;
   return LOIK_OK;
+}
+
+int loik_create(const loik_model_desc* model, const loik_params* params, int32_t batch, int32_t device, loik_solver** out) {
+  return create_impl(model, params, batch, device, out, false);
+}
+
+int32_t loik_model_layout(const loik_model_desc* model, const loik_params* params, int32_t* out, int32_t cap) {
+  if (!out || cap < 0) return fail(LOIK_ERR_INVALID, "loik_model_layout: null argument");
+  loik_solver* h = nullptr;
+  const int rc = create_impl(model, params, 32, 0, &h, true);
+  if (rc) return rc;
+  const ModelC& M = h->mc;
+  std::vector<int32_t> v = {M.off.rows, M.npend, M.nseg, M.nwarp, M.nblevel, M.nflevel, M.nspan, M.nmd};
+  for (int i = 1; i < M.nj; ++i) { v.push_back(M.j[i].carry); v.push_back(M.j[i].pout); v.push_back(M.j[i].npin); v.push_back(M.j[i].mblk); }
+  for (int g = 0; g < M.nseg; ++g) for (short x : {M.seg[g].lo, M.seg[g].hi, M.seg[g].bwarp, M.seg[g].blevel, M.seg[g].fwarp, M.seg[g].flevel}) v.push_back(x);
+  for (int g = 0; g < M.nspan; ++g) for (short x : {M.span[g].lo, M.span[g].hi, M.span[g].md}) v.push_back(x);
+  delete h;  // a dry handle owns no CUDA resource
+  if ((int)v.size() > cap) return fail(LOIK_ERR_INVALID, "loik_model_layout: output buffer too small");
+  std::copy(v.begin(), v.end(), out);
+  return (int32_t)v.size();
 }
 
 void loik_destroy(loik_solver* h) {
