@@ -1,4 +1,5 @@
-"""Design check for the next kernel candidate: one backward joint step -- calc_aba's projection and
+"""Design check of a kernel candidate (DESIGN.md section 9 -- evaluated, not pursued: the two lanes of a pair share one
+instruction stream, so lane-specific work is issued for both and the chain only shrinks to ~0.8x): one backward joint step -- calc_aba's projection and
 the congruence to the parent frame (loik-loid-optimized.hxx:60-75) -- split over TWO lanes per instance.
 
 Lane L owns the columns [A; B^T] of H = [[A, B], [B^T, D]] and the linear halves of the force-like vectors, lane A the
