@@ -26,8 +26,11 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work of a call
  *     is enqueued on it; calls that return data to HOST memory synchronize that stream before returning.
  *   - Not thread-safe per handle (same as the reference: one solver+data pair per thread).
- *   - Joints: 1-DoF revolute / prismatic (aligned or unaligned) anywhere, a free-flyer as the root joint; idx_q / idx_v
- *     are cumulative in joint-id order as in pinocchio (nq = nv = njoints-1 without a free-flyer, +6 / +5 with one).
+ *   - Joints (LOIK_JOINT_*): 1-DoF revolute / prismatic (aligned, unaligned, unbounded), free-flyer, spherical,
+ *     translation and planar joints, each anywhere in the tree; idx_q / idx_v are cumulative in joint-id order as in
+ *     pinocchio.  Joints whose motion subspace depends on q or is stacked (composite, SphericalZYX, universal,
+ *     helical, mimic) are rejected by loik_create with LOIK_ERR_UNSUPPORTED.
+ *   - `verbose` and `logging` (LoikSolverInfo, loik-loid-optimized.hpp:47-127) are accepted and ignored.
  */
 #ifndef LOIK_B200_H_
 #define LOIK_B200_H_
@@ -92,6 +95,33 @@ typedef struct loik_params {
 } loik_params;
 
 typedef struct loik_solver loik_solver;
+
+/* How a batched Solve() is laid out on the GPU (not a reference concept; results do not depend on it beyond the
+ * rounding of mathematically equal expressions).  A solve is a fixed, host-sync-free sequence of launches:
+ *   1. `dense_sweeps` ADMM iterations of every instance in place (one thread per instance, k_iterate);
+ *   2. re-pack rounds of 1,1,2,2,4,4,... iterations (`repack_reps` rounds per size, size growing by `repack_growth`):
+ *      the still-active instances migrate to the dense prefix of a scratch arena, finished ones go home;
+ *      branching trees switch to the segment-parallel kernel (`seg_warps` warps per tile) after `seg_after` sweeps;
+ *      rounds after `hi_priority_after` sweeps run on a high-priority stream (< 0: never);
+ *   3. after `lane_after` sweeps (0: from the start; < 0: never) every instance still active is finished by the
+ *      lane-parallel kernel (8 lanes per instance, state resident in shared memory, device-side work queue).
+ * loik_get_schedule reports the current values; the `lane_*` read-only fields describe the geometry chosen at
+ * creation (lane_available = 0: the model has multi-DoF joints or its record does not fit shared memory). */
+typedef struct loik_schedule {
+  int32_t dense_sweeps;
+  int32_t repack_reps;
+  double repack_growth;
+  int32_t hi_priority_after;
+  int32_t seg_after;
+  int32_t seg_warps;   /* 0 = as many as the tree has parallel chains (at most 4); 1 = one warp per tile only */
+  int32_t lane_after;
+  int32_t use_graph;   /* replay the schedule from a CUDA graph when the stream can be captured */
+  int32_t small_after; /* rounds after this many sweeps are launched with at most `small_grid` CTAs (grid-stride) */
+  int32_t small_grid;
+  int32_t lane_warps_per_cta; /* warps (of 4 instances each) per CTA of the lane-parallel kernel; 0 = chosen from the record size */
+  /* read-only (ignored by loik_set_schedule) */
+  int32_t lane_available, lane_warps_chosen, lane_ctas, lane_smem_bytes;
+} loik_schedule;
 
 /* Per-instance fields readable with loik_get().  Shapes are per instance; the batch dimension leads. */
 typedef enum loik_field {
@@ -252,12 +282,25 @@ LOIK_API int loik_reduce_stats(loik_solver* h, void* stream, void** dev_ptr);
 /* Number of CUDA kernels this handle has launched so far (bench.py's gpu_launches). */
 LOIK_API int64_t loik_launch_count(loik_solver* h);
 
-/* setters of the base class (task-solver-base.hpp:105-141, loik-loid-optimized.hpp:703) */
+/* setters of the base class (task-solver-base.hpp:105-141: set_max_iter, set_tol_abs, set_tol_rel, set_tol_primal_inf,
+ * set_tol_dual_inf, set_rho, set_mu, set_mu_equality_scale_factor) and of the solver (loik-loid-optimized.hpp:703
+ * set_tol_tail_solve); they take effect at the next solve.  loik_get_params = the getters get_max_iter ... get_rho,
+ * get_tol_primal_inf, get_tol_dual_inf (task-solver-base.hpp:87-141) in one call (the per-instance get_mu / get_iter /
+ * residuals / tolerances are loik_get fields). */
 LOIK_API int loik_set_max_iter(loik_solver* h, int32_t max_iter);
 LOIK_API int loik_set_rho(loik_solver* h, double rho);
 LOIK_API int loik_set_mu(loik_solver* h, double mu);
+LOIK_API int loik_set_mu_equality_scale_factor(loik_solver* h, double factor);
+LOIK_API int loik_set_tol_abs(loik_solver* h, double tol);
+LOIK_API int loik_set_tol_rel(loik_solver* h, double tol);
+LOIK_API int loik_set_tol_primal_inf(loik_solver* h, double tol);
+LOIK_API int loik_set_tol_dual_inf(loik_solver* h, double tol);
 LOIK_API int loik_set_tol_tail_solve(loik_solver* h, double tol);
 LOIK_API int loik_set_warm_start(loik_solver* h, int32_t warm_start);
+LOIK_API int loik_get_params(loik_solver* h, loik_params* out);
+/* launch schedule (see loik_schedule) */
+LOIK_API int loik_get_schedule(loik_solver* h, loik_schedule* out);
+LOIK_API int loik_set_schedule(loik_solver* h, const loik_schedule* schedule);
 /* Global stop criterion hook for the batch-sharded multi-GPU mode: number of still-active instances
  * on this rank after the last loik_solve_chunk (device-resident int32, for an NCCL all-reduce). */
 LOIK_API int loik_active_count_device_ptr(loik_solver* h, void** dev_ptr);

@@ -43,7 +43,7 @@ struct JointC {
   int pin[kMaxPin];                 // those blocks (one per tree edge: single writer, no read-modify-write)
   int qkind;                        // how q parametrises the joint: 0 = one scalar, 1 = (cos, sin) (unbounded revolute)
   int nvj, sel0, mblk;              // multi-DoF joints: nv of the joint (3 / 6), the components S selects (4 bits each, dof k in bits 4k..4k+3), index of its md block
-  int pad;
+  int sidx;                         // aligned 1-DoF joints: the component of a [lin; ang] 6-vector S selects (S = e_sidx); -1 otherwise
 };
 
 struct TaskC {
@@ -95,7 +95,7 @@ struct ModelC {
   int nj, nb, nc, npend;
   int max_iter, bounds_per_instance;
   int nseg, nblevel, nflevel, nwarp;
-  int nmd, nv, nq, pad0;           // number of multi-DoF joints; model.nv, model.nq
+  int nmd, nv, nq, href_uniform;   // number of multi-DoF joints; model.nv, model.nq; every joint shares H_ref / v_ref (UpdateReference)
   double mdlb[kMaxMd][6], mdub[kMaxMd][6];  // their bounds when shared by the batch
   SegC seg[kMaxSeg];
   int nspan, pad1;
@@ -1166,40 +1166,40 @@ LOIK_DEV void span_residual(const ModelC& c_model, const double* Ts, double* Td,
 // of Solve() (hpp:377-454) and InfeasibilityTailSolve() (hpp:271-319), per instance.
 // `fixed`: stopping disabled (throughput mode).  Returns the new status; updates mu.
 // ---------------------------------------------------------------------------------------------
-// `writer`: this thread stores the per-instance results (one warp per tile does when several warps share it).
-template <bool DEBUG>
-LOIK_DEV int decide(const ModelC& c_model, double* __restrict__ T, const int status, const int it, const bool fixed, const Carry& cy,
-                    const Resid& rs, double& mu, const bool writer = true) {
-  const ModelC& M = c_model;
-  double* G = glob_blk(T, M.off);
-  const double pres = dmax(cy.pres_task, cy.pres_slack);  // (:498)
-  const double dres = dmax(rs.dres_v, rs.T_inf);          // (:517); dual_residual_vec[6nb:] = Stf_plus_w (:484)
-  if (writer) {
-    st(G, GR_RES + 0, pres);
-    st(G, GR_RES + 1, dres);
-  }
+// decide_core: the decisions alone (no memory access), shared by every iteration kernel; decide<DEBUG>: + the stores
+// into a tile record (`writer`: this thread stores the per-instance results -- one warp per tile does when several
+// warps share it).
+struct Verdict {
+  double pres, dres, tol_p, tol_d;                   // primal / dual residual, their tolerances (tol_*: only if has_tol)
+  double dyqp, ATdy, ubp, lbm, c1, c2, dx;           // CheckFeasibility's scalars (debug rows)
+  bool has_tol;
+};
+LOIK_DEV int decide_core(const ModelC& M, const int status, const int it, const bool fixed, const Carry& cy, const Resid& rs,
+                         const double binf, double& mu, Verdict& V) {
+  V.pres = dmax(cy.pres_task, cy.pres_slack);  // (:498)
+  V.dres = dmax(rs.dres_v, rs.T_inf);          // (:517); dual_residual_vec[6nb:] = Stf_plus_w (:484)
+  const double pres = V.pres, dres = V.dres;
   int ns = status;
-  double dyqp = 0.0, ATdy = 0.0, ubp = 0.0, lbm = 0.0, c1 = 0.0, c2 = 0.0;
-  double dx = dmax(cy.dvis_inf, cy.dnu_inf);
+  V.dyqp = V.ATdy = V.ubp = V.lbm = V.c1 = V.c2 = 0.0;
+  V.tol_p = V.tol_d = 0.0;
+  V.has_tol = status == ST_RUNNING;
+  const double dx = dmax(cy.dvis_inf, cy.dnu_inf);
+  V.dx = dx;
   if (status == ST_RUNNING) {
-    const double binf = ld(G, GR_BINF);
     const double tol_p = M.tol_abs + M.tol_rel * dmax(dmax(cy.Av_inf, cy.nu_inf), dmax(binf, cy.nu_inf));            // (:544-546)
     const double tol_d = M.tol_abs + M.tol_rel * dmax(dmax(rs.Hrefv_inf, dmax(rs.F_inf, rs.T_inf)), M.Hv_inf);      // (:548-552)
-    if (writer) {
-      st(G, GR_RES + 2, tol_p);
-      st(G, GR_RES + 3, tol_d);
-    }
+    V.tol_p = tol_p; V.tol_d = tol_d;
     const bool converged = (pres < tol_p) && (dres < tol_d);                                                        // (:555)
     bool infeasible = false;
     if (it > 1) {                                                                                                   // (hpp:425-427)
-      dyqp = dmax(cy.dfis_inf, dmax(cy.dyis_inf, cy.dw_inf));                                                       // (:576-578)
-      ATdy = dmax(rs.dF_inf, rs.dT_inf);                                                                            // (:580-581)
-      const bool cond1 = ATdy <= M.tol_pinf * dyqp;                                                                 // (:583-584)
-      ubp = cy.bTdy_p + cy.ubdw_p;                                                                                  // (:587-588)
-      lbm = cy.bTdy_m + cy.lbdw_m;                                                                                  // (:589-590)
-      const bool cond2 = (ubp + lbm) <= M.tol_pinf * dyqp;                                                          // (:592-593)
+      V.dyqp = dmax(cy.dfis_inf, dmax(cy.dyis_inf, cy.dw_inf));                                                     // (:576-578)
+      V.ATdy = dmax(rs.dF_inf, rs.dT_inf);                                                                          // (:580-581)
+      const bool cond1 = V.ATdy <= M.tol_pinf * V.dyqp;                                                             // (:583-584)
+      V.ubp = cy.bTdy_p + cy.ubdw_p;                                                                                // (:587-588)
+      V.lbm = cy.bTdy_m + cy.lbdw_m;                                                                                // (:589-590)
+      const bool cond2 = (V.ubp + V.lbm) <= M.tol_pinf * V.dyqp;                                                    // (:592-593)
       infeasible = cond1 && cond2;
-      c1 = cond1; c2 = cond2;
+      V.c1 = cond1; V.c2 = cond2;
     }
     if (fixed) {
       if (pres > 10 * dres) mu *= 10; else if (dres > 10 * pres) mu *= 0.1;
@@ -1217,6 +1217,24 @@ LOIK_DEV int decide(const ModelC& c_model, double* __restrict__ T, const int sta
     if (dx >= M.tol_tail || cy.dz_inf >= M.tol_tail) ns = (it >= M.max_iter) ? ST_INFEASIBLE_DONE : ST_TAIL;
     else ns = ST_INFEASIBLE_DONE;
   }
+  return ns;
+}
+template <bool DEBUG>
+LOIK_DEV int decide(const ModelC& c_model, double* __restrict__ T, const int status, const int it, const bool fixed, const Carry& cy,
+                    const Resid& rs, double& mu, const bool writer = true) {
+  const ModelC& M = c_model;
+  double* G = glob_blk(T, M.off);
+  Verdict V;
+  const double binf = status == ST_RUNNING ? ld(G, GR_BINF) : 0.0;
+  const int ns = decide_core(M, status, it, fixed, cy, rs, binf, mu, V);
+  if (writer) {
+    st(G, GR_RES + 0, V.pres);
+    st(G, GR_RES + 1, V.dres);
+    if (V.has_tol) {
+      st(G, GR_RES + 2, V.tol_p);
+      st(G, GR_RES + 3, V.tol_d);
+    }
+  }
   if (DEBUG && writer) {
     const int N = GR_NORMS;
     st(G, N + 0, cy.bTdy_p); st(G, N + 1, cy.bTdy_m); st(G, N + 2, cy.Av_inf); st(G, N + 3, cy.nu_inf);
@@ -1225,10 +1243,10 @@ LOIK_DEV int decide(const ModelC& c_model, double* __restrict__ T, const int sta
     st(G, N + 12, cy.dfis_inf); st(G, N + 13, cy.dyis_inf); st(G, N + 14, cy.dw_inf);
     st(G, N + 15, cy.pres_task); st(G, N + 16, cy.pres_slack); st(G, N + 17, rs.dres_v); st(G, N + 18, rs.T_inf);
     if (status == ST_RUNNING && it > 1) {
-      st(G, N + 19, dyqp); st(G, N + 20, ATdy); st(G, N + 21, ubp); st(G, N + 22, lbm);
-      st(G, N + 23, c1); st(G, N + 24, c2);
+      st(G, N + 19, V.dyqp); st(G, N + 20, V.ATdy); st(G, N + 21, V.ubp); st(G, N + 22, V.lbm);
+      st(G, N + 23, V.c1); st(G, N + 24, V.c2);
     }
-    if (status == ST_TAIL || it > 1) st(G, N + 25, dx);
+    if (status == ST_TAIL || it > 1) st(G, N + 25, V.dx);
   }
   return ns;
 }

@@ -1,0 +1,568 @@
+// loik_lane.cuh -- the lane-parallel, shared-memory-resident iteration kernel (k_iterate_lane).
+//
+// Mapping: ONE GROUP OF 8 LANES = ONE PROBLEM INSTANCE (4 instances per warp), the whole per-instance state of the
+// ADMM loop resident in SHARED MEMORY for as many iterations as the instance needs, persistent CTAs pulling instances
+// from a device-side work queue.  Where k_iterate (loik_device.cuh) gives one thread a whole instance and streams
+// its state through HBM once per iteration, this kernel
+//   * cuts the dependent chain of a joint step ~4x: lanes 0..5 own the columns of the 6x6 H (its rows, H being
+//     symmetric), lane 6 owns p as a seventh column, so the congruence X* H X*^T (pinocchio SE3actOn, call site
+//     hxx:66) is two column transforms (2 x 24 FMA per lane, the same act_force() the force vectors use) around a
+//     6x6 transpose through shared memory instead of ~270 FMA in one thread; the 6x6 mat-vecs H v, Href v, A v, A^T y
+//     are one dot product per lane;
+//   * touches HBM twice per SOLVE (state in, results out) instead of ~8 KB per instance and iteration: the
+//     backward->forward workspace (His, pis, UDinv, Dinv, r) never leaves the SM;
+//   * has no lock-step with 31 unrelated instances: a group that finishes pulls the next instance from the queue, so
+//     a launch needs no re-pack rounds and the stragglers of a batch (0.06 % of the Panda instances run all 199
+//     iterations) cost ~5 us per iteration instead of ~22 us.
+// The maths restates loik-loid-optimized.hxx exactly as loik_device.cuh does (same per-element expressions wherever
+// an element is produced by one lane; reference file:line cited there); running inf-norms are kept as per-lane
+// partial maxima (max is exactly associative) and combined once per iteration.
+//
+// Scope: trees of 1-DoF joints (every BASELINE robot); models with multi-DoF joints keep the k_iterate path.
+#pragma once
+#include "loik_device.cuh"
+
+namespace loik {
+
+constexpr int kLaneI = 4;  // instances per warp (8 lanes each)
+
+// ---- instance record in shared memory (doubles) ------------------------------------------------------------------
+enum : int { LS_MU = 0, LS_BINF = 1, LS_CTL = 2, LS_RES = 3, LS_ROWS = 8 };
+// per joint: the first 26 entries mirror rows JR_V .. JR_UB of the tile record (loik_device.cuh), then the workspace of
+// the backward sweep: Dinv, r, UDinv (8), and [H | p] as 6 rows of 8 (column c < 6: H(:, c), column 6: p); last liMi =
+// jointPlacements[i] * M_i(q) (FwdPassInit, hxx:263-264), built once when the instance is loaded (q does not change
+// during a solve) instead of three times per joint and iteration.
+enum : int { LJ_V = 0, LJ_F = 6, LJ_FD = 12, LJ_NU = 18, LJ_Z = 19, LJ_W = 20, LJ_T = 21, LJ_SQ = 22, LJ_CQ = 23, LJ_LB = 24,
+             LJ_UB = 25, LJ_COPY = 26, LJ_DINV = 26, LJ_R = 27, LJ_UD = 28, LJ_HP = 36, LJ_XF = 84, LJ_ROWS = 96 };  // XF: liMi = (R 9, t 3)
+static_assert((int)LJ_V == (int)JR_V && (int)LJ_F == (int)JR_F && (int)LJ_FD == (int)JR_FD && (int)LJ_NU == (int)JR_NU && (int)LJ_Z == (int)JR_Z && (int)LJ_W == (int)JR_W && (int)LJ_T == (int)JR_T &&
+              (int)LJ_SQ == (int)JR_JQ && (int)LJ_LB == (int)JR_LB && (int)LJ_UB == (int)JR_UB, "the copied part of a joint record mirrors the tile rows");
+enum : int { LT_Y = TR_Y, LT_ATY = TR_ATY, LT_B = TR_B, LT_ATB = TR_ATB, LT_ROWS = TR_ROWS };
+enum : int { LP_HP = 0, LP_F = 48, LP_ROWS = 56 };       // pending block of a tree edge: [H | p] contribution, F contribution
+enum : int { LX_V = 0, LX_T = 16, LX_ROWS = 96 };        // exchange scratch: 16 scalars, 8 rows of 10 (transposes)
+// ---- per-CTA constants in shared memory ---------------------------------------------------------------------------
+enum : int { CJ_HREF = 0, CJ_HV = 48, CJ_ROWS = 56 };    // per joint: [Href | -Hv] as 6 rows of 8, Hv (8)
+enum : int { CT_AR = 0, CT_ATR = 48, CT_ATA = 96, CT_ROWS = 144 };  // per task: A, A^T, A^T A as 6 rows of 8
+
+struct LaneDims {
+  int joint0, task0, pend0, xch, stride;  // offsets inside an instance record, record stride
+  int ctask0, csize, cpad;                // constants: first task block, size, size padded to 128 B
+};
+__host__ __device__ inline LaneDims lane_dims(const int nb, const int nc, const int npend, const int href_uniform) {
+  LaneDims D;
+  D.joint0 = LS_ROWS;
+  D.task0 = D.joint0 + LJ_ROWS * nb;
+  D.pend0 = D.task0 + LT_ROWS * nc;
+  D.xch = D.pend0 + LP_ROWS * npend;
+  int sz = (D.xch + LX_ROWS + 7) & ~7;
+  if ((sz & 15) == 0) sz += 8;  // stride = 8 (mod 16) doubles: the records of two neighbouring groups cover different banks
+  D.stride = sz;
+  D.ctask0 = CJ_ROWS * (href_uniform ? 1 : nb);  // one [Href | -Hv] block when every joint shares the reference (UpdateReference)
+  D.csize = D.ctask0 + CT_ROWS * nc;
+  D.cpad = (D.csize + 15) & ~15;
+  return D;
+}
+inline size_t lane_smem_bytes(const LaneDims& D, const int warps) { return ((size_t)D.cpad + (size_t)warps * kLaneI * D.stride) * sizeof(double); }
+
+struct LaneP {
+  const double* src;   // arena the instances live in when the kernel starts
+  const int* list;     // optional: queue entry k is slot list[k] of `src` (the survivors of the previous launch)
+  const int* n_list;   // device-resident queue length (with `list`), else `n`
+  int n;
+  const int* origin;   // optional: home slot of slot s of `src` (a packed arena); else the home slot is s
+  double* home;        // arena the results go to
+  int* queue;          // work-queue head (zeroed before the launch)
+  int iters;           // fixed mode: iterations per instance
+  int fixed;           // stopping disabled (throughput mode)
+  int keep_ws;         // the workspace of the last backward pass goes home too (loik_set_keep_workspace)
+};
+
+LOIK_DEV void lds6(const double* p, double (&v)[6]) {
+  const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2),
+                c = *reinterpret_cast<const double2*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+}
+LOIK_DEV void sts6(double* p, const double (&v)[6]) {
+  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+  *reinterpret_cast<double2*>(p + 4) = make_double2(v[4], v[5]);
+}
+LOIK_DEV double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// per-lane partial maxima of the norms whose terms are produced one component per lane
+struct LanePart { double dfis, dyis, Av, ptask, dF, Finf, Hrefv, dresv; };
+
+// ---------------------------------------------------------------------------------------------
+// state in / results out (8 lanes of one group, uncoalesced 8 B accesses: once per solve and instance)
+// ---------------------------------------------------------------------------------------------
+template <int PER, typename F>
+LOIK_DEV void lane_copy_rows(const int total, const int l, F&& body) {  // body(e, phase, slot): phase 0 = load, 1 = store
+  for (int e0 = 0; e0 < total; e0 += 8 * PER) {
+#pragma unroll
+    for (int u = 0; u < PER; ++u) { const int e = e0 + 8 * u + l; if (e < total) body(e, 0, u); }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) { const int e = e0 + 8 * u + l; if (e < total) body(e, 1, u); }
+  }
+}
+LOIK_DEV void lane_load(const ModelC& M, const LaneDims& D, const double* T, double* I, const int l) {
+  const Offs& O = M.off;
+  double buf[8];
+  lane_copy_rows<8>(LJ_COPY * M.nb, l, [&](const int e, const int phase, const int u) {
+    const int j = e / LJ_COPY, r = e - LJ_COPY * j;
+    if (phase == 0) buf[u] = __ldcs(T + (size_t)(O.joint0 + JR_ROWS * j + r) * 32);
+    else I[D.joint0 + LJ_ROWS * j + r] = buf[u];
+  });
+  lane_copy_rows<8>(LT_ROWS * M.nc, l, [&](const int e, const int phase, const int u) {
+    if (phase == 0) buf[u] = __ldcs(T + (size_t)(O.task0 + e) * 32);
+    else I[D.task0 + e] = buf[u];
+  });
+  if (l < 7) {
+    const int row = l == 0 ? GR_MU : (l == 1 ? GR_BINF : (l == 2 ? GR_CTL : GR_RES + (l - 3)));
+    const int dst = l == 0 ? LS_MU : (l == 1 ? LS_BINF : (l == 2 ? LS_CTL : LS_RES + (l - 3)));
+    I[dst] = T[(size_t)(O.glob + row) * 32];
+  }
+}
+// what retire_rows (loik_solver.cu) sends home: v, f, F, nu, z, w, T | y, Aty | mu, control, residuals
+LOIK_DEV void lane_retire(const ModelC& M, const LaneDims& D, const double* I, double* Th, const int l) {
+  const Offs& O = M.off;
+  for (int e = l; e < JR_JQ * M.nb; e += 8) {
+    const int j = e / JR_JQ, r = e - JR_JQ * j;
+    Th[(size_t)(O.joint0 + JR_ROWS * j + r) * 32] = I[D.joint0 + LJ_ROWS * j + r];
+  }
+  for (int e = l; e < TR_B * M.nc; e += 8) {
+    const int k = e / TR_B, r = e - TR_B * k;
+    Th[(size_t)(O.task0 + TR_ROWS * k + r) * 32] = I[D.task0 + LT_ROWS * k + r];
+  }
+  if (l < 6) {
+    const int row = l == 0 ? GR_MU : (l == 1 ? GR_CTL : GR_RES + (l - 2));
+    const int src = l == 0 ? LS_MU : (l == 1 ? LS_CTL : LS_RES + (l - 2));
+    Th[(size_t)(O.glob + row) * 32] = I[src];
+  }
+}
+// opt-in: His (21 packed scalars), pis, UDinv, Dinv, r of the last backward pass
+LOIK_DEV_CALL void lane_retire_workspace(const ModelC& M, const LaneDims& D, const double* I, double* Th, const int l) {
+  const Offs& O = M.off;
+  for (int j = l; j < M.nb; j += 8) {
+    const double* Pj = I + D.joint0 + LJ_ROWS * j;
+    double* Pd = Th + (size_t)(O.joint0 + JR_ROWS * j) * 32;
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        if (a <= b) { st(Pd, JR_H + si(a, b), Pj[LJ_HP + 8 * a + b]); st(Pd, JR_H + 15 + si(a, b), Pj[LJ_HP + 8 * (3 + a) + 3 + b]); }
+        st(Pd, JR_H + 6 + 3 * a + b, Pj[LJ_HP + 8 * a + 3 + b]);
+      }
+    for (int c = 0; c < 6; ++c) { st(Pd, JR_P + c, Pj[LJ_HP + 8 * c + 6]); st(Pd, JR_UD + c, Pj[LJ_UD + c]); }
+    st(Pd, JR_DINV, Pj[LJ_DINV]);
+    st(Pd, JR_R, Pj[LJ_R]);
+  }
+}
+
+LOIK_DEV void lds_xf(const double* p, double (&R)[9], double (&t)[3]) {  // liMi of a joint from its record
+  const double2 a = lds2(p), b = lds2(p + 2), c = lds2(p + 4), d = lds2(p + 6), e = lds2(p + 8), f = lds2(p + 10);
+  R[0] = a.x; R[1] = a.y; R[2] = b.x; R[3] = b.y; R[4] = c.x; R[5] = c.y; R[6] = d.x; R[7] = d.y; R[8] = e.x;
+  t[0] = e.y; t[1] = f.x; t[2] = f.y;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward sweep: FwdPass1 (hxx:290-338) + BwdPassOptimizedVisitor (hxx:345-354, algo :31-81); cf. sweep_backward.
+// Lane c < 6 holds column c of H, lanes 6 and 7 (a duplicate) hold p.
+// ---------------------------------------------------------------------------------------------
+LOIK_DEV void lane_backward(const ModelC& M, const LaneDims& D, const double* CB, double* I, const int l, const double mu,
+                            const double mu_eq, const double (&rhod)[6]) {
+  const double rho = M.rho;
+  const int lc = l < 6 ? l : 6;
+  const bool isp = l >= 6;
+  const double facv = isp ? -rho : 0.0;
+  double* X = I + D.xch;
+  double* XT = X + LX_T;
+  const double* XTrow = XT + 10 * lc;  // row of the transposed exchange this lane reads back (row 6: p itself)
+  double cc[6];  // contribution carried from child i+1: this lane's column of X* H X*^T, resp. X* p
+  bool have_carry = false;
+  double* Pj = I + D.joint0 + LJ_ROWS * M.nb;
+  const int cstep = M.href_uniform ? 0 : CJ_ROWS;
+  const double* Cj = CB + cstep * M.nb + lc;
+  for (int i = M.nb; i >= 1; --i) {
+    const JointC& J = M.j[i];
+    Pj -= LJ_ROWS;
+    Cj -= cstep;
+    __syncwarp();
+    double vold[6], col[6];
+    lds6(Pj + LJ_V, vold);
+    const double w_i = Pj[LJ_W], z_i = Pj[LJ_Z];
+    // FwdPass1: H_i = rho I + Href_i (:304-306); p_i = -rho v_prev_i - Hv_i (:310-313)
+#pragma unroll
+    for (int r = 0; r < 6; ++r) col[r] = fma(facv, vold[r], Cj[CJ_HREF + 8 * r]) + rhod[r];
+    if (J.task >= 0) {  // H_c += mu_eq AtA; p_c += Aty - mu_eq Atb (:327-330)
+      const double* Ck = CB + D.ctask0 + CT_ROWS * J.task;
+      const double* Pk = I + D.task0 + LT_ROWS * J.task;
+      double aty[6], atb[6];
+      lds6(Pk + LT_ATY, aty);
+      lds6(Pk + LT_ATB, atb);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        const double hcol = fma(mu_eq, Ck[CT_ATA + 8 * r + lc], col[r]);
+        const double pcol = col[r] + (aty[r] - mu_eq * atb[r]);
+        col[r] = isp ? pcol : hcol;
+      }
+    }
+    // children's contributions: His[parent] += SE3actOn(...), pis[parent] += liMi.act(...) (:66,:74)
+    for (int n = 0; n < J.npin; ++n) {
+      const double* Pp = I + D.pend0 + LP_ROWS * J.pin[n];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) col[r] += Pp[LP_HP + 8 * r + lc];
+    }
+    if (have_carry) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) col[r] += cc[r];
+    }
+    // hand H_i, p_i (un-projected) to the forward sweep
+#pragma unroll
+    for (int r = 0; r < 6; ++r) Pj[LJ_HP + 8 * r + l] = col[r];
+    // calc_aba (:60-63): U = H S, Dinv = 1 / (S^T U + R_i) with armature R_i = mu_ineq (:294-295), UDinv = U Dinv;
+    // r_i = w_i - mu_ineq z_i (:296) + S^T p_i (:70)
+    double U[6], d, Stp, StU;
+    const int k = J.sidx;
+    if (k >= 0) {
+      // aligned joint, S = e_k: U = H(:, k) = row k of the symmetric H, and S^T p = p_k sits next to it in the stored
+      // [H | p] block; this lane's own U_c (lane 6: p_k) is entry lc of the same row
+      __syncwarp();
+      const double* row = Pj + LJ_HP + 8 * k;
+      lds6(row, U);
+      Stp = row[6];
+      d = row[l];
+      StU = row[k];
+    } else {
+      // unaligned joint: U_c = S^T H(:, c) (H symmetric), one dot product per lane; lane 6 gets S^T p
+      d = St_dot(J, col);
+      __syncwarp();
+      X[LX_V + l] = d;
+      __syncwarp();
+      lds6(X + LX_V, U);
+      Stp = X[LX_V + 6];
+      StU = St_dot(J, U);
+    }
+    const double Dinv = 1.0 / (StU + mu);
+    const double ri = (w_i - mu * z_i) + Stp;
+    double UD[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) UD[c] = U[c] * Dinv;
+    Pj[LJ_UD + l] = d * Dinv;
+    Pj[LJ_DINV] = Dinv;
+    Pj[LJ_R] = ri;
+    have_carry = false;
+    if (J.parent > 0) {
+      // projection: H -= UDinv U^T (calc_aba update_I, :63), p -= UDinv r_i (:71-73)
+      const double m = isp ? ri : d;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) col[r] -= UD[r] * m;
+      double R[9], t[3], y[6], row[6];
+      lds_xf(Pj + LJ_XF, R, t);
+      act_force(R, t, col, y);  // Y = X* H, column by column
+#pragma unroll
+      for (int r = 0; r < 6; ++r) XT[10 * r + l] = y[r];
+      if (isp) sts6(XT + 60, col);  // (the p lanes: their single transform is the second one)
+      __syncwarp();
+      lds6(XTrow, row);
+      act_force(R, t, row, cc);  // row c of Y X*^T = X* (row c of Y): column c of X* H X*^T (SE3actOn, :66); lane 6: liMi.act(p) (:74)
+      if (J.carry) {
+        have_carry = true;
+      } else {
+        double* Pp = I + D.pend0 + LP_ROWS * J.pout;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) Pp[LP_HP + 8 * r + l] = cc[r];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward sweep: FwdPass2OptimizedVisitor (hxx:361-377) + BoxProj (:384-397) + DualUpdate (:404-461) +
+// ComputePrimalResiduals (:494-503); cf. sweep_forward.  The 6-vectors are computed by every lane (they are the
+// chain), f = H v + p / A v / A^T y one component per lane.
+// ---------------------------------------------------------------------------------------------
+LOIK_DEV void lane_forward(const ModelC& M, const LaneDims& D, const double* CB, double* I, const int l, const double mu,
+                           const double mu_eq, Carry& cy, LanePart& pt) {
+  const double inv_mu = 1.0 / mu;
+  const int lc = l < 6 ? l : 5;  // lanes 6, 7 duplicate lane 5
+  double* X = I + D.xch;
+  double v[6] = {0, 0, 0, 0, 0, 0};  // v of joint i-1 on entry of step i
+  double* Pj = I + D.joint0 - LJ_ROWS;
+  for (int i = 1; i <= M.nb; ++i) {
+    const JointC& J = M.j[i];
+    Pj += LJ_ROWS;
+    __syncwarp();
+    double UD[6], vold[6], R[9], t[3];
+    const double2 dr = lds2(Pj + LJ_DINV);  // (Dinv, r)
+    const double2 nz = lds2(Pj + LJ_NU);    // (nu, z) of the previous iterate
+    const double w_old = Pj[LJ_W];
+    double lb = J.lb, ub = J.ub;
+    if (M.bounds_per_instance) { const double2 b2 = lds2(Pj + LJ_LB); lb = b2.x; ub = b2.y; }
+    lds6(Pj + LJ_UD, UD);
+    lds6(Pj + LJ_V, vold);
+    lds_xf(Pj + LJ_XF, R, t);
+    if (J.parent != i - 1) {  // not the joint just swept: the universe (v = 0) or a joint swept earlier (its new v)
+      if (J.parent == 0) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) v[c] = 0.0;
+      } else {
+        lds6(I + D.joint0 + LJ_ROWS * (J.parent - 1) + LJ_V, v);
+      }
+    }
+    // f_i = H_i v_i + p_i needs row lc of H (= column lc), p_lc, and the old f_lc
+    double hc[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) hc[c] = Pj[LJ_HP + 8 * c + lc];
+    const double p_l = Pj[LJ_HP + 8 * lc + 6];
+    const double fold_l = Pj[LJ_F + lc];
+    {
+      double vp[6];
+      actinv_motion(R, t, v, vp);  // vi_parent (:125)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) v[c] = vp[c];
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc += UD[c] * v[c];
+    const double nu = -acc - dr.x * dr.y;  // nu_i = -UDinv^T vp - Dinv r_i (:127)
+    cy.nu_inf = amax(cy.nu_inf, nu);       // (:129-131)
+    S_axpy(J, nu, v);                      // v_i = vp + S nu_i (:133-134)
+    {
+      double dv[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) dv[c] = v[c] - vold[c];
+      cy.dvis_inf = amax6(cy.dvis_inf, dv);  // (:156-158)
+    }
+    cy.dnu_inf = amax(cy.dnu_inf, nu - nz.x);  // (:375)
+    const double z = dmin(ub, dmax(lb, nu + inv_mu * w_old));  // BoxProj (:388)
+    cy.dz_inf = amax(cy.dz_inf, z - nz.y);
+    const double rp = nu - z;
+    cy.pres_slack = amax(cy.pres_slack, rp);
+    const double dw = mu * rp;  // (:454-458)
+    cy.dw_inf = amax(cy.dw_inf, dw);
+    cy.ubdw_p += ub * dmax(dw, 0.0);  // CheckFeasibility's dot products (:588,590)
+    cy.lbdw_m += lb * dmin(dw, 0.0);
+    const double f_l = hc[0] * v[0] + hc[1] * v[1] + hc[2] * v[2] + hc[3] * v[3] + hc[4] * v[4] + hc[5] * v[5] + p_l;  // (:139-140)
+    pt.dfis = amax(pt.dfis, f_l - fold_l);  // (:137-146)
+    __syncwarp();  // every lane has read this joint's previous iterate
+    if (l == 0) sts6(Pj + LJ_V, v);
+    Pj[LJ_F + lc] = f_l;
+    *reinterpret_cast<double2*>(Pj + LJ_NU) = make_double2(nu, z);
+    Pj[LJ_W] = w_old + dw;
+    if (J.task >= 0) {  // DualUpdate for the task on this joint (:410-451)
+      const double* Ck = CB + D.ctask0 + CT_ROWS * J.task;
+      double* Pk = I + D.task0 + LT_ROWS * J.task;
+      const double Av = Ck[CT_ATR + lc] * v[0] + Ck[CT_ATR + 8 + lc] * v[1] + Ck[CT_ATR + 16 + lc] * v[2] + Ck[CT_ATR + 24 + lc] * v[3] +
+                        Ck[CT_ATR + 32 + lc] * v[4] + Ck[CT_ATR + 40 + lc] * v[5];
+      const double e = Av - Pk[LT_B + lc];  // Av_minus_b (:416)
+      const double dy = mu_eq * e;          // delta_yis (:419)
+      const double y_l = Pk[LT_Y + lc] + dy;
+      pt.dyis = amax(pt.dyis, dy);
+      pt.Av = amax(pt.Av, Av);
+      pt.ptask = amax(pt.ptask, e);
+      X[LX_V + l] = dy;
+      X[LX_V + 8 + l] = y_l;
+      __syncwarp();
+      double dys[6], ys[6], bk[6];
+      lds6(X + LX_V, dys);
+      lds6(X + LX_V + 8, ys);
+      lds6(Pk + LT_B, bk);
+      double plus = 0.0, minus = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        plus += bk[a] * dmax(dys[a], 0.0);
+        minus += bk[a] * dmin(dys[a], 0.0);
+      }
+      cy.bTdy_p += plus;
+      cy.bTdy_m += minus;
+      // Aty = A^T y (:425)
+      const double aty = Ck[CT_AR + lc] * ys[0] + Ck[CT_AR + 8 + lc] * ys[1] + Ck[CT_AR + 16 + lc] * ys[2] + Ck[CT_AR + 24 + lc] * ys[3] +
+                         Ck[CT_AR + 32 + lc] * ys[4] + Ck[CT_AR + 40 + lc] * ys[5];
+      Pk[LT_Y + lc] = y_l;
+      Pk[LT_ATY + lc] = aty;
+    }
+  }
+}
+
+// select x[l] for a lane-dependent l in 0..5 (two levels of selects)
+LOIK_DEV double pick6(const double (&x)[6], const int l) {
+  const bool odd = l & 1;
+  const double a = odd ? x[1] : x[0], b = odd ? x[3] : x[2], c = odd ? x[5] : x[4];
+  return l < 2 ? a : (l < 4 ? b : c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Residual sweep: BwdPass2OptimizedVisitor (hxx:468-487, algo :185-241) + ComputeDualResiduals (:510-522); cf.
+// sweep_residual.  F = fis_diff_plus_Aty one component per lane, liMi.act(f_i) by every lane.
+// ---------------------------------------------------------------------------------------------
+LOIK_DEV void lane_residual(const ModelC& M, const LaneDims& D, const double* CB, double* I, const int l, Resid& rs, LanePart& pt) {
+  const int lc = l < 6 ? l : 5;
+  double cF = 0.0;
+  bool have_carry = false;
+  double* Pj = I + D.joint0 + LJ_ROWS * M.nb;
+  const int cstep = M.href_uniform ? 0 : CJ_ROWS;
+  const double* Cj = CB + cstep * M.nb + lc;
+  for (int i = M.nb; i >= 1; --i) {
+    const JointC& J = M.j[i];
+    Pj -= LJ_ROWS;
+    Cj -= cstep;
+    __syncwarp();
+    double f[6], v[6];
+    lds6(Pj + LJ_F, f);
+    lds6(Pj + LJ_V, v);
+    const double2 wt = lds2(Pj + LJ_W);  // (w_i new, T old)
+    const double f_l = Pj[LJ_F + lc], Fold = Pj[LJ_FD + lc], Hv_l = Cj[CJ_HV];
+    double hr[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) hr[c] = Cj[CJ_HREF + 8 * c];
+    const int k = J.sidx;
+    const double Stf = k >= 0 ? Pj[LJ_F + k] : St_dot(J, f);  // S^T f_i
+    double F = 0.0;  // (:370)
+    if (J.task >= 0) F = I[D.task0 + LT_ROWS * J.task + LT_ATY + lc];  // (:438-439)
+    for (int n = 0; n < J.npin; ++n) F += I[D.pend0 + LP_ROWS * J.pin[n] + LP_F + lc];
+    if (have_carry) F += cF;
+    F += -f_l;  // (:210)
+    // Href_v (fwd pass 2, :149-153), recomputed from v_i
+    const double Hrv = hr[0] * v[0] + hr[1] * v[1] + hr[2] * v[2] + hr[3] * v[3] + hr[4] * v[4] + hr[5] * v[5];
+    const double rd = Hrv - Hv_l + F;       // (:228)
+    pt.dF = amax(pt.dF, F - Fold);          // (:215-220)
+    pt.Finf = amax(pt.Finf, F);             // (:223-225)
+    pt.Hrefv = amax(pt.Hrefv, Hrv);
+    pt.dresv = amax(pt.dresv, rd);
+    const double Tn = Stf + wt.x;           // Stf_plus_w (:231-236) and its delta (:471,:482-483)
+    rs.T_inf = amax(rs.T_inf, Tn);
+    rs.dT_inf = amax(rs.dT_inf, Tn - wt.y);
+    __syncwarp();
+    Pj[LJ_FD + lc] = F;
+    Pj[LJ_T] = Tn;
+    have_carry = false;
+    if (J.parent > 0) {  // fis_diff_plus_Aty[parent] += liMi.act(f_i) (:212)
+      double R[9], t[3], c6[6];
+      lds_xf(Pj + LJ_XF, R, t);
+      act_force(R, t, f, c6);
+      cF = pick6(c6, lc);
+      if (J.carry) have_carry = true;
+      else I[D.pend0 + LP_ROWS * J.pout + LP_F + lc] = cF;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The kernel.  blockDim = 32 W; dynamic shared memory = constants + 4 W instance records (lane_smem_bytes).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ ModelC c_model, const LaneP P) {
+  extern __shared__ __align__(16) double lsm[];
+  const ModelC& M = c_model;
+  const LaneDims D = lane_dims(M.nb, M.nc, M.npend, M.href_uniform);
+  double* CB = lsm;
+  for (int e = threadIdx.x; e < D.csize; e += blockDim.x) {
+    double x = 0.0;
+    if (e < D.ctask0) {
+      const int j = e / CJ_ROWS, o = e - CJ_ROWS * j;
+      const JointC& J = M.j[j + 1];
+      if (o < 48) {
+        const int r = o >> 3, c = o & 7;
+        if (c < 6) x = Hel(J.HrA, J.HrB, J.HrD, r, c);
+        else if (c == 6) x = -J.Hv[r];
+      } else if (o - 48 < 6) {
+        x = J.Hv[o - 48];
+      }
+    } else {
+      const int k = (e - D.ctask0) / CT_ROWS, o = (e - D.ctask0) - CT_ROWS * k;
+      const TaskC& K = M.t[k];
+      const int blk = o / 48, r = (o - 48 * blk) >> 3, c = o & 7;
+      if (c < 6) x = blk == 0 ? K.A[6 * r + c] : (blk == 1 ? K.A[6 * c + r] : Hel(K.AtA_A, K.AtA_B, K.AtA_D, r, c));
+    }
+    CB[e] = x;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, l = lane & 7, g = lane >> 3, w = threadIdx.x >> 5;
+  double* I = lsm + D.cpad + (size_t)(w * kLaneI + g) * D.stride;
+  double* X = I + D.xch;
+  const unsigned gmask = 0xffu << (8 * g);
+  const int limit = P.list ? *P.n_list : P.n;
+  double rhod[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) rhod[r] = (r == l) ? M.rho : 0.0;
+  int home_slot = -1;  // >= 0: this group holds an instance
+  int status = ST_CONVERGED, it = 0, left = 0;
+  double mu = 1.0;
+  bool exhausted = false;
+  for (;;) {
+    if (home_slot < 0 && !exhausted) {  // pull the next instance from the queue
+      __syncwarp(gmask);  // the record is free: every lane of the group is done with the previous instance
+      int k = 0;
+      if (l == 0) k = atomicAdd(P.queue, 1);
+      k = __shfl_sync(gmask, k, 8 * g);
+      if (k < limit) {
+        const int s = P.list ? P.list[k] : k;
+        const double* T = P.src + ((size_t)(s >> 5) * M.off.rows) * 32 + (s & 31);
+        lane_load(M, D, T, I, l);
+        __syncwarp(gmask);
+        for (int j = l; j < M.nb; j += 8) {  // liMi of every joint (FwdPassInit, hxx:263-264), once per instance
+          double* Pj = I + D.joint0 + LJ_ROWS * j;
+          double R[9], t[3];
+          make_xf(M.j[j + 1], Pj[LJ_SQ], Pj[LJ_CQ], R, t);
+#pragma unroll
+          for (int c = 0; c < 9; ++c) Pj[LJ_XF + c] = R[c];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) Pj[LJ_XF + 9 + c] = t[c];
+        }
+        __syncwarp(gmask);
+        const int2 ctl = *reinterpret_cast<const int2*>(I + LS_CTL);
+        status = ctl.x; it = ctl.y;
+        mu = I[LS_MU];
+        left = P.iters;
+        if (status < ST_CONVERGED) home_slot = P.origin ? P.origin[s] : s;
+      } else {
+        exhausted = true;
+      }
+    }
+    __syncwarp();
+    const bool act = home_slot >= 0;
+    if (!__any_sync(0xffffffffu, act)) break;
+    // ---- one ADMM iteration of the (up to) four instances of this warp
+    const double mu_eq = M.mu_scale * mu;
+    Carry cy;
+    Resid rs;
+    LanePart pt = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    zero(cy);
+    zero(rs);
+    lane_backward(M, D, CB, I, l, mu, mu_eq, rhod);
+    lane_forward(M, D, CB, I, l, mu, mu_eq, cy, pt);
+    lane_residual(M, D, CB, I, l, rs, pt);
+    {  // combine the per-lane partial maxima: rows = lanes, then one column per lane
+      double* XT = X + LX_T;
+      __syncwarp();
+      double* row = XT + 10 * l;
+      *reinterpret_cast<double2*>(row) = make_double2(pt.dfis, pt.dyis);
+      *reinterpret_cast<double2*>(row + 2) = make_double2(pt.Av, pt.ptask);
+      *reinterpret_cast<double2*>(row + 4) = make_double2(pt.dF, pt.Finf);
+      *reinterpret_cast<double2*>(row + 6) = make_double2(pt.Hrefv, pt.dresv);
+      __syncwarp();
+      const double a0 = XT[l], a1 = XT[10 + l], a2 = XT[20 + l], a3 = XT[30 + l], a4 = XT[40 + l], a5 = XT[50 + l];
+      X[LX_V + 8 + l] = dmax(dmax(dmax(a0, a1), dmax(a2, a3)), dmax(a4, a5));
+      __syncwarp();
+      const double2 t0 = lds2(X + LX_V + 8), t1 = lds2(X + LX_V + 10), t2 = lds2(X + LX_V + 12), t3 = lds2(X + LX_V + 14);
+      cy.dfis_inf = t0.x; cy.dyis_inf = t0.y; cy.Av_inf = t1.x; cy.pres_task = t1.y;
+      rs.dF_inf = t2.x; rs.F_inf = t2.y; rs.Hrefv_inf = t3.x; rs.dres_v = t3.y;
+    }
+    if (act) {
+      ++it;
+      Verdict V;
+      status = decide_core(M, status, it, P.fixed != 0, cy, rs, I[LS_BINF], mu, V);
+      I[LS_RES + 0] = V.pres;
+      I[LS_RES + 1] = V.dres;
+      if (V.has_tol) { I[LS_RES + 2] = V.tol_p; I[LS_RES + 3] = V.tol_d; }
+      const bool done = status >= ST_CONVERGED || (P.fixed && --left <= 0);
+      if (done) {  // results go home; the group is free for the next instance
+        *reinterpret_cast<int2*>(I + LS_CTL) = make_int2(status, it);
+        I[LS_MU] = mu;
+        __syncwarp(gmask);
+        double* Th = P.home + ((size_t)(home_slot >> 5) * M.off.rows) * 32 + (home_slot & 31);
+        lane_retire(M, D, I, Th, l);
+        if (P.keep_ws) lane_retire_workspace(M, D, I, Th, l);
+        home_slot = -1;
+      }
+    }
+  }
+}
+
+}  // namespace loik

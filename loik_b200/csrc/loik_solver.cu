@@ -14,6 +14,7 @@
 
 #include "../../include/loik_b200.h"
 #include "loik_device.cuh"
+#include "loik_lane.cuh"
 
 namespace loik {
 
@@ -714,24 +715,32 @@ struct loik_solver {
   void* d_stage = nullptr; size_t d_stage_bytes = 0;
   int64_t launches = 0;
   int64_t sweeps = 0;
-  int dense_sweeps = 4;  // sweeps on the home arena before the first re-pack (env LOIK_DENSE)
-  int sched_reps = 2;      // re-pack rounds per chunk size (env LOIK_REPS)
-  double sched_growth = 2.0;  // chunk growth factor (env LOIK_GROWTH)
+  int dense_sweeps = 4;  // sweeps on the home arena before the first re-pack
+  int sched_reps = 2;      // re-pack rounds per chunk size
+  double sched_growth = 2.0;  // chunk growth factor
   int last_list = -1;  // index of the list holding the most recent compaction, -1 = none
   // CUDA-graph cache of (reset +) the launch schedule: one graph launch per solve instead of ~60 kernel launches
   cudaGraphExec_t g_exec = nullptr;
   ModelC g_mc{};
-  int g_flags = -1, g_budget = -1, g_dense = -1, g_keep = -1;
+  int g_flags = -1, g_budget = -1, g_dense = -1, g_keep = -1;  // (loik_set_schedule drops the cached graph)
   int64_t g_launches = 0, g_sweeps = 0;
   bool use_graph = true;
   // the latency-bound tail rounds run on a high-priority stream so their few CTAs are dispatched ahead of the
   // bulk kernels of other solvers sharing the GPU
   cudaStream_t hi_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int small_after = 1 << 30, small_grid = 296;  // late rounds: at most small_grid CTAs, grid-stride (env LOIK_SMALL_AFTER / LOIK_SMALL_GRID)
-  int hi_after = 8;  // sweeps after which the schedule moves to the high-priority stream (env LOIK_HI_AFTER, <0: never)
-  int seg_after = 32;  // sweeps after which a branching tree is swept by the segment-parallel kernel (env LOIK_SEG_AFTER)
+  int small_after = 1 << 30, small_grid = 296;  // late rounds: at most small_grid CTAs, grid-stride
+  int hi_after = 8;  // sweeps after which the schedule moves to the high-priority stream (<0: never)
+  int seg_after = 32;  // sweeps after which a branching tree is swept by the segment-parallel kernel
+  int seg_warps = 0;   // warps per tile of that kernel: 0 = as many as the tree has parallel chains (at most 4), 1 = never use it
+  // lane-parallel shared-memory kernel (loik_lane.cuh): finishes every instance still active after `lane_after` sweeps
+  // (0: the whole solve; < 0: never).  Geometry fixed at creation from the model's record size.
+  int lane_after = -1;
+  bool lane_ok = false;
+  int lane_warps_req = 0;  // warps per CTA (0 = chosen from the record size)
+  int sms = 0, smem_optin = 0, smem_sm = 0;
   int sweeps_in_solve = 0;
+  std::vector<int> model_parents, model_types;  // kept for loik_set_schedule (segment re-assignment)
 };
 
 
@@ -780,6 +789,47 @@ static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S, int
   h->launches++;
 }
 
+// Geometry of the lane-parallel kernel for the current problem constants: W warps per CTA = 4 W instance records + the
+// per-CTA constants in shared memory.  Unless the caller fixed W (loik_schedule.lane_warps_per_cta): the smallest CTA that
+// keeps >= 90 % of the warps an SM's shared memory can hold -- small CTAs let the few CTAs that end up with a straggler
+// block less of an SM for the kernels of other solvers.
+struct LaneGeom { int warps = 0, ctas_per_sm = 0, grid = 0; size_t smem = 0; };
+static bool lane_geometry(const loik_solver* h, LaneGeom& G) {
+  const LaneDims D = lane_dims(h->nb, h->nc, h->npend, h->mc.href_uniform);
+  auto ctas_of = [&](int W) -> int {
+    const size_t bytes = lane_smem_bytes(D, W);
+    if (bytes > (size_t)h->smem_optin) return 0;
+    return std::min(32, (int)((size_t)h->smem_sm / (bytes + 1024)));
+  };
+  int W = h->lane_warps_req;
+  if (W <= 0) {
+    int best = 0;
+    for (int w = 1; w <= 8; ++w) best = std::max(best, ctas_of(w) * w);
+    for (int w = 1; w <= 8 && W <= 0; ++w)
+      if (ctas_of(w) > 0 && 10 * ctas_of(w) * w >= 9 * best) W = w;
+  }
+  if (W <= 0 || W > 8 || ctas_of(W) == 0) return false;
+  G.warps = W; G.ctas_per_sm = ctas_of(W); G.smem = lane_smem_bytes(D, W);
+  G.grid = std::min(h->sms * G.ctas_per_sm, (h->batch + kLaneI * W - 1) / (kLaneI * W));
+  return true;
+}
+// The lane-parallel kernel on the instances of `src` (all `batch` slots, or the `*n_list` slots named by `list`);
+// `origin`: home slot of every slot of a packed arena.  Runs every instance to the end of its solve (or `iters`
+// iterations each in fixed mode) and sends the results to the home arena.
+static int launch_lane(loik_solver* h, cudaStream_t st, const double* src, const int* list, const int* n_list, const int* origin,
+                       int fixed, int iters) {
+  LaneGeom G;
+  if (!lane_geometry(h, G)) return fail(LOIK_ERR_STATE, "lane-parallel kernel: the instance record does not fit shared memory");
+  LaneP P{};
+  P.src = src; P.list = list; P.n_list = n_list; P.n = h->batch; P.origin = origin; P.home = h->arena;
+  P.queue = h->d_counts + 3; P.iters = iters; P.fixed = fixed; P.keep_ws = h->S.keep_ws;
+  CK(cudaMemsetAsync(h->d_counts + 3, 0, sizeof(int), st));
+  k_iterate_lane<<<G.grid, 32 * G.warps, G.smem, st>>>(h->mc, P);
+  h->launches++;
+  return LOIK_OK;
+}
+static bool use_lane(const loik_solver* h) { return h->lane_ok && h->lane_after >= 0 && !h->debug; }
+
 static int ensure_stage(loik_solver* h, size_t bytes, bool need_host) {
   if (need_host && bytes > h->h_stage_bytes) {
     if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -827,6 +877,58 @@ static bool is_symmetric(const double* M) {
   return true;
 }
 
+// Maximal register-carried chains of the tree = the segments different warps can sweep (k_iterate_seg); `max_warps`:
+// 0 = as many warps per tile as the tree has parallel chains (at most 4), 1 = one segment, one warp (k_iterate only).
+static void assign_segments(ModelC& M, int max_warps) {
+  const int nj = M.nj;
+  std::vector<int> seg_of(nj, -1), lo, hi;
+  for (int i = 1; i < nj; ++i) {
+    if (!M.j[i].carry) { lo.push_back(i); hi.push_back(i); }
+    else hi.back() = i;
+    seg_of[i] = (int)lo.size() - 1;
+  }
+  const int ns = (int)lo.size();
+  M.nseg = 1; M.nwarp = 1; M.nblevel = 1; M.nflevel = 1;
+  std::memset(M.seg, 0, sizeof(M.seg));
+  M.seg[0] = SegC{1, (short)(nj - 1), 0, 0, 0, 0};
+  if (ns < 2 || ns > kMaxSeg || max_warps == 1) return;
+  std::vector<int> fl(ns, 0), bl(ns, 0), par(ns, -1);
+  for (int g = 0; g < ns; ++g) {
+    const int p = M.j[lo[g]].parent;
+    if (p > 0) { par[g] = seg_of[p]; fl[g] = fl[par[g]] + 1; }
+  }
+  for (int g = ns - 1; g >= 0; --g)
+    if (par[g] >= 0) bl[par[g]] = std::max(bl[par[g]], bl[g] + 1);
+  int nbl = 0, nfl = 0, width = 1;
+  for (int g = 0; g < ns; ++g) { nbl = std::max(nbl, bl[g] + 1); nfl = std::max(nfl, fl[g] + 1); }
+  for (int lv = 0; lv < std::max(nbl, nfl); ++lv) {
+    int cb = 0, cf = 0;
+    for (int g = 0; g < ns; ++g) { cb += bl[g] == lv; cf += fl[g] == lv; }
+    width = std::max(width, std::max(cb, cf));
+  }
+  int NW = std::min(4, width);
+  if (max_warps > 1) NW = std::min(NW, max_warps);
+  if (NW < 2) return;
+  M.nseg = ns; M.nwarp = NW; M.nblevel = nbl; M.nflevel = nfl;
+  // longest-processing-time-first assignment of the segments of every level to the warps
+  auto assign = [&](const std::vector<int>& level, int nlev, bool backward) {
+    for (int lv = 0; lv < nlev; ++lv) {
+      std::vector<int> ids;
+      for (int g = 0; g < ns; ++g) if (level[g] == lv) ids.push_back(g);
+      std::sort(ids.begin(), ids.end(), [&](int a, int b) { return (hi[a] - lo[a]) > (hi[b] - lo[b]); });
+      std::vector<int> load(NW, 0);
+      for (int g : ids) {
+        const int wmin = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        load[wmin] += hi[g] - lo[g] + 1;
+        if (backward) M.seg[g].bwarp = (short)wmin; else M.seg[g].fwarp = (short)wmin;
+      }
+    }
+  };
+  for (int g = 0; g < ns; ++g) { M.seg[g].lo = (short)lo[g]; M.seg[g].hi = (short)hi[g]; M.seg[g].blevel = (short)bl[g]; M.seg[g].flevel = (short)fl[g]; }
+  assign(bl, nbl, true);
+  assign(fl, nfl, false);
+}
+
 extern "C" {
 
 int32_t loik_abi_version(void) { return 1; }
@@ -865,14 +967,6 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
   };
   h->nv = 0; h->nq = 0;
   for (int i = 1; i < nj; ++i) { h->nv += nv_of(i); h->nq += nq_of(i); }
-  if (const char* e = std::getenv("LOIK_DENSE")) { const int v = std::atoi(e); if (v >= 0) h->dense_sweeps = v; }
-  if (const char* e = std::getenv("LOIK_NO_GRAPH")) { if (std::atoi(e) != 0) h->use_graph = false; }
-  if (const char* e = std::getenv("LOIK_SMALL_AFTER")) h->small_after = std::atoi(e);
-  if (const char* e = std::getenv("LOIK_SMALL_GRID")) h->small_grid = std::atoi(e);
-  if (const char* e = std::getenv("LOIK_HI_AFTER")) h->hi_after = std::atoi(e);
-  if (const char* e = std::getenv("LOIK_SEG_AFTER")) h->seg_after = std::atoi(e);
-  if (const char* e = std::getenv("LOIK_REPS")) { const int v = std::atoi(e); if (v >= 1) h->sched_reps = v; }
-  if (const char* e = std::getenv("LOIK_GROWTH")) { const double v = std::atof(e); if (v >= 1.0) h->sched_growth = v; }
   ModelC& M = h->mc;
   std::memset(&M, 0, sizeof(M));
   M.nj = nj; M.nb = nj - 1; M.nc = h->nc;
@@ -900,6 +994,7 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
     J.qkind = unbounded(i) ? 1 : 0;
     // an unbounded revolute joint is its bounded twin everywhere but in how q enters (k_set_q, k_integrate, the q getter)
     if (unbounded(i)) J.jtype = model->joint_types[i] == LOIK_JOINT_RUBU ? LOIK_JOINT_RU : model->joint_types[i] - LOIK_JOINT_RUBX;
+    J.sidx = (J.nvj == 1 && J.jtype <= LOIK_JOINT_PZ) ? (J.jtype <= LOIK_JOINT_RZ ? 3 + J.jtype : J.jtype - LOIK_JOINT_PX) : -1;
   }
   for (int i = 1; i < nj; ++i) {
     JointC& J = M.j[i];
@@ -918,57 +1013,7 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
     else if (M.nspan > 0 && M.span[M.nspan - 1].md == 0) M.span[M.nspan - 1].hi = (short)i;
     else M.span[M.nspan++] = SpanC{(short)i, (short)i, 0, 0};
   }
-  {
-    std::vector<int> seg_of(nj, -1), lo, hi;
-    for (int i = 1; i < nj; ++i) {
-      if (!M.j[i].carry) { lo.push_back(i); hi.push_back(i); }
-      else hi.back() = i;
-      seg_of[i] = (int)lo.size() - 1;
-    }
-    const int ns = (int)lo.size();
-    M.nseg = 1; M.nwarp = 1; M.nblevel = 1; M.nflevel = 1;
-    M.seg[0] = SegC{1, (short)(nj - 1), 0, 0, 0, 0};
-    bool want = ns >= 2 && ns <= kMaxSeg;
-    if (const char* e = std::getenv("LOIK_SEG")) want = want && std::atoi(e) != 0;
-    if (want) {
-      std::vector<int> fl(ns, 0), bl(ns, 0), par(ns, -1);
-      for (int g = 0; g < ns; ++g) {
-        const int p = M.j[lo[g]].parent;
-        if (p > 0) { par[g] = seg_of[p]; fl[g] = fl[par[g]] + 1; }
-      }
-      for (int g = ns - 1; g >= 0; --g)
-        if (par[g] >= 0) bl[par[g]] = std::max(bl[par[g]], bl[g] + 1);
-      int nbl = 0, nfl = 0, width = 1;
-      for (int g = 0; g < ns; ++g) { nbl = std::max(nbl, bl[g] + 1); nfl = std::max(nfl, fl[g] + 1); }
-      for (int lv = 0; lv < std::max(nbl, nfl); ++lv) {
-        int cb = 0, cf = 0;
-        for (int g = 0; g < ns; ++g) { cb += bl[g] == lv; cf += fl[g] == lv; }
-        width = std::max(width, std::max(cb, cf));
-      }
-      int NW = std::min(4, width);
-      if (const char* e = std::getenv("LOIK_NWARP")) NW = std::max(1, std::min(NW, std::atoi(e)));  // tuning knob: warps per tile
-      if (NW >= 2) {
-        M.nseg = ns; M.nwarp = NW; M.nblevel = nbl; M.nflevel = nfl;
-        // longest-processing-time-first assignment of the segments of every level to the warps
-        auto assign = [&](const std::vector<int>& level, int nlev, bool backward) {
-          for (int lv = 0; lv < nlev; ++lv) {
-            std::vector<int> ids;
-            for (int g = 0; g < ns; ++g) if (level[g] == lv) ids.push_back(g);
-            std::sort(ids.begin(), ids.end(), [&](int a, int b) { return (hi[a] - lo[a]) > (hi[b] - lo[b]); });
-            std::vector<int> load(NW, 0);
-            for (int g : ids) {
-              const int wmin = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-              load[wmin] += hi[g] - lo[g] + 1;
-              if (backward) M.seg[g].bwarp = (short)wmin; else M.seg[g].fwarp = (short)wmin;
-            }
-          }
-        };
-        for (int g = 0; g < ns; ++g) { M.seg[g].lo = (short)lo[g]; M.seg[g].hi = (short)hi[g]; M.seg[g].blevel = (short)bl[g]; M.seg[g].flevel = (short)fl[g]; }
-        assign(bl, nbl, true);
-        assign(fl, nfl, false);
-      }
-    }
-  }
+  assign_segments(M, h->seg_warps);
   // tile record layout: [globals | joint blocks | task blocks | pending blocks | debug vectors]
   const int nb = h->nb, nc = std::max(h->nc, 1);
   Offs& O = M.off;
@@ -988,13 +1033,22 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
     const cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) { delete h; return fail(LOIK_ERR_CUDA, std::string("cudaSetDevice(device): ") + cudaGetErrorString(e)); }
   }
+  // every allocation is checked: on failure the partially built handle is destroyed and the CUDA error reported
+#define CKA(call)                                                                                        \
+  do {                                                                                                   \
+    const cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                             \
+      loik_destroy(h);                                                                                   \
+      return fail(LOIK_ERR_CUDA, std::string("loik_create: " #call ": ") + cudaGetErrorString(e_));      \
+    }                                                                                                    \
+  } while (0)
   const size_t arena_doubles = (size_t)h->ntiles * rows * 32;
-  if (cudaMalloc(&h->arena, arena_doubles * sizeof(double)) != cudaSuccess) { delete h; return fail(LOIK_ERR_CUDA, "loik_create: cudaMalloc failed"); }
-  cudaMemset(h->arena, 0, arena_doubles * sizeof(double));
-  cudaMalloc(&h->d_lists, 2 * (size_t)batch * sizeof(int));
-  cudaMalloc(&h->d_counts, 4 * sizeof(int));
-  cudaMemset(h->d_counts, 0, 4 * sizeof(int));
-  cudaMalloc(&h->d_stats, 4 * sizeof(unsigned long long));
+  CKA(cudaMalloc(&h->arena, arena_doubles * sizeof(double)));
+  CKA(cudaMemset(h->arena, 0, arena_doubles * sizeof(double)));
+  CKA(cudaMalloc(&h->d_lists, 2 * (size_t)batch * sizeof(int)));
+  CKA(cudaMalloc(&h->d_counts, 4 * sizeof(int)));
+  CKA(cudaMemset(h->d_counts, 0, 4 * sizeof(int)));
+  CKA(cudaMalloc(&h->d_stats, 4 * sizeof(unsigned long long)));
   {  // row maps of the gettable fields: field -> absolute rows of the tile record, in output order
     std::vector<int> all;
     const int ncq = h->nc;
@@ -1057,20 +1111,28 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
       h->map_len[field] = (int)m.size();
       all.insert(all.end(), m.begin(), m.end());
     }
-    cudaMalloc(&h->d_map, std::max<size_t>(all.size(), 1) * sizeof(int));
-    cudaMemcpy(h->d_map, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice);
+    CKA(cudaMalloc(&h->d_map, std::max<size_t>(all.size(), 1) * sizeof(int)));
+    CKA(cudaMemcpy(h->d_map, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
   {
     int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    cudaStreamCreateWithPriority(&h->hi_stream, cudaStreamNonBlocking, hi);
-    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    CKA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CKA(cudaStreamCreateWithPriority(&h->hi_stream, cudaStreamNonBlocking, hi));
+    CKA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CKA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   }
-  cudaMallocHost(&h->h_counts, 4 * sizeof(int));
-  cudaMallocHost(&h->h_stats, 4 * sizeof(unsigned long long));
+  CKA(cudaMallocHost(&h->h_counts, 4 * sizeof(int)));
+  CKA(cudaMallocHost(&h->h_stats, 4 * sizeof(unsigned long long)));
   h->S.arena = h->arena; h->S.n = batch; h->S.list = nullptr; h->S.n_list = nullptr; h->S.n_active = nullptr;
-  if (cudaGetLastError() != cudaSuccess) { loik_destroy(h); return fail(LOIK_ERR_CUDA, "loik_create: allocation failed"); }
+  CKA(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device));
+  CKA(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  CKA(cudaDeviceGetAttribute(&h->smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+  {
+    LaneGeom G;
+    h->lane_ok = M.nmd == 0 && lane_geometry(h, G);
+    if (h->lane_ok) CKA(cudaFuncSetAttribute(k_iterate_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+  }
+#undef CKA
   *out = h;
   return LOIK_OK;
 }
@@ -1133,6 +1195,7 @@ static int set_problem_consts(loik_solver* h, const double* H_ref, const double*
   double hv_inf = 0; for (int i = 0; i < 6; ++i) hv_inf = std::max(hv_inf, std::fabs(Hv[i]));
   M.Hv_inf = hv_inf;  // = |Hv[0]|inf (ik-id-description-optimized.hpp:95)
   M.bounds_per_instance = bounds_shared ? 0 : 1;
+  M.href_uniform = 1;
   if (bounds_shared)
     for (int i = 1; i < h->nj; ++i)
       if (M.j[i].nvj > 1)
@@ -1213,6 +1276,7 @@ int loik_update_references(loik_solver* h, const double* H_refs, const double* v
     if (n > M.Hv_inf) M.Hv_inf = n;  // only grows (ik-id-description-optimized.hpp:115-117)
     if (i >= 1) { sym_blocks(H_refs + 36 * i, M.j[i].HrA, M.j[i].HrB, M.j[i].HrD); for (int a = 0; a < 6; ++a) M.j[i].Hv[a] = Hv[a]; }
   }
+  M.href_uniform = 0;
   return LOIK_OK;
 }
 
@@ -1248,14 +1312,17 @@ static int ensure_scratch(loik_solver* h) {
 }
 
 static int run_schedule(loik_solver* h, cudaStream_t st0, int budget) {
-  int rc = ensure_scratch(h);
+  const bool lane = use_lane(h);
+  // sweeps done by the tile kernels before the lane-parallel kernel takes every instance that is still active
+  const int pre = lane ? std::min(budget, h->lane_after) : budget;
+  int rc = (pre > h->dense_sweeps) ? ensure_scratch(h) : LOIK_OK;
   if (rc) return rc;
   cudaStream_t st = st0;
   bool forked = false;
   const int B = h->batch;
   int done = 0;
   int li = 0;  // list / count that the NEXT launch reads
-  const int dense = std::min(budget, h->dense_sweeps);
+  const int dense = std::min(pre, h->dense_sweeps);
   StateP X = h->S;  // where the instances of the next launch live: the home arena first
   X.list = nullptr; X.n_list = nullptr;
   if (dense > 0) {
@@ -1268,7 +1335,7 @@ static int run_schedule(loik_solver* h, cudaStream_t st0, int budget) {
   }
   int cur = -1;  // -1 = home arena, else scratch index
   int chunk = 1, reps = 0;
-  while (done < budget) {
+  while (done < pre) {
     if (!forked && h->hi_after >= 0 && done >= h->hi_after && h->hi_stream) {  // tail rounds: high-priority stream
       CK(cudaEventRecord(h->ev_fork, st0));
       CK(cudaStreamWaitEvent(h->hi_stream, h->ev_fork, 0));
@@ -1276,7 +1343,7 @@ static int run_schedule(loik_solver* h, cudaStream_t st0, int budget) {
       forked = true;
     }
     const int y = cur < 0 ? 0 : 1 - cur;
-    const int c = std::min(chunk, budget - done);
+    const int c = std::min(chunk, pre - done);
     StateP P = X;
     P.dst = h->scratch[y];
     P.origin_src = cur < 0 ? nullptr : h->d_origin + (size_t)cur * B;
@@ -1295,6 +1362,11 @@ static int run_schedule(loik_solver* h, cudaStream_t st0, int budget) {
     cur = y; li = 1 - li;
     if (++reps == h->sched_reps) { reps = 0; if (chunk < 64) chunk = std::max(chunk + 1, (int)(chunk * h->sched_growth)); }
   }
+  if (lane && done < budget) {  // everything still active runs to the end of its solve in the lane-parallel kernel
+    rc = launch_lane(h, st, X.arena, X.list, X.n_list, cur < 0 ? nullptr : h->d_origin + (size_t)cur * B, 0, 0);
+    if (rc) return rc;
+    h->sweeps += budget - done;
+  }
   CK(cudaMemsetAsync(h->d_counts + 2, 0, sizeof(int), st));  // nothing is active after a complete schedule
   if (forked) {
     CK(cudaEventRecord(h->ev_join, h->hi_stream));
@@ -1307,8 +1379,8 @@ static int run_schedule(loik_solver* h, cudaStream_t st0, int budget) {
 // (reset +) schedule, replayed from a CUDA graph when the stream can be captured (any stream but the legacy default
 // one).  The graph is re-captured when the parameter block, the reset flags or the iteration budget change.
 static int solve_scheduled_impl(loik_solver* h, cudaStream_t st, int reset_flags, int budget) {
-  int rc = ensure_scratch(h);
-  if (rc) return rc;
+  int rc = LOIK_OK;
+  if ((use_lane(h) ? std::min(budget, h->lane_after) : budget) > h->dense_sweeps) { rc = ensure_scratch(h); if (rc) return rc; }  // (before any capture)
   const bool graphable = h->use_graph && st != nullptr && st != cudaStreamLegacy && !h->debug;
   if (!graphable) {
     if (reset_flags) { rc = launch_reset(h, reset_flags, st); if (rc) return rc; }
@@ -1345,7 +1417,7 @@ static int solve_scheduled(loik_solver* h, cudaStream_t st, int reset_flags, int
   const int rc = solve_scheduled_impl(h, st, reset_flags, budget);
   // the dense sweeps run in place; instances that finish in the migrating launches after them only bring their
   // workspace home with keep_ws
-  if (budget > h->dense_sweeps && !h->S.keep_ws) h->ws_valid = false;
+  if ((budget > h->dense_sweeps || (use_lane(h) && budget > h->lane_after)) && !h->S.keep_ws) h->ws_valid = false;
   return rc;
 }
 
@@ -1455,8 +1527,14 @@ int loik_iterate_fixed(loik_solver* h, int32_t iters, int32_t reset, void* strea
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
   if (reset) { int rc = launch_reset(h, RST_WZ | RST_VFF | RST_YATY | RST_SOLVER, st); if (rc) return rc; }
-  // one launch per iteration, dense: this is the quantity the roofline is quoted on
-  for (int i = 0; i < iters; ++i) launch_iterate(h, st, h->S, 1, 1, 0, h->seg_after <= 0);  // the kernel the bulk of a solve runs
+  if (use_lane(h) && h->lane_after == 0) {
+    // the whole solve runs in the lane-parallel kernel: one launch, `iters` iterations of every instance
+    if (iters > 0) { int rc = launch_lane(h, st, h->arena, nullptr, nullptr, nullptr, 1, iters); if (rc) return rc; }
+    if (!h->S.keep_ws) h->ws_valid = false;
+  } else {
+    // one launch per iteration, dense: this is the quantity the roofline is quoted on
+    for (int i = 0; i < iters; ++i) launch_iterate(h, st, h->S, 1, 1, 0, h->seg_after <= 0);  // the kernel the bulk of a solve runs
+  }
   h->sweeps += iters;
   CK(cudaGetLastError());
   return LOIK_OK;
@@ -1601,10 +1679,58 @@ int loik_reduce_stats(loik_solver* h, void* stream, void** dev_ptr) {
 
 int64_t loik_launch_count(loik_solver* h) { return h ? h->launches : 0; }
 
-int loik_set_max_iter(loik_solver* h, int32_t m) { if (!h) return LOIK_ERR_INVALID; h->prm.max_iter = m; h->mc.max_iter = m; return LOIK_OK; }
-int loik_set_rho(loik_solver* h, double rho) { if (!h) return LOIK_ERR_INVALID; h->prm.rho = rho; h->mc.rho = rho; return LOIK_OK; }
-int loik_set_mu(loik_solver* h, double mu) { if (!h) return LOIK_ERR_INVALID; h->prm.mu = mu; h->mc.mu0 = mu; return LOIK_OK; }
-int loik_set_tol_tail_solve(loik_solver* h, double tol) { if (!h) return LOIK_ERR_INVALID; h->prm.tol_tail_solve = tol; h->mc.tol_tail = tol; return LOIK_OK; }
-int loik_set_warm_start(loik_solver* h, int32_t ws) { if (!h) return LOIK_ERR_INVALID; h->prm.warm_start = ws; return LOIK_OK; }
+// setters / getters of the base class (task-solver-base.hpp:87-141, loik-loid-optimized.hpp:703).  The hyper-parameters
+// travel to the kernels in the parameter block; a cached launch graph is re-captured when that block changes.
+#define LOIK_SETTER(name, type, check, assign)                                                                      \
+  int name(loik_solver* h, type v) {                                                                                \
+    if (!h) return fail(LOIK_ERR_INVALID, #name ": null handle");                                                   \
+    if (!(check)) return fail(LOIK_ERR_INVALID, #name ": value out of range");                                      \
+    assign;                                                                                                         \
+    return LOIK_OK;                                                                                                 \
+  }
+LOIK_SETTER(loik_set_max_iter, int32_t, v >= 0, (h->prm.max_iter = v, h->mc.max_iter = v))
+LOIK_SETTER(loik_set_rho, double, v == v, (h->prm.rho = v, h->mc.rho = v))
+LOIK_SETTER(loik_set_mu, double, v == v, (h->prm.mu = v, h->mc.mu0 = v))
+LOIK_SETTER(loik_set_mu_equality_scale_factor, double, v == v, (h->prm.mu_equality_scale_factor = v, h->mc.mu_scale = v))
+LOIK_SETTER(loik_set_tol_abs, double, v == v, (h->prm.tol_abs = v, h->mc.tol_abs = v))
+LOIK_SETTER(loik_set_tol_rel, double, v == v, (h->prm.tol_rel = v, h->mc.tol_rel = v))
+LOIK_SETTER(loik_set_tol_primal_inf, double, v == v, (h->prm.tol_primal_inf = v, h->mc.tol_pinf = v))
+LOIK_SETTER(loik_set_tol_dual_inf, double, v == v, (h->prm.tol_dual_inf = v, h->mc.tol_dinf = v))
+LOIK_SETTER(loik_set_tol_tail_solve, double, v == v, (h->prm.tol_tail_solve = v, h->mc.tol_tail = v))
+LOIK_SETTER(loik_set_warm_start, int32_t, true, (h->prm.warm_start = v))
+#undef LOIK_SETTER
+
+int loik_get_params(loik_solver* h, loik_params* out) {
+  if (!h || !out) return fail(LOIK_ERR_INVALID, "loik_get_params: null argument");
+  *out = h->prm;
+  return LOIK_OK;
+}
+
+int loik_get_schedule(loik_solver* h, loik_schedule* out) {
+  if (!h || !out) return fail(LOIK_ERR_INVALID, "loik_get_schedule: null argument");
+  out->dense_sweeps = h->dense_sweeps; out->repack_reps = h->sched_reps; out->repack_growth = h->sched_growth;
+  out->hi_priority_after = h->hi_after; out->seg_after = h->seg_after; out->seg_warps = h->seg_warps;
+  out->lane_after = h->lane_after; out->use_graph = h->use_graph ? 1 : 0;
+  out->small_after = h->small_after; out->small_grid = h->small_grid;
+  LaneGeom G;
+  const bool ok = h->lane_ok && lane_geometry(h, G);
+  out->lane_warps_per_cta = h->lane_warps_req;
+  out->lane_available = ok ? 1 : 0; out->lane_warps_chosen = G.warps; out->lane_ctas = G.grid; out->lane_smem_bytes = (int32_t)G.smem;
+  return LOIK_OK;
+}
+
+int loik_set_schedule(loik_solver* h, const loik_schedule* sc) {
+  if (!h || !sc) return fail(LOIK_ERR_INVALID, "loik_set_schedule: null argument");
+  if (sc->dense_sweeps < 0 || sc->repack_reps < 1 || !(sc->repack_growth >= 1.0) || sc->seg_warps < 0 || sc->seg_warps > 4 || sc->small_grid < 1 ||
+      sc->lane_warps_per_cta < 0 || sc->lane_warps_per_cta > 8)
+    return fail(LOIK_ERR_INVALID, "loik_set_schedule: dense_sweeps >= 0, repack_reps >= 1, repack_growth >= 1, 0 <= seg_warps <= 4, small_grid >= 1, 0 <= lane_warps_per_cta <= 8");
+  h->dense_sweeps = sc->dense_sweeps; h->sched_reps = sc->repack_reps; h->sched_growth = sc->repack_growth;
+  h->hi_after = sc->hi_priority_after; h->seg_after = sc->seg_after;
+  h->lane_after = sc->lane_after; h->use_graph = sc->use_graph != 0; h->lane_warps_req = sc->lane_warps_per_cta;
+  h->small_after = sc->small_after; h->small_grid = sc->small_grid;
+  if (sc->seg_warps != h->seg_warps) { h->seg_warps = sc->seg_warps; assign_segments(h->mc, h->seg_warps); }
+  if (h->g_exec) { cudaGraphExecDestroy(h->g_exec); h->g_exec = nullptr; }  // the cached launch graph follows the schedule
+  return LOIK_OK;
+}
 
 }  // extern "C"

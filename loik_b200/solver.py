@@ -42,7 +42,9 @@ NORM_NAMES = ["bT_delta_y_plus", "bT_delta_y_minus", "Av_inf_norm", "nu_inf_norm
 EXPORTS = ["loik_abi_version", "loik_last_error", "loik_create", "loik_destroy", "loik_model_layout", "loik_solve_init",
            "loik_update_references", "loik_solve", "loik_solve_full", "loik_solve_task", "loik_integrate", "loik_iterate_fixed",
            "loik_fwd_pass_init", "loik_reset_recursion", "loik_step", "loik_set_debug", "loik_set_keep_workspace", "loik_get", "loik_get_stats", "loik_reduce_stats", "loik_launch_count",
-           "loik_set_max_iter", "loik_set_rho", "loik_set_mu", "loik_set_tol_tail_solve", "loik_set_warm_start",
+           "loik_set_max_iter", "loik_set_rho", "loik_set_mu", "loik_set_mu_equality_scale_factor", "loik_set_tol_abs",
+           "loik_set_tol_rel", "loik_set_tol_primal_inf", "loik_set_tol_dual_inf", "loik_set_tol_tail_solve",
+           "loik_set_warm_start", "loik_get_params", "loik_get_schedule", "loik_set_schedule",
            "loik_active_count_device_ptr", "loik_solve_begin", "loik_solve_chunk", "loik_solve_end"]
 
 
@@ -58,6 +60,15 @@ class _Params(C.Structure):
                 ("mu_equality_scale_factor", C.c_double), ("mu_update_strat", C.c_int32), ("num_eq_c", C.c_int32),
                 ("eq_c_dim", C.c_int32), ("warm_start", C.c_int32), ("tol_tail_solve", C.c_double),
                 ("verbose", C.c_int32), ("logging", C.c_int32)]
+
+
+class _Schedule(C.Structure):
+    _fields_ = [("dense_sweeps", C.c_int32), ("repack_reps", C.c_int32), ("repack_growth", C.c_double),
+                ("hi_priority_after", C.c_int32), ("seg_after", C.c_int32), ("seg_warps", C.c_int32),
+                ("lane_after", C.c_int32), ("use_graph", C.c_int32), ("small_after", C.c_int32), ("small_grid", C.c_int32),
+                ("lane_warps_per_cta", C.c_int32),
+                ("lane_available", C.c_int32), ("lane_warps_chosen", C.c_int32), ("lane_ctas", C.c_int32),
+                ("lane_smem_bytes", C.c_int32)]
 
 
 def load_library(path: str | None = None):
@@ -100,6 +111,11 @@ def load_library(path: str | None = None):
     lib.loik_set_rho.argtypes = [vp, C.c_double]
     lib.loik_set_mu.argtypes = [vp, C.c_double]
     lib.loik_set_tol_tail_solve.argtypes = [vp, C.c_double]
+    for name in ("mu_equality_scale_factor", "tol_abs", "tol_rel", "tol_primal_inf", "tol_dual_inf"):
+        getattr(lib, "loik_set_" + name).argtypes = [vp, C.c_double]
+    lib.loik_get_params.argtypes = [vp, C.POINTER(_Params)]
+    lib.loik_get_schedule.argtypes = [vp, C.POINTER(_Schedule)]
+    lib.loik_set_schedule.argtypes = [vp, C.POINTER(_Schedule)]
     lib.loik_set_warm_start.argtypes = [vp, i32]
     lib.loik_active_count_device_ptr.argtypes = [vp, C.POINTER(vp)]
     lib.loik_solve_begin.argtypes = [vp, vp]
@@ -398,6 +414,54 @@ class FirstOrderLoikOptimized:
 
     def set_warm_start(self, ws):
         self._check(self._lib.loik_set_warm_start(self._h, int(bool(ws))))
+
+    def set_mu_equality_scale_factor(self, f):
+        self._check(self._lib.loik_set_mu_equality_scale_factor(self._h, float(f)))
+
+    def set_tol_abs(self, tol):
+        self._check(self._lib.loik_set_tol_abs(self._h, float(tol)))
+
+    def set_tol_rel(self, tol):
+        self._check(self._lib.loik_set_tol_rel(self._h, float(tol)))
+
+    def set_tol_primal_inf(self, tol):
+        self._check(self._lib.loik_set_tol_primal_inf(self._h, float(tol)))
+
+    def set_tol_dual_inf(self, tol):
+        self._check(self._lib.loik_set_tol_dual_inf(self._h, float(tol)))
+
+    def get_params(self) -> dict:
+        """The hyper-parameters as the solver holds them (get_max_iter ... get_tol_dual_inf, task-solver-base.hpp:87-141)."""
+        pr = _Params()
+        self._check(self._lib.loik_get_params(self._h, C.byref(pr)))
+        return {name: getattr(pr, name) for name, _ in _Params._fields_}
+
+    def get_rho(self):
+        return self.get_params()["rho"]
+
+    def get_max_iter(self):
+        return self.get_params()["max_iter"]
+
+    def get_tol_primal_inf(self):
+        return self.get_params()["tol_primal_inf"]
+
+    def get_tol_dual_inf(self):
+        return self.get_params()["tol_dual_inf"]
+
+    def get_schedule(self) -> dict:
+        sc = _Schedule()
+        self._check(self._lib.loik_get_schedule(self._h, C.byref(sc)))
+        return {name: getattr(sc, name) for name, _ in _Schedule._fields_}
+
+    def set_schedule(self, **kw):
+        """Change how a batched Solve() is laid out on the GPU (include/loik_b200.h: loik_schedule); unknown keys raise."""
+        sc = _Schedule()
+        self._check(self._lib.loik_get_schedule(self._h, C.byref(sc)))
+        for k, v in kw.items():
+            if k not in dict(_Schedule._fields_) or k in ("lane_available", "lane_warps_chosen", "lane_ctas", "lane_smem_bytes"):
+                raise KeyError(k)
+            setattr(sc, k, v)
+        self._check(self._lib.loik_set_schedule(self._h, C.byref(sc)))
 
     def _field_shape(self, field):
         nb, nc, nv, nq = self.model.nb, self.nc, self.model.nv, self.model.nq
