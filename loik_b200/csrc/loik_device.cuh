@@ -132,6 +132,7 @@ struct StateP {
   int* next_count;
   double* home;
   int keep_ws;        // retiring instances also carry their backward->forward workspace home (loik_set_keep_workspace)
+  int drop_ws;        // the forward sweep drops the consumed workspace lines from L2 (discard_workspace); never with keep_ws
 };
 
 // The batch-uniform block (model, problem constants, hyper-parameters) is passed to every kernel BY VALUE as a
@@ -410,6 +411,20 @@ LOIK_DEV void pf_rows(const double* P, int row0) {
   for (int c = 0; c < N; ++c) pf(P, row0 + c);
 }
 
+// The backward->forward workspace of a joint (rows JR_H .. JR_R: His, pis, UDinv, Dinv, r) is dead once the forward step
+// has consumed it -- the next backward sweep rewrites it before anything reads it -- yet the dirty lines would still be
+// written back to HBM when L2 evicts them (128 of the 165 MB a Panda-65 536 launch writes).  discard.global.L2 drops a
+// line from L2 without the write-back.  The lanes that are executing share the 70 lines of the tile's block (a warp
+// owns a whole tile here); called after the step's loads have been consumed, i.e. have returned for every lane.
+LOIK_DEV void discard_workspace(const double* Pj_lane) {
+  const unsigned am = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int rank = __popc(am & ((1u << lane) - 1u)), n = __popc(am);
+  const char* base = reinterpret_cast<const char*>(Pj_lane - lane) + JR_H * 256;
+  constexpr int kLines = (JR_ROWS - JR_H) * 2;
+  for (int ln = rank; ln < kLines; ln += n) asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + ln * 128) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // Backward sweep: FwdPass1 (hxx:290-338) fused into BwdPassOptimizedVisitor (hxx:345-354, algo :31-81).
 // Leaves for the forward sweep, per joint: H_i and p_i (accumulated over the subtree, un-projected,
@@ -557,7 +572,7 @@ LOIK_DEV void zero(Carry& cy) {
 // Accumulates into `cy` (the caller zeroes it once per iteration).
 template <bool DEBUG>
 LOIK_DEV void sweep_forward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, Carry& cy,
-                            const int lo, const int hi) {
+                            const int lo, const int hi, const bool drop_ws = false) {
   const Offs& O = c_model.off;
   const int nb = c_model.nb;
   const double inv_mu = 1.0 / mu;
@@ -686,6 +701,7 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, const double* Ts, double* Td,
         st(Pk, TR_ATY + a, K.A[a] * y[0] + K.A[6 + a] * y[1] + K.A[12 + a] * y[2] + K.A[18 + a] * y[3] + K.A[24 + a] * y[4] + K.A[30 + a] * y[5]);
       }
     }
+    if (drop_ws) discard_workspace(Pj);
   }
 }
 
@@ -1143,9 +1159,9 @@ LOIK_DEV void span_backward(const ModelC& c_model, const double* Ts, double* Td,
 }
 template <bool DEBUG>
 LOIK_DEV void span_forward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, Carry& cy,
-                           const int lo, const int hi) {
+                           const int lo, const int hi, const bool drop_ws = false) {
   const int k = c_model.j[lo].nvj;
-  if (k == 1) { sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, lo, hi); return; }
+  if (k == 1) { sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, lo, hi, drop_ws); return; }
   Carry tmp = cy;
   if (k == 3) md_forward<DEBUG, 3>(c_model, Ts, Td, mu, mu_eq, tmp, lo);
   else md_forward<DEBUG, 6>(c_model, Ts, Td, mu, mu_eq, tmp, lo);

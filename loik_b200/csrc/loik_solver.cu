@@ -119,6 +119,9 @@ template <bool DEBUG, int MINB, bool MD = false>
 __global__ void __launch_bounds__(kBlock) __maxnreg__(MINB <= 4 ? 255 : (65536 / (kBlock * MINB)) / 8 * 8) k_iterate(const __grid_constant__ ModelC c_model, const StateP S, const int iters, const int fixed) {
   const int limit = S.list ? *S.n_list : (S.n_dev ? *S.n_dev : S.n);
   const int stride = gridDim.x * blockDim.x;
+  // the warp writes a whole tile (in place without a list, or the dense prefix of a migrating launch): its dead workspace
+  // lines can be dropped from L2 (discard_workspace)
+  const bool drop_ws = !DEBUG && S.drop_ws && (S.list == nullptr || S.dst != nullptr);
   // grid-stride over the slots: late rounds are launched with a small grid (the count lives on the device)
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k - (int)threadIdx.x % 32 < limit; k += stride) {
   const int s = k < limit ? (S.list ? S.list[k] : k) : -1;
@@ -143,12 +146,12 @@ __global__ void __launch_bounds__(kBlock) __maxnreg__(MINB <= 4 ? 255 : (65536 /
         zero(rs);
         if (MD) {
           for (int g = c_model.nspan - 1; g >= 0; --g) span_backward(c_model, Ts, Td, mu, mu_eq, c_model.span[g].lo, c_model.span[g].hi, migrate);
-          for (int g = 0; g < c_model.nspan; ++g) span_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, c_model.span[g].lo, c_model.span[g].hi);
+          for (int g = 0; g < c_model.nspan; ++g) span_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, c_model.span[g].lo, c_model.span[g].hi, drop_ws);
           for (int g = c_model.nspan - 1; g >= 0; --g) span_residual<DEBUG>(c_model, Ts, Td, rs, c_model.span[g].lo, c_model.span[g].hi);
         } else {
           const int nb = c_model.nb;
           sweep_backward(c_model, Ts, Td, mu, mu_eq, 1, nb, migrate);
-          sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, 1, nb);
+          sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, 1, nb, drop_ws);
           sweep_residual<DEBUG>(c_model, Ts, Td, rs, 1, nb);
         }
         status = decide<DEBUG>(c_model, Td, status, it, fixed != 0, cy, rs, mu);
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int limit = S.list ? *S.n_list : (S.n_dev ? *S.n_dev : S.n);
   const bool MIG = S.dst != nullptr;
+  const bool drop_ws = !DEBUG && S.drop_ws && (S.list == nullptr || MIG);
   for (int tile = blockIdx.x; tile * 32 < limit; tile += gridDim.x) {
     const int k = tile * 32 + lane;
     const int s = k < limit ? (S.list ? S.list[k] : k) : -1;
@@ -225,8 +229,8 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
         if (alive)
           for (int g = 0; g < c_model.nseg; ++g)
             if (c_model.seg[g].fwarp == w && c_model.seg[g].flevel == lv) {
-              if (MD) span_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, c_model.seg[g].lo, c_model.seg[g].hi);
-              else sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, c_model.seg[g].lo, c_model.seg[g].hi);
+              if (MD) span_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, c_model.seg[g].lo, c_model.seg[g].hi, drop_ws);
+              else sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, c_model.seg[g].lo, c_model.seg[g].hi, drop_ws);
             }
         __syncthreads();
       }
@@ -738,6 +742,7 @@ struct loik_solver {
   int lane_after = -1;
   bool lane_ok = false;
   int lane_warps_req = 0;  // warps per CTA (0 = chosen from the record size)
+  bool drop_ws = true;     // the tile kernels drop the consumed backward->forward workspace from L2 instead of writing it back
   int sms = 0, smem_optin = 0, smem_sm = 0;
   int sweeps_in_solve = 0;
   std::vector<int> model_parents, model_types;  // kept for loik_set_schedule (segment re-assignment)
@@ -750,7 +755,10 @@ static inline int grid_for(int n, int block = kBlock) { return (n + block - 1) /
 // `seg`: use the segment-parallel kernel (several warps per tile) when the tree branches.  It shortens the critical
 // path of a sweep (latency) but spends 2-3.5x the warp-slot time of the one-warp-per-tile kernel per iteration, so
 // the schedule switches to it only for the late rounds, when few tiles are left and latency is all that matters.
-static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S, int iters, int fixed, int max_ctas = 0, bool seg = true) {
+static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S_in, int iters, int fixed, int max_ctas = 0, bool seg = true) {
+  StateP S = S_in;
+  S.drop_ws = (h->drop_ws && !S.keep_ws && !h->debug) ? 1 : 0;
+  if (S.drop_ws) h->ws_valid = false;  // the consumed workspace lines are dropped from L2: undefined until the next backward sweep
   int g = grid_for(h->batch);
   if (max_ctas > 0) g = std::min(g, max_ctas);
   const bool md = h->mc.nmd > 0;  // multi-DoF joints: the instantiations with the span-level dispatch
@@ -1417,7 +1425,7 @@ static int solve_scheduled(loik_solver* h, cudaStream_t st, int reset_flags, int
   const int rc = solve_scheduled_impl(h, st, reset_flags, budget);
   // the dense sweeps run in place; instances that finish in the migrating launches after them only bring their
   // workspace home with keep_ws
-  if ((budget > h->dense_sweeps || (use_lane(h) && budget > h->lane_after)) && !h->S.keep_ws) h->ws_valid = false;
+  if (!h->S.keep_ws && budget > 0 && (h->drop_ws || budget > h->dense_sweeps || (use_lane(h) && budget > h->lane_after))) h->ws_valid = false;
   return rc;
 }
 
@@ -1711,7 +1719,7 @@ int loik_get_schedule(loik_solver* h, loik_schedule* out) {
   out->dense_sweeps = h->dense_sweeps; out->repack_reps = h->sched_reps; out->repack_growth = h->sched_growth;
   out->hi_priority_after = h->hi_after; out->seg_after = h->seg_after; out->seg_warps = h->seg_warps;
   out->lane_after = h->lane_after; out->use_graph = h->use_graph ? 1 : 0;
-  out->small_after = h->small_after; out->small_grid = h->small_grid;
+  out->small_after = h->small_after; out->small_grid = h->small_grid; out->drop_workspace = h->drop_ws ? 1 : 0;
   LaneGeom G;
   const bool ok = h->lane_ok && lane_geometry(h, G);
   out->lane_warps_per_cta = h->lane_warps_req;
@@ -1727,7 +1735,7 @@ int loik_set_schedule(loik_solver* h, const loik_schedule* sc) {
   h->dense_sweeps = sc->dense_sweeps; h->sched_reps = sc->repack_reps; h->sched_growth = sc->repack_growth;
   h->hi_after = sc->hi_priority_after; h->seg_after = sc->seg_after;
   h->lane_after = sc->lane_after; h->use_graph = sc->use_graph != 0; h->lane_warps_req = sc->lane_warps_per_cta;
-  h->small_after = sc->small_after; h->small_grid = sc->small_grid;
+  h->small_after = sc->small_after; h->small_grid = sc->small_grid; h->drop_ws = sc->drop_workspace != 0;
   if (sc->seg_warps != h->seg_warps) { h->seg_warps = sc->seg_warps; assign_segments(h->mc, h->seg_warps); }
   if (h->g_exec) { cudaGraphExecDestroy(h->g_exec); h->g_exec = nullptr; }  // the cached launch graph follows the schedule
   return LOIK_OK;
