@@ -1,15 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the batched LoIK hot path on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload panda|ur10|talos] [--batch B]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload panda|ur10|talos|all] [--batch B]
   python bench.py --impl reference ...      # the CPU restatement of loik-loid-optimized on the host cores
 
-A "step" is one full batched solve (SolveInit's device part excluded, Solve() = ResetRecursion +
-ResetSolver + the ADMM loop, every instance to its own convergence / infeasibility tail / max_iter) of the
-synthetic batch BASELINE.json names; `value` = IK solves per second over all ranks with inputs resident in HBM;
-`e2e` = the same through the public API with HOST buffers (q, b in; z, iteration counts out) inside the timed
-region.  `roofline` is quoted on the ADMM-iteration kernel in fixed-iteration mode (every instance active,
-one launch per iteration): algorithmic bytes per launch = 8*(143 n + 42 nc) * batch.
+A "step" is one full batched solve (Solve() = ResetRecursion + ResetSolver + the ADMM loop, every instance to its own
+convergence / infeasibility tail / max_iter) of a synthetic batch BASELINE.json names.  The parsed headline is
+BASELINE configs[1] (Panda 7-DoF x 65 536); the default run (`--workload all`) also measures configs[2] (UR10 x 262 144)
+and configs[3] (Talos x 16 384; under torchrun this is the per-GPU shard of configs[4], Talos x 131 072 on 8 GPUs) and
+reports them as sub-records under `extra.workloads`, each with its own value / e2e / roofline / mean iterations.
+
+  value      IK solves/s over all ranks, inputs resident in HBM, steps round-robin over `pipeline_depth` solver handles
+             (own HBM state, own stream).  The depth is capped at steps // 2 so that every handle runs at least two timed
+             solves: the timed region is a steady state, not a burst of first solves.
+  e2e        the same through the public API with pinned HOST buffers (q, b in; z, iteration counts out) inside the
+             timed region.
+  roofline   the ADMM-iteration kernel in fixed-iteration mode (every instance active, one launch per iteration):
+             algorithmic bytes per launch = 8*(143 n + 42 nc) * batch / CUDA-event time.
+  extra      un-pipelined latency of one solve, the rate at pipeline depth 4, the converged-only rate, the lane-parallel
+             kernel's fixed-iteration rate, the launch schedule in use.
 
 For N > 1 (torchrun) the batch is sharded across ranks (weak scaling: per-GPU batch fixed); loop control is per
 instance on the device, and the only collective is one all-reduce of four int64 per solve: the global stopping-
@@ -18,6 +27,7 @@ criterion outcome (#converged, #infeasible, #max_iter, total iterations).
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -56,6 +66,15 @@ def peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def source_sha():
+    """Hash of the kernel sources: ties profiles/traffic.json (ncu DRAM bytes) to the build it was captured on."""
+    h = hashlib.sha256()
+    for f in ("loik_device.cuh", "loik_lane.cuh", "loik_solver.cu"):
+        with open(os.path.join(ROOT, "loik_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -103,29 +122,6 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(model, pb, params, seconds_target=12.0, lib=None):
-    """Oracle B (CPU restatement of loik-loid-optimized) on the host cores, bounded sample of the same batch."""
-    from oracle import recursion
-    cores = os.cpu_count() or 1
-    B = pb["q"].shape[0]
-    probe = min(B, 256 * cores)
-    sub = dict(pb, q=pb["q"][:probe], bis=pb["bis"][:probe])
-    t0 = time.perf_counter()
-    recursion.batch_solve(model, params, sub["q"], sub["H_ref"], sub["v_ref"], sub["ids"], sub["Ais"], sub["bis"], sub["lb"],
-                          sub["ub"], nthreads=cores, want_outputs=False, lib=lib)
-    rate = probe / max(time.perf_counter() - t0, 1e-6)
-    n = int(min(B, max(probe, rate * seconds_target)))
-    sub = dict(pb, q=pb["q"][:n], bis=pb["bis"][:n])
-    t0 = time.perf_counter()
-    out = recursion.batch_solve(model, params, sub["q"], sub["H_ref"], sub["v_ref"], sub["ids"], sub["Ais"], sub["bis"],
-                                sub["lb"], sub["ub"], nthreads=cores, want_outputs=False, lib=lib)
-    dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "IK solves/s", "cores": cores, "kind": "port",
-            "sample": f"first {n} of {B} instances of the same batch, {cores} threads, one solver per thread, "
-                      f"{out['total_iters'] / n:.2f} iterations/solve",
-            "iters_per_s": out["total_iters"] / dt}
-
-
 def native_oracle_lib():
     """Rebuild the oracle with -march=native on this host when gcc is present (fairer CPU baseline)."""
     from oracle import recursion
@@ -137,38 +133,69 @@ def native_oracle_lib():
         return recursion.load()
 
 
+def cpu_rate(model, pb, params, lib, per_pass, passes, warm):
+    """Oracle B (CPU restatement of loik-loid-optimized) on all host cores: `warm` untimed + `passes` timed passes over
+    windows of `per_pass` instances of the batch.  Returns (solves/s, iterations/s, mean iterations)."""
+    from oracle import recursion
+    cores = os.cpu_count() or 1
+    B = pb["q"].shape[0]
+    tot_t, tot_n, tot_it = 0.0, 0, 0
+    for i in range(warm + passes):
+        lo = (i * per_pass) % max(B - per_pass + 1, 1)
+        t0 = time.perf_counter()
+        out = recursion.batch_solve(model, params, pb["q"][lo:lo + per_pass], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"],
+                                    pb["bis"][lo:lo + per_pass], pb["lb"], pb["ub"], nthreads=cores, want_outputs=False, lib=lib)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            tot_t += dt; tot_n += per_pass; tot_it += out["total_iters"]
+    return tot_n / tot_t, tot_it / tot_t, tot_it / max(tot_n, 1)
+
+
+def cpu_pass_size(model, pb, params, lib, seconds_per_pass):
+    from oracle import recursion
+    cores = os.cpu_count() or 1
+    B = pb["q"].shape[0]
+    probe = min(B, 128 * cores)
+    recursion.batch_solve(model, params, pb["q"][:probe], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"][:probe],
+                          pb["lb"], pb["ub"], nthreads=cores, want_outputs=False, lib=lib)  # (first call: thread start-up, page faults)
+    t0 = time.perf_counter()
+    recursion.batch_solve(model, params, pb["q"][:probe], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"][:probe],
+                          pb["lb"], pb["ub"], nthreads=cores, want_outputs=False, lib=lib)
+    rate = probe / max(time.perf_counter() - t0, 1e-6)
+    return int(min(B, max(probe, rate * seconds_per_pass)))
+
+
+def cpu_baseline(model, pb, params, lib, seconds_target=12.0):
+    """The reported in-line CPU baseline: warmed, several passes, same protocol as `--impl reference`."""
+    cores = os.cpu_count() or 1
+    B = pb["q"].shape[0]
+    passes = 6
+    n = cpu_pass_size(model, pb, params, lib, seconds_target / (passes + 1))
+    v, its, mean_it = cpu_rate(model, pb, params, lib, n, passes, warm=1)
+    return {"value": v, "unit": "IK solves/s", "cores": cores, "kind": "port",
+            "sample": f"{passes} timed passes (1 warm-up) over windows of {n} of the {B} instances of the same batch, {cores} threads, "
+                      f"one solver per thread, {mean_it:.2f} iterations/solve",
+            "iters_per_s": its}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path (restated: the reference cannot be built offline) on the host cores."""
     if rank != 0:
         return
-    robot, batch = WORKLOADS[args.workload]
+    name = "panda" if args.workload == "all" else args.workload
+    robot, batch = WORKLOADS[name]
     batch = args.batch or batch
     model = robots.get_robot(robot)
     pb = problems.random_batch(model, batch, seed=0)
     params = problems.bench_params(len(pb["ids"]))
     lib = native_oracle_lib()
-    from oracle import recursion
     cores = os.cpu_count() or 1
-    # size one step to ~ (120 s / (steps+warmup)) of CPU work
-    probe = min(batch, 128 * cores)
-    t0 = time.perf_counter()
-    recursion.batch_solve(model, params, pb["q"][:probe], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"][:probe],
-                          pb["lb"], pb["ub"], nthreads=cores, want_outputs=False, lib=lib)
-    rate = probe / max(time.perf_counter() - t0, 1e-6)
-    per_step = int(min(batch, max(probe, rate * 120.0 / (args.steps + args.warmup))))
-    times = []
-    for i in range(args.warmup + args.steps):
-        lo = (i * per_step) % max(batch - per_step + 1, 1)
-        t0 = time.perf_counter()
-        recursion.batch_solve(model, params, pb["q"][lo:lo + per_step], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"],
-                              pb["bis"][lo:lo + per_step], pb["lb"], pb["ub"], nthreads=cores, want_outputs=False, lib=lib)
-        if i >= args.warmup:
-            times.append(time.perf_counter() - t0)
-    total = sum(times)
-    value = per_step * len(times) / total
-    sample = f"{per_step} of {batch} instances per step, {cores} threads, one solver per thread (CPU restatement of loik-loid-optimized; reference not buildable offline)"
+    per_step = cpu_pass_size(model, pb, params, lib, 120.0 / (args.steps + args.warmup))
+    value, its, mean_it = cpu_rate(model, pb, params, lib, per_step, args.steps, warm=args.warmup)
+    sample = (f"{per_step} of {batch} instances per step, {cores} threads, one solver per thread (CPU restatement of "
+              f"loik-loid-optimized; reference not buildable offline), {mean_it:.2f} iterations/solve")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "IK solves/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_step / value, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{robot} batch {batch} per GPU (BASELINE.json configs)", "robot": robot, "n_dof": model.nb,
                        "n_tasks": len(pb["ids"]), "batch_per_gpu": batch, "max_iter": params["max_iter"]},
@@ -177,50 +204,30 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=8)
-    ap.add_argument("--impl", default="loik_b200", choices=["loik_b200", "reference"])
-    ap.add_argument("--workload", default="panda", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config's)")
-    ap.add_argument("--pipeline", type=int, default=32,
-                    help="solver handles (each on its own stream) kept in flight; step i uses handle i %% depth")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-    args.warmup = max(args.warmup, 3)
-
+def run_workload(name, args, rank, world, local_rank, dev, headline):
+    """All measurements of one BASELINE workload on this rank's shard; returns the record (rank 0) or None."""
     import torch
     import torch.distributed as dist
     from loik_b200 import sharded
     from loik_b200 import solver as lk
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    robot, batch = WORKLOADS[args.workload]
+    robot, batch = WORKLOADS[name]
     batch = args.batch or batch
     model = robots.get_robot(robot)
     n, nc = model.nb, len(robots.TASK_JOINTS[robot])
     pb = problems.random_batch(model, batch, seed=0, first_index=rank * batch)  # this rank's shard of the global batch
     params = problems.bench_params(nc)
-    # each handle owns a home arena + two re-pack arenas; keep the pipeline within ~60 GB of HBM
+    steps = args.steps if headline else max(8, min(args.steps, 32))
+    warmup = args.warmup
+    # each handle owns a home arena + two re-pack arenas; keep the pipeline within ~60 GB of HBM.  Depth <= steps // 2:
+    # every handle runs at least two timed solves (steady state)
     rows_est = 48 + 61 * n + 24 * nc + 33 + 14 * n
     bytes_per_handle = 3 * ((batch + 31) // 32) * rows_est * 256
-    D = max(1, min(args.pipeline, int(60e9 // bytes_per_handle)))
+    D = max(1, min(args.pipeline, int(60e9 // bytes_per_handle), max(1, steps // 2)))
     solvers = [lk.make_solver(model, params, batch, device=local_rank) for _ in range(D)]
     drivers = [sharded.ShardedSolver(S, world) for S in solvers]
     streams = [torch.cuda.Stream(device=dev) for _ in range(D)]
+    schedule = solvers[0].get_schedule()
 
     # resident inputs (value) and pinned host inputs/outputs (e2e)
     q_d = torch.as_tensor(pb["q"], device=dev)
@@ -231,8 +238,8 @@ def main():
     it_h = [torch.empty(batch, dtype=torch.int32).pin_memory() for _ in range(D)]
     prob = (pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"])
 
-    def step_resident(i):
-        k = i % D
+    def step_resident(i, depth=D):
+        k = i % depth
         with torch.cuda.stream(streams[k]):
             drivers[k].solve()
 
@@ -252,14 +259,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, nsteps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         cur = torch.cuda.current_stream()
         e0.record(cur)
         for st in streams:
             st.wait_event(e0)
-        for i in range(steps):
+        for i in range(nsteps):
             fn(i)
         for st in streams:
             done = torch.cuda.Event()
@@ -272,85 +279,168 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()  # clocks / throttle reasons are sampled from the warm-up to the end of the last timed region
     for S in solvers:
         S.SolveInit(q_d, prob[0], prob[1], prob[2], prob[3], b_d, pb["lb"], pb["ub"])
-    for i in range(max(args.warmup, D)):  # every handle allocates its re-pack arenas and captures its graph once
+    for i in range(max(warmup, 2 * D)):  # every handle allocates its re-pack arenas and captures its graph, then runs warm once
         step_resident(i)
     barrier()
     launches0 = sum(S.launch_count() for S in solvers)
-    ms_total = timed(step_resident, args.steps)
+    ms_total = timed(step_resident, steps)
     launches = sum(S.launch_count() for S in solvers) - launches0
     stats = solvers[0].stats()
     mean_iters = stats["total_iters"] / batch
-    # latency of one un-pipelined solve (one handle, one stream)
-    ms_single = timed(lambda i: step_resident(0), 3) / 3
+    # latency of one un-pipelined solve (one handle, one stream), and the rate with 4 handles in flight
+    ms_single = timed(lambda i: step_resident(0, 1), 3) / 3
+    d4 = min(4, D)
+    n4 = max(8, 2 * d4)
+    for i in range(d4):
+        step_resident(i, d4)
+    ms_d4 = timed(lambda i: step_resident(i, d4), n4)
 
     # fixed-iteration mode: the roofline kernel (one launch = one ADMM iteration of the whole batch, all active)
     S0 = solvers[0]
-    S0.IterateFixed(3)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    S0.IterateFixed(FIXED_ITERS)
-    e1.record()
-    barrier()
-    ms_fixed = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms_fixed, op=dist.ReduceOp.MAX)
-    ms_iter = float(ms_fixed.item()) / FIXED_ITERS
+    saved_lane_after = schedule["lane_after"]
+
+    def fixed_us(lane_after, iters):
+        S0.set_schedule(lane_after=lane_after)
+        S0.IterateFixed(3)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        S0.IterateFixed(iters)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) * 1e3 / iters
+
+    us_iter = fixed_us(-1, FIXED_ITERS)                     # k_iterate, one launch per iteration
+    us_lane = fixed_us(0, 20) if schedule["lane_available"] else None  # k_iterate_lane, 20 iterations per instance in one launch
+    S0.set_schedule(lane_after=saved_lane_after)
 
     # e2e
     for i in range(max(2, D)):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, steps)
 
+    rec = None
     if rank == 0:
         hbm, how = peaks()
         bpi = algorithmic_bytes_per_instance_iteration(n, nc)
-        achieved = bpi * batch / (ms_iter * 1e-3) / 1e9
-        value = world * batch * args.steps / (ms_total * 1e-3)
-        e2e_v = world * batch * args.steps / (ms_e2e * 1e-3)
-        line = {
-            "metric": METRIC, "value": value, "unit": "IK solves/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        achieved = bpi * batch / (us_iter * 1e-6) / 1e9
+        value = world * batch * steps / (ms_total * 1e-3)
+        e2e_v = world * batch * steps / (ms_e2e * 1e-3)
+        rec = {
+            "value": value, "unit": "IK solves/s", "steps": steps, "ms_per_step": ms_total / steps,
             "config": {"workload": f"{robot} batch {batch} per GPU (BASELINE.json configs)", "robot": robot, "n_dof": n,
                        "n_tasks": nc, "batch_per_gpu": batch, "global_batch": world * batch, "max_iter": params["max_iter"],
                        "l2": "inputs larger than L2: per-iteration working set %.0f MB" % (bpi * batch / 2 ** 20),
                        "parallelism": f"batch-sharded x{world}", "pipeline_depth": D,
                        "pipeline": "step i runs on solver handle i % depth (own HBM state, own stream): the latency-bound "
-                                   "tail of one batch overlaps the bulk of the next",
+                                   "tail of one batch overlaps the bulk of the next; depth <= steps // 2 (steady state)",
                        "mean_iters_per_solve": mean_iters},
-            "ms_per_solve_unpipelined": ms_single,
-            "iters_per_s": world * batch / (ms_iter * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": None, "peak_source": how,
                          "kernel": "k_iterate (1 ADMM iteration / launch, all instances active)",
-                         "algorithmic_bytes_per_launch": bpi * batch, "us_per_launch": ms_iter * 1e3,
+                         "algorithmic_bytes_per_launch": bpi * batch, "us_per_launch": us_iter,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_v, "unit": "IK solves/s", "h2d_bytes_per_step": int(q_h.numel() * 8 + b_h.numel() * 8),
-                    "d2h_bytes_per_step": int(z_h[0].numel() * 8 + it_h[0].numel() * 4), "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks,
-            "solve_stats": {k: int(v) for k, v in stats.items()},
+                    "d2h_bytes_per_step": int(z_h[0].numel() * 8 + it_h[0].numel() * 4), "ms_per_step": ms_e2e / steps},
+            "gpu_launches": int(launches),
+            "extra": {
+                "ms_per_solve_unpipelined": ms_single,
+                "value_pipeline_4": world * batch * n4 / (ms_d4 * 1e-3),
+                "converged_only_solves_per_s": value * stats["converged"] / batch,
+                "iters_per_s": world * batch / (us_iter * 1e-6),
+                "instance_iterations_per_s_whole_solves": value * mean_iters,
+                "lane_kernel": None if us_lane is None else {
+                    "kernel": "k_iterate_lane (8 lanes per instance, state resident in shared memory, 20 iterations per launch)",
+                    "us_per_batch_iteration": us_lane, "iters_per_s": world * batch / (us_lane * 1e-6),
+                    "algorithmic_frac_of_hbm": bpi * batch / (us_lane * 1e-6) / 1e9 / hbm},
+                "schedule": schedule,
+                "solve_stats": {k: int(v) for k, v in stats.items()},
+            },
         }
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):
             try:
                 with open(traffic_file) as f:
-                    line["roofline"]["traffic"] = json.load(f).get(robot)
+                    tj = json.load(f)
+                rec["roofline"]["traffic"] = tj.get(robot)
+                rec["roofline"]["traffic_source"] = ("ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one k_iterate launch, "
+                                                     "scripts/roundend_gpu.sh -> profiles/traffic.json; captured on kernel sources "
+                                                     f"{tj.get('source_sha')}, this build {source_sha()}")
             except Exception:
                 pass
+    for S in solvers:
+        S.close()
+    del solvers, drivers, q_d, b_d, q_h, b_h, z_h, it_h
+    torch.cuda.empty_cache()
+    return rec, (model, pb, params)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="loik_b200", choices=["loik_b200", "reference"])
+    ap.add_argument("--workload", default="all", choices=sorted(WORKLOADS) + ["all"],
+                    help="all (default): Panda is the headline line, UR10 and Talos are reported under extra.workloads")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config's)")
+    ap.add_argument("--pipeline", type=int, default=32,
+                    help="solver handles (each on its own stream) kept in flight; step i uses handle i %% depth")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    head_name = "panda" if args.workload == "all" else args.workload
+    others = ["ur10", "talos"] if args.workload == "all" else []
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # clocks / throttle reasons are sampled from the warm-up to the end of the last timed region
+    head, (model, pb, params) = run_workload(head_name, args, rank, world, local_rank, dev, headline=True)
+    subs = {}
+    for nm in others:
+        rec, _ = run_workload(nm, args, rank, world, local_rank, dev, headline=False)
+        if rank == 0:
+            subs[nm] = rec
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": head["value"], "unit": "IK solves/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": head["config"],
+            "ms_per_solve_unpipelined": head["extra"]["ms_per_solve_unpipelined"],
+            "iters_per_s": head["extra"]["iters_per_s"],
+            "roofline": head["roofline"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": clocks,
+            "solve_stats": head["extra"]["solve_stats"],
+            "extra": dict(head["extra"], workloads=subs),
+        }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(model, pb, params, lib=native_oracle_lib())
+            line["cpu_baseline"] = cpu_baseline(model, pb, params, native_oracle_lib())
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))
-    for S in solvers:
-        S.close()
     if world > 1:
         dist.destroy_process_group()
 

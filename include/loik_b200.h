@@ -257,6 +257,9 @@ LOIK_API int loik_iterate_fixed(loik_solver* h, int32_t iters, int32_t reset, vo
 LOIK_API int loik_fwd_pass_init(loik_solver* h, const double* q, int32_t loc, void* stream);
 /* ik_id_data_.ResetRecursion() + ResetSolver(): what Solve() does before its loop (hpp:370-374). */
 LOIK_API int loik_reset_recursion(loik_solver* h, void* stream);
+/* ResetSolver() alone (hpp:168-186): iteration counter, convergence / infeasibility flags, mu and the feasibility
+ * scalars of every instance; the primal and dual state (nu, z, w, vis, fis, yis, Aty ...) is kept. */
+LOIK_API int loik_reset_solver(loik_solver* h, void* stream);
 /* One step of the current iteration on every instance (the fused ones: on every still-active instance). */
 LOIK_API int loik_step(loik_solver* h, int32_t step_id, void* stream);
 /* Keep the reference's running norms, feasibility scalars and residual vectors readable (slower). */
@@ -310,7 +313,6 @@ LOIK_API int loik_active_count_device_ptr(loik_solver* h, void** dev_ptr);
  * the multi-GPU driver, which interleaves chunks with the stop-criterion all-reduce. */
 LOIK_API int loik_solve_begin(loik_solver* h, void* stream);
 LOIK_API int loik_solve_chunk(loik_solver* h, int32_t iters, void* stream);
-LOIK_API int loik_solve_end(loik_solver* h, void* stream);
 
 LOIK_API int32_t loik_abi_version(void);
 

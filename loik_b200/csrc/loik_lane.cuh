@@ -40,7 +40,7 @@ enum : int { LT_Y = TR_Y, LT_ATY = TR_ATY, LT_B = TR_B, LT_ATB = TR_ATB, LT_ROWS
 enum : int { LP_HP = 0, LP_F = 48, LP_ROWS = 56 };       // pending block of a tree edge: [H | p] contribution, F contribution
 enum : int { LX_V = 0, LX_T = 16, LX_ROWS = 96 };        // exchange scratch: 16 scalars, 8 rows of 10 (transposes)
 // ---- per-CTA constants in shared memory ---------------------------------------------------------------------------
-enum : int { CJ_HREF = 0, CJ_HV = 48, CJ_ROWS = 56 };    // per joint: [Href | -Hv] as 6 rows of 8, Hv (8)
+enum : int { CJ_HREFR = 0, CJ_HREF = 48, CJ_HV = 96, CJ_ROWS = 104 };  // per joint: [Href + rho I | -Hv] and Href as 6 rows of 8, Hv (8)
 enum : int { CT_AR = 0, CT_ATR = 48, CT_ATA = 96, CT_ROWS = 144 };  // per task: A, A^T, A^T A as 6 rows of 8
 
 struct LaneDims {
@@ -89,7 +89,7 @@ LOIK_DEV void sts6(double* p, const double (&v)[6]) {
 LOIK_DEV double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 
 // per-lane partial maxima of the norms whose terms are produced one component per lane
-struct LanePart { double dfis, dyis, Av, ptask, dF, Finf, Hrefv, dresv; };
+struct LanePart { double dfis, dyis, Av, ptask, dF, Finf, Hrefv, dresv, dvis; };
 
 // ---------------------------------------------------------------------------------------------
 // state in / results out (8 lanes of one group, uncoalesced 8 B accesses: once per solve and instance)
@@ -139,10 +139,10 @@ LOIK_DEV void lane_retire(const ModelC& M, const LaneDims& D, const double* I, d
   }
 }
 // opt-in: His (21 packed scalars), pis, UDinv, Dinv, r of the last backward pass
-LOIK_DEV_CALL void lane_retire_workspace(const ModelC& M, const LaneDims& D, const double* I, double* Th, const int l) {
+LOIK_DEV_CALL void lane_retire_workspace(const ModelC& M, const int joint0, const double* I, double* Th, const int l) {
   const Offs& O = M.off;
   for (int j = l; j < M.nb; j += 8) {
-    const double* Pj = I + D.joint0 + LJ_ROWS * j;
+    const double* Pj = I + joint0 + LJ_ROWS * j;
     double* Pd = Th + (size_t)(O.joint0 + JR_ROWS * j) * 32;
     for (int a = 0; a < 3; ++a)
       for (int b = 0; b < 3; ++b) {
@@ -166,7 +166,7 @@ LOIK_DEV void lds_xf(const double* p, double (&R)[9], double (&t)[3]) {  // liMi
 // Lane c < 6 holds column c of H, lanes 6 and 7 (a duplicate) hold p.
 // ---------------------------------------------------------------------------------------------
 LOIK_DEV void lane_backward(const ModelC& M, const LaneDims& D, const double* CB, double* I, const int l, const double mu,
-                            const double mu_eq, const double (&rhod)[6]) {
+                            const double mu_eq) {
   const double rho = M.rho;
   const int lc = l < 6 ? l : 6;
   const bool isp = l >= 6;
@@ -189,7 +189,7 @@ LOIK_DEV void lane_backward(const ModelC& M, const LaneDims& D, const double* CB
     const double w_i = Pj[LJ_W], z_i = Pj[LJ_Z];
     // FwdPass1: H_i = rho I + Href_i (:304-306); p_i = -rho v_prev_i - Hv_i (:310-313)
 #pragma unroll
-    for (int r = 0; r < 6; ++r) col[r] = fma(facv, vold[r], Cj[CJ_HREF + 8 * r]) + rhod[r];
+    for (int r = 0; r < 6; ++r) col[r] = fma(facv, vold[r], Cj[CJ_HREFR + 8 * r]);
     if (J.task >= 0) {  // H_c += mu_eq AtA; p_c += Aty - mu_eq Atb (:327-330)
       const double* Ck = CB + D.ctask0 + CT_ROWS * J.task;
       const double* Pk = I + D.task0 + LT_ROWS * J.task;
@@ -273,6 +273,13 @@ LOIK_DEV void lane_backward(const ModelC& M, const LaneDims& D, const double* CB
   }
 }
 
+// select x[l] for a (lane-dependent or uniform) l in 0..5 (two levels of selects)
+LOIK_DEV double pick6(const double (&x)[6], const int l) {
+  const bool odd = l & 1;
+  const double a = odd ? x[1] : x[0], b = odd ? x[3] : x[2], c = odd ? x[5] : x[4];
+  return l < 2 ? a : (l < 4 ? b : c);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Forward sweep: FwdPass2OptimizedVisitor (hxx:361-377) + BoxProj (:384-397) + DualUpdate (:404-461) +
 // ComputePrimalResiduals (:494-503); cf. sweep_forward.  The 6-vectors are computed by every lane (they are the
@@ -289,14 +296,14 @@ LOIK_DEV void lane_forward(const ModelC& M, const LaneDims& D, const double* CB,
     const JointC& J = M.j[i];
     Pj += LJ_ROWS;
     __syncwarp();
-    double UD[6], vold[6], R[9], t[3];
+    double UD[6], R[9], t[3];
+    const double vold_l = Pj[LJ_V + lc];
     const double2 dr = lds2(Pj + LJ_DINV);  // (Dinv, r)
     const double2 nz = lds2(Pj + LJ_NU);    // (nu, z) of the previous iterate
     const double w_old = Pj[LJ_W];
     double lb = J.lb, ub = J.ub;
     if (M.bounds_per_instance) { const double2 b2 = lds2(Pj + LJ_LB); lb = b2.x; ub = b2.y; }
     lds6(Pj + LJ_UD, UD);
-    lds6(Pj + LJ_V, vold);
     lds_xf(Pj + LJ_XF, R, t);
     if (J.parent != i - 1) {  // not the joint just swept: the universe (v = 0) or a joint swept earlier (its new v)
       if (J.parent == 0) {
@@ -324,12 +331,6 @@ LOIK_DEV void lane_forward(const ModelC& M, const LaneDims& D, const double* CB,
     const double nu = -acc - dr.x * dr.y;  // nu_i = -UDinv^T vp - Dinv r_i (:127)
     cy.nu_inf = amax(cy.nu_inf, nu);       // (:129-131)
     S_axpy(J, nu, v);                      // v_i = vp + S nu_i (:133-134)
-    {
-      double dv[6];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) dv[c] = v[c] - vold[c];
-      cy.dvis_inf = amax6(cy.dvis_inf, dv);  // (:156-158)
-    }
     cy.dnu_inf = amax(cy.dnu_inf, nu - nz.x);  // (:375)
     const double z = dmin(ub, dmax(lb, nu + inv_mu * w_old));  // BoxProj (:388)
     cy.dz_inf = amax(cy.dz_inf, z - nz.y);
@@ -344,6 +345,8 @@ LOIK_DEV void lane_forward(const ModelC& M, const LaneDims& D, const double* CB,
     __syncwarp();  // every lane has read this joint's previous iterate
     if (l == 0) sts6(Pj + LJ_V, v);
     Pj[LJ_F + lc] = f_l;
+    __syncwarp();
+    pt.dvis = amax(pt.dvis, Pj[LJ_V + lc] - vold_l);  // delta_vis_inf_norm (:156-158), one component per lane
     *reinterpret_cast<double2*>(Pj + LJ_NU) = make_double2(nu, z);
     Pj[LJ_W] = w_old + dw;
     if (J.task >= 0) {  // DualUpdate for the task on this joint (:410-451)
@@ -379,13 +382,6 @@ LOIK_DEV void lane_forward(const ModelC& M, const LaneDims& D, const double* CB,
       Pk[LT_ATY + lc] = aty;
     }
   }
-}
-
-// select x[l] for a lane-dependent l in 0..5 (two levels of selects)
-LOIK_DEV double pick6(const double (&x)[6], const int l) {
-  const bool odd = l & 1;
-  const double a = odd ? x[1] : x[0], b = odd ? x[3] : x[2], c = odd ? x[5] : x[4];
-  return l < 2 ? a : (l < 4 ? b : c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -457,12 +453,12 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
     if (e < D.ctask0) {
       const int j = e / CJ_ROWS, o = e - CJ_ROWS * j;
       const JointC& J = M.j[j + 1];
-      if (o < 48) {
-        const int r = o >> 3, c = o & 7;
-        if (c < 6) x = Hel(J.HrA, J.HrB, J.HrD, r, c);
-        else if (c == 6) x = -J.Hv[r];
-      } else if (o - 48 < 6) {
-        x = J.Hv[o - 48];
+      if (o < CJ_HV) {
+        const int r = (o % 48) >> 3, c = o & 7;
+        if (c < 6) x = Hel(J.HrA, J.HrB, J.HrD, r, c) + ((o < CJ_HREF && r == c) ? M.rho : 0.0);  // H_i = rho I + Href_i (:304-306)
+        else if (c == 6 && o < CJ_HREF) x = -J.Hv[r];
+      } else if (o - CJ_HV < 6) {
+        x = J.Hv[o - CJ_HV];
       }
     } else {
       const int k = (e - D.ctask0) / CT_ROWS, o = (e - D.ctask0) - CT_ROWS * k;
@@ -478,9 +474,6 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
   double* X = I + D.xch;
   const unsigned gmask = 0xffu << (8 * g);
   const int limit = P.list ? *P.n_list : P.n;
-  double rhod[6];
-#pragma unroll
-  for (int r = 0; r < 6; ++r) rhod[r] = (r == l) ? M.rho : 0.0;
   int home_slot = -1;  // >= 0: this group holds an instance
   int status = ST_CONVERGED, it = 0, left = 0;
   double mu = 1.0;
@@ -522,10 +515,10 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
     const double mu_eq = M.mu_scale * mu;
     Carry cy;
     Resid rs;
-    LanePart pt = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    LanePart pt = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     zero(cy);
     zero(rs);
-    lane_backward(M, D, CB, I, l, mu, mu_eq, rhod);
+    lane_backward(M, D, CB, I, l, mu, mu_eq);
     lane_forward(M, D, CB, I, l, mu, mu_eq, cy, pt);
     lane_residual(M, D, CB, I, l, rs, pt);
     {  // combine the per-lane partial maxima: rows = lanes, then one column per lane
@@ -536,10 +529,13 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
       *reinterpret_cast<double2*>(row + 2) = make_double2(pt.Av, pt.ptask);
       *reinterpret_cast<double2*>(row + 4) = make_double2(pt.dF, pt.Finf);
       *reinterpret_cast<double2*>(row + 6) = make_double2(pt.Hrefv, pt.dresv);
+      row[8] = pt.dvis;
       __syncwarp();
       const double a0 = XT[l], a1 = XT[10 + l], a2 = XT[20 + l], a3 = XT[30 + l], a4 = XT[40 + l], a5 = XT[50 + l];
       X[LX_V + 8 + l] = dmax(dmax(dmax(a0, a1), dmax(a2, a3)), dmax(a4, a5));
+      if (l == 0) X[LX_V + 7] = dmax(dmax(dmax(XT[8], XT[18]), dmax(XT[28], XT[38])), dmax(XT[48], XT[58]));
       __syncwarp();
+      cy.dvis_inf = X[LX_V + 7];
       const double2 t0 = lds2(X + LX_V + 8), t1 = lds2(X + LX_V + 10), t2 = lds2(X + LX_V + 12), t3 = lds2(X + LX_V + 14);
       cy.dfis_inf = t0.x; cy.dyis_inf = t0.y; cy.Av_inf = t1.x; cy.pres_task = t1.y;
       rs.dF_inf = t2.x; rs.F_inf = t2.y; rs.Hrefv_inf = t3.x; rs.dres_v = t3.y;
@@ -558,7 +554,7 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
         __syncwarp(gmask);
         double* Th = P.home + ((size_t)(home_slot >> 5) * M.off.rows) * 32 + (home_slot & 31);
         lane_retire(M, D, I, Th, l);
-        if (P.keep_ws) lane_retire_workspace(M, D, I, Th, l);
+        if (P.keep_ws) lane_retire_workspace(M, D.joint0, I, Th, l);
         home_slot = -1;
       }
     }

@@ -1139,6 +1139,10 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
     LaneGeom G;
     h->lane_ok = M.nmd == 0 && lane_geometry(h, G);
     if (h->lane_ok) CKA(cudaFuncSetAttribute(k_iterate_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    // default switch point: short trees hand the instances still active after 10 sweeps to the lane-parallel kernel (one
+    // Panda-65 536 solve 5.6 -> 2.2 ms at -5 % pipelined throughput); long / branching trees keep the tile kernels (their
+    // record leaves room for 8 instances per SM only) unless the caller asks (loik_set_schedule)
+    h->lane_after = (h->lane_ok && nb <= 12) ? 10 : -1;
   }
 #undef CKA
   *out = h;
@@ -1453,6 +1457,18 @@ int loik_reset_recursion(loik_solver* h, void* stream) {
   return launch_reset(h, RST_WZ | RST_VFF | RST_YATY | RST_SOLVER, (cudaStream_t)stream);
 }
 
+// ResetSolver() alone (hpp:168-186): iter_, the convergence / infeasibility flags, mu (-> mu_eq, mu_ineq) and the
+// feasibility scalars; the primal and dual state is left as it is (a warm start keeps it).
+int loik_reset_solver(loik_solver* h, void* stream) {
+  if (!h) return fail(LOIK_ERR_INVALID, "null handle");
+  if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_reset_solver: call loik_solve_init first");
+  CK(cudaSetDevice(h->device));
+  const bool ws = h->ws_valid;
+  const int rc = launch_reset(h, RST_SOLVER, (cudaStream_t)stream);
+  h->ws_valid = ws;  // (nothing of the workspace is touched)
+  return rc;
+}
+
 static int check_strategy(loik_solver* h) {
   if (h->prm.mu_update_strat != LOIK_MU_DEFAULT)
     return fail(LOIK_ERR_UNSUPPORTED, "[FirstOrderLoikOptimizedTpl::UpdateMu]: mu update strategy not yet implemented");
@@ -1560,6 +1576,8 @@ int loik_solve_begin(loik_solver* h, void* stream) {
 }
 int loik_solve_chunk(loik_solver* h, int32_t iters, void* stream) {
   if (!h) return fail(LOIK_ERR_INVALID, "null handle");
+  if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_solve_chunk: call loik_solve_init and loik_solve_begin first");
+  if (iters < 1) return fail(LOIK_ERR_INVALID, "loik_solve_chunk: iters must be >= 1");
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
   int rc = LOIK_OK;
@@ -1578,7 +1596,6 @@ int loik_solve_chunk(loik_solver* h, int32_t iters, void* stream) {
   CK(cudaGetLastError());
   return LOIK_OK;
 }
-int loik_solve_end(loik_solver* h, void* stream) { (void)h; (void)stream; return LOIK_OK; }
 int loik_active_count_device_ptr(loik_solver* h, void** dev_ptr) {
   if (!h || !dev_ptr) return fail(LOIK_ERR_INVALID, "null argument");
   *dev_ptr = h->d_counts + 2;

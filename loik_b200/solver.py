@@ -45,7 +45,7 @@ EXPORTS = ["loik_abi_version", "loik_last_error", "loik_create", "loik_destroy",
            "loik_set_max_iter", "loik_set_rho", "loik_set_mu", "loik_set_mu_equality_scale_factor", "loik_set_tol_abs",
            "loik_set_tol_rel", "loik_set_tol_primal_inf", "loik_set_tol_dual_inf", "loik_set_tol_tail_solve",
            "loik_set_warm_start", "loik_get_params", "loik_get_schedule", "loik_set_schedule",
-           "loik_active_count_device_ptr", "loik_solve_begin", "loik_solve_chunk", "loik_solve_end"]
+           "loik_active_count_device_ptr", "loik_solve_begin", "loik_solve_chunk", "loik_reset_solver"]
 
 
 class _ModelDesc(C.Structure):
@@ -120,7 +120,7 @@ def load_library(path: str | None = None):
     lib.loik_active_count_device_ptr.argtypes = [vp, C.POINTER(vp)]
     lib.loik_solve_begin.argtypes = [vp, vp]
     lib.loik_solve_chunk.argtypes = [vp, i32, vp]
-    lib.loik_solve_end.argtypes = [vp, vp]
+    lib.loik_reset_solver.argtypes = [vp, vp]
     if path is None:
         _lib = lib
     return lib
@@ -138,6 +138,13 @@ def _current_stream() -> int:
     except Exception:
         pass
     return 0
+
+
+class _DevArray:
+    """Zero-copy view of a device buffer owned by the library."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 class _Buf:
@@ -313,6 +320,11 @@ class FirstOrderLoikOptimized:
             raise RuntimeError("[IkProblemFormulation::UpdateReferences]: input arguments 'H_refs', 'v_refs' have wrong size!!")
         self._check(self._lib.loik_update_references(self._h, Hb.ptr, vb.ptr, _current_stream()))
 
+    def ResetSolver(self):
+        """ResetSolver() (loik-loid-optimized.hpp:168-186): iteration counter, flags, mu and the feasibility scalars only --
+        the primal / dual state (nu, z, w, vis, fis, yis ...) is kept."""
+        self._check(self._lib.loik_reset_solver(self._h, _current_stream()))
+
     # ---- fused steps (parity tests) -------------------------------------------------------------
     def ResetRecursion(self):
         self._check(self._lib.loik_reset_recursion(self._h, _current_stream()))
@@ -479,6 +491,16 @@ class FirstOrderLoikOptimized:
             out = np.empty(shape, dtype)
             self._check(self._lib.loik_get(self._h, field, out.ctypes.data, LOIK_HOST, _current_stream()))
             return out
+        # an output buffer is written in place: it must already have the right dtype, shape and layout (a converted
+        # copy would silently receive the data instead of `out`)
+        if _is_torch(out):
+            import torch
+            want = torch.int32 if dtype == np.int32 else torch.float64
+            if out.dtype != want or not out.is_contiguous() or tuple(out.shape) != shape:
+                raise RuntimeError(f"get(out=): need a contiguous {want} tensor of shape {shape}")
+        else:
+            if not isinstance(out, np.ndarray) or out.dtype != dtype or not out.flags.c_contiguous or out.shape != shape:
+                raise RuntimeError(f"get(out=): need a C-contiguous {np.dtype(dtype).name} array of shape {shape}")
         b = _Buf(out, dtype)
         self._check(self._lib.loik_get(self._h, field, b.ptr, b.loc, _current_stream()))
         return out
@@ -550,6 +572,17 @@ class FirstOrderLoikOptimized:
         p = C.c_void_p()
         self._check(self._lib.loik_reduce_stats(self._h, _current_stream(), C.byref(p)))
         return int(p.value)
+
+    def stats_tensor(self):
+        """Device tensor (4 int64: #converged, #primal infeasible, #max_iter, sum of iterations) of the last solve: the
+        reduction is enqueued on the current stream; a zero-copy view of a library buffer, valid until the next call."""
+        import torch
+        return torch.as_tensor(_DevArray(self.reduce_stats_ptr(), 4, "<i8"), device=f"cuda:{self.device}")
+
+    def active_tensor(self):
+        """Device tensor (1 int32): instances still active after the last SolveChunk (zero-copy view, see stats_tensor)."""
+        import torch
+        return torch.as_tensor(_DevArray(self.active_count_ptr(), 1, "<i4"), device=f"cuda:{self.device}")
 
     def launch_count(self) -> int:
         return int(self._lib.loik_launch_count(self._h))

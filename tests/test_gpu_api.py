@@ -1,0 +1,174 @@
+"""ABI surface beyond the solves: base-class setters / getters between solves (the cached launch graph must follow),
+ResetSolver() vs ResetRecursion(), the chunked global-stop path of the sharded driver, launch-schedule knobs.  -m gpu."""
+import numpy as np
+import pytest
+
+from loik_b200 import problems, robots, sharded
+from tests.helpers import ctor_kwargs, instance, rel_inf
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu(model, params, batch):
+    from loik_b200 import solver
+    return solver.make_solver(model, params, batch)
+
+
+def _solve_init(G, pb):
+    G.SolveInit(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
+
+
+def _oracle_batch(model, params, pb, **kw):
+    from oracle import recursion
+    return recursion.batch_solve(model, params, pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"],
+                                 pb["lb"], pb["ub"], nthreads=8, **kw)
+
+
+def _check(G, model, params, pb, what):
+    ref = _oracle_batch(model, params, pb)
+    it, mu, st = G.get_iter(), G.get_mu(), G.get_status()
+    same = (it == ref["iters"]) & (mu == ref["mu"]) & ((st & 3) == (ref["status"] & 3))
+    assert same.mean() >= 0.998, f"{what}: {int((~same).sum())} diverged decision traces"
+    assert rel_inf(G.z[same], ref["z"][same]) < 1e-6, what
+
+
+@pytest.mark.parametrize("lane_after", [-1, 0])
+def test_setters_between_solves_follow_into_the_cached_graph(lane_after):
+    """task-solver-base.hpp:105-141: every setter changes the NEXT solve (the launch graph is re-captured when the
+    parameter block changes) and agrees with an oracle constructed with the new value."""
+    import torch
+    model = robots.panda()
+    B = 512
+    pb = problems.random_batch(model, B, seed=31)
+    params = problems.bench_params(1)
+    G = _gpu(model, params, B)
+    G.set_schedule(lane_after=lane_after)
+    _solve_init(G, pb)
+    stream = torch.cuda.Stream()  # a capturable stream: the graph path
+    changes = [("tol_abs", 1e-5), ("tol_rel", 1e-5), ("tol_primal_inf", 1e-3), ("rho", 1e-4), ("mu", 1e-1),
+               ("mu_equality_scale_factor", 1e3), ("tol_tail_solve", 1e-3), ("max_iter", 60), ("tol_dual_inf", 1e-3)]
+    with torch.cuda.stream(stream):
+        G.Solve()
+        stream.synchronize()
+        _check(G, model, params, pb, "initial")
+        for name, val in changes:
+            getattr(G, "set_" + name)(val)
+            params = dict(params, **{name: val})
+            assert G.get_params()[name] == val
+            G.Solve()
+            stream.synchronize()
+            _check(G, model, params, pb, f"after set_{name}({val})")
+    assert G.get_rho() == 1e-4 and G.get_max_iter() == 60 and G.get_tol_primal_inf() == 1e-3 and G.get_tol_dual_inf() == 1e-3
+    G.close()
+
+
+def test_reset_solver_keeps_the_state_reset_recursion_clears_it():
+    """ResetSolver() (hpp:168-186) resets iter / flags / mu only; ResetRecursion() (data hxx:138-154) zeroes w, z, vis, fis,
+    yis, Aty as well.  The oracle's two methods are the reference."""
+    from oracle import recursion
+    model = robots.ur10()
+    B = 32
+    pb = problems.random_batch(model, B, seed=12)
+    params = problems.bench_params(1)
+    G = _gpu(model, params, B)
+    _solve_init(G, pb)
+    G.Solve()
+    z1, w1, v1, y1, mu1 = G.z, G.w, G.vis, G.yis, G.get_mu()
+    assert np.abs(z1).max() > 0 and (G.get_iter() > 0).all()
+    G.ResetSolver()
+    np.testing.assert_array_equal(G.z, z1)
+    np.testing.assert_array_equal(G.w, w1)
+    np.testing.assert_array_equal(G.vis, v1)
+    np.testing.assert_array_equal(G.yis, y1)
+    assert (G.get_iter() == 0).all() and (G.get_mu() == params["mu"]).all() and (G.get_status() == 0).all()
+    # stepping on from the kept state == the oracle after Solve(); ResetSolver(); one iteration
+    G.StepBackward(); G.StepForward(); G.StepResidual()
+    for i in range(B):
+        o = recursion.FirstOrderLoikOptimized(model, **ctor_kwargs(params))
+        o.SolveInit(*instance(pb, i))
+        o.Solve()
+        o.ResetSolver()
+        o.UpdatePrev(); o.ResetInfNorms(); o.FwdPass1(); o.BwdPassOptimizedVisitor()
+        o.FwdPass2OptimizedVisitor(); o.BoxProj(); o.DualUpdate()
+        assert rel_inf(G.z[i], o.z) < 1e-9 and rel_inf(G.nu[i], o.nu) < 1e-9 and rel_inf(G.w[i], o.w) < 1e-9
+    G.ResetRecursion()
+    assert np.abs(G.z).max() == 0 and np.abs(G.w).max() == 0 and np.abs(G.vis).max() == 0 and np.abs(G.yis).max() == 0
+    G.close()
+
+
+@pytest.mark.parametrize("name,B", [("panda", 2048), ("talos", 256)])
+def test_chunked_global_stop_path_matches_solve(name, B):
+    """ShardedSolver.solve_chunked (world 1): chunks of sweeps + the active-count read-back until nothing is active ==
+    Solve(), instance by instance, and stops before max_iter when everything has finished."""
+    model = robots.get_robot(name)
+    pb = problems.random_batch(model, B, seed=14)
+    params = problems.bench_params(len(pb["ids"]))
+    G = _gpu(model, params, B)
+    G.set_schedule(lane_after=-1)
+    _solve_init(G, pb)
+    G.Solve()
+    z, it, mu, st = G.z, G.get_iter(), G.get_mu(), G.get_status()
+    drv = sharded.ShardedSolver(G, 1, chunk=8)
+    sweeps = drv.solve_chunked()
+    np.testing.assert_array_equal(G.get_iter(), it)
+    np.testing.assert_array_equal(G.get_mu(), mu)
+    np.testing.assert_array_equal(G.get_status(), st)
+    np.testing.assert_array_equal(G.z, z)
+    assert sweeps >= it.max() and sweeps - it.max() < 8 and sweeps % 8 == 0 or sweeps == params["max_iter"]
+    tot = drv.solve()
+    assert int(tot[3].item()) == int(it.sum()) and int(tot[0].item()) == int((st & 1).sum())
+    G.close()
+
+
+def test_solve_chunk_needs_a_problem():
+    model = robots.panda()
+    G = _gpu(model, problems.bench_params(1), 8)
+    with pytest.raises(RuntimeError, match="loik_solve_init"):
+        G.SolveChunk(4)
+    G.close()
+
+
+def test_get_into_a_wrong_buffer_raises():
+    """get(out=...) writes in place: a buffer of the wrong dtype / shape / layout is an error, not a silent copy."""
+    import torch
+    from loik_b200 import solver as lk
+    model = robots.panda()
+    B = 16
+    pb = problems.random_batch(model, B, seed=1)
+    G = _gpu(model, problems.bench_params(1), B)
+    _solve_init(G, pb)
+    G.Solve()
+    good = torch.empty(B, model.nv, dtype=torch.float64, device="cuda")
+    G.get(lk.F_Z, out=good)
+    np.testing.assert_array_equal(good.cpu().numpy(), G.z)
+    for bad in (torch.empty(B, model.nv, dtype=torch.float32, device="cuda"), torch.empty(model.nv, B, dtype=torch.float64, device="cuda").t(),
+                torch.empty(B, model.nv + 1, dtype=torch.float64, device="cuda"), np.empty((B, model.nv), np.float32)):
+        with pytest.raises(RuntimeError, match="get\\(out=\\)"):
+            G.get(lk.F_Z, out=bad)
+    G.close()
+
+
+def test_schedule_knobs_do_not_change_results():
+    """Every launch schedule is the same algorithm: dense sweeps, re-pack growth, segment kernel on / off, lane switch
+    point, graph on / off give identical iteration counts and z within rounding."""
+    model = robots.talos()
+    B = 512
+    pb = problems.random_batch(model, B, seed=17)
+    params = problems.bench_params(len(pb["ids"]))
+    G = _gpu(model, params, B)
+    _solve_init(G, pb)
+    G.Solve()
+    z0, it0 = G.z, G.get_iter()
+    for sc in (dict(dense_sweeps=0), dict(dense_sweeps=7, repack_reps=1, repack_growth=3.0), dict(seg_warps=1), dict(seg_warps=2, seg_after=0),
+               dict(use_graph=0), dict(lane_after=5), dict(lane_after=0, lane_warps_per_cta=1), dict(drop_workspace=0),
+               dict(hi_priority_after=-1, small_after=16, small_grid=64)):
+        G.set_schedule(**sc)
+        G.Solve()
+        same = G.get_iter() == it0
+        assert same.mean() >= 0.998, sc
+        assert rel_inf(G.z[same], z0[same]) < 1e-8, sc
+    with pytest.raises(RuntimeError, match="loik_set_schedule"):
+        G.set_schedule(repack_reps=0)
+    with pytest.raises(KeyError):
+        G.set_schedule(lane_ctas=3)
+    G.close()
