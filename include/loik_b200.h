@@ -119,10 +119,13 @@ typedef struct loik_schedule {
   int32_t small_after; /* rounds after this many sweeps are launched with at most `small_grid` CTAs (grid-stride) */
   int32_t small_grid;
   int32_t lane_warps_per_cta; /* warps (of 4 instances each) per CTA of the lane-parallel kernel; 0 = chosen from the record size */
+  int32_t lane_groups_per_instance; /* 8-lane groups per instance in that kernel: 1 (four instances per warp, each group sweeps the
+                                       whole tree), 4 (one instance per warp, the groups sweep different chains of a branching tree
+                                       level by level), 0 = default (1: the four-group form is not faster yet) */
   int32_t drop_workspace;     /* tile kernels: drop the consumed backward->forward workspace lines from L2 (discard.global.L2)
                                  instead of letting them be written back to HBM; never applied with loik_set_keep_workspace */
   /* read-only (ignored by loik_set_schedule) */
-  int32_t lane_available, lane_warps_chosen, lane_ctas, lane_smem_bytes;
+  int32_t lane_available, lane_warps_chosen, lane_groups_chosen, lane_ctas, lane_smem_bytes;
 } loik_schedule;
 
 /* Per-instance fields readable with loik_get().  Shapes are per instance; the batch dimension leads. */

@@ -18,6 +18,12 @@
 // an element is produced by one lane; reference file:line cited there); running inf-norms are kept as per-lane
 // partial maxima (max is exactly associative) and combined once per iteration.
 //
+// Two geometries (template parameter GPI = groups per instance):
+//   GPI = 1  four instances per warp, one 8-lane group each, every group sweeping the whole tree (chains: Panda, UR10);
+//   GPI = 4  ONE instance per warp, its four groups sweeping different chains of a branching tree level by level -- the
+//            segment / level schedule of k_iterate_seg (ModelC::seg) with groups in the role of its warps, the instance
+//            record shared in shared memory, __syncwarp() between the levels.  Talos: 10 joint steps on the critical
+//            path of a sweep instead of 32, at 80 % lane utilisation (32 joint steps on 4 x 10 group steps).
 // Scope: trees of 1-DoF joints (every BASELINE robot); models with multi-DoF joints keep the k_iterate path.
 #pragma once
 #include "loik_device.cuh"
@@ -43,17 +49,20 @@ enum : int { LX_V = 0, LX_T = 16, LX_ROWS = 96 };        // exchange scratch: 16
 enum : int { CJ_HREFR = 0, CJ_HREF = 48, CJ_HV = 96, CJ_ROWS = 104 };  // per joint: [Href + rho I | -Hv] and Href as 6 rows of 8, Hv (8)
 enum : int { CT_AR = 0, CT_ATR = 48, CT_ATA = 96, CT_ROWS = 144 };  // per task: A, A^T, A^T A as 6 rows of 8
 
+enum : int { GC_STRIDE = 24, GC_TOT = 96, GC_ROWS = 120 };  // GPI = 4: the groups' partial norms (4 x 24) and their combination (24)
+
 struct LaneDims {
-  int joint0, task0, pend0, xch, stride;  // offsets inside an instance record, record stride
-  int ctask0, csize, cpad;                // constants: first task block, size, size padded to 128 B
+  int joint0, task0, pend0, xch, gc, stride;  // offsets inside an instance record, record stride
+  int ctask0, csize, cpad;                    // constants: first task block, size, size padded to 128 B
 };
-__host__ __device__ inline LaneDims lane_dims(const int nb, const int nc, const int npend, const int href_uniform) {
+__host__ __device__ inline LaneDims lane_dims(const int nb, const int nc, const int npend, const int href_uniform, const int gpi) {
   LaneDims D;
   D.joint0 = LS_ROWS;
   D.task0 = D.joint0 + LJ_ROWS * nb;
   D.pend0 = D.task0 + LT_ROWS * nc;
   D.xch = D.pend0 + LP_ROWS * npend;
-  int sz = (D.xch + LX_ROWS + 7) & ~7;
+  D.gc = D.xch + LX_ROWS * gpi;  // (one exchange scratch per group)
+  int sz = (D.gc + (gpi > 1 ? GC_ROWS : 0) + 7) & ~7;
   if ((sz & 15) == 0) sz += 8;  // stride = 8 (mod 16) doubles: the records of two neighbouring groups cover different banks
   D.stride = sz;
   D.ctask0 = CJ_ROWS * (href_uniform ? 1 : nb);  // one [Href | -Hv] block when every joint shares the reference (UpdateReference)
@@ -61,7 +70,7 @@ __host__ __device__ inline LaneDims lane_dims(const int nb, const int nc, const 
   D.cpad = (D.csize + 15) & ~15;
   return D;
 }
-inline size_t lane_smem_bytes(const LaneDims& D, const int warps) { return ((size_t)D.cpad + (size_t)warps * kLaneI * D.stride) * sizeof(double); }
+inline size_t lane_smem_bytes(const LaneDims& D, const int warps, const int gpi) { return ((size_t)D.cpad + (size_t)warps * (kLaneI / gpi) * D.stride) * sizeof(double); }
 
 struct LaneP {
   const double* src;   // arena the instances live in when the kernel starts
@@ -94,24 +103,25 @@ struct LanePart { double dfis, dyis, Av, ptask, dF, Finf, Hrefv, dresv, dvis; };
 // ---------------------------------------------------------------------------------------------
 // state in / results out (8 lanes of one group, uncoalesced 8 B accesses: once per solve and instance)
 // ---------------------------------------------------------------------------------------------
+// (l, nl): index of this lane among the nl lanes that share the instance (8, or the whole warp with GPI = 4)
 template <int PER, typename F>
-LOIK_DEV void lane_copy_rows(const int total, const int l, F&& body) {  // body(e, phase, slot): phase 0 = load, 1 = store
-  for (int e0 = 0; e0 < total; e0 += 8 * PER) {
+LOIK_DEV void lane_copy_rows(const int total, const int l, const int nl, F&& body) {  // body(e, phase, slot): phase 0 = load, 1 = store
+  for (int e0 = 0; e0 < total; e0 += nl * PER) {
 #pragma unroll
-    for (int u = 0; u < PER; ++u) { const int e = e0 + 8 * u + l; if (e < total) body(e, 0, u); }
+    for (int u = 0; u < PER; ++u) { const int e = e0 + nl * u + l; if (e < total) body(e, 0, u); }
 #pragma unroll
-    for (int u = 0; u < PER; ++u) { const int e = e0 + 8 * u + l; if (e < total) body(e, 1, u); }
+    for (int u = 0; u < PER; ++u) { const int e = e0 + nl * u + l; if (e < total) body(e, 1, u); }
   }
 }
-LOIK_DEV void lane_load(const ModelC& M, const LaneDims& D, const double* T, double* I, const int l) {
+LOIK_DEV void lane_load(const ModelC& M, const LaneDims& D, const double* T, double* I, const int l, const int nl) {
   const Offs& O = M.off;
   double buf[8];
-  lane_copy_rows<8>(LJ_COPY * M.nb, l, [&](const int e, const int phase, const int u) {
+  lane_copy_rows<8>(LJ_COPY * M.nb, l, nl, [&](const int e, const int phase, const int u) {
     const int j = e / LJ_COPY, r = e - LJ_COPY * j;
     if (phase == 0) buf[u] = __ldcs(T + (size_t)(O.joint0 + JR_ROWS * j + r) * 32);
     else I[D.joint0 + LJ_ROWS * j + r] = buf[u];
   });
-  lane_copy_rows<8>(LT_ROWS * M.nc, l, [&](const int e, const int phase, const int u) {
+  lane_copy_rows<8>(LT_ROWS * M.nc, l, nl, [&](const int e, const int phase, const int u) {
     if (phase == 0) buf[u] = __ldcs(T + (size_t)(O.task0 + e) * 32);
     else I[D.task0 + e] = buf[u];
   });
@@ -122,13 +132,13 @@ LOIK_DEV void lane_load(const ModelC& M, const LaneDims& D, const double* T, dou
   }
 }
 // what retire_rows (loik_solver.cu) sends home: v, f, F, nu, z, w, T | y, Aty | mu, control, residuals
-LOIK_DEV void lane_retire(const ModelC& M, const LaneDims& D, const double* I, double* Th, const int l) {
+LOIK_DEV void lane_retire(const ModelC& M, const LaneDims& D, const double* I, double* Th, const int l, const int nl) {
   const Offs& O = M.off;
-  for (int e = l; e < JR_JQ * M.nb; e += 8) {
+  for (int e = l; e < JR_JQ * M.nb; e += nl) {
     const int j = e / JR_JQ, r = e - JR_JQ * j;
     Th[(size_t)(O.joint0 + JR_ROWS * j + r) * 32] = I[D.joint0 + LJ_ROWS * j + r];
   }
-  for (int e = l; e < TR_B * M.nc; e += 8) {
+  for (int e = l; e < TR_B * M.nc; e += nl) {
     const int k = e / TR_B, r = e - TR_B * k;
     Th[(size_t)(O.task0 + TR_ROWS * k + r) * 32] = I[D.task0 + LT_ROWS * k + r];
   }
@@ -139,9 +149,9 @@ LOIK_DEV void lane_retire(const ModelC& M, const LaneDims& D, const double* I, d
   }
 }
 // opt-in: His (21 packed scalars), pis, UDinv, Dinv, r of the last backward pass
-LOIK_DEV_CALL void lane_retire_workspace(const ModelC& M, const int joint0, const double* I, double* Th, const int l) {
+LOIK_DEV_CALL void lane_retire_workspace(const ModelC& M, const int joint0, const double* I, double* Th, const int l, const int nl) {
   const Offs& O = M.off;
-  for (int j = l; j < M.nb; j += 8) {
+  for (int j = l; j < M.nb; j += nl) {
     const double* Pj = I + joint0 + LJ_ROWS * j;
     double* Pd = Th + (size_t)(O.joint0 + JR_ROWS * j) * 32;
     for (int a = 0; a < 3; ++a)
@@ -165,25 +175,36 @@ LOIK_DEV void lds_xf(const double* p, double (&R)[9], double (&t)[3]) {  // liMi
 // Backward sweep: FwdPass1 (hxx:290-338) + BwdPassOptimizedVisitor (hxx:345-354, algo :31-81); cf. sweep_backward.
 // Lane c < 6 holds column c of H, lanes 6 and 7 (a duplicate) hold p.
 // ---------------------------------------------------------------------------------------------
-LOIK_DEV void lane_backward(const ModelC& M, const LaneDims& D, const double* CB, double* I, const int l, const double mu,
-                            const double mu_eq) {
+// In-sweep synchronisation of the lanes that exchange data (one group).  GPI = 1: all four groups run the same joints in
+// lock-step, the warp is converged and a full-mask __syncwarp() costs nothing; GPI = 4: the groups sweep different chains
+// (different trip counts), so only the group's own lanes may be named.
+template <int GPI>
+LOIK_DEV void lane_sync(const unsigned gmask) {
+  if (GPI == 1) __syncwarp();
+  else __syncwarp(gmask);
+}
+
+// The sweeps work on the joints lo..hi of the tree (GPI = 1: the whole tree; GPI = 4: one chain, cf. SegC), X = the group's
+// exchange scratch.
+template <int GPI>
+LOIK_DEV void lane_backward(const ModelC& M, const LaneDims& D, const double* CB, double* I, double* X, const int l, const unsigned gmask,
+                            const double mu, const double mu_eq, const int lo, const int hi) {
   const double rho = M.rho;
   const int lc = l < 6 ? l : 6;
   const bool isp = l >= 6;
   const double facv = isp ? -rho : 0.0;
-  double* X = I + D.xch;
   double* XT = X + LX_T;
   const double* XTrow = XT + 10 * lc;  // row of the transposed exchange this lane reads back (row 6: p itself)
   double cc[6];  // contribution carried from child i+1: this lane's column of X* H X*^T, resp. X* p
   bool have_carry = false;
-  double* Pj = I + D.joint0 + LJ_ROWS * M.nb;
+  double* Pj = I + D.joint0 + LJ_ROWS * hi;
   const int cstep = M.href_uniform ? 0 : CJ_ROWS;
-  const double* Cj = CB + cstep * M.nb + lc;
-  for (int i = M.nb; i >= 1; --i) {
+  const double* Cj = CB + cstep * hi + lc;
+  for (int i = hi; i >= lo; --i) {
     const JointC& J = M.j[i];
     Pj -= LJ_ROWS;
     Cj -= cstep;
-    __syncwarp();
+    lane_sync<GPI>(gmask);
     double vold[6], col[6];
     lds6(Pj + LJ_V, vold);
     const double w_i = Pj[LJ_W], z_i = Pj[LJ_Z];
@@ -223,7 +244,7 @@ LOIK_DEV void lane_backward(const ModelC& M, const LaneDims& D, const double* CB
     if (k >= 0) {
       // aligned joint, S = e_k: U = H(:, k) = row k of the symmetric H, and S^T p = p_k sits next to it in the stored
       // [H | p] block; this lane's own U_c (lane 6: p_k) is entry lc of the same row
-      __syncwarp();
+      lane_sync<GPI>(gmask);
       const double* row = Pj + LJ_HP + 8 * k;
       lds6(row, U);
       Stp = row[6];
@@ -232,9 +253,9 @@ LOIK_DEV void lane_backward(const ModelC& M, const LaneDims& D, const double* CB
     } else {
       // unaligned joint: U_c = S^T H(:, c) (H symmetric), one dot product per lane; lane 6 gets S^T p
       d = St_dot(J, col);
-      __syncwarp();
+      lane_sync<GPI>(gmask);
       X[LX_V + l] = d;
-      __syncwarp();
+      lane_sync<GPI>(gmask);
       lds6(X + LX_V, U);
       Stp = X[LX_V + 6];
       StU = St_dot(J, U);
@@ -259,7 +280,7 @@ LOIK_DEV void lane_backward(const ModelC& M, const LaneDims& D, const double* CB
 #pragma unroll
       for (int r = 0; r < 6; ++r) XT[10 * r + l] = y[r];
       if (isp) sts6(XT + 60, col);  // (the p lanes: their single transform is the second one)
-      __syncwarp();
+      lane_sync<GPI>(gmask);
       lds6(XTrow, row);
       act_force(R, t, row, cc);  // row c of Y X*^T = X* (row c of Y): column c of X* H X*^T (SE3actOn, :66); lane 6: liMi.act(p) (:74)
       if (J.carry) {
@@ -285,17 +306,17 @@ LOIK_DEV double pick6(const double (&x)[6], const int l) {
 // ComputePrimalResiduals (:494-503); cf. sweep_forward.  The 6-vectors are computed by every lane (they are the
 // chain), f = H v + p / A v / A^T y one component per lane.
 // ---------------------------------------------------------------------------------------------
-LOIK_DEV void lane_forward(const ModelC& M, const LaneDims& D, const double* CB, double* I, const int l, const double mu,
-                           const double mu_eq, Carry& cy, LanePart& pt) {
+template <int GPI>
+LOIK_DEV void lane_forward(const ModelC& M, const LaneDims& D, const double* CB, double* I, double* X, const int l, const unsigned gmask,
+                           const double mu, const double mu_eq, Carry& cy, LanePart& pt, const int lo, const int hi) {
   const double inv_mu = 1.0 / mu;
   const int lc = l < 6 ? l : 5;  // lanes 6, 7 duplicate lane 5
-  double* X = I + D.xch;
   double v[6] = {0, 0, 0, 0, 0, 0};  // v of joint i-1 on entry of step i
-  double* Pj = I + D.joint0 - LJ_ROWS;
-  for (int i = 1; i <= M.nb; ++i) {
+  double* Pj = I + D.joint0 + LJ_ROWS * (lo - 2);
+  for (int i = lo; i <= hi; ++i) {
     const JointC& J = M.j[i];
     Pj += LJ_ROWS;
-    __syncwarp();
+    lane_sync<GPI>(gmask);
     double UD[6], R[9], t[3];
     const double vold_l = Pj[LJ_V + lc];
     const double2 dr = lds2(Pj + LJ_DINV);  // (Dinv, r)
@@ -305,7 +326,7 @@ LOIK_DEV void lane_forward(const ModelC& M, const LaneDims& D, const double* CB,
     if (M.bounds_per_instance) { const double2 b2 = lds2(Pj + LJ_LB); lb = b2.x; ub = b2.y; }
     lds6(Pj + LJ_UD, UD);
     lds_xf(Pj + LJ_XF, R, t);
-    if (J.parent != i - 1) {  // not the joint just swept: the universe (v = 0) or a joint swept earlier (its new v)
+    if (i == lo || J.parent != i - 1) {  // not the joint this group has just swept: the universe (v = 0) or a joint swept earlier (its new v)
       if (J.parent == 0) {
 #pragma unroll
         for (int c = 0; c < 6; ++c) v[c] = 0.0;
@@ -342,10 +363,10 @@ LOIK_DEV void lane_forward(const ModelC& M, const LaneDims& D, const double* CB,
     cy.lbdw_m += lb * dmin(dw, 0.0);
     const double f_l = hc[0] * v[0] + hc[1] * v[1] + hc[2] * v[2] + hc[3] * v[3] + hc[4] * v[4] + hc[5] * v[5] + p_l;  // (:139-140)
     pt.dfis = amax(pt.dfis, f_l - fold_l);  // (:137-146)
-    __syncwarp();  // every lane has read this joint's previous iterate
+    lane_sync<GPI>(gmask);  // every lane has read this joint's previous iterate
     if (l == 0) sts6(Pj + LJ_V, v);
     Pj[LJ_F + lc] = f_l;
-    __syncwarp();
+    lane_sync<GPI>(gmask);
     pt.dvis = amax(pt.dvis, Pj[LJ_V + lc] - vold_l);  // delta_vis_inf_norm (:156-158), one component per lane
     *reinterpret_cast<double2*>(Pj + LJ_NU) = make_double2(nu, z);
     Pj[LJ_W] = w_old + dw;
@@ -362,7 +383,7 @@ LOIK_DEV void lane_forward(const ModelC& M, const LaneDims& D, const double* CB,
       pt.ptask = amax(pt.ptask, e);
       X[LX_V + l] = dy;
       X[LX_V + 8 + l] = y_l;
-      __syncwarp();
+      lane_sync<GPI>(gmask);
       double dys[6], ys[6], bk[6];
       lds6(X + LX_V, dys);
       lds6(X + LX_V + 8, ys);
@@ -388,18 +409,20 @@ LOIK_DEV void lane_forward(const ModelC& M, const LaneDims& D, const double* CB,
 // Residual sweep: BwdPass2OptimizedVisitor (hxx:468-487, algo :185-241) + ComputeDualResiduals (:510-522); cf.
 // sweep_residual.  F = fis_diff_plus_Aty one component per lane, liMi.act(f_i) by every lane.
 // ---------------------------------------------------------------------------------------------
-LOIK_DEV void lane_residual(const ModelC& M, const LaneDims& D, const double* CB, double* I, const int l, Resid& rs, LanePart& pt) {
+template <int GPI>
+LOIK_DEV void lane_residual(const ModelC& M, const LaneDims& D, const double* CB, double* I, const int l, const unsigned gmask, Resid& rs,
+                            LanePart& pt, const int lo, const int hi) {
   const int lc = l < 6 ? l : 5;
   double cF = 0.0;
   bool have_carry = false;
-  double* Pj = I + D.joint0 + LJ_ROWS * M.nb;
+  double* Pj = I + D.joint0 + LJ_ROWS * hi;
   const int cstep = M.href_uniform ? 0 : CJ_ROWS;
-  const double* Cj = CB + cstep * M.nb + lc;
-  for (int i = M.nb; i >= 1; --i) {
+  const double* Cj = CB + cstep * hi + lc;
+  for (int i = hi; i >= lo; --i) {
     const JointC& J = M.j[i];
     Pj -= LJ_ROWS;
     Cj -= cstep;
-    __syncwarp();
+    lane_sync<GPI>(gmask);
     double f[6], v[6];
     lds6(Pj + LJ_F, f);
     lds6(Pj + LJ_V, v);
@@ -425,7 +448,7 @@ LOIK_DEV void lane_residual(const ModelC& M, const LaneDims& D, const double* CB
     const double Tn = Stf + wt.x;           // Stf_plus_w (:231-236) and its delta (:471,:482-483)
     rs.T_inf = amax(rs.T_inf, Tn);
     rs.dT_inf = amax(rs.dT_inf, Tn - wt.y);
-    __syncwarp();
+    lane_sync<GPI>(gmask);
     Pj[LJ_FD + lc] = F;
     Pj[LJ_T] = Tn;
     have_carry = false;
@@ -441,12 +464,13 @@ LOIK_DEV void lane_residual(const ModelC& M, const LaneDims& D, const double* CB
 }
 
 // ---------------------------------------------------------------------------------------------
-// The kernel.  blockDim = 32 W; dynamic shared memory = constants + 4 W instance records (lane_smem_bytes).
+// The kernel.  blockDim = 32 W; dynamic shared memory = constants + (4 / GPI) W instance records (lane_smem_bytes).
 // ---------------------------------------------------------------------------------------------
+template <int GPI>
 __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ ModelC c_model, const LaneP P) {
   extern __shared__ __align__(16) double lsm[];
   const ModelC& M = c_model;
-  const LaneDims D = lane_dims(M.nb, M.nc, M.npend, M.href_uniform);
+  const LaneDims D = lane_dims(M.nb, M.nc, M.npend, M.href_uniform, GPI);
   double* CB = lsm;
   for (int e = threadIdx.x; e < D.csize; e += blockDim.x) {
     double x = 0.0;
@@ -470,26 +494,29 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, l = lane & 7, g = lane >> 3, w = threadIdx.x >> 5;
-  double* I = lsm + D.cpad + (size_t)(w * kLaneI + g) * D.stride;
-  double* X = I + D.xch;
   const unsigned gmask = 0xffu << (8 * g);
+  // the lanes that share one instance: an 8-lane group, or the whole warp
+  const int wl = GPI == 1 ? l : lane, nl = GPI == 1 ? 8 : 32;
+  const unsigned imask = GPI == 1 ? gmask : 0xffffffffu;
+  double* I = lsm + D.cpad + (size_t)(GPI == 1 ? w * kLaneI + g : w) * D.stride;
+  double* X = I + D.xch + (GPI == 1 ? 0 : g * LX_ROWS);
   const int limit = P.list ? *P.n_list : P.n;
-  int home_slot = -1;  // >= 0: this group holds an instance
+  int home_slot = -1;  // >= 0: these lanes hold an instance
   int status = ST_CONVERGED, it = 0, left = 0;
   double mu = 1.0;
   bool exhausted = false;
   for (;;) {
     if (home_slot < 0 && !exhausted) {  // pull the next instance from the queue
-      __syncwarp(gmask);  // the record is free: every lane of the group is done with the previous instance
+      __syncwarp(imask);  // the record is free: every lane is done with the previous instance
       int k = 0;
-      if (l == 0) k = atomicAdd(P.queue, 1);
-      k = __shfl_sync(gmask, k, 8 * g);
+      if (wl == 0) k = atomicAdd(P.queue, 1);
+      k = __shfl_sync(imask, k, GPI == 1 ? 8 * g : 0);
       if (k < limit) {
         const int s = P.list ? P.list[k] : k;
         const double* T = P.src + ((size_t)(s >> 5) * M.off.rows) * 32 + (s & 31);
-        lane_load(M, D, T, I, l);
-        __syncwarp(gmask);
-        for (int j = l; j < M.nb; j += 8) {  // liMi of every joint (FwdPassInit, hxx:263-264), once per instance
+        lane_load(M, D, T, I, wl, nl);
+        __syncwarp(imask);
+        for (int j = wl; j < M.nb; j += nl) {  // liMi of every joint (FwdPassInit, hxx:263-264), once per instance
           double* Pj = I + D.joint0 + LJ_ROWS * j;
           double R[9], t[3];
           make_xf(M.j[j + 1], Pj[LJ_SQ], Pj[LJ_CQ], R, t);
@@ -498,7 +525,7 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
 #pragma unroll
           for (int c = 0; c < 3; ++c) Pj[LJ_XF + 9 + c] = t[c];
         }
-        __syncwarp(gmask);
+        __syncwarp(imask);
         const int2 ctl = *reinterpret_cast<const int2*>(I + LS_CTL);
         status = ctl.x; it = ctl.y;
         mu = I[LS_MU];
@@ -511,34 +538,113 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
     __syncwarp();
     const bool act = home_slot >= 0;
     if (!__any_sync(0xffffffffu, act)) break;
-    // ---- one ADMM iteration of the (up to) four instances of this warp
+    // ---- one ADMM iteration of the instance(s) of this warp
     const double mu_eq = M.mu_scale * mu;
     Carry cy;
     Resid rs;
     LanePart pt = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     zero(cy);
     zero(rs);
-    lane_backward(M, D, CB, I, l, mu, mu_eq);
-    lane_forward(M, D, CB, I, l, mu, mu_eq, cy, pt);
-    lane_residual(M, D, CB, I, l, rs, pt);
-    {  // combine the per-lane partial maxima: rows = lanes, then one column per lane
+    if (GPI == 1) {
+      lane_backward<1>(M, D, CB, I, X, l, gmask, mu, mu_eq, 1, M.nb);
+      lane_forward<1>(M, D, CB, I, X, l, gmask, mu, mu_eq, cy, pt, 1, M.nb);
+      lane_residual<1>(M, D, CB, I, l, gmask, rs, pt, 1, M.nb);
+    } else {
+      // group g sweeps the chains assigned to "warp" g of the segment schedule, level by level (children before parents
+      // on the way to the root, parents before children on the way out); chains exchange data through the pending blocks
+      // and the parents' v rows of the shared record.  All four groups enter a sweep TOGETHER, each with its own joint
+      // range (round r = the r-th chain of the group at this level; an empty range when it has none): the groups then
+      // run the joint steps in lock-step and a group with a shorter chain simply leaves the loop earlier.  (Calling the
+      // sweep from inside a per-chain branch would serialise the groups: SIMT executes one side of a branch at a time.)
+      auto chain_of = [&](const bool backward, const int lv, const int r, int& lo, int& hi) {
+        lo = 1; hi = 0;
+        int cnt = 0;
+        for (int sg = 0; sg < M.nseg; ++sg) {
+          const SegC& sc = M.seg[sg];
+          if ((backward ? sc.bwarp : sc.fwarp) == g && (backward ? sc.blevel : sc.flevel) == lv) {
+            if (cnt == r) { lo = sc.lo; hi = sc.hi; }
+            ++cnt;
+          }
+        }
+      };
+      for (int lv = 0; lv < M.nblevel; ++lv) {
+        for (int r = 0;; ++r) {
+          int lo, hi;
+          chain_of(true, lv, r, lo, hi);
+          if (__ballot_sync(0xffffffffu, hi >= lo) == 0u) break;
+          lane_backward<GPI>(M, D, CB, I, X, l, gmask, mu, mu_eq, lo, hi);
+        }
+        __syncwarp();
+      }
+      for (int lv = 0; lv < M.nflevel; ++lv) {
+        for (int r = 0;; ++r) {
+          int lo, hi;
+          chain_of(false, lv, r, lo, hi);
+          if (__ballot_sync(0xffffffffu, hi >= lo) == 0u) break;
+          lane_forward<GPI>(M, D, CB, I, X, l, gmask, mu, mu_eq, cy, pt, lo, hi);
+        }
+        __syncwarp();
+      }
+      for (int lv = 0; lv < M.nblevel; ++lv) {
+        for (int r = 0;; ++r) {
+          int lo, hi;
+          chain_of(true, lv, r, lo, hi);
+          if (__ballot_sync(0xffffffffu, hi >= lo) == 0u) break;
+          lane_residual<GPI>(M, D, CB, I, l, gmask, rs, pt, lo, hi);
+        }
+        __syncwarp();
+      }
+    }
+    {  // combine the per-lane partial maxima of the group: rows = lanes, then one column per lane
       double* XT = X + LX_T;
-      __syncwarp();
+      lane_sync<GPI>(gmask);
       double* row = XT + 10 * l;
       *reinterpret_cast<double2*>(row) = make_double2(pt.dfis, pt.dyis);
       *reinterpret_cast<double2*>(row + 2) = make_double2(pt.Av, pt.ptask);
       *reinterpret_cast<double2*>(row + 4) = make_double2(pt.dF, pt.Finf);
       *reinterpret_cast<double2*>(row + 6) = make_double2(pt.Hrefv, pt.dresv);
       row[8] = pt.dvis;
-      __syncwarp();
+      lane_sync<GPI>(gmask);
       const double a0 = XT[l], a1 = XT[10 + l], a2 = XT[20 + l], a3 = XT[30 + l], a4 = XT[40 + l], a5 = XT[50 + l];
       X[LX_V + 8 + l] = dmax(dmax(dmax(a0, a1), dmax(a2, a3)), dmax(a4, a5));
       if (l == 0) X[LX_V + 7] = dmax(dmax(dmax(XT[8], XT[18]), dmax(XT[28], XT[38])), dmax(XT[48], XT[58]));
-      __syncwarp();
+      lane_sync<GPI>(gmask);
       cy.dvis_inf = X[LX_V + 7];
       const double2 t0 = lds2(X + LX_V + 8), t1 = lds2(X + LX_V + 10), t2 = lds2(X + LX_V + 12), t3 = lds2(X + LX_V + 14);
       cy.dfis_inf = t0.x; cy.dyis_inf = t0.y; cy.Av_inf = t1.x; cy.pres_task = t1.y;
       rs.dF_inf = t2.x; rs.F_inf = t2.y; rs.Hrefv_inf = t3.x; rs.dres_v = t3.y;
+    }
+    if (GPI > 1) {
+      // combine the groups' norms / sums in a fixed group order (as k_iterate_seg combines its warps): entries 8..11 of
+      // Carry are sums, everything else an inf-norm; afterwards every lane holds the instance's values
+      static_assert(sizeof(Carry) == kCarryRows * sizeof(double) && sizeof(Resid) == 7 * sizeof(double), "Carry / Resid are arrays of doubles");
+      double* GC = I + D.gc;
+      if (l == 0) {
+        const double* c = reinterpret_cast<const double*>(&cy);
+        const double* r = reinterpret_cast<const double*>(&rs);
+        double* o = GC + GC_STRIDE * g;
+#pragma unroll
+        for (int q = 0; q < kCarryRows; q += 2) *reinterpret_cast<double2*>(o + q) = make_double2(c[q], c[q + 1]);
+#pragma unroll
+        for (int q = 0; q < 6; q += 2) *reinterpret_cast<double2*>(o + kCarryRows + q) = make_double2(r[q], r[q + 1]);
+        o[kCarryRows + 6] = r[6];
+      }
+      __syncwarp();
+      if (lane < kCarryRows + 7) {
+        const double a = GC[lane], b = GC[GC_STRIDE + lane], c = GC[2 * GC_STRIDE + lane], d = GC[3 * GC_STRIDE + lane];
+        const bool is_sum = lane >= 8 && lane <= 11;
+        GC[GC_TOT + lane] = is_sum ? ((a + b) + c) + d : dmax(dmax(a, b), dmax(c, d));
+      }
+      __syncwarp();
+      {
+        double* c = reinterpret_cast<double*>(&cy);
+        double* r = reinterpret_cast<double*>(&rs);
+#pragma unroll
+        for (int q = 0; q < kCarryRows; q += 2) { const double2 t = lds2(GC + GC_TOT + q); c[q] = t.x; c[q + 1] = t.y; }
+#pragma unroll
+        for (int q = 0; q < 6; q += 2) { const double2 t = lds2(GC + GC_TOT + kCarryRows + q); r[q] = t.x; r[q + 1] = t.y; }
+        r[6] = GC[GC_TOT + kCarryRows + 6];
+      }
     }
     if (act) {
       ++it;
@@ -548,13 +654,13 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
       I[LS_RES + 1] = V.dres;
       if (V.has_tol) { I[LS_RES + 2] = V.tol_p; I[LS_RES + 3] = V.tol_d; }
       const bool done = status >= ST_CONVERGED || (P.fixed && --left <= 0);
-      if (done) {  // results go home; the group is free for the next instance
+      if (done) {  // results go home; the lanes are free for the next instance
         *reinterpret_cast<int2*>(I + LS_CTL) = make_int2(status, it);
         I[LS_MU] = mu;
-        __syncwarp(gmask);
+        __syncwarp(imask);
         double* Th = P.home + ((size_t)(home_slot >> 5) * M.off.rows) * 32 + (home_slot & 31);
-        lane_retire(M, D, I, Th, l);
-        if (P.keep_ws) lane_retire_workspace(M, D.joint0, I, Th, l);
+        lane_retire(M, D, I, Th, wl, nl);
+        if (P.keep_ws) lane_retire_workspace(M, D.joint0, I, Th, wl, nl);
         home_slot = -1;
       }
     }

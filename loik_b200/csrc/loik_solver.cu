@@ -742,6 +742,7 @@ struct loik_solver {
   int lane_after = -1;
   bool lane_ok = false;
   int lane_warps_req = 0;  // warps per CTA (0 = chosen from the record size)
+  int lane_gpi_req = 0;    // groups of 8 lanes per instance: 1, 4, or 0 = default (1)
   bool drop_ws = true;     // the tile kernels drop the consumed backward->forward workspace from L2 instead of writing it back
   int sms = 0, smem_optin = 0, smem_sm = 0;
   int sweeps_in_solve = 0;
@@ -801,11 +802,15 @@ static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S_in, 
 // per-CTA constants in shared memory.  Unless the caller fixed W (loik_schedule.lane_warps_per_cta): the smallest CTA that
 // keeps >= 90 % of the warps an SM's shared memory can hold -- small CTAs let the few CTAs that end up with a straggler
 // block less of an SM for the kernels of other solvers.
-struct LaneGeom { int warps = 0, ctas_per_sm = 0, grid = 0; size_t smem = 0; };
+struct LaneGeom { int gpi = 1, warps = 0, ctas_per_sm = 0, grid = 0; size_t smem = 0; };
 static bool lane_geometry(const loik_solver* h, LaneGeom& G) {
-  const LaneDims D = lane_dims(h->nb, h->nc, h->npend, h->mc.href_uniform);
+  // groups per instance.  Four groups of a warp on the chains of one instance is correct and tested but not faster yet:
+  // the groups run different joints, the hardware schedules them as separate SIMT sub-warps (34.5 vs 35.3 us per Talos
+  // iteration of a lone instance), so the default stays one group per instance
+  const int gpi = h->lane_gpi_req > 0 ? h->lane_gpi_req : 1;
+  const LaneDims D = lane_dims(h->nb, h->nc, h->npend, h->mc.href_uniform, gpi);
   auto ctas_of = [&](int W) -> int {
-    const size_t bytes = lane_smem_bytes(D, W);
+    const size_t bytes = lane_smem_bytes(D, W, gpi);
     if (bytes > (size_t)h->smem_optin) return 0;
     return std::min(32, (int)((size_t)h->smem_sm / (bytes + 1024)));
   };
@@ -817,8 +822,9 @@ static bool lane_geometry(const loik_solver* h, LaneGeom& G) {
       if (ctas_of(w) > 0 && 10 * ctas_of(w) * w >= 9 * best) W = w;
   }
   if (W <= 0 || W > 8 || ctas_of(W) == 0) return false;
-  G.warps = W; G.ctas_per_sm = ctas_of(W); G.smem = lane_smem_bytes(D, W);
-  G.grid = std::min(h->sms * G.ctas_per_sm, (h->batch + kLaneI * W - 1) / (kLaneI * W));
+  const int per_cta = (kLaneI / gpi) * W;
+  G.gpi = gpi; G.warps = W; G.ctas_per_sm = ctas_of(W); G.smem = lane_smem_bytes(D, W, gpi);
+  G.grid = std::min(h->sms * G.ctas_per_sm, (h->batch + per_cta - 1) / per_cta);
   return true;
 }
 // The lane-parallel kernel on the instances of `src` (all `batch` slots, or the `*n_list` slots named by `list`);
@@ -832,7 +838,8 @@ static int launch_lane(loik_solver* h, cudaStream_t st, const double* src, const
   P.src = src; P.list = list; P.n_list = n_list; P.n = h->batch; P.origin = origin; P.home = h->arena;
   P.queue = h->d_counts + 3; P.iters = iters; P.fixed = fixed; P.keep_ws = h->S.keep_ws;
   CK(cudaMemsetAsync(h->d_counts + 3, 0, sizeof(int), st));
-  k_iterate_lane<<<G.grid, 32 * G.warps, G.smem, st>>>(h->mc, P);
+  if (G.gpi == 1) k_iterate_lane<1><<<G.grid, 32 * G.warps, G.smem, st>>>(h->mc, P);
+  else k_iterate_lane<4><<<G.grid, 32 * G.warps, G.smem, st>>>(h->mc, P);
   h->launches++;
   return LOIK_OK;
 }
@@ -1138,7 +1145,10 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
   {
     LaneGeom G;
     h->lane_ok = M.nmd == 0 && lane_geometry(h, G);
-    if (h->lane_ok) CKA(cudaFuncSetAttribute(k_iterate_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    if (h->lane_ok) {
+      CKA(cudaFuncSetAttribute(k_iterate_lane<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+      CKA(cudaFuncSetAttribute(k_iterate_lane<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+    }
     // default switch point: short trees hand the instances still active after 10 sweeps to the lane-parallel kernel (one
     // Panda-65 536 solve 5.6 -> 2.2 ms at -5 % pipelined throughput); long / branching trees keep the tile kernels (their
     // record leaves room for 8 instances per SM only) unless the caller asks (loik_set_schedule)
@@ -1739,7 +1749,7 @@ int loik_get_schedule(loik_solver* h, loik_schedule* out) {
   out->small_after = h->small_after; out->small_grid = h->small_grid; out->drop_workspace = h->drop_ws ? 1 : 0;
   LaneGeom G;
   const bool ok = h->lane_ok && lane_geometry(h, G);
-  out->lane_warps_per_cta = h->lane_warps_req;
+  out->lane_warps_per_cta = h->lane_warps_req; out->lane_groups_per_instance = h->lane_gpi_req; out->lane_groups_chosen = G.gpi;
   out->lane_available = ok ? 1 : 0; out->lane_warps_chosen = G.warps; out->lane_ctas = G.grid; out->lane_smem_bytes = (int32_t)G.smem;
   return LOIK_OK;
 }
@@ -1747,11 +1757,11 @@ int loik_get_schedule(loik_solver* h, loik_schedule* out) {
 int loik_set_schedule(loik_solver* h, const loik_schedule* sc) {
   if (!h || !sc) return fail(LOIK_ERR_INVALID, "loik_set_schedule: null argument");
   if (sc->dense_sweeps < 0 || sc->repack_reps < 1 || !(sc->repack_growth >= 1.0) || sc->seg_warps < 0 || sc->seg_warps > 4 || sc->small_grid < 1 ||
-      sc->lane_warps_per_cta < 0 || sc->lane_warps_per_cta > 8)
-    return fail(LOIK_ERR_INVALID, "loik_set_schedule: dense_sweeps >= 0, repack_reps >= 1, repack_growth >= 1, 0 <= seg_warps <= 4, small_grid >= 1, 0 <= lane_warps_per_cta <= 8");
+      sc->lane_warps_per_cta < 0 || sc->lane_warps_per_cta > 8 || (sc->lane_groups_per_instance != 0 && sc->lane_groups_per_instance != 1 && sc->lane_groups_per_instance != 4))
+    return fail(LOIK_ERR_INVALID, "loik_set_schedule: dense_sweeps >= 0, repack_reps >= 1, repack_growth >= 1, 0 <= seg_warps <= 4, small_grid >= 1, 0 <= lane_warps_per_cta <= 8, lane_groups_per_instance in {0, 1, 4}");
   h->dense_sweeps = sc->dense_sweeps; h->sched_reps = sc->repack_reps; h->sched_growth = sc->repack_growth;
   h->hi_after = sc->hi_priority_after; h->seg_after = sc->seg_after;
-  h->lane_after = sc->lane_after; h->use_graph = sc->use_graph != 0; h->lane_warps_req = sc->lane_warps_per_cta;
+  h->lane_after = sc->lane_after; h->use_graph = sc->use_graph != 0; h->lane_warps_req = sc->lane_warps_per_cta; h->lane_gpi_req = sc->lane_groups_per_instance;
   h->small_after = sc->small_after; h->small_grid = sc->small_grid; h->drop_ws = sc->drop_workspace != 0;
   if (sc->seg_warps != h->seg_warps) { h->seg_warps = sc->seg_warps; assign_segments(h->mc, h->seg_warps); }
   if (h->g_exec) { cudaGraphExecDestroy(h->g_exec); h->g_exec = nullptr; }  // the cached launch graph follows the schedule

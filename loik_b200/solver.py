@@ -66,8 +66,8 @@ class _Schedule(C.Structure):
     _fields_ = [("dense_sweeps", C.c_int32), ("repack_reps", C.c_int32), ("repack_growth", C.c_double),
                 ("hi_priority_after", C.c_int32), ("seg_after", C.c_int32), ("seg_warps", C.c_int32),
                 ("lane_after", C.c_int32), ("use_graph", C.c_int32), ("small_after", C.c_int32), ("small_grid", C.c_int32),
-                ("lane_warps_per_cta", C.c_int32), ("drop_workspace", C.c_int32),
-                ("lane_available", C.c_int32), ("lane_warps_chosen", C.c_int32), ("lane_ctas", C.c_int32),
+                ("lane_warps_per_cta", C.c_int32), ("lane_groups_per_instance", C.c_int32), ("drop_workspace", C.c_int32),
+                ("lane_available", C.c_int32), ("lane_warps_chosen", C.c_int32), ("lane_groups_chosen", C.c_int32), ("lane_ctas", C.c_int32),
                 ("lane_smem_bytes", C.c_int32)]
 
 
@@ -470,7 +470,7 @@ class FirstOrderLoikOptimized:
         sc = _Schedule()
         self._check(self._lib.loik_get_schedule(self._h, C.byref(sc)))
         for k, v in kw.items():
-            if k not in dict(_Schedule._fields_) or k in ("lane_available", "lane_warps_chosen", "lane_ctas", "lane_smem_bytes"):
+            if k not in dict(_Schedule._fields_) or k in ("lane_available", "lane_warps_chosen", "lane_groups_chosen", "lane_ctas", "lane_smem_bytes"):
                 raise KeyError(k)
             setattr(sc, k, v)
         self._check(self._lib.loik_set_schedule(self._h, C.byref(sc)))

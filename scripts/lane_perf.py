@@ -47,7 +47,7 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); S.IterateFixed(K); e1.record(); torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / K
-            line = (f"{name} B={B} lane_after={la} (W={sc['lane_warps_chosen']} ctas={sc['lane_ctas']} smem={sc['lane_smem_bytes']}): "
+            line = (f"{name} B={B} lane_after={la} (W={sc['lane_warps_chosen']} gpi={sc['lane_groups_chosen']} ctas={sc['lane_ctas']} smem={sc['lane_smem_bytes']}): "
                     f"fixed {us:.1f} us/iter = {B/us:.0f} M inst-it/s = {bpi*B/us/1e3/6547.5:.3f} of HBM (algorithmic)")
             for _ in range(2):
                 S.Solve()

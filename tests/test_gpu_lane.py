@@ -52,14 +52,18 @@ def _oracle_iteration(o, it, fixed=True):
     o.UpdateMu()
 
 
-@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "panda9", "ur10c"])
-def test_lane_iterations_vs_oracle_method_by_method(name):
-    """k iterations in fixed-iteration mode (stopping disabled) == the oracle's public methods called k times."""
+@pytest.mark.parametrize("name,gpi", [("panda", 1), ("ur10", 1), ("talos", 1), ("panda9", 1), ("ur10c", 1),
+                                      ("talos", 4), ("panda9", 4), ("ur10", 4)])
+def test_lane_iterations_vs_oracle_method_by_method(name, gpi):
+    """k iterations in fixed-iteration mode (stopping disabled) == the oracle's public methods called k times.
+    gpi = 1: one 8-lane group per instance sweeps the whole tree; gpi = 4: the four groups of a warp sweep different
+    chains of ONE instance level by level (Talos: 5 chains, panda9: the two fingers; ur10: the degenerate single chain)."""
     model = robots.get_robot(name)
     B = 24
     pb = problems.random_batch(model, B, seed=11)
     params = problems.bench_params(len(pb["ids"]))
-    G = _gpu(model, params, B, lane_after=0)
+    G = _gpu(model, params, B, lane_after=0, lane_groups_per_instance=gpi)
+    assert G.get_schedule()["lane_groups_chosen"] == gpi
     G.set_keep_workspace(True)
     _solve_init(G, pb)
     O = []
@@ -135,14 +139,29 @@ def _compare_solves(model, params, pb, what, schedule, tol=1e-6, max_diverged_fr
     G.close()
 
 
-@pytest.mark.parametrize("name,B", [("panda", 4096), ("ur10", 4096), ("talos", 1024), ("panda9", 1024), ("ur10c", 2048)])
+@pytest.mark.parametrize("name,B,gpi", [("panda", 4096, 1), ("ur10", 4096, 1), ("talos", 1024, 1), ("panda9", 1024, 1), ("ur10c", 2048, 1),
+                                        ("talos", 1024, 4), ("panda9", 1024, 4)])
 @pytest.mark.parametrize("lane_after", [0, 3, 7, 40])
-def test_lane_full_solves(name, B, lane_after):
+def test_lane_full_solves(name, B, gpi, lane_after):
     """Full solves (max_iter 200): the whole solve in the lane kernel (0), the hand-over from the home arena after the
-    dense sweeps (3: list mode, no origin map) and from a packed scratch arena (7, 40: list + origin map)."""
+    dense sweeps (3: list mode, no origin map) and from a packed scratch arena (7, 40: list + origin map); one group
+    per instance and, for the branching trees, four groups per instance."""
     model = robots.get_robot(name)
     pb = problems.random_batch(model, B, seed=0)
-    _compare_solves(model, problems.bench_params(len(pb["ids"])), pb, name, dict(lane_after=lane_after), max_diverged_frac=0.002)
+    _compare_solves(model, problems.bench_params(len(pb["ids"])), pb, name, dict(lane_after=lane_after, lane_groups_per_instance=gpi),
+                    max_diverged_frac=0.002)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_lane_random_trees(seed):
+    """Random trees of every 1-DoF joint type (aligned / unaligned / unbounded revolute, prismatic), two tasks, random
+    branching: both geometries of the lane kernel against the oracle, iteration by iteration decisions included."""
+    model = robots.random_tree(12 + 3 * seed, seed=seed, continuous=0.3 if seed % 2 else 0.0)
+    tasks = [model.nj - 1, max(1, model.nj // 2)]
+    pb = problems.random_batch(model, 256, seed=seed, task_joints=tasks)
+    params = dict(problems.FIXTURE_PARAMS, max_iter=200, num_eq_c=2)
+    for gpi in (1, 4):
+        _compare_solves(model, params, pb, f"tree{seed} gpi{gpi}", dict(lane_after=0, lane_groups_per_instance=gpi), max_diverged_frac=0.004)
 
 
 @pytest.mark.parametrize("B", [1, 3, 4, 5, 31, 33, 100])
