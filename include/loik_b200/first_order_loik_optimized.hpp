@@ -6,9 +6,9 @@
 //
 // Differences, all forced by batching: vectors carry a leading batch dimension (row-major, one row per instance),
 // the caller-owned IkIdData of the reference lives in HBM inside the handle (read it back with z(), nu(), w() ...),
-// and the model is the flat table `loik_b200::Model` below.  With Pinocchio available, `loik_b200::Model` is filled
-// from a pinocchio::Model by `from_pinocchio()` (compile with -DLOIK_B200_WITH_PINOCCHIO; not compilable in the
-// offline build container, reviewed by eye -- SURVEY.md section 7 step 10).
+// and the model is the flat table `loik_b200::Model` below.  The single-instance facade with the reference's exact
+// argument types (const pinocchio::Model&, caller-owned IkIdData&, Eigen / aligned-vector arguments, results written
+// back into the IkIdData members) is loik_b200/loik_pinocchio.hpp.
 #pragma once
 #include <cstdint>
 #include <stdexcept>
@@ -17,13 +17,12 @@
 
 #include "../loik_b200.h"
 
-#ifdef LOIK_B200_WITH_PINOCCHIO
-#include <pinocchio/multibody/model.hpp>
-#endif
-
 namespace loik_b200 {
 
+#ifndef LOIK_B200_ADMM_STRAT_DEFINED
+#define LOIK_B200_ADMM_STRAT_DEFINED
 enum ADMMPenaltyUpdateStrat { DEFAULT = LOIK_MU_DEFAULT, OSQP = LOIK_MU_OSQP, MAXEIGENVALUE = LOIK_MU_MAXEIGENVALUE };
+#endif
 
 // What the hot path reads from pinocchio::Model (loik-loid-optimized.hxx:46-47,258-265).
 struct Model {
@@ -34,61 +33,6 @@ struct Model {
   std::vector<double> placement_R;  // [njoints][9] row-major
   std::vector<double> placement_p;  // [njoints][3]
 };
-
-#ifdef LOIK_B200_WITH_PINOCCHIO
-// pinocchio::Model -> flat tables.  Only 1-DoF revolute / prismatic joints (aligned or unaligned) are supported.
-inline Model from_pinocchio(const pinocchio::Model& m) {
-  Model out;
-  out.njoints = m.njoints; out.nv = m.nv;
-  out.parents.assign(m.njoints, 0); out.joint_types.assign(m.njoints, 0);
-  out.joint_axes.assign(3 * m.njoints, 0.0); out.placement_R.assign(9 * m.njoints, 0.0); out.placement_p.assign(3 * m.njoints, 0.0);
-  int idx_q = 0, idx_v = 0;  // cumulative, as pinocchio lays q and v out
-  for (int i = 0; i < m.njoints; ++i) {
-    out.parents[i] = static_cast<int32_t>(m.parents[i]);
-    const auto& M = m.jointPlacements[i];
-    for (int r = 0; r < 3; ++r) { out.placement_p[3 * i + r] = M.translation()[r]; for (int c = 0; c < 3; ++c) out.placement_R[9 * i + 3 * r + c] = M.rotation()(r, c); }
-    if (i == 0) { out.joint_axes[2] = 1.0; continue; }
-    const std::string s = m.joints[i].shortname();
-    double ax[3] = {0, 0, 0};
-    int code = -1;
-    if (s == "JointModelRX") { code = LOIK_JOINT_RX; ax[0] = 1; }
-    else if (s == "JointModelRY") { code = LOIK_JOINT_RY; ax[1] = 1; }
-    else if (s == "JointModelRZ") { code = LOIK_JOINT_RZ; ax[2] = 1; }
-    else if (s == "JointModelPX") { code = LOIK_JOINT_PX; ax[0] = 1; }
-    else if (s == "JointModelPY") { code = LOIK_JOINT_PY; ax[1] = 1; }
-    else if (s == "JointModelPZ") { code = LOIK_JOINT_PZ; ax[2] = 1; }
-    else if (s == "JointModelRevoluteUnaligned") {
-      code = LOIK_JOINT_RU;
-      const auto& a = boost::get<pinocchio::JointModelRevoluteUnaligned>(m.joints[i].toVariant()).axis;
-      ax[0] = a[0]; ax[1] = a[1]; ax[2] = a[2];
-    } else if (s == "JointModelPrismaticUnaligned") {
-      code = LOIK_JOINT_PU;
-      const auto& a = boost::get<pinocchio::JointModelPrismaticUnaligned>(m.joints[i].toVariant()).axis;
-      ax[0] = a[0]; ax[1] = a[1]; ax[2] = a[2];
-    } else if (s == "JointModelFreeFlyer") { code = LOIK_JOINT_FF; ax[2] = 1; }
-    else if (s == "JointModelSpherical") { code = LOIK_JOINT_SPHERICAL; ax[2] = 1; }
-    else if (s == "JointModelTranslation") { code = LOIK_JOINT_TRANSLATION; ax[2] = 1; }
-    else if (s == "JointModelPlanar") { code = LOIK_JOINT_PLANAR; ax[2] = 1; }
-    else if (s == "JointModelRUBX") { code = LOIK_JOINT_RUBX; ax[0] = 1; }
-    else if (s == "JointModelRUBY") { code = LOIK_JOINT_RUBY; ax[1] = 1; }
-    else if (s == "JointModelRUBZ") { code = LOIK_JOINT_RUBZ; ax[2] = 1; }
-    else if (s == "JointModelRevoluteUnboundedUnaligned") {
-      code = LOIK_JOINT_RUBU;
-      const auto& a = boost::get<pinocchio::JointModelRevoluteUnboundedUnaligned>(m.joints[i].toVariant()).axis;
-      ax[0] = a[0]; ax[1] = a[1]; ax[2] = a[2];
-    } else {
-      throw std::runtime_error("loik_b200::from_pinocchio: unsupported joint type " + s);
-    }
-    if (m.joints[i].idx_v() != idx_v || m.joints[i].idx_q() != idx_q)
-      throw std::runtime_error("loik_b200::from_pinocchio: unexpected idx_q / idx_v layout");
-    idx_q += m.joints[i].nq();
-    idx_v += m.joints[i].nv();
-    out.joint_types[i] = code;
-    for (int c = 0; c < 3; ++c) out.joint_axes[3 * i + c] = ax[c];
-  }
-  return out;
-}
-#endif
 
 class FirstOrderLoikOptimized {
  public:
@@ -157,7 +101,10 @@ class FirstOrderLoikOptimized {
   // His() / pis() after Solve(), as the reference leaves them in ik_id_data (tests/loik-loid.cpp:597-615): opt-in, a
   // finished instance then brings its backward-pass workspace home too (off: those getters throw after a solve)
   void set_keep_workspace(bool on) { check(loik_set_keep_workspace(h_, on ? 1 : 0)); }
-  void ResetSolver() { check(loik_reset_recursion(h_, stream_)); }  // Solve()'s ResetRecursion + ResetSolver (hpp:370-374)
+  // ResetSolver() (hpp:168-186): iteration counter, flags, mu, feasibility scalars -- the primal / dual state is kept
+  void ResetSolver() { check(loik_reset_solver(h_, stream_)); }
+  // ik_id_data_.ResetRecursion() + ResetSolver(): what Solve() does before its loop (hpp:370-374)
+  void ResetRecursion() { check(loik_reset_recursion(h_, stream_)); }
   void FwdPassInit(const std::vector<double>& q) { check(loik_fwd_pass_init(h_, q.data(), LOIK_HOST, stream_)); }
   void UpdatePrev() { step(LOIK_STEP_UPDATE_PREV); }
   void ResetInfNorms() { step(LOIK_STEP_RESET_INF_NORMS); }
@@ -200,6 +147,13 @@ class FirstOrderLoikOptimized {
   void set_rho(double r) { check(loik_set_rho(h_, r)); }
   void set_mu(double m) { check(loik_set_mu(h_, m)); }
   void set_tol_tail_solve(double t) { check(loik_set_tol_tail_solve(h_, t)); }
+  void set_tol_abs(double t) { check(loik_set_tol_abs(h_, t)); }
+  void set_tol_rel(double t) { check(loik_set_tol_rel(h_, t)); }
+  void set_tol_primal_inf(double t) { check(loik_set_tol_primal_inf(h_, t)); }
+  void set_tol_dual_inf(double t) { check(loik_set_tol_dual_inf(h_, t)); }
+  void set_mu_equality_scale_factor(double f) { check(loik_set_mu_equality_scale_factor(h_, f)); }
+  loik_params get_params() const { loik_params p; check(loik_get_params(h_, &p)); return p; }  // get_max_iter() ... get_tol_dual_inf()
+  double get_rho() const { return get_params().rho; }
   loik_solver* handle() const { return h_; }
 
  private:
