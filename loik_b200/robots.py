@@ -76,6 +76,16 @@ class RobotModel:
     v_max: np.ndarray         # [nv] joint velocity limits (ub = -lb)
     joint_names: list
 
+    @classmethod
+    def from_tables(cls, name, parent, jtype, axis, placement_R, placement_p, q_min=None, q_max=None, v_max=None, joint_names=None):
+        """A model from flat tables (e.g. the dump of a pinocchio::Model, oracle/ref_recipe); limits default to +-pi / 2."""
+        m = cls(name, np.asarray(parent, np.int32), np.asarray(jtype, np.int32), np.asarray(axis, float), np.asarray(placement_R, float),
+                np.asarray(placement_p, float), None, None, None, joint_names or [f"j{i}" for i in range(len(parent))])
+        m.q_min = -np.pi * np.ones(m.nq) if q_min is None else np.asarray(q_min, float)
+        m.q_max = np.pi * np.ones(m.nq) if q_max is None else np.asarray(q_max, float)
+        m.v_max = 2.0 * np.ones(m.nv) if v_max is None else np.asarray(v_max, float)
+        return m
+
     @property
     def nj(self) -> int:
         return int(self.parent.shape[0])

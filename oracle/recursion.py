@@ -20,11 +20,12 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
 
-def build(force: bool = False, march: str | None = None, out: str | None = None) -> str:
-    """Compile the oracle with gcc (``make -C oracle``).  Returns the .so path."""
+def build(force: bool = False, march: str | None = None, out: str | None = None, fp_contract: str = "off") -> str:
+    """Compile the oracle with gcc (``make -C oracle``).  Returns the .so path.  ``fp_contract="fast"`` (with
+    ``march="native"``: FMA) builds the same source with a different rounding, for the sensitivity test."""
     if out is not None:
         src = os.path.join(_HERE, "loik_oracle.c")
-        flags = ["-O3", f"-march={march or 'native'}", "-std=c99", "-fPIC", "-fvisibility=hidden", "-ffp-contract=off"]
+        flags = ["-O3", f"-march={march or 'native'}", "-std=c99", "-fPIC", "-fvisibility=hidden", f"-ffp-contract={fp_contract}"]
         subprocess.check_call(["gcc", *flags, "-shared", "-o", out, src, "-lm", "-lpthread"])
         return out
     src = os.path.join(_HERE, "loik_oracle.c")

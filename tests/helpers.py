@@ -21,10 +21,21 @@ def instance(pb, i):
     return [pb["q"][i], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"][i], pb["lb"], pb["ub"]]
 
 
+REL_FLOOR = 1e-9
+
+
 def rel_inf(a, b):
-    """max_i |a_i - b_i| / max(1, |b|_inf) -- the rel-inf distance north_star quotes (1e-6 gate)."""
+    """|a - b|_inf / |b|_inf -- the rel-inf distance north_star quotes (1e-6 gate).  Truly relative: the denominator is the
+    reference's own norm; only below |b|_inf = 1e-9 (quantities that are zero up to rounding, e.g. the multiplier w of a
+    bound that never became active) does it turn into an absolute test at 1e-9 * gate."""
     a, b = np.asarray(a, float), np.asarray(b, float)
-    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max())) if a.size else 0.0
+    return float(np.abs(a - b).max() / max(REL_FLOOR, np.abs(b).max())) if a.size else 0.0
+
+
+def rel_inf_rows(a, b):
+    """rel_inf of every instance (row) of two batched arrays at once."""
+    a, b = np.asarray(a, float).reshape(len(a), -1), np.asarray(b, float).reshape(len(b), -1)
+    return np.abs(a - b).max(axis=1) / np.maximum(REL_FLOOR, np.abs(b).max(axis=1))
 
 
 def check_abs_or_rel(a, b, tol=1e-10, what=""):

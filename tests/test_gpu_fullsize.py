@@ -1,7 +1,8 @@
-"""Full-size (BASELINE.json) parity through size-independent properties, plus ragged / edge-case batches.  -m gpu.
+"""Full-size (BASELINE.json) parity, plus ragged / edge-case batches.  -m gpu.
 
-At 65 536 / 262 144 / 16 384 instances the oracle cannot solve everything in seconds, so the CUDA path is checked by
-(1) a seeded sample of instances against the oracle, (2) properties that hold for every instance regardless of size:
+At 65 536 / 262 144 / 16 384 instances the CUDA path is checked (1) instance by instance against the oracle (all of them:
+the C oracle solves a full-size batch in about a second on the host cores) and (2) through properties that hold for
+every instance regardless of size:
 permutation equivariance (an instance's result does not depend on its slot, its tile neighbours or the re-packing
 order), sub-batch invariance, idempotence of repeated solves, feasibility of z (box) and the KKT-style residual
 identities the iterates satisfy by construction.
@@ -10,7 +11,7 @@ import numpy as np
 import pytest
 
 from loik_b200 import problems, robots
-from tests.helpers import ctor_kwargs, rel_inf
+from tests.helpers import ctor_kwargs, rel_inf, rel_inf_rows
 
 pytestmark = pytest.mark.gpu
 
@@ -29,7 +30,7 @@ def _solve(G, pb):
 
 
 @pytest.mark.parametrize("name,B", FULL)
-def test_full_size_sample_vs_oracle_and_properties(name, B):
+def test_full_size_every_instance_vs_oracle_and_properties(name, B):
     from oracle import recursion
     model = robots.get_robot(name)
     pb = problems.random_batch(model, B, seed=0)
@@ -49,18 +50,17 @@ def test_full_size_sample_vs_oracle_and_properties(name, B):
     lo = (r["w"] < -tol) & conv[:, None]
     assert (np.abs(r["z"] - pb["ub"])[up] < 5e-2).all()
     assert (np.abs(r["z"] - pb["lb"])[lo] < 5e-2).all()
-    # (1) seeded sample against the oracle
+    # (1) EVERY instance of the full-size batch against the oracle (a second on the host cores): identical decision
+    # traces (iteration count, final mu, status) and z, nu, w, y within 1e-6 rel-inf
     rng = np.random.default_rng(1)
-    idx = np.sort(rng.choice(B, size=768 if not name.startswith("talos") else 256, replace=False))
-    sub = dict(pb, q=pb["q"][idx], bis=pb["bis"][idx])
-    ref = recursion.batch_solve(model, params, sub["q"], sub["H_ref"], sub["v_ref"], sub["ids"], sub["Ais"], sub["bis"], sub["lb"],
-                                sub["ub"], nthreads=8)
-    same = (r["it"][idx] == ref["iters"]) & (r["mu"][idx] == ref["mu"]) & ((r["st"][idx] & 3) == (ref["status"] & 3))
-    assert same.mean() >= 0.998, f"{(~same).sum()} diverged decision traces in the sample"
-    for j in np.nonzero(same)[0]:
-        i = idx[j]
-        assert rel_inf(r["z"][i], ref["z"][j]) < 1e-6 and rel_inf(r["nu"][i], ref["nu"][j]) < 1e-6
-        assert rel_inf(r["w"][i], ref["w"][j]) < 1e-6 and rel_inf(r["y"][i], ref["y"][j]) < 1e-6
+    ref = recursion.batch_solve(model, params, pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"],
+                                nthreads=8)
+    same = (r["it"] == ref["iters"]) & (r["mu"] == ref["mu"]) & ((r["st"] & 3) == (ref["status"] & 3))
+    print(f"[{name} x {B}] diverged decision traces: {int((~same).sum())}")
+    assert same.mean() >= 0.9998, f"{(~same).sum()} diverged decision traces of {B}"
+    worst = max(rel_inf_rows(r[k][same], ref[k][same]).max() for k in ("z", "nu", "w", "y"))
+    print(f"[{name} x {B}] worst rel-inf over z, nu, w, y of {int(same.sum())} instances: {worst:.3e}")
+    assert worst < 1e-6
     # (2) idempotence: the same handle solving again reproduces itself bit for bit
     G.Solve()
     np.testing.assert_array_equal(G.z, r["z"])

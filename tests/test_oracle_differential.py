@@ -9,6 +9,8 @@ the non-optimized one on one fixture (``/root/reference/tests/loik-loid.cpp``):
   test_loik_solve_split                                     :261-303
 This is what pins the oracle (PARITY UNPINNED by known answers: the reference has no golden vectors).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -287,3 +289,66 @@ def test_unbounded_revolute_equals_bounded_twin():
     assert np.abs(q1[:, 0] - np.cos(th[:, 0])).max() < 1e-6 and np.abs(q1[:, 7] - np.sin(th[:, 5])).max() < 1e-6
     assert np.abs(np.hypot(q1[:, 0], q1[:, 1]) - 1.0).max() < 1e-6
     np.testing.assert_allclose(q1[:, 2:6], th[:, 1:5], rtol=0, atol=1e-15)
+
+
+def test_multidof_step_tolerance_is_rounding_sensitivity(tmp_path):
+    """Why the GPU step tests of trees with multi-DoF joints use 5e-9 instead of the reference comparator's 1e-10
+    (tests/test_gpu_parity.py::test_multi_dof_joints_anywhere_step_by_step): the SAME oracle source built once without
+    and once with FMA contraction -- two roundings of one formula -- already differs by that much on those trees (below a
+    free-flyer, H - H (H + mu I)^-1 H is a difference of nearly equal matrices: mu = 1e-2 next to task weights of 1e2),
+    while on trees of 1-DoF joints the two builds agree to 1e-10.  No formula differs; the arithmetic is that sensitive."""
+    import shutil
+    import subprocess
+
+    from oracle import recursion
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    have_fma = "fma" in open("/proc/cpuinfo").read() if os.path.exists("/proc/cpuinfo") else False
+    if not have_fma:
+        pytest.skip("host CPU has no FMA: cannot build a second rounding of the oracle")
+    lib_a = recursion.load(recursion.build(out=str(tmp_path / "a.so"), march="native", fp_contract="off"))
+    lib_b = recursion.load(recursion.build(out=str(tmp_path / "b.so"), march="native", fp_contract="fast"))
+
+    def worst_step_deviation(model, pb, params):
+        worst = 0.0
+        for i in range(pb["q"].shape[0]):
+            sols = []
+            for lib in (lib_a, lib_b):
+                o = recursion.FirstOrderLoikOptimized(model, **ctor_kwargs(params), lib=lib)
+                o.SolveInit(pb["q"][i], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"][i], pb["lb"], pb["ub"])
+                o.ResetSolver()
+                sols.append(o)
+            for it in range(1, 4):
+                for o in sols:
+                    o.UpdatePrev(); o.ResetInfNorms(); o.FwdPass1(); o.BwdPassOptimizedVisitor()
+                    o.FwdPass2OptimizedVisitor(); o.BoxProj(); o.DualUpdate(); o.ComputeResiduals(); o.CheckConvergence()
+                    o.UpdateMu()
+                if sols[0].get_mu() != sols[1].get_mu():
+                    break
+                for f in ("His", "pis", "vis", "fis", "nu", "z", "w", "yis"):
+                    a, b = getattr(sols[0], f), getattr(sols[1], f)
+                    d = np.abs(a - b).max()
+                    scale = max(np.abs(a).max(), np.abs(b).max(), 1.0)
+                    worst = max(worst, d / scale)
+        return worst
+
+    params = dict(problems.FIXTURE_PARAMS, max_iter=200, num_eq_c=2)
+    rng = np.random.default_rng(5)
+    md, plain = 0.0, 0.0
+    for seed in range(5):
+        multidof = (0.3, 0.3, 0.6, 1.0, 0.4)[seed]
+        model = robots.random_tree(9 + seed, 40 + seed, multidof=multidof)
+        ids = np.array(sorted(np.random.default_rng(300 + seed).choice(np.arange(1, model.nj), size=2, replace=False)), np.int32)
+        Hs = rng.normal(size=(6, 6))
+        pb = dict(q=model.normalize(rng.uniform(model.q_min, model.q_max, size=(12, model.nq))), H_ref=np.eye(6) + 0.1 * (Hs + Hs.T),
+                  v_ref=0.1 * rng.normal(size=6), ids=ids, Ais=np.stack([np.eye(6) + 0.3 * rng.normal(size=(6, 6)) for _ in range(2)]),
+                  bis=rng.uniform(-0.5, 0.5, size=(12, 2, 6)), lb=-model.v_max, ub=model.v_max)
+        md = max(md, worst_step_deviation(model, pb, params))
+        model1 = robots.random_tree(9 + seed, 40 + seed, multidof=0.0)
+        pb1 = dict(pb, q=model1.normalize(rng.uniform(model1.q_min, model1.q_max, size=(12, model1.nq))), lb=-model1.v_max, ub=model1.v_max,
+                   ids=np.array([model1.nj - 1, max(1, model1.nj // 2)], np.int32))
+        plain = max(plain, worst_step_deviation(model1, pb1, params))
+    print(f"two roundings of the oracle: trees with multi-DoF joints differ by {md:.2e}, trees of 1-DoF joints by {plain:.2e}")
+    assert plain < 1e-10, "1-DoF trees: the reference comparator's tolerance holds between two roundings"
+    assert md < 5e-9, "the GPU tests' multi-DoF step tolerance covers the rounding sensitivity"
+    assert md > 10 * plain or md > 1e-11, "multi-DoF trees are measurably more sensitive (otherwise tighten the GPU tolerance)"
