@@ -147,7 +147,8 @@ typedef enum loik_field {
   LOIK_F_LIMI,         /* [nb][12]  ik_id_data.liMi[1..]: rotation (9, row-major) then translation (3) */
   LOIK_F_MU,           /* [1]       get_mu() */
   LOIK_F_ITER,         /* [1] int32 get_iter() */
-  LOIK_F_STATUS,       /* [1] int32 bit0 converged, bit1 primal_infeasible, bit2 stopped at max_iter */
+  LOIK_F_STATUS,       /* [1] int32 bit0 converged_, bit1 primal_infeasible_ (both can be set: the reference evaluates both checks of an
+                          iteration, hpp:421-432, and stops on converged_ first), bit2 stopped at max_iter */
   LOIK_F_RESIDUALS,    /* [4]       primal_residual, dual_residual, tol_primal, tol_dual */
   LOIK_F_NORMS,        /* [LOIK_NUM_NORMS] the running norms / sums of IkIdDataTypeOptimized + feasibility scalars
                           (only maintained when loik_set_debug(h,1)); order: loik_norm_index */
@@ -215,14 +216,18 @@ LOIK_API const char* loik_last_error(void);
  *   q        [batch][nq]
  *   H_ref    [36] one symmetric 6x6 broadcast to all joints (UpdateReference), v_ref [6]
  *   task_joint_ids [nc] joint ids carrying a task (distinct, in 1..njoints-1), shared by the batch
- *   A        [nc][36] shared by the batch
+ *   A        [batch][nc][36] if A_per_instance (every instance its own task matrices: e.g. a world-frame end-effector
+ *            task, whose A depends on q), else [nc][36] shared by the batch (HOST)
  *   b        [batch][nc][6] if b_per_instance else [nc][6]
  *   lb, ub   [batch][nv] if bounds_per_instance else [nv] (HOST)
- * H_ref, v_ref, task_joint_ids, A and batch-shared lb/ub are always HOST pointers (small, batch-uniform: they
- * travel to the kernels in the parameter block); `loc` applies to q, b and per-instance lb/ub. */
+ * H_ref, v_ref, task_joint_ids and the batch-shared forms of A and lb/ub are always HOST pointers (small, batch-uniform:
+ * they travel to the kernels in the parameter block); `loc` applies to q, b and the per-instance forms of A and lb/ub.
+ * Per-instance A costs 57 more rows per task in HBM (A and A^T A, read once per iteration each): 8 * (143 n + 99 nc)
+ * algorithmic bytes per instance and iteration instead of 8 * (143 n + 42 nc). */
 LOIK_API int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const double* v_ref, int32_t n_ids,
-                             const int32_t* task_joint_ids, const double* A, const double* b, int32_t b_per_instance,
-                             const double* lb, const double* ub, int32_t bounds_per_instance, int32_t loc, void* stream);
+                             const int32_t* task_joint_ids, const double* A, int32_t A_per_instance, const double* b,
+                             int32_t b_per_instance, const double* lb, const double* ub, int32_t bounds_per_instance, int32_t loc,
+                             void* stream);
 
 /* problem_.UpdateReferences(H_refs, v_refs)  (ik-id-description-optimized.hpp:103-121): per-joint references,
  * H_refs [njoints][36], v_refs [njoints][6], HOST pointers; call after loik_solve_init. */
@@ -236,13 +241,15 @@ LOIK_API int loik_update_references(loik_solver* h, const double* H_refs, const 
 LOIK_API int loik_solve(loik_solver* h, void* stream);
 /* Solve(q, H_ref, v_ref, ids, Ais, bis, lb, ub)  (hpp:475-580) = SolveInit + main loop (no ResetRecursion). */
 LOIK_API int loik_solve_full(loik_solver* h, const double* q, const double* H_ref, const double* v_ref, int32_t n_ids,
-                             const int32_t* task_joint_ids, const double* A, const double* b, int32_t b_per_instance,
-                             const double* lb, const double* ub, int32_t bounds_per_instance, int32_t loc, void* stream);
+                             const int32_t* task_joint_ids, const double* A, int32_t A_per_instance, const double* b,
+                             int32_t b_per_instance, const double* lb, const double* ub, int32_t bounds_per_instance, int32_t loc,
+                             void* stream);
 /* Solve(q, c_id, Ai, bi)  (hpp:596-695): tailored / trajectory-tracking form: Reset(warm_start), ResetSolver,
- * UpdateEqConstraint(c_id, Ai, bi), FwdPassInit(q), main loop.  Ai [36] HOST; q [batch][nq], bi [batch][6]
- * (or [6] if !b_per_instance) at `loc`.  q == NULL keeps the device-resident configuration (see loik_integrate). */
-LOIK_API int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double* Ai, const double* bi,
-                             int32_t b_per_instance, int32_t loc, void* stream);
+ * UpdateEqConstraint(c_id, Ai, bi), FwdPassInit(q), main loop.  Ai [36] HOST, or [batch][36] at `loc` if A_per_instance
+ * (which must match loik_solve_init's); q [batch][nq], bi [batch][6] (or [6] if !b_per_instance) at `loc`.  q == NULL
+ * keeps the device-resident configuration (see loik_integrate). */
+LOIK_API int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double* Ai, int32_t A_per_instance,
+                             const double* bi, int32_t b_per_instance, int32_t loc, void* stream);
 
 /* Outer IK loop on the device (the step after the hot path; README.md:5 of the reference: "differential IK ... to be
  * integrated"): q <- pinocchio::integrate(model, q, dt * z) -- q + dt z for vector-space joints, the SO(2) update of the

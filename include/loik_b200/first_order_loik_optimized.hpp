@@ -53,13 +53,14 @@ class FirstOrderLoikOptimized {
   FirstOrderLoikOptimized(const FirstOrderLoikOptimized&) = delete;
   FirstOrderLoikOptimized& operator=(const FirstOrderLoikOptimized&) = delete;
 
-  // SolveInit(q, H_ref, v_ref, ids, Ais, bis, lb, ub)  (hpp:335-338).  q [batch][nq]; bis [batch][nc][6]; lb/ub [nv].
+  // SolveInit(q, H_ref, v_ref, ids, Ais, bis, lb, ub)  (hpp:335-338).  q [batch][nq]; Ais [nc][36] or [batch][nc][36];
+  // bis [batch][nc][6] or [nc][6]; lb/ub [nv].
   void SolveInit(const std::vector<double>& q, const std::vector<double>& H_ref, const std::vector<double>& v_ref,
                  const std::vector<int32_t>& active_task_constraint_ids, const std::vector<double>& Ais,
                  const std::vector<double>& bis, const std::vector<double>& lb, const std::vector<double>& ub) {
     validate(active_task_constraint_ids, Ais, bis, lb, ub);
     check(loik_solve_init(h_, q.data(), H_ref.data(), v_ref.data(), (int32_t)active_task_constraint_ids.size(),
-                          active_task_constraint_ids.data(), Ais.data(), bis.data(), per_instance(bis), lb.data(), ub.data(), 0,
+                          active_task_constraint_ids.data(), Ais.data(), a_per_instance(Ais, active_task_constraint_ids.size()), bis.data(), per_instance(bis), lb.data(), ub.data(), 0,
                           LOIK_HOST, stream_));
   }
   void Solve() { check(loik_solve(h_, stream_)); }  // hpp:368
@@ -68,13 +69,13 @@ class FirstOrderLoikOptimized {
              const std::vector<double>& bis, const std::vector<double>& lb, const std::vector<double>& ub) {  // hpp:475-478
     validate(active_task_constraint_ids, Ais, bis, lb, ub);
     check(loik_solve_full(h_, q.data(), H_ref.data(), v_ref.data(), (int32_t)active_task_constraint_ids.size(),
-                          active_task_constraint_ids.data(), Ais.data(), bis.data(), per_instance(bis), lb.data(), ub.data(), 0,
+                          active_task_constraint_ids.data(), Ais.data(), a_per_instance(Ais, active_task_constraint_ids.size()), bis.data(), per_instance(bis), lb.data(), ub.data(), 0,
                           LOIK_HOST, stream_));
   }
   // Solve(q, c_id, Ai, bi)  (hpp:596-597): bi [batch][6] or [6]
   void Solve(const std::vector<double>& q, int c_id, const std::vector<double>& Ai, const std::vector<double>& bi) {
-    check(loik_solve_task(h_, q.data(), c_id, Ai.data(), bi.data(), bi.size() == (size_t)batch_ * 6 && batch_ > 1 ? 1 : 0, LOIK_HOST,
-                          stream_));
+    check(loik_solve_task(h_, q.data(), c_id, Ai.data(), Ai.size() == (size_t)batch_ * 36 && batch_ > 1 ? 1 : 0, bi.data(),
+                          bi.size() == (size_t)batch_ * 6 && batch_ > 1 ? 1 : 0, LOIK_HOST, stream_));
   }
 
   // results: ik_id_data.z / nu / w / yis / vis / fis of the reference, batch-major
@@ -126,7 +127,8 @@ class FirstOrderLoikOptimized {
   // outer IK loop on the device: q <- integrate(q, dt z), then Solve(c_id, Ai, bi) on the device-resident q
   void Integrate(double dt) { check(loik_integrate(h_, dt, stream_)); }
   void Solve(int c_id, const std::vector<double>& Ai, const std::vector<double>& bi) {
-    check(loik_solve_task(h_, nullptr, c_id, Ai.data(), bi.data(), bi.size() == (size_t)batch_ * 6 && batch_ > 1 ? 1 : 0, LOIK_HOST, stream_));
+    check(loik_solve_task(h_, nullptr, c_id, Ai.data(), Ai.size() == (size_t)batch_ * 36 && batch_ > 1 ? 1 : 0, bi.data(),
+                          bi.size() == (size_t)batch_ * 6 && batch_ > 1 ? 1 : 0, LOIK_HOST, stream_));
   }
   std::vector<double> His() const { return get(LOIK_F_H, 36 * (model_.njoints - 1)); }   // after the per-step methods, or after Solve() with set_keep_workspace(true)
   std::vector<double> pis() const { return get(LOIK_F_P, 6 * (model_.njoints - 1)); }    // same
@@ -161,10 +163,12 @@ class FirstOrderLoikOptimized {
     if (rc != LOIK_OK) throw std::runtime_error(loik_last_error());
   }
   int per_instance(const std::vector<double>& bis) const { return bis.size() == (size_t)batch_ * nc_ * 6 && batch_ > 1 ? 1 : 0; }
+  // Ais [nc][36] shared by the batch, or [batch][nc][36]: every instance its own task matrices
+  int a_per_instance(const std::vector<double>& Ais, size_t n_ids) const { return Ais.size() == (size_t)batch_ * n_ids * 36 && batch_ > 1 ? 1 : 0; }
   void validate(const std::vector<int32_t>& ids, const std::vector<double>& Ais, const std::vector<double>& bis,
                 const std::vector<double>& lb, const std::vector<double>& ub) const {
     // ik-id-description-optimized.hpp:132-134, :328-335
-    if (Ais.size() != ids.size() * 36 || (bis.size() != ids.size() * 6 && bis.size() != (size_t)batch_ * ids.size() * 6))
+    if ((Ais.size() != ids.size() * 36 && Ais.size() != (size_t)batch_ * ids.size() * 36) || (bis.size() != ids.size() * 6 && bis.size() != (size_t)batch_ * ids.size() * 6))
       throw std::runtime_error("[IkProblemFormulation::UpdateEqConstraints]: task_constraint_ids, Ais, and bis have different size !!!");
     if (lb.size() != ub.size())
       throw std::runtime_error("[IkProblemFormulation::UpdateIneqConstraints]: lower bound and upper bound have different dimensions!!!");

@@ -147,7 +147,7 @@ class FirstOrderLoikOptimizedTpl {
                  const PINOCCHIO_ALIGNED_STD_VECTOR(Mat6x6)& Ais, const PINOCCHIO_ALIGNED_STD_VECTOR(Vec6)& bis, const DVec& lb,
                  const DVec& ub) {
     Problem pr(*this, q, H_ref, v_ref, active_task_constraint_ids, Ais, bis, lb, ub);
-    check(loik_solve_init(h_, pr.q.data(), pr.H.data(), pr.v.data(), (int32_t)pr.ids.size(), pr.ids.data(), pr.A.data(), pr.b.data(), 1,
+    check(loik_solve_init(h_, pr.q.data(), pr.H.data(), pr.v.data(), (int32_t)pr.ids.size(), pr.ids.data(), pr.A.data(), 0, pr.b.data(), 1,
                           pr.lb.data(), pr.ub.data(), 0, LOIK_HOST, stream_));
     write_back(false);
   }
@@ -160,7 +160,7 @@ class FirstOrderLoikOptimizedTpl {
   void Solve(const DVec& q, const Mat6x6& H_ref, const Motion& v_ref, const std::vector<Index>& active_task_constraint_ids,
              const PINOCCHIO_ALIGNED_STD_VECTOR(Mat6x6)& Ais, const PINOCCHIO_ALIGNED_STD_VECTOR(Vec6)& bis, const DVec& lb, const DVec& ub) {
     Problem pr(*this, q, H_ref, v_ref, active_task_constraint_ids, Ais, bis, lb, ub);
-    check(loik_solve_full(h_, pr.q.data(), pr.H.data(), pr.v.data(), (int32_t)pr.ids.size(), pr.ids.data(), pr.A.data(), pr.b.data(), 1,
+    check(loik_solve_full(h_, pr.q.data(), pr.H.data(), pr.v.data(), (int32_t)pr.ids.size(), pr.ids.data(), pr.A.data(), 0, pr.b.data(), 1,
                           pr.lb.data(), pr.ub.data(), 0, LOIK_HOST, stream_));
     write_back(true);
   }
@@ -169,7 +169,7 @@ class FirstOrderLoikOptimizedTpl {
     std::vector<double> qv(q.size()), A(36), b(6);
     for (int k = 0; k < (int)q.size(); ++k) qv[k] = q[k];
     for (int r = 0; r < 6; ++r) { b[r] = bi[r]; for (int c = 0; c < 6; ++c) A[6 * r + c] = Ai(r, c); }
-    check(loik_solve_task(h_, qv.data(), (int32_t)c_id, A.data(), b.data(), 1, LOIK_HOST, stream_));
+    check(loik_solve_task(h_, qv.data(), (int32_t)c_id, A.data(), 0, b.data(), 1, LOIK_HOST, stream_));
     write_back(true);
   }
   // hpp:168-186: iteration counter, flags, mu and the feasibility scalars; the primal / dual state is kept

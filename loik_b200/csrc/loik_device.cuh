@@ -28,7 +28,10 @@ constexpr int kMaxSeg = 16;   // chains of the tree that can be swept by differe
 constexpr int kMaxMd = 8;     // multi-DoF joints (free-flyer, spherical, translation) per model
 
 // status of an instance (per-instance loop control of Solve()/InfeasibilityTailSolve())
-enum : int { ST_RUNNING = 0, ST_TAIL = 1, ST_CONVERGED = 2, ST_INFEASIBLE_DONE = 3, ST_MAXITER = 4 };
+// ST_CONVERGED_PINF: converged_ with primal_infeasible_ raised in the same iteration -- the reference evaluates both
+// checks before it looks at either flag (hpp:421-432), stops on converged_ first and leaves primal_infeasible_ set for
+// get_primal_infeasibility_status() (0.03 % of a UR10-262 144 batch end this way)
+enum : int { ST_RUNNING = 0, ST_TAIL = 1, ST_CONVERGED = 2, ST_INFEASIBLE_DONE = 3, ST_MAXITER = 4, ST_CONVERGED_PINF = 5 };
 
 struct JointC {
   double plR[9], plp[3], axis[3];   // model.jointPlacements[i], joint axis
@@ -61,7 +64,9 @@ enum : int {  // rows of a joint block
   JR_H = 27, JR_P = 48, JR_UD = 54, JR_DINV = 60, JR_R = 61,                      // backward -> forward workspace (35 rows)
   JR_ROWS = 62
 };
-enum : int { TR_Y = 0, TR_ATY = 6, TR_B = 12, TR_ATB = 18, TR_ROWS = 24 };        // rows of a task block
+// rows of a task block: state y, Aty | per-instance problem data b, A^T b | per-instance task matrix A (row-major 6x6)
+// and A^T A (21 scalars: LL sym, LA, AA sym) when the batch does not share A (ModelC::a_per)
+enum : int { TR_Y = 0, TR_ATY = 6, TR_B = 12, TR_ATB = 18, TR_A = 24, TR_ATA = 60, TR_ROWS = 81 };
 enum : int { PR_H = 0, PR_F = 27, PR_ROWS = 33 };                                 // rows of a pending-accumulator block
 enum : int { GR_MU = 0, GR_BINF = 1, GR_CTL = 2, GR_RES = 3, GR_CARRY = 7, GR_NORMS = 21, GR_ROWS = 49 };  // globals (norms: 28 rows)
 
@@ -78,7 +83,7 @@ enum : int { FR_NU = 0, FR_Z = 6, FR_W = 12, FR_T = 18,   // state (24 rows)
 struct Offs {
   int glob, joint0, task0, pend0;  // first row of the globals, of joint 1, of task 0, of pending slot 0
   int ff0;                         // first row of the multi-DoF blocks (FR_ROWS each)
-  int prv, drv;                    // debug: primal / dual residual vectors (6 nb + nv rows each)
+  int prv, drv, drows;             // debug arena (StateP::dbg, allocated by loik_set_debug): primal / dual residual vectors (6 nb + nv rows each), rows per tile
   int rows;                        // rows per tile record
 };
 
@@ -96,9 +101,8 @@ struct ModelC {
   int max_iter, bounds_per_instance;
   int nseg, nblevel, nflevel, nwarp;
   int nmd, nv, nq, href_uniform;   // number of multi-DoF joints; model.nv, model.nq; every joint shares H_ref / v_ref (UpdateReference)
-  double mdlb[kMaxMd][6], mdub[kMaxMd][6];  // their bounds when shared by the batch
   SegC seg[kMaxSeg];
-  int nspan, pad1;
+  int nspan, a_per;                // a_per: A_k (and A_k^T A_k) differ per instance: rows TR_A / TR_ATA of the task blocks, not TaskC
   SpanC span[kMaxSpan];
   Offs off;
   double rho, mu0, mu_scale, tol_abs, tol_rel, tol_pinf, tol_dinf, tol_tail, Hv_inf;
@@ -133,6 +137,7 @@ struct StateP {
   double* home;
   int keep_ws;        // retiring instances also carry their backward->forward workspace home (loik_set_keep_workspace)
   int drop_ws;        // the forward sweep drops the consumed workspace lines from L2 (discard_workspace); never with keep_ws
+  double* dbg;        // debug mode only: tile records of the residual vectors (Offs::prv / drv rows, Offs::drows per tile), by home slot
 };
 
 // The batch-uniform block (model, problem constants, hyper-parameters) is passed to every kernel BY VALUE as a
@@ -154,8 +159,12 @@ LOIK_DEV void st_cs(double* P, int row, double x) { __stcs(P + row * 32, x); }
 // block base pointers: computed once per joint step, rows inside a block are immediates
 LOIK_DEV double* joint_blk(double* T, const Offs& O, int ji) { return T + (size_t)(O.joint0 + JR_ROWS * ji) * 32; }
 LOIK_DEV double* task_blk(double* T, const Offs& O, int k) { return T + (size_t)(O.task0 + TR_ROWS * k) * 32; }
+// task matrices: batch-shared (parameter block) or per instance (rows of the task block Pk)
+LOIK_DEV double task_A(const ModelC& M, const TaskC& K, const double* Pk, int i) { return M.a_per ? Pk[(TR_A + i) * 32] : K.A[i]; }
 LOIK_DEV double* pend_blk(double* T, const Offs& O, int k) { return T + (size_t)(O.pend0 + PR_ROWS * k) * 32; }
 LOIK_DEV double* glob_blk(double* T, const Offs& O) { return T + (size_t)O.glob * 32; }
+// this lane's record of the debug arena (instances never migrate in debug mode: slot = home slot)
+LOIK_DEV double* dbg_ptr(const StateP& S, const ModelC& c_model, int s) { return S.dbg ? S.dbg + ((size_t)(s >> 5) * c_model.off.drows) * 32 + (s & 31) : nullptr; }
 LOIK_DEV double* md_blk(double* T, const Offs& O, int m) { return T + (size_t)(O.ff0 + FR_ROWS * m) * 32; }
 __host__ __device__ __forceinline__ constexpr int s6(int i, int j) { return i <= j ? i * 6 - (i * (i - 1)) / 2 + (j - i) : j * 6 - (j * (j - 1)) / 2 + (i - j); }
 // Running inf-norms and the box projection are compare + select: sm_100a has no fp64 min/max instruction, and
@@ -485,10 +494,22 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, const double* Ts, double* Td
     A[0] += rho; A[3] += rho; A[5] += rho; D[0] += rho; D[3] += rho; D[5] += rho;
     if (J.task >= 0) {  // H_c += mu_eq AtA; p_c += Aty - mu_eq Atb (:327-330)
       const TaskC& K = c_model.t[J.task];
+      if (c_model.a_per) {  // per-instance A: A^T A from the task block (and, migrating, A and A^T A travel with the instance)
+        const double* Pk = task_blk(const_cast<double*>(Ts), O, J.task);
 #pragma unroll
-      for (int c = 0; c < 6; ++c) { A[c] += mu_eq * K.AtA_A[c]; D[c] += mu_eq * K.AtA_D[c]; }
+        for (int c = 0; c < 6; ++c) { A[c] += mu_eq * ld(Pk, TR_ATA + c); D[c] += mu_eq * ld(Pk, TR_ATA + 15 + c); }
 #pragma unroll
-      for (int c = 0; c < 9; ++c) B[c] += mu_eq * K.AtA_B[c];
+        for (int c = 0; c < 9; ++c) B[c] += mu_eq * ld(Pk, TR_ATA + 6 + c);
+        if (migrate) {
+          double* Pd = task_blk(Td, O, J.task);
+          for (int c = TR_A; c < TR_ROWS; ++c) st(Pd, c, ld(Pk, c));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { A[c] += mu_eq * K.AtA_A[c]; D[c] += mu_eq * K.AtA_D[c]; }
+#pragma unroll
+        for (int c = 0; c < 9; ++c) B[c] += mu_eq * K.AtA_B[c];
+      }
 #pragma unroll
       for (int c = 0; c < 6; ++c) p[c] += aty[c] - mu_eq * atb[c];
     }
@@ -572,7 +593,7 @@ LOIK_DEV void zero(Carry& cy) {
 // Accumulates into `cy` (the caller zeroes it once per iteration).
 template <bool DEBUG>
 LOIK_DEV void sweep_forward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, Carry& cy,
-                            const int lo, const int hi, const bool drop_ws = false) {
+                            const int lo, const int hi, const bool drop_ws = false, double* Dg = nullptr) {
   const Offs& O = c_model.off;
   const int nb = c_model.nb;
   const double inv_mu = 1.0 / mu;
@@ -670,7 +691,7 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, const double* Ts, double* Td,
     st(Pj, JR_NU, nu);
     st(Pj, JR_Z, z);
     st(Pj, JR_W, w_old + dw);
-    if (DEBUG) st(Td, O.prv + 6 * nb + J.idxv, rp);
+    if (DEBUG && Dg) st(Dg, O.prv + 6 * nb + J.idxv, rp);
     if (J.task >= 0) {  // DualUpdate for the task on this joint (:410-451)
       const TaskC& K = c_model.t[J.task];
       double* Pk = task_blk(Td, O, J.task);
@@ -681,7 +702,8 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, const double* Ts, double* Td,
       double plus = 0.0, minus = 0.0;
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
-        const double Av = K.A[6 * a] * v[0] + K.A[6 * a + 1] * v[1] + K.A[6 * a + 2] * v[2] + K.A[6 * a + 3] * v[3] + K.A[6 * a + 4] * v[4] + K.A[6 * a + 5] * v[5];
+        const double Av = task_A(c_model, K, Pk, 6 * a) * v[0] + task_A(c_model, K, Pk, 6 * a + 1) * v[1] + task_A(c_model, K, Pk, 6 * a + 2) * v[2] +
+                          task_A(c_model, K, Pk, 6 * a + 3) * v[3] + task_A(c_model, K, Pk, 6 * a + 4) * v[4] + task_A(c_model, K, Pk, 6 * a + 5) * v[5];
         const double e = Av - bk[a];       // Av_minus_b (:416)
         const double dy = mu_eq * e;       // delta_yis (:419)
         y[a] = yk[a] + dy;
@@ -690,7 +712,7 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, const double* Ts, double* Td,
         cy.pres_task = amax(cy.pres_task, e);
         plus += bk[a] * dmax(dy, 0.0);
         minus += bk[a] * dmin(dy, 0.0);
-        if (DEBUG) st(Td, O.prv + 6 * ji + a, e);
+        if (DEBUG && Dg) st(Dg, O.prv + 6 * ji + a, e);
       }
       cy.bTdy_p += plus;
       cy.bTdy_m += minus;
@@ -698,7 +720,8 @@ LOIK_DEV void sweep_forward(const ModelC& c_model, const double* Ts, double* Td,
       for (int a = 0; a < 6; ++a) {
         st(Pk, TR_Y + a, y[a]);
         // Aty = A^T y (:425)
-        st(Pk, TR_ATY + a, K.A[a] * y[0] + K.A[6 + a] * y[1] + K.A[12 + a] * y[2] + K.A[18 + a] * y[3] + K.A[24 + a] * y[4] + K.A[30 + a] * y[5]);
+        st(Pk, TR_ATY + a, task_A(c_model, K, Pk, a) * y[0] + task_A(c_model, K, Pk, 6 + a) * y[1] + task_A(c_model, K, Pk, 12 + a) * y[2] +
+                               task_A(c_model, K, Pk, 18 + a) * y[3] + task_A(c_model, K, Pk, 24 + a) * y[4] + task_A(c_model, K, Pk, 30 + a) * y[5]);
       }
     }
     if (drop_ws) discard_workspace(Pj);
@@ -717,7 +740,7 @@ struct Resid {
 LOIK_DEV void zero(Resid& rs) { rs.dres_v = rs.dres_nu = rs.Hrefv_inf = rs.F_inf = rs.T_inf = rs.dF_inf = rs.dT_inf = 0.0; }
 // Accumulates into `rs` (the caller zeroes it once per iteration and sets dres_nu = T_inf at the end, hxx:484).
 template <bool DEBUG>
-LOIK_DEV void sweep_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs, const int lo, const int hi) {
+LOIK_DEV void sweep_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs, const int lo, const int hi, double* Dg = nullptr) {
   const Offs& O = c_model.off;
   const int nb = c_model.nb;
   double cF[6];
@@ -790,10 +813,10 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, const double* Ts, double* Td
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       st_cs(Pj, JR_FD + c, F[c]);
-      if (DEBUG) st(Td, O.drv + 6 * ji + c, rd[c]);
+      if (DEBUG && Dg) st(Dg, O.drv + 6 * ji + c, rd[c]);
     }
     st_cs(Pj, JR_T, Tn);
-    if (DEBUG) st(Td, O.drv + 6 * nb + J.idxv, Tn);
+    if (DEBUG && Dg) st(Dg, O.drv + 6 * nb + J.idxv, Tn);
     have_carry = false;
     if (J.parent > 0) {  // fis_diff_plus_Aty[parent] += liMi.act(f_i) (:212)
       double R[9], t[3];
@@ -886,7 +909,7 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
     if (J.task >= 0) {
       const double* Pks = task_blk(const_cast<double*>(Ts), O, J.task);
       double* Pk = task_blk(Td, O, J.task);
-      for (int c = 0; c < 12; ++c) st(Pk, TR_B + c, ldc(Pks, TR_B + c));
+      for (int c = TR_B; c < (c_model.a_per ? TR_ROWS : TR_A); ++c) st(Pk, c, ldc(Pks, c));
     }
   }
 #pragma unroll
@@ -900,9 +923,12 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
     const TaskC& Kt = c_model.t[J.task];
     const double* Pk = task_blk(const_cast<double*>(Ts), O, J.task);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { A[c] += mu_eq * Kt.AtA_A[c]; D[c] += mu_eq * Kt.AtA_D[c]; p[c] += ld(Pk, TR_ATY + c) - mu_eq * ld(Pk, TR_ATB + c); }
+    for (int c = 0; c < 6; ++c) {
+      A[c] += mu_eq * (c_model.a_per ? ld(Pk, TR_ATA + c) : Kt.AtA_A[c]); D[c] += mu_eq * (c_model.a_per ? ld(Pk, TR_ATA + 15 + c) : Kt.AtA_D[c]);
+      p[c] += ld(Pk, TR_ATY + c) - mu_eq * ld(Pk, TR_ATB + c);
+    }
 #pragma unroll
-    for (int c = 0; c < 9; ++c) B[c] += mu_eq * Kt.AtA_B[c];
+    for (int c = 0; c < 9; ++c) B[c] += mu_eq * (c_model.a_per ? ld(Pk, TR_ATA + 6 + c) : Kt.AtA_B[c]);
   }
   for (int n = 0; n < J.npin; ++n) {
     const double* Pp = pend_blk(Td, O, J.pin[n]);
@@ -986,7 +1012,7 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
 }
 
 template <bool DEBUG, int K>
-LOIK_DEV_CALL void md_forward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, Carry& cy, const int i) {
+LOIK_DEV_CALL void md_forward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, Carry& cy, const int i, double* Dg) {
   const Offs& O = c_model.off;
   const JointC& J = c_model.j[i];
   const int nb = c_model.nb;
@@ -1050,8 +1076,7 @@ LOIK_DEV_CALL void md_forward(const ModelC& c_model, const double* Ts, double* T
   }
 #pragma unroll
   for (int c = 0; c < K; ++c) {
-    const double lb = c_model.bounds_per_instance ? ld(Pf, FR_LB + c) : c_model.mdlb[J.mblk][c];
-    const double ub = c_model.bounds_per_instance ? ld(Pf, FR_UB + c) : c_model.mdub[J.mblk][c];
+    const double lb = ld(Pf, FR_LB + c), ub = ld(Pf, FR_UB + c);  // (rows of the md block: per instance, or the shared bounds replicated by k_set_bounds)
     const double w_old = ld(Pfs, FR_W + c);
     cy.dnu_inf = amax(cy.dnu_inf, nu[c] - ld(Pfs, FR_NU + c));
     const double z = dmin(ub, dmax(lb, nu[c] + inv_mu * w_old));
@@ -1063,7 +1088,7 @@ LOIK_DEV_CALL void md_forward(const ModelC& c_model, const double* Ts, double* T
     cy.ubdw_p += ub * dmax(dw, 0.0);
     cy.lbdw_m += lb * dmin(dw, 0.0);
     st(Pf, FR_NU + c, nu[c]); st(Pf, FR_Z + c, z); st(Pf, FR_W + c, w_old + dw);
-    if (DEBUG) st(Td, O.prv + 6 * nb + J.idxv + c, rp);
+    if (DEBUG && Dg) st(Dg, O.prv + 6 * nb + J.idxv + c, rp);
   }
   if (J.task >= 0) {  // DualUpdate for a task on this joint (:410-451)
     const TaskC& Kt = c_model.t[J.task];
@@ -1072,24 +1097,26 @@ LOIK_DEV_CALL void md_forward(const ModelC& c_model, const double* Ts, double* T
     double y[6], plus = 0.0, minus = 0.0;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
-      const double Av = Kt.A[6 * a] * v[0] + Kt.A[6 * a + 1] * v[1] + Kt.A[6 * a + 2] * v[2] + Kt.A[6 * a + 3] * v[3] + Kt.A[6 * a + 4] * v[4] + Kt.A[6 * a + 5] * v[5];
+      const double Av = task_A(c_model, Kt, Pk, 6 * a) * v[0] + task_A(c_model, Kt, Pk, 6 * a + 1) * v[1] + task_A(c_model, Kt, Pk, 6 * a + 2) * v[2] +
+                        task_A(c_model, Kt, Pk, 6 * a + 3) * v[3] + task_A(c_model, Kt, Pk, 6 * a + 4) * v[4] + task_A(c_model, Kt, Pk, 6 * a + 5) * v[5];
       const double bi = ld(Pk, TR_B + a), e = Av - bi, dy = mu_eq * e;
       y[a] = ld(Pks, TR_Y + a) + dy;
       cy.dyis_inf = amax(cy.dyis_inf, dy); cy.Av_inf = amax(cy.Av_inf, Av); cy.pres_task = amax(cy.pres_task, e);
       plus += bi * dmax(dy, 0.0); minus += bi * dmin(dy, 0.0);
-      if (DEBUG) st(Td, O.prv + 6 * (i - 1) + a, e);
+      if (DEBUG && Dg) st(Dg, O.prv + 6 * (i - 1) + a, e);
     }
     cy.bTdy_p += plus; cy.bTdy_m += minus;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
       st(Pk, TR_Y + a, y[a]);
-      st(Pk, TR_ATY + a, Kt.A[a] * y[0] + Kt.A[6 + a] * y[1] + Kt.A[12 + a] * y[2] + Kt.A[18 + a] * y[3] + Kt.A[24 + a] * y[4] + Kt.A[30 + a] * y[5]);
+      st(Pk, TR_ATY + a, task_A(c_model, Kt, Pk, a) * y[0] + task_A(c_model, Kt, Pk, 6 + a) * y[1] + task_A(c_model, Kt, Pk, 12 + a) * y[2] +
+                             task_A(c_model, Kt, Pk, 18 + a) * y[3] + task_A(c_model, Kt, Pk, 24 + a) * y[4] + task_A(c_model, Kt, Pk, 30 + a) * y[5]);
     }
   }
 }
 
 template <bool DEBUG, int K>
-LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs, const int i) {
+LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs, const int i, double* Dg) {
   const Offs& O = c_model.off;
   const JointC& J = c_model.j[i];
   const int nb = c_model.nb;
@@ -1128,7 +1155,7 @@ LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* 
     const double rd = Hrv[c] - J.Hv[c] + F[c];
     rs.dres_v = amax(rs.dres_v, rd);
     st(Pj, JR_FD + c, F[c]);
-    if (DEBUG) st(Td, O.drv + 6 * (i - 1) + c, rd);
+    if (DEBUG && Dg) st(Dg, O.drv + 6 * (i - 1) + c, rd);
   }
 #pragma unroll
   for (int c = 0; c < K; ++c) {
@@ -1136,7 +1163,7 @@ LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* 
     rs.T_inf = amax(rs.T_inf, Tn);
     rs.dT_inf = amax(rs.dT_inf, Tn - ld(Pfs, FR_T + c));
     st(Pf, FR_T + c, Tn);
-    if (DEBUG) st(Td, O.drv + 6 * nb + J.idxv + c, Tn);
+    if (DEBUG && Dg) st(Dg, O.drv + 6 * nb + J.idxv + c, Tn);
   }
   if (J.parent > 0) {  // fis_diff_plus_Aty[parent] += liMi.act(f_i) (:212)
     double R[9], t[3], cF[6];
@@ -1159,21 +1186,21 @@ LOIK_DEV void span_backward(const ModelC& c_model, const double* Ts, double* Td,
 }
 template <bool DEBUG>
 LOIK_DEV void span_forward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, Carry& cy,
-                           const int lo, const int hi, const bool drop_ws = false) {
+                           const int lo, const int hi, const bool drop_ws = false, double* Dg = nullptr) {
   const int k = c_model.j[lo].nvj;
-  if (k == 1) { sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, lo, hi, drop_ws); return; }
+  if (k == 1) { sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, lo, hi, drop_ws, Dg); return; }
   Carry tmp = cy;
-  if (k == 3) md_forward<DEBUG, 3>(c_model, Ts, Td, mu, mu_eq, tmp, lo);
-  else md_forward<DEBUG, 6>(c_model, Ts, Td, mu, mu_eq, tmp, lo);
+  if (k == 3) md_forward<DEBUG, 3>(c_model, Ts, Td, mu, mu_eq, tmp, lo, Dg);
+  else md_forward<DEBUG, 6>(c_model, Ts, Td, mu, mu_eq, tmp, lo, Dg);
   cy = tmp;
 }
 template <bool DEBUG>
-LOIK_DEV void span_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs, const int lo, const int hi) {
+LOIK_DEV void span_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs, const int lo, const int hi, double* Dg = nullptr) {
   const int k = c_model.j[lo].nvj;
-  if (k == 1) { sweep_residual<DEBUG>(c_model, Ts, Td, rs, lo, hi); return; }
+  if (k == 1) { sweep_residual<DEBUG>(c_model, Ts, Td, rs, lo, hi, Dg); return; }
   Resid tmp = rs;
-  if (k == 3) md_residual<DEBUG, 3>(c_model, Ts, Td, tmp, lo);
-  else md_residual<DEBUG, 6>(c_model, Ts, Td, tmp, lo);
+  if (k == 3) md_residual<DEBUG, 3>(c_model, Ts, Td, tmp, lo, Dg);
+  else md_residual<DEBUG, 6>(c_model, Ts, Td, tmp, lo, Dg);
   rs = tmp;
 }
 
@@ -1220,7 +1247,7 @@ LOIK_DEV int decide_core(const ModelC& M, const int status, const int it, const 
     if (fixed) {
       if (pres > 10 * dres) mu *= 10; else if (dres > 10 * pres) mu *= 0.1;
     } else if (converged) {
-      ns = ST_CONVERGED;
+      ns = infeasible ? ST_CONVERGED_PINF : ST_CONVERGED;
     } else if (infeasible) {
       // entering InfeasibilityTailSolve: first evaluation of its while-condition (hpp:275-284)
       if (dx >= M.tol_tail || cy.dz_inf >= M.tol_tail) ns = (it >= M.max_iter) ? ST_INFEASIBLE_DONE : ST_TAIL;
@@ -1297,8 +1324,11 @@ LOIK_DEV void fine_fwdpass1(const ModelC& M, double* __restrict__ T, const doubl
     if (J.task >= 0) {
       const TaskC& K = M.t[J.task];
       const double* Pk = task_blk(T, O, J.task);
-      for (int c = 0; c < 6; ++c) { A[c] += mu_eq * K.AtA_A[c]; D[c] += mu_eq * K.AtA_D[c]; p[c] += ld(Pk, TR_ATY + c) - mu_eq * ld(Pk, TR_ATB + c); }
-      for (int c = 0; c < 9; ++c) B[c] += mu_eq * K.AtA_B[c];
+      for (int c = 0; c < 6; ++c) {
+        A[c] += mu_eq * (M.a_per ? ld(Pk, TR_ATA + c) : K.AtA_A[c]); D[c] += mu_eq * (M.a_per ? ld(Pk, TR_ATA + 15 + c) : K.AtA_D[c]);
+        p[c] += ld(Pk, TR_ATY + c) - mu_eq * ld(Pk, TR_ATB + c);
+      }
+      for (int c = 0; c < 9; ++c) B[c] += mu_eq * (M.a_per ? ld(Pk, TR_ATA + 6 + c) : K.AtA_B[c]);
     }
     const double r0 = ld(Pj, JR_W) - mu * ld(Pj, JR_Z);
     for (int c = 0; c < 6; ++c) { st(Pj, JR_H + c, A[c]); st(Pj, JR_H + 15 + c, D[c]); st(Pj, JR_P + c, p[c]); }
@@ -1347,7 +1377,7 @@ LOIK_DEV void fine_fwdpass2(const ModelC& M, double* __restrict__ T) {
   st(G, GR_NORMS + N_DVIS, dvis); st(G, GR_NORMS + N_DNU, dnu);
 }
 // BoxProj (hxx:384-397)
-LOIK_DEV void fine_boxproj(const ModelC& M, double* __restrict__ T, const double mu) {
+LOIK_DEV void fine_boxproj(const ModelC& M, double* __restrict__ T, const double mu, double* Dg) {
   const Offs& O = M.off;
   double* G = glob_blk(T, O);
   double dz = 0.0, slack = 0.0;
@@ -1360,13 +1390,13 @@ LOIK_DEV void fine_boxproj(const ModelC& M, double* __restrict__ T, const double
     dz = amax(dz, z - ld(Pj, JR_Z));
     slack = amax(slack, nu - z);
     st(Pj, JR_Z, z);
-    st(T, O.prv + 6 * M.nb + J.idxv, nu - z);
+    if (Dg) st(Dg, O.prv + 6 * M.nb + J.idxv, nu - z);
   }
   st(G, GR_NORMS + N_DZ, dz);
   st(G, GR_NORMS + N_PRES_SLACK, slack);
 }
 // DualUpdate (hxx:404-461)
-LOIK_DEV void fine_dualupdate(const ModelC& M, double* __restrict__ T, const double mu, const double mu_eq) {
+LOIK_DEV void fine_dualupdate(const ModelC& M, double* __restrict__ T, const double mu, const double mu_eq, double* Dg) {
   const Offs& O = M.off;
   double* G = glob_blk(T, O);
   double dyis = ld(G, GR_NORMS + N_DYIS), Av_inf = ld(G, GR_NORMS + N_AV), bp = ld(G, GR_NORMS + N_BTDY_P), bm = ld(G, GR_NORMS + N_BTDY_M);
@@ -1378,17 +1408,19 @@ LOIK_DEV void fine_dualupdate(const ModelC& M, double* __restrict__ T, const dou
     double v[6], y[6], plus = 0.0, minus = 0.0;
     for (int c = 0; c < 6; ++c) v[c] = ld(Pj, JR_V + c);
     for (int a = 0; a < 6; ++a) {
-      const double Av = K.A[6 * a] * v[0] + K.A[6 * a + 1] * v[1] + K.A[6 * a + 2] * v[2] + K.A[6 * a + 3] * v[3] + K.A[6 * a + 4] * v[4] + K.A[6 * a + 5] * v[5];
+      const double Av = task_A(M, K, Pk, 6 * a) * v[0] + task_A(M, K, Pk, 6 * a + 1) * v[1] + task_A(M, K, Pk, 6 * a + 2) * v[2] +
+                        task_A(M, K, Pk, 6 * a + 3) * v[3] + task_A(M, K, Pk, 6 * a + 4) * v[4] + task_A(M, K, Pk, 6 * a + 5) * v[5];
       const double bi = ld(Pk, TR_B + a), e = Av - bi, dy = mu_eq * e;
       y[a] = ld(Pk, TR_Y + a) + dy;
       dyis = amax(dyis, dy); Av_inf = amax(Av_inf, Av); ptask = amax(ptask, e);
       plus += bi * dmax(dy, 0.0); minus += bi * dmin(dy, 0.0);
-      st(T, O.prv + 6 * (K.joint - 1) + a, e);
+      if (Dg) st(Dg, O.prv + 6 * (K.joint - 1) + a, e);
     }
     bp += plus; bm += minus;
     for (int a = 0; a < 6; ++a) {
       st(Pk, TR_Y + a, y[a]);
-      st(Pk, TR_ATY + a, K.A[a] * y[0] + K.A[6 + a] * y[1] + K.A[12 + a] * y[2] + K.A[18 + a] * y[3] + K.A[24 + a] * y[4] + K.A[30 + a] * y[5]);
+      st(Pk, TR_ATY + a, task_A(M, K, Pk, a) * y[0] + task_A(M, K, Pk, 6 + a) * y[1] + task_A(M, K, Pk, 12 + a) * y[2] + task_A(M, K, Pk, 18 + a) * y[3] +
+                             task_A(M, K, Pk, 24 + a) * y[4] + task_A(M, K, Pk, 30 + a) * y[5]);
     }
   }
   double dw_inf = 0.0, ubdw = 0.0, lbdw = 0.0;
@@ -1406,12 +1438,12 @@ LOIK_DEV void fine_dualupdate(const ModelC& M, double* __restrict__ T, const dou
   st(G, GR_CARRY + 10, ubdw); st(G, GR_CARRY + 11, lbdw);
 }
 // ComputeResiduals (hxx:529-533)
-LOIK_DEV void fine_compute_residuals(const ModelC& M, double* __restrict__ T) {
+LOIK_DEV void fine_compute_residuals(const ModelC& M, double* __restrict__ T, double* Dg) {
   double* G = glob_blk(T, M.off);
   st(G, GR_RES + 0, dmax(ld(G, GR_NORMS + N_PRES_TASK), ld(G, GR_NORMS + N_PRES_SLACK)));
   Resid rs;
   zero(rs);
-  sweep_residual<true>(M, T, T, rs, 1, M.nb);
+  sweep_residual<true>(M, T, T, rs, 1, M.nb, Dg);
   st(G, GR_NORMS + N_F, rs.F_inf); st(G, GR_NORMS + N_T, rs.T_inf); st(G, GR_NORMS + N_DF, rs.dF_inf); st(G, GR_NORMS + N_DT, rs.dT_inf);
   st(G, GR_NORMS + N_DRES_V, rs.dres_v); st(G, GR_NORMS + N_DRES_NU, rs.T_inf);
   st(G, GR_RES + 1, dmax(rs.dres_v, rs.T_inf));

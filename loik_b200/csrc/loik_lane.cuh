@@ -42,7 +42,7 @@ enum : int { LJ_V = 0, LJ_F = 6, LJ_FD = 12, LJ_NU = 18, LJ_Z = 19, LJ_W = 20, L
              LJ_UB = 25, LJ_COPY = 26, LJ_DINV = 26, LJ_R = 27, LJ_UD = 28, LJ_HP = 36, LJ_XF = 84, LJ_ROWS = 96 };  // XF: liMi = (R 9, t 3)
 static_assert((int)LJ_V == (int)JR_V && (int)LJ_F == (int)JR_F && (int)LJ_FD == (int)JR_FD && (int)LJ_NU == (int)JR_NU && (int)LJ_Z == (int)JR_Z && (int)LJ_W == (int)JR_W && (int)LJ_T == (int)JR_T &&
               (int)LJ_SQ == (int)JR_JQ && (int)LJ_LB == (int)JR_LB && (int)LJ_UB == (int)JR_UB, "the copied part of a joint record mirrors the tile rows");
-enum : int { LT_Y = TR_Y, LT_ATY = TR_ATY, LT_B = TR_B, LT_ATB = TR_ATB, LT_ROWS = TR_ROWS };
+enum : int { LT_Y = TR_Y, LT_ATY = TR_ATY, LT_B = TR_B, LT_ATB = TR_ATB, LT_ROWS = 24 };  // (the tile's task block also holds per-instance A, A^T A)
 enum : int { LP_HP = 0, LP_F = 48, LP_ROWS = 56 };       // pending block of a tree edge: [H | p] contribution, F contribution
 enum : int { LX_V = 0, LX_T = 16, LX_ROWS = 96 };        // exchange scratch: 16 scalars, 8 rows of 10 (transposes)
 // ---- per-CTA constants in shared memory ---------------------------------------------------------------------------
@@ -52,14 +52,15 @@ enum : int { CT_AR = 0, CT_ATR = 48, CT_ATA = 96, CT_ROWS = 144 };  // per task:
 enum : int { GC_STRIDE = 24, GC_TOT = 96, GC_ROWS = 120 };  // GPI = 4: the groups' partial norms (4 x 24) and their combination (24)
 
 struct LaneDims {
-  int joint0, task0, pend0, xch, gc, stride;  // offsets inside an instance record, record stride
+  int joint0, task0, tmat0, pend0, xch, gc, stride;  // offsets inside an instance record, record stride
   int ctask0, csize, cpad;                    // constants: first task block, size, size padded to 128 B
 };
-__host__ __device__ inline LaneDims lane_dims(const int nb, const int nc, const int npend, const int href_uniform, const int gpi) {
+__host__ __device__ inline LaneDims lane_dims(const int nb, const int nc, const int npend, const int href_uniform, const int gpi, const int a_per) {
   LaneDims D;
   D.joint0 = LS_ROWS;
   D.task0 = D.joint0 + LJ_ROWS * nb;
-  D.pend0 = D.task0 + LT_ROWS * nc;
+  D.tmat0 = D.task0 + LT_ROWS * nc;          // per-instance task matrices (A, A^T, A^T A as in the constants), if any
+  D.pend0 = D.tmat0 + (a_per ? CT_ROWS * nc : 0);
   D.xch = D.pend0 + LP_ROWS * npend;
   D.gc = D.xch + LX_ROWS * gpi;  // (one exchange scratch per group)
   int sz = (D.gc + (gpi > 1 ? GC_ROWS : 0) + 7) & ~7;
@@ -122,9 +123,23 @@ LOIK_DEV void lane_load(const ModelC& M, const LaneDims& D, const double* T, dou
     else I[D.joint0 + LJ_ROWS * j + r] = buf[u];
   });
   lane_copy_rows<8>(LT_ROWS * M.nc, l, nl, [&](const int e, const int phase, const int u) {
-    if (phase == 0) buf[u] = __ldcs(T + (size_t)(O.task0 + e) * 32);
+    const int k = e / LT_ROWS, r = e - LT_ROWS * k;
+    if (phase == 0) buf[u] = __ldcs(T + (size_t)(O.task0 + TR_ROWS * k + r) * 32);
     else I[D.task0 + e] = buf[u];
   });
+  if (M.a_per) {  // per-instance task matrices: A (36 rows) and the packed A^T A (21 rows) -> the [6][8] blocks of the constants' layout
+    for (int e = l; e < CT_ROWS * M.nc; e += nl) {
+      const int k = e / CT_ROWS, o = e - CT_ROWS * k, blk = o / 48, r = (o - 48 * blk) >> 3, c = o & 7;
+      const double* Pk = T + (size_t)(O.task0 + TR_ROWS * k) * 32;
+      double x = 0.0;
+      if (c < 6) {
+        if (blk == 0) x = ld(Pk, TR_A + 6 * r + c);
+        else if (blk == 1) x = ld(Pk, TR_A + 6 * c + r);
+        else x = ld(Pk, TR_ATA + (r < 3 ? (c < 3 ? si(r, c) : 6 + 3 * r + (c - 3)) : (c < 3 ? 6 + 3 * c + (r - 3) : 15 + si(r - 3, c - 3))));
+      }
+      I[D.tmat0 + e] = x;
+    }
+  }
   if (l < 7) {
     const int row = l == 0 ? GR_MU : (l == 1 ? GR_BINF : (l == 2 ? GR_CTL : GR_RES + (l - 3)));
     const int dst = l == 0 ? LS_MU : (l == 1 ? LS_BINF : (l == 2 ? LS_CTL : LS_RES + (l - 3)));
@@ -212,7 +227,7 @@ LOIK_DEV void lane_backward(const ModelC& M, const LaneDims& D, const double* CB
 #pragma unroll
     for (int r = 0; r < 6; ++r) col[r] = fma(facv, vold[r], Cj[CJ_HREFR + 8 * r]);
     if (J.task >= 0) {  // H_c += mu_eq AtA; p_c += Aty - mu_eq Atb (:327-330)
-      const double* Ck = CB + D.ctask0 + CT_ROWS * J.task;
+      const double* Ck = M.a_per ? I + D.tmat0 + CT_ROWS * J.task : CB + D.ctask0 + CT_ROWS * J.task;
       const double* Pk = I + D.task0 + LT_ROWS * J.task;
       double aty[6], atb[6];
       lds6(Pk + LT_ATY, aty);
@@ -371,7 +386,7 @@ LOIK_DEV void lane_forward(const ModelC& M, const LaneDims& D, const double* CB,
     *reinterpret_cast<double2*>(Pj + LJ_NU) = make_double2(nu, z);
     Pj[LJ_W] = w_old + dw;
     if (J.task >= 0) {  // DualUpdate for the task on this joint (:410-451)
-      const double* Ck = CB + D.ctask0 + CT_ROWS * J.task;
+      const double* Ck = M.a_per ? I + D.tmat0 + CT_ROWS * J.task : CB + D.ctask0 + CT_ROWS * J.task;
       double* Pk = I + D.task0 + LT_ROWS * J.task;
       const double Av = Ck[CT_ATR + lc] * v[0] + Ck[CT_ATR + 8 + lc] * v[1] + Ck[CT_ATR + 16 + lc] * v[2] + Ck[CT_ATR + 24 + lc] * v[3] +
                         Ck[CT_ATR + 32 + lc] * v[4] + Ck[CT_ATR + 40 + lc] * v[5];
@@ -470,7 +485,7 @@ template <int GPI>
 __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ ModelC c_model, const LaneP P) {
   extern __shared__ __align__(16) double lsm[];
   const ModelC& M = c_model;
-  const LaneDims D = lane_dims(M.nb, M.nc, M.npend, M.href_uniform, GPI);
+  const LaneDims D = lane_dims(M.nb, M.nc, M.npend, M.href_uniform, GPI, M.a_per);
   double* CB = lsm;
   for (int e = threadIdx.x; e < D.csize; e += blockDim.x) {
     double x = 0.0;

@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kBlock) __maxnreg__(MINB <= 4 ? 255 : (65536 /
     const double* Ts = MIG ? tile_ptr(S, c_model, s) : Td;
     const int2 ctl = ld_ctl(c_model, Ts);
     int status = ctl.x;
+    double* Dg = DEBUG ? dbg_ptr(S, c_model, s) : nullptr;  // (debug mode runs in place: s is the home slot)
     if (status < ST_CONVERGED) {
       int it = ctl.y;
       double mu = ld(glob_blk(const_cast<double*>(Ts), c_model.off), GR_MU);
@@ -146,13 +147,13 @@ __global__ void __launch_bounds__(kBlock) __maxnreg__(MINB <= 4 ? 255 : (65536 /
         zero(rs);
         if (MD) {
           for (int g = c_model.nspan - 1; g >= 0; --g) span_backward(c_model, Ts, Td, mu, mu_eq, c_model.span[g].lo, c_model.span[g].hi, migrate);
-          for (int g = 0; g < c_model.nspan; ++g) span_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, c_model.span[g].lo, c_model.span[g].hi, drop_ws);
-          for (int g = c_model.nspan - 1; g >= 0; --g) span_residual<DEBUG>(c_model, Ts, Td, rs, c_model.span[g].lo, c_model.span[g].hi);
+          for (int g = 0; g < c_model.nspan; ++g) span_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, c_model.span[g].lo, c_model.span[g].hi, drop_ws, Dg);
+          for (int g = c_model.nspan - 1; g >= 0; --g) span_residual<DEBUG>(c_model, Ts, Td, rs, c_model.span[g].lo, c_model.span[g].hi, Dg);
         } else {
           const int nb = c_model.nb;
           sweep_backward(c_model, Ts, Td, mu, mu_eq, 1, nb, migrate);
-          sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, 1, nb, drop_ws);
-          sweep_residual<DEBUG>(c_model, Ts, Td, rs, 1, nb);
+          sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, 1, nb, drop_ws, Dg);
+          sweep_residual<DEBUG>(c_model, Ts, Td, rs, 1, nb, Dg);
         }
         status = decide<DEBUG>(c_model, Td, status, it, fixed != 0, cy, rs, mu);
         Ts = Td; migrate = false;
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(kBlock) k_step_forward(const __grid_constant__
   const double mu = ld(G, GR_MU);
   Carry cy;
   zero(cy);
-  for (int g = 0; g < c_model.nspan; ++g) span_forward<true>(c_model, T, T, mu, c_model.mu_scale * mu, cy, c_model.span[g].lo, c_model.span[g].hi);
+  for (int g = 0; g < c_model.nspan; ++g) span_forward<true>(c_model, T, T, mu, c_model.mu_scale * mu, cy, c_model.span[g].lo, c_model.span[g].hi, false, dbg_ptr(S, c_model, s));
   const double* c = reinterpret_cast<const double*>(&cy);
   for (int k = 0; k < kCarryRows; ++k) st(G, GR_CARRY + k, c[k]);
   // ComputePrimalResiduals (hxx:494-503)
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(kBlock) k_step_residual(const __grid_constant_
   for (int k = 0; k < kCarryRows; ++k) c[k] = ld(G, GR_CARRY + k);
   Resid rs;
   zero(rs);
-  for (int g = c_model.nspan - 1; g >= 0; --g) span_residual<true>(c_model, T, T, rs, c_model.span[g].lo, c_model.span[g].hi);
+  for (int g = c_model.nspan - 1; g >= 0; --g) span_residual<true>(c_model, T, T, rs, c_model.span[g].lo, c_model.span[g].hi, dbg_ptr(S, c_model, s));
   double mu = ld(G, GR_MU);
   const int it = ctl.y + 1;
   status = decide<true>(c_model, T, status, it, fixed != 0, cy, rs, mu);
@@ -389,9 +390,9 @@ __global__ void __launch_bounds__(kBlock) k_fine(const __grid_constant__ ModelC 
     case LOIK_STEP_FWD_PASS1: fine_fwdpass1(c_model, T, mu, mu_eq); break;
     case LOIK_STEP_BWD_PASS: sweep_backward(c_model, T, T, mu, mu_eq, 1, c_model.nb); break;
     case LOIK_STEP_FWD_PASS2: fine_fwdpass2(c_model, T); break;
-    case LOIK_STEP_BOX_PROJ: fine_boxproj(c_model, T, mu); break;
-    case LOIK_STEP_DUAL_UPDATE: fine_dualupdate(c_model, T, mu, mu_eq); break;
-    case LOIK_STEP_COMPUTE_RESIDUALS: fine_compute_residuals(c_model, T); break;
+    case LOIK_STEP_BOX_PROJ: fine_boxproj(c_model, T, mu, dbg_ptr(S, c_model, s)); break;
+    case LOIK_STEP_DUAL_UPDATE: fine_dualupdate(c_model, T, mu, mu_eq, dbg_ptr(S, c_model, s)); break;
+    case LOIK_STEP_COMPUTE_RESIDUALS: fine_compute_residuals(c_model, T, dbg_ptr(S, c_model, s)); break;
     case LOIK_STEP_CHECK_CONVERGENCE: fine_check_convergence(c_model, T); break;
     case LOIK_STEP_CHECK_FEASIBILITY: fine_check_feasibility(c_model, T); break;
     case LOIK_STEP_UPDATE_MU: fine_update_mu(c_model, T); break;
@@ -578,9 +579,11 @@ __global__ void __launch_bounds__(128) k_integrate(const __grid_constant__ Model
   }
 }
 
-// UpdateEqConstraints (ik-id-description-optimized.hpp:127-171), per-instance part: b, Atb = A^T b, |b|inf.
-// task < 0: all tasks, bis_inf_norm reset; task >= 0: UpdateEqConstraint for that slot (:178-218), norm only grows.
-__global__ void k_set_b(const __grid_constant__ ModelC c_model, const StateP S, const double* __restrict__ b, const int per_instance, const int task) {
+// UpdateEqConstraints (ik-id-description-optimized.hpp:127-171), per-instance part: b, Atb = A^T b, |b|inf, and -- when the
+// batch does not share the task matrices (Ain != nullptr: [n][nc][36], or [n][36] for one task) -- A and AtA = A^T A
+// (:162).  task < 0: all tasks, bis_inf_norm reset; task >= 0: UpdateEqConstraint for that slot (:178-218), norm only grows.
+__global__ void k_set_b(const __grid_constant__ ModelC c_model, const StateP S, const double* __restrict__ b, const int per_instance, const int task,
+                        const double* __restrict__ Ain) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
   double* T = tile_ptr(S, c_model, s);
@@ -590,48 +593,68 @@ __global__ void k_set_b(const __grid_constant__ ModelC c_model, const StateP S, 
   double binf = task < 0 ? 0.0 : ld(G, GR_BINF);
   const int k0 = task < 0 ? 0 : task, k1 = task < 0 ? nc : task + 1;
   for (int k = k0; k < k1; ++k) {
+    double* Pk = task_blk(T, O, k);
     double bk[6];
     for (int a = 0; a < 6; ++a) {
       const size_t src = task < 0 ? (per_instance ? ((size_t)s * nc + k) * 6 + a : (size_t)k * 6 + a)
                                   : (per_instance ? (size_t)s * 6 + a : (size_t)a);
       bk[a] = b[src];
-      st(task_blk(T, O, k), TR_B + a, bk[a]);
+      st(Pk, TR_B + a, bk[a]);
       binf = fmax(binf, fabs(bk[a]));
     }
-    const double* A = c_model.t[k].A;
+    if (Ain) {
+      const double* As = Ain + (task < 0 ? ((size_t)s * nc + k) * 36 : (size_t)s * 36);
+      for (int i = 0; i < 36; ++i) st(Pk, TR_A + i, As[i]);
+      for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 6; ++j) {
+          double acc = 0.0;
+          for (int r = 0; r < 6; ++r) acc += As[6 * r + i] * As[6 * r + j];  // (same order as the host's A^T A of the shared case)
+          // packed like TaskC: LL (sym, 6), LA (9), AA (sym, 6)
+          if (j < 3) st(Pk, TR_ATA + si(i, j), acc);
+          else if (i >= 3) st(Pk, TR_ATA + 15 + si(i - 3, j - 3), acc);
+          else st(Pk, TR_ATA + 6 + 3 * i + (j - 3), acc);
+        }
+    }
     for (int a = 0; a < 6; ++a) {
       double acc = 0.0;
-      for (int r = 0; r < 6; ++r) acc += A[6 * r + a] * bk[r];
-      st(task_blk(T, O, k), TR_ATB + a, acc);
+      for (int r = 0; r < 6; ++r) acc += task_A(c_model, c_model.t[k], Pk, 6 * r + a) * bk[r];
+      st(Pk, TR_ATB + a, acc);
     }
   }
   st(G, GR_BINF, binf);
 }
 
-__global__ void k_set_bounds(const __grid_constant__ ModelC c_model, const StateP S, const double* __restrict__ lb, const double* __restrict__ ub) {
+// UpdateIneqConstraints (ik-id-description-optimized.hpp:325-339), per-instance part: lb / ub [n][nv] (per_instance), or the
+// batch-shared [nv] replicated into the rows of the multi-DoF joints (their bounds are always read from rows; the shared
+// bounds of 1-DoF joints travel in the parameter block)
+__global__ void k_set_bounds(const __grid_constant__ ModelC c_model, const StateP S, const double* __restrict__ lb, const double* __restrict__ ub,
+                             const int per_instance) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
   double* T = tile_ptr(S, c_model, s);
   const int nb = c_model.nb, nv = c_model.nv;
+  const size_t o = per_instance ? (size_t)s * nv : 0;
   for (int i = 1; i <= nb; ++i) {
     if (c_model.j[i].nvj > 1) {
       double* Pf = md_blk(T, c_model.off, c_model.j[i].mblk);
-      for (int c = 0; c < c_model.j[i].nvj; ++c) { st(Pf, FR_LB + c, lb[(size_t)s * nv + c_model.j[i].idxv + c]); st(Pf, FR_UB + c, ub[(size_t)s * nv + c_model.j[i].idxv + c]); }
+      for (int c = 0; c < c_model.j[i].nvj; ++c) { st(Pf, FR_LB + c, lb[o + c_model.j[i].idxv + c]); st(Pf, FR_UB + c, ub[o + c_model.j[i].idxv + c]); }
       continue;
     }
+    if (!per_instance) continue;
     double* Pj = joint_blk(T, c_model.off, i - 1);
-    st(Pj, JR_LB, lb[(size_t)s * nv + c_model.j[i].idxv]);
-    st(Pj, JR_UB, ub[(size_t)s * nv + c_model.j[i].idxv]);
+    st(Pj, JR_LB, lb[o + c_model.j[i].idxv]);
+    st(Pj, JR_UB, ub[o + c_model.j[i].idxv]);
   }
 }
 
 // batch-major gather of `nrows` rows: dst[s][k] = tile(s)[map[k]][lane(s)]  (map = absolute row indices).
+// (`base` / `tile_rows`: the arena and its rows per tile -- the state arena, or the debug arena for the residual vectors)
 __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ ModelC c_model, const StateP S, const int nrows, const int* __restrict__ map,
-                                                double* __restrict__ dst) {
+                                                double* __restrict__ dst, const double* __restrict__ base, const int tile_rows) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)S.n * nrows) return;
   const int s = (int)(idx / nrows), k = (int)(idx % nrows);
-  dst[idx] = map[k] < 0 ? 0.0 : tile_ptr(S, c_model, s)[(size_t)map[k] * 32];
+  dst[idx] = map[k] < 0 ? 0.0 : base[((size_t)(s >> 5) * tile_rows + map[k]) * 32 + (s & 31)];
 }
 __global__ void k_gather_limi(const __grid_constant__ ModelC c_model, const StateP S, double* __restrict__ dst) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -655,14 +678,15 @@ __global__ void k_gather_ctl(const __grid_constant__ ModelC c_model, const State
   const int2 c = ld_ctl(c_model, tile_ptr(S, c_model, s));
   const int stt = c.x;
   dst[s] = which == 0 ? c.y
-                      : ((stt == ST_CONVERGED ? 1 : 0) | ((stt == ST_TAIL || stt == ST_INFEASIBLE_DONE) ? 2 : 0) | (stt == ST_MAXITER ? 4 : 0));
+                      : (((stt == ST_CONVERGED || stt == ST_CONVERGED_PINF) ? 1 : 0) | ((stt == ST_TAIL || stt == ST_INFEASIBLE_DONE || stt == ST_CONVERGED_PINF) ? 2 : 0) |
+                         (stt == ST_MAXITER ? 4 : 0));
 }
 // out[0..2] = #converged, #infeasible, #maxiter; out[3] = sum iters
 __global__ void k_stats(const __grid_constant__ ModelC c_model, const StateP S, unsigned long long* __restrict__ out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   int stt = -1, it = 0;
   if (s < S.n) { const int2 c = ld_ctl(c_model, tile_ptr(S, c_model, s)); stt = c.x; it = c.y; }
-  const unsigned c = __ballot_sync(0xffffffffu, stt == ST_CONVERGED);
+  const unsigned c = __ballot_sync(0xffffffffu, stt == ST_CONVERGED || stt == ST_CONVERGED_PINF);  // (how the solve ended)
   const unsigned f = __ballot_sync(0xffffffffu, stt == ST_TAIL || stt == ST_INFEASIBLE_DONE);
   const unsigned m = __ballot_sync(0xffffffffu, stt == ST_MAXITER);
   for (int o = 16; o > 0; o >>= 1) it += __shfl_down_sync(0xffffffffu, it, o);
@@ -808,7 +832,7 @@ static bool lane_geometry(const loik_solver* h, LaneGeom& G) {
   // the groups run different joints, the hardware schedules them as separate SIMT sub-warps (34.5 vs 35.3 us per Talos
   // iteration of a lone instance), so the default stays one group per instance
   const int gpi = h->lane_gpi_req > 0 ? h->lane_gpi_req : 1;
-  const LaneDims D = lane_dims(h->nb, h->nc, h->npend, h->mc.href_uniform, gpi);
+  const LaneDims D = lane_dims(h->nb, h->nc, h->npend, h->mc.href_uniform, gpi, h->mc.a_per);
   auto ctas_of = [&](int W) -> int {
     const size_t bytes = lane_smem_bytes(D, W, gpi);
     if (bytes > (size_t)h->smem_optin) return 0;
@@ -946,7 +970,7 @@ static void assign_segments(ModelC& M, int max_warps) {
 
 extern "C" {
 
-int32_t loik_abi_version(void) { return 1; }
+int32_t loik_abi_version(void) { return 2; }
 const char* loik_last_error(void) { return g_err.c_str(); }
 
 // `dry`: stop after the host-side part (validation, tree bookkeeping, tile-record layout) and hand back a handle that
@@ -1038,9 +1062,8 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
   O.task0 = rows; rows += TR_ROWS * nc;
   O.pend0 = rows; rows += PR_ROWS * std::max(npend, 1);
   O.ff0 = rows; rows += FR_ROWS * nmd;
-  O.prv = rows; rows += 6 * nb + h->nv;
-  O.drv = rows; rows += 6 * nb + h->nv;
   O.rows = rows;
+  O.prv = 0; O.drv = 6 * nb + h->nv; O.drows = 2 * (6 * nb + h->nv);  // (a separate arena, allocated by loik_set_debug)
   if (dry) { *out = h; return LOIK_OK; }
   {
     int ndev = 0;
@@ -1183,7 +1206,7 @@ void loik_destroy(loik_solver* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  cudaFree(h->arena); cudaFree(h->scratch[0]); cudaFree(h->scratch[1]); cudaFree(h->d_origin); cudaFree(h->d_lists); cudaFree(h->d_counts); cudaFree(h->d_stats); cudaFree(h->d_map);
+  cudaFree(h->S.dbg); cudaFree(h->arena); cudaFree(h->scratch[0]); cudaFree(h->scratch[1]); cudaFree(h->d_origin); cudaFree(h->d_lists); cudaFree(h->d_counts); cudaFree(h->d_stats); cudaFree(h->d_map);
   if (h->g_exec) cudaGraphExecDestroy(h->g_exec);
   if (h->hi_stream) cudaStreamDestroy(h->hi_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1204,24 +1227,29 @@ static int launch_reset(loik_solver* h, int flags, cudaStream_t st) {
   return LOIK_OK;
 }
 
-// problem_.UpdateReference / UpdateIneqConstraints / UpdateEqConstraints: the batch-uniform part goes to the constant block
+// problem_.UpdateReference / UpdateIneqConstraints / UpdateEqConstraints: the batch-uniform part goes to the constant block.
+// Everything is validated before the handle's block is touched (a failed call leaves the previous problem intact).
+// A == nullptr: the task matrices are per instance (rows of the task blocks, k_set_b).
 static int set_problem_consts(loik_solver* h, const double* H_ref, const double* v_ref, int n_ids, const int32_t* ids,
                               const double* A, const double* lb, const double* ub, bool bounds_shared) {
-  ModelC& M = h->mc;
   if (n_ids != h->nc)
     return fail(LOIK_ERR_INVALID, "[IkProblemFormulation::UpdateEqConstraints]: number of equality constraints doesn't match initialization!!!");
   if (!is_symmetric(H_ref))
     return fail(LOIK_ERR_UNSUPPORTED, "loik_solve_init: H_ref must be symmetric (the optimized path's SE3actOn reads only the LL, LA, AA blocks)");
+  for (int k = 0; k < n_ids; ++k) {
+    if (ids[k] < 1 || ids[k] >= h->nj) return fail(LOIK_ERR_INVALID, "loik_solve_init: task joint id out of range [1, njoints-1]");
+    for (int k2 = 0; k2 < k; ++k2)
+      if (ids[k2] == ids[k])
+        return fail(LOIK_ERR_UNSUPPORTED, "[IkProblemFormulation::UpdateEqConstraint]: multiple constraint specification for the same link id, not supported, terminating !!!");
+  }
+  ModelC& M = h->mc;
   double Hv[6];
   for (int i = 0; i < 6; ++i) { Hv[i] = 0; for (int j = 0; j < 6; ++j) Hv[i] += H_ref[6 * i + j] * v_ref[j]; }
   double hv_inf = 0; for (int i = 0; i < 6; ++i) hv_inf = std::max(hv_inf, std::fabs(Hv[i]));
   M.Hv_inf = hv_inf;  // = |Hv[0]|inf (ik-id-description-optimized.hpp:95)
   M.bounds_per_instance = bounds_shared ? 0 : 1;
   M.href_uniform = 1;
-  if (bounds_shared)
-    for (int i = 1; i < h->nj; ++i)
-      if (M.j[i].nvj > 1)
-        for (int c = 0; c < M.j[i].nvj; ++c) { M.mdlb[M.j[i].mblk][c] = lb[M.j[i].idxv + c]; M.mdub[M.j[i].mblk][c] = ub[M.j[i].idxv + c]; }
+  M.a_per = A ? 0 : 1;
   for (int i = 1; i < h->nj; ++i) {
     JointC& J = M.j[i];
     sym_blocks(H_ref, J.HrA, J.HrB, J.HrD);
@@ -1231,12 +1259,11 @@ static int set_problem_consts(loik_solver* h, const double* H_ref, const double*
   }
   for (int k = 0; k < n_ids; ++k) {
     const int c = ids[k];
-    if (c < 1 || c >= h->nj) return fail(LOIK_ERR_INVALID, "loik_solve_init: task joint id out of range [1, njoints-1]");
-    if (M.j[c].task >= 0)
-      return fail(LOIK_ERR_UNSUPPORTED, "[IkProblemFormulation::UpdateEqConstraint]: multiple constraint specification for the same link id, not supported, terminating !!!");
     M.j[c].task = k;
     TaskC& T = M.t[k];
+    std::memset(&T, 0, sizeof(T));
     T.joint = c;
+    if (!A) continue;
     double AtA[36];
     for (int i = 0; i < 36; ++i) T.A[i] = A[36 * k + i];
     for (int i = 0; i < 6; ++i)
@@ -1247,7 +1274,7 @@ static int set_problem_consts(loik_solver* h, const double* H_ref, const double*
 }
 
 int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const double* v_ref, int32_t n_ids,
-                    const int32_t* ids, const double* A, const double* b, int32_t b_per_instance, const double* lb,
+                    const int32_t* ids, const double* A, int32_t A_per_instance, const double* b, int32_t b_per_instance, const double* lb,
                     const double* ub, int32_t bounds_per_instance, int32_t loc, void* stream) {
   if (!h || !q || !H_ref || !v_ref || !lb || !ub || (n_ids > 0 && (!ids || !A || !b))) return fail(LOIK_ERR_INVALID, "loik_solve_init: null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1256,19 +1283,29 @@ int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const 
   const size_t q_bytes = (size_t)B * h->nq * sizeof(double);
   const size_t b_bytes = (size_t)(b_per_instance ? B : 1) * nc * 6 * sizeof(double);
   const size_t bd_bytes = (size_t)(bounds_per_instance ? B : 1) * h->nv * sizeof(double);
+  const size_t A_bytes = A_per_instance ? (size_t)B * nc * 36 * sizeof(double) : 0;
   if (loc != LOIK_HOST && loc != LOIK_DEVICE && loc != LOIK_HOST_PINNED) return fail(LOIK_ERR_INVALID, "loik_solve_init: bad loc");
-  // batch-shared bounds are batch-uniform data like H_ref: always host pointers, they travel in the kernel parameter block
-  int rc = set_problem_consts(h, H_ref, v_ref, n_ids, ids, A, lb, ub, !bounds_per_instance);
+  // batch-shared bounds / task matrices are batch-uniform data like H_ref: always host pointers, they travel in the kernel parameter block
+  int rc = set_problem_consts(h, H_ref, v_ref, n_ids, ids, A_per_instance ? nullptr : A, lb, ub, !bounds_per_instance);
   if (rc) return rc;
-  if (loc != LOIK_DEVICE) { rc = ensure_stage(h, q_bytes + b_bytes + 2 * bd_bytes + 64, loc == LOIK_HOST); if (rc) return rc; }
-  const void *dq, *db = nullptr, *dlb = nullptr, *dub = nullptr;
+  const bool md_shared = !bounds_per_instance && h->mc.nmd > 0;  // shared bounds of multi-DoF joints: replicated into their rows (HOST pointers)
+  if (loc != LOIK_DEVICE || md_shared) {
+    rc = ensure_stage(h, q_bytes + b_bytes + 2 * bd_bytes + A_bytes + 64, loc == LOIK_HOST || md_shared);
+    if (rc) return rc;
+  }
+  const void *dq, *db = nullptr, *dlb = nullptr, *dub = nullptr, *dA = nullptr;
   size_t off = 0;
   rc = to_device(h, q, q_bytes, loc, off, st, &dq); if (rc) return rc; off += q_bytes;
   if (nc > 0) { rc = to_device(h, b, b_bytes, loc, off, st, &db); if (rc) return rc; off += b_bytes; }
   if (bounds_per_instance) {
     rc = to_device(h, lb, bd_bytes, loc, off, st, &dlb); if (rc) return rc; off += bd_bytes;
     rc = to_device(h, ub, bd_bytes, loc, off, st, &dub); if (rc) return rc; off += bd_bytes;
+  } else if (md_shared) {
+    off = q_bytes + b_bytes;  // (a fixed place in the staging buffer, whatever was staged before)
+    rc = to_device(h, lb, bd_bytes, LOIK_HOST, off, st, &dlb); if (rc) return rc; off += bd_bytes;
+    rc = to_device(h, ub, bd_bytes, LOIK_HOST, off, st, &dub); if (rc) return rc; off += bd_bytes;
   }
+  if (A_per_instance && nc > 0) { rc = to_device(h, A, A_bytes, loc, off, st, &dA); if (rc) return rc; off += A_bytes; }
   // ik_id_data_.Reset(warm_start) + ResetSolver() + FwdPassInit's y/Aty wipe (hpp:346-359, hxx:270-278)
   const int flags = RST_SOLVER | (h->prm.warm_start ? 0 : (RST_WZ | RST_NU | RST_VFF | RST_YATY));
   k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, flags);
@@ -1276,13 +1313,13 @@ int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const 
   k_set_q<<<grid_for(B), kBlock, kBlock * h->nq * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);
   h->launches += 2;
   h->last_list = -1;
-  if (nc > 0) { k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)db, b_per_instance, -1); h->launches++; }
-  if (bounds_per_instance) {
-    k_set_bounds<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)dlb, (const double*)dub);
+  if (nc > 0) { k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)db, b_per_instance, -1, (const double*)dA); h->launches++; }
+  if (bounds_per_instance || md_shared) {
+    k_set_bounds<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)dlb, (const double*)dub, bounds_per_instance ? 1 : 0);
     h->launches++;
   }
   CK(cudaGetLastError());
-  if (loc == LOIK_HOST) CK(cudaStreamSynchronize(st));  // the staging buffer may be reused by the next call
+  if (loc == LOIK_HOST || md_shared) CK(cudaStreamSynchronize(st));  // the staging buffer may be reused by the next call
   h->problem_set = true;
   return LOIK_OK;
 }
@@ -1337,14 +1374,15 @@ static int run_schedule(loik_solver* h, cudaStream_t st0, int budget) {
   const bool lane = use_lane(h);
   // sweeps done by the tile kernels before the lane-parallel kernel takes every instance that is still active
   const int pre = lane ? std::min(budget, h->lane_after) : budget;
-  int rc = (pre > h->dense_sweeps) ? ensure_scratch(h) : LOIK_OK;
+  const int dense_sweeps = h->debug ? budget : h->dense_sweeps;  // debug mode: in place throughout (the debug arena is indexed by home slot)
+  int rc = (pre > dense_sweeps) ? ensure_scratch(h) : LOIK_OK;
   if (rc) return rc;
   cudaStream_t st = st0;
   bool forked = false;
   const int B = h->batch;
   int done = 0;
   int li = 0;  // list / count that the NEXT launch reads
-  const int dense = std::min(pre, h->dense_sweeps);
+  const int dense = std::min(pre, dense_sweeps);
   StateP X = h->S;  // where the instances of the next launch live: the home arena first
   X.list = nullptr; X.n_list = nullptr;
   if (dense > 0) {
@@ -1497,16 +1535,16 @@ int loik_solve(loik_solver* h, void* stream) {
 }
 
 int loik_solve_full(loik_solver* h, const double* q, const double* H_ref, const double* v_ref, int32_t n_ids,
-                    const int32_t* ids, const double* A, const double* b, int32_t b_per_instance, const double* lb,
+                    const int32_t* ids, const double* A, int32_t A_per_instance, const double* b, int32_t b_per_instance, const double* lb,
                     const double* ub, int32_t bounds_per_instance, int32_t loc, void* stream) {
   if (h) { int rc = check_strategy(h); if (rc) return rc; }
-  int rc = loik_solve_init(h, q, H_ref, v_ref, n_ids, ids, A, b, b_per_instance, lb, ub, bounds_per_instance, loc, stream);
+  int rc = loik_solve_init(h, q, H_ref, v_ref, n_ids, ids, A, A_per_instance, b, b_per_instance, lb, ub, bounds_per_instance, loc, stream);
   if (rc) return rc;
   if (h->prm.max_iter < 2) return LOIK_OK;
   return solve_scheduled(h, (cudaStream_t)stream, 0, h->prm.max_iter);
 }
 
-int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double* Ai, const double* bi,
+int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double* Ai, int32_t A_per_instance, const double* bi,
                     int32_t b_per_instance, int32_t loc, void* stream) {
   if (!h || !Ai || !bi) return fail(LOIK_ERR_INVALID, "loik_solve_task: null argument");
   if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_solve_task: call loik_solve_init first");
@@ -1519,22 +1557,29 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
   int k = -1;
   for (int t = 0; t < h->nc; ++t) if (M.t[t].joint == c_id) k = t;
   if (k < 0) return fail(LOIK_ERR_INVALID, "[IkProblemFormulation::UpdateEqConstraint]: constraint doesn't yet exist at link 'c_id' !!! ");
-  TaskC& T = M.t[k];
-  double AtA[36];
-  for (int i = 0; i < 36; ++i) T.A[i] = Ai[i];
-  for (int i = 0; i < 6; ++i)
-    for (int j = 0; j < 6; ++j) { double s = 0; for (int r = 0; r < 6; ++r) s += T.A[6 * r + i] * T.A[6 * r + j]; AtA[6 * i + j] = s; }
-  sym_blocks(AtA, T.AtA_A, T.AtA_B, T.AtA_D);
+  if ((A_per_instance != 0) != (M.a_per != 0))
+    return fail(LOIK_ERR_INVALID, "loik_solve_task: Ai must be per instance exactly when the task matrices of loik_solve_init were (all tasks of a handle "
+                                  "keep their matrices in the same place)");
+  if (!A_per_instance) {
+    TaskC& T = M.t[k];
+    double AtA[36];
+    for (int i = 0; i < 36; ++i) T.A[i] = Ai[i];
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) { double s = 0; for (int r = 0; r < 6; ++r) s += T.A[6 * r + i] * T.A[6 * r + j]; AtA[6 * i + j] = s; }
+    sym_blocks(AtA, T.AtA_A, T.AtA_B, T.AtA_D);
+  }
   const int B = h->batch;
   const size_t q_bytes = (size_t)B * h->nq * sizeof(double), b_bytes = (size_t)(b_per_instance ? B : 1) * 6 * sizeof(double);
-  if (loc != LOIK_DEVICE) { rc = ensure_stage(h, q_bytes + b_bytes + 64, loc == LOIK_HOST); if (rc) return rc; }
-  const void *dq = nullptr, *db;
+  const size_t A_bytes = A_per_instance ? (size_t)B * 36 * sizeof(double) : 0;
+  if (loc != LOIK_DEVICE) { rc = ensure_stage(h, q_bytes + b_bytes + A_bytes + 64, loc == LOIK_HOST); if (rc) return rc; }
+  const void *dq = nullptr, *db, *dA = nullptr;
   if (q) { rc = to_device(h, q, q_bytes, loc, 0, st, &dq); if (rc) return rc; }
   rc = to_device(h, bi, b_bytes, loc, q_bytes, st, &db); if (rc) return rc;
+  if (A_per_instance) { rc = to_device(h, Ai, A_bytes, loc, q_bytes + b_bytes, st, &dA); if (rc) return rc; }
   const int flags = RST_SOLVER | (h->prm.warm_start ? 0 : (RST_WZ | RST_NU | RST_VFF | RST_YATY));
   k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, flags);
   h->ws_valid = true;
-  k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)db, b_per_instance, k);
+  k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)db, b_per_instance, k, (const double*)dA);
   if (q) k_set_q<<<grid_for(B), kBlock, kBlock * h->nq * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);  // else: keep the device-resident q (loik_integrate)
   h->launches += 3;
   h->last_list = -1;
@@ -1645,6 +1690,12 @@ int loik_set_keep_workspace(loik_solver* h, int32_t on) {
 
 int loik_set_debug(loik_solver* h, int32_t on) {
   if (!h) return fail(LOIK_ERR_INVALID, "null handle");
+  if (on && !h->S.dbg) {  // the residual vectors of the debug kernels live in an arena of their own (production arenas do not carry them)
+    CK(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->ntiles * h->mc.off.drows * 32 * sizeof(double);
+    CK(cudaMalloc(&h->S.dbg, bytes));
+    CK(cudaMemset(h->S.dbg, 0, bytes));
+  }
   h->debug = on != 0;
   return LOIK_OK;
 }
@@ -1659,11 +1710,13 @@ int loik_get(loik_solver* h, int32_t field, void* dst, int32_t loc, void* stream
   if (field < 0 || field > LOIK_F_Q) return fail(LOIK_ERR_INVALID, "loik_get: unknown field");
   const bool is_int = field == LOIK_F_ITER || field == LOIK_F_STATUS;
   const bool is_ws = field == LOIK_F_H || field == LOIK_F_P || field == LOIK_F_UDINV || field == LOIK_F_DINV || field == LOIK_F_R;
+  if ((field == LOIK_F_PRIMAL_RES_VEC || field == LOIK_F_DUAL_RES_VEC) && !h->S.dbg)
+    return fail(LOIK_ERR_STATE, "loik_get: the residual vectors are only kept in debug mode (loik_set_debug(h, 1) before stepping / solving)");
   if (is_ws && !h->ws_valid)
     return fail(LOIK_ERR_STATE, "loik_get: the backward-pass workspace (His, pis, UDinv, Dinv, r) of the last solve was not kept; "
                                 "call loik_set_keep_workspace(h, 1) before solving");
   const int rows = is_int ? 1 : (field == LOIK_F_LIMI ? 12 * nb : h->map_len[field]);
-  (void)nc; (void)O;
+  (void)nc;
   const size_t bytes = (size_t)B * rows * (is_int ? sizeof(int) : sizeof(double));
   void* ddst = dst;
   if (loc != LOIK_DEVICE) { rc = ensure_stage(h, bytes, loc == LOIK_HOST); if (rc) return rc; ddst = h->d_stage; }
@@ -1673,7 +1726,9 @@ int loik_get(loik_solver* h, int32_t field, void* dst, int32_t loc, void* stream
     k_gather_ctl<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, field == LOIK_F_ITER ? 0 : 1, (int*)ddst);
   } else {
     const size_t total = (size_t)B * rows;
-    k_gather<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->mc, h->S, rows, h->d_map + h->map_off[field], (double*)ddst);
+    const bool dbg_field = field == LOIK_F_PRIMAL_RES_VEC || field == LOIK_F_DUAL_RES_VEC;
+    k_gather<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->mc, h->S, rows, h->d_map + h->map_off[field], (double*)ddst,
+                                                              dbg_field ? h->S.dbg : h->arena, dbg_field ? O.drows : O.rows);
   }
   h->launches++;
   CK(cudaGetLastError());

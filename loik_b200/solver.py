@@ -87,12 +87,12 @@ def load_library(path: str | None = None):
     lib.loik_create.argtypes = [C.POINTER(_ModelDesc), C.POINTER(_Params), i32, i32, C.POINTER(vp)]
     lib.loik_destroy.argtypes = [vp]
     lib.loik_destroy.restype = None
-    prob = [dp, dp, dp, i32, ip, dp, dp, i32, dp, dp, i32, i32, vp]
+    prob = [dp, dp, dp, i32, ip, dp, i32, dp, i32, dp, dp, i32, i32, vp]
     lib.loik_solve_init.argtypes = [vp] + prob
     lib.loik_solve_full.argtypes = [vp] + prob
     lib.loik_update_references.argtypes = [vp, dp, dp, vp]
     lib.loik_solve.argtypes = [vp, vp]
-    lib.loik_solve_task.argtypes = [vp, dp, i32, dp, dp, i32, i32, vp]
+    lib.loik_solve_task.argtypes = [vp, dp, i32, dp, i32, dp, i32, i32, vp]
     lib.loik_iterate_fixed.argtypes = [vp, i32, i32, vp]
     lib.loik_integrate.argtypes = [vp, C.c_double, vp]
     lib.loik_reset_recursion.argtypes = [vp, vp]
@@ -249,10 +249,18 @@ class FirstOrderLoikOptimized:
         ids = np.ascontiguousarray(ids, np.int32)
         H = _Buf(np.asarray(H_ref, np.float64).reshape(36))
         vr = _Buf(np.asarray(v_ref, np.float64).reshape(6))
-        A = _Buf(np.asarray(Ais, np.float64).reshape(-1, 36))
-        if A.shape[0] != ids.shape[0]:
-            raise RuntimeError("[IkProblemFormulation::UpdateEqConstraints]: task_constraint_ids, Ais, and bis have "
-                               "different size !!!")
+        # Ais: [nc, 6, 6] shared by the batch (host), or [B, nc, 6, 6]: every instance its own task matrices
+        a_per = int(_is_torch(Ais) and Ais.dim() == 4 or (not _is_torch(Ais)) and np.ndim(Ais) == 4)
+        if a_per:
+            A = _Buf(Ais)
+            if tuple(A.shape) != (B, ids.shape[0], 6, 6):
+                raise RuntimeError("[IkProblemFormulation::UpdateEqConstraints]: task_constraint_ids, Ais, and bis have "
+                                   "different size !!!")
+        else:
+            A = _Buf(np.asarray(Ais.cpu() if _is_torch(Ais) else Ais, np.float64).reshape(-1, 36))
+            if A.shape[0] != ids.shape[0]:
+                raise RuntimeError("[IkProblemFormulation::UpdateEqConstraints]: task_constraint_ids, Ais, and bis have "
+                                   "different size !!!")
         if ids.shape[0] != nc:
             raise RuntimeError("[IkProblemFormulation::UpdateEqConstraints]: number of equality constraints doesn't "
                                "match initialization!!!")
@@ -277,14 +285,14 @@ class FirstOrderLoikOptimized:
         else:
             raise RuntimeError("IkProblemFormulation::UpdateIneqConstraints]: inequality constraint dimension has "
                                "changed, this is not supported currently!!!")
-        locs = {qb.loc, bb.loc} | ({lbb.loc, ubb.loc} if bd_per else set())
+        locs = {qb.loc, bb.loc} | ({lbb.loc, ubb.loc} if bd_per else set()) | ({A.loc} if a_per else set())
         if len(locs) != 1:
-            raise RuntimeError("q, bis (and per-instance bounds) must all be host arrays or all be CUDA tensors")
+            raise RuntimeError("q, bis (and per-instance Ais / bounds) must all be host arrays or all be CUDA tensors")
         loc = locs.pop()
         if not bd_per and lbb.loc == LOIK_DEVICE:  # batch-shared bounds are always read on the host
             lbb, ubb = _Buf(lbb.obj.cpu().numpy()), _Buf(ubb.obj.cpu().numpy())
         keep = (qb, H, vr, ids, A, bb, lbb, ubb)
-        args = (qb.ptr, H.ptr, vr.ptr, int(ids.shape[0]), ids.ctypes.data, A.ptr, bb.ptr, b_per, lbb.ptr, ubb.ptr,
+        args = (qb.ptr, H.ptr, vr.ptr, int(ids.shape[0]), ids.ctypes.data, A.ptr, a_per, bb.ptr, b_per, lbb.ptr, ubb.ptr,
                 bd_per, loc, _current_stream())
         return keep, args
 
@@ -300,16 +308,20 @@ class FirstOrderLoikOptimized:
             self._check(self._lib.loik_solve_full(self._h, *a))
         elif len(args) == 4:
             q, c_id, Ai, bi = args
-            Ab, bb = _Buf(np.asarray(Ai, np.float64).reshape(36)), _Buf(bi)
+            bb = _Buf(bi)
+            a_per = int((Ai.dim() if _is_torch(Ai) else np.ndim(Ai)) == 3)  # [B, 6, 6]: every instance its own Ai
+            Ab = _Buf(Ai) if a_per else _Buf(np.asarray(Ai.cpu() if _is_torch(Ai) else Ai, np.float64).reshape(36))
+            if a_per and (tuple(Ab.shape) != (self.batch, 6, 6) or Ab.loc != bb.loc):
+                raise RuntimeError("a per-instance Ai must be [batch, 6, 6] and live where bi lives")
             b_per = int(int(np.prod(bb.shape)) == self.batch * 6 and (self.batch > 1 or len(bb.shape) == 2))
             if q is None:  # keep the device-resident configuration (after Integrate)
-                self._check(self._lib.loik_solve_task(self._h, None, int(c_id), Ab.ptr, bb.ptr, b_per, bb.loc,
+                self._check(self._lib.loik_solve_task(self._h, None, int(c_id), Ab.ptr, a_per, bb.ptr, b_per, bb.loc,
                                                       _current_stream()))
                 return
             qb = _Buf(q)
             if qb.loc != bb.loc:
                 raise RuntimeError("q and bi must both be host arrays or both be CUDA tensors")
-            self._check(self._lib.loik_solve_task(self._h, qb.ptr, int(c_id), Ab.ptr, bb.ptr, b_per, qb.loc,
+            self._check(self._lib.loik_solve_task(self._h, qb.ptr, int(c_id), Ab.ptr, a_per, bb.ptr, b_per, qb.loc,
                                                   _current_stream()))
         else:
             raise TypeError("Solve() takes 0, 4 or 8 arguments")

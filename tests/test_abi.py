@@ -23,7 +23,7 @@ def test_header_symbols_exported():
         assert hasattr(lib, n), f"{n} declared in include/loik_b200.h but not exported"
     assert sorted(solver.EXPORTS) == names
     lib.loik_abi_version.restype = ctypes.c_int32
-    assert lib.loik_abi_version() == 1
+    assert lib.loik_abi_version() == 2  # (2: A_per_instance in loik_solve_init / _full / _task)
 
 
 def test_enums_match_header():
