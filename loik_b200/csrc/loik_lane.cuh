@@ -479,6 +479,272 @@ LOIK_DEV void lane_residual(const ModelC& M, const LaneDims& D, const double* CB
 }
 
 // ---------------------------------------------------------------------------------------------
+// GPI = 4: the same three sweeps with the four groups of a warp on different chains of ONE instance.  SIMT runs one
+// instruction stream per warp, so the groups only work in parallel if they execute the SAME steps: every sweep is a
+// uniform loop of `steps` joint steps (the longest chain of the round); group g works on joint hi - t (resp. lo + t) of
+// its own chain while that is inside [lo, hi] (`valid`) and afterwards repeats the arithmetic on a clamped joint with
+// every store, norm update and hand-over switched off.  All exchanges between lanes are synchronised at the top level of
+// the loop (full-mask __syncwarp(), free in converged code); branches that depend on the joint (task, root, pending
+// blocks) are short and contain no synchronisation, except the rare task update (group mask).
+// ---------------------------------------------------------------------------------------------
+LOIK_DEV void wide_backward(const ModelC& M, const LaneDims& D, const double* CB, double* I, double* X, const int l, const double mu,
+                            const double mu_eq, const int lo, const int hi, const int steps) {
+  const double rho = M.rho;
+  const int lc = l < 6 ? l : 6;
+  const bool isp = l >= 6;
+  const double facv = isp ? -rho : 0.0;
+  double* XT = X + LX_T;
+  const double* XTrow = XT + 10 * lc;
+  const int cstep = M.href_uniform ? 0 : CJ_ROWS;
+  double cc[6] = {0, 0, 0, 0, 0, 0};
+  bool have_carry = false;
+  for (int t = 0; t < steps; ++t) {
+    const bool valid = hi - t >= lo;
+    const int i = valid ? hi - t : lo;
+    const JointC& J = M.j[i];
+    double* Pj = I + D.joint0 + LJ_ROWS * (i - 1);
+    const double* Cj = CB + cstep * (i - 1) + lc;
+    __syncwarp();
+    double vold[6], col[6];
+    lds6(Pj + LJ_V, vold);
+    const double w_i = Pj[LJ_W], z_i = Pj[LJ_Z];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) col[r] = fma(facv, vold[r], Cj[CJ_HREFR + 8 * r]);
+    if (J.task >= 0) {
+      const double* Ck = M.a_per ? I + D.tmat0 + CT_ROWS * J.task : CB + D.ctask0 + CT_ROWS * J.task;
+      const double* Pk = I + D.task0 + LT_ROWS * J.task;
+      double aty[6], atb[6];
+      lds6(Pk + LT_ATY, aty);
+      lds6(Pk + LT_ATB, atb);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        const double hcol = fma(mu_eq, Ck[CT_ATA + 8 * r + lc], col[r]);
+        const double pcol = col[r] + (aty[r] - mu_eq * atb[r]);
+        col[r] = isp ? pcol : hcol;
+      }
+    }
+    for (int n = 0; n < J.npin; ++n) {
+      const double* Pp = I + D.pend0 + LP_ROWS * J.pin[n];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) col[r] += Pp[LP_HP + 8 * r + lc];
+    }
+    if (have_carry) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) col[r] += cc[r];
+    }
+    const int k = J.sidx;
+    double d_un = 0.0;
+    if (k < 0) d_un = St_dot(J, col);  // unaligned joint: U_c = S^T H(:, c), lane 6: S^T p
+    if (valid) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) Pj[LJ_HP + 8 * r + l] = col[r];
+    }
+    X[LX_V + l] = d_un;
+    __syncwarp();
+    double U[6], d, Stp, StU;
+    if (k >= 0) {
+      // (an invalid step reads the block its group stored in an earlier, valid step: finite values, results unused)
+      const double* row = Pj + LJ_HP + 8 * k;
+      lds6(row, U);
+      Stp = row[6];
+      d = row[l];
+      StU = row[k];
+    } else {
+      lds6(X + LX_V, U);
+      Stp = X[LX_V + 6];
+      d = d_un;
+      StU = St_dot(J, U);
+    }
+    const double Dinv = 1.0 / (StU + mu);
+    const double ri = (w_i - mu * z_i) + Stp;
+    double UD[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) UD[c] = U[c] * Dinv;
+    if (valid) {
+      Pj[LJ_UD + l] = d * Dinv;
+      Pj[LJ_DINV] = Dinv;
+      Pj[LJ_R] = ri;
+    }
+    // projection + transformation to the parent frame, by every group (a root joint's result is simply not handed on)
+    const double m = isp ? ri : d;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) col[r] -= UD[r] * m;
+    double R[9], tr[3], y[6], row[6];
+    lds_xf(Pj + LJ_XF, R, tr);
+    act_force(R, tr, col, y);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) XT[10 * r + l] = y[r];
+    if (isp) sts6(XT + 60, col);
+    __syncwarp();
+    lds6(XTrow, row);
+    act_force(R, tr, row, cc);
+    const bool give = valid && J.parent > 0;
+    have_carry = give && J.carry != 0;
+    if (give && !J.carry) {
+      double* Pp = I + D.pend0 + LP_ROWS * J.pout;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) Pp[LP_HP + 8 * r + l] = cc[r];
+    }
+  }
+}
+
+LOIK_DEV void wide_forward(const ModelC& M, const LaneDims& D, const double* CB, double* I, double* X, const int l, const unsigned gmask,
+                           const double mu, const double mu_eq, Carry& cy, LanePart& pt, const int lo, const int hi, const int steps) {
+  const double inv_mu = 1.0 / mu;
+  const int lc = l < 6 ? l : 5;
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  for (int t = 0; t < steps; ++t) {
+    const bool valid = lo + t <= hi;
+    const int i = valid ? lo + t : lo;
+    const JointC& J = M.j[i];
+    double* Pj = I + D.joint0 + LJ_ROWS * (i - 1);
+    __syncwarp();
+    double UD[6], R[9], tr[3];
+    const double vold_l = Pj[LJ_V + lc];
+    const double2 dr = lds2(Pj + LJ_DINV);
+    const double2 nz = lds2(Pj + LJ_NU);
+    const double w_old = Pj[LJ_W];
+    double lb = J.lb, ub = J.ub;
+    if (M.bounds_per_instance) { const double2 b2 = lds2(Pj + LJ_LB); lb = b2.x; ub = b2.y; }
+    lds6(Pj + LJ_UD, UD);
+    lds_xf(Pj + LJ_XF, R, tr);
+    if (t == 0 || J.parent != i - 1) {
+      if (J.parent == 0) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) v[c] = 0.0;
+      } else {
+        lds6(I + D.joint0 + LJ_ROWS * (J.parent - 1) + LJ_V, v);
+      }
+    }
+    double hc[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) hc[c] = Pj[LJ_HP + 8 * c + lc];
+    const double p_l = Pj[LJ_HP + 8 * lc + 6];
+    const double fold_l = Pj[LJ_F + lc];
+    {
+      double vp[6];
+      actinv_motion(R, tr, v, vp);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) v[c] = vp[c];
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc += UD[c] * v[c];
+    const double nu = -acc - dr.x * dr.y;
+    S_axpy(J, nu, v);
+    const double z = dmin(ub, dmax(lb, nu + inv_mu * w_old));
+    const double rp = nu - z;
+    const double dw = mu * rp;
+    const double f_l = hc[0] * v[0] + hc[1] * v[1] + hc[2] * v[2] + hc[3] * v[3] + hc[4] * v[4] + hc[5] * v[5] + p_l;
+    if (valid) {
+      cy.nu_inf = amax(cy.nu_inf, nu);
+      cy.dnu_inf = amax(cy.dnu_inf, nu - nz.x);
+      cy.dz_inf = amax(cy.dz_inf, z - nz.y);
+      cy.pres_slack = amax(cy.pres_slack, rp);
+      cy.dw_inf = amax(cy.dw_inf, dw);
+      cy.ubdw_p += ub * dmax(dw, 0.0);
+      cy.lbdw_m += lb * dmin(dw, 0.0);
+      pt.dfis = amax(pt.dfis, f_l - fold_l);
+    }
+    __syncwarp();
+    if (valid) {
+      if (l == 0) sts6(Pj + LJ_V, v);
+      Pj[LJ_F + lc] = f_l;
+      *reinterpret_cast<double2*>(Pj + LJ_NU) = make_double2(nu, z);
+      Pj[LJ_W] = w_old + dw;
+    }
+    __syncwarp();
+    if (valid) pt.dvis = amax(pt.dvis, Pj[LJ_V + lc] - vold_l);
+    if (valid && J.task >= 0) {  // DualUpdate for the task on this joint (:410-451); only the group that owns the joint is here
+      const double* Ck = M.a_per ? I + D.tmat0 + CT_ROWS * J.task : CB + D.ctask0 + CT_ROWS * J.task;
+      double* Pk = I + D.task0 + LT_ROWS * J.task;
+      const double Av = Ck[CT_ATR + lc] * v[0] + Ck[CT_ATR + 8 + lc] * v[1] + Ck[CT_ATR + 16 + lc] * v[2] + Ck[CT_ATR + 24 + lc] * v[3] +
+                        Ck[CT_ATR + 32 + lc] * v[4] + Ck[CT_ATR + 40 + lc] * v[5];
+      const double e = Av - Pk[LT_B + lc];
+      const double dy = mu_eq * e;
+      const double y_l = Pk[LT_Y + lc] + dy;
+      pt.dyis = amax(pt.dyis, dy);
+      pt.Av = amax(pt.Av, Av);
+      pt.ptask = amax(pt.ptask, e);
+      X[LX_V + l] = dy;
+      X[LX_V + 8 + l] = y_l;
+      __syncwarp(gmask);
+      double dys[6], ys[6], bk[6];
+      lds6(X + LX_V, dys);
+      lds6(X + LX_V + 8, ys);
+      lds6(Pk + LT_B, bk);
+      double plus = 0.0, minus = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        plus += bk[a] * dmax(dys[a], 0.0);
+        minus += bk[a] * dmin(dys[a], 0.0);
+      }
+      cy.bTdy_p += plus;
+      cy.bTdy_m += minus;
+      const double aty = Ck[CT_AR + lc] * ys[0] + Ck[CT_AR + 8 + lc] * ys[1] + Ck[CT_AR + 16 + lc] * ys[2] + Ck[CT_AR + 24 + lc] * ys[3] +
+                         Ck[CT_AR + 32 + lc] * ys[4] + Ck[CT_AR + 40 + lc] * ys[5];
+      __syncwarp(gmask);
+      Pk[LT_Y + lc] = y_l;
+      Pk[LT_ATY + lc] = aty;
+    }
+  }
+}
+
+LOIK_DEV void wide_residual(const ModelC& M, const LaneDims& D, const double* CB, double* I, const int l, Resid& rs, LanePart& pt,
+                            const int lo, const int hi, const int steps) {
+  const int lc = l < 6 ? l : 5;
+  const int cstep = M.href_uniform ? 0 : CJ_ROWS;
+  double cF = 0.0;
+  bool have_carry = false;
+  for (int t = 0; t < steps; ++t) {
+    const bool valid = hi - t >= lo;
+    const int i = valid ? hi - t : lo;
+    const JointC& J = M.j[i];
+    double* Pj = I + D.joint0 + LJ_ROWS * (i - 1);
+    const double* Cj = CB + cstep * (i - 1) + lc;
+    __syncwarp();
+    double f[6], v[6];
+    lds6(Pj + LJ_F, f);
+    lds6(Pj + LJ_V, v);
+    const double2 wt = lds2(Pj + LJ_W);
+    const double f_l = Pj[LJ_F + lc], Fold = Pj[LJ_FD + lc], Hv_l = Cj[CJ_HV];
+    double hr[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) hr[c] = Cj[CJ_HREF + 8 * c];
+    const int k = J.sidx;
+    const double Stf = k >= 0 ? Pj[LJ_F + k] : St_dot(J, f);
+    double F = 0.0;
+    if (J.task >= 0) F = I[D.task0 + LT_ROWS * J.task + LT_ATY + lc];
+    for (int n = 0; n < J.npin; ++n) F += I[D.pend0 + LP_ROWS * J.pin[n] + LP_F + lc];
+    if (have_carry) F += cF;
+    F += -f_l;
+    const double Hrv = hr[0] * v[0] + hr[1] * v[1] + hr[2] * v[2] + hr[3] * v[3] + hr[4] * v[4] + hr[5] * v[5];
+    const double rd = Hrv - Hv_l + F;
+    const double Tn = Stf + wt.x;
+    if (valid) {
+      pt.dF = amax(pt.dF, F - Fold);
+      pt.Finf = amax(pt.Finf, F);
+      pt.Hrefv = amax(pt.Hrefv, Hrv);
+      pt.dresv = amax(pt.dresv, rd);
+      rs.T_inf = amax(rs.T_inf, Tn);
+      rs.dT_inf = amax(rs.dT_inf, Tn - wt.y);
+    }
+    __syncwarp();
+    if (valid) {
+      Pj[LJ_FD + lc] = F;
+      Pj[LJ_T] = Tn;
+    }
+    double R[9], tr[3], c6[6];
+    lds_xf(Pj + LJ_XF, R, tr);
+    act_force(R, tr, f, c6);
+    cF = pick6(c6, lc);
+    const bool give = valid && J.parent > 0;
+    have_carry = give && J.carry != 0;
+    if (give && !J.carry) I[D.pend0 + LP_ROWS * J.pout + LP_F + lc] = cF;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // The kernel.  blockDim = 32 W; dynamic shared memory = constants + (4 / GPI) W instance records (lane_smem_bytes).
 // ---------------------------------------------------------------------------------------------
 template <int GPI>
@@ -568,9 +834,8 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
       // group g sweeps the chains assigned to "warp" g of the segment schedule, level by level (children before parents
       // on the way to the root, parents before children on the way out); chains exchange data through the pending blocks
       // and the parents' v rows of the shared record.  All four groups enter a sweep TOGETHER, each with its own joint
-      // range (round r = the r-th chain of the group at this level; an empty range when it has none): the groups then
-      // run the joint steps in lock-step and a group with a shorter chain simply leaves the loop earlier.  (Calling the
-      // sweep from inside a per-chain branch would serialise the groups: SIMT executes one side of a branch at a time.)
+      // range (round r = the r-th chain of the group at this level; an empty range when it has none) and the same number
+      // of steps (wide_backward).
       auto chain_of = [&](const bool backward, const int lv, const int r, int& lo, int& hi) {
         lo = 1; hi = 0;
         int cnt = 0;
@@ -586,8 +851,9 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
         for (int r = 0;; ++r) {
           int lo, hi;
           chain_of(true, lv, r, lo, hi);
-          if (__ballot_sync(0xffffffffu, hi >= lo) == 0u) break;
-          lane_backward<GPI>(M, D, CB, I, X, l, gmask, mu, mu_eq, lo, hi);
+          const int steps = __reduce_max_sync(0xffffffffu, hi - lo + 1);  // the longest chain of this round (0: none left)
+          if (steps <= 0) break;
+          wide_backward(M, D, CB, I, X, l, mu, mu_eq, lo, hi, steps);
         }
         __syncwarp();
       }
@@ -595,8 +861,9 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
         for (int r = 0;; ++r) {
           int lo, hi;
           chain_of(false, lv, r, lo, hi);
-          if (__ballot_sync(0xffffffffu, hi >= lo) == 0u) break;
-          lane_forward<GPI>(M, D, CB, I, X, l, gmask, mu, mu_eq, cy, pt, lo, hi);
+          const int steps = __reduce_max_sync(0xffffffffu, hi - lo + 1);
+          if (steps <= 0) break;
+          wide_forward(M, D, CB, I, X, l, gmask, mu, mu_eq, cy, pt, lo, hi, steps);
         }
         __syncwarp();
       }
@@ -604,8 +871,9 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
         for (int r = 0;; ++r) {
           int lo, hi;
           chain_of(true, lv, r, lo, hi);
-          if (__ballot_sync(0xffffffffu, hi >= lo) == 0u) break;
-          lane_residual<GPI>(M, D, CB, I, l, gmask, rs, pt, lo, hi);
+          const int steps = __reduce_max_sync(0xffffffffu, hi - lo + 1);
+          if (steps <= 0) break;
+          wide_residual(M, D, CB, I, l, rs, pt, lo, hi, steps);
         }
         __syncwarp();
       }
