@@ -47,8 +47,8 @@ extern "C" {
 #define LOIK_API
 #endif
 
-#define LOIK_MAX_JOINTS 64 /* njoints incl. universe */
-#define LOIK_MAX_TASKS 8
+#define LOIK_MAX_JOINTS 104 /* njoints incl. universe (the batch-uniform model block travels to the kernels by value) */
+#define LOIK_MAX_TASKS 32   /* 6-D tasks; up to 8 keep a batch-shared A in the parameter block, more keep A in HBM rows */
 
 /* joint type codes: pinocchio JointModelRX/RY/RZ, PX/PY/PZ, RevoluteUnaligned, PrismaticUnaligned */
 enum { LOIK_JOINT_RX = 0, LOIK_JOINT_RY, LOIK_JOINT_RZ, LOIK_JOINT_PX, LOIK_JOINT_PY, LOIK_JOINT_PZ,

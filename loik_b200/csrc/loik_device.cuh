@@ -21,11 +21,15 @@
 
 namespace loik {
 
-constexpr int kMaxJoints = 64;
-constexpr int kMaxTasks = 8;
-constexpr int kMaxPin = 6;    // children per joint that are not carried in registers
-constexpr int kMaxSeg = 16;   // chains of the tree that can be swept by different warps
-constexpr int kMaxMd = 8;     // multi-DoF joints (free-flyer, spherical, translation) per model
+// Capacities of the batch-uniform parameter block (ModelC travels to every kernel BY VALUE: 32 764 bytes of parameter
+// space).  The per-joint record is packed (references through an index, shorts) so that 104 joints fit.
+constexpr int kMaxJoints = 104;  // model.njoints incl. the universe
+constexpr int kMaxTasks = 8;     // tasks whose matrix A is shared by the batch (kept in the block); more tasks (up to kMaxTasksAll)
+constexpr int kMaxTasksAll = 32; //   keep A per instance in the task rows of the tile record (ModelC::a_per)
+constexpr int kMaxHref = 33;     // distinct (H_ref, v_ref) references: 1 after UpdateReference, one per joint after UpdateReferences
+constexpr int kMaxPin = 6;       // children per joint that are not carried in registers
+constexpr int kMaxSeg = 16;      // chains of the tree that can be swept by different warps
+constexpr int kMaxMd = 16;       // multi-DoF joints (free-flyer, spherical, translation, planar) per model
 
 // status of an instance (per-instance loop control of Solve()/InfeasibilityTailSolve())
 // ST_CONVERGED_PINF: converged_ with primal_infeasible_ raised in the same iteration -- the reference evaluates both
@@ -33,26 +37,30 @@ constexpr int kMaxMd = 8;     // multi-DoF joints (free-flyer, spherical, transl
 // get_primal_infeasibility_status() (0.03 % of a UR10-262 144 batch end this way)
 enum : int { ST_RUNNING = 0, ST_TAIL = 1, ST_CONVERGED = 2, ST_INFEASIBLE_DONE = 3, ST_MAXITER = 4, ST_CONVERGED_PINF = 5 };
 
+struct HrefC {
+  double A[6], B[9], D[6];          // problem_.H_refs_[i] as blocks LL (sym), LA, AA (sym)
+  double Hv[6];                     // problem_.Hv[i] = H_ref v_ref
+};
+
 struct JointC {
   double plR[9], plp[3], axis[3];   // model.jointPlacements[i], joint axis
-  double HrA[6], HrB[9], HrD[6];    // problem_.H_refs_[i] as blocks LL (sym), LA, AA (sym)
-  double Hv[6];                     // problem_.Hv[i] = H_ref v_ref
   double lb, ub;                    // problem_.lb_/ub_ for this joint's dof (when shared by the batch)
-  int parent, jtype, task;          // task: slot of the task on this joint or -1
-  int idxv, idxq;                   // jmodel.idx_v(), jmodel.idx_q()
-  int carry;                        // contribution to the parent travels in registers (parent == i-1, only child)
-  int pout;                         // else (parent > 0): the pending block this joint writes its contribution to
-  int npin;                         // number of children that hand their contribution over through a pending block
-  int pin[kMaxPin];                 // those blocks (one per tree edge: single writer, no read-modify-write)
-  int qkind;                        // how q parametrises the joint: 0 = one scalar, 1 = (cos, sin) (unbounded revolute)
-  int nvj, sel0, mblk;              // multi-DoF joints: nv of the joint (3 / 6), the components S selects (4 bits each, dof k in bits 4k..4k+3), index of its md block
-  int sidx;                         // aligned 1-DoF joints: the component of a [lin; ang] 6-vector S selects (S = e_sidx); -1 otherwise
+  int sel0;                         // multi-DoF joints: the components S selects (4 bits each, dof k in bits 4k..4k+3)
+  short parent, jtype, task;        // task: slot of the task on this joint or -1
+  short idxv, idxq;                 // jmodel.idx_v(), jmodel.idx_q()
+  short carry;                      // contribution to the parent travels in registers (parent == i-1, only child)
+  short pout;                       // else (parent > 0): the pending block this joint writes its contribution to
+  short npin;                       // number of children that hand their contribution over through a pending block
+  short qkind;                      // how q parametrises the joint: 0 = one scalar, 1 = (cos, sin) (unbounded revolute)
+  short nvj, mblk;                  // multi-DoF joints: nv of the joint (3 / 6), index of its md block
+  short sidx;                       // aligned 1-DoF joints: the component of a [lin; ang] 6-vector S selects (S = e_sidx); -1 otherwise
+  short href;                       // this joint's entry of ModelC::href
+  short pin[kMaxPin];               // the pending blocks read (one per tree edge: single writer, no read-modify-write)
 };
 
 struct TaskC {
   double A[36];                     // problem_.Ais_[k]
   double AtA_A[6], AtA_B[9], AtA_D[6];
-  int joint, pad;
 };
 
 // Tile record layout.  Rows are grouped so that everything one joint step touches is contiguous and
@@ -106,9 +114,12 @@ struct ModelC {
   SpanC span[kMaxSpan];
   Offs off;
   double rho, mu0, mu_scale, tol_abs, tol_rel, tol_pinf, tol_dinf, tol_tail, Hv_inf;
+  short task_joint[kMaxTasksAll];  // joint of every task slot (TaskC::joint only exists for the first kMaxTasks)
+  HrefC href[kMaxHref];
   JointC j[kMaxJoints];
   TaskC t[kMaxTasks];
 };
+static_assert(sizeof(ModelC) <= 32764 - 256, "ModelC + StateP + scalars must fit the kernel parameter space");
 
 // Sweep-to-sweep scalars of one iteration (the reference keeps them in IkIdData, data hpp:259-329).
 struct Carry {
@@ -451,6 +462,7 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, const double* Ts, double* Td
   bool have_carry = false;
   for (int i = hi; i >= lo; --i) {
     const JointC& J = c_model.j[i];
+    const HrefC& Hr = c_model.href[J.href];
     double* Pj = joint_blk(Td, O, i - 1);
     const double* Ps = joint_blk(const_cast<double*>(Ts), O, i - 1);
     if (i > lo) {
@@ -486,11 +498,11 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, const double* Ts, double* Td
     // previous iterate here, which is the reference's vis_prev (UpdatePrev, data hxx:192-197).
     double A[6], B[9], D[6], p[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) p[c] = -rho * vold[c] - J.Hv[c];
+    for (int c = 0; c < 6; ++c) p[c] = -rho * vold[c] - Hr.Hv[c];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { A[c] = J.HrA[c]; D[c] = J.HrD[c]; }
+    for (int c = 0; c < 6; ++c) { A[c] = Hr.A[c]; D[c] = Hr.D[c]; }
 #pragma unroll
-    for (int c = 0; c < 9; ++c) B[c] = J.HrB[c];
+    for (int c = 0; c < 9; ++c) B[c] = Hr.B[c];
     A[0] += rho; A[3] += rho; A[5] += rho; D[0] += rho; D[3] += rho; D[5] += rho;
     if (J.task >= 0) {  // H_c += mu_eq AtA; p_c += Aty - mu_eq Atb (:327-330)
       const TaskC& K = c_model.t[J.task];
@@ -747,6 +759,7 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, const double* Ts, double* Td
   bool have_carry = false;
   for (int i = hi; i >= lo; --i) {
     const JointC& J = c_model.j[i];
+    const HrefC& Hr = c_model.href[J.href];
     const int ji = i - 1;
     double* Pj = joint_blk(Td, O, ji);
     const double* Ps = joint_blk(const_cast<double*>(Ts), O, ji);
@@ -790,15 +803,15 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, const double* Ts, double* Td
     double Hrv[6], rd[6];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      Hrv[a] = J.HrA[si(a, 0)] * v[0] + J.HrA[si(a, 1)] * v[1] + J.HrA[si(a, 2)] * v[2] + J.HrB[3 * a] * v[3] + J.HrB[3 * a + 1] * v[4] + J.HrB[3 * a + 2] * v[5];
-      Hrv[3 + a] = J.HrB[a] * v[0] + J.HrB[3 + a] * v[1] + J.HrB[6 + a] * v[2] + J.HrD[si(a, 0)] * v[3] + J.HrD[si(a, 1)] * v[4] + J.HrD[si(a, 2)] * v[5];
+      Hrv[a] = Hr.A[si(a, 0)] * v[0] + Hr.A[si(a, 1)] * v[1] + Hr.A[si(a, 2)] * v[2] + Hr.B[3 * a] * v[3] + Hr.B[3 * a + 1] * v[4] + Hr.B[3 * a + 2] * v[5];
+      Hrv[3 + a] = Hr.B[a] * v[0] + Hr.B[3 + a] * v[1] + Hr.B[6 + a] * v[2] + Hr.D[si(a, 0)] * v[3] + Hr.D[si(a, 1)] * v[4] + Hr.D[si(a, 2)] * v[5];
     }
     {
       double dF[6];
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
         dF[c] = F[c] - Fold[c];
-        rd[c] = Hrv[c] - J.Hv[c] + F[c];            // (:228)
+        rd[c] = Hrv[c] - Hr.Hv[c] + F[c];            // (:228)
       }
       rs.dF_inf = amax6(rs.dF_inf, dF);             // (:215-220)
       rs.F_inf = amax6(rs.F_inf, F);                // (:223-225)
@@ -895,6 +908,7 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
                           const bool migrate) {
   const Offs& O = c_model.off;
   const JointC& J = c_model.j[i];
+    const HrefC& Hr = c_model.href[J.href];
   int sel[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) sel[k] = (J.sel0 >> (4 * k)) & 7;
@@ -913,11 +927,11 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
     }
   }
 #pragma unroll
-  for (int c = 0; c < 6; ++c) { p[c] = -rho * ld(Pjs, JR_V + c) - J.Hv[c]; A[c] = J.HrA[c]; D[c] = J.HrD[c]; }
+  for (int c = 0; c < 6; ++c) { p[c] = -rho * ld(Pjs, JR_V + c) - Hr.Hv[c]; A[c] = Hr.A[c]; D[c] = Hr.D[c]; }
 #pragma unroll
   for (int c = 0; c < K; ++c) { w[c] = ld(Pfs, FR_W + c); z[c] = ld(Pfs, FR_Z + c); }
 #pragma unroll
-  for (int c = 0; c < 9; ++c) B[c] = J.HrB[c];
+  for (int c = 0; c < 9; ++c) B[c] = Hr.B[c];
   A[0] += rho; A[3] += rho; A[5] += rho; D[0] += rho; D[3] += rho; D[5] += rho;
   if (J.task >= 0) {
     const TaskC& Kt = c_model.t[J.task];
@@ -1119,6 +1133,7 @@ template <bool DEBUG, int K>
 LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs, const int i, double* Dg) {
   const Offs& O = c_model.off;
   const JointC& J = c_model.j[i];
+    const HrefC& Hr = c_model.href[J.href];
   const int nb = c_model.nb;
   int sel[K];
 #pragma unroll
@@ -1143,8 +1158,8 @@ LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* 
   double Hrv[6];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    Hrv[a] = J.HrA[si(a, 0)] * v[0] + J.HrA[si(a, 1)] * v[1] + J.HrA[si(a, 2)] * v[2] + J.HrB[3 * a] * v[3] + J.HrB[3 * a + 1] * v[4] + J.HrB[3 * a + 2] * v[5];
-    Hrv[3 + a] = J.HrB[a] * v[0] + J.HrB[3 + a] * v[1] + J.HrB[6 + a] * v[2] + J.HrD[si(a, 0)] * v[3] + J.HrD[si(a, 1)] * v[4] + J.HrD[si(a, 2)] * v[5];
+    Hrv[a] = Hr.A[si(a, 0)] * v[0] + Hr.A[si(a, 1)] * v[1] + Hr.A[si(a, 2)] * v[2] + Hr.B[3 * a] * v[3] + Hr.B[3 * a + 1] * v[4] + Hr.B[3 * a + 2] * v[5];
+    Hrv[3 + a] = Hr.B[a] * v[0] + Hr.B[3 + a] * v[1] + Hr.B[6 + a] * v[2] + Hr.D[si(a, 0)] * v[3] + Hr.D[si(a, 1)] * v[4] + Hr.D[si(a, 2)] * v[5];
   }
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
@@ -1152,7 +1167,7 @@ LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* 
     rs.dF_inf = amax(rs.dF_inf, F[c] - Fold[c]);
     rs.F_inf = amax(rs.F_inf, F[c]);
     rs.Hrefv_inf = amax(rs.Hrefv_inf, Hrv[c]);
-    const double rd = Hrv[c] - J.Hv[c] + F[c];
+    const double rd = Hrv[c] - Hr.Hv[c] + F[c];
     rs.dres_v = amax(rs.dres_v, rd);
     st(Pj, JR_FD + c, F[c]);
     if (DEBUG && Dg) st(Dg, O.drv + 6 * (i - 1) + c, rd);
@@ -1316,10 +1331,11 @@ LOIK_DEV void fine_fwdpass1(const ModelC& M, double* __restrict__ T, const doubl
   const Offs& O = M.off;
   for (int i = 1; i <= M.nb; ++i) {
     const JointC& J = M.j[i];
+    const HrefC& Hr = M.href[J.href];
     double* Pj = joint_blk(T, O, i - 1);
     double A[6], B[9], D[6], p[6];
-    for (int c = 0; c < 6; ++c) { p[c] = -M.rho * ld(Pj, JR_V + c) - J.Hv[c]; A[c] = J.HrA[c]; D[c] = J.HrD[c]; }
-    for (int c = 0; c < 9; ++c) B[c] = J.HrB[c];
+    for (int c = 0; c < 6; ++c) { p[c] = -M.rho * ld(Pj, JR_V + c) - Hr.Hv[c]; A[c] = Hr.A[c]; D[c] = Hr.D[c]; }
+    for (int c = 0; c < 9; ++c) B[c] = Hr.B[c];
     A[0] += M.rho; A[3] += M.rho; A[5] += M.rho; D[0] += M.rho; D[3] += M.rho; D[5] += M.rho;
     if (J.task >= 0) {
       const TaskC& K = M.t[J.task];
@@ -1344,6 +1360,7 @@ LOIK_DEV void fine_fwdpass2(const ModelC& M, double* __restrict__ T) {
   double dnu = 0.0;
   for (int i = 1; i <= M.nb; ++i) {
     const JointC& J = M.j[i];
+    const HrefC& Hr = M.href[J.href];
     double* Pj = joint_blk(T, O, i - 1);
     double vin[6], R[9], t[3], v[6];
     for (int c = 0; c < 6; ++c) vin[c] = J.parent == 0 ? 0.0 : ld(joint_blk(T, O, J.parent - 1), JR_V + c);
@@ -1361,8 +1378,8 @@ LOIK_DEV void fine_fwdpass2(const ModelC& M, double* __restrict__ T) {
     for (int a = 0; a < 3; ++a) {
       f[a] = A[si(a, 0)] * v[0] + A[si(a, 1)] * v[1] + A[si(a, 2)] * v[2] + B[3 * a] * v[3] + B[3 * a + 1] * v[4] + B[3 * a + 2] * v[5] + ld(Pj, JR_P + a);
       f[3 + a] = B[a] * v[0] + B[3 + a] * v[1] + B[6 + a] * v[2] + D[si(a, 0)] * v[3] + D[si(a, 1)] * v[4] + D[si(a, 2)] * v[5] + ld(Pj, JR_P + 3 + a);
-      Hrv[a] = J.HrA[si(a, 0)] * v[0] + J.HrA[si(a, 1)] * v[1] + J.HrA[si(a, 2)] * v[2] + J.HrB[3 * a] * v[3] + J.HrB[3 * a + 1] * v[4] + J.HrB[3 * a + 2] * v[5];
-      Hrv[3 + a] = J.HrB[a] * v[0] + J.HrB[3 + a] * v[1] + J.HrB[6 + a] * v[2] + J.HrD[si(a, 0)] * v[3] + J.HrD[si(a, 1)] * v[4] + J.HrD[si(a, 2)] * v[5];
+      Hrv[a] = Hr.A[si(a, 0)] * v[0] + Hr.A[si(a, 1)] * v[1] + Hr.A[si(a, 2)] * v[2] + Hr.B[3 * a] * v[3] + Hr.B[3 * a + 1] * v[4] + Hr.B[3 * a + 2] * v[5];
+      Hrv[3 + a] = Hr.B[a] * v[0] + Hr.B[3 + a] * v[1] + Hr.B[6 + a] * v[2] + Hr.D[si(a, 0)] * v[3] + Hr.D[si(a, 1)] * v[4] + Hr.D[si(a, 2)] * v[5];
     }
     for (int c = 0; c < 6; ++c) {
       dvis = amax(dvis, v[c] - ld(Pj, JR_V + c));
@@ -1404,7 +1421,7 @@ LOIK_DEV void fine_dualupdate(const ModelC& M, double* __restrict__ T, const dou
   for (int k = 0; k < M.nc; ++k) {
     const TaskC& K = M.t[k];
     double* Pk = task_blk(T, O, k);
-    const double* Pj = joint_blk(T, O, K.joint - 1);
+    const double* Pj = joint_blk(T, O, M.task_joint[k] - 1);
     double v[6], y[6], plus = 0.0, minus = 0.0;
     for (int c = 0; c < 6; ++c) v[c] = ld(Pj, JR_V + c);
     for (int a = 0; a < 6; ++a) {
@@ -1414,7 +1431,7 @@ LOIK_DEV void fine_dualupdate(const ModelC& M, double* __restrict__ T, const dou
       y[a] = ld(Pk, TR_Y + a) + dy;
       dyis = amax(dyis, dy); Av_inf = amax(Av_inf, Av); ptask = amax(ptask, e);
       plus += bi * dmax(dy, 0.0); minus += bi * dmin(dy, 0.0);
-      if (Dg) st(Dg, O.prv + 6 * (K.joint - 1) + a, e);
+      if (Dg) st(Dg, O.prv + 6 * (M.task_joint[k] - 1) + a, e);
     }
     bp += plus; bm += minus;
     for (int a = 0; a < 6; ++a) {

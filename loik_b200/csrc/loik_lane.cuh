@@ -758,12 +758,13 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
     if (e < D.ctask0) {
       const int j = e / CJ_ROWS, o = e - CJ_ROWS * j;
       const JointC& J = M.j[j + 1];
+    const HrefC& Hr = M.href[J.href];
       if (o < CJ_HV) {
         const int r = (o % 48) >> 3, c = o & 7;
-        if (c < 6) x = Hel(J.HrA, J.HrB, J.HrD, r, c) + ((o < CJ_HREF && r == c) ? M.rho : 0.0);  // H_i = rho I + Href_i (:304-306)
-        else if (c == 6 && o < CJ_HREF) x = -J.Hv[r];
+        if (c < 6) x = Hel(Hr.A, Hr.B, Hr.D, r, c) + ((o < CJ_HREF && r == c) ? M.rho : 0.0);  // H_i = rho I + Href_i (:304-306)
+        else if (c == 6 && o < CJ_HREF) x = -Hr.Hv[r];
       } else if (o - CJ_HV < 6) {
-        x = J.Hv[o - CJ_HV];
+        x = Hr.Hv[o - CJ_HV];
       }
     } else {
       const int k = (e - D.ctask0) / CT_ROWS, o = (e - D.ctask0) - CT_ROWS * k;

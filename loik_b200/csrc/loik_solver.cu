@@ -583,7 +583,7 @@ __global__ void __launch_bounds__(128) k_integrate(const __grid_constant__ Model
 // batch does not share the task matrices (Ain != nullptr: [n][nc][36], or [n][36] for one task) -- A and AtA = A^T A
 // (:162).  task < 0: all tasks, bis_inf_norm reset; task >= 0: UpdateEqConstraint for that slot (:178-218), norm only grows.
 __global__ void k_set_b(const __grid_constant__ ModelC c_model, const StateP S, const double* __restrict__ b, const int per_instance, const int task,
-                        const double* __restrict__ Ain) {
+                        const double* __restrict__ Ain, const int Ain_per_instance) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
   double* T = tile_ptr(S, c_model, s);
@@ -603,7 +603,8 @@ __global__ void k_set_b(const __grid_constant__ ModelC c_model, const StateP S, 
       binf = fmax(binf, fabs(bk[a]));
     }
     if (Ain) {
-      const double* As = Ain + (task < 0 ? ((size_t)s * nc + k) * 36 : (size_t)s * 36);
+      // (Ain_per_instance == 0: one set of matrices for the batch, kept in the rows because there are more tasks than TaskC slots)
+      const double* As = Ain + (task < 0 ? ((size_t)(Ain_per_instance ? s : 0) * nc + k) * 36 : (size_t)(Ain_per_instance ? s : 0) * 36);
       for (int i = 0; i < 36; ++i) st(Pk, TR_A + i, As[i]);
       for (int i = 0; i < 6; ++i)
         for (int j = i; j < 6; ++j) {
@@ -617,7 +618,7 @@ __global__ void k_set_b(const __grid_constant__ ModelC c_model, const StateP S, 
     }
     for (int a = 0; a < 6; ++a) {
       double acc = 0.0;
-      for (int r = 0; r < 6; ++r) acc += task_A(c_model, c_model.t[k], Pk, 6 * r + a) * bk[r];
+      for (int r = 0; r < 6; ++r) acc += task_A(c_model, c_model.t[k < kMaxTasks ? k : 0], Pk, 6 * r + a) * bk[r];
       st(Pk, TR_ATB + a, acc);
     }
   }
@@ -723,6 +724,7 @@ struct loik_solver {
   loik_params prm{};
   ModelC mc{};          // host copy of this solver's constant block
   bool problem_set = false;
+  bool a_user_per = false;  // the caller's task matrices are per instance (loik_solve_init)
   bool debug = false;
   // backward->forward workspace (His, pis, UDinv, Dinv, r) of the home arena is the last backward pass of every
   // instance: true after in-place steps, false after a scheduled solve whose instances migrated without keep_ws
@@ -869,6 +871,13 @@ static int launch_lane(loik_solver* h, cudaStream_t st, const double* src, const
 }
 static bool use_lane(const loik_solver* h) { return h->lane_ok && h->lane_after >= 0 && !h->debug; }
 
+// FwdPassInit stages q through shared memory (blockDim x nq doubles): the block shrinks for models whose q would not fit 48 KB
+static void launch_set_q(loik_solver* h, cudaStream_t st, const double* dq) {
+  int block = kBlock;
+  while (block > 32 && (size_t)block * h->nq * sizeof(double) > 48 * 1024) block /= 2;
+  k_set_q<<<grid_for(h->batch, block), block, (size_t)block * h->nq * sizeof(double), st>>>(h->mc, h->S, dq);
+}
+
 static int ensure_stage(loik_solver* h, size_t bytes, bool need_host) {
   if (need_host && bytes > h->h_stage_bytes) {
     if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -983,6 +992,7 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
   if (params->eq_c_dim != 6)
     return fail(LOIK_ERR_INVALID, "[IkProblemFormulation::IkProblemFormulation]: equality constraint dimension is not 6, problem formulation not supported !!!");
   if (nj < 2 || nj > LOIK_MAX_JOINTS) return fail(LOIK_ERR_INVALID, "loik_create: njoints out of range [2, LOIK_MAX_JOINTS]");
+  static_assert(LOIK_MAX_JOINTS == kMaxJoints && LOIK_MAX_TASKS == kMaxTasksAll, "include/loik_b200.h and loik_device.cuh must agree");
   if (params->num_eq_c < 0 || params->num_eq_c > LOIK_MAX_TASKS) return fail(LOIK_ERR_INVALID, "loik_create: num_eq_c out of range [0, LOIK_MAX_TASKS]");
   if (batch < 1) return fail(LOIK_ERR_INVALID, "loik_create: batch must be >= 1");
   for (int i = 1; i < nj; ++i) {
@@ -1172,10 +1182,11 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
       CKA(cudaFuncSetAttribute(k_iterate_lane<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
       CKA(cudaFuncSetAttribute(k_iterate_lane<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
     }
-    // default switch point: short trees hand the instances still active after 10 sweeps to the lane-parallel kernel (one
-    // Panda-65 536 solve 5.6 -> 2.2 ms at -5 % pipelined throughput); long / branching trees keep the tile kernels (their
-    // record leaves room for 8 instances per SM only) unless the caller asks (loik_set_schedule)
-    h->lane_after = (h->lane_ok && nb <= 12) ? 10 : -1;
+    // default switch point: short trees hand the instances still active after 32 sweeps to the lane-parallel kernel (one
+    // Panda-65 536 solve 5.4 -> 2.8 ms, 57.6 -> 69 M solves/s with 10 solves in flight, -3 % with 32; a switch after 10 sweeps
+    // gives 2.3 ms at 58 / 61 M); long / branching trees keep the tile kernels (their record leaves room for 8 instances
+    // per SM only) unless the caller asks (loik_set_schedule)
+    h->lane_after = (h->lane_ok && nb <= 12) ? 32 : -1;
   }
 #undef CKA
   *out = h;
@@ -1249,21 +1260,22 @@ static int set_problem_consts(loik_solver* h, const double* H_ref, const double*
   M.Hv_inf = hv_inf;  // = |Hv[0]|inf (ik-id-description-optimized.hpp:95)
   M.bounds_per_instance = bounds_shared ? 0 : 1;
   M.href_uniform = 1;
-  M.a_per = A ? 0 : 1;
+  M.a_per = (A && n_ids <= kMaxTasks) ? 0 : 1;  // (more tasks than TaskC slots: the matrices live in the task rows too, k_set_b)
+  sym_blocks(H_ref, M.href[0].A, M.href[0].B, M.href[0].D);  // UpdateReference: one reference broadcast to every joint
+  for (int c = 0; c < 6; ++c) M.href[0].Hv[c] = Hv[c];
   for (int i = 1; i < h->nj; ++i) {
     JointC& J = M.j[i];
-    sym_blocks(H_ref, J.HrA, J.HrB, J.HrD);
-    for (int c = 0; c < 6; ++c) J.Hv[c] = Hv[c];
+    J.href = 0;
     J.task = -1;
     if (bounds_shared) { J.lb = lb[J.idxv]; J.ub = ub[J.idxv]; }
   }
+  std::memset(M.t, 0, sizeof(M.t));
   for (int k = 0; k < n_ids; ++k) {
     const int c = ids[k];
-    M.j[c].task = k;
+    M.j[c].task = (short)k;
+    M.task_joint[k] = (short)c;
+    if (M.a_per) continue;
     TaskC& T = M.t[k];
-    std::memset(&T, 0, sizeof(T));
-    T.joint = c;
-    if (!A) continue;
     double AtA[36];
     for (int i = 0; i < 36; ++i) T.A[i] = A[36 * k + i];
     for (int i = 0; i < 6; ++i)
@@ -1283,14 +1295,16 @@ int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const 
   const size_t q_bytes = (size_t)B * h->nq * sizeof(double);
   const size_t b_bytes = (size_t)(b_per_instance ? B : 1) * nc * 6 * sizeof(double);
   const size_t bd_bytes = (size_t)(bounds_per_instance ? B : 1) * h->nv * sizeof(double);
-  const size_t A_bytes = A_per_instance ? (size_t)B * nc * 36 * sizeof(double) : 0;
   if (loc != LOIK_HOST && loc != LOIK_DEVICE && loc != LOIK_HOST_PINNED) return fail(LOIK_ERR_INVALID, "loik_solve_init: bad loc");
   // batch-shared bounds / task matrices are batch-uniform data like H_ref: always host pointers, they travel in the kernel parameter block
   int rc = set_problem_consts(h, H_ref, v_ref, n_ids, ids, A_per_instance ? nullptr : A, lb, ub, !bounds_per_instance);
   if (rc) return rc;
+  h->a_user_per = A_per_instance != 0;
   const bool md_shared = !bounds_per_instance && h->mc.nmd > 0;  // shared bounds of multi-DoF joints: replicated into their rows (HOST pointers)
-  if (loc != LOIK_DEVICE || md_shared) {
-    rc = ensure_stage(h, q_bytes + b_bytes + 2 * bd_bytes + A_bytes + 64, loc == LOIK_HOST || md_shared);
+  const bool a_rows_shared = h->mc.a_per && !A_per_instance && nc > 0;  // more shared task matrices than TaskC slots: into the task rows (HOST pointer)
+  const size_t A_bytes = A_per_instance ? (size_t)B * nc * 36 * sizeof(double) : (a_rows_shared ? (size_t)nc * 36 * sizeof(double) : 0);
+  if (loc != LOIK_DEVICE || md_shared || a_rows_shared) {
+    rc = ensure_stage(h, q_bytes + b_bytes + 2 * bd_bytes + A_bytes + 64, loc == LOIK_HOST || md_shared || a_rows_shared);
     if (rc) return rc;
   }
   const void *dq, *db = nullptr, *dlb = nullptr, *dub = nullptr, *dA = nullptr;
@@ -1306,20 +1320,21 @@ int loik_solve_init(loik_solver* h, const double* q, const double* H_ref, const 
     rc = to_device(h, ub, bd_bytes, LOIK_HOST, off, st, &dub); if (rc) return rc; off += bd_bytes;
   }
   if (A_per_instance && nc > 0) { rc = to_device(h, A, A_bytes, loc, off, st, &dA); if (rc) return rc; off += A_bytes; }
+  else if (a_rows_shared) { off = q_bytes + b_bytes + 2 * bd_bytes; rc = to_device(h, A, A_bytes, LOIK_HOST, off, st, &dA); if (rc) return rc; }
   // ik_id_data_.Reset(warm_start) + ResetSolver() + FwdPassInit's y/Aty wipe (hpp:346-359, hxx:270-278)
   const int flags = RST_SOLVER | (h->prm.warm_start ? 0 : (RST_WZ | RST_NU | RST_VFF | RST_YATY));
   k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, flags);
   h->ws_valid = true;
-  k_set_q<<<grid_for(B), kBlock, kBlock * h->nq * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);
+  launch_set_q(h, st, (const double*)dq);
   h->launches += 2;
   h->last_list = -1;
-  if (nc > 0) { k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)db, b_per_instance, -1, (const double*)dA); h->launches++; }
+  if (nc > 0) { k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)db, b_per_instance, -1, (const double*)dA, A_per_instance ? 1 : 0); h->launches++; }
   if (bounds_per_instance || md_shared) {
     k_set_bounds<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)dlb, (const double*)dub, bounds_per_instance ? 1 : 0);
     h->launches++;
   }
   CK(cudaGetLastError());
-  if (loc == LOIK_HOST || md_shared) CK(cudaStreamSynchronize(st));  // the staging buffer may be reused by the next call
+  if (loc == LOIK_HOST || md_shared || a_rows_shared) CK(cudaStreamSynchronize(st));  // the staging buffer may be reused by the next call
   h->problem_set = true;
   return LOIK_OK;
 }
@@ -1328,14 +1343,30 @@ int loik_update_references(loik_solver* h, const double* H_refs, const double* v
   (void)stream;
   if (!h || !H_refs || !v_refs) return fail(LOIK_ERR_INVALID, "loik_update_references: null argument");
   ModelC& M = h->mc;
-  for (int i = 0; i < h->nj; ++i) {
+  for (int i = 0; i < h->nj; ++i)
     if (!is_symmetric(H_refs + 36 * i)) return fail(LOIK_ERR_UNSUPPORTED, "loik_update_references: H_refs[i] must be symmetric");
+  // distinct (H_ref, v_ref) pairs go to the reference table of the parameter block, joints point into it
+  std::vector<int> entry(h->nj, 0), first;
+  for (int i = 1; i < h->nj; ++i) {
+    int e = -1;
+    for (size_t k = 0; k < first.size() && e < 0; ++k)
+      if (!std::memcmp(H_refs + 36 * i, H_refs + 36 * first[k], 36 * sizeof(double)) && !std::memcmp(v_refs + 6 * i, v_refs + 6 * first[k], 6 * sizeof(double))) e = (int)k;
+    if (e < 0) { e = (int)first.size(); first.push_back(i); }
+    entry[i] = e;
+  }
+  if ((int)first.size() > kMaxHref) return fail(LOIK_ERR_UNSUPPORTED, "loik_update_references: more distinct (H_ref, v_ref) pairs than the parameter block holds (kMaxHref)");
+  for (int i = 0; i < h->nj; ++i) {
     double Hv[6], n = 0;
     for (int a = 0; a < 6; ++a) { Hv[a] = 0; for (int c = 0; c < 6; ++c) Hv[a] += H_refs[36 * i + 6 * a + c] * v_refs[6 * i + c]; n = std::max(n, std::fabs(Hv[a])); }
     if (n > M.Hv_inf) M.Hv_inf = n;  // only grows (ik-id-description-optimized.hpp:115-117)
-    if (i >= 1) { sym_blocks(H_refs + 36 * i, M.j[i].HrA, M.j[i].HrB, M.j[i].HrD); for (int a = 0; a < 6; ++a) M.j[i].Hv[a] = Hv[a]; }
+    if (i >= 1) {
+      HrefC& R = M.href[entry[i]];
+      sym_blocks(H_refs + 36 * i, R.A, R.B, R.D);
+      for (int a = 0; a < 6; ++a) R.Hv[a] = Hv[a];
+      M.j[i].href = (short)entry[i];
+    }
   }
-  M.href_uniform = 0;
+  M.href_uniform = first.size() <= 1 ? 1 : 0;
   return LOIK_OK;
 }
 
@@ -1491,7 +1522,7 @@ int loik_fwd_pass_init(loik_solver* h, const double* q, int32_t loc, void* strea
   if (loc != LOIK_DEVICE) { rc = ensure_stage(h, q_bytes + 64, loc == LOIK_HOST); if (rc) return rc; }
   const void* dq;
   rc = to_device(h, q, q_bytes, loc, 0, st, &dq); if (rc) return rc;
-  k_set_q<<<grid_for(h->batch), kBlock, kBlock * h->nq * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);
+  launch_set_q(h, st, (const double*)dq);
   h->launches++;
   CK(cudaGetLastError());
   if (loc == LOIK_HOST) CK(cudaStreamSynchronize(st));
@@ -1555,12 +1586,13 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
   ModelC& M = h->mc;
   // problem_.UpdateEqConstraint(c_id, Ai, bi) (ik-id-description-optimized.hpp:178-218)
   int k = -1;
-  for (int t = 0; t < h->nc; ++t) if (M.t[t].joint == c_id) k = t;
+  for (int t = 0; t < h->nc; ++t) if (M.task_joint[t] == c_id) k = t;
   if (k < 0) return fail(LOIK_ERR_INVALID, "[IkProblemFormulation::UpdateEqConstraint]: constraint doesn't yet exist at link 'c_id' !!! ");
-  if ((A_per_instance != 0) != (M.a_per != 0))
+  if ((A_per_instance != 0) != h->a_user_per)
     return fail(LOIK_ERR_INVALID, "loik_solve_task: Ai must be per instance exactly when the task matrices of loik_solve_init were (all tasks of a handle "
                                   "keep their matrices in the same place)");
-  if (!A_per_instance) {
+  const bool a_rows_shared = M.a_per && !A_per_instance;
+  if (!M.a_per) {
     TaskC& T = M.t[k];
     double AtA[36];
     for (int i = 0; i < 36; ++i) T.A[i] = Ai[i];
@@ -1570,21 +1602,22 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
   }
   const int B = h->batch;
   const size_t q_bytes = (size_t)B * h->nq * sizeof(double), b_bytes = (size_t)(b_per_instance ? B : 1) * 6 * sizeof(double);
-  const size_t A_bytes = A_per_instance ? (size_t)B * 36 * sizeof(double) : 0;
-  if (loc != LOIK_DEVICE) { rc = ensure_stage(h, q_bytes + b_bytes + A_bytes + 64, loc == LOIK_HOST); if (rc) return rc; }
+  const size_t A_bytes = A_per_instance ? (size_t)B * 36 * sizeof(double) : (a_rows_shared ? 36 * sizeof(double) : 0);
+  if (loc != LOIK_DEVICE || a_rows_shared) { rc = ensure_stage(h, q_bytes + b_bytes + A_bytes + 64, loc == LOIK_HOST || a_rows_shared); if (rc) return rc; }
   const void *dq = nullptr, *db, *dA = nullptr;
   if (q) { rc = to_device(h, q, q_bytes, loc, 0, st, &dq); if (rc) return rc; }
   rc = to_device(h, bi, b_bytes, loc, q_bytes, st, &db); if (rc) return rc;
   if (A_per_instance) { rc = to_device(h, Ai, A_bytes, loc, q_bytes + b_bytes, st, &dA); if (rc) return rc; }
+  else if (a_rows_shared) { rc = to_device(h, Ai, A_bytes, LOIK_HOST, q_bytes + b_bytes, st, &dA); if (rc) return rc; }
   const int flags = RST_SOLVER | (h->prm.warm_start ? 0 : (RST_WZ | RST_NU | RST_VFF | RST_YATY));
   k_reset<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, flags);
   h->ws_valid = true;
-  k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)db, b_per_instance, k, (const double*)dA);
-  if (q) k_set_q<<<grid_for(B), kBlock, kBlock * h->nq * sizeof(double), st>>>(h->mc, h->S, (const double*)dq);  // else: keep the device-resident q (loik_integrate)
+  k_set_b<<<grid_for(B, 128), 128, 0, st>>>(h->mc, h->S, (const double*)db, b_per_instance, k, (const double*)dA, A_per_instance ? 1 : 0);
+  if (q) launch_set_q(h, st, (const double*)dq);  // else: keep the device-resident q (loik_integrate)
   h->launches += 3;
   h->last_list = -1;
   CK(cudaGetLastError());
-  if (loc == LOIK_HOST) CK(cudaStreamSynchronize(st));
+  if (loc == LOIK_HOST || a_rows_shared) CK(cudaStreamSynchronize(st));
   if (h->prm.max_iter < 2) return LOIK_OK;
   return solve_scheduled(h, st, 0, h->prm.max_iter);
 }

@@ -70,7 +70,7 @@ def test_model_validation_needs_no_gpu():
     m.parent = m.parent.copy(); m.parent[2] = 5
     with pytest.raises(RuntimeError, match="parents"):
         solver.make_solver(m, P, 4)
-    many = robots._build("many_md", [(f"s{i}", i, "S", None, (0.1, 0, 0), (0, 0, 0), None, None, 1.0) for i in range(9)])
+    many = robots._build("many_md", [(f"s{i}", i, "S", None, (0.1, 0, 0), (0, 0, 0), None, None, 1.0) for i in range(17)])  # kMaxMd = 16
     with pytest.raises(RuntimeError, match="multi-DoF"):
         solver.make_solver(many, P, 4)
     with pytest.raises(RuntimeError, match="equality constraint dimension is not 6"):

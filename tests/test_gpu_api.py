@@ -172,3 +172,70 @@ def test_schedule_knobs_do_not_change_results():
     with pytest.raises(KeyError):
         G.set_schedule(lane_ctas=3)
     G.close()
+
+
+def test_large_model_100_joints_16_tasks():
+    """The reference has no size limit (state sized from model.njoints, loik-loid-data-optimized.hxx:40-104).  A random tree
+    of 100 joints with 16 tasks (more than the 8 task matrices the parameter block holds: A goes to the task rows) and
+    per-joint references (UpdateReferences, one (H_ref, v_ref) pair per joint up to the table size): fused steps and full
+    solves against the oracle."""
+    from oracle import recursion
+    from tests.helpers import check_abs_or_rel
+    model = robots.random_tree(100, seed=123, branching=0.15)
+    assert model.nj == 101
+    rng = np.random.default_rng(7)
+    nc = 16
+    tasks = sorted(rng.choice(np.arange(5, model.nj), size=nc, replace=False).tolist())
+    B = 40
+    pb = problems.random_batch(model, B, seed=3, task_joints=tasks)
+    pb["Ais"] = np.eye(6)[None] + 0.2 * rng.standard_normal((nc, 6, 6))
+    params = dict(problems.FIXTURE_PARAMS, max_iter=60, num_eq_c=nc)
+    # 20 distinct references spread over the joints (the table holds 33)
+    H_pool = [np.eye(6) + 0.1 * (lambda a: a @ a.T)(rng.standard_normal((6, 6))) for _ in range(20)]
+    v_pool = 0.05 * rng.standard_normal((20, 6))
+    pick = rng.integers(0, 20, size=model.nj)
+    H_refs, v_refs = np.stack([H_pool[k] for k in pick]), v_pool[pick]
+    G = _gpu(model, params, B)
+    assert G.get_schedule()["lane_available"] in (0, 1)
+    G.set_debug(True)
+    _solve_init(G, pb)
+    G.UpdateReferences(H_refs, v_refs)
+    G.ResetRecursion()
+    O = []
+    for i in range(B):
+        o = recursion.FirstOrderLoikOptimized(model, **ctor_kwargs(params))
+        o.SolveInit(pb["q"][i], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"][i], pb["lb"], pb["ub"])
+        o.UpdateReferences(H_refs, v_refs)
+        o.ResetSolver()
+        O.append(o)
+    for it in (1, 2):
+        stopped = []
+        for o in O:
+            o.UpdatePrev(); o.ResetInfNorms(); o.FwdPass1(); o.BwdPassOptimizedVisitor(); o.FwdPass2OptimizedVisitor(); o.BoxProj(); o.DualUpdate()
+            o.ComputeResiduals(); o.CheckConvergence()
+            if it > 1:
+                o.CheckFeasibility()
+            stopped.append(o.get_convergence_status() or o.get_primal_infeasibility_status())
+            if not stopped[-1]:
+                o.UpdateMu()  # (the loop of Solve() leaves before UpdateMu when a flag is raised, hpp:421-446)
+        G.StepBackward(); G.StepForward(); G.StepResidual()
+        H, nu, z, y, mu = G.His, G.nu, G.z, G.yis, G.get_mu()
+        for i, o in enumerate(O):
+            check_abs_or_rel(H[i], o.His[1:], 1e-10, f"it{it} His")
+            check_abs_or_rel(nu[i], o.nu, 1e-10, f"it{it} nu")
+            check_abs_or_rel(z[i], o.z, 1e-10, f"it{it} z")
+            check_abs_or_rel(y[i], o.yis, 1e-10, f"it{it} yis")
+            assert mu[i] == o.get_mu()
+        if any(stopped):
+            break
+    G.set_debug(False)
+    G.Solve()
+    it, zz = G.get_iter(), G.z
+    for i, o in enumerate(O):
+        o.Solve()
+        assert it[i] == o.get_iter(), f"instance {i}"
+        assert rel_inf(zz[i], o.z) < 1e-6
+    G.close()
+    too_big = robots.random_tree(104, seed=1)
+    with pytest.raises(RuntimeError, match="njoints out of range"):
+        _gpu(too_big, problems.bench_params(1), 4)
