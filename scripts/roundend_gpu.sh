@@ -1,22 +1,30 @@
 #!/bin/bash
-# Everything the round's profiles/ are made from, in one gpurun call (1 GPU): tests, bench lines, ncu launch list + full captures.
-TAG=${1:-r1}
+# Everything the round's profiles/ are made from, in one gpurun call (1 GPU): tests, bench lines, ncu launch list + full captures
+# of the benched build, DRAM traffic of the roofline kernel (-> profiles/traffic.json via scripts/summarize_profiles.py).
+TAG=${1:-r2}
 mkdir -p gpurun_out
 echo "== pytest -m gpu"; python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-echo "== bench (default = panda)"; python bench.py > gpurun_out/bench_${TAG}_panda.json 2> gpurun_out/bench_${TAG}_panda.err; tail -c 600 gpurun_out/bench_${TAG}_panda.json
-for w in ur10 talos; do python bench.py --workload $w --no-cpu-baseline > gpurun_out/bench_${TAG}_$w.json 2> gpurun_out/bench_${TAG}_$w.err; done
+echo "== bench (default: panda headline + ur10 / talos sub-records)"
+python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; tail -c 300 gpurun_out/bench_${TAG}.json
+echo "== bench as the driver runs it"; python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_${TAG}_driver.json 2> gpurun_out/bench_${TAG}_driver.err
 echo "== reference arm"; python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_${TAG}_reference.json 2>&1
 echo "== tracking / single instance"
 python scripts/bench_tracking.py > gpurun_out/tracking_${TAG}_panda_warm.json 2>/dev/null
-python scripts/bench_tracking.py --cold > gpurun_out/tracking_${TAG}_panda_cold.json 2>/dev/null
 python scripts/bench_tracking.py --robot talos --batch 16384 --cpu-sample 1024 > gpurun_out/tracking_${TAG}_talos_warm.json 2>/dev/null
 python scripts/single_instance.py > gpurun_out/single_instance_${TAG}.json 2>/dev/null
+echo "== schedule sweep (switch point of the lane-parallel kernel)"
+LANE_AFTERS=-1,10,32 DEPTHS=1,4,10,32 python scripts/lane_perf.py panda 2>&1 | tail -3 > gpurun_out/lane_sweep_${TAG}.txt
+LANE_AFTERS=-1,32 DEPTHS=1,4,16 python scripts/lane_perf.py ur10 2>&1 | tail -2 >> gpurun_out/lane_sweep_${TAG}.txt
+LANE_AFTERS=-1,16 DEPTHS=1,4,16 python scripts/lane_perf.py talos 2>&1 | tail -2 >> gpurun_out/lane_sweep_${TAG}.txt
+cat gpurun_out/lane_sweep_${TAG}.txt
 echo "== ncu launch list"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_${TAG}.csv \
-    python bench.py --steps 2 --warmup 3 --pipeline 1 --no-cpu-baseline > gpurun_out/launches_${TAG}.log 2>&1
-echo "== ncu full"
+    python bench.py --workload panda --steps 2 --warmup 3 --pipeline 1 --no-cpu-baseline > gpurun_out/launches_${TAG}.log 2>&1
+echo "== ncu full: the roofline kernel (k_iterate, one dense iteration per launch) and the lane-parallel kernel"
 for r in panda ur10 talos; do
-  ncu --set full --clock-control none --import-source on -k regex:k_iterate -s 10 -c 2 -f -o gpurun_out/prof_${TAG}_$r \
-      python scripts/quick_perf.py $r > gpurun_out/prof_${TAG}_$r.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:k_iterate -s 6 -c 2 -f -o gpurun_out/prof_${TAG}_$r \
+      python scripts/lane_prof.py $r -1 1 > gpurun_out/prof_${TAG}_$r.log 2>&1
 done
-ls -la gpurun_out | tail -20
+ncu --set full --clock-control none --import-source on -k regex:k_iterate_lane -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_lane_panda \
+    python scripts/lane_prof.py panda 0 4 > gpurun_out/prof_${TAG}_lane_panda.log 2>&1
+ls -la gpurun_out | tail -24

@@ -27,4 +27,17 @@ for name, B in (("panda9", 100), ("talos", 70)):
     S.ResetRecursion(); S.StepBackward(); S.StepForward(); S.StepResidual()
     _ = S.His, S.norms(), S.liMi, S.stats()
     S.close()
+    # the lane-parallel shared-memory kernel: whole solves, the hand-over from a packed arena, four groups per instance,
+    # per-instance task matrices, the backward-pass workspace brought home
+    rng = np.random.default_rng(0)
+    for sched in (dict(lane_after=0), dict(lane_after=6), dict(lane_after=0, lane_groups_per_instance=4)):
+        S = lk.make_solver(model, problems.bench_params(len(pb["ids"]), max_iter=40), B)
+        S.set_schedule(**sched)
+        S.set_keep_workspace(True)
+        A = np.eye(6)[None, None] + 0.1 * rng.standard_normal((B, len(pb["ids"]), 6, 6))
+        S.SolveInit(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], A, pb["bis"], pb["lb"], pb["ub"])
+        S.Solve()
+        _ = S.His, S.z
+        S.IterateFixed(3)
+        S.close()
     print(name, "ok")

@@ -1,7 +1,8 @@
 #!/bin/bash
-# development aid: sweep of the launch-schedule knobs (env) on the pipelined solve
-export CUDA_DEVICE_MAX_CONNECTIONS=32
+# development aid: sweep of the launch-schedule knobs (loik_set_schedule, through scripts/lane_perf.py's SCHED variable)
+# on one solve alone and on pipelined solves
 R=${1:-panda}
-for cfg in "LOIK_DENSE=4" "LOIK_DENSE=3" "LOIK_DENSE=5" "LOIK_HI_AFTER=-1" "LOIK_HI_AFTER=4" "LOIK_HI_AFTER=16" "LOIK_REPS=3" "LOIK_REPS=1" "LOIK_GROWTH=1.5" "LOIK_REPS=3 LOIK_GROWTH=1.5" "LOIK_DENSE=5 LOIK_REPS=3"; do
-  echo -n "$cfg: "; env $cfg PIPE=1 DEPTHS=32 python scripts/quick_perf.py $R 2>&1 | grep pipeline
+for cfg in "dense_sweeps=4" "dense_sweeps=3" "dense_sweeps=5" "hi_priority_after=-1" "hi_priority_after=4" "repack_reps=3" "repack_reps=1" \
+           "repack_growth=1.5" "drop_workspace=0" "lane_warps_per_cta=2"; do
+  echo -n "$cfg: "; SCHED=$cfg LANE_AFTERS=${LANE_AFTERS:-32} DEPTHS=${DEPTHS:-1,10,32} python scripts/lane_perf.py $R 2>&1 | tail -1 | cut -c60-
 done

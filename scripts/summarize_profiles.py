@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r1"
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r2"
 
 KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
@@ -41,7 +41,7 @@ def launch_list():
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(OUT, f"{TAG}_launches.txt"), "w") as f:
         f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised): compare SHARES, not absolutes\n")
-        f.write(f"# command: python bench.py --steps 2 --warmup 3 --pipeline 1 --no-cpu-baseline ({len(rows)} launches captured)\n")
+        f.write(f"# command: python bench.py --workload panda --steps 2 --warmup 3 --pipeline 1 --no-cpu-baseline ({len(rows)} launches captured)\n")
         f.write(f"{'kernel':60s} {'launches':>9s} {'total_us':>12s} {'share':>7s} {'avg_us':>10s}\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k[:60]:60s} {n:9d} {t / 1e3:12.1f} {t / tot:7.3f} {t / n / 1e3:10.2f}\n")
@@ -64,7 +64,7 @@ def full(name):
         out.append(d)
     det = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
     with open(os.path.join(OUT, f"{TAG}_ncu_full_{name}.txt"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:k_iterate (python scripts/quick_perf.py {name})\n")
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:k_iterate (scripts/roundend_gpu.sh; {name})\n")
         for d in out:
             f.write(json.dumps(d, indent=1) + "\n")
         f.write("\n# ---- details page of the first captured launch ----\n")
@@ -83,6 +83,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     launch_list()
     traffic = {}
+    full("lane_panda")
     for nm in ("panda", "talos", "ur10"):
         o = full(nm)
         if o:
@@ -99,5 +100,9 @@ if __name__ == "__main__":
                                         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct",
                                         "smsp__inst_executed.sum")})
     if traffic:
+        sys.path.insert(0, ROOT)
+        import bench
+        traffic["source_sha"] = bench.source_sha()  # the kernel sources these captures were taken on (bench.py reports a mismatch)
+        traffic["tag"] = TAG
         with open(os.path.join(OUT, "traffic.json"), "w") as f:
             json.dump(traffic, f)
