@@ -21,8 +21,10 @@ echo "== ncu launch list"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --workload panda --steps 2 --warmup 3 --pipeline 1 --no-cpu-baseline > gpurun_out/launches_${TAG}.log 2>&1
 echo "== ncu full: the roofline kernel (k_iterate, one dense iteration per launch) and the lane-parallel kernel"
+# (scripts/lane_prof.py <robot> -1 1: three fixed-iteration launches of ONE dense iteration each, then a Solve(); the second
+#  and third of those launches are captured)
 for r in panda ur10 talos; do
-  ncu --set full --clock-control none --import-source on -k regex:k_iterate -s 6 -c 2 -f -o gpurun_out/prof_${TAG}_$r \
+  ncu --set full --clock-control none --import-source on -k regex:k_iterate -s 1 -c 2 -f -o gpurun_out/prof_${TAG}_$r \
       python scripts/lane_prof.py $r -1 1 > gpurun_out/prof_${TAG}_$r.log 2>&1
 done
 ncu --set full --clock-control none --import-source on -k regex:k_iterate_lane -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_lane_panda \
