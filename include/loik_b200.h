@@ -121,7 +121,7 @@ typedef struct loik_schedule {
   int32_t lane_warps_per_cta; /* warps (of 4 instances each) per CTA of the lane-parallel kernel; 0 = chosen from the record size */
   int32_t lane_groups_per_instance; /* 8-lane groups per instance in that kernel: 1 (four instances per warp, each group sweeps the
                                        whole tree), 4 (one instance per warp, the groups sweep different chains of a branching tree
-                                       level by level), 0 = default (1: the four-group form is not faster yet) */
+                                       level by level through a host-built step table), 0 = default (4 when the tree branches, else 1) */
   int32_t drop_workspace;     /* tile kernels: drop the consumed backward->forward workspace lines from L2 (discard.global.L2)
                                  instead of letting them be written back to HBM; never applied with loik_set_keep_workspace */
   /* read-only (ignored by loik_set_schedule) */
@@ -208,6 +208,12 @@ LOIK_API void loik_destroy(loik_solver* h);
  * backward warp, backward level, forward warp, forward level}; per span {lo, hi, nv of a multi-DoF joint or 0}.
  * Returns n, or < 0 (same validation and messages as loik_create; cap too small). */
 LOIK_API int32_t loik_model_layout(const loik_model_desc* model, const loik_params* params, int32_t* out, int32_t cap);
+/* The step table of the lane-parallel kernel's wide geometry (four 8-lane groups of a warp on different chains of one
+ * instance), same conventions: out = {#backward steps, #forward steps}, then for every step of the backward order and
+ * of the forward order four entries (group 0..3) of {joint, parent, flags (1 valid, 2 first of a chain, 4 result goes to a
+ * pending block, 8 root joint, 16 reads pending blocks), offset of the joint's block in the shared-memory record, pending
+ * block written, aligned axis index or -1, offset of the parent's block}. */
+LOIK_API int32_t loik_wide_table(const loik_model_desc* model, const loik_params* params, int32_t* out, int32_t cap);
 LOIK_API const char* loik_last_error(void);
 
 /* ---- problem set-up -------------------------------------------------------------------------- */

@@ -55,6 +55,7 @@ struct JointC {
   short nvj, mblk;                  // multi-DoF joints: nv of the joint (3 / 6), index of its md block
   short sidx;                       // aligned 1-DoF joints: the component of a [lin; ang] 6-vector S selects (S = e_sidx); -1 otherwise
   short href;                       // this joint's entry of ModelC::href
+  short loff;                       // k_iterate_lane<4>: offset of the joint's block in the shared-memory instance record (assign_segments)
   short pin[kMaxPin];               // the pending blocks read (one per tree edge: single writer, no read-modify-write)
 };
 
@@ -110,6 +111,7 @@ struct ModelC {
   int nseg, nblevel, nflevel, nwarp;
   int nmd, nv, nq, href_uniform;   // number of multi-DoF joints; model.nv, model.nq; every joint shares H_ref / v_ref (UpdateReference)
   SegC seg[kMaxSeg];
+  int nsb, nsf;                    // steps of the wide sweeps of k_iterate_lane<4> (backward / forward order; build_wide_table)
   int nspan, a_per;                // a_per: A_k (and A_k^T A_k) differ per instance: rows TR_A / TR_ATA of the task blocks, not TaskC
   SpanC span[kMaxSpan];
   Offs off;

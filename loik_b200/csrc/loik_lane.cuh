@@ -39,12 +39,17 @@ enum : int { LS_MU = 0, LS_BINF = 1, LS_CTL = 2, LS_RES = 3, LS_ROWS = 8 };
 // jointPlacements[i] * M_i(q) (FwdPassInit, hxx:263-264), built once when the instance is loaded (q does not change
 // during a solve) instead of three times per joint and iteration.
 enum : int { LJ_V = 0, LJ_F = 6, LJ_FD = 12, LJ_NU = 18, LJ_Z = 19, LJ_W = 20, LJ_T = 21, LJ_SQ = 22, LJ_CQ = 23, LJ_LB = 24,
-             LJ_UB = 25, LJ_COPY = 26, LJ_DINV = 26, LJ_R = 27, LJ_UD = 28, LJ_HP = 36, LJ_XF = 84, LJ_ROWS = 96 };  // XF: liMi = (R 9, t 3)
+             LJ_UB = 25, LJ_COPY = 26, LJ_DINV = 26, LJ_R = 27, LJ_UD = 28, LJ_HP = 36, LJ_XF = 84, LJ_ROWS = 96,    // XF: liMi = (R 9, t 3)
+             // GPI = 4: the four groups of a warp work on DIFFERENT joints of one record at the same time; a joint's block starts
+             // 4 x (its group) doubles into a 108-double slot (JointC::loff), so that the groups' 16 B broadcast loads hit
+             // four different bank quads and their 64 B per-lane accesses pair up into two wavefronts
+             LJ_SLOT_WIDE = 108 };
 static_assert((int)LJ_V == (int)JR_V && (int)LJ_F == (int)JR_F && (int)LJ_FD == (int)JR_FD && (int)LJ_NU == (int)JR_NU && (int)LJ_Z == (int)JR_Z && (int)LJ_W == (int)JR_W && (int)LJ_T == (int)JR_T &&
               (int)LJ_SQ == (int)JR_JQ && (int)LJ_LB == (int)JR_LB && (int)LJ_UB == (int)JR_UB, "the copied part of a joint record mirrors the tile rows");
 enum : int { LT_Y = TR_Y, LT_ATY = TR_ATY, LT_B = TR_B, LT_ATB = TR_ATB, LT_ROWS = 24 };  // (the tile's task block also holds per-instance A, A^T A)
 enum : int { LP_HP = 0, LP_F = 48, LP_ROWS = 56 };       // pending block of a tree edge: [H | p] contribution, F contribution
-enum : int { LX_V = 0, LX_T = 16, LX_ROWS = 96 };        // exchange scratch: 16 scalars, 8 rows of 10 (transposes)
+enum : int { LX_V = 0, LX_T = 16, LX_ROWS = 96,          // exchange scratch: 16 scalars, 8 rows of 10 (transposes)
+             LX_DUMMY = 96, LX_ROWS_WIDE = 200 };        // GPI = 4: + a block that takes the stores of a group without work; stride = 8 (mod 16)
 // ---- per-CTA constants in shared memory ---------------------------------------------------------------------------
 enum : int { CJ_HREFR = 0, CJ_HREF = 48, CJ_HV = 96, CJ_ROWS = 104 };  // per joint: [Href + rho I | -Hv] and Href as 6 rows of 8, Hv (8)
 enum : int { CT_AR = 0, CT_ATR = 48, CT_ATA = 96, CT_ROWS = 144 };  // per task: A, A^T, A^T A as 6 rows of 8
@@ -53,22 +58,26 @@ enum : int { GC_STRIDE = 24, GC_TOT = 96, GC_ROWS = 120 };  // GPI = 4: the grou
 
 struct LaneDims {
   int joint0, task0, tmat0, pend0, xch, gc, stride;  // offsets inside an instance record, record stride
-  int ctask0, csize, cpad;                    // constants: first task block, size, size padded to 128 B
+  int ctask0, csize, tab0, cpad;              // constants: first task block, size, step table of the wide sweeps, size padded to 128 B
+  int xstride;                                // exchange scratch per group
 };
-__host__ __device__ inline LaneDims lane_dims(const int nb, const int nc, const int npend, const int href_uniform, const int gpi, const int a_per) {
+__host__ __device__ inline LaneDims lane_dims(const int nb, const int nc, const int npend, const int href_uniform, const int gpi, const int a_per,
+                                              const int wide_steps) {
   LaneDims D;
   D.joint0 = LS_ROWS;
-  D.task0 = D.joint0 + LJ_ROWS * nb;
+  D.task0 = D.joint0 + (gpi > 1 ? LJ_SLOT_WIDE : LJ_ROWS) * nb;
   D.tmat0 = D.task0 + LT_ROWS * nc;          // per-instance task matrices (A, A^T, A^T A as in the constants), if any
   D.pend0 = D.tmat0 + (a_per ? CT_ROWS * nc : 0);
   D.xch = D.pend0 + LP_ROWS * npend;
-  D.gc = D.xch + LX_ROWS * gpi;  // (one exchange scratch per group)
+  D.xstride = gpi > 1 ? LX_ROWS_WIDE : LX_ROWS;
+  D.gc = D.xch + D.xstride * gpi;  // (one exchange scratch per group)
   int sz = (D.gc + (gpi > 1 ? GC_ROWS : 0) + 7) & ~7;
   if ((sz & 15) == 0) sz += 8;  // stride = 8 (mod 16) doubles: the records of two neighbouring groups cover different banks
   D.stride = sz;
   D.ctask0 = CJ_ROWS * (href_uniform ? 1 : nb);  // one [Href | -Hv] block when every joint shares the reference (UpdateReference)
   D.csize = D.ctask0 + CT_ROWS * nc;
-  D.cpad = (D.csize + 15) & ~15;
+  D.tab0 = (D.csize + 1) & ~1;                        // 4 x int4 = 8 doubles per step of the wide sweeps (backward order, then forward order)
+  D.cpad = (D.tab0 + (gpi > 1 ? 8 * wide_steps : 0) + 15) & ~15;
   return D;
 }
 inline size_t lane_smem_bytes(const LaneDims& D, const int warps, const int gpi) { return ((size_t)D.cpad + (size_t)warps * (kLaneI / gpi) * D.stride) * sizeof(double); }
@@ -84,6 +93,7 @@ struct LaneP {
   int iters;           // fixed mode: iterations per instance
   int fixed;           // stopping disabled (throughput mode)
   int keep_ws;         // the workspace of the last backward pass goes home too (loik_set_keep_workspace)
+  const int4* tab;     // GPI = 4: step table of the wide sweeps (ModelC::nsb backward steps, then ModelC::nsf forward steps, 4 entries each)
 };
 
 LOIK_DEV void lds6(const double* p, double (&v)[6]) {
@@ -114,13 +124,14 @@ LOIK_DEV void lane_copy_rows(const int total, const int l, const int nl, F&& bod
     for (int u = 0; u < PER; ++u) { const int e = e0 + nl * u + l; if (e < total) body(e, 1, u); }
   }
 }
-LOIK_DEV void lane_load(const ModelC& M, const LaneDims& D, const double* T, double* I, const int l, const int nl) {
+LOIK_DEV int lane_joff(const ModelC& M, const bool wide, const int j) { return wide ? M.j[j + 1].loff : LJ_ROWS * j; }  // block of joint j + 1
+LOIK_DEV void lane_load(const ModelC& M, const LaneDims& D, const double* T, double* I, const int l, const int nl, const bool wide) {
   const Offs& O = M.off;
   double buf[8];
   lane_copy_rows<8>(LJ_COPY * M.nb, l, nl, [&](const int e, const int phase, const int u) {
     const int j = e / LJ_COPY, r = e - LJ_COPY * j;
     if (phase == 0) buf[u] = __ldcs(T + (size_t)(O.joint0 + JR_ROWS * j + r) * 32);
-    else I[D.joint0 + LJ_ROWS * j + r] = buf[u];
+    else I[D.joint0 + lane_joff(M, wide, j) + r] = buf[u];
   });
   lane_copy_rows<8>(LT_ROWS * M.nc, l, nl, [&](const int e, const int phase, const int u) {
     const int k = e / LT_ROWS, r = e - LT_ROWS * k;
@@ -147,11 +158,11 @@ LOIK_DEV void lane_load(const ModelC& M, const LaneDims& D, const double* T, dou
   }
 }
 // what retire_rows (loik_solver.cu) sends home: v, f, F, nu, z, w, T | y, Aty | mu, control, residuals
-LOIK_DEV void lane_retire(const ModelC& M, const LaneDims& D, const double* I, double* Th, const int l, const int nl) {
+LOIK_DEV void lane_retire(const ModelC& M, const LaneDims& D, const double* I, double* Th, const int l, const int nl, const bool wide) {
   const Offs& O = M.off;
   for (int e = l; e < JR_JQ * M.nb; e += nl) {
     const int j = e / JR_JQ, r = e - JR_JQ * j;
-    Th[(size_t)(O.joint0 + JR_ROWS * j + r) * 32] = I[D.joint0 + LJ_ROWS * j + r];
+    Th[(size_t)(O.joint0 + JR_ROWS * j + r) * 32] = I[D.joint0 + lane_joff(M, wide, j) + r];
   }
   for (int e = l; e < TR_B * M.nc; e += nl) {
     const int k = e / TR_B, r = e - TR_B * k;
@@ -164,10 +175,10 @@ LOIK_DEV void lane_retire(const ModelC& M, const LaneDims& D, const double* I, d
   }
 }
 // opt-in: His (21 packed scalars), pis, UDinv, Dinv, r of the last backward pass
-LOIK_DEV_CALL void lane_retire_workspace(const ModelC& M, const int joint0, const double* I, double* Th, const int l, const int nl) {
+LOIK_DEV_CALL void lane_retire_workspace(const ModelC& M, const int joint0, const double* I, double* Th, const int l, const int nl, const bool wide) {
   const Offs& O = M.off;
   for (int j = l; j < M.nb; j += nl) {
-    const double* Pj = I + joint0 + LJ_ROWS * j;
+    const double* Pj = I + joint0 + lane_joff(M, wide, j);
     double* Pd = Th + (size_t)(O.joint0 + JR_ROWS * j) * 32;
     for (int a = 0; a < 3; ++a)
       for (int b = 0; b < 3; ++b) {
@@ -480,29 +491,37 @@ LOIK_DEV void lane_residual(const ModelC& M, const LaneDims& D, const double* CB
 
 // ---------------------------------------------------------------------------------------------
 // GPI = 4: the same three sweeps with the four groups of a warp on different chains of ONE instance.  SIMT runs one
-// instruction stream per warp, so the groups only work in parallel if they execute the SAME steps: every sweep is a
-// uniform loop of `steps` joint steps (the longest chain of the round); group g works on joint hi - t (resp. lo + t) of
-// its own chain while that is inside [lo, hi] (`valid`) and afterwards repeats the arithmetic on a clamped joint with
-// every store, norm update and hand-over switched off.  All exchanges between lanes are synchronised at the top level of
-// the loop (full-mask __syncwarp(), free in converged code); branches that depend on the joint (task, root, pending
-// blocks) are short and contain no synchronisation, except the rare task update (group mask).
+// instruction stream per warp, so the groups only work in parallel if they execute the SAME instructions: every sweep is
+// one flat loop over the steps of a host-built table (build_wide_table, loik_solver.cu; WideStep), four entries per step:
+// what group g does in that step -- the joint, whether the step is real (`valid`), whether it starts a chain, where its
+// result goes.  A group without work in a step repeats the arithmetic on joint 1 with every store redirected to a
+// scratch block of its own and every norm update fed a zero, so the hot path has no branch that differs between the
+// groups; the per-joint branches that remain (task on the joint, contributions of several children, unaligned axis) are
+// rare.  All exchanges between lanes are synchronised at the top level of the loop (full-mask __syncwarp(), free in
+// converged code).  The level order of the table (children before parents towards the root, parents first on the way
+// out) makes the pending blocks and the parents' v rows valid when a step reads them: a step's stores are separated
+// from the next step's loads by the __syncwarp() at its top.
 // ---------------------------------------------------------------------------------------------
-LOIK_DEV void wide_backward(const ModelC& M, const LaneDims& D, const double* CB, double* I, double* X, const int l, const double mu,
-                            const double mu_eq, const int lo, const int hi, const int steps) {
+struct WideStep { int joint_parent, flags, loff_pout, sidx_ploff; };  // joint | parent << 16; WF_*; JointC::loff | pout << 16; (aligned axis index or -1) & 0xffff | parent's loff << 16
+enum : int { WF_VALID = 1, WF_FIRST = 2, WF_GIVE = 4, WF_ROOT = 8, WF_PINS = 16 };  // FIRST: first step of a chain; GIVE: result goes to a pending block
+
+LOIK_DEV void wide_backward(const ModelC& M, const LaneDims& D, const double* CB, double* I, double* X, const int l, const int g,
+                            const double mu, const double mu_eq, const int4* tab, const int nsteps) {
   const double rho = M.rho;
   const int lc = l < 6 ? l : 6;
   const bool isp = l >= 6;
   const double facv = isp ? -rho : 0.0;
   double* XT = X + LX_T;
+  double* XD = X + LX_DUMMY;
   const double* XTrow = XT + 10 * lc;
   const int cstep = M.href_uniform ? 0 : CJ_ROWS;
   double cc[6] = {0, 0, 0, 0, 0, 0};
-  bool have_carry = false;
-  for (int t = 0; t < steps; ++t) {
-    const bool valid = hi - t >= lo;
-    const int i = valid ? hi - t : lo;
-    const JointC& J = M.j[i];
-    double* Pj = I + D.joint0 + LJ_ROWS * (i - 1);
+  for (int s = 0; s < nsteps; ++s) {
+    const int4 ws = tab[4 * s + g];
+    const int i = ws.x & 0xffff;
+    const bool valid = ws.y & WF_VALID, carry_in = valid && !(ws.y & WF_FIRST);
+    double* Pj = I + D.joint0 + (ws.z & 0xffff);
+    double* Pw = valid ? Pj : XD;
     const double* Cj = CB + cstep * (i - 1) + lc;
     __syncwarp();
     double vold[6], col[6];
@@ -510,9 +529,10 @@ LOIK_DEV void wide_backward(const ModelC& M, const LaneDims& D, const double* CB
     const double w_i = Pj[LJ_W], z_i = Pj[LJ_Z];
 #pragma unroll
     for (int r = 0; r < 6; ++r) col[r] = fma(facv, vold[r], Cj[CJ_HREFR + 8 * r]);
-    if (J.task >= 0) {
-      const double* Ck = M.a_per ? I + D.tmat0 + CT_ROWS * J.task : CB + D.ctask0 + CT_ROWS * J.task;
-      const double* Pk = I + D.task0 + LT_ROWS * J.task;
+    const int task = valid ? M.j[i].task : -1;
+    if (task >= 0) {
+      const double* Ck = M.a_per ? I + D.tmat0 + CT_ROWS * task : CB + D.ctask0 + CT_ROWS * task;
+      const double* Pk = I + D.task0 + LT_ROWS * task;
       double aty[6], atb[6];
       lds6(Pk + LT_ATY, aty);
       lds6(Pk + LT_ATB, atb);
@@ -523,27 +543,26 @@ LOIK_DEV void wide_backward(const ModelC& M, const LaneDims& D, const double* CB
         col[r] = isp ? pcol : hcol;
       }
     }
-    for (int n = 0; n < J.npin; ++n) {
-      const double* Pp = I + D.pend0 + LP_ROWS * J.pin[n];
+    if (ws.y & WF_PINS) {
+      const JointC& J = M.j[i];
+      for (int n = 0; n < J.npin; ++n) {
+        const double* Pp = I + D.pend0 + LP_ROWS * J.pin[n];
 #pragma unroll
-      for (int r = 0; r < 6; ++r) col[r] += Pp[LP_HP + 8 * r + lc];
+        for (int r = 0; r < 6; ++r) col[r] += Pp[LP_HP + 8 * r + lc];
+      }
     }
-    if (have_carry) {
 #pragma unroll
-      for (int r = 0; r < 6; ++r) col[r] += cc[r];
-    }
-    const int k = J.sidx;
+    for (int r = 0; r < 6; ++r) col[r] += carry_in ? cc[r] : 0.0;  // the child swept one step earlier (same chain)
+    const int k = (short)(ws.w & 0xffff);
     double d_un = 0.0;
-    if (k < 0) d_un = St_dot(J, col);  // unaligned joint: U_c = S^T H(:, c), lane 6: S^T p
-    if (valid) {
+    if (k < 0) d_un = St_dot(M.j[i], col);  // unaligned joint: U_c = S^T H(:, c), lane 6: S^T p
 #pragma unroll
-      for (int r = 0; r < 6; ++r) Pj[LJ_HP + 8 * r + l] = col[r];
-    }
+    for (int r = 0; r < 6; ++r) Pw[LJ_HP + 8 * r + l] = col[r];
     X[LX_V + l] = d_un;
     __syncwarp();
     double U[6], d, Stp, StU;
     if (k >= 0) {
-      // (an invalid step reads the block its group stored in an earlier, valid step: finite values, results unused)
+      // (a group without work reads the block of joint 1 while its owner may be writing it: finite values, results unused)
       const double* row = Pj + LJ_HP + 8 * k;
       lds6(row, U);
       Stp = row[6];
@@ -553,18 +572,16 @@ LOIK_DEV void wide_backward(const ModelC& M, const LaneDims& D, const double* CB
       lds6(X + LX_V, U);
       Stp = X[LX_V + 6];
       d = d_un;
-      StU = St_dot(J, U);
+      StU = St_dot(M.j[i], U);
     }
     const double Dinv = 1.0 / (StU + mu);
     const double ri = (w_i - mu * z_i) + Stp;
     double UD[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) UD[c] = U[c] * Dinv;
-    if (valid) {
-      Pj[LJ_UD + l] = d * Dinv;
-      Pj[LJ_DINV] = Dinv;
-      Pj[LJ_R] = ri;
-    }
+    Pw[LJ_UD + l] = d * Dinv;
+    Pw[LJ_DINV] = Dinv;
+    Pw[LJ_R] = ri;
     // projection + transformation to the parent frame, by every group (a root joint's result is simply not handed on)
     const double m = isp ? ri : d;
 #pragma unroll
@@ -578,43 +595,39 @@ LOIK_DEV void wide_backward(const ModelC& M, const LaneDims& D, const double* CB
     __syncwarp();
     lds6(XTrow, row);
     act_force(R, tr, row, cc);
-    const bool give = valid && J.parent > 0;
-    have_carry = give && J.carry != 0;
-    if (give && !J.carry) {
-      double* Pp = I + D.pend0 + LP_ROWS * J.pout;
+    double* Pp = (ws.y & WF_GIVE) ? I + D.pend0 + LP_ROWS * (ws.z >> 16) : XD;
 #pragma unroll
-      for (int r = 0; r < 6; ++r) Pp[LP_HP + 8 * r + l] = cc[r];
-    }
+    for (int r = 0; r < 6; ++r) Pp[LP_HP + 8 * r + l] = cc[r];
   }
 }
 
-LOIK_DEV void wide_forward(const ModelC& M, const LaneDims& D, const double* CB, double* I, double* X, const int l, const unsigned gmask,
-                           const double mu, const double mu_eq, Carry& cy, LanePart& pt, const int lo, const int hi, const int steps) {
+LOIK_DEV void wide_forward(const ModelC& M, const LaneDims& D, const double* CB, double* I, double* X, const int l, const int g,
+                           const unsigned gmask, const double mu, const double mu_eq, Carry& cy, LanePart& pt, const int4* tab, const int nsteps) {
   const double inv_mu = 1.0 / mu;
   const int lc = l < 6 ? l : 5;
+  double* XD = X + LX_DUMMY;
   double v[6] = {0, 0, 0, 0, 0, 0};
-  for (int t = 0; t < steps; ++t) {
-    const bool valid = lo + t <= hi;
-    const int i = valid ? lo + t : lo;
-    const JointC& J = M.j[i];
-    double* Pj = I + D.joint0 + LJ_ROWS * (i - 1);
+  for (int s = 0; s < nsteps; ++s) {
+    const int4 ws = tab[4 * s + g];
+    const int i = ws.x & 0xffff, parent = ws.x >> 16;
+    const bool valid = ws.y & WF_VALID;
+    double* Pj = I + D.joint0 + (ws.z & 0xffff);
+    double* Pw = valid ? Pj : XD;
     __syncwarp();
     double UD[6], R[9], tr[3];
     const double vold_l = Pj[LJ_V + lc];
     const double2 dr = lds2(Pj + LJ_DINV);
     const double2 nz = lds2(Pj + LJ_NU);
     const double w_old = Pj[LJ_W];
-    double lb = J.lb, ub = J.ub;
-    if (M.bounds_per_instance) { const double2 b2 = lds2(Pj + LJ_LB); lb = b2.x; ub = b2.y; }
+    const double2 b2 = lds2(Pj + LJ_LB);  // (batch-shared bounds are written into the record when the instance is loaded)
+    const double lb = b2.x, ub = b2.y;
     lds6(Pj + LJ_UD, UD);
     lds_xf(Pj + LJ_XF, R, tr);
-    if (t == 0 || J.parent != i - 1) {
-      if (J.parent == 0) {
+    if (ws.y & WF_FIRST) {  // first joint of a chain: the parent's v comes from its record (zero for a root joint)
+      double vq[6];
+      lds6(I + D.joint0 + (ws.w >> 16) + LJ_V, vq);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) v[c] = 0.0;
-      } else {
-        lds6(I + D.joint0 + LJ_ROWS * (J.parent - 1) + LJ_V, v);
-      }
+      for (int c = 0; c < 6; ++c) v[c] = parent > 0 ? vq[c] : 0.0;
     }
     double hc[6];
 #pragma unroll
@@ -631,33 +644,38 @@ LOIK_DEV void wide_forward(const ModelC& M, const LaneDims& D, const double* CB,
 #pragma unroll
     for (int c = 0; c < 6; ++c) acc += UD[c] * v[c];
     const double nu = -acc - dr.x * dr.y;
-    S_axpy(J, nu, v);
+    const int k = (short)(ws.w & 0xffff);
+    if (k >= 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) v[c] += c == k ? nu : 0.0;  // v_i = vp + S nu_i (:133-134), aligned axis
+    } else {
+      S_axpy(M.j[i], nu, v);
+    }
     const double z = dmin(ub, dmax(lb, nu + inv_mu * w_old));
     const double rp = nu - z;
     const double dw = mu * rp;
     const double f_l = hc[0] * v[0] + hc[1] * v[1] + hc[2] * v[2] + hc[3] * v[3] + hc[4] * v[4] + hc[5] * v[5] + p_l;
-    if (valid) {
-      cy.nu_inf = amax(cy.nu_inf, nu);
-      cy.dnu_inf = amax(cy.dnu_inf, nu - nz.x);
-      cy.dz_inf = amax(cy.dz_inf, z - nz.y);
-      cy.pres_slack = amax(cy.pres_slack, rp);
-      cy.dw_inf = amax(cy.dw_inf, dw);
-      cy.ubdw_p += ub * dmax(dw, 0.0);
-      cy.lbdw_m += lb * dmin(dw, 0.0);
-      pt.dfis = amax(pt.dfis, f_l - fold_l);
+    {
+      cy.nu_inf = amax(cy.nu_inf, valid ? nu : 0.0);
+      cy.dnu_inf = amax(cy.dnu_inf, valid ? nu - nz.x : 0.0);
+      cy.dz_inf = amax(cy.dz_inf, valid ? z - nz.y : 0.0);
+      cy.pres_slack = amax(cy.pres_slack, valid ? rp : 0.0);
+      cy.dw_inf = amax(cy.dw_inf, valid ? dw : 0.0);
+      cy.ubdw_p += valid ? ub * dmax(dw, 0.0) : 0.0;
+      cy.lbdw_m += valid ? lb * dmin(dw, 0.0) : 0.0;
+      pt.dfis = amax(pt.dfis, valid ? f_l - fold_l : 0.0);
     }
     __syncwarp();
-    if (valid) {
-      if (l == 0) sts6(Pj + LJ_V, v);
-      Pj[LJ_F + lc] = f_l;
-      *reinterpret_cast<double2*>(Pj + LJ_NU) = make_double2(nu, z);
-      Pj[LJ_W] = w_old + dw;
-    }
+    if (l == 0) sts6(Pw + LJ_V, v);
+    Pw[LJ_F + lc] = f_l;
+    *reinterpret_cast<double2*>(Pw + LJ_NU) = make_double2(nu, z);
+    Pw[LJ_W] = w_old + dw;
     __syncwarp();
-    if (valid) pt.dvis = amax(pt.dvis, Pj[LJ_V + lc] - vold_l);
-    if (valid && J.task >= 0) {  // DualUpdate for the task on this joint (:410-451); only the group that owns the joint is here
-      const double* Ck = M.a_per ? I + D.tmat0 + CT_ROWS * J.task : CB + D.ctask0 + CT_ROWS * J.task;
-      double* Pk = I + D.task0 + LT_ROWS * J.task;
+    pt.dvis = amax(pt.dvis, valid ? Pj[LJ_V + lc] - vold_l : 0.0);
+    const int task = valid ? M.j[i].task : -1;
+    if (task >= 0) {  // DualUpdate for the task on this joint (:410-451); only the group that owns the joint is here
+      const double* Ck = M.a_per ? I + D.tmat0 + CT_ROWS * task : CB + D.ctask0 + CT_ROWS * task;
+      double* Pk = I + D.task0 + LT_ROWS * task;
       const double Av = Ck[CT_ATR + lc] * v[0] + Ck[CT_ATR + 8 + lc] * v[1] + Ck[CT_ATR + 16 + lc] * v[2] + Ck[CT_ATR + 24 + lc] * v[3] +
                         Ck[CT_ATR + 32 + lc] * v[4] + Ck[CT_ATR + 40 + lc] * v[5];
       const double e = Av - Pk[LT_B + lc];
@@ -690,17 +708,18 @@ LOIK_DEV void wide_forward(const ModelC& M, const LaneDims& D, const double* CB,
   }
 }
 
-LOIK_DEV void wide_residual(const ModelC& M, const LaneDims& D, const double* CB, double* I, const int l, Resid& rs, LanePart& pt,
-                            const int lo, const int hi, const int steps) {
+LOIK_DEV void wide_residual(const ModelC& M, const LaneDims& D, const double* CB, double* I, double* X, const int l, const int g, Resid& rs,
+                            LanePart& pt, const int4* tab, const int nsteps) {
   const int lc = l < 6 ? l : 5;
   const int cstep = M.href_uniform ? 0 : CJ_ROWS;
+  double* XD = X + LX_DUMMY;
   double cF = 0.0;
-  bool have_carry = false;
-  for (int t = 0; t < steps; ++t) {
-    const bool valid = hi - t >= lo;
-    const int i = valid ? hi - t : lo;
-    const JointC& J = M.j[i];
-    double* Pj = I + D.joint0 + LJ_ROWS * (i - 1);
+  for (int s = 0; s < nsteps; ++s) {
+    const int4 ws = tab[4 * s + g];
+    const int i = ws.x & 0xffff;
+    const bool valid = ws.y & WF_VALID, carry_in = valid && !(ws.y & WF_FIRST);
+    double* Pj = I + D.joint0 + (ws.z & 0xffff);
+    double* Pw = valid ? Pj : XD;
     const double* Cj = CB + cstep * (i - 1) + lc;
     __syncwarp();
     double f[6], v[6];
@@ -711,36 +730,35 @@ LOIK_DEV void wide_residual(const ModelC& M, const LaneDims& D, const double* CB
     double hr[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) hr[c] = Cj[CJ_HREF + 8 * c];
-    const int k = J.sidx;
-    const double Stf = k >= 0 ? Pj[LJ_F + k] : St_dot(J, f);
+    const int k = (short)(ws.w & 0xffff);
+    const double Stf = k >= 0 ? Pj[LJ_F + k] : St_dot(M.j[i], f);
     double F = 0.0;
-    if (J.task >= 0) F = I[D.task0 + LT_ROWS * J.task + LT_ATY + lc];
-    for (int n = 0; n < J.npin; ++n) F += I[D.pend0 + LP_ROWS * J.pin[n] + LP_F + lc];
-    if (have_carry) F += cF;
+    const int task = valid ? M.j[i].task : -1;
+    if (task >= 0) F = I[D.task0 + LT_ROWS * task + LT_ATY + lc];
+    if (ws.y & WF_PINS) {
+      const JointC& J = M.j[i];
+      for (int n = 0; n < J.npin; ++n) F += I[D.pend0 + LP_ROWS * J.pin[n] + LP_F + lc];
+    }
+    F += carry_in ? cF : 0.0;
     F += -f_l;
     const double Hrv = hr[0] * v[0] + hr[1] * v[1] + hr[2] * v[2] + hr[3] * v[3] + hr[4] * v[4] + hr[5] * v[5];
     const double rd = Hrv - Hv_l + F;
     const double Tn = Stf + wt.x;
-    if (valid) {
-      pt.dF = amax(pt.dF, F - Fold);
-      pt.Finf = amax(pt.Finf, F);
-      pt.Hrefv = amax(pt.Hrefv, Hrv);
-      pt.dresv = amax(pt.dresv, rd);
-      rs.T_inf = amax(rs.T_inf, Tn);
-      rs.dT_inf = amax(rs.dT_inf, Tn - wt.y);
-    }
+    pt.dF = amax(pt.dF, valid ? F - Fold : 0.0);
+    pt.Finf = amax(pt.Finf, valid ? F : 0.0);
+    pt.Hrefv = amax(pt.Hrefv, valid ? Hrv : 0.0);
+    pt.dresv = amax(pt.dresv, valid ? rd : 0.0);
+    rs.T_inf = amax(rs.T_inf, valid ? Tn : 0.0);
+    rs.dT_inf = amax(rs.dT_inf, valid ? Tn - wt.y : 0.0);
     __syncwarp();
-    if (valid) {
-      Pj[LJ_FD + lc] = F;
-      Pj[LJ_T] = Tn;
-    }
+    Pw[LJ_FD + lc] = F;
+    Pw[LJ_T] = Tn;
     double R[9], tr[3], c6[6];
     lds_xf(Pj + LJ_XF, R, tr);
     act_force(R, tr, f, c6);
     cF = pick6(c6, lc);
-    const bool give = valid && J.parent > 0;
-    have_carry = give && J.carry != 0;
-    if (give && !J.carry) I[D.pend0 + LP_ROWS * J.pout + LP_F + lc] = cF;
+    double* Pp = (ws.y & WF_GIVE) ? I + D.pend0 + LP_ROWS * (ws.z >> 16) : XD;
+    Pp[LP_F + lc] = cF;
   }
 }
 
@@ -751,8 +769,12 @@ template <int GPI>
 __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ ModelC c_model, const LaneP P) {
   extern __shared__ __align__(16) double lsm[];
   const ModelC& M = c_model;
-  const LaneDims D = lane_dims(M.nb, M.nc, M.npend, M.href_uniform, GPI, M.a_per);
+  const LaneDims D = lane_dims(M.nb, M.nc, M.npend, M.href_uniform, GPI, M.a_per, M.nsb + M.nsf);
   double* CB = lsm;
+  const int4* tabB = reinterpret_cast<const int4*>(lsm + D.tab0);
+  const int4* tabF = tabB + 4 * M.nsb;
+  if (GPI > 1)
+    for (int e = threadIdx.x; e < 4 * (M.nsb + M.nsf); e += blockDim.x) reinterpret_cast<int4*>(lsm + D.tab0)[e] = P.tab[e];
   for (int e = threadIdx.x; e < D.csize; e += blockDim.x) {
     double x = 0.0;
     if (e < D.ctask0) {
@@ -781,7 +803,7 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
   const int wl = GPI == 1 ? l : lane, nl = GPI == 1 ? 8 : 32;
   const unsigned imask = GPI == 1 ? gmask : 0xffffffffu;
   double* I = lsm + D.cpad + (size_t)(GPI == 1 ? w * kLaneI + g : w) * D.stride;
-  double* X = I + D.xch + (GPI == 1 ? 0 : g * LX_ROWS);
+  double* X = I + D.xch + (GPI == 1 ? 0 : g * LX_ROWS_WIDE);
   const int limit = P.list ? *P.n_list : P.n;
   int home_slot = -1;  // >= 0: these lanes hold an instance
   int status = ST_CONVERGED, it = 0, left = 0;
@@ -796,16 +818,17 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
       if (k < limit) {
         const int s = P.list ? P.list[k] : k;
         const double* T = P.src + ((size_t)(s >> 5) * M.off.rows) * 32 + (s & 31);
-        lane_load(M, D, T, I, wl, nl);
+        lane_load(M, D, T, I, wl, nl, GPI > 1);
         __syncwarp(imask);
         for (int j = wl; j < M.nb; j += nl) {  // liMi of every joint (FwdPassInit, hxx:263-264), once per instance
-          double* Pj = I + D.joint0 + LJ_ROWS * j;
+          double* Pj = I + D.joint0 + lane_joff(M, GPI > 1, j);
           double R[9], t[3];
           make_xf(M.j[j + 1], Pj[LJ_SQ], Pj[LJ_CQ], R, t);
 #pragma unroll
           for (int c = 0; c < 9; ++c) Pj[LJ_XF + c] = R[c];
 #pragma unroll
           for (int c = 0; c < 3; ++c) Pj[LJ_XF + 9 + c] = t[c];
+          if (GPI > 1 && !M.bounds_per_instance) { Pj[LJ_LB] = M.j[j + 1].lb; Pj[LJ_UB] = M.j[j + 1].ub; }  // (the wide sweeps read the bounds from the record)
         }
         __syncwarp(imask);
         const int2 ctl = *reinterpret_cast<const int2*>(I + LS_CTL);
@@ -832,52 +855,11 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
       lane_forward<1>(M, D, CB, I, X, l, gmask, mu, mu_eq, cy, pt, 1, M.nb);
       lane_residual<1>(M, D, CB, I, l, gmask, rs, pt, 1, M.nb);
     } else {
-      // group g sweeps the chains assigned to "warp" g of the segment schedule, level by level (children before parents
-      // on the way to the root, parents before children on the way out); chains exchange data through the pending blocks
-      // and the parents' v rows of the shared record.  All four groups enter a sweep TOGETHER, each with its own joint
-      // range (round r = the r-th chain of the group at this level; an empty range when it has none) and the same number
-      // of steps (wide_backward).
-      auto chain_of = [&](const bool backward, const int lv, const int r, int& lo, int& hi) {
-        lo = 1; hi = 0;
-        int cnt = 0;
-        for (int sg = 0; sg < M.nseg; ++sg) {
-          const SegC& sc = M.seg[sg];
-          if ((backward ? sc.bwarp : sc.fwarp) == g && (backward ? sc.blevel : sc.flevel) == lv) {
-            if (cnt == r) { lo = sc.lo; hi = sc.hi; }
-            ++cnt;
-          }
-        }
-      };
-      for (int lv = 0; lv < M.nblevel; ++lv) {
-        for (int r = 0;; ++r) {
-          int lo, hi;
-          chain_of(true, lv, r, lo, hi);
-          const int steps = __reduce_max_sync(0xffffffffu, hi - lo + 1);  // the longest chain of this round (0: none left)
-          if (steps <= 0) break;
-          wide_backward(M, D, CB, I, X, l, mu, mu_eq, lo, hi, steps);
-        }
-        __syncwarp();
-      }
-      for (int lv = 0; lv < M.nflevel; ++lv) {
-        for (int r = 0;; ++r) {
-          int lo, hi;
-          chain_of(false, lv, r, lo, hi);
-          const int steps = __reduce_max_sync(0xffffffffu, hi - lo + 1);
-          if (steps <= 0) break;
-          wide_forward(M, D, CB, I, X, l, gmask, mu, mu_eq, cy, pt, lo, hi, steps);
-        }
-        __syncwarp();
-      }
-      for (int lv = 0; lv < M.nblevel; ++lv) {
-        for (int r = 0;; ++r) {
-          int lo, hi;
-          chain_of(true, lv, r, lo, hi);
-          const int steps = __reduce_max_sync(0xffffffffu, hi - lo + 1);
-          if (steps <= 0) break;
-          wide_residual(M, D, CB, I, l, rs, pt, lo, hi, steps);
-        }
-        __syncwarp();
-      }
+      // the four groups sweep different chains of the instance, step by step through the host-built table (wide_backward)
+      wide_backward(M, D, CB, I, X, l, g, mu, mu_eq, tabB, M.nsb);
+      wide_forward(M, D, CB, I, X, l, g, gmask, mu, mu_eq, cy, pt, tabF, M.nsf);
+      wide_residual(M, D, CB, I, X, l, g, rs, pt, tabB, M.nsb);
+      __syncwarp();
     }
     {  // combine the per-lane partial maxima of the group: rows = lanes, then one column per lane
       double* XT = X + LX_T;
@@ -943,8 +925,8 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
         I[LS_MU] = mu;
         __syncwarp(imask);
         double* Th = P.home + ((size_t)(home_slot >> 5) * M.off.rows) * 32 + (home_slot & 31);
-        lane_retire(M, D, I, Th, wl, nl);
-        if (P.keep_ws) lane_retire_workspace(M, D.joint0, I, Th, wl, nl);
+        lane_retire(M, D, I, Th, wl, nl, GPI > 1);
+        if (P.keep_ws) lane_retire_workspace(M, D.joint0, I, Th, wl, nl, GPI > 1);
         home_slot = -1;
       }
     }

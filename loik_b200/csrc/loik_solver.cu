@@ -733,6 +733,7 @@ struct loik_solver {
   int* d_lists = nullptr;   // two compaction lists of `batch` ints
   double* scratch[2] = {nullptr, nullptr};  // packed arenas (allocated at the first solve)
   int* d_origin = nullptr;  // [2][batch] home slot of every packed slot
+  int4* d_wide_tab = nullptr;  // step table of the wide sweeps of k_iterate_lane<4> (build_wide_table)
   int* d_counts = nullptr;  // [0],[1]: list lengths (ping-pong); [2]: n_active
   unsigned long long* d_stats = nullptr;
   int* h_counts = nullptr;  // pinned
@@ -830,11 +831,11 @@ static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S_in, 
 // block less of an SM for the kernels of other solvers.
 struct LaneGeom { int gpi = 1, warps = 0, ctas_per_sm = 0, grid = 0; size_t smem = 0; };
 static bool lane_geometry(const loik_solver* h, LaneGeom& G) {
-  // groups per instance.  Four groups of a warp on the chains of one instance is correct and tested but not faster yet:
-  // the groups run different joints, the hardware schedules them as separate SIMT sub-warps (34.5 vs 35.3 us per Talos
-  // iteration of a lone instance), so the default stays one group per instance
-  const int gpi = h->lane_gpi_req > 0 ? h->lane_gpi_req : 1;
-  const LaneDims D = lane_dims(h->nb, h->nc, h->npend, h->mc.href_uniform, gpi, h->mc.a_per);
+  // groups per instance: the four groups of a warp on different chains of one instance (wide sweeps, loik_lane.cuh) when the
+  // tree branches (Talos: 12 steps per sweep instead of 32, 18.6 vs 31.4 us per iteration of a lone instance), else one
+  // group per instance (on a serial chain the wide sweeps only add their bookkeeping: Panda 9.9 vs 6.9 us)
+  const int gpi = h->lane_gpi_req > 0 ? h->lane_gpi_req : (h->mc.nwarp >= 2 ? 4 : 1);
+  const LaneDims D = lane_dims(h->nb, h->nc, h->npend, h->mc.href_uniform, gpi, h->mc.a_per, h->mc.nsb + h->mc.nsf);
   auto ctas_of = [&](int W) -> int {
     const size_t bytes = lane_smem_bytes(D, W, gpi);
     if (bytes > (size_t)h->smem_optin) return 0;
@@ -862,7 +863,7 @@ static int launch_lane(loik_solver* h, cudaStream_t st, const double* src, const
   if (!lane_geometry(h, G)) return fail(LOIK_ERR_STATE, "lane-parallel kernel: the instance record does not fit shared memory");
   LaneP P{};
   P.src = src; P.list = list; P.n_list = n_list; P.n = h->batch; P.origin = origin; P.home = h->arena;
-  P.queue = h->d_counts + 3; P.iters = iters; P.fixed = fixed; P.keep_ws = h->S.keep_ws;
+  P.queue = h->d_counts + 3; P.iters = iters; P.fixed = fixed; P.keep_ws = h->S.keep_ws; P.tab = h->d_wide_tab;
   CK(cudaMemsetAsync(h->d_counts + 3, 0, sizeof(int), st));
   if (G.gpi == 1) k_iterate_lane<1><<<G.grid, 32 * G.warps, G.smem, st>>>(h->mc, P);
   else k_iterate_lane<4><<<G.grid, 32 * G.warps, G.smem, st>>>(h->mc, P);
@@ -977,6 +978,89 @@ static void assign_segments(ModelC& M, int max_warps) {
   assign(fl, nfl, false);
 }
 
+// Step table of the wide sweeps of k_iterate_lane<4> (loik_lane.cuh: the four 8-lane groups of a warp on different chains of
+// one instance): per sweep direction a flat list of steps, four entries (WideStep) per step.  The chains are the segments of
+// the tree (ModelC::seg); a chain may start once the chains it depends on have ended (towards the root: every chain hanging
+// off it; on the way out: the chain of its parent joint) -- a step's stores are separated from the next step's loads by
+// the __syncwarp() at the top of a step, so "ended in an earlier step" is all the ordering needed.  List scheduling on four
+// groups, longest remaining path first (Talos: 10 steps per sweep, arms 8 -> torso 2, for 32 joints).  A group without work
+// in a step gets an entry without WF_VALID on joint 1.  Also fixes the blocks of the joints in the shared-memory record
+// (JointC::loff): joint i starts 4 x (group that sweeps it towards the root) doubles (mod 16) into its 108-double slot.
+static void build_wide_table(ModelC& M, std::vector<int4>& tab) {
+  tab.clear();
+  // the chains: maximal runs of joints whose contribution travels in registers (JointC::carry), as in assign_segments but
+  // without its cap on their number
+  std::vector<int> clo, chi, seg_of(M.nj, 0);
+  for (int i = 1; i < M.nj; ++i) {
+    if (!M.j[i].carry) { clo.push_back(i); chi.push_back(i); }
+    else chi.back() = i;
+    seg_of[i] = (int)clo.size() - 1;
+  }
+  const int ns = (int)clo.size();
+  std::vector<int> len(ns), par(ns, -1);
+  for (int c = 0; c < ns; ++c) {
+    len[c] = chi[c] - clo[c] + 1;
+    const int p = M.j[clo[c]].parent;
+    if (p > 0) par[c] = seg_of[p];
+  }
+  struct Slot { int start, group; };
+  auto schedule = [&](const bool backward, std::vector<Slot>& slot) {
+    // remaining path: backward = the chain and its ancestors, forward = the chain and its longest descendant line
+    std::vector<int> prio(ns, 0);
+    if (backward) { for (int c = 0; c < ns; ++c) prio[c] = len[c] + (par[c] >= 0 ? prio[par[c]] : 0); }  // (parents have smaller indices)
+    else { for (int c = ns - 1; c >= 0; --c) { prio[c] += len[c]; if (par[c] >= 0) prio[par[c]] = std::max(prio[par[c]], prio[c]); } }
+    slot.assign(ns, Slot{-1, -1});
+    int free_at[4] = {0, 0, 0, 0}, done = 0, nsteps = 0;
+    for (int t = 0; done < ns; ++t) {
+      for (int g = 0; g < 4; ++g) {
+        if (free_at[g] > t) continue;
+        int best = -1;
+        for (int c = 0; c < ns; ++c) {
+          if (slot[c].start >= 0) continue;
+          bool ready = true;
+          if (backward) { for (int k = 0; k < ns; ++k) if (par[k] == c && (slot[k].start < 0 || slot[k].start + len[k] > t)) ready = false; }
+          else if (par[c] >= 0) ready = slot[par[c]].start >= 0 && slot[par[c]].start + len[par[c]] <= t;
+          if (ready && (best < 0 || prio[c] > prio[best])) best = c;
+        }
+        if (best < 0) continue;
+        slot[best] = Slot{t, g};
+        free_at[g] = t + len[best];
+        nsteps = std::max(nsteps, free_at[g]);
+        ++done;
+      }
+    }
+    return nsteps;
+  };
+  std::vector<Slot> sb, sf;
+  M.nsb = schedule(true, sb);
+  M.nsf = schedule(false, sf);
+  for (int c = 0; c < ns; ++c)
+    for (int i = clo[c]; i <= chi[c]; ++i) M.j[i].loff = (short)(LJ_SLOT_WIDE * (i - 1) + 4 * ((sb[c].group - 3 * (i - 1)) & 3));
+  auto emit = [&](const bool backward, const std::vector<Slot>& slot, const int nsteps) {
+    const size_t base = tab.size();
+    tab.resize(base + 4 * (size_t)nsteps, make_int4(1, 0, (int)M.j[1].loff, 0));
+    for (int c = 0; c < ns; ++c)
+      for (int t = 0; t < len[c]; ++t) {
+        const int i = backward ? chi[c] - t : clo[c] + t;
+        const JointC& J = M.j[i];
+        int flags = WF_VALID | (t == 0 ? WF_FIRST : 0) | (J.parent == 0 ? WF_ROOT : 0) | (J.npin > 0 ? WF_PINS : 0);
+        if (J.parent > 0 && !J.carry) flags |= WF_GIVE;
+        tab[base + 4 * (size_t)(slot[c].start + t) + slot[c].group] =
+            make_int4(i | (J.parent << 16), flags, (int)J.loff | ((int)J.pout << 16), ((int)J.sidx & 0xffff) | ((J.parent > 0 ? (int)M.j[J.parent].loff : 0) << 16));
+      }
+  };
+  emit(true, sb, M.nsb);
+  emit(false, sf, M.nsf);
+}
+static int upload_wide_table(loik_solver* h) {
+  std::vector<int4> tab;
+  build_wide_table(h->mc, tab);
+  if (h->d_wide_tab) { cudaFree(h->d_wide_tab); h->d_wide_tab = nullptr; }
+  CK(cudaMalloc(&h->d_wide_tab, tab.size() * sizeof(int4)));
+  CK(cudaMemcpy(h->d_wide_tab, tab.data(), tab.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  return LOIK_OK;
+}
+
 extern "C" {
 
 int32_t loik_abi_version(void) { return 2; }
@@ -1063,6 +1147,7 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
     else M.span[M.nspan++] = SpanC{(short)i, (short)i, 0, 0};
   }
   assign_segments(M, h->seg_warps);
+  { std::vector<int4> tab; build_wide_table(M, tab); }  // (sets nsb / nsf; uploaded once the CUDA side exists)
   // tile record layout: [globals | joint blocks | task blocks | pending blocks | debug vectors]
   const int nb = h->nb, nc = std::max(h->nc, 1);
   Offs& O = M.off;
@@ -1093,6 +1178,7 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
   const size_t arena_doubles = (size_t)h->ntiles * rows * 32;
   CKA(cudaMalloc(&h->arena, arena_doubles * sizeof(double)));
   CKA(cudaMemset(h->arena, 0, arena_doubles * sizeof(double)));
+  if (upload_wide_table(h) != LOIK_OK) { loik_destroy(h); return LOIK_ERR_CUDA; }
   CKA(cudaMalloc(&h->d_lists, 2 * (size_t)batch * sizeof(int)));
   CKA(cudaMalloc(&h->d_counts, 4 * sizeof(int)));
   CKA(cudaMemset(h->d_counts, 0, 4 * sizeof(int)));
@@ -1213,11 +1299,27 @@ int32_t loik_model_layout(const loik_model_desc* model, const loik_params* param
   return (int32_t)v.size();
 }
 
+int32_t loik_wide_table(const loik_model_desc* model, const loik_params* params, int32_t* out, int32_t cap) {
+  if (!out || cap < 0) return fail(LOIK_ERR_INVALID, "loik_wide_table: null argument");
+  loik_solver* h = nullptr;
+  const int rc = create_impl(model, params, 32, 0, &h, true);
+  if (rc) return rc;
+  std::vector<int4> tab;
+  build_wide_table(h->mc, tab);
+  std::vector<int32_t> v = {h->mc.nsb, h->mc.nsf};
+  for (const int4& e : tab)
+    for (int x : {e.x & 0xffff, e.x >> 16, e.y, e.z & 0xffff, e.z >> 16, (int)(short)(e.w & 0xffff), e.w >> 16}) v.push_back(x);
+  delete h;
+  if ((int)v.size() > cap) return fail(LOIK_ERR_INVALID, "loik_wide_table: output buffer too small");
+  std::copy(v.begin(), v.end(), out);
+  return (int32_t)v.size();
+}
+
 void loik_destroy(loik_solver* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  cudaFree(h->S.dbg); cudaFree(h->arena); cudaFree(h->scratch[0]); cudaFree(h->scratch[1]); cudaFree(h->d_origin); cudaFree(h->d_lists); cudaFree(h->d_counts); cudaFree(h->d_stats); cudaFree(h->d_map);
+  cudaFree(h->S.dbg); cudaFree(h->arena); cudaFree(h->scratch[0]); cudaFree(h->scratch[1]); cudaFree(h->d_origin); cudaFree(h->d_lists); cudaFree(h->d_counts); cudaFree(h->d_wide_tab); cudaFree(h->d_stats); cudaFree(h->d_map);
   if (h->g_exec) cudaGraphExecDestroy(h->g_exec);
   if (h->hi_stream) cudaStreamDestroy(h->hi_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1851,7 +1953,11 @@ int loik_set_schedule(loik_solver* h, const loik_schedule* sc) {
   h->hi_after = sc->hi_priority_after; h->seg_after = sc->seg_after;
   h->lane_after = sc->lane_after; h->use_graph = sc->use_graph != 0; h->lane_warps_req = sc->lane_warps_per_cta; h->lane_gpi_req = sc->lane_groups_per_instance;
   h->small_after = sc->small_after; h->small_grid = sc->small_grid; h->drop_ws = sc->drop_workspace != 0;
-  if (sc->seg_warps != h->seg_warps) { h->seg_warps = sc->seg_warps; assign_segments(h->mc, h->seg_warps); }
+  if (sc->seg_warps != h->seg_warps) {
+    h->seg_warps = sc->seg_warps; assign_segments(h->mc, h->seg_warps);
+    int rc = upload_wide_table(h);
+    if (rc) return rc;
+  }
   if (h->g_exec) { cudaGraphExecDestroy(h->g_exec); h->g_exec = nullptr; }  // the cached launch graph follows the schedule
   return LOIK_OK;
 }

@@ -39,7 +39,7 @@ NORM_NAMES = ["bT_delta_y_plus", "bT_delta_y_minus", "Av_inf_norm", "nu_inf_norm
               "primal_infeasibility_cond_1", "primal_infeasibility_cond_2", "delta_x_qp_inf_norm", "converged",
               "primal_infeasible"]
 
-EXPORTS = ["loik_abi_version", "loik_last_error", "loik_create", "loik_destroy", "loik_model_layout", "loik_solve_init",
+EXPORTS = ["loik_abi_version", "loik_last_error", "loik_create", "loik_destroy", "loik_model_layout", "loik_wide_table", "loik_solve_init",
            "loik_update_references", "loik_solve", "loik_solve_full", "loik_solve_task", "loik_integrate", "loik_iterate_fixed",
            "loik_fwd_pass_init", "loik_reset_recursion", "loik_step", "loik_set_debug", "loik_set_keep_workspace", "loik_get", "loik_get_stats", "loik_reduce_stats", "loik_launch_count",
            "loik_set_max_iter", "loik_set_rho", "loik_set_mu", "loik_set_mu_equality_scale_factor", "loik_set_tol_abs",
@@ -101,6 +101,8 @@ def load_library(path: str | None = None):
     lib.loik_set_debug.argtypes = [vp, i32]
     lib.loik_model_layout.argtypes = [vp, vp, C.POINTER(C.c_int32), i32]
     lib.loik_model_layout.restype = i32
+    lib.loik_wide_table.argtypes = [vp, vp, C.POINTER(C.c_int32), i32]
+    lib.loik_wide_table.restype = i32
     lib.loik_set_keep_workspace.argtypes = [vp, i32]
     lib.loik_get.argtypes = [vp, i32, vp, i32, vp]
     lib.loik_get_stats.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -166,6 +168,38 @@ class _Buf:
             self.ptr = a.ctypes.data
             self.loc = LOIK_HOST
             self.shape = a.shape
+
+
+def _dry_args(model, params):
+    keep = [np.ascontiguousarray(model.parent, np.int32), np.ascontiguousarray(model.jtype, np.int32),
+            np.ascontiguousarray(model.axis, np.float64), np.ascontiguousarray(model.placement_R, np.float64),
+            np.ascontiguousarray(model.placement_p, np.float64)]
+    md = _ModelDesc(model.nj, keep[0].ctypes.data_as(C.POINTER(C.c_int32)), keep[1].ctypes.data_as(C.POINTER(C.c_int32)),
+                    keep[2].ctypes.data_as(C.POINTER(C.c_double)), keep[3].ctypes.data_as(C.POINTER(C.c_double)),
+                    keep[4].ctypes.data_as(C.POINTER(C.c_double)))
+    P = params
+    pr = _Params(int(P["max_iter"]), P["tol_abs"], P["tol_rel"], P["tol_primal_inf"], P["tol_dual_inf"], P["rho"], P["mu"],
+                 P["mu_equality_scale_factor"], int(P.get("mu_update_strat", 0)), int(P["num_eq_c"]), int(P.get("eq_c_dim", 6)),
+                 int(bool(P.get("warm_start", False))), P.get("tol_tail_solve", 1e-1), 0, 0)
+    return keep, md, pr
+
+
+def wide_table(model, params, lib=None):
+    """Step table of the lane-parallel kernel's wide geometry (``loik_wide_table``; no CUDA needed): per sweep direction a
+    list of steps, each a list of four dicts (one per 8-lane group)."""
+    lib = lib or load_library()
+    keep, md, pr = _dry_args(model, params)
+    cap = 2 + 2 * 4 * 7 * model.nj
+    out = (C.c_int32 * cap)()
+    n = lib.loik_wide_table(C.byref(md), C.byref(pr), out, cap)
+    if n < 0:
+        raise RuntimeError(lib.loik_last_error().decode())
+    v = list(out[:n])
+    nsb, nsf = v[:2]
+    names = ("joint", "parent", "flags", "loff", "pout", "sidx", "parent_loff")
+    ent = [dict(zip(names, v[2 + 7 * e:2 + 7 * e + 7])) for e in range(4 * (nsb + nsf))]
+    steps = [ent[4 * s:4 * s + 4] for s in range(nsb + nsf)]
+    return dict(backward=steps[:nsb], forward=steps[nsb:])
 
 
 def model_layout(model, params, lib=None):

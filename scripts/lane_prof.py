@@ -18,7 +18,7 @@ B = int(os.environ.get("BATCH", {"panda": 65536, "ur10": 262144, "talos": 16384}
 model = robots.get_robot(name)
 pb = problems.random_batch(model, B, seed=0)
 S = lk.make_solver(model, problems.bench_params(len(pb["ids"])), B)
-S.set_schedule(lane_after=la)
+S.set_schedule(lane_after=la, lane_groups_per_instance=int(os.environ.get("GPI", "0")))
 S.SolveInit(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
 for _ in range(3):
     S.IterateFixed(iters)

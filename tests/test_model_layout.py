@@ -128,3 +128,90 @@ def test_too_many_branching_children():
     L = _layout(ok)
     assert L["npend"] == 6 and L["joints"][0]["npin"] == 6
     _check_invariants(ok, L, 1)
+
+
+# ---- the step table of the lane-parallel kernel's wide geometry (k_iterate_lane<4>, loik_lane.cuh) ---------------------
+WF_VALID, WF_FIRST, WF_GIVE, WF_ROOT, WF_PINS = 1, 2, 4, 8, 16
+LJ_ROWS, LJ_SLOT_WIDE = 96, 108
+
+
+def _check_wide_table(model, nc=1):
+    params = problems.bench_params(nc)
+    L = solver.model_layout(model, params)
+    W = solver.wide_table(model, params)
+    J, parent = L["joints"], model.parent
+    seg_of, c = {}, -1  # chains = maximal runs of register-carried joints
+    for i in range(1, model.nj):
+        c += 0 if J[i - 1]["carry"] else 1
+        seg_of[i] = c
+    for direction in ("backward", "forward"):
+        at = {}  # joint -> (step, group)
+        prev = [None] * 4
+        for s, step in enumerate(W[direction]):
+            assert len(step) == 4
+            for g, e in enumerate(step):
+                if not e["flags"] & WF_VALID:
+                    assert e["joint"] == 1 and e["flags"] == 0  # a group without work: joint 1, nothing stored
+                    prev[g] = None
+                    continue
+                i = e["joint"]
+                assert i not in at, "every joint is swept exactly once"
+                at[i] = (s, g)
+                assert e["parent"] == parent[i]
+                assert bool(e["flags"] & WF_ROOT) == (parent[i] == 0)
+                assert bool(e["flags"] & WF_PINS) == (J[i - 1]["npin"] > 0)
+                assert bool(e["flags"] & WF_GIVE) == (parent[i] > 0 and not J[i - 1]["carry"])
+                if e["flags"] & WF_GIVE:
+                    assert e["pout"] == J[i - 1]["pout"]
+                # a chain continues on the same group in the next step; its first step is flagged
+                cont = prev[g] is not None and seg_of[prev[g]] == seg_of[i] and prev[g] == (i + 1 if direction == "backward" else i - 1)
+                assert bool(e["flags"] & WF_FIRST) == (not cont)
+                if not e["flags"] & WF_FIRST:  # inside a chain the hand-over is the register carry
+                    assert J[i if direction == "backward" else i - 1]["carry"] == 1
+                prev[g] = i
+        assert sorted(at) == list(range(1, model.nj))
+        for i in range(1, model.nj):  # dependencies: strictly earlier steps, or the previous step of the same group (registers)
+            p = parent[i]
+            if p == 0:
+                continue
+            (si, gi), (sp, gp) = at[i], at[p]
+            if direction == "backward":
+                assert si < sp
+                if J[i - 1]["carry"]:
+                    assert gi == gp and sp == si + 1
+            else:
+                assert sp < si
+    # ---- blocks of the joints in the shared-memory record: inside their slot, 16 B aligned, 4 x group (mod 16) doubles
+    offs = {}
+    for step in W["backward"]:
+        for g, e in enumerate(step):
+            if e["flags"] & WF_VALID:
+                i = e["joint"]
+                offs[i] = e["loff"]
+                assert LJ_SLOT_WIDE * (i - 1) <= e["loff"] and e["loff"] + LJ_ROWS <= LJ_SLOT_WIDE * i
+                assert e["loff"] % 2 == 0 and e["loff"] % 16 == 4 * g
+    for step in W["forward"]:
+        for e in step:
+            if e["flags"] & WF_VALID:
+                assert e["loff"] == offs[e["joint"]]
+                if e["parent"] > 0:
+                    assert e["parent_loff"] == offs[e["parent"]]
+    return W
+
+
+@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "talos_ff"])
+def test_wide_table_robots(name):
+    model = robots.get_robot(name)
+    if any(model.nv_joint(i) > 1 for i in range(1, model.nj)):
+        pytest.skip("the lane-parallel kernel covers trees of 1-DoF joints")
+    W = _check_wide_table(model)
+    if name == "talos":  # the critical path: an arm (8 joints) and the torso (2), with the legs and the head alongside
+        assert len(W["backward"]) == 10 and len(W["forward"]) == 10
+    if name == "panda":
+        assert len(W["backward"]) == 7
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_wide_table_random_trees(seed):
+    model = robots.random_tree(4 + 5 * seed, seed=100 + seed, branching=0.35)
+    _check_wide_table(model, nc=2)
