@@ -49,7 +49,10 @@ static_assert((int)LJ_V == (int)JR_V && (int)LJ_F == (int)JR_F && (int)LJ_FD == 
 enum : int { LT_Y = TR_Y, LT_ATY = TR_ATY, LT_B = TR_B, LT_ATB = TR_ATB, LT_ROWS = 24 };  // (the tile's task block also holds per-instance A, A^T A)
 enum : int { LP_HP = 0, LP_F = 48, LP_ROWS = 56 };       // pending block of a tree edge: [H | p] contribution, F contribution
 enum : int { LX_V = 0, LX_T = 16, LX_ROWS = 96,          // exchange scratch: 16 scalars, 8 rows of 10 (transposes)
-             LX_DUMMY = 96, LX_ROWS_WIDE = 200 };        // GPI = 4: + a block that takes the stores of a group without work; stride = 8 (mod 16)
+             // GPI = 4: + two joint-block-sized dummies for the steps in which a group has no work: one that is only read
+             // (zeros, bounds -1 / 1, liMi = identity: every norm term the step produces is exactly 0) and, right behind it,
+             // one that takes the step's stores; stride = 8 (mod 16)
+             LX_RDUMMY = 96, LX_WDUMMY = 192, LX_ROWS_WIDE = 296 };
 // ---- per-CTA constants in shared memory ---------------------------------------------------------------------------
 enum : int { CJ_HREFR = 0, CJ_HREF = 48, CJ_HV = 96, CJ_ROWS = 104 };  // per joint: [Href + rho I | -Hv] and Href as 6 rows of 8, Hv (8)
 enum : int { CT_AR = 0, CT_ATR = 48, CT_ATA = 96, CT_ROWS = 144 };  // per task: A, A^T, A^T A as 6 rows of 8
@@ -58,7 +61,7 @@ enum : int { GC_STRIDE = 24, GC_TOT = 96, GC_ROWS = 120 };  // GPI = 4: the grou
 
 struct LaneDims {
   int joint0, task0, tmat0, pend0, xch, gc, stride;  // offsets inside an instance record, record stride
-  int ctask0, csize, tab0, cpad;              // constants: first task block, size, step table of the wide sweeps, size padded to 128 B
+  int ctask0, csize, cz0, tab0, cpad;         // constants: first task block, size, a zero joint block and the step table of the wide sweeps, size padded to 128 B
   int xstride;                                // exchange scratch per group
 };
 __host__ __device__ inline LaneDims lane_dims(const int nb, const int nc, const int npend, const int href_uniform, const int gpi, const int a_per,
@@ -76,8 +79,9 @@ __host__ __device__ inline LaneDims lane_dims(const int nb, const int nc, const 
   D.stride = sz;
   D.ctask0 = CJ_ROWS * (href_uniform ? 1 : nb);  // one [Href | -Hv] block when every joint shares the reference (UpdateReference)
   D.csize = D.ctask0 + CT_ROWS * nc;
-  D.tab0 = (D.csize + 1) & ~1;                        // 4 x int4 = 8 doubles per step of the wide sweeps (backward order, then forward order)
-  D.cpad = (D.tab0 + (gpi > 1 ? 8 * wide_steps : 0) + 15) & ~15;
+  D.cz0 = (D.csize + 1) & ~1;                         // (the constants of a step without work)
+  D.tab0 = D.cz0 + (gpi > 1 ? CJ_ROWS : 0);           // 4 x int4 = 8 doubles per step of the wide sweeps (backward order, then forward order, one spare step)
+  D.cpad = (D.tab0 + (gpi > 1 ? 8 * (wide_steps + 1) : 0) + 15) & ~15;
   return D;
 }
 inline size_t lane_smem_bytes(const LaneDims& D, const int warps, const int gpi) { return ((size_t)D.cpad + (size_t)warps * (kLaneI / gpi) * D.stride) * sizeof(double); }
@@ -494,15 +498,17 @@ LOIK_DEV void lane_residual(const ModelC& M, const LaneDims& D, const double* CB
 // instruction stream per warp, so the groups only work in parallel if they execute the SAME instructions: every sweep is
 // one flat loop over the steps of a host-built table (build_wide_table, loik_solver.cu; WideStep), four entries per step:
 // what group g does in that step -- the joint, whether the step is real (`valid`), whether it starts a chain, where its
-// result goes.  A group without work in a step repeats the arithmetic on joint 1 with every store redirected to a
-// scratch block of its own and every norm update fed a zero, so the hot path has no branch that differs between the
-// groups; the per-joint branches that remain (task on the joint, contributions of several children, unaligned axis) are
-// rare.  All exchanges between lanes are synchronised at the top level of the loop (full-mask __syncwarp(), free in
+// result goes.  A group without work in a step runs the same arithmetic on an all-zero joint block and all-zero constants
+// (LX_RDUMMY, LaneDims::cz0: every value it produces, hence every norm term, is exactly 0) with its stores redirected to
+// a scratch block, so the hot path has neither a branch nor a select that depends on `valid`; the per-joint branches that
+// remain (task on the joint, contributions of several children, unaligned axis) are rare.  The kernel copies the table
+// to shared memory once per CTA and patches in what depends on the problem (the task on a joint) and on the record
+// layout (the dummy blocks).  All exchanges between lanes are synchronised at the top level of the loop (full-mask __syncwarp(), free in
 // converged code).  The level order of the table (children before parents towards the root, parents first on the way
 // out) makes the pending blocks and the parents' v rows valid when a step reads them: a step's stores are separated
 // from the next step's loads by the __syncwarp() at its top.
 // ---------------------------------------------------------------------------------------------
-struct WideStep { int joint_parent, flags, loff_pout, sidx_ploff; };  // joint | parent << 16; WF_*; JointC::loff | pout << 16; (aligned axis index or -1) & 0xffff | parent's loff << 16
+struct WideStep { int joint_parent, flags, loff_pout, sidx_ploff; };  // joint | parent << 16; WF_* | (task + 1) << 8 (in the kernel's copy); block offset | pout << 16; (aligned axis index or -1) & 0xffff | parent's block offset << 16
 enum : int { WF_VALID = 1, WF_FIRST = 2, WF_GIVE = 4, WF_ROOT = 8, WF_PINS = 16 };  // FIRST: first step of a chain; GIVE: result goes to a pending block
 
 LOIK_DEV void wide_backward(const ModelC& M, const LaneDims& D, const double* CB, double* I, double* X, const int l, const int g,
@@ -512,24 +518,27 @@ LOIK_DEV void wide_backward(const ModelC& M, const LaneDims& D, const double* CB
   const bool isp = l >= 6;
   const double facv = isp ? -rho : 0.0;
   double* XT = X + LX_T;
-  double* XD = X + LX_DUMMY;
+  double* XD = X + LX_WDUMMY;
+  const double* CZ = CB + D.cz0 + lc;
   const double* XTrow = XT + 10 * lc;
   const int cstep = M.href_uniform ? 0 : CJ_ROWS;
   double cc[6] = {0, 0, 0, 0, 0, 0};
+  int4 nxt = tab[g];
   for (int s = 0; s < nsteps; ++s) {
-    const int4 ws = tab[4 * s + g];
+    const int4 ws = nxt;
+    nxt = tab[4 * (s + 1) + g];  // (the table has a spare step behind the last one)
     const int i = ws.x & 0xffff;
     const bool valid = ws.y & WF_VALID, carry_in = valid && !(ws.y & WF_FIRST);
     double* Pj = I + D.joint0 + (ws.z & 0xffff);
-    double* Pw = valid ? Pj : XD;
-    const double* Cj = CB + cstep * (i - 1) + lc;
+    double* Pw = Pj + (valid ? 0 : LX_WDUMMY - LX_RDUMMY);
+    const double* Cj = valid ? CB + cstep * (i - 1) + lc : CZ;
     __syncwarp();
     double vold[6], col[6];
     lds6(Pj + LJ_V, vold);
     const double w_i = Pj[LJ_W], z_i = Pj[LJ_Z];
 #pragma unroll
     for (int r = 0; r < 6; ++r) col[r] = fma(facv, vold[r], Cj[CJ_HREFR + 8 * r]);
-    const int task = valid ? M.j[i].task : -1;
+    const int task = ((ws.y >> 8) & 0xff) - 1;
     if (task >= 0) {
       const double* Ck = M.a_per ? I + D.tmat0 + CT_ROWS * task : CB + D.ctask0 + CT_ROWS * task;
       const double* Pk = I + D.task0 + LT_ROWS * task;
@@ -605,14 +614,15 @@ LOIK_DEV void wide_forward(const ModelC& M, const LaneDims& D, const double* CB,
                            const unsigned gmask, const double mu, const double mu_eq, Carry& cy, LanePart& pt, const int4* tab, const int nsteps) {
   const double inv_mu = 1.0 / mu;
   const int lc = l < 6 ? l : 5;
-  double* XD = X + LX_DUMMY;
   double v[6] = {0, 0, 0, 0, 0, 0};
+  int4 nxt = tab[g];
   for (int s = 0; s < nsteps; ++s) {
-    const int4 ws = tab[4 * s + g];
+    const int4 ws = nxt;
+    nxt = tab[4 * (s + 1) + g];
     const int i = ws.x & 0xffff, parent = ws.x >> 16;
     const bool valid = ws.y & WF_VALID;
     double* Pj = I + D.joint0 + (ws.z & 0xffff);
-    double* Pw = valid ? Pj : XD;
+    double* Pw = Pj + (valid ? 0 : LX_WDUMMY - LX_RDUMMY);
     __syncwarp();
     double UD[6], R[9], tr[3];
     const double vold_l = Pj[LJ_V + lc];
@@ -655,15 +665,15 @@ LOIK_DEV void wide_forward(const ModelC& M, const LaneDims& D, const double* CB,
     const double rp = nu - z;
     const double dw = mu * rp;
     const double f_l = hc[0] * v[0] + hc[1] * v[1] + hc[2] * v[2] + hc[3] * v[3] + hc[4] * v[4] + hc[5] * v[5] + p_l;
-    {
-      cy.nu_inf = amax(cy.nu_inf, valid ? nu : 0.0);
-      cy.dnu_inf = amax(cy.dnu_inf, valid ? nu - nz.x : 0.0);
-      cy.dz_inf = amax(cy.dz_inf, valid ? z - nz.y : 0.0);
-      cy.pres_slack = amax(cy.pres_slack, valid ? rp : 0.0);
-      cy.dw_inf = amax(cy.dw_inf, valid ? dw : 0.0);
-      cy.ubdw_p += valid ? ub * dmax(dw, 0.0) : 0.0;
-      cy.lbdw_m += valid ? lb * dmin(dw, 0.0) : 0.0;
-      pt.dfis = amax(pt.dfis, valid ? f_l - fold_l : 0.0);
+    {  // (a step without work: nu = z = dw = f = 0 exactly)
+      cy.nu_inf = amax(cy.nu_inf, nu);
+      cy.dnu_inf = amax(cy.dnu_inf, nu - nz.x);
+      cy.dz_inf = amax(cy.dz_inf, z - nz.y);
+      cy.pres_slack = amax(cy.pres_slack, rp);
+      cy.dw_inf = amax(cy.dw_inf, dw);
+      cy.ubdw_p += ub * dmax(dw, 0.0);
+      cy.lbdw_m += lb * dmin(dw, 0.0);
+      pt.dfis = amax(pt.dfis, f_l - fold_l);
     }
     __syncwarp();
     if (l == 0) sts6(Pw + LJ_V, v);
@@ -671,8 +681,8 @@ LOIK_DEV void wide_forward(const ModelC& M, const LaneDims& D, const double* CB,
     *reinterpret_cast<double2*>(Pw + LJ_NU) = make_double2(nu, z);
     Pw[LJ_W] = w_old + dw;
     __syncwarp();
-    pt.dvis = amax(pt.dvis, valid ? Pj[LJ_V + lc] - vold_l : 0.0);
-    const int task = valid ? M.j[i].task : -1;
+    pt.dvis = amax(pt.dvis, Pj[LJ_V + lc] - vold_l);  // (a step without work reads the zero block again)
+    const int task = ((ws.y >> 8) & 0xff) - 1;
     if (task >= 0) {  // DualUpdate for the task on this joint (:410-451); only the group that owns the joint is here
       const double* Ck = M.a_per ? I + D.tmat0 + CT_ROWS * task : CB + D.ctask0 + CT_ROWS * task;
       double* Pk = I + D.task0 + LT_ROWS * task;
@@ -712,15 +722,18 @@ LOIK_DEV void wide_residual(const ModelC& M, const LaneDims& D, const double* CB
                             LanePart& pt, const int4* tab, const int nsteps) {
   const int lc = l < 6 ? l : 5;
   const int cstep = M.href_uniform ? 0 : CJ_ROWS;
-  double* XD = X + LX_DUMMY;
+  double* XD = X + LX_WDUMMY;
+  const double* CZ = CB + D.cz0 + lc;
   double cF = 0.0;
+  int4 nxt = tab[g];
   for (int s = 0; s < nsteps; ++s) {
-    const int4 ws = tab[4 * s + g];
+    const int4 ws = nxt;
+    nxt = tab[4 * (s + 1) + g];
     const int i = ws.x & 0xffff;
     const bool valid = ws.y & WF_VALID, carry_in = valid && !(ws.y & WF_FIRST);
     double* Pj = I + D.joint0 + (ws.z & 0xffff);
-    double* Pw = valid ? Pj : XD;
-    const double* Cj = CB + cstep * (i - 1) + lc;
+    double* Pw = Pj + (valid ? 0 : LX_WDUMMY - LX_RDUMMY);
+    const double* Cj = valid ? CB + cstep * (i - 1) + lc : CZ;
     __syncwarp();
     double f[6], v[6];
     lds6(Pj + LJ_F, f);
@@ -733,7 +746,7 @@ LOIK_DEV void wide_residual(const ModelC& M, const LaneDims& D, const double* CB
     const int k = (short)(ws.w & 0xffff);
     const double Stf = k >= 0 ? Pj[LJ_F + k] : St_dot(M.j[i], f);
     double F = 0.0;
-    const int task = valid ? M.j[i].task : -1;
+    const int task = ((ws.y >> 8) & 0xff) - 1;
     if (task >= 0) F = I[D.task0 + LT_ROWS * task + LT_ATY + lc];
     if (ws.y & WF_PINS) {
       const JointC& J = M.j[i];
@@ -744,12 +757,12 @@ LOIK_DEV void wide_residual(const ModelC& M, const LaneDims& D, const double* CB
     const double Hrv = hr[0] * v[0] + hr[1] * v[1] + hr[2] * v[2] + hr[3] * v[3] + hr[4] * v[4] + hr[5] * v[5];
     const double rd = Hrv - Hv_l + F;
     const double Tn = Stf + wt.x;
-    pt.dF = amax(pt.dF, valid ? F - Fold : 0.0);
-    pt.Finf = amax(pt.Finf, valid ? F : 0.0);
-    pt.Hrefv = amax(pt.Hrefv, valid ? Hrv : 0.0);
-    pt.dresv = amax(pt.dresv, valid ? rd : 0.0);
-    rs.T_inf = amax(rs.T_inf, valid ? Tn : 0.0);
-    rs.dT_inf = amax(rs.dT_inf, valid ? Tn - wt.y : 0.0);
+    pt.dF = amax(pt.dF, F - Fold);  // (a step without work: f = v = F = T = 0 exactly)
+    pt.Finf = amax(pt.Finf, F);
+    pt.Hrefv = amax(pt.Hrefv, Hrv);
+    pt.dresv = amax(pt.dresv, rd);
+    rs.T_inf = amax(rs.T_inf, Tn);
+    rs.dT_inf = amax(rs.dT_inf, Tn - wt.y);
     __syncwarp();
     Pw[LJ_FD + lc] = F;
     Pw[LJ_T] = Tn;
@@ -773,8 +786,15 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
   double* CB = lsm;
   const int4* tabB = reinterpret_cast<const int4*>(lsm + D.tab0);
   const int4* tabF = tabB + 4 * M.nsb;
-  if (GPI > 1)
-    for (int e = threadIdx.x; e < 4 * (M.nsb + M.nsf); e += blockDim.x) reinterpret_cast<int4*>(lsm + D.tab0)[e] = P.tab[e];
+  if (GPI > 1) {
+    for (int e = threadIdx.x; e < 4 * (M.nsb + M.nsf + 1); e += blockDim.x) {
+      int4 ws = e < 4 * (M.nsb + M.nsf) ? P.tab[e] : make_int4(1, 0, 0, 0);
+      if (ws.y & WF_VALID) ws.y |= (M.j[ws.x & 0xffff].task + 1) << 8;                                  // the task on the joint (SolveInit)
+      else ws.z = D.xch + (e & 3) * LX_ROWS_WIDE + LX_RDUMMY - D.joint0;                                // this group's zero block
+      reinterpret_cast<int4*>(lsm + D.tab0)[e] = ws;
+    }
+    for (int e = threadIdx.x; e < CJ_ROWS; e += blockDim.x) lsm[D.cz0 + e] = 0.0;
+  }
   for (int e = threadIdx.x; e < D.csize; e += blockDim.x) {
     double x = 0.0;
     if (e < D.ctask0) {
@@ -804,6 +824,16 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
   const unsigned imask = GPI == 1 ? gmask : 0xffffffffu;
   double* I = lsm + D.cpad + (size_t)(GPI == 1 ? w * kLaneI + g : w) * D.stride;
   double* X = I + D.xch + (GPI == 1 ? 0 : g * LX_ROWS_WIDE);
+  if (GPI > 1) {  // the dummy blocks of this group (never written again: lane_load only touches joints, tasks and globals)
+    for (int e = l; e < LX_ROWS_WIDE - LX_RDUMMY; e += 8) X[LX_RDUMMY + e] = 0.0;
+    __syncwarp();
+    if (l == 0) {
+      double* Z = X + LX_RDUMMY;
+      Z[LJ_LB] = -1.0; Z[LJ_UB] = 1.0;
+      Z[LJ_XF] = 1.0; Z[LJ_XF + 4] = 1.0; Z[LJ_XF + 8] = 1.0;
+    }
+    __syncwarp();
+  }
   const int limit = P.list ? *P.n_list : P.n;
   int home_slot = -1;  // >= 0: these lanes hold an instance
   int status = ST_CONVERGED, it = 0, left = 0;
