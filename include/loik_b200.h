@@ -238,6 +238,12 @@ LOIK_API int loik_solve_init(loik_solver* h, const double* q, const double* H_re
 /* problem_.UpdateReferences(H_refs, v_refs)  (ik-id-description-optimized.hpp:103-121): per-joint references,
  * H_refs [njoints][36], v_refs [njoints][6], HOST pointers; call after loik_solve_init. */
 LOIK_API int loik_update_references(loik_solver* h, const double* H_refs, const double* v_refs, void* stream);
+/* The same with a reference velocity of its own for every instance (a batch of independent problems: e.g. the previous
+ * solution of each trajectory as v_ref): H_refs [njoints][36] HOST (per joint, shared by the batch), v_refs
+ * [batch][njoints][6] at `loc`.  Stays in force until the next loik_solve_init.  Costs 6 more rows per joint in HBM
+ * (H_ref v_ref, read twice per iteration): 8 * (155 n + 42 nc) algorithmic bytes per instance and iteration; solves with
+ * per-instance references run on the tile kernels only (the lane-parallel kernel keeps the references in per-CTA constants). */
+LOIK_API int loik_update_references_batch(loik_solver* h, const double* H_refs, const double* v_refs, int32_t loc, void* stream);
 
 /* ---- solving --------------------------------------------------------------------------------- */
 /* Solve()  (hpp:368-455): ResetRecursion + ResetSolver + main loop, every instance to its own

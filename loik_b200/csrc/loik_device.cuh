@@ -71,7 +71,8 @@ enum : int {  // rows of a joint block
   JR_V = 0, JR_F = 6, JR_FD = 12, JR_NU = 18, JR_Z = 19, JR_W = 20, JR_T = 21,  // persistent state (22 rows)
   JR_JQ = 22, JR_LB = 24, JR_UB = 25, JR_Q = 26,                                  // per-instance problem data (5 rows)
   JR_H = 27, JR_P = 48, JR_UD = 54, JR_DINV = 60, JR_R = 61,                      // backward -> forward workspace (35 rows)
-  JR_ROWS = 62
+  JR_HV = 62,                                                                      // H_ref v_ref of this instance (only touched with per-instance references, ModelC::vref_per)
+  JR_ROWS = 68
 };
 // rows of a task block: state y, Aty | per-instance problem data b, A^T b | per-instance task matrix A (row-major 6x6)
 // and A^T A (21 scalars: LL sym, LA, AA sym) when the batch does not share A (ModelC::a_per)
@@ -112,6 +113,7 @@ struct ModelC {
   int nmd, nv, nq, href_uniform;   // number of multi-DoF joints; model.nv, model.nq; every joint shares H_ref / v_ref (UpdateReference)
   SegC seg[kMaxSeg];
   int nsb, nsf;                    // steps of the wide sweeps of k_iterate_lane<4> (backward / forward order; build_wide_table)
+  int vref_per, pad1;              // v_ref differs per instance (loik_update_references_batch): H_ref v_ref in rows JR_HV, not HrefC::Hv
   int nspan, a_per;                // a_per: A_k (and A_k^T A_k) differ per instance: rows TR_A / TR_ATA of the task blocks, not TaskC
   SpanC span[kMaxSpan];
   Offs off;
@@ -174,6 +176,12 @@ LOIK_DEV double* joint_blk(double* T, const Offs& O, int ji) { return T + (size_
 LOIK_DEV double* task_blk(double* T, const Offs& O, int k) { return T + (size_t)(O.task0 + TR_ROWS * k) * 32; }
 // task matrices: batch-shared (parameter block) or per instance (rows of the task block Pk)
 LOIK_DEV double task_A(const ModelC& M, const TaskC& K, const double* Pk, int i) { return M.a_per ? Pk[(TR_A + i) * 32] : K.A[i]; }
+// H_ref v_ref of joint block P (problem_.Hv[i], ik-id-description-optimized.hpp:93,113): batch-shared or this instance's own
+// VR: compiled in only for the general instantiations of the iteration kernels (template parameter MD: models with multi-DoF
+// joints or per-instance references); the kernels the BASELINE robots run read the constant and carry no extra code
+// (1.2 % of a dense Panda launch when it was a run-time test).  Plain load: a migrating launch writes these rows.
+template <bool VR>
+LOIK_DEV double hv_of(const ModelC& M, const HrefC& Hr, const double* P, int c) { return (VR && M.vref_per) ? ld(P, JR_HV + c) : Hr.Hv[c]; }
 LOIK_DEV double* pend_blk(double* T, const Offs& O, int k) { return T + (size_t)(O.pend0 + PR_ROWS * k) * 32; }
 LOIK_DEV double* glob_blk(double* T, const Offs& O) { return T + (size_t)O.glob * 32; }
 // this lane's record of the debug arena (instances never migrate in debug mode: slot = home slot)
@@ -443,7 +451,7 @@ LOIK_DEV void discard_workspace(const double* Pj_lane) {
   const int lane = threadIdx.x & 31;
   const int rank = __popc(am & ((1u << lane) - 1u)), n = __popc(am);
   const char* base = reinterpret_cast<const char*>(Pj_lane - lane) + JR_H * 256;
-  constexpr int kLines = (JR_ROWS - JR_H) * 2;
+  constexpr int kLines = (JR_HV - JR_H) * 2;  // (rows JR_HV.. behind the workspace are problem data)
   for (int ln = rank; ln < kLines; ln += n) asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + ln * 128) : "memory");
 }
 
@@ -456,6 +464,7 @@ LOIK_DEV void discard_workspace(const double* Pj_lane) {
 // Td, where everything is written (and where what this iteration has already written is read back).  Ts == Td except
 // in the first iteration of a migrating launch, whose backward sweep also carries the problem data rows over
 // (`migrate`), so that the forward and residual sweeps read them from Td.
+template <bool VR = false>
 LOIK_DEV void sweep_backward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq,
                              const int lo, const int hi, const bool migrate = false) {
   const Offs& O = c_model.off;
@@ -500,7 +509,7 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, const double* Ts, double* Td
     // previous iterate here, which is the reference's vis_prev (UpdatePrev, data hxx:192-197).
     double A[6], B[9], D[6], p[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) p[c] = -rho * vold[c] - Hr.Hv[c];
+    for (int c = 0; c < 6; ++c) p[c] = -rho * vold[c] - hv_of<VR>(c_model, Hr, Ps, c);
 #pragma unroll
     for (int c = 0; c < 6; ++c) { A[c] = Hr.A[c]; D[c] = Hr.D[c]; }
 #pragma unroll
@@ -560,6 +569,8 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, const double* Ts, double* Td
       st(Pj, JR_JQ, qa); st(Pj, JR_JQ + 1, qb);
 #pragma unroll
       for (int c = 0; c < 3; ++c) st(Pj, JR_LB + c, cst[c]);
+      if (VR && c_model.vref_per)
+        for (int c = 0; c < 6; ++c) st(Pj, JR_HV + c, ldc(Ps, JR_HV + c));
       if (J.task >= 0) {
         double* Pk = task_blk(Td, O, J.task);
 #pragma unroll
@@ -753,7 +764,7 @@ struct Resid {
 // ---------------------------------------------------------------------------------------------
 LOIK_DEV void zero(Resid& rs) { rs.dres_v = rs.dres_nu = rs.Hrefv_inf = rs.F_inf = rs.T_inf = rs.dF_inf = rs.dT_inf = 0.0; }
 // Accumulates into `rs` (the caller zeroes it once per iteration and sets dres_nu = T_inf at the end, hxx:484).
-template <bool DEBUG>
+template <bool DEBUG, bool VR = false>
 LOIK_DEV void sweep_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs, const int lo, const int hi, double* Dg = nullptr) {
   const Offs& O = c_model.off;
   const int nb = c_model.nb;
@@ -813,7 +824,11 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, const double* Ts, double* Td
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
         dF[c] = F[c] - Fold[c];
-        rd[c] = Hrv[c] - Hr.Hv[c] + F[c];            // (:228)
+        rd[c] = Hrv[c] - hv_of<VR>(c_model, Hr, Pj, c) + F[c];  // (:228)
+      }
+      if (VR && c_model.vref_per) {  // |Hv|inf of this instance enters tol_dual next to |Href v|inf (:548-552): max is associative
+#pragma unroll
+        for (int c = 0; c < 6; ++c) rs.Hrefv_inf = amax(rs.Hrefv_inf, ld(Pj, JR_HV + c));
       }
       rs.dF_inf = amax6(rs.dF_inf, dF);             // (:215-220)
       rs.F_inf = amax6(rs.F_inf, F);                // (:223-225)
@@ -927,9 +942,11 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
       double* Pk = task_blk(Td, O, J.task);
       for (int c = TR_B; c < (c_model.a_per ? TR_ROWS : TR_A); ++c) st(Pk, c, ldc(Pks, c));
     }
+    if (c_model.vref_per)
+      for (int c = 0; c < 6; ++c) st(Pj, JR_HV + c, ldc(Pjs, JR_HV + c));
   }
 #pragma unroll
-  for (int c = 0; c < 6; ++c) { p[c] = -rho * ld(Pjs, JR_V + c) - Hr.Hv[c]; A[c] = Hr.A[c]; D[c] = Hr.D[c]; }
+  for (int c = 0; c < 6; ++c) { p[c] = -rho * ld(Pjs, JR_V + c) - hv_of<true>(c_model, Hr, Pjs, c); A[c] = Hr.A[c]; D[c] = Hr.D[c]; }
 #pragma unroll
   for (int c = 0; c < K; ++c) { w[c] = ld(Pfs, FR_W + c); z[c] = ld(Pfs, FR_Z + c); }
 #pragma unroll
@@ -1169,7 +1186,9 @@ LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* 
     rs.dF_inf = amax(rs.dF_inf, F[c] - Fold[c]);
     rs.F_inf = amax(rs.F_inf, F[c]);
     rs.Hrefv_inf = amax(rs.Hrefv_inf, Hrv[c]);
-    const double rd = Hrv[c] - Hr.Hv[c] + F[c];
+    const double hv = hv_of<true>(c_model, Hr, Pj, c);
+    if (c_model.vref_per) rs.Hrefv_inf = amax(rs.Hrefv_inf, hv);  // (this instance's |Hv|inf, see sweep_residual)
+    const double rd = Hrv[c] - hv + F[c];
     rs.dres_v = amax(rs.dres_v, rd);
     st(Pj, JR_FD + c, F[c]);
     if (DEBUG && Dg) st(Dg, O.drv + 6 * (i - 1) + c, rd);
@@ -1197,7 +1216,7 @@ LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* 
 LOIK_DEV void span_backward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, const int lo,
                             const int hi, const bool migrate) {
   const int k = c_model.j[lo].nvj;
-  if (k == 1) sweep_backward(c_model, Ts, Td, mu, mu_eq, lo, hi, migrate);
+  if (k == 1) sweep_backward<true>(c_model, Ts, Td, mu, mu_eq, lo, hi, migrate);
   else if (k == 3) md_backward<3>(c_model, Ts, Td, mu, mu_eq, lo, migrate);
   else md_backward<6>(c_model, Ts, Td, mu, mu_eq, lo, migrate);
 }
@@ -1214,7 +1233,7 @@ LOIK_DEV void span_forward(const ModelC& c_model, const double* Ts, double* Td, 
 template <bool DEBUG>
 LOIK_DEV void span_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs, const int lo, const int hi, double* Dg = nullptr) {
   const int k = c_model.j[lo].nvj;
-  if (k == 1) { sweep_residual<DEBUG>(c_model, Ts, Td, rs, lo, hi, Dg); return; }
+  if (k == 1) { sweep_residual<DEBUG, true>(c_model, Ts, Td, rs, lo, hi, Dg); return; }
   Resid tmp = rs;
   if (k == 3) md_residual<DEBUG, 3>(c_model, Ts, Td, tmp, lo, Dg);
   else md_residual<DEBUG, 6>(c_model, Ts, Td, tmp, lo, Dg);
@@ -1336,7 +1355,7 @@ LOIK_DEV void fine_fwdpass1(const ModelC& M, double* __restrict__ T, const doubl
     const HrefC& Hr = M.href[J.href];
     double* Pj = joint_blk(T, O, i - 1);
     double A[6], B[9], D[6], p[6];
-    for (int c = 0; c < 6; ++c) { p[c] = -M.rho * ld(Pj, JR_V + c) - Hr.Hv[c]; A[c] = Hr.A[c]; D[c] = Hr.D[c]; }
+    for (int c = 0; c < 6; ++c) { p[c] = -M.rho * ld(Pj, JR_V + c) - hv_of<true>(M, Hr, Pj, c); A[c] = Hr.A[c]; D[c] = Hr.D[c]; }
     for (int c = 0; c < 9; ++c) B[c] = Hr.B[c];
     A[0] += M.rho; A[3] += M.rho; A[5] += M.rho; D[0] += M.rho; D[3] += M.rho; D[5] += M.rho;
     if (J.task >= 0) {
@@ -1462,7 +1481,7 @@ LOIK_DEV void fine_compute_residuals(const ModelC& M, double* __restrict__ T, do
   st(G, GR_RES + 0, dmax(ld(G, GR_NORMS + N_PRES_TASK), ld(G, GR_NORMS + N_PRES_SLACK)));
   Resid rs;
   zero(rs);
-  sweep_residual<true>(M, T, T, rs, 1, M.nb, Dg);
+  sweep_residual<true, true>(M, T, T, rs, 1, M.nb, Dg);
   st(G, GR_NORMS + N_F, rs.F_inf); st(G, GR_NORMS + N_T, rs.T_inf); st(G, GR_NORMS + N_DF, rs.dF_inf); st(G, GR_NORMS + N_DT, rs.dT_inf);
   st(G, GR_NORMS + N_DRES_V, rs.dres_v); st(G, GR_NORMS + N_DRES_NU, rs.T_inf);
   st(G, GR_RES + 1, dmax(rs.dres_v, rs.T_inf));

@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kBlock) k_fine(const __grid_constant__ ModelC 
   switch (which) {
     case LOIK_STEP_RESET_INF_NORMS: fine_reset_inf_norms(c_model, T); break;
     case LOIK_STEP_FWD_PASS1: fine_fwdpass1(c_model, T, mu, mu_eq); break;
-    case LOIK_STEP_BWD_PASS: sweep_backward(c_model, T, T, mu, mu_eq, 1, c_model.nb); break;
+    case LOIK_STEP_BWD_PASS: sweep_backward<true>(c_model, T, T, mu, mu_eq, 1, c_model.nb); break;
     case LOIK_STEP_FWD_PASS2: fine_fwdpass2(c_model, T); break;
     case LOIK_STEP_BOX_PROJ: fine_boxproj(c_model, T, mu, dbg_ptr(S, c_model, s)); break;
     case LOIK_STEP_DUAL_UPDATE: fine_dualupdate(c_model, T, mu, mu_eq, dbg_ptr(S, c_model, s)); break;
@@ -648,6 +648,26 @@ __global__ void k_set_bounds(const __grid_constant__ ModelC c_model, const State
   }
 }
 
+// problem_.UpdateReferences with a v_ref of its own for every instance (v_refs [n][njoints][6]): Hv_i = H_ref_i v_ref_i
+// (ik-id-description-optimized.hpp:113) into rows JR_HV of the joint blocks; H_ref_i from the reference table
+__global__ void k_set_vref(const __grid_constant__ ModelC c_model, const StateP S, const double* __restrict__ v_refs) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S.n) return;
+  double* T = tile_ptr(S, c_model, s);
+  const int nb = c_model.nb;
+  for (int i = 1; i <= nb; ++i) {
+    const HrefC& Hr = c_model.href[c_model.j[i].href];
+    const double* vr = v_refs + ((size_t)s * (nb + 1) + i) * 6;
+    double v[6];
+    for (int c = 0; c < 6; ++c) v[c] = vr[c];
+    double* Pj = joint_blk(T, c_model.off, i - 1);
+    for (int a = 0; a < 3; ++a) {
+      st(Pj, JR_HV + a, Hr.A[si(a, 0)] * v[0] + Hr.A[si(a, 1)] * v[1] + Hr.A[si(a, 2)] * v[2] + Hr.B[3 * a] * v[3] + Hr.B[3 * a + 1] * v[4] + Hr.B[3 * a + 2] * v[5]);
+      st(Pj, JR_HV + 3 + a, Hr.B[a] * v[0] + Hr.B[3 + a] * v[1] + Hr.B[6 + a] * v[2] + Hr.D[si(a, 0)] * v[3] + Hr.D[si(a, 1)] * v[4] + Hr.D[si(a, 2)] * v[5]);
+    }
+  }
+}
+
 // batch-major gather of `nrows` rows: dst[s][k] = tile(s)[map[k]][lane(s)]  (map = absolute row indices).
 // (`base` / `tile_rows`: the arena and its rows per tile -- the state arena, or the debug arena for the residual vectors)
 __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ ModelC c_model, const StateP S, const int nrows, const int* __restrict__ map,
@@ -789,7 +809,7 @@ static void launch_iterate(loik_solver* h, cudaStream_t st, const StateP& S_in, 
   if (S.drop_ws) h->ws_valid = false;  // the consumed workspace lines are dropped from L2: undefined until the next backward sweep
   int g = grid_for(h->batch);
   if (max_ctas > 0) g = std::min(g, max_ctas);
-  const bool md = h->mc.nmd > 0;  // multi-DoF joints: the instantiations with the span-level dispatch
+  const bool md = h->mc.nmd > 0 || h->mc.vref_per;  // multi-DoF joints or per-instance references: the general instantiations (span-level dispatch)
   if (seg && h->mc.nwarp > 1 && !h->debug) {  // segment-parallel: one CTA (nwarp warps) per tile
     int gt = h->ntiles;
     if (max_ctas > 0) gt = std::min(gt, max_ctas);
@@ -870,7 +890,7 @@ static int launch_lane(loik_solver* h, cudaStream_t st, const double* src, const
   h->launches++;
   return LOIK_OK;
 }
-static bool use_lane(const loik_solver* h) { return h->lane_ok && h->lane_after >= 0 && !h->debug; }
+static bool use_lane(const loik_solver* h) { return h->lane_ok && h->lane_after >= 0 && !h->debug && !h->mc.vref_per; }  // (the lane record has no rows for per-instance references)
 
 // FwdPassInit stages q through shared memory (blockDim x nq doubles): the block shrinks for models whose q would not fit 48 KB
 static void launch_set_q(loik_solver* h, cudaStream_t st, const double* dq) {
@@ -1362,6 +1382,7 @@ static int set_problem_consts(loik_solver* h, const double* H_ref, const double*
   M.Hv_inf = hv_inf;  // = |Hv[0]|inf (ik-id-description-optimized.hpp:95)
   M.bounds_per_instance = bounds_shared ? 0 : 1;
   M.href_uniform = 1;
+  M.vref_per = 0;
   M.a_per = (A && n_ids <= kMaxTasks) ? 0 : 1;  // (more tasks than TaskC slots: the matrices live in the task rows too, k_set_b)
   sym_blocks(H_ref, M.href[0].A, M.href[0].B, M.href[0].D);  // UpdateReference: one reference broadcast to every joint
   for (int c = 0; c < 6; ++c) M.href[0].Hv[c] = Hv[c];
@@ -1469,6 +1490,29 @@ int loik_update_references(loik_solver* h, const double* H_refs, const double* v
     }
   }
   M.href_uniform = first.size() <= 1 ? 1 : 0;
+  return LOIK_OK;
+}
+
+int loik_update_references_batch(loik_solver* h, const double* H_refs, const double* v_refs, int32_t loc, void* stream) {
+  if (!h || !H_refs || !v_refs) return fail(LOIK_ERR_INVALID, "loik_update_references_batch: null argument");
+  if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_update_references_batch: call loik_solve_init first");
+  // the weights go through the shared path (reference table, symmetry check) with v_ref = 0: |Hv|inf does not grow there
+  std::vector<double> zero(6 * (size_t)h->nj, 0.0);
+  int rc = loik_update_references(h, H_refs, zero.data(), stream);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  const size_t bytes = (size_t)h->batch * h->nj * 6 * sizeof(double);
+  if (loc != LOIK_DEVICE) { rc = ensure_stage(h, bytes, loc == LOIK_HOST); if (rc) return rc; }
+  const void* dv = nullptr;
+  rc = to_device(h, v_refs, bytes, loc, 0, st, &dv);
+  if (rc) return rc;
+  h->mc.vref_per = 1;
+  k_set_vref<<<grid_for(h->batch, 128), 128, 0, st>>>(h->mc, h->S, (const double*)dv);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (loc == LOIK_HOST) CK(cudaStreamSynchronize(st));  // the staging buffer is reused by the next call
+  if (h->g_exec) { cudaGraphExecDestroy(h->g_exec); h->g_exec = nullptr; }  // (the schedule may change: no lane kernel with per-instance references)
   return LOIK_OK;
 }
 

@@ -40,7 +40,7 @@ NORM_NAMES = ["bT_delta_y_plus", "bT_delta_y_minus", "Av_inf_norm", "nu_inf_norm
               "primal_infeasible"]
 
 EXPORTS = ["loik_abi_version", "loik_last_error", "loik_create", "loik_destroy", "loik_model_layout", "loik_wide_table", "loik_solve_init",
-           "loik_update_references", "loik_solve", "loik_solve_full", "loik_solve_task", "loik_integrate", "loik_iterate_fixed",
+           "loik_update_references", "loik_update_references_batch", "loik_solve", "loik_solve_full", "loik_solve_task", "loik_integrate", "loik_iterate_fixed",
            "loik_fwd_pass_init", "loik_reset_recursion", "loik_step", "loik_set_debug", "loik_set_keep_workspace", "loik_get", "loik_get_stats", "loik_reduce_stats", "loik_launch_count",
            "loik_set_max_iter", "loik_set_rho", "loik_set_mu", "loik_set_mu_equality_scale_factor", "loik_set_tol_abs",
            "loik_set_tol_rel", "loik_set_tol_primal_inf", "loik_set_tol_dual_inf", "loik_set_tol_tail_solve",
@@ -91,6 +91,7 @@ def load_library(path: str | None = None):
     lib.loik_solve_init.argtypes = [vp] + prob
     lib.loik_solve_full.argtypes = [vp] + prob
     lib.loik_update_references.argtypes = [vp, dp, dp, vp]
+    lib.loik_update_references_batch.argtypes = [vp, dp, vp, i32, vp]
     lib.loik_solve.argtypes = [vp, vp]
     lib.loik_solve_task.argtypes = [vp, dp, i32, dp, i32, dp, i32, i32, vp]
     lib.loik_iterate_fixed.argtypes = [vp, i32, i32, vp]
@@ -361,6 +362,15 @@ class FirstOrderLoikOptimized:
             raise TypeError("Solve() takes 0, 4 or 8 arguments")
 
     def UpdateReferences(self, H_refs, v_refs):
+        """problem_.UpdateReferences(H_refs, v_refs) (ik-id-description-optimized.hpp:103-121).  ``v_refs`` of shape
+        ``[batch][njoints][6]`` (numpy or a CUDA tensor) gives every instance its own reference velocities."""
+        if getattr(v_refs, "ndim", 0) == 3:
+            Hb = _Buf(np.asarray(H_refs, np.float64).reshape(-1))
+            vb = _Buf(v_refs)
+            if Hb.shape[0] != 36 * self.model.nj or tuple(vb.shape) != (self.batch, self.model.nj, 6):
+                raise RuntimeError("[IkProblemFormulation::UpdateReferences]: input arguments 'H_refs', 'v_refs' have wrong size!!")
+            self._check(self._lib.loik_update_references_batch(self._h, Hb.ptr, vb.ptr, vb.loc, _current_stream()))
+            return
         Hb, vb = _Buf(np.asarray(H_refs, np.float64).reshape(-1)), _Buf(np.asarray(v_refs, np.float64).reshape(-1))
         if Hb.shape[0] != 36 * self.model.nj or vb.shape[0] != 6 * self.model.nj:
             raise RuntimeError("[IkProblemFormulation::UpdateReferences]: input arguments 'H_refs', 'v_refs' have wrong size!!")

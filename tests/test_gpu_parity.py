@@ -513,6 +513,80 @@ def test_update_references_per_joint():
     G.close()
 
 
+@pytest.mark.parametrize("name,B,kw", [("panda9", 160, {}), ("talos", 96, {}), ("talos_ff", 64, {}), ("panda", 2048, dict(max_iter=200))])
+def test_update_references_per_instance(name, B, kw):
+    """loik_update_references_batch: per-joint weights shared by the batch, a reference velocity of its own for every instance
+    and joint (UpdateReferences applied to each instance of the batch, ik-id-description-optimized.hpp:103-121), through
+    dense sweeps, migrating re-pack launches and (Talos) the segment kernel; fused steps at 1e-10 and full solves against
+    the oracle driven instance by instance.  The second solve runs through the cached launch graph."""
+    model = robots.get_robot(name)
+    rng = np.random.default_rng(5)
+    pb = problems.random_batch(model, B, seed=23)
+    nc = len(pb["ids"])
+    H_refs = np.zeros((model.nj, 6, 6))
+    for i in range(model.nj):
+        M = rng.normal(size=(6, 6))
+        H_refs[i] = np.eye(6) * rng.uniform(0.5, 2.0) + 0.05 * (M + M.T)
+    v_refs = 0.05 * rng.normal(size=(B, model.nj, 6))
+    params = problems.bench_params(nc, **(kw or dict(max_iter=60)))
+    G = _gpu(model, params, B)
+    _solve_init(G, pb)
+    G.UpdateReferences(H_refs, v_refs)
+    # two fused iterations, field by field (incl. tol_dual, which sees this instance's |H_ref v_ref|inf)
+    D = _gpu(model, params, B)
+    D.set_debug(True)
+    _solve_init(D, pb)
+    D.UpdateReferences(H_refs, v_refs)
+    D.ResetRecursion()
+    pick = list(range(0, B, max(1, B // 8)))
+    O = []
+    for i in pick:
+        o = _oracle(model, params)
+        o.SolveInit(*instance(pb, i))
+        o.UpdateReferences(H_refs, v_refs[i])
+        o.ResetSolver()
+        O.append(o)
+    for itn in (1, 2):
+        D.StepBackward(); D.StepForward(); D.StepResidual()
+        vis, fis, nu, res = D.vis, D.fis, D.nu, D.get(18)
+        for i, o in zip(pick, O):
+            o.UpdatePrev(); o.ResetInfNorms(); o.FwdPass1(); o.BwdPassOptimizedVisitor(); o.FwdPass2OptimizedVisitor(); o.BoxProj()
+            o.DualUpdate(); o.ComputeResiduals(); o.CheckConvergence()
+            if itn > 1:
+                o.CheckFeasibility()
+            o.UpdateMu()
+            tol = 1e-8 if any(model.nv_joint(j) > 1 for j in range(1, model.nj)) else 1e-10
+            check_abs_or_rel(vis[i], o.vis[1:], tol, "vis")
+            check_abs_or_rel(fis[i], o.fis[1:], tol * max(1.0, np.abs(o.fis).max()), "fis")
+            check_abs_or_rel(nu[i], o.nu, tol, "nu")
+            check_abs_or_rel(res[i, 3], o.get_tol_dual(), 1e-8, "tol_dual")
+    D.close()
+    for rep in range(2):
+        G.Solve()
+    z, it, mu = G.z, G.get_iter(), G.get_mu()
+    bad, worst = 0, 0.0
+    for i in range(0, B, max(1, B // 160)):
+        o = _oracle(model, params)
+        o.SolveInit(*instance(pb, i))
+        o.UpdateReferences(H_refs, v_refs[i])
+        o.Solve()
+        if o.get_iter() != it[i] or o.get_mu() != mu[i]:
+            bad += 1
+            continue
+        worst = max(worst, rel_inf(z[i], o.z))
+    assert bad == 0 and worst < 1e-6, (bad, worst)
+    # SolveInit puts the batch back on one shared reference
+    _solve_init(G, pb)
+    G.Solve()
+    o = _oracle(model, params)
+    o.SolveInit(*instance(pb, 3))
+    o.Solve()
+    assert o.get_iter() == G.get_iter()[3] and rel_inf(G.z[3], o.z) < 1e-6
+    with pytest.raises(RuntimeError, match="wrong size"):
+        G.UpdateReferences(H_refs, v_refs[:, :-1])
+    G.close()
+
+
 @pytest.mark.parametrize("name", ["panda", "ur10", "talos", "panda9", "ur10c"])
 def test_against_committed_golden_fixtures(name):
     """CUDA path vs tests/golden/random_*.npz (frozen oracle-pair outputs, scripts/make_golden.py) -- no oracle call."""
