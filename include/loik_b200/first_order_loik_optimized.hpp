@@ -118,9 +118,15 @@ class FirstOrderLoikOptimized {
   void CheckConvergence() { step(LOIK_STEP_CHECK_CONVERGENCE); }
   void CheckFeasibility() { step(LOIK_STEP_CHECK_FEASIBILITY); }
   void UpdateMu() { step(LOIK_STEP_UPDATE_MU); }
-  // problem_.UpdateReferences(H_refs, v_refs)  (ik-id-description-optimized.hpp:103-121): [njoints][36], [njoints][6]
+  // problem_.UpdateReferences(H_refs, v_refs)  (ik-id-description-optimized.hpp:103-121): [njoints][36], [njoints][6];
+  // v_refs of size [batch][njoints][6] gives every instance its own reference velocities
   void UpdateReferences(const std::vector<double>& H_refs, const std::vector<double>& v_refs) {
-    if (H_refs.size() != (size_t)model_.njoints * 36 || v_refs.size() != (size_t)model_.njoints * 6)
+    const size_t nj = (size_t)model_.njoints;
+    if (H_refs.size() == nj * 36 && batch_ > 1 && v_refs.size() == (size_t)batch_ * nj * 6) {
+      check(loik_update_references_batch(h_, H_refs.data(), v_refs.data(), LOIK_HOST, stream_));
+      return;
+    }
+    if (H_refs.size() != nj * 36 || v_refs.size() != nj * 6)
       throw std::runtime_error("[IkProblemFormulation::UpdateReferences]: input arguments 'H_refs', 'v_refs' have wrong size!!");
     check(loik_update_references(h_, H_refs.data(), v_refs.data(), stream_));
   }
