@@ -31,7 +31,7 @@ import math
 
 import numpy as np
 
-RX, RY, RZ, PX, PY, PZ, RU, PU, FF, RUBX, RUBY, RUBZ, RUBU, SPH, TRA, PLA = range(16)
+RX, RY, RZ, PX, PY, PZ, RU, PU, FF, RUBX, RUBY, RUBZ, RUBU, SPH, TRA, PLA, ZYX = range(17)
 _AXES = {"x": (1.0, 0.0, 0.0), "y": (0.0, 1.0, 0.0), "z": (0.0, 0.0, 1.0)}
 
 
@@ -109,11 +109,11 @@ class RobotModel:
 
     def nv_joint(self, i: int) -> int:
         jt = int(self.jtype[i])
-        return 6 if jt == FF else (3 if jt in (SPH, TRA, PLA) else 1)
+        return 6 if jt == FF else (3 if jt in (SPH, TRA, PLA, ZYX) else 1)
 
     def nq_joint(self, i: int) -> int:
         jt = int(self.jtype[i])
-        return {FF: 7, SPH: 4, TRA: 3, PLA: 4}.get(jt, 2 if RUBX <= jt <= RUBU else 1)
+        return {FF: 7, SPH: 4, TRA: 3, PLA: 4, ZYX: 3}.get(jt, 2 if RUBX <= jt <= RUBU else 1)
 
     def quaternion_slices(self):
         """(start, stop) of every unit quaternion inside q (free-flyer: q[iq+3:iq+7], spherical: q[iq:iq+4])."""
@@ -194,7 +194,7 @@ class RobotModel:
                     res = np.where((np.sum(res * quat, axis=-1) < 0.0)[..., None], -res, res)
                 res = res * ((3.0 - np.sum(res * res, axis=-1)) / 2.0)[..., None]        # quaternion::firstOrderNormalize
                 out[..., iq + o:iq + o + 4] = res
-            elif jt == TRA:
+            elif jt in (TRA, ZYX):  # vector spaces
                 out[..., iq:iq + 3] = q[..., iq:iq + 3] + v[..., iv:iv + 3]
             elif jt == PLA:  # SpecialEuclideanOperationTpl<2>::integrate_impl: (R0, t0) * exp(v)
                 c0, s0 = q[..., iq + 2], q[..., iq + 3]
@@ -223,7 +223,7 @@ class RobotModel:
         assert self.parent[0] == 0
         for i in range(1, self.nj):
             assert 0 <= self.parent[i] < i, "joints must be numbered parent < child"
-            assert 0 <= self.jtype[i] <= PLA
+            assert 0 <= self.jtype[i] <= ZYX
             assert abs(np.linalg.norm(self.axis[i]) - 1.0) < 1e-12
             R = self.placement_R[i]
             assert np.allclose(R @ R.T, np.eye(3), atol=1e-12)
@@ -241,12 +241,12 @@ def _build(name, joints) -> RobotModel:
     qmin, qmax, vmax, names = [], [], [], ["universe"]
     for i, (jn, par, jt, ax, xyz, rpy, lo, hi, vm) in enumerate(joints, start=1):
         parent[i] = par
-        if jt in ("FF", "S", "T", "PL"):
-            jtype[i] = {"FF": FF, "S": SPH, "T": TRA, "PL": PLA}[jt]
+        if jt in ("FF", "S", "T", "PL", "ZYX"):
+            jtype[i] = {"FF": FF, "S": SPH, "T": TRA, "PL": PLA, "ZYX": ZYX}[jt]
             axis[i] = (0.0, 0.0, 1.0)
             R[i] = rpy_to_matrix(*rpy)
             p[i] = xyz
-            nqj, nvj = {"FF": (7, 6), "S": (4, 3), "T": (3, 3), "PL": (4, 3)}[jt]
+            nqj, nvj = {"FF": (7, 6), "S": (4, 3), "T": (3, 3), "PL": (4, 3), "ZYX": (3, 3)}[jt]  # (ZYX: three Euler angles, away from the gimbal lock at +-pi/2)
             qmin += [-1.0] * nqj   # position box; the quaternion part is normalised by the samplers
             qmax += [1.0] * nqj
             vmax += [vm] * nvj
@@ -373,7 +373,7 @@ def talos(floating: bool = False) -> RobotModel:
 
 
 def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0.3, prismatic: float = 0.25,
-                continuous: float = 0.0, multidof: float = 0.0, max_multidof: int = 8) -> RobotModel:
+                continuous: float = 0.0, multidof: float = 0.0, max_multidof: int = 8, zyx: float = 0.0) -> RobotModel:
     """Seeded random kinematic tree covering every joint type (parity stress tests)."""
     rng = np.random.default_rng(seed)
     J = []
@@ -386,6 +386,9 @@ def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0
         if multidof > 0.0 and rng.random() < multidof and n_md < max_multidof:  # spherical / translation / free-flyer anywhere in the tree
             kind = ("S", "T", "FF", "PL")[int(rng.integers(0, 4))]
             n_md += 1
+        if zyx > 0.0 and rng.random() < zyx and n_md < max_multidof and kind not in ("S", "T", "FF", "PL"):  # JointModelSphericalZYX: S depends on q
+            kind = "ZYX"
+            n_md += 1
         if rng.random() < unaligned:
             ax = rng.normal(size=3)
         else:
@@ -394,7 +397,7 @@ def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0
         rpy = tuple(rng.uniform(-math.pi, math.pi, size=3))
         lo, hi = (-0.3, 0.3) if kind == "P" else (-2.5, 2.5)
         J.append((f"j{i}", par, kind, ax, xyz, rpy, lo, hi, float(rng.uniform(1.0, 4.0))))
-    return _build(f"random{nb}_s{seed}" + ("c" if continuous > 0.0 else "") + ("m" if multidof > 0.0 else ""), J)
+    return _build(f"random{nb}_s{seed}" + ("c" if continuous > 0.0 else "") + ("m" if multidof > 0.0 else "") + ("z" if zyx > 0.0 else ""), J)
 
 
 ROBOTS = {"panda": panda, "panda9": lambda: panda(True), "ur10": ur10, "ur10c": lambda: ur10(True), "talos": talos,

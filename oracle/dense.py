@@ -37,7 +37,15 @@ def dual_action_matrix(R, t):
     return X
 
 
-def joint_subspace(jtype, axis):
+def joint_subspace(jtype, axis, q=None):
+    """jdata.S(); `q` (the joint's configuration) is only needed where the subspace depends on it (SphericalZYX)."""
+    if jtype == 16:  # JointModelSphericalZYX (pinocchio joint-spherical-ZYX.hpp): w_body = E(q) qdot for R = Rz(q0) Ry(q1) Rx(q2)
+        if q is None:
+            return np.zeros((6, 3))
+        c1, s1, c2, s2 = np.cos(q[1]), np.sin(q[1]), np.cos(q[2]), np.sin(q[2])
+        S = np.zeros((6, 3))
+        S[3:] = [[-s1, 0.0, 1.0], [c1 * s2, c2, 0.0], [c1 * c2, -s2, 0.0]]
+        return S
     if jtype == 8:  # free-flyer
         return np.eye(6)
     if jtype == 13:  # spherical: S = [0; I3]
@@ -65,6 +73,14 @@ def joint_transform(jtype, axis, q):
     """jmodel.calc -> jdata.M(): (R, p).  q: scalar for 1-DoF joints, (x, y, z, qx, qy, qz, qw) for the free-flyer."""
     if jtype == 14:
         return np.eye(3), np.asarray(q[:3], float).copy()
+    if jtype == 16:  # SphericalZYX: three elementary rotations multiplied out (independent of the closed form in oracle B)
+        def rot(k, a):
+            c, s_ = np.cos(a), np.sin(a)
+            i, j = (k + 1) % 3, (k + 2) % 3
+            M = np.eye(3)
+            M[i, i] = c; M[i, j] = -s_; M[j, i] = s_; M[j, j] = c
+            return M
+        return rot(2, float(q[0])) @ rot(1, float(q[1])) @ rot(0, float(q[2])), np.zeros(3)
     if jtype == 15:  # planar: q = (x, y, cos, sin)
         c, s_ = float(q[2]), float(q[3])
         return np.array([[c, -s_, 0.0], [s_, c, 0.0], [0.0, 0.0, 1.0]]), np.array([float(q[0]), float(q[1]), 0.0])
@@ -160,6 +176,8 @@ class FirstOrderLoik:
         for i in range(1, self.nj):
             iq = mdl.idx_q(i)
             MR, Mp = joint_transform(int(mdl.jtype[i]), mdl.axis[i], q[iq:iq + mdl.nq_joint(i)])
+            if int(mdl.jtype[i]) == 16:
+                self.S[i] = joint_subspace(16, mdl.axis[i], q[iq:iq + 3])
             R = mdl.placement_R[i] @ MR
             p = mdl.placement_p[i] + mdl.placement_R[i] @ Mp
             self.liMi[i] = (R, p)
@@ -378,7 +396,7 @@ class FirstOrderLoik:
             self.UpdateMu()
 
 
-def kkt_report(model, liMi, task_ids, Ais, bis, H_ref, v_ref, lb, ub, v, nu, z, f, y, w):
+def kkt_report(model, liMi, task_ids, Ais, bis, H_ref, v_ref, lb, ub, v, nu, z, f, y, w, q=None):
     """KKT residuals of the QP of SURVEY.md section 0 at a primal-dual point (independent of ADMM):
     kinematics, task, stationarity in v and nu, box feasibility, complementarity of w."""
     nj = model.nj
@@ -390,7 +408,7 @@ def kkt_report(model, liMi, task_ids, Ais, bis, H_ref, v_ref, lb, ub, v, nu, z, 
     for i in range(1, nj):
         par = int(model.parent[i])
         R, t = liMi[i]
-        S = joint_subspace(int(model.jtype[i]), model.axis[i])
+        S = joint_subspace(int(model.jtype[i]), model.axis[i], None if q is None else q[model.idx_q(i):model.idx_q(i) + model.nq_joint(i)])
         iv, nvj = model.idx_v(i), model.nv_joint(i)
         vp = np.linalg.inv(action_matrix(R, t)) @ (v[par] if par > 0 else np.zeros(6))
         kin = max(kin, np.abs(-v[i] + vp + S @ nu[iv:iv + nvj]).max())
@@ -402,7 +420,7 @@ def kkt_report(model, liMi, task_ids, Ais, bis, H_ref, v_ref, lb, ub, v, nu, z, 
         A = np.asarray(Ais[k]).reshape(6, 6)
         stat_v[c] += A.T @ y[k]
         task = max(task, np.abs(A @ v[c] - bis[k]).max())
-    stat_nu = np.concatenate([joint_subspace(int(model.jtype[i]), model.axis[i]).T @ f[i]
+    stat_nu = np.concatenate([joint_subspace(int(model.jtype[i]), model.axis[i], None if q is None else q[model.idx_q(i):model.idx_q(i) + model.nq_joint(i)]).T @ f[i]
                               + w[model.idx_v(i):model.idx_v(i) + model.nv_joint(i)] for i in range(1, nj)])
     out["kinematics"] = kin
     out["task"] = task

@@ -32,9 +32,9 @@
 
 #define LO_API __attribute__((visibility("default")))
 
-enum { JT_RX = 0, JT_RY, JT_RZ, JT_PX, JT_PY, JT_PZ, JT_RU, JT_PU, JT_FF, JT_RUBX, JT_RUBY, JT_RUBZ, JT_RUBU, JT_SPH, JT_TRA, JT_PLA };
-static int jt_nv(int jt) { return jt == JT_FF ? 6 : ((jt == JT_SPH || jt == JT_TRA || jt == JT_PLA) ? 3 : 1); }
-static int jt_nq(int jt) { return jt == JT_FF ? 7 : ((jt == JT_SPH || jt == JT_PLA) ? 4 : (jt == JT_TRA ? 3 : ((jt >= JT_RUBX && jt <= JT_RUBU) ? 2 : 1))); }
+enum { JT_RX = 0, JT_RY, JT_RZ, JT_PX, JT_PY, JT_PZ, JT_RU, JT_PU, JT_FF, JT_RUBX, JT_RUBY, JT_RUBZ, JT_RUBU, JT_SPH, JT_TRA, JT_PLA, JT_ZYX };
+static int jt_nv(int jt) { return jt == JT_FF ? 6 : ((jt == JT_SPH || jt == JT_TRA || jt == JT_PLA || jt == JT_ZYX) ? 3 : 1); }
+static int jt_nq(int jt) { return jt == JT_FF ? 7 : ((jt == JT_SPH || jt == JT_PLA) ? 4 : ((jt == JT_TRA || jt == JT_ZYX) ? 3 : ((jt >= JT_RUBX && jt <= JT_RUBU) ? 2 : 1))); }
 
 typedef struct lo_solver {
   /* ---- model (what the hot path reads from pinocchio::Model) ---- */
@@ -195,8 +195,20 @@ static void joint_S(int jt, const double *axis, double *S) { /* S[6*row + col], 
     case JT_SPH: for (int k = 0; k < 3; ++k) S[6 * (3 + k) + k] = 1.0; break; /* JointModelSpherical: S = [0; I3] */
     case JT_TRA: for (int k = 0; k < 3; ++k) S[6 * k + k] = 1.0; break;       /* JointModelTranslation: S = [I3; 0] */
     case JT_PLA: S[6 * 0 + 0] = 1.0; S[6 * 1 + 1] = 1.0; S[6 * 5 + 2] = 1.0; break; /* JointModelPlanar: (vx, vy, wz) */
+    case JT_ZYX: break; /* JointModelSphericalZYX: S depends on q, filled by joint_S_of_q (FwdPassInit) */
     default: for (int k = 0; k < 6; ++k) S[7 * k] = 1.0; break; /* free-flyer: identity */
   }
+}
+
+/* JointModelSphericalZYX::calc (pinocchio joint-spherical-ZYX.hpp): the motion subspace depends on the configuration,
+ * S = [0; E(q)] with the body angular velocity w = E(q) qdot for R = Rz(q0) Ry(q1) Rx(q2). */
+static void joint_S_of_q(int jt, const double *qv, double *S) {
+  if (jt != JT_ZYX) return;
+  const double c1 = cos(qv[1]), s1 = sin(qv[1]), c2 = cos(qv[2]), s2 = sin(qv[2]);
+  memset(S, 0, 36 * sizeof(double));
+  S[6 * 3 + 0] = -s1;     S[6 * 3 + 1] = 0.0; S[6 * 3 + 2] = 1.0;
+  S[6 * 4 + 0] = c1 * s2; S[6 * 4 + 1] = c2;  S[6 * 4 + 2] = 0.0;
+  S[6 * 5 + 0] = c1 * c2; S[6 * 5 + 1] = -s2; S[6 * 5 + 2] = 0.0;
 }
 
 /* P5: jmodel.calc(jdata, q) -> jdata.M(): revolute M = (Rot(axis,q), 0), prismatic M = (I, axis q).
@@ -225,6 +237,13 @@ static void joint_M(int jt, const double *axis, const double *qv, double *MR, do
   if (jt == JT_PLA) { /* JointModelPlanar::calc: rotation about z from (cos, sin) = (q[2], q[3]) as given, translation (x, y, 0) */
     MR[0] = qv[2]; MR[1] = -qv[3]; MR[3] = qv[3]; MR[4] = qv[2];
     Mp[0] = qv[0]; Mp[1] = qv[1];
+    return;
+  }
+  if (jt == JT_ZYX) { /* JointModelSphericalZYX::calc: R = Rz(q0) Ry(q1) Rx(q2) */
+    const double c0 = cos(qv[0]), s0 = sin(qv[0]), c1 = cos(qv[1]), s1 = sin(qv[1]), c2 = cos(qv[2]), s2 = sin(qv[2]);
+    MR[0] = c0 * c1; MR[1] = c0 * s1 * s2 - s0 * c2; MR[2] = c0 * s1 * c2 + s0 * s2;
+    MR[3] = s0 * c1; MR[4] = s0 * s1 * s2 + c0 * c2; MR[5] = s0 * s1 * c2 - c0 * s2;
+    MR[6] = -s1;     MR[7] = c1 * s2;                MR[8] = c1 * c2;
     return;
   }
   if (jt == JT_FF || jt == JT_SPH) { /* q = (x, y, z, qx, qy, qz, qw): M = (R(quat), p); spherical: q = (qx, qy, qz, qw), p = 0 */
@@ -526,6 +545,7 @@ LO_API void lo_fwd_pass_init(lo_solver *s, const double *q) {
     double MR[9], Mp[3], t[3];
     int par = s->parent[i];
     joint_M(s->jtype[i], s->axis + 3 * i, q + s->idxq[i], MR, Mp);
+    joint_S_of_q(s->jtype[i], q + s->idxq[i], s->jS + 36 * i); /* jmodel.calc also sets jdata.S for configuration-dependent subspaces */
     /* liMi = jointPlacements[i] * M : (R1 R2, p1 + R1 p2) */
     m3mul(s->plR + 9 * i, MR, s->liMi_R + 9 * i);
     for (int a = 0; a < 3; ++a)

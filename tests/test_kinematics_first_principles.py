@@ -36,6 +36,8 @@ def _fk(model, q):
             pj = q[iq:iq + 3].copy() if jt == 8 else np.zeros(3)
         elif jt == 14:
             Rj, pj = np.eye(3), q[iq:iq + 3].copy()
+        elif jt == 16:  # SphericalZYX: yaw about z, then pitch about the new y, then roll about the new x
+            Rj, pj = _rot([0, 0, 1.0], q[iq]) @ _rot([0, 1.0, 0], q[iq + 1]) @ _rot([1.0, 0, 0], q[iq + 2]), np.zeros(3)
         elif jt == 15:  # planar: x, y, heading (cos, sin)
             Rj, pj = _rot([0, 0, 1.0], np.arctan2(q[iq + 3], q[iq + 2])), np.array([q[iq], q[iq + 1], 0.0])
         elif jt <= 2 or jt == 6:
@@ -77,7 +79,7 @@ def _move(model, q, v):
                               [2 * (x * z - y * ww), 2 * (y * z + x * ww), 1 - 2 * (x * x + y * y)]])
                 out[iq:iq + 3] = q[iq:iq + 3] + R @ v[iv:iv + 3]
             out[qs] = _quat_mul(q[qs], dq)
-        elif jt == 14:
+        elif jt in (14, 16):  # vector spaces: translation, Euler angles
             out[iq:iq + 3] = q[iq:iq + 3] + v[iv:iv + 3]
         elif jt == 15:  # body-frame (vx, vy, wz), first order in |v|
             th = np.arctan2(q[iq + 3], q[iq + 2])
@@ -125,11 +127,14 @@ def test_link_velocities_are_time_derivatives_of_forward_kinematics(name):
         _check(model, pr, f"{name}[{k}]")
 
 
-@pytest.mark.parametrize("seed,continuous,multidof", [(0, 0.0, 0.0), (1, 0.0, 0.0), (2, 0.5, 0.0), (3, 1.0, 0.0), (4, 0.0, 0.4), (5, 0.3, 0.5)])
-def test_link_velocities_random_trees(seed, continuous, multidof):
+@pytest.mark.parametrize("seed,continuous,multidof,zyx", [(0, 0.0, 0.0, 0.0), (1, 0.0, 0.0, 0.0), (2, 0.5, 0.0, 0.0), (3, 1.0, 0.0, 0.0), (4, 0.0, 0.4, 0.0),
+                                                          (5, 0.3, 0.5, 0.0), (6, 0.0, 0.0, 0.4), (7, 0.2, 0.3, 0.4), (8, 0.0, 0.0, 1.0)])
+def test_link_velocities_random_trees(seed, continuous, multidof, zyx):
     """Every joint type (aligned / unaligned, revolute / prismatic / unbounded revolute / spherical / translation /
-    free-flyer anywhere), random placements, branching."""
-    model = robots.random_tree(11, seed, continuous=continuous, multidof=multidof)
+    free-flyer / SphericalZYX -- whose motion subspace depends on q -- anywhere), random placements, branching."""
+    model = robots.random_tree(11, seed, continuous=continuous, multidof=multidof, zyx=zyx)
+    if zyx > 0.0:
+        assert (model.jtype == 16).any()
     rng = np.random.default_rng(500 + seed)
     ids = np.array(sorted(rng.choice(np.arange(1, model.nj), size=2, replace=False)), np.int32)
     pr = dict(q=model.normalize(rng.uniform(model.q_min, model.q_max)), H_ref=np.eye(6), v_ref=np.zeros(6), ids=ids,

@@ -120,12 +120,13 @@ def test_optimized_correctness_component_wise(name, bound):
         step_once_and_compare(A, B, model, it, f"{name} it{it}")
 
 
-@pytest.mark.parametrize("seed,continuous,multidof", [(0, 0.0, 0.0), (1, 0.0, 0.0), (2, 0.0, 0.0), (3, 0.0, 0.0), (4, 0.5, 0.0),
-                                                      (5, 0.5, 0.0), (6, 1.0, 0.0), (7, 0.0, 0.3), (8, 0.3, 0.3), (9, 0.0, 0.6)])
-def test_component_wise_random_trees(seed, continuous, multidof):
+@pytest.mark.parametrize("seed,continuous,multidof,zyx", [(0, 0.0, 0.0, 0.0), (1, 0.0, 0.0, 0.0), (2, 0.0, 0.0, 0.0), (3, 0.0, 0.0, 0.0), (4, 0.5, 0.0, 0.0),
+                                                          (5, 0.5, 0.0, 0.0), (6, 1.0, 0.0, 0.0), (7, 0.0, 0.3, 0.0), (8, 0.3, 0.3, 0.0), (9, 0.0, 0.6, 0.0),
+                                                          (10, 0.0, 0.0, 0.4), (11, 0.3, 0.3, 0.4), (12, 0.0, 0.0, 1.0)])
+def test_component_wise_random_trees(seed, continuous, multidof, zyx):
     """Same, on seeded random trees with every joint type (aligned/unaligned, revolute/prismatic/unbounded revolute,
     and -- oracles only so far -- spherical / translation joints and free-flyers anywhere in the tree), branching."""
-    model = robots.random_tree(12, seed, continuous=continuous, multidof=multidof)
+    model = robots.random_tree(12, seed, continuous=continuous, multidof=multidof, zyx=zyx)  # (zyx: JointModelSphericalZYX, S depends on q)
     rng = np.random.default_rng(100 + seed)
     params = dict(problems.FIXTURE_PARAMS, max_iter=2, num_eq_c=2)
     ids = np.array(sorted(rng.choice(np.arange(1, model.nj), size=2, replace=False)), np.int32)
