@@ -58,7 +58,9 @@ enum { LOIK_JOINT_RX = 0, LOIK_JOINT_RY, LOIK_JOINT_RZ, LOIK_JOINT_PX, LOIK_JOIN
        LOIK_JOINT_RUBX, LOIK_JOINT_RUBY, LOIK_JOINT_RUBZ, LOIK_JOINT_RUBU,
        LOIK_JOINT_SPHERICAL,   /* JointModelSpherical (nq 4 = unit quaternion x y z w, nv 3, S = [0; I3]) */
        LOIK_JOINT_TRANSLATION, /* JointModelTranslation (nq = nv = 3, S = [I3; 0]) */
-       LOIK_JOINT_PLANAR       /* JointModelPlanar (nq 4 = x y cos sin, nv 3 = vx vy wz: S selects components 0, 1, 5) */ };
+       LOIK_JOINT_PLANAR,      /* JointModelPlanar (nq 4 = x y cos sin, nv 3 = vx vy wz: S selects components 0, 1, 5) */
+       LOIK_JOINT_SPHERICAL_ZYX /* JointModelSphericalZYX (nq = nv = 3: yaw, pitch, roll; R = Rz Ry Rx; the motion subspace
+                                   S = [0; E(q)] depends on the configuration) */ };
 
 /* where a caller buffer lives: pageable host memory (staged + synchronous), device memory (asynchronous),
  * or page-locked host memory (asynchronous DMA; the caller synchronizes the stream before reusing / reading it) */

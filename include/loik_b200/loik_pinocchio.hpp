@@ -84,7 +84,8 @@ inline FlatModel flatten(const Model& m) {
         {"JointModelPX", LOIK_JOINT_PX, 0}, {"JointModelPY", LOIK_JOINT_PY, 1}, {"JointModelPZ", LOIK_JOINT_PZ, 2},
         {"JointModelRUBX", LOIK_JOINT_RUBX, 0}, {"JointModelRUBY", LOIK_JOINT_RUBY, 1}, {"JointModelRUBZ", LOIK_JOINT_RUBZ, 2},
         {"JointModelFreeFlyer", LOIK_JOINT_FF, 2}, {"JointModelSpherical", LOIK_JOINT_SPHERICAL, 2},
-        {"JointModelTranslation", LOIK_JOINT_TRANSLATION, 2}, {"JointModelPlanar", LOIK_JOINT_PLANAR, 2}};
+        {"JointModelTranslation", LOIK_JOINT_TRANSLATION, 2}, {"JointModelPlanar", LOIK_JOINT_PLANAR, 2},
+        {"JointModelSphericalZYX", LOIK_JOINT_SPHERICAL_ZYX, 2}};
     for (const auto& a : kAligned)
       if (s == a.name) { code = a.code; ax[0] = ax[1] = ax[2] = 0.0; ax[a.axis] = 1.0; }
     if (code < 0) {

@@ -88,7 +88,8 @@ enum : int { FR_NU = 0, FR_Z = 6, FR_W = 12, FR_T = 18,   // state (24 rows)
              FR_LB = 24, FR_UB = 30, FR_Q = 36,          // problem data (19 rows): bounds, q (up to 7: x y z qx qy qz qw)
              FR_XF = 43,                                 // liMi = placement * M(q): rotation (9, row-major), translation (3)
              FR_DINV = 55, FR_R = 76, FR_UD = 82,        // workspace: Dinv (21, symmetric packed), r (6), UDinv (6 x K, [a][k])
-             FR_ROWS = 118 };
+             FR_S = 118,                                 // configuration-dependent motion subspace S = [0; E(q)] (SphericalZYX): E 3 x 3 row-major (k_set_q)
+             FR_ROWS = 127 };
 
 struct Offs {
   int glob, joint0, task0, pend0;  // first row of the globals, of joint 1, of task 0, of pending slot 0
@@ -920,7 +921,7 @@ LOIK_DEV void md_load_xf(const double* Pf, double (&R)[9], double (&t)[3]) {
   for (int c = 0; c < 3; ++c) t[c] = ld(Pf, FR_XF + 9 + c);
 }
 
-template <int K>
+template <int K, bool DS = false>
 LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, const int i,
                           const bool migrate) {
   const Offs& O = c_model.off;
@@ -970,16 +971,34 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
 #pragma unroll
     for (int c = 0; c < 9; ++c) B[c] += ld(Pp, PR_H + 6 + c);
   }
+  // U = H S: the selected columns of H (read in place below), or (DS: S = [0; E(q)], K = 3) the angular columns of H times E
+  double E[DS ? 9 : 1], Ud[DS ? 6 : 1][K];
+  if (DS) {
+#pragma unroll
+    for (int c = 0; c < 9; ++c) E[c] = ld(migrate ? Pfs : Pf, FR_S + c);
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int k = 0; k < K; ++k) Ud[a][k] = Hel(A, B, D, a, 3) * E[k] + Hel(A, B, D, a, 4) * E[3 + k] + Hel(A, B, D, a, 5) * E[6 + k];
+    if (migrate)
+      for (int c = 0; c < 9; ++c) st(Pf, FR_S + c, E[c]);
+  }
   double Mx[K * K], Dinv[K * (K + 1) / 2], r[K];
 #pragma unroll
   for (int a = 0; a < K; ++a)
 #pragma unroll
-    for (int b = 0; b < K; ++b) Mx[K * a + b] = Hel(A, B, D, sel[a], sel[b]);
+    for (int b = 0; b < K; ++b) {  // S^T U
+      if (DS) Mx[K * a + b] = E[a] * Ud[3][b] + E[3 + a] * Ud[4][b] + E[6 + a] * Ud[5][b];
+      else Mx[K * a + b] = Hel(A, B, D, sel[a], sel[b]);
+    }
 #pragma unroll
   for (int c = 0; c < K; ++c) Mx[(K + 1) * c] += mu;  // armature R = mu_ineq (hxx:294-295)
   spd_inverse<K>(Mx, Dinv);
 #pragma unroll
-  for (int c = 0; c < K; ++c) r[c] = (w[c] - mu * z[c]) + p[sel[c]];  // r = w - mu z (:296) + S^T p (:70)
+  for (int c = 0; c < K; ++c) {  // r = w - mu z (:296) + S^T p (:70)
+    if (DS) r[c] = (w[c] - mu * z[c]) + (E[c] * p[3] + E[3 + c] * p[4] + E[6 + c] * p[5]);
+    else r[c] = (w[c] - mu * z[c]) + p[sel[c]];
+  }
 #pragma unroll
   for (int c = 0; c < 6; ++c) { st(Pj, JR_H + c, A[c]); st(Pj, JR_H + 15 + c, D[c]); st(Pj, JR_P + c, p[c]); }
 #pragma unroll
@@ -989,7 +1008,7 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
 #pragma unroll
   for (int c = 0; c < K * (K + 1) / 2; ++c) st(Pf, FR_DINV + c, Dinv[c]);
   if (J.parent > 0) {
-    // UDinv = U Dinv with U = H S (the selected columns of H); H -= UDinv U^T (:63); p -= UDinv r (:71-73)
+    // UDinv = U Dinv; H -= UDinv U^T (:63); p -= UDinv r (:71-73)
     double UD[6][K];
 #pragma unroll
     for (int a = 0; a < 6; ++a)
@@ -997,7 +1016,7 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
       for (int k = 0; k < K; ++k) {
         double sum = 0.0;
 #pragma unroll
-        for (int l = 0; l < K; ++l) sum += Hel(A, B, D, a, sel[l]) * Dinv[sk<K>(l, k)];
+        for (int l = 0; l < K; ++l) sum += (DS ? Ud[a][l] : Hel(A, B, D, a, sel[l])) * Dinv[sk<K>(l, k)];
         UD[a][k] = sum;
         st(Pf, FR_UD + K * a + k, sum);
       }
@@ -1005,7 +1024,7 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
-      for (int k = 0; k < K; ++k) U[a][k] = Hel(A, B, D, a, sel[k]);
+      for (int k = 0; k < K; ++k) U[a][k] = DS ? Ud[a][k] : Hel(A, B, D, a, sel[k]);
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
@@ -1044,7 +1063,7 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
   }
 }
 
-template <bool DEBUG, int K>
+template <bool DEBUG, int K, bool DS = false>
 LOIK_DEV_CALL void md_forward(const ModelC& c_model, const double* Ts, double* Td, const double mu, const double mu_eq, Carry& cy, const int i, double* Dg) {
   const Offs& O = c_model.off;
   const JointC& J = c_model.j[i];
@@ -1094,7 +1113,14 @@ LOIK_DEV_CALL void md_forward(const ModelC& c_model, const double* Ts, double* T
     cy.nu_inf = amax(cy.nu_inf, nu[k]);
   }
 #pragma unroll
-  for (int k = 0; k < K; ++k) v[sel[k]] += nu[k];  // v_i = vp + S nu (:133-134)
+  for (int k = 0; k < K; ++k) {  // v_i = vp + S nu (:133-134)
+    if (DS) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) v[3 + a] += ld(Pf, FR_S + 3 * a + k) * nu[k];
+    } else {
+      v[sel[k]] += nu[k];
+    }
+  }
 #pragma unroll
   for (int c = 0; c < 6; ++c) cy.dvis_inf = amax(cy.dvis_inf, v[c] - vold[c]);
 #pragma unroll
@@ -1148,7 +1174,7 @@ LOIK_DEV_CALL void md_forward(const ModelC& c_model, const double* Ts, double* T
   }
 }
 
-template <bool DEBUG, int K>
+template <bool DEBUG, int K, bool DS = false>
 LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* Td, Resid& rs, const int i, double* Dg) {
   const Offs& O = c_model.off;
   const JointC& J = c_model.j[i];
@@ -1195,7 +1221,8 @@ LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* 
   }
 #pragma unroll
   for (int c = 0; c < K; ++c) {
-    const double Tn = f[sel[c]] + ld(Pf, FR_W + c);  // S^T f + w (:231)
+    const double Stf = DS ? ld(Pf, FR_S + c) * f[3] + ld(Pf, FR_S + 3 + c) * f[4] + ld(Pf, FR_S + 6 + c) * f[5] : f[sel[c]];
+    const double Tn = Stf + ld(Pf, FR_W + c);  // S^T f + w (:231)
     rs.T_inf = amax(rs.T_inf, Tn);
     rs.dT_inf = amax(rs.dT_inf, Tn - ld(Pfs, FR_T + c));
     st(Pf, FR_T + c, Tn);
@@ -1217,6 +1244,7 @@ LOIK_DEV void span_backward(const ModelC& c_model, const double* Ts, double* Td,
                             const int hi, const bool migrate) {
   const int k = c_model.j[lo].nvj;
   if (k == 1) sweep_backward<true>(c_model, Ts, Td, mu, mu_eq, lo, hi, migrate);
+  else if (k == 3 && c_model.j[lo].jtype == LOIK_JOINT_SPHERICAL_ZYX) md_backward<3, true>(c_model, Ts, Td, mu, mu_eq, lo, migrate);
   else if (k == 3) md_backward<3>(c_model, Ts, Td, mu, mu_eq, lo, migrate);
   else md_backward<6>(c_model, Ts, Td, mu, mu_eq, lo, migrate);
 }
@@ -1226,7 +1254,8 @@ LOIK_DEV void span_forward(const ModelC& c_model, const double* Ts, double* Td, 
   const int k = c_model.j[lo].nvj;
   if (k == 1) { sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, lo, hi, drop_ws, Dg); return; }
   Carry tmp = cy;
-  if (k == 3) md_forward<DEBUG, 3>(c_model, Ts, Td, mu, mu_eq, tmp, lo, Dg);
+  if (k == 3 && c_model.j[lo].jtype == LOIK_JOINT_SPHERICAL_ZYX) md_forward<DEBUG, 3, true>(c_model, Ts, Td, mu, mu_eq, tmp, lo, Dg);
+  else if (k == 3) md_forward<DEBUG, 3>(c_model, Ts, Td, mu, mu_eq, tmp, lo, Dg);
   else md_forward<DEBUG, 6>(c_model, Ts, Td, mu, mu_eq, tmp, lo, Dg);
   cy = tmp;
 }
@@ -1235,7 +1264,8 @@ LOIK_DEV void span_residual(const ModelC& c_model, const double* Ts, double* Td,
   const int k = c_model.j[lo].nvj;
   if (k == 1) { sweep_residual<DEBUG, true>(c_model, Ts, Td, rs, lo, hi, Dg); return; }
   Resid tmp = rs;
-  if (k == 3) md_residual<DEBUG, 3>(c_model, Ts, Td, tmp, lo, Dg);
+  if (k == 3 && c_model.j[lo].jtype == LOIK_JOINT_SPHERICAL_ZYX) md_residual<DEBUG, 3, true>(c_model, Ts, Td, tmp, lo, Dg);
+  else if (k == 3) md_residual<DEBUG, 3>(c_model, Ts, Td, tmp, lo, Dg);
   else md_residual<DEBUG, 6>(c_model, Ts, Td, tmp, lo, Dg);
   rs = tmp;
 }

@@ -436,6 +436,19 @@ __global__ void k_reset(const __grid_constant__ ModelC c_model, const StateP S, 
   }
 }
 
+// JointModelSphericalZYX::calc (pinocchio joint-spherical-ZYX.hpp): M = Rz(q0) Ry(q1) Rx(q2) and the angular block E(q) of the
+// motion subspace S = [0; E] (body angular velocity = E qdot)
+LOIK_DEV void zyx_calc(const double q0, const double q1, const double q2, double (&M)[9], double (&E)[9]) {
+  double s0, c0, s1, c1, s2, c2;
+  sincos(q0, &s0, &c0); sincos(q1, &s1, &c1); sincos(q2, &s2, &c2);
+  M[0] = c0 * c1; M[1] = c0 * s1 * s2 - s0 * c2; M[2] = c0 * s1 * c2 + s0 * s2;
+  M[3] = s0 * c1; M[4] = s0 * s1 * s2 + c0 * c2; M[5] = s0 * s1 * c2 - c0 * s2;
+  M[6] = -s1;     M[7] = c1 * s2;                M[8] = c1 * c2;
+  E[0] = -s1;     E[1] = 0.0; E[2] = 1.0;
+  E[3] = c1 * s2; E[4] = c2;  E[5] = 0.0;
+  E[6] = c1 * c2; E[7] = -s2; E[8] = 0.0;
+}
+
 // FwdPassInit (hxx:253-283): the q-dependent part of liMi, kept as (sin q, cos q) / (q, 0) per joint.
 // q is batch-major [n][nq]; it is staged through shared memory so both the read and the write coalesce.
 __global__ void __launch_bounds__(kBlock) k_set_q(const __grid_constant__ ModelC c_model, const StateP S, const double* __restrict__ q) {
@@ -454,12 +467,16 @@ __global__ void __launch_bounds__(kBlock) k_set_q(const __grid_constant__ ModelC
       const JointC& J = c_model.j[i];
       const double* qj = sh + threadIdx.x * nq + J.idxq;
       double* Pf = md_blk(T, c_model.off, J.mblk);
-      const int nqj = jt == LOIK_JOINT_FF ? 7 : (jt == LOIK_JOINT_TRANSLATION ? 3 : 4);
+      const int nqj = jt == LOIK_JOINT_FF ? 7 : ((jt == LOIK_JOINT_TRANSLATION || jt == LOIK_JOINT_SPHERICAL_ZYX) ? 3 : 4);
       for (int c = 0; c < nqj; ++c) st(Pf, FR_Q + c, qj[c]);
       double M[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pq[3] = {0, 0, 0};
       if (jt == LOIK_JOINT_PLANAR) {  // JointModelPlanar::calc: R = Rz from (cos, sin) = (q[2], q[3]) as given, p = (x, y, 0)
         M[0] = qj[2]; M[1] = -qj[3]; M[3] = qj[3]; M[4] = qj[2];
         pq[0] = qj[0]; pq[1] = qj[1];
+      } else if (jt == LOIK_JOINT_SPHERICAL_ZYX) {
+        double E[9];
+        zyx_calc(qj[0], qj[1], qj[2], M, E);
+        for (int c = 0; c < 9; ++c) st(Pf, FR_S + c, E[c]);
       } else if (jt != LOIK_JOINT_TRANSLATION) {
         const int o = jt == LOIK_JOINT_FF ? 3 : 0;
         const double x = qj[o], y = qj[o + 1], z = qj[o + 2], w = qj[o + 3];
@@ -507,6 +524,11 @@ __global__ void __launch_bounds__(128) k_integrate(const __grid_constant__ Model
       double M[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pq[3] = {0, 0, 0};
       if (jt == LOIK_JOINT_TRANSLATION) {
         for (int c = 0; c < 3; ++c) { pq[c] = ld(Pf, FR_Q + c) + dt * ld(Pf, FR_Z + c); st(Pf, FR_Q + c, pq[c]); }
+      } else if (jt == LOIK_JOINT_SPHERICAL_ZYX) {  // three Euler angles: a vector space; M and S follow the new configuration
+        double qn[3], E[9];
+        for (int c = 0; c < 3; ++c) { qn[c] = ld(Pf, FR_Q + c) + dt * ld(Pf, FR_Z + c); st(Pf, FR_Q + c, qn[c]); }
+        zyx_calc(qn[0], qn[1], qn[2], M, E);
+        for (int c = 0; c < 9; ++c) st(Pf, FR_S + c, E[c]);
       } else if (jt == LOIK_JOINT_PLANAR) {
         // SpecialEuclideanOperationTpl<2>::integrate_impl: (R0, t0) * exp(v): t = vcross - R vcross with vcross = (-vy, vx) / omega
         const double c0 = ld(Pf, FR_Q + 2), s0 = ld(Pf, FR_Q + 3);
@@ -1101,10 +1123,10 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
   if (batch < 1) return fail(LOIK_ERR_INVALID, "loik_create: batch must be >= 1");
   for (int i = 1; i < nj; ++i) {
     if (model->parents[i] < 0 || model->parents[i] >= i) return fail(LOIK_ERR_INVALID, "loik_create: parents[i] must be < i");
-    if (model->joint_types[i] < 0 || model->joint_types[i] > LOIK_JOINT_PLANAR)
-      return fail(LOIK_ERR_UNSUPPORTED, "loik_create: unsupported joint type (1-DoF revolute/prismatic joints, free-flyer, spherical, translation and planar joints are supported)");
+    if (model->joint_types[i] < 0 || model->joint_types[i] > LOIK_JOINT_SPHERICAL_ZYX)
+      return fail(LOIK_ERR_UNSUPPORTED, "loik_create: unsupported joint type (1-DoF revolute/prismatic joints, free-flyer, spherical, SphericalZYX, translation and planar joints are supported)");
   }
-  auto nv_of = [&](int i) { const int t = model->joint_types[i]; return t == LOIK_JOINT_FF ? 6 : ((t == LOIK_JOINT_SPHERICAL || t == LOIK_JOINT_TRANSLATION || t == LOIK_JOINT_PLANAR) ? 3 : 1); };
+  auto nv_of = [&](int i) { const int t = model->joint_types[i]; return t == LOIK_JOINT_FF ? 6 : ((t == LOIK_JOINT_SPHERICAL || t == LOIK_JOINT_TRANSLATION || t == LOIK_JOINT_PLANAR || t == LOIK_JOINT_SPHERICAL_ZYX) ? 3 : 1); };
   {
     int nmd = 0;
     for (int i = 1; i < nj; ++i) nmd += nv_of(i) > 1;
@@ -1116,7 +1138,7 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
   auto unbounded = [&](int i) { return model->joint_types[i] >= LOIK_JOINT_RUBX && model->joint_types[i] <= LOIK_JOINT_RUBU; };
   auto nq_of = [&](int i) {
     const int t = model->joint_types[i];
-    return t == LOIK_JOINT_FF ? 7 : ((t == LOIK_JOINT_SPHERICAL || t == LOIK_JOINT_PLANAR) ? 4 : (t == LOIK_JOINT_TRANSLATION ? 3 : (unbounded(i) ? 2 : 1)));
+    return t == LOIK_JOINT_FF ? 7 : ((t == LOIK_JOINT_SPHERICAL || t == LOIK_JOINT_PLANAR) ? 4 : ((t == LOIK_JOINT_TRANSLATION || t == LOIK_JOINT_SPHERICAL_ZYX) ? 3 : (unbounded(i) ? 2 : 1)));
   };
   h->nv = 0; h->nq = 0;
   for (int i = 1; i < nj; ++i) { h->nv += nv_of(i); h->nq += nq_of(i); }

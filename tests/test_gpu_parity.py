@@ -707,6 +707,56 @@ def test_multi_dof_joints_anywhere_full_solves(seed, multidof):
                     max_diverged_frac=0.01)
 
 
+@pytest.mark.parametrize("seed,multidof,zyx", [(0, 0.0, 0.4), (1, 0.3, 0.4), (2, 0.0, 1.0)])
+def test_spherical_zyx_joints_step_by_step(seed, multidof, zyx):
+    """JointModelSphericalZYX anywhere in a random tree: the motion subspace S = [0; E(q)] differs per instance (rows FR_S of
+    the multi-DoF block, written by FwdPassInit), U = H S is a product instead of a column selection: every fused step
+    against the oracle."""
+    model = robots.random_tree(9 + seed, 141 + seed, multidof=multidof, zyx=zyx)
+    assert (model.jtype == robots.ZYX).any()
+    pb = _multidof_problem(model, 33, seed)
+    _compare_steps(model, dict(problems.FIXTURE_PARAMS, max_iter=200, num_eq_c=2), pb, 3, f"zyxtree{seed}", tol=5e-9)
+
+
+@pytest.mark.parametrize("seed,multidof", [(0, 0.0), (1, 0.4)])
+def test_spherical_zyx_joints_full_solves_and_integrate(seed, multidof):
+    """Full solves (migrating launches carry the S rows along) on trees with SphericalZYX joints, then the device-side
+    outer loop: q <- q + dt z for the Euler angles, M and S of the new configuration, warm-started tracking solve."""
+    model = robots.random_tree(10 + 2 * seed, 160 + seed, multidof=multidof, zyx=0.5)
+    assert (model.jtype == robots.ZYX).any()
+    B = 300
+    pb = _multidof_problem(model, B, 20 + seed)
+    params = dict(problems.FIXTURE_PARAMS, max_iter=120, num_eq_c=2, tol_abs=1e-3, tol_rel=1e-3)
+    _compare_solves(model, params, pb, f"zyxsolve{seed}", max_diverged_frac=0.01)
+    G = _gpu(model, params, B)
+    _solve_init(G, pb)
+    np.testing.assert_array_equal(G.q, pb["q"])
+    L = G.liMi
+    for i in range(0, B, 37):
+        o = _oracle(model, params)
+        o.SolveInit(*instance(pb, i))
+        np.testing.assert_allclose(L[i][:, :9].reshape(-1, 3, 3), o.liMi_R[1:], rtol=0, atol=1e-14)
+    G.Solve()
+    zz = G.z
+    G.Integrate(0.05)
+    q1 = model.integrate(pb["q"], 0.05 * zz)
+    np.testing.assert_allclose(G.q, q1, rtol=0, atol=5e-15)
+    c_id = int(pb["ids"][0])
+    G.Solve(None, c_id, pb["Ais"][0], pb["bis"][:, 0])
+    z2, it2 = G.z, G.get_iter()
+    bad = 0
+    for i in range(0, B, 11):
+        o = _oracle(model, params)
+        o.Solve(*instance(pb, i))
+        o.Solve(q1[i], c_id, pb["Ais"][0], pb["bis"][i, 0])
+        if o.get_iter() != it2[i]:
+            bad += 1
+            continue
+        assert rel_inf(z2[i], o.z) < 1e-6, i
+    assert bad <= 1
+    G.close()
+
+
 def test_multi_dof_fwd_pass_init_and_integrate():
     """FwdPassInit for multi-DoF joints (liMi = placement * M(q): quaternion of free-flyer / spherical joints, offset of
     translation joints) against the oracle, the q getter layout, and the device-side integrate of a tree whose only
