@@ -259,7 +259,8 @@ LOIK_API int loik_solve_full(loik_solver* h, const double* q, const double* H_re
                              int32_t b_per_instance, const double* lb, const double* ub, int32_t bounds_per_instance, int32_t loc,
                              void* stream);
 /* Solve(q, c_id, Ai, bi)  (hpp:596-695): tailored / trajectory-tracking form: Reset(warm_start), ResetSolver,
- * UpdateEqConstraint(c_id, Ai, bi), FwdPassInit(q), main loop.  Ai [36] HOST, or [batch][36] at `loc` if A_per_instance
+ * UpdateEqConstraint(c_id, Ai, bi), FwdPassInit(q), main loop.  Ai [36] HOST, or [batch][36] at `loc` if A_per_instance;
+ * Ai == NULL is the UpdateEqConstraint(c_id, bi) overload (ik-id-description-optimized.hpp:224): the task keeps its matrix.  Ai
  * (which must match loik_solve_init's); q [batch][nq], bi [batch][6] (or [6] if !b_per_instance) at `loc`.  q == NULL
  * keeps the device-resident configuration (see loik_integrate). */
 LOIK_API int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double* Ai, int32_t A_per_instance,

@@ -1745,7 +1745,7 @@ int loik_solve_full(loik_solver* h, const double* q, const double* H_ref, const 
 
 int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double* Ai, int32_t A_per_instance, const double* bi,
                     int32_t b_per_instance, int32_t loc, void* stream) {
-  if (!h || !Ai || !bi) return fail(LOIK_ERR_INVALID, "loik_solve_task: null argument");
+  if (!h || !bi) return fail(LOIK_ERR_INVALID, "loik_solve_task: null argument");
   if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_solve_task: call loik_solve_init first");
   int rc = check_strategy(h);
   if (rc) return rc;
@@ -1756,11 +1756,13 @@ int loik_solve_task(loik_solver* h, const double* q, int32_t c_id, const double*
   int k = -1;
   for (int t = 0; t < h->nc; ++t) if (M.task_joint[t] == c_id) k = t;
   if (k < 0) return fail(LOIK_ERR_INVALID, "[IkProblemFormulation::UpdateEqConstraint]: constraint doesn't yet exist at link 'c_id' !!! ");
-  if ((A_per_instance != 0) != h->a_user_per)
+  // Ai == NULL: UpdateEqConstraint(c_id, bi) (:224-240): new target, the task keeps its matrix
+  if (!Ai) A_per_instance = 0;
+  if (Ai && (A_per_instance != 0) != h->a_user_per)
     return fail(LOIK_ERR_INVALID, "loik_solve_task: Ai must be per instance exactly when the task matrices of loik_solve_init were (all tasks of a handle "
                                   "keep their matrices in the same place)");
-  const bool a_rows_shared = M.a_per && !A_per_instance;
-  if (!M.a_per) {
+  const bool a_rows_shared = Ai && M.a_per && !A_per_instance;
+  if (Ai && !M.a_per) {
     TaskC& T = M.t[k];
     double AtA[36];
     for (int i = 0; i < 36; ++i) T.A[i] = Ai[i];

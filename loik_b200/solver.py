@@ -344,10 +344,15 @@ class FirstOrderLoikOptimized:
         elif len(args) == 4:
             q, c_id, Ai, bi = args
             bb = _Buf(bi)
-            a_per = int((Ai.dim() if _is_torch(Ai) else np.ndim(Ai)) == 3)  # [B, 6, 6]: every instance its own Ai
-            Ab = _Buf(Ai) if a_per else _Buf(np.asarray(Ai.cpu() if _is_torch(Ai) else Ai, np.float64).reshape(36))
-            if a_per and (tuple(Ab.shape) != (self.batch, 6, 6) or Ab.loc != bb.loc):
-                raise RuntimeError("a per-instance Ai must be [batch, 6, 6] and live where bi lives")
+            if Ai is None:  # UpdateEqConstraint(c_id, bi) (ik-id-description-optimized.hpp:224): the task keeps its matrix
+                class _Null:
+                    ptr = None
+                a_per, Ab = 0, _Null()
+            else:
+                a_per = int((Ai.dim() if _is_torch(Ai) else np.ndim(Ai)) == 3)  # [B, 6, 6]: every instance its own Ai
+                Ab = _Buf(Ai) if a_per else _Buf(np.asarray(Ai.cpu() if _is_torch(Ai) else Ai, np.float64).reshape(36))
+                if a_per and (tuple(Ab.shape) != (self.batch, 6, 6) or Ab.loc != bb.loc):
+                    raise RuntimeError("a per-instance Ai must be [batch, 6, 6] and live where bi lives")
             b_per = int(int(np.prod(bb.shape)) == self.batch * 6 and (self.batch > 1 or len(bb.shape) == 2))
             if q is None:  # keep the device-resident configuration (after Integrate)
                 self._check(self._lib.loik_solve_task(self._h, None, int(c_id), Ab.ptr, a_per, bb.ptr, b_per, bb.loc,

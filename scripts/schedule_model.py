@@ -1,4 +1,4 @@
-"""Warp-iteration model of the batched solve's launch schedule (DESIGN.md sections 2 and 9: "lanes idling next to
+"""Analysis aid (not a test of product code): warp-iteration model of the batched solve's launch schedule (DESIGN.md sections 2 and 9: "lanes idling next to
 unfinished neighbours inside a launch cost ~10 %").
 
 `plan` restates run_schedule (loik_b200/csrc/loik_solver.cu): `dense` sweeps on the home arena, then migrating launches
@@ -8,9 +8,13 @@ long as its slowest lane needs (at most the launch's iteration count), so the sc
 sum over launches and warps of max over lanes of min(chunk, remaining) warp-iterations against the ideal
 sum(iterations) / 32.  The per-instance iteration counts come from the CPU oracle on the bench's Panda batch.
 """
+import os
+import sys
+
 import numpy as np
 
-from loik_b200 import problems, robots
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from loik_b200 import problems, robots  # noqa: E402
 
 
 def plan(budget, dense=4, reps=2, growth=2.0, cap=64):
@@ -54,25 +58,13 @@ def _panda_iteration_counts(B=16384):
     return ref["iters"], params["max_iter"]
 
 
-def test_plan_covers_the_budget():
-    for budget in (1, 2, 3, 4, 5, 8, 50, 199, 200, 1000):
-        for dense in (0, 3, 4):
-            p = plan(budget, dense=dense)
-            assert sum(p) == budget and all(c >= 1 for c in p) and max(p) <= max(64, dense)
-    assert plan(200) == [4, 1, 1, 2, 2, 4, 4, 8, 8, 16, 16, 32, 32, 64, 6]  # 15 iteration launches for max_iter = 200
-
-
-def test_default_schedule_overhead_on_the_panda_batch():
+if __name__ == "__main__":
     iters, max_iter = _panda_iteration_counts()
     ideal = iters.sum() / 32
     spent, left = warp_iterations(iters, plan(max_iter))
-    assert left == 0  # every instance is done within the budget
-    ratio = spent / ideal
-    print(f"default schedule: {ratio:.3f} x the ideal warp-iterations (mean {iters.mean():.2f} iterations per instance)")
-    assert 1.0 <= ratio < 1.16
-    # never re-packing (one launch of max_iter iterations) is what the schedule is there to avoid
     never, _ = warp_iterations(iters, [max_iter])
-    assert never / ideal > 3.0
-    # the knobs sit on the flat optimum of the model: no (dense, reps) neighbour is more than 5 % better
-    best = min(warp_iterations(iters, plan(max_iter, dense=d, reps=r))[0] for d in (3, 4, 5) for r in (2, 3))
-    assert spent <= 1.05 * best
+    print(f"default schedule {plan(max_iter)}: {spent / ideal:.3f} x the ideal warp-iterations "
+          f"(mean {iters.mean():.2f} iterations per instance, {left} instances left); one launch of {max_iter} iterations: {never / ideal:.2f} x")
+    for d in (3, 4, 5):
+        for r in (2, 3):
+            print(f"  dense {d}, reps {r}: {warp_iterations(iters, plan(max_iter, dense=d, reps=r))[0] / ideal:.3f}")

@@ -239,3 +239,38 @@ def test_large_model_100_joints_16_tasks():
     too_big = robots.random_tree(104, seed=1)
     with pytest.raises(RuntimeError, match="njoints out of range"):
         _gpu(too_big, problems.bench_params(1), 4)
+
+
+@pytest.mark.parametrize("a_per", [False, True])
+def test_update_eq_constraint_target_only(a_per):
+    """problem_.UpdateEqConstraint(c_id, bi) (ik-id-description-optimized.hpp:224-240) through Solve(q, c_id, None, bi): a new
+    target, the task keeps the matrix it was given at SolveInit (batch-shared in the parameter block, or one per instance
+    in the task rows); an unknown link id fails with the reference's message."""
+    from oracle import recursion
+    model = robots.panda()
+    B = 96
+    rng = np.random.default_rng(8)
+    pb = problems.random_batch(model, B, seed=31)
+    A = np.eye(6) + 0.2 * rng.standard_normal((B, 1, 6, 6)) if a_per else (np.eye(6) + 0.2 * rng.standard_normal((1, 6, 6)))
+    pb = dict(pb, Ais=A)
+    params = dict(problems.bench_params(1), warm_start=True)
+    G = _gpu(model, params, B)
+    G.Solve(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], pb["lb"], pb["ub"])
+    b2 = problems.random_batch(model, B, seed=32)["bis"][:, 0]
+    c_id = int(pb["ids"][0])
+    G.Solve(pb["q"], c_id, None, b2)
+    z, it = G.z, G.get_iter()
+    bad = 0
+    for i in range(B):
+        Ai = A[i] if a_per else A
+        o = recursion.FirstOrderLoikOptimized(model, **ctor_kwargs(params))
+        o.Solve(pb["q"][i], pb["H_ref"], pb["v_ref"], pb["ids"], Ai, pb["bis"][i], pb["lb"], pb["ub"])
+        o.Solve(pb["q"][i], c_id, Ai[0], b2[i])
+        if o.get_iter() != it[i]:
+            bad += 1
+            continue
+        assert rel_inf(z[i], o.z) < 1e-6, i
+    assert bad == 0
+    with pytest.raises(RuntimeError, match="constraint doesn't yet exist"):
+        G.Solve(pb["q"], c_id - 1, None, b2)
+    G.close()
