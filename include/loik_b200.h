@@ -126,6 +126,8 @@ typedef struct loik_schedule {
                                        level by level through a host-built step table), 0 = default (4 when the tree branches, else 1) */
   int32_t drop_workspace;     /* tile kernels: drop the consumed backward->forward workspace lines from L2 (discard.global.L2)
                                  instead of letting them be written back to HBM; never applied with loik_set_keep_workspace */
+  double lane_hard_first_ratio; /* hand-over to the lane-parallel kernel: instances still in the main loop whose residual exceeds this many
+                                   times its tolerance are queued first (they bound the latency of the solve); 0 = slot order */
   /* read-only (ignored by loik_set_schedule) */
   int32_t lane_available, lane_warps_chosen, lane_groups_chosen, lane_ctas, lane_smem_bytes;
 } loik_schedule;

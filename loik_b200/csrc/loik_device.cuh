@@ -150,6 +150,12 @@ struct StateP {
   int* origin_dst;
   int* next_list;
   int* next_count;
+  // hand-over to the lane-parallel kernel: survivors that look far from done (main loop, residual > hard_ratio x its
+  // tolerance) claim from the front of next_list as usual, the others from its END (next_back counts them), so that the
+  // kernel's work queue starts with the instances whose remaining iterations bound the solve's latency
+  int* next_back;
+  int next_cap;
+  double hard_ratio;
   double* home;
   int keep_ws;        // retiring instances also carry their backward->forward workspace home (loik_set_keep_workspace)
   int drop_ws;        // the forward sweep drops the consumed workspace lines from L2 (discard_workspace); never with keep_ws

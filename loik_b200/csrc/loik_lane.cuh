@@ -90,6 +90,8 @@ struct LaneP {
   const double* src;   // arena the instances live in when the kernel starts
   const int* list;     // optional: queue entry k is slot list[k] of `src` (the survivors of the previous launch)
   const int* n_list;   // device-resident queue length (with `list`), else `n`
+  const int* n_back;   // optional: that many more entries at the END of `list` (list[cap - 1], list[cap - 2], ...), queued behind the first *n_list
+  int cap;
   int n;
   const int* origin;   // optional: home slot of slot s of `src` (a packed arena); else the home slot is s
   double* home;        // arena the results go to
@@ -834,7 +836,9 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
     }
     __syncwarp();
   }
-  const int limit = P.list ? *P.n_list : P.n;
+  const int nfront = P.list ? *P.n_list : P.n;
+  const int nback = (P.list && P.n_back) ? *P.n_back : 0;
+  const int limit = nfront + nback;
   int home_slot = -1;  // >= 0: these lanes hold an instance
   int status = ST_CONVERGED, it = 0, left = 0;
   double mu = 1.0;
@@ -842,11 +846,13 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
   for (;;) {
     if (home_slot < 0 && !exhausted) {  // pull the next instance from the queue
       __syncwarp(imask);  // the record is free: every lane is done with the previous instance
-      int k = 0;
+      int s = -1, k = 0;
       if (wl == 0) k = atomicAdd(P.queue, 1);
       k = __shfl_sync(imask, k, GPI == 1 ? 8 * g : 0);
-      if (k < limit) {
-        const int s = P.list ? P.list[k] : k;
+      // (an ordered hand-over, LaneP::n_back: the far-from-done instances at the front of the list come first, then the rest from its end)
+      if (k < limit) s = P.list ? P.list[k < nfront ? k : P.cap - 1 - (k - nfront)] : k;
+      else exhausted = true;
+      if (s >= 0) {
         const double* T = P.src + ((size_t)(s >> 5) * M.off.rows) * 32 + (s & 31);
         lane_load(M, D, T, I, wl, nl, GPI > 1);
         __syncwarp(imask);
@@ -866,8 +872,6 @@ __global__ void __launch_bounds__(256) k_iterate_lane(const __grid_constant__ Mo
         mu = I[LS_MU];
         left = P.iters;
         if (status < ST_CONVERGED) home_slot = P.origin ? P.origin[s] : s;
-      } else {
-        exhausted = true;
       }
     }
     __syncwarp();

@@ -94,14 +94,32 @@ LOIK_DEV void migrate_globals(const ModelC& c_model, const double* Ts, double* T
 
 // Survivors of a launch claim the slots of the next one (order inside a warp is preserved, so neighbours stay
 // neighbours and the gather of the next launch's first iteration stays mostly coalesced).
-LOIK_DEV void claim_next(const StateP& S, const bool active, const int slot_now) {
-  const unsigned m = __ballot_sync(0xffffffffu, active);
-  if (!m) return;
+LOIK_DEV void claim_next(const StateP& S, const bool active, const int slot_now, const bool hard = true) {
   const int lane = threadIdx.x & 31;
-  int base = 0;
-  if (lane == 0) base = atomicAdd(S.next_count, __popc(m));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (active) S.next_list[base + __popc(m & ((1u << lane) - 1))] = slot_now;
+  const unsigned m = __ballot_sync(0xffffffffu, active && (hard || !S.next_back));
+  if (m) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(S.next_count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (m >> lane & 1u) S.next_list[base + __popc(m & ((1u << lane) - 1))] = slot_now;
+  }
+  if (S.next_back) {  // (hand-over to the lane-parallel kernel: the rest queues up from the end of the list)
+    const unsigned e = __ballot_sync(0xffffffffu, active && !hard);
+    if (e) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(S.next_back, __popc(e));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (e >> lane & 1u) S.next_list[S.next_cap - 1 - (base + __popc(e & ((1u << lane) - 1)))] = slot_now;
+    }
+  }
+}
+// "far from done": still in the main loop with a residual more than hard_ratio x its tolerance away (rows GR_RES, just written by
+// decide).  After 4 Panda iterations a ratio of 20 flags a third of the running instances and every one that goes on for more
+// than 50 iterations; instances on the infeasibility tail finish within a few iterations
+LOIK_DEV bool looks_hard(const ModelC& c_model, const StateP& S, const double* Td, const int status) {
+  if (status == ST_TAIL) return false;
+  const double* G = glob_blk(const_cast<double*>(Td), c_model.off);
+  return ld(G, GR_RES + 0) > S.hard_ratio * ld(G, GR_RES + 2) || ld(G, GR_RES + 1) > S.hard_ratio * ld(G, GR_RES + 3);
 }
 
 // One launch = up to `iters` ADMM iterations of every active instance (all three sweeps + decisions
@@ -125,7 +143,7 @@ __global__ void __launch_bounds__(kBlock) __maxnreg__(MINB <= 4 ? 255 : (65536 /
   // grid-stride over the slots: late rounds are launched with a small grid (the count lives on the device)
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k - (int)threadIdx.x % 32 < limit; k += stride) {
   const int s = k < limit ? (S.list ? S.list[k] : k) : -1;
-  bool active = false;
+  bool active = false, hard = true;
   if (s >= 0) {
     const bool MIG = S.dst != nullptr;
     double* Td = MIG ? tile_of(S.dst, c_model, k) : tile_ptr(S, c_model, s);
@@ -162,6 +180,7 @@ __global__ void __launch_bounds__(kBlock) __maxnreg__(MINB <= 4 ? 255 : (65536 /
       st_ctl(c_model, Td, status, it);
       st(glob_blk(Td, c_model.off), GR_MU, mu);
       active = status < ST_CONVERGED;
+      if (S.next_back && active) hard = looks_hard(c_model, S, Td, status);
       if (!active && S.home) {  // finished away from home: the results go to the home slot now
         const int* origin = MIG ? S.origin_dst : S.origin_src;
         if (origin) {
@@ -176,7 +195,7 @@ __global__ void __launch_bounds__(kBlock) __maxnreg__(MINB <= 4 ? 255 : (65536 /
     const unsigned m = __ballot_sync(0xffffffffu, active);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(S.n_active, __popc(m));
   }
-  if (S.next_list) claim_next(S, active, S.dst ? k : s);
+  if (S.next_list) claim_next(S, active, S.dst ? k : s, hard);
   }
 }
 
@@ -279,12 +298,13 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
       Ts = Td; migrate = false;
       __syncthreads();  // part[] is rewritten in the next iteration
     }
-    bool active = false;
+    bool active = false, hard = true;
     if (was_active) {
       active = status < ST_CONVERGED;
       if (w == 0) {
         st_ctl(c_model, Td, status, it);
         st(glob_blk(Td, c_model.off), GR_MU, mu);
+        if (S.next_back && active) hard = looks_hard(c_model, S, Td, status);
         // (the last iteration's stores of the other warps are ordered before this by the barrier that ends it)
         if (!active && S.home) {
           const int* origin = MIG ? S.origin_dst : S.origin_src;
@@ -301,7 +321,7 @@ __global__ void __launch_bounds__(32 * NW, NW <= 2 ? 4 : 2)
         const unsigned m = __ballot_sync(0xffffffffu, active);
         if (lane == 0 && m) atomicAdd(S.n_active, __popc(m));
       }
-      if (S.next_list) claim_next(S, active, S.dst ? k : s);
+      if (S.next_list) claim_next(S, active, S.dst ? k : s, hard);
     }
     __syncthreads();  // the next tile's first sweeps must not overtake this tile's result stores of warp 0
   }
@@ -776,7 +796,7 @@ struct loik_solver {
   double* scratch[2] = {nullptr, nullptr};  // packed arenas (allocated at the first solve)
   int* d_origin = nullptr;  // [2][batch] home slot of every packed slot
   int4* d_wide_tab = nullptr;  // step table of the wide sweeps of k_iterate_lane<4> (build_wide_table)
-  int* d_counts = nullptr;  // [0],[1]: list lengths (ping-pong); [2]: n_active
+  int* d_counts = nullptr;  // [0],[1]: list lengths (ping-pong); [2]: n_active; [3]: work-queue head of the lane kernel; [5]: entries queued from the end of its list
   unsigned long long* d_stats = nullptr;
   int* h_counts = nullptr;  // pinned
   unsigned long long* h_stats = nullptr;
@@ -811,7 +831,8 @@ struct loik_solver {
   int lane_after = -1;
   bool lane_ok = false;
   int lane_warps_req = 0;  // warps per CTA (0 = chosen from the record size)
-  int lane_gpi_req = 0;    // groups of 8 lanes per instance: 1, 4, or 0 = default (1)
+  int lane_gpi_req = 0;    // groups of 8 lanes per instance: 1, 4, or 0 = default (4 for branching trees)
+  double hard_ratio = 20.0;  // hand-over to the lane kernel: residual / tolerance beyond which an instance queues up first (0: no ordering)
   bool drop_ws = true;     // the tile kernels drop the consumed backward->forward workspace from L2 instead of writing it back
   int sms = 0, smem_optin = 0, smem_sm = 0;
   int sweeps_in_solve = 0;
@@ -900,11 +921,11 @@ static bool lane_geometry(const loik_solver* h, LaneGeom& G) {
 // `origin`: home slot of every slot of a packed arena.  Runs every instance to the end of its solve (or `iters`
 // iterations each in fixed mode) and sends the results to the home arena.
 static int launch_lane(loik_solver* h, cudaStream_t st, const double* src, const int* list, const int* n_list, const int* origin,
-                       int fixed, int iters) {
+                       int fixed, int iters, const int* n_back = nullptr) {
   LaneGeom G;
   if (!lane_geometry(h, G)) return fail(LOIK_ERR_STATE, "lane-parallel kernel: the instance record does not fit shared memory");
   LaneP P{};
-  P.src = src; P.list = list; P.n_list = n_list; P.n = h->batch; P.origin = origin; P.home = h->arena;
+  P.src = src; P.list = list; P.n_list = n_list; P.n_back = n_back; P.cap = h->batch; P.n = h->batch; P.origin = origin; P.home = h->arena;
   P.queue = h->d_counts + 3; P.iters = iters; P.fixed = fixed; P.keep_ws = h->S.keep_ws; P.tab = h->d_wide_tab;
   CK(cudaMemsetAsync(h->d_counts + 3, 0, sizeof(int), st));
   if (G.gpi == 1) k_iterate_lane<1><<<G.grid, 32 * G.warps, G.smem, st>>>(h->mc, P);
@@ -1222,8 +1243,8 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
   CKA(cudaMemset(h->arena, 0, arena_doubles * sizeof(double)));
   if (upload_wide_table(h) != LOIK_OK) { loik_destroy(h); return LOIK_ERR_CUDA; }
   CKA(cudaMalloc(&h->d_lists, 2 * (size_t)batch * sizeof(int)));
-  CKA(cudaMalloc(&h->d_counts, 4 * sizeof(int)));
-  CKA(cudaMemset(h->d_counts, 0, 4 * sizeof(int)));
+  CKA(cudaMalloc(&h->d_counts, 8 * sizeof(int)));
+  CKA(cudaMemset(h->d_counts, 0, 8 * sizeof(int)));
   CKA(cudaMalloc(&h->d_stats, 4 * sizeof(unsigned long long)));
   {  // row maps of the gettable fields: field -> absolute rows of the tile record, in output order
     std::vector<int> all;
@@ -1582,12 +1603,16 @@ static int run_schedule(loik_solver* h, cudaStream_t st0, int budget) {
   int done = 0;
   int li = 0;  // list / count that the NEXT launch reads
   const int dense = std::min(pre, dense_sweeps);
+  // the tile launch right before the lane-parallel kernel orders its survivors: far-from-done first (StateP::next_back)
+  const bool hand_over = lane && pre < budget && h->hard_ratio > 0.0;
+  bool two_ended = false;
   StateP X = h->S;  // where the instances of the next launch live: the home arena first
   X.list = nullptr; X.n_list = nullptr;
   if (dense > 0) {
     CK(cudaMemsetAsync(h->d_counts + li, 0, sizeof(int), st));
     StateP P = h->S;
     P.next_list = h->d_lists + (size_t)li * B; P.next_count = h->d_counts + li;
+    if (hand_over && dense == pre) { CK(cudaMemsetAsync(h->d_counts + 5, 0, sizeof(int), st)); P.next_back = h->d_counts + 5; P.next_cap = B; P.hard_ratio = h->hard_ratio; two_ended = true; }
     launch_iterate(h, st, P, dense, 0, 0, h->seg_after <= 0);
     h->sweeps += dense; done += dense;
     X.list = P.next_list; X.n_list = P.next_count;
@@ -1615,6 +1640,7 @@ static int run_schedule(loik_solver* h, cudaStream_t st0, int budget) {
       nlist = h->d_lists + (size_t)(1 - li) * B; ncount = h->d_counts + (1 - li);
     }
     P.next_list = nlist; P.next_count = ncount;
+    if (hand_over && done + c == pre && nlist) { CK(cudaMemsetAsync(h->d_counts + 5, 0, sizeof(int), st)); P.next_back = h->d_counts + 5; P.next_cap = B; P.hard_ratio = h->hard_ratio; two_ended = true; }
     launch_iterate(h, st, P, c, 0, done >= h->small_after ? h->small_grid : 0, done >= h->seg_after);
     h->sweeps += c; done += c;
     X = h->S; X.arena = h->scratch[y]; X.list = nlist; X.n_list = ncount;
@@ -1622,7 +1648,7 @@ static int run_schedule(loik_solver* h, cudaStream_t st0, int budget) {
     if (++reps == h->sched_reps) { reps = 0; if (chunk < 64) chunk = std::max(chunk + 1, (int)(chunk * h->sched_growth)); }
   }
   if (lane && done < budget) {  // everything still active runs to the end of its solve in the lane-parallel kernel
-    rc = launch_lane(h, st, X.arena, X.list, X.n_list, cur < 0 ? nullptr : h->d_origin + (size_t)cur * B, 0, 0);
+    rc = launch_lane(h, st, X.arena, X.list, X.n_list, cur < 0 ? nullptr : h->d_origin + (size_t)cur * B, 0, 0, two_ended ? h->d_counts + 5 : nullptr);
     if (rc) return rc;
     h->sweeps += budget - done;
   }
@@ -2005,6 +2031,7 @@ int loik_get_schedule(loik_solver* h, loik_schedule* out) {
   out->hi_priority_after = h->hi_after; out->seg_after = h->seg_after; out->seg_warps = h->seg_warps;
   out->lane_after = h->lane_after; out->use_graph = h->use_graph ? 1 : 0;
   out->small_after = h->small_after; out->small_grid = h->small_grid; out->drop_workspace = h->drop_ws ? 1 : 0;
+  out->lane_hard_first_ratio = h->hard_ratio;
   LaneGeom G;
   const bool ok = h->lane_ok && lane_geometry(h, G);
   out->lane_warps_per_cta = h->lane_warps_req; out->lane_groups_per_instance = h->lane_gpi_req; out->lane_groups_chosen = G.gpi;
@@ -2015,12 +2042,13 @@ int loik_get_schedule(loik_solver* h, loik_schedule* out) {
 int loik_set_schedule(loik_solver* h, const loik_schedule* sc) {
   if (!h || !sc) return fail(LOIK_ERR_INVALID, "loik_set_schedule: null argument");
   if (sc->dense_sweeps < 0 || sc->repack_reps < 1 || !(sc->repack_growth >= 1.0) || sc->seg_warps < 0 || sc->seg_warps > 4 || sc->small_grid < 1 ||
-      sc->lane_warps_per_cta < 0 || sc->lane_warps_per_cta > 8 || (sc->lane_groups_per_instance != 0 && sc->lane_groups_per_instance != 1 && sc->lane_groups_per_instance != 4))
+      sc->lane_warps_per_cta < 0 || sc->lane_warps_per_cta > 8 || !(sc->lane_hard_first_ratio >= 0.0) || (sc->lane_groups_per_instance != 0 && sc->lane_groups_per_instance != 1 && sc->lane_groups_per_instance != 4))
     return fail(LOIK_ERR_INVALID, "loik_set_schedule: dense_sweeps >= 0, repack_reps >= 1, repack_growth >= 1, 0 <= seg_warps <= 4, small_grid >= 1, 0 <= lane_warps_per_cta <= 8, lane_groups_per_instance in {0, 1, 4}");
   h->dense_sweeps = sc->dense_sweeps; h->sched_reps = sc->repack_reps; h->sched_growth = sc->repack_growth;
   h->hi_after = sc->hi_priority_after; h->seg_after = sc->seg_after;
   h->lane_after = sc->lane_after; h->use_graph = sc->use_graph != 0; h->lane_warps_req = sc->lane_warps_per_cta; h->lane_gpi_req = sc->lane_groups_per_instance;
   h->small_after = sc->small_after; h->small_grid = sc->small_grid; h->drop_ws = sc->drop_workspace != 0;
+  h->hard_ratio = sc->lane_hard_first_ratio;
   if (sc->seg_warps != h->seg_warps) {
     h->seg_warps = sc->seg_warps; assign_segments(h->mc, h->seg_warps);
     int rc = upload_wide_table(h);

@@ -66,7 +66,7 @@ class _Schedule(C.Structure):
     _fields_ = [("dense_sweeps", C.c_int32), ("repack_reps", C.c_int32), ("repack_growth", C.c_double),
                 ("hi_priority_after", C.c_int32), ("seg_after", C.c_int32), ("seg_warps", C.c_int32),
                 ("lane_after", C.c_int32), ("use_graph", C.c_int32), ("small_after", C.c_int32), ("small_grid", C.c_int32),
-                ("lane_warps_per_cta", C.c_int32), ("lane_groups_per_instance", C.c_int32), ("drop_workspace", C.c_int32),
+                ("lane_warps_per_cta", C.c_int32), ("lane_groups_per_instance", C.c_int32), ("drop_workspace", C.c_int32), ("lane_hard_first_ratio", C.c_double),
                 ("lane_available", C.c_int32), ("lane_warps_chosen", C.c_int32), ("lane_groups_chosen", C.c_int32), ("lane_ctas", C.c_int32),
                 ("lane_smem_bytes", C.c_int32)]
 
