@@ -15,7 +15,8 @@ python scripts/single_instance.py > gpurun_out/single_instance_${TAG}.json 2>/de
 echo "== schedule sweep (switch point of the lane-parallel kernel)"
 LANE_AFTERS=-1,10,32 DEPTHS=1,4,10,32 python scripts/lane_perf.py panda 2>&1 | tail -3 > gpurun_out/lane_sweep_${TAG}.txt
 LANE_AFTERS=-1,32 DEPTHS=1,4,16 python scripts/lane_perf.py ur10 2>&1 | tail -2 >> gpurun_out/lane_sweep_${TAG}.txt
-LANE_AFTERS=-1,16 DEPTHS=1,4,16 python scripts/lane_perf.py talos 2>&1 | tail -2 >> gpurun_out/lane_sweep_${TAG}.txt
+LANE_AFTERS=-1,8,32 DEPTHS=1,4,16 python scripts/lane_perf.py talos 2>&1 | tail -3 >> gpurun_out/lane_sweep_${TAG}.txt
+python scripts/lane_latency.py panda,ur10,talos 2>&1 | tail -9 > gpurun_out/lane_latency_${TAG}.txt
 cat gpurun_out/lane_sweep_${TAG}.txt
 echo "== ncu launch list"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_${TAG}.csv \
@@ -29,4 +30,6 @@ for r in panda ur10 talos; do
 done
 ncu --set full --clock-control none --import-source on -k regex:k_iterate_lane -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_lane_panda \
     python scripts/lane_prof.py panda 0 4 > gpurun_out/prof_${TAG}_lane_panda.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_iterate_lane -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_lane_talos \
+    python scripts/lane_prof.py talos 0 4 > gpurun_out/prof_${TAG}_lane_talos.log 2>&1
 ls -la gpurun_out | tail -24

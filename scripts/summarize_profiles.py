@@ -84,6 +84,7 @@ if __name__ == "__main__":
     launch_list()
     traffic = {}
     full("lane_panda")
+    full("lane_talos")
     for nm in ("panda", "talos", "ur10"):
         o = full(nm)
         if o:
