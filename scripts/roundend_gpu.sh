@@ -32,4 +32,7 @@ ncu --set full --clock-control none --import-source on -k regex:k_iterate_lane -
     python scripts/lane_prof.py panda 0 4 > gpurun_out/prof_${TAG}_lane_panda.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_iterate_lane -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_lane_talos \
     python scripts/lane_prof.py talos 0 4 > gpurun_out/prof_${TAG}_lane_talos.log 2>&1
+# the summaries are made here, next to the captures (five .ncu-rep files exceed what gpurun brings back); the two Panda captures travel too
+PROFILES_OUT=gpurun_out/profiles_out python scripts/summarize_profiles.py ${TAG} > gpurun_out/summarize_${TAG}.log 2>&1
+rm -f gpurun_out/prof_${TAG}_ur10.ncu-rep gpurun_out/prof_${TAG}_talos.ncu-rep gpurun_out/prof_${TAG}_lane_talos.ncu-rep
 ls -la gpurun_out | tail -24

@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "profiles")
+OUT = os.environ.get("PROFILES_OUT", os.path.join(ROOT, "profiles"))  # (on the GPU box: gpurun_out/profiles_out, the only directory that travels back)
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r2"
 
 KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
