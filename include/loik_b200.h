@@ -242,12 +242,14 @@ LOIK_API int loik_solve_init(loik_solver* h, const double* q, const double* H_re
 /* problem_.UpdateReferences(H_refs, v_refs)  (ik-id-description-optimized.hpp:103-121): per-joint references,
  * H_refs [njoints][36], v_refs [njoints][6], HOST pointers; call after loik_solve_init. */
 LOIK_API int loik_update_references(loik_solver* h, const double* H_refs, const double* v_refs, void* stream);
-/* The same with a reference velocity of its own for every instance (a batch of independent problems: e.g. the previous
- * solution of each trajectory as v_ref): H_refs [njoints][36] HOST (per joint, shared by the batch), v_refs
- * [batch][njoints][6] at `loc`.  Stays in force until the next loik_solve_init.  Costs 6 more rows per joint in HBM
- * (H_ref v_ref, read twice per iteration): 8 * (155 n + 42 nc) algorithmic bytes per instance and iteration; solves with
- * per-instance references run on the tile kernels only (the lane-parallel kernel keeps the references in per-CTA constants). */
-LOIK_API int loik_update_references_batch(loik_solver* h, const double* H_refs, const double* v_refs, int32_t loc, void* stream);
+/* The same with references of its own for every instance (a batch of independent problems: e.g. the previous solution of each
+ * trajectory as v_ref): v_refs [batch][njoints][6] at `loc`; H_refs [njoints][36] HOST (per joint, shared by the batch), or, if
+ * H_per_instance, [batch][njoints][36] at `loc` (symmetric; checked when the buffer is on the host).  Stays in force until the
+ * next loik_solve_init.  Costs 6 (+21 with per-instance weights) more rows per joint in HBM, read twice per iteration:
+ * 8 * (155 n + 42 nc) resp. 8 * (197 n + 42 nc) algorithmic bytes per instance and iteration; such solves run on the general
+ * instantiations of the tile kernels (the lane-parallel kernel keeps the references in per-CTA constants). */
+LOIK_API int loik_update_references_batch(loik_solver* h, const double* H_refs, int32_t H_per_instance, const double* v_refs, int32_t loc,
+                                          void* stream);
 
 /* ---- solving --------------------------------------------------------------------------------- */
 /* Solve()  (hpp:368-455): ResetRecursion + ResetSolver + main loop, every instance to its own

@@ -119,11 +119,11 @@ class FirstOrderLoikOptimized {
   void CheckFeasibility() { step(LOIK_STEP_CHECK_FEASIBILITY); }
   void UpdateMu() { step(LOIK_STEP_UPDATE_MU); }
   // problem_.UpdateReferences(H_refs, v_refs)  (ik-id-description-optimized.hpp:103-121): [njoints][36], [njoints][6];
-  // v_refs of size [batch][njoints][6] gives every instance its own reference velocities
+  // v_refs of size [batch][njoints][6] gives every instance its own reference velocities, H_refs of size [batch][njoints][36] its own weights
   void UpdateReferences(const std::vector<double>& H_refs, const std::vector<double>& v_refs) {
     const size_t nj = (size_t)model_.njoints;
-    if (H_refs.size() == nj * 36 && batch_ > 1 && v_refs.size() == (size_t)batch_ * nj * 6) {
-      check(loik_update_references_batch(h_, H_refs.data(), v_refs.data(), LOIK_HOST, stream_));
+    if (batch_ > 1 && v_refs.size() == (size_t)batch_ * nj * 6 && (H_refs.size() == nj * 36 || H_refs.size() == (size_t)batch_ * nj * 36)) {
+      check(loik_update_references_batch(h_, H_refs.data(), H_refs.size() != nj * 36, v_refs.data(), LOIK_HOST, stream_));
       return;
     }
     if (H_refs.size() != nj * 36 || v_refs.size() != nj * 6)

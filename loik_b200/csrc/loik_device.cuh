@@ -72,7 +72,8 @@ enum : int {  // rows of a joint block
   JR_JQ = 22, JR_LB = 24, JR_UB = 25, JR_Q = 26,                                  // per-instance problem data (5 rows)
   JR_H = 27, JR_P = 48, JR_UD = 54, JR_DINV = 60, JR_R = 61,                      // backward -> forward workspace (35 rows)
   JR_HV = 62,                                                                      // H_ref v_ref of this instance (only touched with per-instance references, ModelC::vref_per)
-  JR_ROWS = 68
+  JR_HREF = 68,                                                                    // H_ref of this instance, 21 scalars like H (only touched with ModelC::href_per)
+  JR_ROWS = 89
 };
 // rows of a task block: state y, Aty | per-instance problem data b, A^T b | per-instance task matrix A (row-major 6x6)
 // and A^T A (21 scalars: LL sym, LA, AA sym) when the batch does not share A (ModelC::a_per)
@@ -114,7 +115,7 @@ struct ModelC {
   int nmd, nv, nq, href_uniform;   // number of multi-DoF joints; model.nv, model.nq; every joint shares H_ref / v_ref (UpdateReference)
   SegC seg[kMaxSeg];
   int nsb, nsf;                    // steps of the wide sweeps of k_iterate_lane<4> (backward / forward order; build_wide_table)
-  int vref_per, pad1;              // v_ref differs per instance (loik_update_references_batch): H_ref v_ref in rows JR_HV, not HrefC::Hv
+  int vref_per, href_per;          // v_ref / also H_ref differ per instance (loik_update_references_batch): H_ref v_ref in rows JR_HV, not HrefC::Hv
   int nspan, a_per;                // a_per: A_k (and A_k^T A_k) differ per instance: rows TR_A / TR_ATA of the task blocks, not TaskC
   SpanC span[kMaxSpan];
   Offs off;
@@ -189,6 +190,22 @@ LOIK_DEV double task_A(const ModelC& M, const TaskC& K, const double* Pk, int i)
 // (1.2 % of a dense Panda launch when it was a run-time test).  Plain load: a migrating launch writes these rows.
 template <bool VR>
 LOIK_DEV double hv_of(const ModelC& M, const HrefC& Hr, const double* P, int c) { return (VR && M.vref_per) ? ld(P, JR_HV + c) : Hr.Hv[c]; }
+// per-instance weights (ModelC::href_per): rows JR_HREF of joint block P replace the reference table's blocks
+LOIK_DEV void href_rows(const double* P, double (&A)[6], double (&B)[9], double (&D)[6]) {
+#pragma unroll
+  for (int c = 0; c < 6; ++c) { A[c] = ld(P, JR_HREF + c); D[c] = ld(P, JR_HREF + 15 + c); }
+#pragma unroll
+  for (int c = 0; c < 9; ++c) B[c] = ld(P, JR_HREF + 6 + c);
+}
+LOIK_DEV void href_times(const double* P, const double (&v)[6], double (&Hrv)[6]) {
+  double A[6], B[9], D[6];
+  href_rows(P, A, B, D);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    Hrv[a] = A[si(a, 0)] * v[0] + A[si(a, 1)] * v[1] + A[si(a, 2)] * v[2] + B[3 * a] * v[3] + B[3 * a + 1] * v[4] + B[3 * a + 2] * v[5];
+    Hrv[3 + a] = B[a] * v[0] + B[3 + a] * v[1] + B[6 + a] * v[2] + D[si(a, 0)] * v[3] + D[si(a, 1)] * v[4] + D[si(a, 2)] * v[5];
+  }
+}
 LOIK_DEV double* pend_blk(double* T, const Offs& O, int k) { return T + (size_t)(O.pend0 + PR_ROWS * k) * 32; }
 LOIK_DEV double* glob_blk(double* T, const Offs& O) { return T + (size_t)O.glob * 32; }
 // this lane's record of the debug arena (instances never migrate in debug mode: slot = home slot)
@@ -521,6 +538,7 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, const double* Ts, double* Td
     for (int c = 0; c < 6; ++c) { A[c] = Hr.A[c]; D[c] = Hr.D[c]; }
 #pragma unroll
     for (int c = 0; c < 9; ++c) B[c] = Hr.B[c];
+    if (VR && c_model.href_per) href_rows(Ps, A, B, D);
     A[0] += rho; A[3] += rho; A[5] += rho; D[0] += rho; D[3] += rho; D[5] += rho;
     if (J.task >= 0) {  // H_c += mu_eq AtA; p_c += Aty - mu_eq Atb (:327-330)
       const TaskC& K = c_model.t[J.task];
@@ -577,7 +595,7 @@ LOIK_DEV void sweep_backward(const ModelC& c_model, const double* Ts, double* Td
 #pragma unroll
       for (int c = 0; c < 3; ++c) st(Pj, JR_LB + c, cst[c]);
       if (VR && c_model.vref_per)
-        for (int c = 0; c < 6; ++c) st(Pj, JR_HV + c, ldc(Ps, JR_HV + c));
+        for (int c = 0; c < (c_model.href_per ? JR_ROWS - JR_HV : 6); ++c) st(Pj, JR_HV + c, ldc(Ps, JR_HV + c));  // (H_ref v_ref, and H_ref behind it)
       if (J.task >= 0) {
         double* Pk = task_blk(Td, O, J.task);
 #pragma unroll
@@ -826,6 +844,7 @@ LOIK_DEV void sweep_residual(const ModelC& c_model, const double* Ts, double* Td
       Hrv[a] = Hr.A[si(a, 0)] * v[0] + Hr.A[si(a, 1)] * v[1] + Hr.A[si(a, 2)] * v[2] + Hr.B[3 * a] * v[3] + Hr.B[3 * a + 1] * v[4] + Hr.B[3 * a + 2] * v[5];
       Hrv[3 + a] = Hr.B[a] * v[0] + Hr.B[3 + a] * v[1] + Hr.B[6 + a] * v[2] + Hr.D[si(a, 0)] * v[3] + Hr.D[si(a, 1)] * v[4] + Hr.D[si(a, 2)] * v[5];
     }
+    if (VR && c_model.href_per) href_times(Pj, v, Hrv);
     {
       double dF[6];
 #pragma unroll
@@ -950,7 +969,7 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
       for (int c = TR_B; c < (c_model.a_per ? TR_ROWS : TR_A); ++c) st(Pk, c, ldc(Pks, c));
     }
     if (c_model.vref_per)
-      for (int c = 0; c < 6; ++c) st(Pj, JR_HV + c, ldc(Pjs, JR_HV + c));
+      for (int c = 0; c < (c_model.href_per ? JR_ROWS - JR_HV : 6); ++c) st(Pj, JR_HV + c, ldc(Pjs, JR_HV + c));
   }
 #pragma unroll
   for (int c = 0; c < 6; ++c) { p[c] = -rho * ld(Pjs, JR_V + c) - hv_of<true>(c_model, Hr, Pjs, c); A[c] = Hr.A[c]; D[c] = Hr.D[c]; }
@@ -958,6 +977,7 @@ LOIK_DEV_CALL void md_backward(const ModelC& c_model, const double* Ts, double* 
   for (int c = 0; c < K; ++c) { w[c] = ld(Pfs, FR_W + c); z[c] = ld(Pfs, FR_Z + c); }
 #pragma unroll
   for (int c = 0; c < 9; ++c) B[c] = Hr.B[c];
+  if (c_model.href_per) href_rows(Pjs, A, B, D);
   A[0] += rho; A[3] += rho; A[5] += rho; D[0] += rho; D[3] += rho; D[5] += rho;
   if (J.task >= 0) {
     const TaskC& Kt = c_model.t[J.task];
@@ -1212,6 +1232,7 @@ LOIK_DEV_CALL void md_residual(const ModelC& c_model, const double* Ts, double* 
     Hrv[a] = Hr.A[si(a, 0)] * v[0] + Hr.A[si(a, 1)] * v[1] + Hr.A[si(a, 2)] * v[2] + Hr.B[3 * a] * v[3] + Hr.B[3 * a + 1] * v[4] + Hr.B[3 * a + 2] * v[5];
     Hrv[3 + a] = Hr.B[a] * v[0] + Hr.B[3 + a] * v[1] + Hr.B[6 + a] * v[2] + Hr.D[si(a, 0)] * v[3] + Hr.D[si(a, 1)] * v[4] + Hr.D[si(a, 2)] * v[5];
   }
+  if (c_model.href_per) href_times(Pj, v, Hrv);
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     F[c] += -f[c];
@@ -1393,6 +1414,7 @@ LOIK_DEV void fine_fwdpass1(const ModelC& M, double* __restrict__ T, const doubl
     double A[6], B[9], D[6], p[6];
     for (int c = 0; c < 6; ++c) { p[c] = -M.rho * ld(Pj, JR_V + c) - hv_of<true>(M, Hr, Pj, c); A[c] = Hr.A[c]; D[c] = Hr.D[c]; }
     for (int c = 0; c < 9; ++c) B[c] = Hr.B[c];
+    if (M.href_per) href_rows(Pj, A, B, D);
     A[0] += M.rho; A[3] += M.rho; A[5] += M.rho; D[0] += M.rho; D[3] += M.rho; D[5] += M.rho;
     if (J.task >= 0) {
       const TaskC& K = M.t[J.task];
@@ -1438,6 +1460,7 @@ LOIK_DEV void fine_fwdpass2(const ModelC& M, double* __restrict__ T) {
       Hrv[a] = Hr.A[si(a, 0)] * v[0] + Hr.A[si(a, 1)] * v[1] + Hr.A[si(a, 2)] * v[2] + Hr.B[3 * a] * v[3] + Hr.B[3 * a + 1] * v[4] + Hr.B[3 * a + 2] * v[5];
       Hrv[3 + a] = Hr.B[a] * v[0] + Hr.B[3 + a] * v[1] + Hr.B[6 + a] * v[2] + Hr.D[si(a, 0)] * v[3] + Hr.D[si(a, 1)] * v[4] + Hr.D[si(a, 2)] * v[5];
     }
+    if (M.href_per) href_times(Pj, v, Hrv);
     for (int c = 0; c < 6; ++c) {
       dvis = amax(dvis, v[c] - ld(Pj, JR_V + c));
       dfis = amax(dfis, f[c] - ld(Pj, JR_F + c));

@@ -691,8 +691,9 @@ __global__ void k_set_bounds(const __grid_constant__ ModelC c_model, const State
 }
 
 // problem_.UpdateReferences with a v_ref of its own for every instance (v_refs [n][njoints][6]): Hv_i = H_ref_i v_ref_i
-// (ik-id-description-optimized.hpp:113) into rows JR_HV of the joint blocks; H_ref_i from the reference table
-__global__ void k_set_vref(const __grid_constant__ ModelC c_model, const StateP S, const double* __restrict__ v_refs) {
+// (ik-id-description-optimized.hpp:113) into rows JR_HV of the joint blocks; H_ref_i from the reference table, or (H_refs)
+// this instance's own weights
+__global__ void k_set_vref(const __grid_constant__ ModelC c_model, const StateP S, const double* __restrict__ v_refs, const double* __restrict__ H_refs) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S.n) return;
   double* T = tile_ptr(S, c_model, s);
@@ -700,12 +701,25 @@ __global__ void k_set_vref(const __grid_constant__ ModelC c_model, const StateP 
   for (int i = 1; i <= nb; ++i) {
     const HrefC& Hr = c_model.href[c_model.j[i].href];
     const double* vr = v_refs + ((size_t)s * (nb + 1) + i) * 6;
-    double v[6];
+    double v[6], A[6], B[9], D[6];
     for (int c = 0; c < 6; ++c) v[c] = vr[c];
     double* Pj = joint_blk(T, c_model.off, i - 1);
+    if (H_refs) {  // this instance's own weights [n][njoints][36], symmetric: the LL, LA, AA blocks go to rows JR_HREF
+      const double* H = H_refs + ((size_t)s * (nb + 1) + i) * 36;
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          if (a <= b) { A[si(a, b)] = H[6 * a + b]; D[si(a, b)] = H[6 * (3 + a) + 3 + b]; }
+          B[3 * a + b] = H[6 * a + 3 + b];
+        }
+      for (int c = 0; c < 6; ++c) { st(Pj, JR_HREF + c, A[c]); st(Pj, JR_HREF + 15 + c, D[c]); }
+      for (int c = 0; c < 9; ++c) st(Pj, JR_HREF + 6 + c, B[c]);
+    } else {
+      for (int c = 0; c < 6; ++c) { A[c] = Hr.A[c]; D[c] = Hr.D[c]; }
+      for (int c = 0; c < 9; ++c) B[c] = Hr.B[c];
+    }
     for (int a = 0; a < 3; ++a) {
-      st(Pj, JR_HV + a, Hr.A[si(a, 0)] * v[0] + Hr.A[si(a, 1)] * v[1] + Hr.A[si(a, 2)] * v[2] + Hr.B[3 * a] * v[3] + Hr.B[3 * a + 1] * v[4] + Hr.B[3 * a + 2] * v[5]);
-      st(Pj, JR_HV + 3 + a, Hr.B[a] * v[0] + Hr.B[3 + a] * v[1] + Hr.B[6 + a] * v[2] + Hr.D[si(a, 0)] * v[3] + Hr.D[si(a, 1)] * v[4] + Hr.D[si(a, 2)] * v[5]);
+      st(Pj, JR_HV + a, A[si(a, 0)] * v[0] + A[si(a, 1)] * v[1] + A[si(a, 2)] * v[2] + B[3 * a] * v[3] + B[3 * a + 1] * v[4] + B[3 * a + 2] * v[5]);
+      st(Pj, JR_HV + 3 + a, B[a] * v[0] + B[3 + a] * v[1] + B[6 + a] * v[2] + D[si(a, 0)] * v[3] + D[si(a, 1)] * v[4] + D[si(a, 2)] * v[5]);
     }
   }
 }
@@ -1426,6 +1440,7 @@ static int set_problem_consts(loik_solver* h, const double* H_ref, const double*
   M.bounds_per_instance = bounds_shared ? 0 : 1;
   M.href_uniform = 1;
   M.vref_per = 0;
+  M.href_per = 0;
   M.a_per = (A && n_ids <= kMaxTasks) ? 0 : 1;  // (more tasks than TaskC slots: the matrices live in the task rows too, k_set_b)
   sym_blocks(H_ref, M.href[0].A, M.href[0].B, M.href[0].D);  // UpdateReference: one reference broadcast to every joint
   for (int c = 0; c < 6; ++c) M.href[0].Hv[c] = Hv[c];
@@ -1536,22 +1551,30 @@ int loik_update_references(loik_solver* h, const double* H_refs, const double* v
   return LOIK_OK;
 }
 
-int loik_update_references_batch(loik_solver* h, const double* H_refs, const double* v_refs, int32_t loc, void* stream) {
+int loik_update_references_batch(loik_solver* h, const double* H_refs, int32_t H_per_instance, const double* v_refs, int32_t loc, void* stream) {
   if (!h || !H_refs || !v_refs) return fail(LOIK_ERR_INVALID, "loik_update_references_batch: null argument");
   if (!h->problem_set) return fail(LOIK_ERR_STATE, "loik_update_references_batch: call loik_solve_init first");
-  // the weights go through the shared path (reference table, symmetry check) with v_ref = 0: |Hv|inf does not grow there
-  std::vector<double> zero(6 * (size_t)h->nj, 0.0);
-  int rc = loik_update_references(h, H_refs, zero.data(), stream);
-  if (rc) return rc;
+  int rc = LOIK_OK;
+  if (!H_per_instance) {
+    // the weights go through the shared path (reference table, symmetry check) with v_ref = 0: |Hv|inf does not grow there
+    std::vector<double> zero(6 * (size_t)h->nj, 0.0);
+    rc = loik_update_references(h, H_refs, zero.data(), stream);
+    if (rc) return rc;
+  } else if (loc != LOIK_DEVICE) {
+    for (size_t i = 0; i < (size_t)h->batch * h->nj; ++i)
+      if (!is_symmetric(H_refs + 36 * i)) return fail(LOIK_ERR_UNSUPPORTED, "loik_update_references_batch: every H_ref must be symmetric");
+  }
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
-  const size_t bytes = (size_t)h->batch * h->nj * 6 * sizeof(double);
-  if (loc != LOIK_DEVICE) { rc = ensure_stage(h, bytes, loc == LOIK_HOST); if (rc) return rc; }
-  const void* dv = nullptr;
-  rc = to_device(h, v_refs, bytes, loc, 0, st, &dv);
+  const size_t v_bytes = (size_t)h->batch * h->nj * 6 * sizeof(double), H_bytes = H_per_instance ? 6 * v_bytes : 0;
+  if (loc != LOIK_DEVICE) { rc = ensure_stage(h, v_bytes + H_bytes, loc == LOIK_HOST); if (rc) return rc; }
+  const void *dv = nullptr, *dH = nullptr;
+  rc = to_device(h, v_refs, v_bytes, loc, 0, st, &dv);
   if (rc) return rc;
+  if (H_per_instance) { rc = to_device(h, H_refs, H_bytes, loc, v_bytes, st, &dH); if (rc) return rc; }
   h->mc.vref_per = 1;
-  k_set_vref<<<grid_for(h->batch, 128), 128, 0, st>>>(h->mc, h->S, (const double*)dv);
+  h->mc.href_per = H_per_instance ? 1 : 0;
+  k_set_vref<<<grid_for(h->batch, 128), 128, 0, st>>>(h->mc, h->S, (const double*)dv, (const double*)dH);
   h->launches++;
   CK(cudaGetLastError());
   if (loc == LOIK_HOST) CK(cudaStreamSynchronize(st));  // the staging buffer is reused by the next call

@@ -91,7 +91,7 @@ def load_library(path: str | None = None):
     lib.loik_solve_init.argtypes = [vp] + prob
     lib.loik_solve_full.argtypes = [vp] + prob
     lib.loik_update_references.argtypes = [vp, dp, dp, vp]
-    lib.loik_update_references_batch.argtypes = [vp, dp, vp, i32, vp]
+    lib.loik_update_references_batch.argtypes = [vp, vp, i32, vp, i32, vp]
     lib.loik_solve.argtypes = [vp, vp]
     lib.loik_solve_task.argtypes = [vp, dp, i32, dp, i32, dp, i32, i32, vp]
     lib.loik_iterate_fixed.argtypes = [vp, i32, i32, vp]
@@ -368,13 +368,16 @@ class FirstOrderLoikOptimized:
 
     def UpdateReferences(self, H_refs, v_refs):
         """problem_.UpdateReferences(H_refs, v_refs) (ik-id-description-optimized.hpp:103-121).  ``v_refs`` of shape
-        ``[batch][njoints][6]`` (numpy or a CUDA tensor) gives every instance its own reference velocities."""
+        ``[batch][njoints][6]`` (numpy or a CUDA tensor) gives every instance its own reference velocities, ``H_refs`` of shape
+        ``[batch][njoints][6][6]`` its own weights as well."""
         if getattr(v_refs, "ndim", 0) == 3:
-            Hb = _Buf(np.asarray(H_refs, np.float64).reshape(-1))
+            h_per = int(getattr(H_refs, "ndim", 0) == 4)  # [batch, njoints, 6, 6]: every instance its own weights
+            Hb = _Buf(H_refs) if h_per else _Buf(np.asarray(H_refs, np.float64).reshape(-1))
             vb = _Buf(v_refs)
-            if Hb.shape[0] != 36 * self.model.nj or tuple(vb.shape) != (self.batch, self.model.nj, 6):
+            ok_H = tuple(Hb.shape) == (self.batch, self.model.nj, 6, 6) and Hb.loc == vb.loc if h_per else Hb.shape[0] == 36 * self.model.nj
+            if not ok_H or tuple(vb.shape) != (self.batch, self.model.nj, 6):
                 raise RuntimeError("[IkProblemFormulation::UpdateReferences]: input arguments 'H_refs', 'v_refs' have wrong size!!")
-            self._check(self._lib.loik_update_references_batch(self._h, Hb.ptr, vb.ptr, vb.loc, _current_stream()))
+            self._check(self._lib.loik_update_references_batch(self._h, Hb.ptr, h_per, vb.ptr, vb.loc, _current_stream()))
             return
         Hb, vb = _Buf(np.asarray(H_refs, np.float64).reshape(-1)), _Buf(np.asarray(v_refs, np.float64).reshape(-1))
         if Hb.shape[0] != 36 * self.model.nj or vb.shape[0] != 6 * self.model.nj:

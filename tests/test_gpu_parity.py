@@ -513,8 +513,9 @@ def test_update_references_per_joint():
     G.close()
 
 
-@pytest.mark.parametrize("name,B,kw", [("panda9", 160, {}), ("talos", 96, {}), ("talos_ff", 64, {}), ("panda", 2048, dict(max_iter=200))])
-def test_update_references_per_instance(name, B, kw):
+@pytest.mark.parametrize("name,B,kw,h_per", [("panda9", 160, {}, False), ("talos", 96, {}, False), ("talos_ff", 64, {}, False), ("panda", 2048, dict(max_iter=200), False),
+                                             ("panda9", 160, {}, True), ("talos", 96, {}, True), ("talos_ff", 64, {}, True), ("panda", 2048, dict(max_iter=200), True)])
+def test_update_references_per_instance(name, B, kw, h_per):
     """loik_update_references_batch: per-joint weights shared by the batch, a reference velocity of its own for every instance
     and joint (UpdateReferences applied to each instance of the batch, ik-id-description-optimized.hpp:103-121), through
     dense sweeps, migrating re-pack launches and (Talos) the segment kernel; fused steps at 1e-10 and full solves against
@@ -528,6 +529,10 @@ def test_update_references_per_instance(name, B, kw):
         M = rng.normal(size=(6, 6))
         H_refs[i] = np.eye(6) * rng.uniform(0.5, 2.0) + 0.05 * (M + M.T)
     v_refs = 0.05 * rng.normal(size=(B, model.nj, 6))
+    if h_per:  # every instance its own symmetric weights too
+        W = rng.normal(size=(B, model.nj, 6, 6))
+        H_refs = H_refs[None] * rng.uniform(0.7, 1.4, size=(B, model.nj, 1, 1)) + 0.03 * (W + W.transpose(0, 1, 3, 2))
+    Hof = (lambda i: H_refs[i]) if h_per else (lambda i: H_refs)
     params = problems.bench_params(nc, **(kw or dict(max_iter=60)))
     G = _gpu(model, params, B)
     _solve_init(G, pb)
@@ -543,7 +548,7 @@ def test_update_references_per_instance(name, B, kw):
     for i in pick:
         o = _oracle(model, params)
         o.SolveInit(*instance(pb, i))
-        o.UpdateReferences(H_refs, v_refs[i])
+        o.UpdateReferences(Hof(i), v_refs[i])
         o.ResetSolver()
         O.append(o)
     for itn in (1, 2):
@@ -568,7 +573,7 @@ def test_update_references_per_instance(name, B, kw):
     for i in range(0, B, max(1, B // 160)):
         o = _oracle(model, params)
         o.SolveInit(*instance(pb, i))
-        o.UpdateReferences(H_refs, v_refs[i])
+        o.UpdateReferences(Hof(i), v_refs[i])
         o.Solve()
         if o.get_iter() != it[i] or o.get_mu() != mu[i]:
             bad += 1
@@ -584,6 +589,10 @@ def test_update_references_per_instance(name, B, kw):
     assert o.get_iter() == G.get_iter()[3] and rel_inf(G.z[3], o.z) < 1e-6
     with pytest.raises(RuntimeError, match="wrong size"):
         G.UpdateReferences(H_refs, v_refs[:, :-1])
+    if h_per:
+        with pytest.raises(RuntimeError, match="symmetric"):
+            Hn = H_refs.copy(); Hn[1, 2, 0, 1] += 0.3
+            G.UpdateReferences(Hn, v_refs)
     G.close()
 
 

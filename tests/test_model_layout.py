@@ -11,7 +11,7 @@ import pytest
 
 from loik_b200 import problems, robots, solver
 
-JR_ROWS, TR_ROWS, PR_ROWS, FR_ROWS, GR_ROWS = 68, 81, 33, 127, 49  # loik_device.cuh
+JR_ROWS, TR_ROWS, PR_ROWS, FR_ROWS, GR_ROWS = 89, 81, 33, 127, 49  # loik_device.cuh
 
 
 def _layout(model, nc=1):
