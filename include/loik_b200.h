@@ -28,9 +28,11 @@
  *   - Not thread-safe per handle (same as the reference: one solver+data pair per thread).
  *   - Joints (LOIK_JOINT_*): 1-DoF revolute / prismatic (aligned, unaligned, unbounded), free-flyer, spherical,
  *     translation and planar joints, each anywhere in the tree; idx_q / idx_v are cumulative in joint-id order as in
- *     pinocchio.  Joints whose motion subspace depends on q or is stacked (composite, SphericalZYX, universal,
- *     helical, mimic) are rejected by loik_create with LOIK_ERR_UNSUPPORTED.
- *   - `verbose` and `logging` (LoikSolverInfo, loik-loid-optimized.hpp:47-127) are accepted and ignored.
+ *     pinocchio; JointModelSphericalZYX (configuration-dependent motion subspace).  Composite, universal, helical and
+ *     mimic joints are rejected by loik_create with LOIK_ERR_UNSUPPORTED.
+ *   - `logging` (LoikSolverInfo, loik-loid-optimized.hpp:47-127,406-420) keeps the per-iteration residuals / mu of every
+ *     instance (loik_set_logging, loik_get_history) and, like the reference's, costs speed: such solves run on the debug
+ *     instantiation of the iteration kernel.  `verbose` is accepted and ignored.
  */
 #ifndef LOIK_B200_H_
 #define LOIK_B200_H_
@@ -93,7 +95,7 @@ typedef struct loik_params {
   int32_t warm_start;
   double tol_tail_solve;
   int32_t verbose; /* accepted, ignored on device */
-  int32_t logging; /* accepted, ignored on device */
+  int32_t logging; /* != 0: loik_set_logging(h, 1) at creation */
 } loik_params;
 
 typedef struct loik_solver loik_solver;
@@ -293,6 +295,16 @@ LOIK_API int loik_reset_solver(loik_solver* h, void* stream);
 LOIK_API int loik_step(loik_solver* h, int32_t step_id, void* stream);
 /* Keep the reference's running norms, feasibility scalars and residual vectors readable (slower). */
 LOIK_API int loik_set_debug(loik_solver* h, int32_t on);
+/* logging_ / LoikSolverInfo (loik-loid-optimized.hpp:47-127, filled at :406-420 and in InfeasibilityTailSolve :290-306): keep, for
+ * every instance and iteration of the following solves, LOIK_HISTORY_COLS values -- primal_residual_task, primal_residual_slack,
+ * dual_residual_v, dual_residual_nu, mu (the value the iteration ran with; mu_eq = mu_equality_scale_factor * mu, mu_ineq = mu),
+ * delta_x_qp_inf_norm, delta_z_inf_norm, 1 if the iteration belonged to the tail solve.  Switches debug mode on (the log is written
+ * by the debug instantiation of the iteration kernel: in place, slower).  Capacity = max_iter at the time of the call.
+ * loik_get_history copies [batch][capacity][LOIK_HISTORY_COLS]; rows [0, get_iter()) of an instance are valid. */
+#define LOIK_HISTORY_COLS 8
+LOIK_API int loik_set_logging(loik_solver* h, int32_t on);
+LOIK_API int32_t loik_history_capacity(loik_solver* h);
+LOIK_API int loik_get_history(loik_solver* h, double* dst, int32_t loc, void* stream);
 /* The reference leaves the workspace of the last backward pass in the caller's data after Solve(): His, pis
  * (ik_id_data, read by tests/loik-loid.cpp:597-615) and jdata.UDinv()/Dinv(), r.  A batched solve packs the
  * still-active instances into dense tiles as it goes, and by default only the state rows of a finished instance

@@ -99,6 +99,14 @@ class FirstOrderLoikOptimized {
   // tests/loik-loid.cpp:340-478): the per-step methods one by one and the feasibility scalars.  They need
   // set_debug(true) (the production path fuses the steps and keeps no running norms) and work on every instance.
   void set_debug(bool on) { check(loik_set_debug(h_, on ? 1 : 0)); }
+  // logging_ / LoikSolverInfo (hpp:47-127): per-iteration log of the following solves, [batch][capacity][LOIK_HISTORY_COLS]
+  void set_logging(bool on) { check(loik_set_logging(h_, on ? 1 : 0)); }
+  int history_capacity() const { return loik_history_capacity(h_); }
+  std::vector<double> history() const {
+    std::vector<double> out((size_t)batch_ * history_capacity() * LOIK_HISTORY_COLS);
+    check(loik_get_history(h_, out.data(), LOIK_HOST, stream_));
+    return out;
+  }
   // His() / pis() after Solve(), as the reference leaves them in ik_id_data (tests/loik-loid.cpp:597-615): opt-in, a
   // finished instance then brings its backward-pass workspace home too (off: those getters throw after a solve)
   void set_keep_workspace(bool on) { check(loik_set_keep_workspace(h_, on ? 1 : 0)); }

@@ -192,6 +192,13 @@ class FirstOrderLoikOptimizedTpl {
   Scalar get_tol_primal_inf() const { return params().tol_primal_inf; }
   Scalar get_tol_dual_inf() const { return params().tol_dual_inf; }
   Scalar get_rho() const { return params().rho; }
+  // loik_solver_info_ (hpp:47-127; constructed with logging = true): rows [0, get_iter()) of [capacity][LOIK_HISTORY_COLS] =
+  // primal_residual_task, primal_residual_slack, dual_residual_v, dual_residual_nu, mu, delta_x_qp_inf_norm, delta_z_inf_norm, tail flag
+  std::vector<double> get_solver_log() const {
+    std::vector<double> out((size_t)loik_history_capacity(h_) * LOIK_HISTORY_COLS);
+    check(loik_get_history(h_, out.data(), LOIK_HOST, stream_));
+    return out;
+  }
   void set_max_iter(const int v) { check(loik_set_max_iter(h_, v)); }
   void set_tol_abs(const Scalar v) { check(loik_set_tol_abs(h_, v)); }
   void set_tol_rel(const Scalar v) { check(loik_set_tol_rel(h_, v)); }

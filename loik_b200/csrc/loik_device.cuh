@@ -134,6 +134,11 @@ struct Carry {
 };
 constexpr int kCarryRows = 14;
 
+// per-iteration record of the solver log (loik_get_history): what loik-loid-optimized.hpp:406-420 pushes into LoikSolverInfo after
+// ComputeResiduals -- primal_residual_task, primal_residual_slack, dual_residual_v, dual_residual_nu, mu (the value the iteration
+// ran with; mu_eq = mu_equality_scale_factor * mu, mu_ineq = mu) -- plus what the tail-solve lists hold (hpp:290-306):
+// delta_x_qp_inf_norm, delta_z_inf_norm, and whether the iteration belonged to InfeasibilityTailSolve
+constexpr int kHistCols = 8;
 struct StateP {
   double* arena;      // tile records
   int n;              // slots in use (instances)
@@ -160,6 +165,8 @@ struct StateP {
   double* home;
   int keep_ws;        // retiring instances also carry their backward->forward workspace home (loik_set_keep_workspace)
   int drop_ws;        // the forward sweep drops the consumed workspace lines from L2 (discard_workspace); never with keep_ws
+  double* hist;       // logging (LoikSolverInfo, loik_set_logging): [slot][hist_cap][kHistCols] per-iteration records of debug-mode solves
+  int hist_cap;
   double* dbg;        // debug mode only: tile records of the residual vectors (Offs::prv / drv rows, Offs::drows per tile), by home slot
 };
 

@@ -173,7 +173,14 @@ __global__ void __launch_bounds__(kBlock) __maxnreg__(MINB <= 4 ? 255 : (65536 /
           sweep_forward<DEBUG>(c_model, Ts, Td, mu, mu_eq, cy, 1, nb, drop_ws, Dg);
           sweep_residual<DEBUG>(c_model, Ts, Td, rs, 1, nb, Dg);
         }
+        const double mu_used = mu;
+        const int status_was = status;
         status = decide<DEBUG>(c_model, Td, status, it, fixed != 0, cy, rs, mu);
+        if (DEBUG && S.hist && it <= S.hist_cap) {  // the solver log (debug mode runs in place: s is the home slot)
+          double* Hh = S.hist + ((size_t)s * S.hist_cap + (it - 1)) * kHistCols;
+          Hh[0] = cy.pres_task; Hh[1] = cy.pres_slack; Hh[2] = rs.dres_v; Hh[3] = rs.T_inf; Hh[4] = mu_used;
+          Hh[5] = dmax(cy.dvis_inf, cy.dnu_inf); Hh[6] = cy.dz_inf; Hh[7] = status_was == ST_TAIL ? 1.0 : 0.0;
+        }
         Ts = Td; migrate = false;
         if (status >= ST_CONVERGED) break;
       }
@@ -809,6 +816,8 @@ struct loik_solver {
   int* d_lists = nullptr;   // two compaction lists of `batch` ints
   double* scratch[2] = {nullptr, nullptr};  // packed arenas (allocated at the first solve)
   int* d_origin = nullptr;  // [2][batch] home slot of every packed slot
+  double* d_hist = nullptr;  // solver log (loik_set_logging): [batch][hist_cap][kHistCols]
+  int hist_cap = 0;
   int4* d_wide_tab = nullptr;  // step table of the wide sweeps of k_iterate_lane<4> (build_wide_table)
   int* d_counts = nullptr;  // [0],[1]: list lengths (ping-pong); [2]: n_active; [3]: work-queue head of the lane kernel; [5]: entries queued from the end of its list
   unsigned long long* d_stats = nullptr;
@@ -1353,6 +1362,7 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
   }
 #undef CKA
   *out = h;
+  if (params->logging && loik_set_logging(h, 1) != LOIK_OK) { loik_destroy(h); *out = nullptr; return LOIK_ERR_CUDA; }
   return LOIK_OK;
 }
 
@@ -1396,7 +1406,7 @@ void loik_destroy(loik_solver* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  cudaFree(h->S.dbg); cudaFree(h->arena); cudaFree(h->scratch[0]); cudaFree(h->scratch[1]); cudaFree(h->d_origin); cudaFree(h->d_lists); cudaFree(h->d_counts); cudaFree(h->d_wide_tab); cudaFree(h->d_stats); cudaFree(h->d_map);
+  cudaFree(h->S.dbg); cudaFree(h->arena); cudaFree(h->scratch[0]); cudaFree(h->scratch[1]); cudaFree(h->d_origin); cudaFree(h->d_lists); cudaFree(h->d_counts); cudaFree(h->d_hist); cudaFree(h->d_wide_tab); cudaFree(h->d_stats); cudaFree(h->d_map);
   if (h->g_exec) cudaGraphExecDestroy(h->g_exec);
   if (h->hi_stream) cudaStreamDestroy(h->hi_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1949,6 +1959,34 @@ int loik_set_debug(loik_solver* h, int32_t on) {
     CK(cudaMemset(h->S.dbg, 0, bytes));
   }
   h->debug = on != 0;
+  return LOIK_OK;
+}
+
+static_assert(kHistCols == LOIK_HISTORY_COLS, "include/loik_b200.h and loik_device.cuh must agree");
+int loik_set_logging(loik_solver* h, int32_t on) {
+  if (!h) return fail(LOIK_ERR_INVALID, "null handle");
+  if (!on) { h->S.hist = nullptr; return LOIK_OK; }
+  int rc = loik_set_debug(h, 1);  // the log is written by the debug instantiation of the iteration kernel (in place, one launch)
+  if (rc) return rc;
+  const int cap = std::max(1, h->prm.max_iter);
+  if (!h->d_hist || h->hist_cap < cap) {
+    if (h->d_hist) cudaFree(h->d_hist);
+    h->d_hist = nullptr;
+    CK(cudaMalloc(&h->d_hist, (size_t)h->batch * cap * kHistCols * sizeof(double)));
+    CK(cudaMemset(h->d_hist, 0, (size_t)h->batch * cap * kHistCols * sizeof(double)));
+    h->hist_cap = cap;
+  }
+  h->S.hist = h->d_hist; h->S.hist_cap = h->hist_cap;
+  return LOIK_OK;
+}
+int32_t loik_history_capacity(loik_solver* h) { return h ? h->hist_cap : 0; }
+int loik_get_history(loik_solver* h, double* dst, int32_t loc, void* stream) {
+  if (!h || !dst) return fail(LOIK_ERR_INVALID, "loik_get_history: null argument");
+  if (!h->d_hist) return fail(LOIK_ERR_STATE, "loik_get_history: logging is off (loik_params.logging / loik_set_logging)");
+  CK(cudaSetDevice(h->device));
+  const size_t bytes = (size_t)h->batch * h->hist_cap * kHistCols * sizeof(double);
+  CK(cudaMemcpyAsync(dst, h->d_hist, bytes, loc == LOIK_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  if (loc != LOIK_DEVICE) CK(cudaStreamSynchronize((cudaStream_t)stream));
   return LOIK_OK;
 }
 

@@ -41,7 +41,7 @@ NORM_NAMES = ["bT_delta_y_plus", "bT_delta_y_minus", "Av_inf_norm", "nu_inf_norm
 
 EXPORTS = ["loik_abi_version", "loik_last_error", "loik_create", "loik_destroy", "loik_model_layout", "loik_wide_table", "loik_solve_init",
            "loik_update_references", "loik_update_references_batch", "loik_solve", "loik_solve_full", "loik_solve_task", "loik_integrate", "loik_iterate_fixed",
-           "loik_fwd_pass_init", "loik_reset_recursion", "loik_step", "loik_set_debug", "loik_set_keep_workspace", "loik_get", "loik_get_stats", "loik_reduce_stats", "loik_launch_count",
+           "loik_fwd_pass_init", "loik_reset_recursion", "loik_step", "loik_set_debug", "loik_set_logging", "loik_history_capacity", "loik_get_history", "loik_set_keep_workspace", "loik_get", "loik_get_stats", "loik_reduce_stats", "loik_launch_count",
            "loik_set_max_iter", "loik_set_rho", "loik_set_mu", "loik_set_mu_equality_scale_factor", "loik_set_tol_abs",
            "loik_set_tol_rel", "loik_set_tol_primal_inf", "loik_set_tol_dual_inf", "loik_set_tol_tail_solve",
            "loik_set_warm_start", "loik_get_params", "loik_get_schedule", "loik_set_schedule",
@@ -100,6 +100,10 @@ def load_library(path: str | None = None):
     lib.loik_fwd_pass_init.argtypes = [vp, dp, i32, vp]
     lib.loik_step.argtypes = [vp, i32, vp]
     lib.loik_set_debug.argtypes = [vp, i32]
+    lib.loik_set_logging.argtypes = [vp, i32]
+    lib.loik_history_capacity.argtypes = [vp]
+    lib.loik_history_capacity.restype = i32
+    lib.loik_get_history.argtypes = [vp, vp, i32, vp]
     lib.loik_model_layout.argtypes = [vp, vp, C.POINTER(C.c_int32), i32]
     lib.loik_model_layout.restype = i32
     lib.loik_wide_table.argtypes = [vp, vp, C.POINTER(C.c_int32), i32]
@@ -456,6 +460,20 @@ class FirstOrderLoikOptimized:
     def set_debug(self, on=True):
         self._check(self._lib.loik_set_debug(self._h, int(bool(on))))
 
+    def set_logging(self, on=True):
+        """logging_ / LoikSolverInfo (loik-loid-optimized.hpp:47-127): keep the per-iteration log of the following solves."""
+        self._check(self._lib.loik_set_logging(self._h, int(bool(on))))
+
+    HISTORY_COLS = ("primal_residual_task", "primal_residual_slack", "dual_residual_v", "dual_residual_nu", "mu",
+                    "delta_x_qp_inf_norm", "delta_z_inf_norm", "tail_solve")
+
+    def history(self):
+        """[batch][capacity][8] solver log (columns: HISTORY_COLS); rows [0, get_iter()[i]) of instance i are valid."""
+        cap = int(self._lib.loik_history_capacity(self._h))
+        out = np.empty((self.batch, cap, len(self.HISTORY_COLS)))
+        self._check(self._lib.loik_get_history(self._h, out.ctypes.data, LOIK_HOST, _current_stream()))
+        return out
+
     def set_keep_workspace(self, on=True):
         """His / pis / UDinv / Dinv / r of the last backward pass stay readable after Solve(), as the reference leaves
         them in ik_id_data (tests/loik-loid.cpp:597-615); off, those getters raise after a solve instead of returning
@@ -658,4 +676,4 @@ def make_solver(model, params: dict, batch: int, device: int = 0) -> FirstOrderL
                                    p["rho"], p["mu"], p["mu_equality_scale_factor"], p.get("mu_update_strat", 0),
                                    p["num_eq_c"], p.get("eq_c_dim", 6), model, batch=batch,
                                    warm_start=p.get("warm_start", False), tol_tail_solve=p["tol_tail_solve"],
-                                   device=device)
+                                   logging=p.get("logging", False), device=device)

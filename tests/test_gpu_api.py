@@ -274,3 +274,35 @@ def test_update_eq_constraint_target_only(a_per):
     with pytest.raises(RuntimeError, match="constraint doesn't yet exist"):
         G.Solve(pb["q"], c_id - 1, None, b2)
     G.close()
+
+
+@pytest.mark.parametrize("name,via_ctor", [("panda", False), ("talos", True)])
+def test_logging_history_matches_the_oracle_log(name, via_ctor):
+    """logging_ / LoikSolverInfo (loik-loid-optimized.hpp:406-420 and :290-306): the per-iteration primal / dual residual and mu
+    of every instance, main loop and tail solve, against the log of the oracle driven the same way."""
+    from oracle import recursion
+    model = robots.get_robot(name)
+    B = 64
+    pb = problems.random_batch(model, B, seed=12)
+    params = dict(problems.bench_params(len(pb["ids"]), max_iter=80), logging=via_ctor)
+    G = _gpu(model, params, B)
+    if not via_ctor:
+        G.set_logging(True)
+    _solve_init(G, pb)
+    G.Solve()
+    H, it = G.history(), G.get_iter()
+    assert H.shape == (B, 80, 8)
+    tails = 0
+    for i in range(B):
+        o = recursion.FirstOrderLoikOptimized(model, **ctor_kwargs(params))
+        o.Solve(*instance(pb, i))
+        n = o.get_iter()
+        assert n == it[i] and int(o.scalar("hist_len")) == n
+        h = H[i, :n]
+        np.testing.assert_array_equal(h[:, 4], o.hist_mu)
+        np.testing.assert_allclose(np.maximum(h[:, 0], h[:, 1]), o.hist_primal_residual, rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(np.maximum(h[:, 2], h[:, 3]), o.hist_dual_residual, rtol=1e-6, atol=1e-9)
+        tails += int(h[:, 7].sum() > 0)
+        assert (np.diff(h[:, 7]) >= 0).all()  # once on the infeasibility tail, an instance stays there
+    assert tails > 0
+    G.close()
