@@ -315,10 +315,11 @@ def run_workload(name, args, rank, world, local_rank, dev, headline):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) * 1e3 / iters
 
-    # the latency-oriented schedule of long / branching trees (their default keeps the tile kernels for throughput)
-    ms_single_lane = None
-    if schedule["lane_available"] and schedule["lane_after"] < 0:
-        S0.set_schedule(lane_after=8)
+    # the latency-oriented schedule (the defaults favour pipelined throughput): the lane-parallel kernel takes over early
+    ms_single_lane, lat_after = None, None
+    if schedule["lane_available"]:
+        lat_after = 8 if schedule["lane_after"] < 0 else 4
+        S0.set_schedule(lane_after=lat_after)
         step_resident(0, 1)
         ms_single_lane = timed(lambda i: step_resident(0, 1), 3) / 3
         S0.set_schedule(lane_after=saved_lane_after)
@@ -357,7 +358,7 @@ def run_workload(name, args, rank, world, local_rank, dev, headline):
             "gpu_launches": int(launches),
             "extra": {
                 "ms_per_solve_unpipelined": ms_single,
-                "ms_per_solve_unpipelined_lane_after_8": ms_single_lane,
+                "ms_per_solve_unpipelined_latency_schedule": None if ms_single_lane is None else {"lane_after": lat_after, "ms": ms_single_lane},
                 "value_pipeline_4": world * batch * n4 / (ms_d4 * 1e-3),
                 "converged_only_solves_per_s": value * stats["converged"] / batch,
                 "iters_per_s": world * batch / (us_iter * 1e-6),
