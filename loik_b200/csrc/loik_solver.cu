@@ -74,12 +74,12 @@ LOIK_DEV_CALL void retire_workspace(const ModelC& c_model, const double* Ts, dou
   for (int j = 0; j < c_model.nb; ++j) {
     const double* Ps = joint_blk(const_cast<double*>(Ts), O, j);
     double* Pd = joint_blk(Th, O, j);
-    for (int r = JR_H; r < JR_ROWS; ++r) st(Pd, r, ld(Ps, r));
+    for (int r = JR_H; r < JR_HV; ++r) st(Pd, r, ld(Ps, r));  // (the rows behind the workspace are problem data: they never left home)
   }
   for (int m = 0; m < c_model.nmd; ++m) {
     const double* Ps = md_blk(const_cast<double*>(Ts), O, m);
     double* Pd = md_blk(Th, O, m);
-    for (int r = FR_DINV; r < FR_ROWS; ++r) st(Pd, r, ld(Ps, r));
+    for (int r = FR_DINV; r < FR_S; ++r) st(Pd, r, ld(Ps, r));
   }
 }
 

@@ -566,6 +566,7 @@ def test_update_references_per_instance(name, B, kw, h_per):
             check_abs_or_rel(nu[i], o.nu, tol, "nu")
             check_abs_or_rel(res[i, 3], o.get_tol_dual(), 1e-8, "tol_dual")
     D.close()
+    G.set_keep_workspace(True)  # (instances that retire from a re-packed arena bring their workspace home: the reference rows behind it must stay)
     for rep in range(2):
         G.Solve()
     z, it, mu = G.z, G.get_iter(), G.get_mu()
