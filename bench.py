@@ -52,6 +52,7 @@ WORKLOADS = {  # BASELINE.json configs[1..3]: (robot, per-GPU batch)
     "talos_ff": ("talos_ff", 16384),  # floating base (free-flyer root, nv = 38): not a BASELINE config, SURVEY.md 8(f) rank 4
 }
 FIXED_ITERS = 50
+SAT_ITERS = 10     # dense iterations per handle and round in the launches-in-flight measurement
 METRIC = "IK solves/sec (batch, device-timed)"
 
 
@@ -326,6 +327,22 @@ def run_workload(name, args, rank, world, local_rank, dev, headline):
     us_iter = fixed_us(-1, FIXED_ITERS)                     # k_iterate, one launch per iteration
     us_lane = fixed_us(0, 20) if schedule["lane_available"] else None  # k_iterate_lane, 20 iterations per instance in one launch
     S0.set_schedule(lane_after=saved_lane_after)
+    # the same kernel with launches of several solver handles in flight (what the pipelined solves run as): one launch alone
+    # leaves warp slots empty when the batch is small (Talos-16 384: 512 warps on 1 184 slots)
+    nsat = min(8, D)
+    for S in solvers[:nsat]:
+        S.set_schedule(lane_after=-1)
+        S.IterateFixed(1)  # (reset: every instance active again; fixed mode keeps them active)
+
+    def sat_round(i):
+        for k in range(nsat):
+            with torch.cuda.stream(streams[k]):
+                solvers[k].IterateFixed(SAT_ITERS, reset=False)
+    sat_round(0)
+    us_sat = timed(sat_round, 2) * 1e3 / (2 * SAT_ITERS * nsat)  # per launch-equivalent
+    for S in solvers[:nsat]:
+        S.set_schedule(lane_after=saved_lane_after)
+        S.SolveInit(q_d, prob[0], prob[1], prob[2], prob[3], b_d, pb["lb"], pb["ub"])
 
     # e2e
     for i in range(max(2, D)):
@@ -362,6 +379,8 @@ def run_workload(name, args, rank, world, local_rank, dev, headline):
                 "value_pipeline_4": world * batch * n4 / (ms_d4 * 1e-3),
                 "converged_only_solves_per_s": value * stats["converged"] / batch,
                 "iters_per_s": world * batch / (us_iter * 1e-6),
+                "dense_kernel_with_launches_in_flight": {"handles": nsat, "us_per_launch_equivalent": us_sat, "iters_per_s": world * batch / (us_sat * 1e-6),
+                                                         "algorithmic_frac_of_hbm": bpi * batch / (us_sat * 1e-6) / 1e9 / hbm},
                 "instance_iterations_per_s_whole_solves": value * mean_iters,
                 "lane_kernel": None if us_lane is None else {
                     "kernel": "k_iterate_lane (8 lanes per instance, state resident in shared memory, 20 iterations per launch)",
