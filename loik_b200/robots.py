@@ -401,10 +401,12 @@ def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0
 
 
 ROBOTS = {"panda": panda, "panda9": lambda: panda(True), "ur10": ur10, "ur10c": lambda: ur10(True), "talos": talos,
-          "talos_ff": lambda: talos(True)}
+          "talos_ff": lambda: talos(True),
+          # a seeded tree with every multi-DoF joint type incl. SphericalZYX (golden fixture tests/golden/random_tree_zyx.npz)
+          "tree_zyx": lambda: dataclasses.replace(random_tree(11, 205, multidof=0.4, zyx=0.5), name="tree_zyx")}
 
 # End-effector task joints used by the BASELINE.json configs.
-TASK_JOINTS = {"panda": [7], "panda9": [7], "ur10": [6], "ur10c": [6], "talos": [21, 29], "talos_ff": [22, 30]}
+TASK_JOINTS = {"panda": [7], "panda9": [7], "ur10": [6], "ur10c": [6], "talos": [21, 29], "talos_ff": [22, 30], "tree_zyx": [6, 11]}
 
 
 def get_robot(name: str) -> RobotModel:

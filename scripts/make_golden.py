@@ -31,10 +31,15 @@ def solve_both(model, params, args):
     return B
 
 
+ONLY = set(sys.argv[1:])  # optional: regenerate only the named random_* fixtures
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # 1. the reference's fixture (tests/loik-loid.cpp:87-165) on the synthetic tables, bounds as in :559-671
     for name in ("talos", "panda", "ur10"):
+        if ONLY:
+            continue
         model = robots.get_robot(name)
         pr = problems.fixture_problem(model, 2.0)
         params = dict(problems.FIXTURE_PARAMS, max_iter=8)
@@ -44,7 +49,9 @@ def main():
                  primal_infeasible=B.get_primal_infeasibility_status(), primal_residual=B.get_primal_residual(),
                  dual_residual=B.get_dual_residual())
     # 2. seeded random instances of the BASELINE configs, full solves (max_iter = 200)
-    for name, n in (("panda", 48), ("ur10", 48), ("talos", 16), ("panda9", 16), ("ur10c", 32)):
+    for name, n in (("panda", 48), ("ur10", 48), ("talos", 16), ("panda9", 16), ("ur10c", 32), ("tree_zyx", 24)):
+        if ONLY and name not in ONLY:
+            continue
         model = robots.get_robot(name)
         pb = problems.random_batch(model, n, seed=1234)
         params = problems.bench_params(len(pb["ids"]))

@@ -29,7 +29,7 @@ def test_fixture_golden(name):
         assert rel_inf(getattr(B, nm), g[nm]) < 1e-9, nm
 
 
-@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "panda9", "ur10c"])
+@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "panda9", "ur10c", "tree_zyx"])
 def test_random_golden(name):
     g = np.load(os.path.join(GOLD, f"random_{name}.npz"))
     model = robots.get_robot(name)

@@ -597,7 +597,7 @@ def test_update_references_per_instance(name, B, kw, h_per):
     G.close()
 
 
-@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "panda9", "ur10c"])
+@pytest.mark.parametrize("name", ["panda", "ur10", "talos", "panda9", "ur10c", "tree_zyx"])
 def test_against_committed_golden_fixtures(name):
     """CUDA path vs tests/golden/random_*.npz (frozen oracle-pair outputs, scripts/make_golden.py) -- no oracle call."""
     import os
