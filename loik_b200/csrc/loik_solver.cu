@@ -816,6 +816,7 @@ struct loik_solver {
   int* d_lists = nullptr;   // two compaction lists of `batch` ints
   double* scratch[2] = {nullptr, nullptr};  // packed arenas (allocated at the first solve)
   int* d_origin = nullptr;  // [2][batch] home slot of every packed slot
+  bool debug_by_logging = false;  // debug mode was switched on by loik_set_logging (and goes off with it)
   double* d_hist = nullptr;  // solver log (loik_set_logging): [batch][hist_cap][kHistCols]
   int hist_cap = 0;
   int4* d_wide_tab = nullptr;  // step table of the wide sweeps of k_iterate_lane<4> (build_wide_table)
@@ -1558,6 +1559,7 @@ int loik_update_references(loik_solver* h, const double* H_refs, const double* v
     }
   }
   M.href_uniform = first.size() <= 1 ? 1 : 0;
+  M.vref_per = 0; M.href_per = 0;  // (per-joint references shared by the batch replace per-instance ones; loik_update_references_batch sets them again)
   return LOIK_OK;
 }
 
@@ -1965,9 +1967,15 @@ int loik_set_debug(loik_solver* h, int32_t on) {
 static_assert(kHistCols == LOIK_HISTORY_COLS, "include/loik_b200.h and loik_device.cuh must agree");
 int loik_set_logging(loik_solver* h, int32_t on) {
   if (!h) return fail(LOIK_ERR_INVALID, "null handle");
-  if (!on) { h->S.hist = nullptr; return LOIK_OK; }
+  if (!on) {
+    h->S.hist = nullptr;
+    if (h->debug_by_logging) { h->debug = false; h->debug_by_logging = false; }
+    return LOIK_OK;
+  }
+  if (!h->debug) h->debug_by_logging = true;
   int rc = loik_set_debug(h, 1);  // the log is written by the debug instantiation of the iteration kernel (in place, one launch)
   if (rc) return rc;
+  CK(cudaSetDevice(h->device));
   const int cap = std::max(1, h->prm.max_iter);
   if (!h->d_hist || h->hist_cap < cap) {
     if (h->d_hist) cudaFree(h->d_hist);
