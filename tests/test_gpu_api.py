@@ -306,3 +306,27 @@ def test_logging_history_matches_the_oracle_log(name, via_ctor):
         assert (np.diff(h[:, 7]) >= 0).all()  # once on the infeasibility tail, an instance stays there
     assert tails > 0
     G.close()
+
+
+@pytest.mark.parametrize("name,lane_after", [("panda", 32), ("panda", 0), ("talos", -1), ("talos_ff", -1)])
+def test_no_task_constraints(name, lane_after):
+    """num_eq_c = 0: no task block is ever touched (the record still holds one, unused); tile kernels and the lane kernel."""
+    from oracle import recursion
+    model = robots.get_robot(name)
+    B = 200
+    rng = np.random.default_rng(4)
+    params = dict(problems.FIXTURE_PARAMS, max_iter=60, num_eq_c=0)
+    q = model.normalize(rng.uniform(model.q_min, model.q_max, size=(B, model.nq)))
+    v_ref = 0.3 * rng.normal(size=6)
+    G = _gpu(model, params, B)
+    if G.get_schedule()["lane_available"]:
+        G.set_schedule(lane_after=lane_after)
+    G.SolveInit(q, np.eye(6), v_ref, np.zeros(0, np.int32), np.zeros((0, 6, 6)), np.zeros((B, 0, 6)), -model.v_max, model.v_max)
+    G.Solve()
+    z, it = G.z, G.get_iter()
+    for i in range(0, B, 9):
+        o = recursion.FirstOrderLoikOptimized(model, **ctor_kwargs(params))
+        o.Solve(q[i], np.eye(6), v_ref, np.zeros(0, np.int32), np.zeros((0, 6, 6)), np.zeros((0, 6)), -model.v_max, model.v_max)
+        assert o.get_iter() == it[i], i
+        assert rel_inf(z[i], o.z) < 1e-6, i
+    G.close()

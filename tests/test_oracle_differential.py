@@ -353,3 +353,21 @@ def test_multidof_step_tolerance_is_rounding_sensitivity(tmp_path):
     assert plain < 1e-10, "1-DoF trees: the reference comparator's tolerance holds between two roundings"
     assert md < 5e-9, "the GPU tests' multi-DoF step tolerance covers the rounding sensitivity"
     assert md > 10 * plain or md > 1e-11, "multi-DoF trees are measurably more sensitive (otherwise tighten the GPU tolerance)"
+
+
+@pytest.mark.parametrize("name", ["panda", "talos", "talos_ff"])
+def test_no_task_constraints(name):
+    """num_eq_c = 0 (ik-id-description-optimized.hpp:30-59 accepts it; UpdateEqConstraints with empty lists): only the reference
+    term and the box remain.  A == B, and the answer is the closed form of the box-constrained regularisation."""
+    model = robots.get_robot(name)
+    rng = np.random.default_rng(3)
+    params = dict(problems.FIXTURE_PARAMS, max_iter=60, num_eq_c=0)
+    q = model.normalize(rng.uniform(model.q_min, model.q_max))
+    args = (q, np.eye(6), 0.3 * rng.normal(size=6), np.zeros(0, np.int32), np.zeros((0, 6, 6)), np.zeros((0, 6)), -model.v_max, model.v_max)
+    A, B = make_pair(model, params)
+    A.Solve(*args)
+    B.Solve(*args)
+    assert A.iter == B.get_iter() and A.mu == B.get_mu()
+    check_abs_or_rel(B.z, A.z, 1e-9, "z")
+    check_abs_or_rel(B.nu, A.nu, 1e-9, "nu")
+    assert np.abs(B.z).max() > 1e-3
