@@ -330,3 +330,25 @@ def test_no_task_constraints(name, lane_after):
         assert o.get_iter() == it[i], i
         assert rel_inf(z[i], o.z) < 1e-6, i
     G.close()
+
+
+def test_infinite_bounds_behave_like_the_reference():
+    """lb = -inf, ub = +inf (no box): BoxProj is the identity, ub^T max(dw, 0) is inf * 0 = NaN in the reference's CheckFeasibility
+    (hxx:587-590) and both of its comparisons are false -- the CUDA path must take the same decisions (never "primal infeasible")."""
+    from oracle import recursion
+    model = robots.panda()
+    B = 128
+    pb = problems.random_batch(model, B, seed=17)
+    inf = np.full(model.nv, np.inf)
+    params = problems.bench_params(1, max_iter=60)
+    G = _gpu(model, params, B)
+    G.SolveInit(pb["q"], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"], -inf, inf)
+    G.Solve()
+    z, it, st = G.z, G.get_iter(), G.get_status()
+    assert not (st & 2).any()
+    for i in range(0, B, 5):
+        o = recursion.FirstOrderLoikOptimized(model, **ctor_kwargs(params))
+        o.Solve(pb["q"][i], pb["H_ref"], pb["v_ref"], pb["ids"], pb["Ais"], pb["bis"][i], -inf, inf)
+        assert o.get_iter() == it[i] and not o.get_primal_infeasibility_status(), i
+        assert rel_inf(z[i], o.z) < 1e-6, i
+    G.close()
