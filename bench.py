@@ -290,6 +290,11 @@ def run_workload(name, args, rank, world, local_rank, dev, headline):
     launches = sum(S.launch_count() for S in solvers) - launches0
     stats = solvers[0].stats()
     mean_iters = stats["total_iters"] / batch
+    # share of the instance-iterations of a solve that the roofline kernel (k_iterate) executes: everything up to the switch to the
+    # lane-parallel kernel (an ncu launch list shows device TIME, where the latency-bound tail of the lane kernel weighs far more)
+    it_all = solvers[0].get_iter().astype(np.int64)
+    la = schedule["lane_after"] if (schedule["lane_available"] and schedule["lane_after"] >= 0) else 10 ** 9
+    work_share = float(np.minimum(it_all, la).sum()) / max(1, int(it_all.sum()))
     # latency of one un-pipelined solve (one handle, one stream), and the rate with 4 handles in flight
     ms_single = timed(lambda i: step_resident(0, 1), 3) / 3
     d4 = min(4, D)
@@ -369,6 +374,7 @@ def run_workload(name, args, rank, world, local_rank, dev, headline):
                          "traffic": None, "peak_source": how,
                          "kernel": "k_iterate (1 ADMM iteration / launch, all instances active)",
                          "algorithmic_bytes_per_launch": bpi * batch, "us_per_launch": us_iter,
+                         "share_of_instance_iterations": work_share,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_v, "unit": "IK solves/s", "h2d_bytes_per_step": int(q_h.numel() * 8 + b_h.numel() * 8),
                     "d2h_bytes_per_step": int(z_h[0].numel() * 8 + it_h[0].numel() * 4), "ms_per_step": ms_e2e / steps},
