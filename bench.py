@@ -170,7 +170,7 @@ def cpu_baseline(model, pb, params, lib, seconds_target=12.0):
     """The reported in-line CPU baseline: warmed, several passes, same protocol as `--impl reference`."""
     cores = os.cpu_count() or 1
     B = pb["q"].shape[0]
-    passes = 6
+    passes = 20  # (a pass over the whole Panda batch takes ~70 ms on 16 cores: ~1.5 s of wall clock, ~20 core-seconds in all)
     n = cpu_pass_size(model, pb, params, lib, seconds_target / (passes + 1))
     v, its, mean_it = cpu_rate(model, pb, params, lib, n, passes, warm=1)
     return {"value": v, "unit": "IK solves/s", "cores": cores, "kind": "port",
