@@ -13,17 +13,17 @@
 //     backward->forward workspace (His, pis, UDinv, Dinv, r) never leaves the SM;
 //   * has no lock-step with 31 unrelated instances: a group that finishes pulls the next instance from the queue, so
 //     a launch needs no re-pack rounds and the stragglers of a batch (0.06 % of the Panda instances run all 199
-//     iterations) cost ~5 us per iteration instead of ~22 us.
+//     iterations) cost 6.9 us per iteration instead of 27 us.
 // The maths restates loik-loid-optimized.hxx exactly as loik_device.cuh does (same per-element expressions wherever
 // an element is produced by one lane; reference file:line cited there); running inf-norms are kept as per-lane
 // partial maxima (max is exactly associative) and combined once per iteration.
 //
 // Two geometries (template parameter GPI = groups per instance):
 //   GPI = 1  four instances per warp, one 8-lane group each, every group sweeping the whole tree (chains: Panda, UR10);
-//   GPI = 4  ONE instance per warp, its four groups sweeping different chains of a branching tree level by level -- the
-//            segment / level schedule of k_iterate_seg (ModelC::seg) with groups in the role of its warps, the instance
-//            record shared in shared memory, __syncwarp() between the levels.  Talos: 10 joint steps on the critical
-//            path of a sweep instead of 32, at 80 % lane utilisation (32 joint steps on 4 x 10 group steps).
+//   GPI = 4  ONE instance per warp, its four groups sweeping different chains of a branching tree at the same time, step by
+//            step through a host-built, list-scheduled table (build_wide_table, loik_solver.cu), the instance record shared in
+//            shared memory, a __syncwarp() per step.  Talos: 10 steps per sweep instead of 32 (32 joint steps on 4 x 10 group
+//            steps), 12.3 us per iteration of a lone instance instead of 31.5.
 // Scope: trees of 1-DoF joints (every BASELINE robot); models with multi-DoF joints keep the k_iterate path.
 #pragma once
 #include "loik_device.cuh"

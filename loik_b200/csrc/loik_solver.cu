@@ -1356,9 +1356,10 @@ static int create_impl(const loik_model_desc* model, const loik_params* params, 
       CKA(cudaFuncSetAttribute(k_iterate_lane<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
     }
     // default switch point: short trees hand the instances still active after 32 sweeps to the lane-parallel kernel (one
-    // Panda-65 536 solve 5.4 -> 2.8 ms, 57.6 -> 69 M solves/s with 10 solves in flight, -3 % with 32; a switch after 10 sweeps
-    // gives 2.3 ms at 58 / 61 M); long / branching trees keep the tile kernels (their record leaves room for 8 instances
-    // per SM only) unless the caller asks (loik_set_schedule)
+    // Panda-65 536 solve 5.4 -> 2.8 ms, 57 -> 72 M solves/s with 10 solves in flight, -2 % with 32; a switch after 10 sweeps
+    // gives 2.3 ms at 63 / 66 M); long / branching trees keep the tile kernels for throughput (Talos: the wide lane geometry
+    // holds 5 instances per SM; lane_after = 8 gives one solve in 6.5 instead of 13.8 ms at 4.2 instead of 6.7 M solves/s
+    // pipelined) unless the caller asks (loik_set_schedule)
     h->lane_after = (h->lane_ok && nb <= 12) ? 32 : -1;
   }
 #undef CKA

@@ -377,7 +377,7 @@ def random_tree(nb: int, seed: int, branching: float = 0.3, unaligned: float = 0
     """Seeded random kinematic tree covering every joint type (parity stress tests)."""
     rng = np.random.default_rng(seed)
     J = []
-    n_md = 0  # (the CUDA kernels take up to kMaxMd = 8 multi-DoF joints per model)
+    n_md = 0  # (the CUDA kernels take up to kMaxMd = 16; the default of 8 keeps existing seeds unchanged multi-DoF joints per model)
     for i in range(1, nb + 1):
         par = i - 1 if (i == 1 or rng.random() > branching) else int(rng.integers(0, i))
         kind = "P" if rng.random() < prismatic else "R"
